@@ -1,0 +1,985 @@
+// dem_core.cu -- C ABI (include/dem_b200.h) of the B200-native DEM core: context, device arena, the step loop and the
+// contact-list rebuild driver.  Replaces, for the hot path only, the two worker loops of the reference
+// (dT workerThread src/DEM/dT.cpp:2324-2479, kT workerThread src/DEM/kT.cpp:218-320) and their
+// cudaMemcpy mailbox hand-shake (dT.cpp:1989-2038, kT.cpp:193-216) with ONE in-order stream: the rebuild runs on the
+// same GPU right before the force kernel that first uses the list, so the list is never stale by more than
+// cd_update_freq steps and no peer copies exist.  There is no CPU fallback: without a device every entry point fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dem_kernels.h"
+
+using namespace demb;
+
+namespace {
+
+struct ListBuf {
+    uint2* pair = nullptr;
+    uint4* cinfo = nullptr;
+    float4* hist = nullptr;
+    uint32_t* seg_start = nullptr;
+    uint32_t* seg_count = nullptr;
+    uint32_t* count = nullptr;
+    float4* force = nullptr;
+};
+
+}  // namespace
+
+struct DemCtx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int num_sms = 148;
+    std::string err;
+    bool initialized = false;
+    bool params_set = false;
+    DemSimParams sp{};
+
+    // host copies of the flattened input
+    std::vector<float4> h_comp, h_massprop;
+    std::vector<MatPair> h_matpair;
+    uint32_t nMat = 0;
+    std::vector<AnalObj> h_anal;
+    std::vector<uint8_t> h_masks;
+    std::vector<float> h_extra;
+    std::vector<Prescr> h_presc;
+    std::vector<OwnerState> h_state;
+    std::vector<uint2> h_sph;
+    std::vector<uint16_t> h_sph_comp, h_sph_mat;
+    std::vector<uint32_t> h_sph_owner;
+    std::vector<float4> h_tri1, h_tri2, h_tri3;
+    std::vector<uint2> h_tri_info;
+    uint32_t nOwners = 0, nSpheres = 0, nAnal = 0, nTri = 0, nClumpOwners = 0;
+    float rmax = 0.f, max_extra = 0.f;
+    uint32_t any_mask = 0;
+
+    // device arrays
+    OwnerState* d_state = nullptr;
+    Wrench* d_wrench = nullptr;
+    Wrench* d_acc = nullptr;
+    uint2* d_sph = nullptr;
+    float4* d_comp = nullptr;
+    float4* d_massprop = nullptr;
+    MatPair* d_matpair = nullptr;
+    AnalObj* d_anal = nullptr;
+    uint8_t* d_masks = nullptr;
+    float* d_extra = nullptr;
+    Prescr* d_presc = nullptr;
+    uint32_t* d_flags = nullptr;
+    float* d_maxvel = nullptr;
+    double* d_reduce = nullptr;
+    ListBuf ss[2], sa[2];
+    int cur = 0;  // index of the current list buffers
+    uint64_t capacity = 0;
+    // rebuild scratch
+    GridInfo* d_grid = nullptr;
+    float4* d_sphF = nullptr;
+    uint32_t* d_keys[2] = {nullptr, nullptr};
+    uint32_t* d_vals[2] = {nullptr, nullptr};
+    uint32_t* d_cellStart = nullptr;
+    float4* d_sortedSph = nullptr;
+    uint2* d_sortedMeta = nullptr;
+    uint32_t* d_cnt = nullptr;
+    uint32_t* d_saCnt = nullptr;
+    uint32_t* d_rs_hist = nullptr;
+    uint32_t* d_scan_tmp = nullptr;
+    uint32_t max_cells = 0;
+    int key_bits = 8;
+    // pinned read-back
+    uint32_t* h_pinned = nullptr;  // [0]=ssCount [1]=saCount [2..4]=flags, [8..] GridInfo
+
+    // bookkeeping
+    uint64_t n_steps = 0, n_rebuilds = 0, launches = 0, device_bytes = 0;
+    uint64_t steps_since_rebuild = 0;
+    bool need_rebuild = true;
+    double sim_time = 0.0;
+    uint64_t n_ss = 0, n_sa = 0;
+    GridInfo last_grid{};
+    uint32_t overflow_seen = 0;
+    int force_grid = 148 * 4;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+int fail(DemCtx* c, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, DEM_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+    } while (0)
+
+template <typename T>
+int dalloc(DemCtx* ctx, T** p, size_t n) {
+    if (n == 0) n = 1;
+    CK(cudaMalloc((void**)p, n * sizeof(T)));
+    ctx->device_bytes += n * sizeof(T);
+    return DEM_OK;
+}
+template <typename T>
+void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, bool force) {
+    int rc;
+    if ((rc = dalloc(ctx, &L.pair, cap))) return rc;
+    if ((rc = dalloc(ctx, &L.cinfo, cap))) return rc;
+    if (hist && (rc = dalloc(ctx, &L.hist, cap))) return rc;
+    if (force && (rc = dalloc(ctx, &L.force, cap))) return rc;
+    if ((rc = dalloc(ctx, &L.seg_start, (size_t)nSph + 1))) return rc;
+    if ((rc = dalloc(ctx, &L.seg_count, (size_t)nSph + 1))) return rc;
+    if ((rc = dalloc(ctx, &L.count, 4))) return rc;
+    CK(cudaMemset(L.seg_start, 0, sizeof(uint32_t) * ((size_t)nSph + 1)));
+    CK(cudaMemset(L.seg_count, 0, sizeof(uint32_t) * ((size_t)nSph + 1)));
+    CK(cudaMemset(L.count, 0, sizeof(uint32_t) * 4));
+    return DEM_OK;
+}
+void free_list(ListBuf& L) {
+    dfree(L.pair); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.seg_start); dfree(L.seg_count);
+    dfree(L.count);
+}
+
+ContactList as_list(const ListBuf& L) {
+    ContactList c;
+    c.pair = L.pair; c.cinfo = L.cinfo; c.hist = L.hist; c.seg_start = L.seg_start; c.seg_count = L.seg_count;
+    c.count = L.count; c.force = L.force;
+    return c;
+}
+
+DevParams make_params(const DemCtx* c) {
+    DevParams P;
+    memset(&P, 0, sizeof(P));
+    const DemSimParams& s = c->sp;
+    P.nvXp2 = s.nvXp2; P.nvYp2 = s.nvYp2;
+    P.l = s.l; P.voxelSize = s.voxelSize; P.inv_l = 1.0 / s.l;
+    for (int k = 0; k < 3; k++) { P.LBF[k] = s.LBF[k]; P.G[k] = s.G[k]; }
+    P.h = s.h;
+    P.half_h = (float)(0.5 * s.h);
+    P.integrator = s.integrator;
+    P.nOwners = c->nOwners; P.nSpheres = c->nSpheres; P.nAnal = c->nAnal; P.nTri = c->nTri; P.nMat = c->nMat;
+    P.beta = s.beta; P.approxMaxVel = s.approxMaxVel; P.expSafetyMulti = s.expSafetyMulti;
+    P.expSafetyAdder = s.expSafetyAdder;
+    P.maxDrift = s.cd_update_freq;
+    P.drift_h = s.h * (float)s.cd_update_freq;
+    P.state = c->d_state; P.wrench = c->d_wrench; P.acc_out = c->d_acc;
+    P.sph = c->d_sph; P.comp = c->d_comp; P.massprop = c->d_massprop; P.matpair = c->d_matpair; P.anal = c->d_anal;
+    P.familyMasks = c->d_masks; P.familyExtraMargin = c->d_extra; P.presc = c->d_presc;
+    P.ss = as_list(c->ss[c->cur]);
+    P.sa = as_list(c->sa[c->cur]);
+    P.flags = c->d_flags; P.maxvel = c->d_maxvel;
+    return P;
+}
+
+CdParams make_cd(const DemCtx* c) {
+    CdParams C;
+    memset(&C, 0, sizeof(C));
+    C.grid = c->d_grid;
+    for (int k = 0; k < 3; k++) C.ext[k] = c->sp.userBoxMax[k] - c->sp.userBoxMin[k];
+    // the binned region is the target box: positions are LBF relative and LBF is the target box corner
+    for (int k = 0; k < 3; k++) {
+        const float e = 2.f * (c->sp.userBoxMin[k] - c->sp.LBF[k]) + (c->sp.userBoxMax[k] - c->sp.userBoxMin[k]);
+        if (e > C.ext[k]) C.ext[k] = e;
+    }
+    C.rmax = c->rmax; C.max_extra = c->max_extra; C.max_cells = c->max_cells; C.any_mask = c->any_mask;
+    C.capacity = (uint32_t)c->capacity;
+    C.sphF = c->d_sphF;
+    C.keys[0] = c->d_keys[0]; C.keys[1] = c->d_keys[1]; C.vals[0] = c->d_vals[0]; C.vals[1] = c->d_vals[1];
+    C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedMeta = c->d_sortedMeta;
+    C.cnt = c->d_cnt; C.saCnt = c->d_saCnt;
+    C.oldss = as_list(c->ss[c->cur]);
+    C.oldsa = as_list(c->sa[c->cur]);
+    C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp;
+    return C;
+}
+
+void free_device(DemCtx* c) {
+    dfree(c->d_state); dfree(c->d_wrench); dfree(c->d_acc); dfree(c->d_sph); dfree(c->d_comp); dfree(c->d_massprop);
+    dfree(c->d_matpair); dfree(c->d_anal); dfree(c->d_masks); dfree(c->d_extra); dfree(c->d_presc);
+    dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce);
+    for (int k = 0; k < 2; k++) { free_list(c->ss[k]); free_list(c->sa[k]); }
+    dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
+    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_cnt);
+    dfree(c->d_saCnt); dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
+    c->device_bytes = 0;
+}
+
+int alloc_lists(DemCtx* ctx, uint64_t cap) {
+    const bool hist = ctx->sp.force_model == DEM_HERTZIAN;
+    const bool rec = ctx->sp.record_contact_forces != 0;
+    int rc;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = alloc_list(ctx, ctx->ss[k], cap, ctx->nSpheres, hist, rec))) return rc;
+        if ((rc = alloc_list(ctx, ctx->sa[k], cap, ctx->nSpheres, hist, rec))) return rc;
+    }
+    ctx->capacity = cap;
+    return DEM_OK;
+}
+
+// one contact-list rebuild into the "other" buffers, then swap. Syncs once (reads the counts back).
+int rebuild(DemCtx* ctx) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        DevParams P = make_params(ctx);
+        CdParams C = make_cd(ctx);
+        // the new list goes to the other buffer pair; the current one is the "old" list (history source)
+        P.ss = as_list(ctx->ss[ctx->cur ^ 1]);
+        P.sa = as_list(ctx->sa[ctx->cur ^ 1]);
+        cudaStream_t s = ctx->stream;
+        CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 4, s));
+        int launches = launch_cd_prepare(P, C, s);
+        int sorted_buf = 0;
+        launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
+        launches += launch_cd_sweep(P, C, sorted_buf, s);
+        ctx->launches += launches;
+        CK(cudaMemcpyAsync(ctx->h_pinned + 0, P.ss.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 1, P.sa.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_flags, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 24, C.cnt + ctx->nSpheres, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 25, C.saCnt + ctx->nSpheres, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        memcpy(&ctx->last_grid, ctx->h_pinned + 8, sizeof(GridInfo));
+        if (ctx->h_pinned[3] != 0) {
+            return fail(ctx, DEM_ERR_VELOCITY,
+                        "an owner has a non-finite or too large velocity (max seen %.6g, limit %.6g) at t=%.9g",
+                        ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
+        }
+        if (ctx->h_pinned[2] != 0) {
+            // capacity overflow: grow both list pairs, keep the old list (history source) intact, redo
+            ctx->overflow_seen++;
+            const uint64_t need = std::max<uint64_t>(ctx->h_pinned[24], ctx->h_pinned[25]);
+            const uint64_t newcap = std::max<uint64_t>(need + need / 4 + 1024, ctx->capacity * 2);
+            if (newcap > 0xfffffff0ull) return fail(ctx, DEM_ERR_CAPACITY, "contact list exceeds 2^32 entries");
+            // only the target buffers must grow for this attempt; the old buffers grow too so later swaps stay valid
+            ListBuf oldss = ctx->ss[ctx->cur], oldsa = ctx->sa[ctx->cur];
+            const uint64_t oldcap = ctx->capacity;
+            const bool hist = ctx->sp.force_model == DEM_HERTZIAN, rec = ctx->sp.record_contact_forces != 0;
+            free_list(ctx->ss[ctx->cur ^ 1]);
+            free_list(ctx->sa[ctx->cur ^ 1]);
+            int rc;
+            if ((rc = alloc_list(ctx, ctx->ss[ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
+            if ((rc = alloc_list(ctx, ctx->sa[ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
+            ListBuf nss, nsa;
+            if ((rc = alloc_list(ctx, nss, newcap, ctx->nSpheres, hist, rec))) return rc;
+            if ((rc = alloc_list(ctx, nsa, newcap, ctx->nSpheres, hist, rec))) return rc;
+            auto copy_list = [&](ListBuf& dst, const ListBuf& src) -> cudaError_t {
+                cudaError_t e;
+                if ((e = cudaMemcpy(dst.pair, src.pair, sizeof(uint2) * oldcap, cudaMemcpyDeviceToDevice))) return e;
+                if ((e = cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice))) return e;
+                if (src.hist && (e = cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice))) return e;
+                if ((e = cudaMemcpy(dst.seg_start, src.seg_start, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice))) return e;
+                if ((e = cudaMemcpy(dst.seg_count, src.seg_count, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice))) return e;
+                return cudaMemcpy(dst.count, src.count, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice);
+            };
+            CK(copy_list(nss, oldss));
+            CK(copy_list(nsa, oldsa));
+            free_list(oldss);
+            free_list(oldsa);
+            ctx->ss[ctx->cur] = nss;
+            ctx->sa[ctx->cur] = nsa;
+            ctx->capacity = newcap;
+            continue;
+        }
+        ctx->cur ^= 1;
+        ctx->n_ss = ctx->h_pinned[0];
+        ctx->n_sa = ctx->h_pinned[1];
+        ctx->n_rebuilds++;
+        ctx->steps_since_rebuild = 0;
+        ctx->need_rebuild = false;
+        return DEM_OK;
+    }
+    return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
+}
+
+int enqueue_step(DemCtx* ctx) {
+    if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+        int rc = rebuild(ctx);
+        if (rc) return rc;
+    }
+    DevParams P = make_params(ctx);
+    launch_force(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->force_grid, ctx->stream,
+                 ctx->nAnal > 0);
+    launch_integrate(P, ctx->stream);
+    ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
+    ctx->n_steps++;
+    ctx->steps_since_rebuild++;
+    ctx->sim_time += (double)ctx->sp.h;
+    return DEM_OK;
+}
+
+}  // namespace
+
+// ===============================================================================================================
+extern "C" {
+
+int dem_abi_version(void) { return DEM_B200_ABI_VERSION; }
+
+int dem_host_figure_out_nv(const float box_min[3], const float box_max[3], uint32_t nv_p2[3], double* l,
+                           double* voxel_size) {
+    // DEMSolver::figureOutNV, APIPrivate.cpp:373-487 (m_box_dir_length_is_exact == NONE)
+    float XYZ[3] = {box_max[0] - box_min[0], box_max[1] - box_min[1], box_max[2] - box_min[2]};
+    int rank[3] = {0, 1, 2};
+    for (int i = 0; i < 2; i++)
+        for (int j = i + 1; j < 3; j++)
+            if (XYZ[i] > XYZ[j]) { std::swap(XYZ[i], XYZ[j]); std::swap(rank[i], rank[j]); }
+    const float user321[3] = {XYZ[0], XYZ[1], XYZ[2]};
+    int more[2] = {0, 0};
+    while (XYZ[0] < XYZ[1]) {
+        if (std::sqrt(2.) * XYZ[0] > XYZ[1]) break;
+        more[0]++;
+        XYZ[0] *= 2.;
+    }
+    while (XYZ[1] < XYZ[2]) {
+        if (std::sqrt(2.) * XYZ[1] > XYZ[2]) break;
+        more[1]++;
+        XYZ[1] *= 2.;
+    }
+    const int total = 64 - 2 * more[0] - more[1];
+    int b3 = total / 3, left = total % 3;
+    int b2 = b3 + more[0], b1 = b2 + more[1];
+    while (left > 0) {
+        if (b3 < b2) b3++; else if (b2 < b1) b2++; else b1++;
+        left--;
+    }
+    const int bits[3] = {b3, b2, b1};
+    const double l3 = (double)user321[0] / std::pow(2., 16) / std::pow(2., b3);
+    const double l2 = (double)user321[1] / std::pow(2., 16) / std::pow(2., b2);
+    const double l1 = (double)user321[2] / std::pow(2., 16) / std::pow(2., b1);
+    *l = std::max(l3, std::max(l2, l1));
+    for (int p = 0; p < 3; p++) nv_p2[rank[p]] = (uint32_t)bits[p];
+    *voxel_size = (double)((size_t)1 << 16) * (*l);
+    return DEM_OK;
+}
+
+int dem_host_box_domain(float x, float y, float z, float user_min[3], float user_max[3], float target_min[3],
+                        float target_max[3]) {
+    // InstructBoxDomainDimension, APIPublic.cpp:845-872 (DEFAULT_BOX_DOMAIN_ENLARGE_RATIO = 0.2f, Defines.h:449)
+    const float dims[3] = {x, y, z};
+    const float ratio = 0.2f;
+    for (int k = 0; k < 3; k++) {
+        user_min[k] = (float)(-dims[k] / 2.);
+        user_max[k] = (float)(dims[k] / 2.);
+        const float enl = (float)(dims[k] * ratio / 2.);
+        target_min[k] = user_min[k] - enl;
+        target_max[k] = user_max[k] + enl;
+    }
+    return DEM_OK;
+}
+
+int dem_host_encode_positions(const DemSimParams* p, const float* xyz, uint64_t n, uint64_t* voxelID, uint16_t* locX,
+                              uint16_t* locY, uint16_t* locZ) {
+    if (!p || !xyz) return DEM_ERR_INVALID;
+    for (uint64_t i = 0; i < n; i++) {
+        double X[3];
+        for (int k = 0; k < 3; k++) X[k] = (double)(xyz[3 * i + k] - p->LBF[k]);  // float subtraction, dT.cpp
+        const uint64_t nx = (uint64_t)(X[0] / p->voxelSize), ny = (uint64_t)(X[1] / p->voxelSize),
+                       nz = (uint64_t)(X[2] / p->voxelSize);
+        locX[i] = (uint16_t)((X[0] - (double)nx * p->voxelSize) / p->l);
+        locY[i] = (uint16_t)((X[1] - (double)ny * p->voxelSize) / p->l);
+        locZ[i] = (uint16_t)((X[2] - (double)nz * p->voxelSize) / p->l);
+        voxelID[i] = nx + (ny << p->nvXp2) + (nz << (p->nvXp2 + p->nvYp2));
+    }
+    return DEM_OK;
+}
+
+int dem_ctx_create(DemCtx** out, int device) {
+    if (!out) return DEM_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return DEM_ERR_NO_GPU;
+    if (device < 0 || device >= ndev) return DEM_ERR_INVALID;
+    DemCtx* ctx = new DemCtx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return DEM_ERR_CUDA;
+    }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    ctx->num_sms = prop.multiProcessorCount;
+    cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocDefault);
+    for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev[k]);
+    *out = ctx;
+    return DEM_OK;
+}
+
+int dem_ctx_destroy(DemCtx* ctx) {
+    if (!ctx) return DEM_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_device(ctx);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (int k = 0; k < 4; k++)
+        if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return DEM_OK;
+}
+
+const char* dem_last_error(const DemCtx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int dem_set_stream(DemCtx* ctx, void* cuda_stream) {
+    if (!ctx) return DEM_ERR_INVALID;
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return DEM_OK;
+}
+
+int dem_set_params(DemCtx* ctx, const DemSimParams* p) {
+    if (!ctx || !p) return DEM_ERR_INVALID;
+    if (p->cd_update_freq < 1) return fail(ctx, DEM_ERR_INVALID, "cd_update_freq must be >= 1");
+    if (!(p->l > 0) || !(p->h > 0)) return fail(ctx, DEM_ERR_INVALID, "l and h must be positive");
+    if (p->force_model > DEM_HERTZIAN_FRICTIONLESS || p->integrator > DEM_EXTENDED_TAYLOR)
+        return fail(ctx, DEM_ERR_INVALID, "unknown force model / integrator");
+    if (ctx->initialized && (p->force_model != ctx->sp.force_model ||
+                             p->record_contact_forces != ctx->sp.record_contact_forces))
+        return fail(ctx, DEM_ERR_INVALID, "force model / force record cannot change after dem_initialize");
+    ctx->sp = *p;
+    ctx->params_set = true;
+    ctx->need_rebuild = true;
+    return DEM_OK;
+}
+
+int dem_upload_templates(DemCtx* ctx, uint32_t nComp, const float* radii, const float* relX, const float* relY,
+                         const float* relZ, uint32_t nMassProps, const float* mass, const float* moiX,
+                         const float* moiY, const float* moiZ) {
+    if (!ctx || (nComp && (!radii || !relX || !relY || !relZ)) || (nMassProps && (!mass || !moiX || !moiY || !moiZ)))
+        return DEM_ERR_INVALID;
+    if (nComp > 65535) return fail(ctx, DEM_ERR_INVALID, "more than 65535 distinct clump components");
+    ctx->h_comp.resize(nComp);
+    ctx->rmax = 0.f;
+    for (uint32_t i = 0; i < nComp; i++) {
+        ctx->h_comp[i] = make_float4(relX[i], relY[i], relZ[i], radii[i]);
+        ctx->rmax = std::max(ctx->rmax, radii[i]);
+    }
+    ctx->h_massprop.resize(nMassProps);
+    for (uint32_t i = 0; i < nMassProps; i++) ctx->h_massprop[i] = make_float4(mass[i], moiX[i], moiY[i], moiZ[i]);
+    return DEM_OK;
+}
+
+int dem_upload_materials(DemCtx* ctx, uint32_t nMat, const float* E, const float* nu, const float* CoR,
+                         const float* mu, const float* Crr) {
+    if (!ctx || !nMat || !E || !nu || !CoR || !mu || !Crr) return DEM_ERR_INVALID;
+    if (nMat > 255) return fail(ctx, DEM_ERR_INVALID, "more than 255 materials");
+    ctx->nMat = nMat;
+    ctx->h_matpair.resize((size_t)nMat * nMat);
+    for (uint32_t a = 0; a < nMat; a++)
+        for (uint32_t b = 0; b < nMat; b++) {
+            MatPair m;
+            // matProxy2ContactParam<float>, DEMHelperKernels.cuh:433-444
+            const float invE = (1.f - nu[a] * nu[a]) / E[a] + (1.f - nu[b] * nu[b]) / E[b];
+            m.E_cnt = 1.f / invE;
+            const float invG = 2.f * (2.f - nu[a]) * (1.f + nu[a]) / E[a] + 2.f * (2.f - nu[b]) * (1.f + nu[b]) / E[b];
+            m.G_cnt = 1.f / invG;
+            // FullHertzianForceModel.cu:59-60
+            const float cor = CoR[a * nMat + b];
+            const float loge = (float)((cor < 1e-12) ? std::log(1e-12) : (double)logf(cor));
+            m.beta = (float)(loge / std::sqrt(loge * loge + 9.869604401089358));
+            m.mu = mu[a * nMat + b];
+            m.Crr = Crr[a * nMat + b];
+            m.CoR = cor;
+            m.pad0 = m.pad1 = 0.f;
+            ctx->h_matpair[(size_t)a * nMat + b] = m;
+        }
+    return DEM_OK;
+}
+
+int dem_upload_analytical(DemCtx* ctx, uint32_t nAnal, const uint32_t* objOwner, const uint8_t* objType,
+                          const uint16_t* objMaterial, const float* objNormal, const float* relPosX,
+                          const float* relPosY, const float* relPosZ, const float* rotX, const float* rotY,
+                          const float* rotZ, const float* size1, const float* size2, const float* size3,
+                          const float* objMass) {
+    if (!ctx) return DEM_ERR_INVALID;
+    if (nAnal > 255) return fail(ctx, DEM_ERR_INVALID, "more than 255 analytical components (objID_t is 8 bit)");
+    ctx->h_anal.resize(nAnal);
+    for (uint32_t i = 0; i < nAnal; i++) {
+        AnalObj a;
+        memset(&a, 0, sizeof(a));
+        a.relx = relPosX[i]; a.rely = relPosY[i]; a.relz = relPosZ[i];
+        a.rotx = rotX[i]; a.roty = rotY[i]; a.rotz = rotZ[i];
+        a.size1 = size1[i]; a.size2 = size2[i]; a.size3 = size3[i];
+        a.normal_sign = objNormal[i];
+        a.mass = objMass[i];
+        a.owner = objOwner[i]; a.type = objType[i]; a.material = objMaterial[i];
+        if (a.type == DEM_ANAL_PLATE) return fail(ctx, DEM_ERR_INVALID, "plates are not supported (nor by the reference, DEMHelperKernels.cuh:491-493)");
+        ctx->h_anal[i] = a;
+    }
+    ctx->nAnal = nAnal;
+    return DEM_OK;
+}
+
+int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMargin, const DemPrescription* presc) {
+    if (!ctx) return DEM_ERR_INVALID;
+    ctx->h_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
+    ctx->h_extra.assign(DEM_NUM_FAMILIES, 0.f);
+    ctx->h_presc.resize(DEM_NUM_FAMILIES);
+    memset(ctx->h_presc.data(), 0, sizeof(Prescr) * DEM_NUM_FAMILIES);
+    if (masks) memcpy(ctx->h_masks.data(), masks, DEM_NUM_FAMILY_MASKS);
+    if (extraMargin) memcpy(ctx->h_extra.data(), extraMargin, sizeof(float) * DEM_NUM_FAMILIES);
+    if (presc) memcpy(ctx->h_presc.data(), presc, sizeof(Prescr) * DEM_NUM_FAMILIES);
+    ctx->any_mask = 0;
+    for (uint8_t m : ctx->h_masks) ctx->any_mask |= m;
+    ctx->max_extra = 0.f;
+    for (float e : ctx->h_extra) ctx->max_extra = std::max(ctx->max_extra, e);
+    if (ctx->initialized) {
+        cudaSetDevice(ctx->device);
+        CK(cudaMemcpyAsync(ctx->d_masks, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_extra, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_presc, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->need_rebuild = true;
+    }
+    return DEM_OK;
+}
+
+int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, const uint16_t* locX,
+                      const uint16_t* locY, const uint16_t* locZ, const float* oriQw, const float* oriQx,
+                      const float* oriQy, const float* oriQz, const float* vX, const float* vY, const float* vZ,
+                      const float* omgBarX, const float* omgBarY, const float* omgBarZ, const uint8_t* familyID,
+                      const uint16_t* inertiaPropOffsets) {
+    if (!ctx || (nOwners && (!voxelID || !locX || !locY || !locZ || !oriQw || !oriQx || !oriQy || !oriQz || !vX ||
+                             !vY || !vZ || !omgBarX || !omgBarY || !omgBarZ || !familyID || !inertiaPropOffsets)))
+        return DEM_ERR_INVALID;
+    if (ctx->h_massprop.empty()) return fail(ctx, DEM_ERR_INVALID, "dem_upload_templates must precede dem_upload_owners");
+    ctx->h_state.resize(nOwners);
+    for (uint32_t o = 0; o < nOwners; o++) {
+        OwnerState s;
+        s.pos.voxel = voxelID[o];
+        s.pos.lx = locX[o]; s.pos.ly = locY[o]; s.pos.lz = locZ[o];
+        s.pos.family = familyID[o];
+        s.pos.flags = 0;
+        s.quat = make_float4(oriQw[o], oriQx[o], oriQy[o], oriQz[o]);
+        if (inertiaPropOffsets[o] >= ctx->h_massprop.size())
+            return fail(ctx, DEM_ERR_INVALID, "owner %u refers to mass property %u (only %zu loaded)", o,
+                        (unsigned)inertiaPropOffsets[o], ctx->h_massprop.size());
+        s.vel = make_float4(vX[o], vY[o], vZ[o], ctx->h_massprop[inertiaPropOffsets[o]].x);
+        uint32_t bits = inertiaPropOffsets[o];
+        float fb;
+        memcpy(&fb, &bits, 4);
+        s.omg = make_float4(omgBarX[o], omgBarY[o], omgBarZ[o], fb);
+        ctx->h_state[o] = s;
+    }
+    ctx->nOwners = nOwners;
+    return DEM_OK;
+}
+
+int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClumpBody,
+                       const uint16_t* clumpComponentOffset, const uint16_t* sphereMaterialOffset) {
+    if (!ctx || (nSpheres && (!ownerClumpBody || !clumpComponentOffset || !sphereMaterialOffset))) return DEM_ERR_INVALID;
+    ctx->h_sph.resize(nSpheres);
+    uint32_t maxOwner = 0;
+    for (uint32_t i = 0; i < nSpheres; i++) {
+        if (clumpComponentOffset[i] >= ctx->h_comp.size())
+            return fail(ctx, DEM_ERR_INVALID, "sphere %u refers to component %u (only %zu loaded)", i,
+                        (unsigned)clumpComponentOffset[i], ctx->h_comp.size());
+        if (ctx->nMat && sphereMaterialOffset[i] >= ctx->nMat)
+            return fail(ctx, DEM_ERR_INVALID, "sphere %u refers to material %u (only %u loaded)", i,
+                        (unsigned)sphereMaterialOffset[i], ctx->nMat);
+        ctx->h_sph[i] = make_uint2(ownerClumpBody[i], (uint32_t)clumpComponentOffset[i] | ((uint32_t)sphereMaterialOffset[i] << 16));
+        maxOwner = std::max(maxOwner, ownerClumpBody[i]);
+    }
+    ctx->nSpheres = nSpheres;
+    ctx->nClumpOwners = nSpheres ? maxOwner + 1 : 0;
+    return DEM_OK;
+}
+
+int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, const float* node1, const float* node2,
+                         const float* node3, const uint16_t* triMaterialOffset) {
+    if (!ctx) return DEM_ERR_INVALID;
+    if (nTri != 0) return fail(ctx, DEM_ERR_INVALID, "sphere--triangle contacts are not built yet (SURVEY.md 8 row a8)");
+    (void)ownerMesh; (void)node1; (void)node2; (void)node3; (void)triMaterialOffset;
+    ctx->nTri = 0;
+    return DEM_OK;
+}
+
+int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
+    if (!ctx) return DEM_ERR_INVALID;
+    if (!ctx->params_set) return fail(ctx, DEM_ERR_INVALID, "dem_set_params must precede dem_initialize");
+    if (ctx->h_matpair.empty()) return fail(ctx, DEM_ERR_INVALID, "no materials uploaded");
+    if (ctx->h_masks.empty()) {
+        int rc = dem_upload_families(ctx, nullptr, nullptr, nullptr);
+        if (rc) return rc;
+    }
+    for (uint32_t i = 0; i < ctx->nSpheres; i++)
+        if (ctx->h_sph[i].x >= ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "sphere %u refers to owner %u (only %u owners)", i, ctx->h_sph[i].x, ctx->nOwners);
+    for (uint32_t i = 0; i < ctx->nAnal; i++)
+        if (ctx->h_anal[i].owner >= ctx->nOwners || ctx->h_anal[i].material >= ctx->nMat)
+            return fail(ctx, DEM_ERR_INVALID, "analytical component %u has a bad owner or material", i);
+    CK(cudaSetDevice(ctx->device));
+    free_device(ctx);
+    int rc;
+    const uint32_t nO = ctx->nOwners, nS = ctx->nSpheres;
+    if ((rc = dalloc(ctx, &ctx->d_state, nO))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_wrench, nO))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_acc, nO))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sph, nS))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_comp, ctx->h_comp.size()))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_massprop, ctx->h_massprop.size()))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_matpair, ctx->h_matpair.size()))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_anal, ctx->h_anal.size()))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_masks, DEM_NUM_FAMILY_MASKS))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_extra, DEM_NUM_FAMILIES))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_presc, DEM_NUM_FAMILIES))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_flags, 4))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_maxvel, 4))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_reduce, 4))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_grid, 1))) return rc;
+    CK(cudaMemcpy(ctx->d_state, ctx->h_state.data(), sizeof(OwnerState) * nO, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_wrench, 0, sizeof(Wrench) * std::max<size_t>(nO, 1)));
+    CK(cudaMemset(ctx->d_acc, 0, sizeof(Wrench) * std::max<size_t>(nO, 1)));
+    CK(cudaMemcpy(ctx->d_sph, ctx->h_sph.data(), sizeof(uint2) * nS, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_comp, ctx->h_comp.data(), sizeof(float4) * ctx->h_comp.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_massprop, ctx->h_massprop.data(), sizeof(float4) * ctx->h_massprop.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_matpair, ctx->h_matpair.data(), sizeof(MatPair) * ctx->h_matpair.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_anal, ctx->h_anal.data(), sizeof(AnalObj) * ctx->h_anal.size(), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_masks, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_extra, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_presc, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice));
+    CK(cudaMemset(ctx->d_flags, 0, sizeof(uint32_t) * 4));
+
+    // broad-phase sizing: the smallest cell the device may ever pick bounds the cell table and the sort key width
+    {
+        const DemSimParams& s = ctx->sp;
+        const float margin_min = (s.beta >= 0.f) ? s.beta : (float)((double)s.expSafetyAdder * s.h * s.cd_update_freq);
+        const float cs_min = 2.f * (ctx->rmax + std::max(margin_min, 0.f)) * 1.0005f + 1e-30f;
+        CdParams C = make_cd(ctx);
+        double cells = 1.0;
+        for (int k = 0; k < 3; k++) cells *= std::max(1.0, std::ceil((double)C.ext[k] / cs_min));
+        const double cap = std::max(65536.0, std::min(67108864.0, std::max(4194304.0, 8.0 * nS)));
+        ctx->max_cells = (uint32_t)std::min(cells, cap);
+        ctx->key_bits = 1;
+        while ((1ull << ctx->key_bits) < (unsigned long long)ctx->max_cells) ctx->key_bits++;
+    }
+    if ((rc = dalloc(ctx, &ctx->d_sphF, nS))) return rc;
+    for (int k = 0; k < 2; k++) {
+        if ((rc = dalloc(ctx, &ctx->d_keys[k], nS))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_vals[k], nS))) return rc;
+    }
+    if ((rc = dalloc(ctx, &ctx->d_cellStart, (size_t)ctx->max_cells + 2))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sortedSph, nS))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sortedMeta, nS))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_cnt, (size_t)nS + 2))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_saCnt, (size_t)nS + 2))) return rc;
+    const size_t rs_blocks = ((size_t)nS + 4095) / 4096 + 1;
+    if ((rc = dalloc(ctx, &ctx->d_rs_hist, 256 * rs_blocks))) return rc;
+    const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
+    if ((rc = dalloc(ctx, &ctx->d_scan_tmp, scan_n / 4096 + 2))) return rc;
+
+    uint64_t cap = contact_capacity ? contact_capacity : (uint64_t)nS * 8 + 1024;
+    if ((rc = alloc_lists(ctx, cap))) return rc;
+    ctx->cur = 0;
+
+    // grid-stride force kernels: a whole number of CTAs per SM
+    ctx->force_grid = ctx->num_sms * 8;
+    ctx->initialized = true;
+    ctx->need_rebuild = true;
+    ctx->steps_since_rebuild = 0;
+    ctx->n_ss = ctx->n_sa = 0;
+    return DEM_OK;
+}
+
+int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_t* idB, const uint8_t* type,
+                     const float* wildcards4) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if (n && (!idA || !idB || !type)) return DEM_ERR_INVALID;
+    if (n > ctx->capacity) return fail(ctx, DEM_ERR_CAPACITY, "dem_set_contacts: %llu contacts exceed capacity %llu",
+                                       (unsigned long long)n, (unsigned long long)ctx->capacity);
+    CK(cudaSetDevice(ctx->device));
+    // Build host-side "previous" lists grouped by sphere A so that the next rebuild carries the history over.
+    const uint32_t nS = ctx->nSpheres;
+    for (int which = 0; which < 2; which++) {
+        std::vector<uint64_t> idx;
+        for (uint64_t i = 0; i < n; i++) {
+            const bool is_ss = type[i] == DEM_CNT_SPHERE_SPHERE;
+            const bool is_sa = type[i] > 10;
+            if ((which == 0 && is_ss) || (which == 1 && is_sa)) idx.push_back(i);
+        }
+        std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return idA[a] < idA[b]; });
+        std::vector<uint2> pair(idx.size());
+        std::vector<uint4> cinfo(idx.size());
+        std::vector<float4> hist(idx.size());
+        std::vector<uint32_t> start(nS + 1, 0), count(nS + 1, 0);
+        for (size_t k = 0; k < idx.size(); k++) {
+            const uint64_t i = idx[k];
+            if (idA[i] >= nS) return fail(ctx, DEM_ERR_INVALID, "contact %llu: bad geometry A", (unsigned long long)i);
+            pair[k] = make_uint2(idA[i], idB[i]);
+            float4 h = make_float4(0, 0, 0, 0);
+            if (wildcards4) h = make_float4(wildcards4[4 * i], wildcards4[4 * i + 1], wildcards4[4 * i + 2], wildcards4[4 * i + 3]);
+            hist[k] = h;
+            const bool alive = (h.x != 0.f || h.y != 0.f || h.z != 0.f || h.w != 0.f);
+            cinfo[k] = make_uint4(0, 0, 0, alive ? 0x80000000u : 0u);
+            count[idA[i]]++;
+        }
+        for (uint32_t s = 0, run = 0; s < nS; s++) { start[s] = run; run += count[s]; }
+        ListBuf& L = (which == 0) ? ctx->ss[ctx->cur] : ctx->sa[ctx->cur];
+        const uint32_t cnt = (uint32_t)idx.size();
+        CK(cudaMemcpy(L.pair, pair.data(), sizeof(uint2) * idx.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.cinfo, cinfo.data(), sizeof(uint4) * idx.size(), cudaMemcpyHostToDevice));
+        if (L.hist) CK(cudaMemcpy(L.hist, hist.data(), sizeof(float4) * idx.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.seg_start, start.data(), sizeof(uint32_t) * (nS + 1), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.seg_count, count.data(), sizeof(uint32_t) * (nS + 1), cudaMemcpyHostToDevice));
+        // the old list is only a history source: its count is not used by force kernels until the rebuild swaps
+        const uint32_t zero = 0;
+        (void)cnt;
+        CK(cudaMemcpy(L.count, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    ctx->need_rebuild = true;
+    return DEM_OK;
+}
+
+int dem_rebuild_contacts(DemCtx* ctx) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    return rebuild(ctx);
+}
+
+int dem_step_async(DemCtx* ctx, uint64_t n_steps) {
+    if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
+    CK(cudaSetDevice(ctx->device));
+    for (uint64_t i = 0; i < n_steps; i++) {
+        int rc = enqueue_step(ctx);
+        if (rc) return rc;
+    }
+    CK(cudaGetLastError());
+    return DEM_OK;
+}
+
+int dem_sync(DemCtx* ctx) {
+    if (!ctx) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DEM_OK;
+}
+
+int dem_step(DemCtx* ctx, uint64_t n_steps) {
+    int rc = dem_step_async(ctx, n_steps);
+    if (rc) return rc;
+    return dem_sync(ctx);
+}
+
+int dem_do_dynamics(DemCtx* ctx, double t) {
+    if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
+    if (t <= 0.0) {
+        // dry run: only (re)build the contact list (DoDynamicsThenSync(0), dT.cpp:2393-2398)
+        return dem_rebuild_contacts(ctx);
+    }
+    // the reference's loop: for (double cycle = 0; cycle < t; cycle += (double)h) with the float-rounded h (dT.cpp:2401)
+    uint64_t n = 0;
+    const double h = (double)ctx->sp.h;
+    for (double cycle = 0.0; cycle < t; cycle += h) n++;
+    return dem_step(ctx, n);
+}
+
+int dem_update_step_size(DemCtx* ctx, float h) {
+    if (!ctx || !(h > 0)) return DEM_ERR_INVALID;
+    ctx->sp.h = h;
+    ctx->need_rebuild = true;  // margins depend on h
+    return DEM_OK;
+}
+
+int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* voxelID, uint16_t* locX,
+                             uint16_t* locY, uint16_t* locZ, float* oriQ, float* vel, float* omg, float* acc,
+                             float* angacc, uint8_t* family) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<OwnerState> st(n);
+    CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    std::vector<Wrench> ac;
+    if (acc || angacc) {
+        ac.resize(n);
+        CK(cudaMemcpy(ac.data(), ctx->d_acc + first, sizeof(Wrench) * n, cudaMemcpyDeviceToHost));
+    }
+    for (uint32_t i = 0; i < n; i++) {
+        const OwnerState& s = st[i];
+        if (voxelID) voxelID[i] = s.pos.voxel;
+        if (locX) locX[i] = s.pos.lx;
+        if (locY) locY[i] = s.pos.ly;
+        if (locZ) locZ[i] = s.pos.lz;
+        if (family) family[i] = s.pos.family;
+        if (oriQ) { oriQ[4 * i] = s.quat.x; oriQ[4 * i + 1] = s.quat.y; oriQ[4 * i + 2] = s.quat.z; oriQ[4 * i + 3] = s.quat.w; }
+        if (vel) { vel[3 * i] = s.vel.x; vel[3 * i + 1] = s.vel.y; vel[3 * i + 2] = s.vel.z; }
+        if (omg) { omg[3 * i] = s.omg.x; omg[3 * i + 1] = s.omg.y; omg[3 * i + 2] = s.omg.z; }
+        if (acc) { acc[3 * i] = ac[i].f.x; acc[3 * i + 1] = ac[i].f.y; acc[3 * i + 2] = ac[i].f.z; }
+        if (angacc) { angacc[3 * i] = ac[i].t.x; angacc[3 * i + 1] = ac[i].t.y; angacc[3 * i + 2] = ac[i].t.z; }
+    }
+    return DEM_OK;
+}
+
+int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz32, double* xyz64) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<OwnerState> st(n);
+    CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    const DemSimParams& p = ctx->sp;
+    for (uint32_t i = 0; i < n; i++) {
+        const OwnerPos& s = st[i].pos;
+        const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
+        const uint64_t vy = (s.voxel >> p.nvXp2) & ((1ull << p.nvYp2) - 1ull);
+        const uint64_t vz = s.voxel >> (p.nvXp2 + p.nvYp2);
+        const double X[3] = {(double)vx * p.voxelSize + (double)s.lx * p.l, (double)vy * p.voxelSize + (double)s.ly * p.l,
+                             (double)vz * p.voxelSize + (double)s.lz * p.l};
+        for (int k = 0; k < 3; k++) {
+            if (xyz64) xyz64[3 * i + k] = X[k] + (double)p.LBF[k];
+            // the reference decodes in float and adds the float LBF (dT.cpp:3062-3076)
+            if (xyz32) xyz32[3 * i + k] = (float)(X[k] + (double)p.LBF[k]);
+        }
+    }
+    return DEM_OK;
+}
+
+int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float* pos, const float* oriQ,
+                           const float* vel, const float* omg, const uint8_t* family) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<OwnerState> st(n);
+    CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) {
+        OwnerState& s = st[i];
+        if (pos) {
+            uint64_t v;
+            uint16_t lx, ly, lz;
+            dem_host_encode_positions(&ctx->sp, pos + 3 * i, 1, &v, &lx, &ly, &lz);
+            s.pos.voxel = v; s.pos.lx = lx; s.pos.ly = ly; s.pos.lz = lz;
+        }
+        if (oriQ) s.quat = make_float4(oriQ[4 * i], oriQ[4 * i + 1], oriQ[4 * i + 2], oriQ[4 * i + 3]);
+        if (vel) { s.vel.x = vel[3 * i]; s.vel.y = vel[3 * i + 1]; s.vel.z = vel[3 * i + 2]; }
+        if (omg) { s.omg.x = omg[3 * i]; s.omg.y = omg[3 * i + 1]; s.omg.z = omg[3 * i + 2]; }
+        if (family) s.pos.family = family[i];
+    }
+    CK(cudaMemcpy(ctx->d_state + first, st.data(), sizeof(OwnerState) * n, cudaMemcpyHostToDevice));
+    ctx->need_rebuild = true;
+    return DEM_OK;
+}
+
+int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB, uint8_t* type,
+                          float* wildcards4, float* force_xyz) {
+    if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t nss = ctx->n_ss, nsa = ctx->n_sa, n = nss + nsa;
+    *n_out = n;
+    if (!idA && !idB && !type && !wildcards4 && !force_xyz) return DEM_OK;
+    if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
+    struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; };
+    std::vector<Row> rows;
+    rows.reserve(n);
+    for (int which = 0; which < 2; which++) {
+        const ListBuf& L = which == 0 ? ctx->ss[ctx->cur] : ctx->sa[ctx->cur];
+        const uint64_t m = which == 0 ? nss : nsa;
+        std::vector<uint2> pair(m);
+        std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0));
+        CK(cudaMemcpy(pair.data(), L.pair, sizeof(uint2) * m, cudaMemcpyDeviceToHost));
+        if (L.hist) CK(cudaMemcpy(hist.data(), L.hist, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        if (L.force) CK(cudaMemcpy(frc.data(), L.force, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        std::vector<uint4> ci(m);
+        CK(cudaMemcpy(ci.data(), L.cinfo, sizeof(uint4) * m, cudaMemcpyDeviceToHost));
+        for (uint64_t i = 0; i < m; i++) {
+            Row r;
+            r.a = pair[i].x; r.b = pair[i].y;
+            if (which == 0) r.t = DEM_CNT_SPHERE_SPHERE;
+            else r.t = (ctx->h_anal[pair[i].y].type == DEM_ANAL_PLANE) ? DEM_CNT_SPHERE_PLANE : DEM_CNT_SPHERE_CYL;
+            // history words of contacts that are not alive are stale by construction: report zeros
+            r.h = (ci[i].w & 0x80000000u) ? hist[i] : make_float4(0, 0, 0, 0);
+            r.f = frc[i];
+            rows.push_back(r);
+        }
+    }
+    std::sort(rows.begin(), rows.end(), [](const Row& x, const Row& y) {
+        if (x.t != y.t) return x.t < y.t;
+        if (x.a != y.a) return x.a < y.a;
+        return x.b < y.b;
+    });
+    for (uint64_t i = 0; i < n; i++) {
+        if (idA) idA[i] = rows[i].a;
+        if (idB) idB[i] = rows[i].b;
+        if (type) type[i] = rows[i].t;
+        if (wildcards4) { wildcards4[4 * i] = rows[i].h.x; wildcards4[4 * i + 1] = rows[i].h.y; wildcards4[4 * i + 2] = rows[i].h.z; wildcards4[4 * i + 3] = rows[i].h.w; }
+        if (force_xyz) { force_xyz[3 * i] = rows[i].f.x; force_xyz[3 * i + 1] = rows[i].f.y; force_xyz[3 * i + 2] = rows[i].f.z; }
+    }
+    return DEM_OK;
+}
+
+int dem_get_stats(DemCtx* ctx, DemStats* out) {
+    if (!ctx || !out) return DEM_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->n_steps = ctx->n_steps; out->n_rebuilds = ctx->n_rebuilds;
+    out->n_contacts_ss = ctx->n_ss; out->n_contacts_sa = ctx->n_sa; out->n_contacts_st = 0;
+    out->contact_capacity = ctx->capacity; out->kernel_launches = ctx->launches; out->device_bytes = ctx->device_bytes;
+    out->sim_time = ctx->sim_time; out->max_margin = ctx->last_grid.max_margin; out->cell_size = ctx->last_grid.cs;
+    out->n_cells[0] = ctx->last_grid.nbx; out->n_cells[1] = ctx->last_grid.nby; out->n_cells[2] = ctx->last_grid.nbz;
+    out->overflow = ctx->overflow_seen;
+    return DEM_OK;
+}
+
+int dem_reduce(DemCtx* ctx, int kind, double* out) {
+    if (!ctx || !ctx->initialized || !out) return DEM_ERR_INVALID;
+    if (kind < DEM_REDUCE_MAX_ABSV || kind > DEM_REDUCE_TOTAL_MASS) return fail(ctx, DEM_ERR_INVALID, "unknown reduction");
+    CK(cudaSetDevice(ctx->device));
+    const double init = (kind == DEM_REDUCE_MIN_Z) ? 1e300 : ((kind == DEM_REDUCE_MAX_Z) ? -1e300 : 0.0);
+    CK(cudaMemcpyAsync(ctx->d_reduce, &init, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DevParams P = make_params(ctx);
+    P.nOwners = ctx->nClumpOwners;  // inspectors of the reference look at clumps only
+    ctx->launches += launch_reduce(P, kind, ctx->d_reduce, ctx->stream);
+    CK(cudaMemcpyAsync(out, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DEM_OK;
+}
+
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[4]) {
+    if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    double acc[4] = {0, 0, 0, 0};
+    cudaStream_t s = ctx->stream;
+    for (uint64_t i = 0; i < n_steps; i++) {
+        CK(cudaEventRecord(ctx->ev[0], s));
+        if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+            int rc = rebuild(ctx);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(ctx->ev[1], s));
+        DevParams P = make_params(ctx);
+        launch_force(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->force_grid, s, ctx->nAnal > 0);
+        CK(cudaEventRecord(ctx->ev[2], s));
+        launch_integrate(P, s);
+        CK(cudaEventRecord(ctx->ev[3], s));
+        ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
+        ctx->n_steps++;
+        ctx->steps_since_rebuild++;
+        ctx->sim_time += (double)ctx->sp.h;
+        CK(cudaEventSynchronize(ctx->ev[3]));
+        float ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); acc[0] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); acc[1] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); acc[2] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3])); acc[3] += ms;
+    }
+    for (int k = 0; k < 4; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;
+    return DEM_OK;
+}
+
+}  // extern "C"

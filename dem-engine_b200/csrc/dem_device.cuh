@@ -1,0 +1,203 @@
+// dem_device.cuh -- device data layout and math helpers of the B200-native DEM core.
+//
+// HBM layout (see DESIGN.md "Data layout"):
+//   owners  : four 16-byte records per owner, each fetched with ONE 128-bit load
+//             pos  {u64 voxelID; u16 locX,locY,locZ; u8 family; u8 flags}   (the reference's voxelID/locX/locY/locZ/
+//                   familyID arrays, src/DEM/Defines.h:272-280, packed)
+//             quat {w,x,y,z}     vel {vx,vy,vz,mass}     omg {wx,wy,wz, bits(inertiaPropOffset)}
+//           + one 32-byte wrench accumulator {Fx,Fy,Fz,0 | Tx,Ty,Tz,0} (force in world frame, torque in body frame),
+//             the target of 128-bit vector reductions (red.global.add.v4.f32, sm_90+).
+//   spheres : uint2 {owner, comp | material<<16}
+//   contacts: uint2 {geoA, geoB} + float4 history {delta_tan_xyz, delta_time} per list (sphere-sphere,
+//             sphere-analytical, sphere-triangle are separate lists, so no per-contact type byte is stored).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace demb {
+
+struct __align__(16) OwnerPos {
+    unsigned long long voxel;
+    unsigned short lx, ly, lz;
+    unsigned char family;
+    unsigned char flags;
+};
+static_assert(sizeof(OwnerPos) == 16, "OwnerPos must be one 128-bit word");
+
+// 64-byte owner record: one 128-byte line holds two owners; a gather costs exactly two 32-byte sectors
+struct __align__(64) OwnerState {
+    OwnerPos pos;
+    float4 quat;  // w,x,y,z
+    float4 vel;   // vx,vy,vz, mass
+    float4 omg;   // body-frame angular velocity, w = bits(inertiaPropOffset)
+};
+static_assert(sizeof(OwnerState) == 64, "OwnerState must be 64 bytes");
+
+struct __align__(32) Wrench {
+    float4 f;  // world-frame force sum
+    float4 t;  // body-frame torque sum
+};
+
+// per material pair, precomputed on the host exactly as matProxy2ContactParam<float> and the beta expression of
+// FullHertzianForceModel.cu:59-60 evaluate them
+struct __align__(16) MatPair {
+    float E_cnt, G_cnt, beta, mu;
+    float Crr, CoR, pad0, pad1;
+};
+
+struct __align__(16) AnalObj {
+    float relx, rely, relz;  // component position in owner frame
+    float rotx, roty, rotz;  // plane normal / cylinder axis in owner frame
+    float size1, size2, size3;
+    float normal_sign;  // objNormal
+    float mass;
+    uint32_t owner;
+    uint32_t type;
+    uint32_t material;
+    uint32_t pad0, pad1;
+};
+
+struct Prescr {  // == DemPrescription (88 bytes)
+    uint8_t used;
+    uint8_t linVelPrescribed[3];
+    uint8_t rotVelPrescribed[3];
+    uint8_t linPosPrescribed[3];
+    uint8_t rotPosPrescribed;
+    uint8_t hasLinVel[3];
+    uint8_t hasRotVel[3];
+    uint8_t hasLinPos[3];
+    uint8_t hasAcc[3];
+    uint8_t hasAngAcc[3];
+    uint8_t pad_[2];
+    float linVel[3];
+    float rotVel[3];
+    float linPos[3];
+    float acc[3];
+    float angAcc[3];
+};
+static_assert(sizeof(Prescr) == 88, "Prescr must match DemPrescription");
+
+// one contact list
+struct ContactList {
+    uint2* pair;         // {geoA, geoB}: sphere ids (geoB = analytical component / triangle id for the other lists)
+    uint4* cinfo;        // compiled record {ownerA, ownerB|objID, compA | compB<<16, matpair | alive<<31}
+    float4* hist;        // delta_tan_xyz, delta_time
+    uint32_t* seg_start; // per sphere A: first contact of A in this list
+    uint32_t* seg_count; // per sphere A: number of contacts of A
+    uint32_t* count;     // device-resident number of contacts
+    float4* force;       // optional per-contact force record (xyz) -- nullptr when SetNoForceRecord
+};
+
+// Everything a kernel needs, passed by value (__grid_constant__)
+struct DevParams {
+    // position code
+    uint32_t nvXp2, nvYp2;
+    double l, voxelSize, inv_l;
+    float LBF[3];
+    float G[3];
+    float h;
+    float half_h;  // (float)(0.5*h)
+    uint32_t integrator;
+    uint32_t nOwners, nSpheres, nAnal, nTri, nMat;
+    // margin policy
+    float beta, approxMaxVel, expSafetyMulti, expSafetyAdder;
+    float drift_h;  // h * maxDrift as the reference forms it: (double)(..)*ts*maxDrift, evaluated per owner
+    uint32_t maxDrift;
+    // owners
+    OwnerState* state;
+    Wrench* wrench;
+    Wrench* acc_out;  // optional per-owner {a, alpha} read-out (nullptr = off)
+    // spheres / templates
+    const uint2* sph;
+    const float4* comp;      // {relx, rely, relz, radius}
+    const float4* massprop;  // {mass, moiX, moiY, moiZ}
+    const MatPair* matpair;  // nMat x nMat
+    const AnalObj* anal;
+    const float4* tri_n1;  // triangle nodes in owner frame (xyz, w unused)
+    const float4* tri_n2;
+    const float4* tri_n3;
+    const uint2* tri_info;  // {ownerMesh, material}
+    const uint8_t* familyMasks;
+    const float* familyExtraMargin;
+    const Prescr* presc;
+    // contact lists
+    ContactList ss, sa, st;
+    // status flags (device): [0] capacity overflow, [1] non-finite / too-fast owner, [2] cell overflow
+    uint32_t* flags;
+    float* maxvel;  // device float: max |v| seen by the last margin pass
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator*(float s, float3 a) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float3 cross(float3 a, float3 b) {
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float length(float3 a) { return sqrtf(dot(a, a)); }
+
+// applyOriQToVector3 (reference src/kernel/DEMHelperKernels.cuh:161-173); q = {w,x,y,z}
+__device__ __forceinline__ float3 rotate(float3 v, float4 q) {
+    const float w = q.x, x = q.y, y = q.z, z = q.w;
+    float3 r;
+    r.x = (2.0f * (w * w + x * x) - 1.0f) * v.x + (2.0f * (x * y - w * z)) * v.y + (2.0f * (x * z + w * y)) * v.z;
+    r.y = (2.0f * (x * y + w * z)) * v.x + (2.0f * (w * w + y * y) - 1.0f) * v.y + (2.0f * (y * z - w * x)) * v.z;
+    r.z = (2.0f * (x * z - w * y)) * v.x + (2.0f * (y * z + w * x)) * v.y + (2.0f * (w * w + z * z) - 1.0f) * v.z;
+    return r;
+}
+__device__ __forceinline__ float3 rotate_inv(float3 v, float4 q) {
+    return rotate(v, make_float4(q.x, -q.y, -q.z, -q.w));
+}
+
+// integer world coordinates in units of l (voxel index * 2^16 + sub-voxel), reference DEMHelperKernels.cuh:91-134
+__device__ __forceinline__ void pos_ints(const OwnerPos& p, uint32_t nvXp2, uint32_t nvYp2, long long& ix,
+                                         long long& iy, long long& iz) {
+    const unsigned long long vx = p.voxel & ((1ull << nvXp2) - 1ull);
+    const unsigned long long vy = (p.voxel >> nvXp2) & ((1ull << nvYp2) - 1ull);
+    const unsigned long long vz = p.voxel >> (nvXp2 + nvYp2);
+    ix = (long long)((vx << 16) | p.lx);
+    iy = (long long)((vy << 16) | p.ly);
+    iz = (long long)((vz << 16) | p.lz);
+}
+// decode exactly as voxelIDToPosition<double>: X = vx*voxelSize + sub*l (LBF-relative)
+__device__ __forceinline__ void pos_decode(const OwnerPos& p, const DevParams& P, double& X, double& Y, double& Z) {
+    const unsigned long long vx = p.voxel & ((1ull << P.nvXp2) - 1ull);
+    const unsigned long long vy = (p.voxel >> P.nvXp2) & ((1ull << P.nvYp2) - 1ull);
+    const unsigned long long vz = p.voxel >> (P.nvXp2 + P.nvYp2);
+    X = (double)vx * P.voxelSize + (double)p.lx * P.l;
+    Y = (double)vy * P.voxelSize + (double)p.ly * P.l;
+    Z = (double)vz * P.voxelSize + (double)p.lz * P.l;
+}
+// positionToVoxelID (reference DEMHelperKernels.cuh:137-159): truncating encode
+__device__ __forceinline__ void pos_encode(OwnerPos& p, const DevParams& P, double X, double Y, double Z) {
+    const unsigned long long nx = (unsigned long long)(X / P.voxelSize);
+    const unsigned long long ny = (unsigned long long)(Y / P.voxelSize);
+    const unsigned long long nz = (unsigned long long)(Z / P.voxelSize);
+    p.lx = (unsigned short)((X - (double)nx * P.voxelSize) / P.l);
+    p.ly = (unsigned short)((Y - (double)ny * P.voxelSize) / P.l);
+    p.lz = (unsigned short)((Z - (double)nz * P.voxelSize) / P.l);
+    p.voxel = nx + (ny << P.nvXp2) + (nz << (P.nvXp2 + P.nvYp2));
+}
+
+__device__ __forceinline__ uint32_t mask_pair(uint32_t i, uint32_t j) {
+    const uint32_t a = min(i, j), b = max(i, j);
+    return (1u + b) * b / 2u + a;
+}
+
+// 128-bit vector reduction into global memory (sm_90+): SASS REDG.E.ADD.F32x4
+__device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f)
+                 : "memory");
+}
+
+template <typename T>
+__device__ __forceinline__ T ldg128(const T* p) {
+    static_assert(sizeof(T) == 16, "128-bit load");
+    int4 r = __ldg(reinterpret_cast<const int4*>(p));
+    return *reinterpret_cast<T*>(&r);
+}
+
+}  // namespace demb

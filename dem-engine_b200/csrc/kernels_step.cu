@@ -1,0 +1,410 @@
+// kernels_step.cu -- per-step hot kernels: contact force (Hertz-Mindlin with history / frictionless Hertz) and
+// owner integration.  Hand-written for sm_100a; HBM-bound by design:
+//   * every owner gather is two 256-bit loads of one 64-byte record (LDG.E.ENL2.256),
+//   * the contact stream is a 128-bit compiled record + a 128-bit history word, the history word being touched only
+//     for contacts that are (or just stopped being) in physical touch,
+//   * owner wrenches are scattered with 128-bit vector reductions (REDG.E.ADD.F32x4) into a 32-byte accumulator that
+//     stays L2-resident.
+// Reference behaviour being reproduced: src/kernel/DEMCalcForceKernels.cu:44-267 (calculateContactForces),
+// DEMCustomizablePolicies/FullHertzianForceModel.cu, FrictionlessHertzianForceModel.cu,
+// src/kernel/DEMCollectForceKernels_Compact.cu:13-102 (forceToAcc), src/kernel/DEMIntegrationKernels.cu:100-264.
+#include "dem_kernels.h"
+
+namespace demb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// gathered end point
+struct End {
+    float4 q;    // w,x,y,z
+    float3 v;    // linear velocity
+    float3 w;    // body-frame angular velocity (omgBar)
+    float mass;
+};
+
+__device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, uint32_t o, OwnerPos& pos, End& e) {
+    // two 256-bit loads: {pos,quat} and {vel,omg}
+    const float* base = reinterpret_cast<const float*>(st + o);
+    uint32_t a0, a1, a2, a3;
+    float q0, q1, q2, q3, v0, v1, v2, v3, w0, w1, w2, w3;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=f"(q0), "=f"(q1), "=f"(q2), "=f"(q3)
+                 : "l"(base));
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3), "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
+                 : "l"(base + 8));
+    pos.voxel = ((unsigned long long)a1 << 32) | a0;
+    pos.lx = (unsigned short)(a2 & 0xffffu);
+    pos.ly = (unsigned short)(a2 >> 16);
+    pos.lz = (unsigned short)(a3 & 0xffffu);
+    pos.family = (unsigned char)((a3 >> 16) & 0xffu);
+    pos.flags = (unsigned char)(a3 >> 24);
+    e.q = make_float4(q0, q1, q2, q3);
+    e.v = f3(v0, v1, v2);
+    e.mass = v3;
+    e.w = f3(w0, w1, w2);
+}
+
+// Hertz-Mindlin with history (MODEL 0) or frictionless Hertz (MODEL 1).
+//   depth > 0, n = unit normal B->A, cA/cB = contact point in the body frames of A/B.
+// Returns force on A (world) and the torque-only rolling-resistance pseudo force.
+template <int MODEL>
+__device__ __forceinline__ void contact_model(const MatPair& mp, float h, float depth, float3 n, float3 cA, float3 cB,
+                                              const End& A, const End& B, float rA, float rB, float4& hist,
+                                              float3& force, float3& troll) {
+    const float3 rotVelCPA = rotate(cross(A.w, cA), A.q);
+    const float3 rotVelCPB = rotate(cross(B.w, cB), B.q);
+    const float3 velB2A = (A.v + rotVelCPA) - (B.v + rotVelCPB);
+    const float projection = dot(velB2A, n);
+    const float mass_eff = (A.mass * B.mass) / (A.mass + B.mass);
+    const float sqrt_Rd = sqrtf(depth * ((rA * rB) / (rA + rB)));
+    const float Sn = 2.f * mp.E_cnt * sqrt_Rd;
+    const float k_n = 0.6666666666666666f * Sn;
+    const float gamma_n = 1.825741858350554f * mp.beta * sqrtf(Sn * mass_eff);
+    force = (k_n * depth + gamma_n * projection) * n;
+    troll = f3(0.f, 0.f, 0.f);
+    if (MODEL == 0) {
+        const float3 vrel_tan = velB2A - projection * n;
+        float3 delta_tan = f3(hist.x, hist.y, hist.z);
+        delta_tan = delta_tan + h * vrel_tan;
+        delta_tan = delta_tan - dot(delta_tan, n) * n;
+        float delta_time = hist.w + h;
+        if (mp.Crr > 0.f) {
+            bool add = true;
+            const float R_eff = sqrtf((rA * rB) / (rA + rB));
+            const float kn_simple = 1.3333333333333333f * mp.E_cnt * sqrtf(R_eff);
+            const float gn_simple = -2.f * sqrtf(1.6666666666666667f * mass_eff * mp.E_cnt) * mp.beta * powf(R_eff, 0.25f);
+            const float d_coeff = gn_simple / (2.f * sqrtf(kn_simple * mass_eff));
+            if (d_coeff < 1.0f) {
+                const float t_collision = 3.1415926535897932f * sqrtf(mass_eff / (kn_simple * (1.f - d_coeff * d_coeff)));
+                if (delta_time <= t_collision) add = false;
+            }
+            if (add) {
+                const float3 v_rot = rotVelCPB - rotVelCPA;
+                const float v_rot_mag = length(v_rot);
+                if (v_rot_mag > 1e-12f) troll = (v_rot * (1.f / v_rot_mag)) * (mp.Crr * length(force));
+            }
+        }
+        if (mp.mu > 0.f) {
+            const float kt = 8.f * mp.G_cnt * sqrt_Rd;
+            const float gt = -1.825741858350554f * mp.beta * sqrtf(mass_eff * kt);
+            float3 tf = (-kt) * delta_tan - gt * vrel_tan;
+            const float ft = length(tf);
+            if (ft > 1e-12f) {
+                const float ft_max = length(force) * mp.mu;
+                if (ft > ft_max) {
+                    tf = (ft_max / ft) * tf;
+                    delta_tan = (tf + gt * vrel_tan) * (1.f / (-kt));
+                }
+            } else {
+                tf = f3(0.f, 0.f, 0.f);
+            }
+            force = force + tf;
+        }
+        hist = make_float4(delta_tan.x, delta_tan.y, delta_tan.z, delta_time);
+    }
+}
+
+// scatter the wrench of one contact to both owners (forceToAcc semantics, but sums force / body-frame torque;
+// the division by mass / MOI happens once per owner in the integrator)
+__device__ __forceinline__ void scatter_wrench(Wrench* __restrict__ wr, uint32_t oA, uint32_t oB, float3 force,
+                                               float3 troll, float3 cA, float3 cB, float4 qA, float4 qB) {
+    const float3 FA = rotate_inv(force + troll, qA);
+    const float3 TA = cross(cA, FA);
+    red_add_v4(&wr[oA].f, force.x, force.y, force.z);
+    red_add_v4(&wr[oA].t, TA.x, TA.y, TA.z);
+    const float3 nf = f3(-force.x, -force.y, -force.z);
+    const float3 FB = rotate_inv(f3(-1.f * (force.x + troll.x), -1.f * (force.y + troll.y), -1.f * (force.z + troll.z)), qB);
+    const float3 TB = cross(cB, FB);
+    red_add_v4(&wr[oB].f, nf.x, nf.y, nf.z);
+    red_add_v4(&wr[oB].t, TB.x, TB.y, TB.z);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sphere--sphere contacts.  One thread per contact, grid-stride over a DEVICE-resident count (no host sync).
+template <int MODEL, bool RECORD>
+__global__ void __launch_bounds__(256) k_force_ss(const __grid_constant__ DevParams P) {
+    const uint32_t n = *P.ss.count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const uint4 ci = __ldcs(&P.ss.cinfo[c]);  // streaming: evict-first
+        const uint32_t oA = ci.x, oB = ci.y;
+        const bool alive = (ci.w >> 31) != 0u;
+        float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODEL == 0 && alive) hist = __ldcs(&P.ss.hist[c]);
+        const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
+        const float4 compB = __ldg(&P.comp[ci.z >> 16]);
+        OwnerPos pA, pB;
+        End A, B;
+        load_owner(P.state, oA, pA, A);
+        load_owner(P.state, oB, pB, B);
+
+        // ---- narrow phase (checkSpheresOverlap<double,float>, DEMHelperKernels.cuh:292-326) ----
+        const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
+        const float3 relB = rotate(f3(compB.x, compB.y, compB.z), B.q);
+        long long ax, ay, az, bx, by, bz;
+        pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
+        pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
+        // centre(A) - centre(B): exact integer owner difference (units of l) + rotated offsets
+        const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
+        const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
+        const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const float rA = compA.w, rB = compB.w;
+        const double R = (double)rA + (double)rB;
+        float3 nrm = f3((float)dx, (float)dy, (float)dz);
+        const float mag = sqrtf(dot(nrm, nrm));
+        // overlap = R - |d| = (R^2 - d^2) / (R + |d|): numerator in double, the rest in float
+        const float depth = (float)(R * R - d2) / ((float)R + mag);
+
+        if (depth > 0.f) {
+            nrm = nrm * (1.f / mag);
+            // contact point = centre(B) + (rB - depth/2) n ; relative to each owner (float lever arms)
+            const float s = rB - 0.5f * depth;
+            const float3 cpB_w = relB + s * nrm;                                   // CP - ownerB
+            const float3 cpA_w = f3(relA.x - (float)dx, relA.y - (float)dy, relA.z - (float)dz) + s * nrm;  // CP - ownerA
+            const float3 cA = rotate_inv(cpA_w, A.q);
+            const float3 cB = rotate_inv(cpB_w, B.q);
+            const MatPair mp = P.matpair[ci.w & 0xffffu];
+            float3 force, troll;
+            contact_model<MODEL>(mp, P.h, depth, nrm, cA, cB, A, B, rA, rB, hist, force, troll);
+            scatter_wrench(P.wrench, oA, oB, force, troll, cA, cB, A.q, B.q);
+            if (MODEL == 0) {
+                __stcs(&P.ss.hist[c], hist);
+                if (!alive) P.ss.cinfo[c].w = ci.w | 0x80000000u;
+            }
+            if (RECORD) P.ss.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+        } else {
+            // not in touch: destroy history (FullHertzianForceModel.cu:129-136, DEMCalcForceKernels.cu:258-261)
+            if (MODEL == 0 && alive) {
+                __stcs(&P.ss.hist[c], make_float4(0.f, 0.f, 0.f, 0.f));
+                P.ss.cinfo[c].w = ci.w & 0x7fffffffu;
+            }
+            if (RECORD) P.ss.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sphere--analytical contacts (planes, infinite cylinders): checkSphereEntityOverlap, DEMHelperKernels.cuh:459-521
+template <int MODEL, bool RECORD>
+__global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevParams P) {
+    const uint32_t n = *P.sa.count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const uint4 ci = P.sa.cinfo[c];
+        const uint32_t oA = ci.x;
+        const AnalObj ob = P.anal[ci.y];
+        const uint32_t oB = ob.owner;
+        const bool alive = (ci.w >> 31) != 0u;
+        float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODEL == 0 && alive) hist = P.sa.hist[c];
+        const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
+        OwnerPos pA, pB;
+        End A, B;
+        load_owner(P.state, oA, pA, A);
+        load_owner(P.state, oB, pB, B);
+        B.mass = ob.mass;  // objMass (DEMCalcForceKernels.cu:198)
+        const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
+        const float3 relB = rotate(f3(ob.relx, ob.rely, ob.relz), B.q);
+        const float3 dirB = rotate(f3(ob.rotx, ob.roty, ob.rotz), B.q);
+        long long ax, ay, az, bx, by, bz;
+        pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
+        pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
+        // sphere centre minus entity point
+        const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
+        const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
+        const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
+        const float rA = compA.w;
+        float depth;
+        float3 nrm;
+        float3 cpA_w;  // CP - ownerA
+        if (ob.type == DEM_ANAL_PLANE) {
+            const float dist = (float)(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z);
+            depth = (float)((double)rA - (double)dist);
+            const float s = (float)((double)dist + ((double)rA - (double)dist) / 2.0);
+            nrm = dirB;
+            cpA_w = relA - s * dirB;
+        } else {  // DEM_ANAL_CYL_INF
+            // sph2cyl = B - A, minus its axial projection
+            const float proj = (float)(-(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z));
+            const double sx = -dx - (double)(proj * dirB.x);
+            const double sy = -dy - (double)(proj * dirB.y);
+            const double sz = -dz - (double)(proj * dirB.z);
+            const double dr = sqrt(sx * sx + sy * sy + sz * sz);
+            const float cyl_rad = ob.size1;
+            const double dep = (double)rA - (double)ob.normal_sign * ((double)cyl_rad - dr);
+            depth = (float)dep;
+            if (dr >= 1e-12) {
+                const double k = (double)ob.normal_sign / dr;
+                nrm = f3((float)(k * sx), (float)(k * sy), (float)(k * sz));
+                const float s = (float)((double)rA - dep / 2.0);
+                cpA_w = relA - s * nrm;
+            } else {
+                nrm = dirB;
+                cpA_w = relA;
+            }
+        }
+        if (depth > 0.f) {
+            // CP - ownerB = (CP - ownerA) + (ownerA - ownerB)
+            const float3 cpB_w = f3((float)((double)cpA_w.x + (double)(ax - bx) * P.l),
+                                    (float)((double)cpA_w.y + (double)(ay - by) * P.l),
+                                    (float)((double)cpA_w.z + (double)(az - bz) * P.l));
+            const float3 cA = rotate_inv(cpA_w, A.q);
+            const float3 cB = rotate_inv(cpB_w, B.q);
+            const MatPair mp = P.matpair[ci.w & 0xffffu];
+            float3 force, troll;
+            contact_model<MODEL>(mp, P.h, depth, nrm, cA, cB, A, B, rA, 1e15f, hist, force, troll);
+            scatter_wrench(P.wrench, oA, oB, force, troll, cA, cB, A.q, B.q);
+            if (MODEL == 0) {
+                P.sa.hist[c] = hist;
+                if (!alive) P.sa.cinfo[c].w = ci.w | 0x80000000u;
+            }
+            if (RECORD) P.sa.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+        } else {
+            if (MODEL == 0 && alive) {
+                P.sa.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P.sa.cinfo[c].w = ci.w & 0x7fffffffu;
+            }
+            if (RECORD) P.sa.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// integrateOwners (DEMIntegrationKernels.cu:100-264). One thread per owner, 64-byte state in / out.
+__global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= P.nOwners) return;
+    OwnerPos pos;
+    End e;
+    load_owner(P.state, o, pos, e);
+    const float inertiaBits = P.state[o].omg.w;
+    const float4 mp = __ldg(&P.massprop[__float_as_uint(inertiaBits)]);
+    const Wrench wr = P.wrench[o];
+    const float h = P.h;
+
+    bool LinVelP[3] = {false, false, false}, RotVelP[3] = {false, false, false}, LinP[3] = {false, false, false};
+    bool RotP = false;
+    double X[3];
+    pos_decode(pos, P, X[0], X[1], X[2]);
+    X[0] += (double)P.LBF[0];
+    X[1] += (double)P.LBF[1];
+    X[2] += (double)P.LBF[2];
+    float v[3] = {e.v.x, e.v.y, e.v.z}, w[3] = {e.w.x, e.w.y, e.w.z};
+    float oldv[3] = {v[0], v[1], v[2]}, oldw[3] = {w[0], w[1], w[2]};
+    float extra_acc[3] = {0.f, 0.f, 0.f}, extra_ang[3] = {0.f, 0.f, 0.f};
+    const Prescr* pr = P.presc + pos.family;
+    if (pr->used) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (pr->hasLinVel[k]) v[k] = pr->linVel[k];
+            if (pr->hasRotVel[k]) w[k] = pr->rotVel[k];
+            LinVelP[k] = pr->linVelPrescribed[k];
+            RotVelP[k] = pr->rotVelPrescribed[k];
+            if (pr->hasLinPos[k]) X[k] = pr->linPos[k];
+            LinP[k] = pr->linPosPrescribed[k];
+            if (pr->hasAcc[k]) extra_acc[k] = pr->acc[k];
+            if (pr->hasAngAcc[k]) extra_ang[k] = pr->angAcc[k];
+        }
+        RotP = pr->rotPosPrescribed;
+    }
+    // a = F/m, alpha = T/I (the reference accumulates F_i/m per contact; same sum up to rounding)
+    const float acc[3] = {wr.f.x / mp.x, wr.f.y / mp.x, wr.f.z / mp.x};
+    const float ang[3] = {wr.t.x / mp.y, wr.t.y / mp.z, wr.t.z / mp.w};
+    float vup[3] = {0.f, 0.f, 0.f}, wup[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (!LinVelP[k]) {
+            vup[k] = (acc[k] + extra_acc[k] + P.G[k]) * h;
+            v[k] += vup[k];
+        } else {
+            oldv[k] = v[k];
+        }
+        if (!RotVelP[k]) {
+            wup[k] = (ang[k] + extra_ang[k]) * h;
+            w[k] += wup[k];
+        } else {
+            oldw[k] = w[k];
+        }
+    }
+    float vp[3], wp[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (P.integrator == DEM_EXTENDED_TAYLOR) {
+            vp[k] = oldv[k] + vup[k] * 0.5f;
+            wp[k] = oldw[k] + wup[k] * 0.5f;
+        } else if (P.integrator == DEM_CENTERED_DIFFERENCE) {
+            vp[k] = oldv[k] + vup[k];
+            wp[k] = oldw[k] + wup[k];
+        } else {
+            vp[k] = oldv[k];
+            wp[k] = oldw[k];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (!LinP[k]) X[k] += (double)vp[k] * (double)h;
+        X[k] -= (double)P.LBF[k];
+    }
+    pos_encode(pos, P, X[0], X[1], X[2]);
+    float4 q = e.q;
+    if (!RotP) {
+        const float hh = P.half_h;
+        const float b2 = hh * wp[0], c2 = hh * wp[1], d2 = hh * wp[2];
+        const float a1 = q.x, b1 = q.y, c1 = q.z, d1 = q.w;
+        const float Aq = a1 - b1 * b2 - c1 * c2 - d1 * d2;
+        const float Bq = a1 * b2 + b1 + c1 * d2 - d1 * c2;
+        const float Cq = a1 * c2 - b1 * d2 + c1 + d1 * b2;
+        const float Dq = a1 * d2 + b1 * c2 - c1 * b2 + d1;
+        const float len = sqrtf(Bq * Bq + Cq * Cq + Dq * Dq + Aq * Aq);
+        q = make_float4(Aq / len, Bq / len, Cq / len, Dq / len);
+    }
+    OwnerState out;
+    out.pos = pos;
+    out.quat = q;
+    out.vel = make_float4(v[0], v[1], v[2], e.mass);
+    out.omg = make_float4(w[0], w[1], w[2], inertiaBits);
+    int4* dst = reinterpret_cast<int4*>(P.state + o);
+    const int4* src = reinterpret_cast<const int4*>(&out);
+    dst[0] = src[0];
+    dst[1] = src[1];
+    dst[2] = src[2];
+    dst[3] = src[3];
+    // per-owner acceleration read-out (ContactAcc / ContactAngAccLocal trackers), only when requested
+    if (P.acc_out) {
+        P.acc_out[o].f = make_float4(acc[0], acc[1], acc[2], 0.f);
+        P.acc_out[o].t = make_float4(ang[0], ang[1], ang[2], 0.f);
+    }
+    // consume the wrench: the accumulator is zero again for the next step's reductions (prepareAccArrays,
+    // DEMPrepForceKernels.cu:14-37, fused here)
+    int4* wz = reinterpret_cast<int4*>(P.wrench + o);
+    wz[0] = make_int4(0, 0, 0, 0);
+    wz[1] = make_int4(0, 0, 0, 0);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void launch_force(const DevParams& P, int model, bool record, int grid, cudaStream_t s, bool have_sa) {
+    const int block = 256;
+#define LAUNCH(K)                                   \
+    K<<<grid, block, 0, s>>>(P)
+    if (model == DEM_HERTZIAN) {
+        if (record) { LAUNCH((k_force_ss<0, true>)); } else { LAUNCH((k_force_ss<0, false>)); }
+        if (have_sa) {
+            if (record) { LAUNCH((k_force_sa<0, true>)); } else { LAUNCH((k_force_sa<0, false>)); }
+        }
+    } else {
+        if (record) { LAUNCH((k_force_ss<1, true>)); } else { LAUNCH((k_force_ss<1, false>)); }
+        if (have_sa) {
+            if (record) { LAUNCH((k_force_sa<1, true>)); } else { LAUNCH((k_force_sa<1, false>)); }
+        }
+    }
+#undef LAUNCH
+}
+
+void launch_integrate(const DevParams& P, cudaStream_t s) {
+    const int block = 256;
+    const int grid = (int)((P.nOwners + block - 1) / block);
+    if (grid > 0) k_integrate<<<grid, block, 0, s>>>(P);
+}
+
+}  // namespace demb

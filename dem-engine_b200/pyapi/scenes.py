@@ -1,0 +1,355 @@
+"""Synthetic DEM scenes and the host-side flattening that DEMSolver::Initialize performs.
+
+`Scene` is the user-level description (materials, clump templates, clumps, analytical boundaries, solver settings)
+mirroring the calls a reference demo script makes (LoadMaterial / LoadClumpType / AddClumps / InstructBoxDomain* ...).
+`flatten(scene)` produces the reference's flattened SoA arrays (owners ordered clumps, analytical objects, meshes;
+src/DEM/dT.cpp:638-1024 populateEntityArrays of the reference) as a `FlatWorld`, which both the CUDA engine
+(pyapi.demb200.Engine.load_flat) and the CPU oracle (oracle.pyoracle.World, tests only) consume.
+
+World sizing uses the product's own host routines (dem_host_box_domain / dem_host_figure_out_nv /
+dem_host_encode_positions of libdemcore.so).
+"""
+import ctypes as C
+import math
+from types import SimpleNamespace
+
+import numpy as np
+
+from . import demb200 as D
+
+RESERVED_FAMILY = 255
+ANAL_PLANE, ANAL_CYL_INF = 0, 2
+
+# data/clumps/3_clump.csv of the reference (x,y,z,r) -- three overlapping spheres
+CLUMP3 = np.array([[0.5, 0.341729, 0.0, 0.8], [0.0, -0.658271, 0.0, 0.8], [-0.5, 0.341729, 0.0, 0.8]], "f4")
+CLUMP3_VOLUME = 5.5886717
+CLUMP3_MOI = (2.928, 2.6029, 3.9908)  # as DEMdemo_Mixer.cpp:68-72 uses them
+
+
+class Scene:
+    def __init__(self):
+        self.materials = []          # dicts E, nu, CoR, mu, Crr
+        self.material_pairs = {}     # (prop, i, j) -> value
+        self.templates = []          # dicts mass, moi(3), radii, relpos(n,3), mats(n)
+        self.clump_type = np.zeros(0, "i4")
+        self.clump_xyz = np.zeros((0, 3), "f4")
+        self.clump_vel = np.zeros((0, 3), "f4")
+        self.clump_omg = np.zeros((0, 3), "f4")
+        self.clump_quat = np.zeros((0, 4), "f4")   # w,x,y,z
+        self.clump_family = np.zeros(0, "u1")
+        self.ext_objs = []           # dicts family, mass, moi, pos, quat(wxyz), comps=[dict(type,pos,dir,size1,normal,mat)]
+        self.box = (1.0, 1.0, 1.0)
+        self.bounding = "none"       # none | all | top_open | only_bottom | only_sides
+        self.bounding_mat = 0
+        self.h = 1e-5
+        self.G = (0.0, 0.0, -9.81)
+        self.force_model = D.HERTZIAN
+        self.integrator = D.EXTENDED_TAYLOR
+        self.cd_update_freq = 20
+        self.beta = -1.0             # <0: velocity based margin
+        self.approxMaxVel = 1e15
+        self.expSafetyMulti = 1.0
+        self.expSafetyAdder = 3.0    # m_expand_base_vel default, API.h:1484
+        self.errOutVel = 1e3
+        self.record_contact_forces = 0
+        self.fixed_families = [RESERVED_FAMILY]
+        self.disabled_pairs = []
+        self.prescribed = {}         # family -> dict(linvel=(..), angvel=(..), dictate=True)
+
+    # -- LoadMaterial / LoadClumpType / LoadSphereType -------------------------------------------------------------
+    def load_material(self, **props):
+        self.materials.append(dict(props))
+        return len(self.materials) - 1
+
+    def load_clump_type(self, mass, moi, radii, relpos, mat):
+        radii = np.asarray(radii, "f4").reshape(-1)
+        relpos = np.asarray(relpos, "f4").reshape(-1, 3)
+        mats = np.full(len(radii), mat, "u2") if np.isscalar(mat) else np.asarray(mat, "u2")
+        self.templates.append(dict(mass=np.float32(mass), moi=np.asarray(moi, "f4"), radii=radii, relpos=relpos, mats=mats))
+        return len(self.templates) - 1
+
+    def load_sphere_type(self, mass, radius, mat):
+        moi = 2.0 / 5.0 * mass * radius * radius  # LoadSphereType, API.h:386
+        return self.load_clump_type(mass, (moi, moi, moi), [radius], [[0, 0, 0]], mat)
+
+    def add_clumps(self, types, xyz, vel=None, omg=None, quat=None, family=0):
+        xyz = np.asarray(xyz, "f4").reshape(-1, 3)
+        n = len(xyz)
+        types = np.full(n, types, "i4") if np.isscalar(types) else np.asarray(types, "i4")
+        self.clump_type = np.concatenate([self.clump_type, types])
+        self.clump_xyz = np.concatenate([self.clump_xyz, xyz])
+        self.clump_vel = np.concatenate([self.clump_vel, np.zeros((n, 3), "f4") if vel is None else np.broadcast_to(np.asarray(vel, "f4"), (n, 3))])
+        self.clump_omg = np.concatenate([self.clump_omg, np.zeros((n, 3), "f4") if omg is None else np.broadcast_to(np.asarray(omg, "f4"), (n, 3))])
+        q = np.tile(np.array([1, 0, 0, 0], "f4"), (n, 1)) if quat is None else np.asarray(quat, "f4").reshape(n, 4)
+        self.clump_quat = np.concatenate([self.clump_quat, q])
+        fam = np.full(n, family, "u1") if np.isscalar(family) else np.asarray(family, "u1")
+        self.clump_family = np.concatenate([self.clump_family, fam])
+
+    def add_plane(self, pos, normal, mat, family=RESERVED_FAMILY):
+        nrm = np.asarray(normal, "f4")
+        nrm = nrm / np.float32(math.sqrt(float(np.dot(nrm, nrm))))
+        self.ext_objs.append(dict(family=family, mass=1e6, moi=(1e6, 1e6, 1e6), pos=(0, 0, 0), quat=(1, 0, 0, 0),
+                                  comps=[dict(type=ANAL_PLANE, pos=pos, dir=nrm, size1=0.0, normal=0.0, mat=mat)]))
+        return len(self.ext_objs) - 1
+
+    def add_cylinder(self, pos, axis, rad, mat, normal=0.0, family=RESERVED_FAMILY):
+        ax = np.asarray(axis, "f4")
+        ax = ax / np.float32(math.sqrt(float(np.dot(ax, ax))))
+        self.ext_objs.append(dict(family=family, mass=1e6, moi=(1e6, 1e6, 1e6), pos=(0, 0, 0), quat=(1, 0, 0, 0),
+                                  comps=[dict(type=ANAL_CYL_INF, pos=pos, dir=ax, size1=rad, normal=normal, mat=mat)]))
+        return len(self.ext_objs) - 1
+
+
+def _bounding_box_planes(scene, umin, umax):
+    """addWorldBoundingBox, src/DEM/APIPrivate.cpp:955-1014 of the reference: ONE external object with up to 6 planes."""
+    mode = scene.bounding
+    if mode == "none":
+        return None
+    bottom = mode in ("only_bottom", "top_open", "all")
+    sides = mode in ("only_sides", "top_open", "all")
+    top = mode == "all"
+    c = ((umin + umax) / np.float32(2.0)).astype("f4")
+    comps = []
+    mk = lambda pos, n: dict(type=ANAL_PLANE, pos=np.asarray(pos, "f4"), dir=np.asarray(n, "f4"), size1=0.0, normal=0.0,
+                             mat=scene.bounding_mat)
+    if bottom:
+        comps.append(mk((c[0], c[1], umin[2]), (0, 0, 1)))
+    if sides:
+        comps.append(mk((umin[0], c[1], c[2]), (1, 0, 0)))
+        comps.append(mk((umax[0], c[1], c[2]), (-1, 0, 0)))
+        comps.append(mk((c[0], umin[1], c[2]), (0, 1, 0)))
+        comps.append(mk((c[0], umax[1], c[2]), (0, -1, 0)))
+    if top:
+        comps.append(mk((c[0], c[1], umax[2]), (0, 0, -1)))
+    return dict(family=RESERVED_FAMILY, mass=1e6, moi=(1e6, 1e6, 1e6), pos=(0, 0, 0), quat=(1, 0, 0, 0), comps=comps)
+
+
+def flatten(scene):
+    f = SimpleNamespace()
+    umin, umax, tmin, tmax = D.host_box_domain(*[float(v) for v in scene.box])
+    f.userBoxMin, f.userBoxMax = umin, umax
+    f.nvXp2, f.nvYp2, f.nvZp2, f.l, f.voxelSize = D.host_figure_out_nv(tmin, tmax)
+    f.LBF = tmin.copy()
+    f.G = np.asarray(scene.G, "f4")
+    f.h = np.float32(scene.h)
+    f.integrator, f.force_model, f.cd_update_freq = scene.integrator, scene.force_model, int(scene.cd_update_freq)
+    f.beta, f.approxMaxVel = np.float32(scene.beta), np.float32(scene.approxMaxVel)
+    f.expSafetyMulti, f.expSafetyAdder = np.float32(scene.expSafetyMulti), np.float32(scene.expSafetyAdder)
+    f.errOutVel, f.record_contact_forces = np.float32(scene.errOutVel), int(scene.record_contact_forces)
+
+    ext = list(scene.ext_objs)
+    bb = _bounding_box_planes(scene, umin, umax)
+    if bb is not None:
+        ext.append(bb)  # added at Initialize, i.e. after the user's own external objects
+
+    # ---- templates ----
+    comp_start, radii, rel = [], [], []
+    for t in scene.templates:
+        comp_start.append(len(radii))
+        radii.extend(t["radii"].tolist())
+        rel.extend(t["relpos"].tolist())
+    f.nComp = len(radii)
+    f.Radii = np.asarray(radii, "f4")
+    relarr = np.asarray(rel, "f4").reshape(-1, 3)
+    f.CDRelPosX, f.CDRelPosY, f.CDRelPosZ = (np.ascontiguousarray(relarr[:, k]) for k in range(3))
+    # mass properties: clump templates, then external objects (then meshes)
+    mass = [t["mass"] for t in scene.templates] + [e["mass"] for e in ext]
+    moi = [t["moi"] for t in scene.templates] + [e["moi"] for e in ext]
+    f.nMassProps = len(mass)
+    f.MassProperties = np.asarray(mass, "f4")
+    moi = np.asarray(moi, "f4").reshape(-1, 3)
+    f.moiX, f.moiY, f.moiZ = (np.ascontiguousarray(moi[:, k]) for k in range(3))
+
+    # ---- materials (equipMaterials, APIPrivate.cpp:1877-2026) ----
+    n = len(scene.materials)
+    f.nMat = n
+    f.E = np.array([m.get("E", 0.0) for m in scene.materials], "f4")
+    f.nu = np.array([m.get("nu", 0.0) for m in scene.materials], "f4")
+    for prop in ("CoR", "mu", "Crr"):
+        t = np.zeros((n, n), "f4")
+        for i, m in enumerate(scene.materials):
+            t[i, i] = np.float32(m.get(prop, 0.0))
+        for i in range(n):
+            for j in range(n):
+                if i != j:
+                    t[i, j] = np.float32((float(t[i, i]) + float(t[j, j])) / 2.0)
+        for (p, i, j), v in scene.material_pairs.items():
+            if p == prop:
+                t[i, j] = t[j, i] = np.float32(v)
+        setattr(f, prop, np.ascontiguousarray(t.reshape(-1)))
+
+    # ---- owners: clumps, then analytical objects ----
+    nC, nE = len(scene.clump_type), len(ext)
+    f.nOwners = nC + nE
+    f.nClumps = nC
+    xyz = np.concatenate([scene.clump_xyz, np.asarray([e["pos"] for e in ext], "f4").reshape(-1, 3)]).astype("f4")
+    p = D.DemSimParams()
+    p.nvXp2, p.nvYp2, p.nvZp2, p.l, p.voxelSize = f.nvXp2, f.nvYp2, f.nvZp2, f.l, f.voxelSize
+    for k in range(3):
+        p.LBF[k] = float(f.LBF[k])
+    f.voxelID, f.locX, f.locY, f.locZ = (np.zeros(max(f.nOwners, 1), dt) for dt in ("u8", "u2", "u2", "u2"))
+    xyzc = np.ascontiguousarray(xyz)
+    D.load_library().dem_host_encode_positions(C.byref(p), D._p(xyzc), C.c_uint64(f.nOwners), D._p(f.voxelID),
+                                               D._p(f.locX), D._p(f.locY), D._p(f.locZ))
+    quat = np.concatenate([scene.clump_quat, np.asarray([e["quat"] for e in ext], "f4").reshape(-1, 4)]).astype("f4")
+    f.oriQw, f.oriQx, f.oriQy, f.oriQz = (np.ascontiguousarray(quat[:, k]) if len(quat) else np.zeros(1, "f4") for k in range(4))
+    vel = np.concatenate([scene.clump_vel, np.zeros((nE, 3), "f4")]).astype("f4")
+    omg = np.concatenate([scene.clump_omg, np.zeros((nE, 3), "f4")]).astype("f4")
+    f.vX, f.vY, f.vZ = (np.ascontiguousarray(vel[:, k]) if len(vel) else np.zeros(1, "f4") for k in range(3))
+    f.omgBarX, f.omgBarY, f.omgBarZ = (np.ascontiguousarray(omg[:, k]) if len(omg) else np.zeros(1, "f4") for k in range(3))
+    f.familyID = np.concatenate([scene.clump_family, np.asarray([e["family"] for e in ext], "u1")]).astype("u1")
+    if len(f.familyID) == 0:
+        f.familyID = np.zeros(1, "u1")
+    nT = len(scene.templates)
+    f.inertiaPropOffsets = np.concatenate([scene.clump_type.astype("u2"), (nT + np.arange(nE)).astype("u2")]).astype("u2")
+    if len(f.inertiaPropOffsets) == 0:
+        f.inertiaPropOffsets = np.zeros(1, "u2")
+
+    # ---- spheres ----
+    ncomp_of = np.array([len(t["radii"]) for t in scene.templates], "i8")
+    counts = ncomp_of[scene.clump_type] if nC else np.zeros(0, "i8")
+    f.nSpheres = int(counts.sum())
+    f.ownerClumpBody = np.repeat(np.arange(nC, dtype="u4"), counts).astype("u4")
+    starts = np.asarray(comp_start, "i8")
+    first = np.cumsum(counts) - counts
+    within = np.arange(f.nSpheres, dtype="i8") - np.repeat(first, counts)
+    f.clumpComponentOffset = (np.repeat(starts[scene.clump_type], counts) + within).astype("u2") if nC else np.zeros(1, "u2")
+    allmats = np.concatenate([t["mats"] for t in scene.templates]).astype("u2") if nT else np.zeros(1, "u2")
+    f.sphereMaterialOffset = allmats[f.clumpComponentOffset].astype("u2") if nC else np.zeros(1, "u2")
+    if f.nSpheres == 0:
+        f.ownerClumpBody = np.zeros(1, "u4")
+
+    # ---- analytical components ----
+    comps = [(nC + i, c) for i, e in enumerate(ext) for c in e["comps"]]
+    f.nAnal = len(comps)
+    g = lambda fn, dt: np.asarray([fn(o, c) for o, c in comps], dt) if comps else np.zeros(1, dt)
+    f.objOwner = g(lambda o, c: o, "u4")
+    f.objType = g(lambda o, c: c["type"], "u1")
+    f.objMaterial = g(lambda o, c: c["mat"], "u2")
+    f.objNormal = g(lambda o, c: c["normal"], "f4")
+    f.objRelPosX, f.objRelPosY, f.objRelPosZ = (g(lambda o, c, k=k: c["pos"][k], "f4") for k in range(3))
+    f.objRotX, f.objRotY, f.objRotZ = (g(lambda o, c, k=k: c["dir"][k], "f4") for k in range(3))
+    f.objSize1 = g(lambda o, c: c["size1"], "f4")
+    f.objSize2 = np.zeros(max(f.nAnal, 1), "f4")
+    f.objSize3 = np.zeros(max(f.nAnal, 1), "f4")
+    f.objMass = g(lambda o, c: ext[o - nC]["mass"], "f4")
+
+    # ---- families ----
+    f.familyMasks = np.zeros(D.PRESC_DTYPE.itemsize and 32896, "u1")
+    for a, b in scene.disabled_pairs:
+        i, j = (a, b) if a <= b else (b, a)
+        f.familyMasks[(1 + j) * j // 2 + i] = 1
+    f.familyExtraMarginSize = np.zeros(256, "f4")
+    f.prescriptions = np.zeros(256, D.PRESC_DTYPE)
+    for fam in scene.fixed_families:
+        pr = f.prescriptions[fam]
+        pr["used"] = 1
+        for k in ("linVelPrescribed", "rotVelPrescribed", "linPosPrescribed", "hasLinVel", "hasRotVel"):
+            pr[k] = 1
+        pr["rotPosPrescribed"] = 1
+    for fam, d in scene.prescribed.items():
+        pr = f.prescriptions[fam]
+        pr["used"] = 1
+        dictate = 1 if d.get("dictate", True) else 0
+        for key, has, val, flag in (("linvel", "hasLinVel", "linVel", "linVelPrescribed"),
+                                    ("angvel", "hasRotVel", "rotVel", "rotVelPrescribed")):
+            if key in d:
+                for k in range(3):
+                    if d[key][k] is not None:
+                        pr[has][k] = 1
+                        pr[val][k] = d[key][k]
+                        pr[flag][k] = dictate
+    return f
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# samplers (HCPSampler / DEMBoxGridSampler of src/DEM/utils/Samplers.hpp, float arithmetic)
+def hcp_box(center, halfsize, sep):
+    f = np.float32
+    c, s = np.asarray(center, "f4"), np.asarray(halfsize, "f4")
+    bl = c - s
+    dx = f(sep)
+    dy = f(sep) * f(math.sqrt(3.0) / 2)
+    dz = f(sep) * f(math.sqrt(2.0 / 3.0))
+    nx, ny, nz = int(2 * s[0] / dx) + 1, int(2 * s[1] / dy) + 1, int(2 * s[2] / dz) + 1
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    offy = np.where(k % 2 == 0, f(0), dy / f(3)).astype("f4")
+    offx = np.where((j + k) % 2 == 0, f(0), dx / f(2)).astype("f4")
+    pts = np.stack([bl[0] + (offx + i.astype("f4") * dx), bl[1] + (offy + j.astype("f4") * dy),
+                    bl[2] + k.astype("f4") * dz], -1).astype("f4").reshape(-1, 3)
+    eps = 1e-6
+    ok = np.all(np.abs(pts - c) <= s + eps, axis=1)
+    return pts[ok]
+
+
+def grid_box(center, halfsize, sep):
+    c, s = np.asarray(center, "f4"), np.asarray(halfsize, "f4")
+    bl = c - s
+    sep = np.broadcast_to(np.asarray(sep, "f4"), (3,))
+    n = [int(2 * s[k] / sep[k]) + 1 for k in range(3)]
+    i, j, k = np.meshgrid(np.arange(n[0]), np.arange(n[1]), np.arange(n[2]), indexing="ij")
+    pts = np.stack([bl[0] + i.astype("f4") * sep[0], bl[1] + j.astype("f4") * sep[1], bl[2] + k.astype("f4") * sep[2]], -1)
+    return pts.astype("f4").reshape(-1, 3)
+
+
+def random_unit_quats(n, seed=4150):
+    rng = np.random.RandomState(seed)
+    q = rng.normal(size=(n, 4)).astype("f4")
+    q /= np.linalg.norm(q, axis=1, keepdims=True).astype("f4")
+    return q.astype("f4")
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# BASELINE.json configs
+def config1_spheres(n_side=22, h=2e-6, cd_update_freq=10, seed=0, jitter=0.0, box=0.2, drop_height=None):
+    """C1: ~10k monodisperse single-sphere grains (r = 1.25 mm, BallDrop materials) on a cubic lattice of spacing 2.01 r
+    dropped into a 0.2 x 0.2 m top-open box, frictionless Hertz."""
+    s = Scene()
+    r = 0.00125
+    mat = s.load_material(E=7e7, nu=0.24, CoR=0.9, mu=0.0, Crr=0.0)
+    mass = 2500.0 * 4.0 / 3.0 * math.pi * r ** 3
+    t = s.load_sphere_type(mass, r, mat)
+    s.box = (box, box, box)
+    s.bounding, s.bounding_mat = "top_open", mat
+    sep = 2.01 * r
+    half = (n_side - 1) * sep / 2.0
+    zc = -box / 2.0 + r * 1.05 + half if drop_height is None else drop_height
+    pts = grid_box((0, 0, zc), (half + 1e-7, half + 1e-7, half + 1e-7), sep)
+    if jitter > 0:
+        rng = np.random.RandomState(seed)
+        pts = pts + (rng.uniform(-1, 1, pts.shape) * jitter * r).astype("f4")
+    s.add_clumps(t, pts)
+    s.h, s.G = h, (0, 0, -9.81)
+    s.force_model = D.HERTZIAN_FRICTIONLESS
+    s.cd_update_freq = cd_update_freq
+    return s
+
+
+def config2_clumps(nx, ny, nz, scale=0.005, h=5e-6, cd_update_freq=20, seed=4150, mu=0.2, Crr=0.0,
+                   force_model=D.HERTZIAN, spacing=3.0, init_vel=None):
+    """C2: clumps of 3_clump.csv scaled to `scale` (mass / MOI as DEMdemo_Mixer.cpp:68-72), HCP-like lattice of spacing
+    3*scale with nx*ny*nz sites, random orientations, in a top-open box, Hertz-Mindlin with history."""
+    s = Scene()
+    mat = s.load_material(E=1e8, nu=0.3, CoR=0.6, mu=mu, Crr=Crr)
+    mass = 2.6e3 * CLUMP3_VOLUME * scale ** 3
+    moi = np.array(CLUMP3_MOI) * 2.6e3 * scale ** 5
+    t = s.load_clump_type(mass, moi, CLUMP3[:, 3] * scale, CLUMP3[:, :3] * scale, mat)
+    sep = spacing * scale
+    dx, dy, dz = sep, sep * math.sqrt(3.0) / 2, sep * math.sqrt(2.0 / 3.0)
+    wall_gap = 2.0 * scale
+    bx, by = nx * dx + 2 * wall_gap, ny * dy + 2 * wall_gap
+    bz = (nz * dz + 2 * wall_gap) * 1.25
+    s.box = (bx, by, bz)
+    s.bounding, s.bounding_mat = "top_open", mat
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    offy = np.where(k % 2 == 0, 0.0, dy / 3)
+    offx = np.where((j + k) % 2 == 0, 0.0, dx / 2)
+    x = -bx / 2 + wall_gap + 0.25 * dx + offx + i * dx
+    y = -by / 2 + wall_gap + 0.25 * dy + offy + j * dy
+    z = -bz / 2 + wall_gap + k * dz
+    pts = np.stack([x, y, z], -1).reshape(-1, 3).astype("f4")
+    s.add_clumps(t, pts, quat=random_unit_quats(len(pts), seed), vel=init_vel)
+    s.h, s.G = h, (0, 0, -9.81)
+    s.force_model = force_model
+    s.cd_update_freq = cd_update_freq
+    return s

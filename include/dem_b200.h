@@ -1,0 +1,212 @@
+/*
+ * dem_b200.h -- C ABI of the B200-native DEM stepping core (libdemcore.so).
+ *
+ * This is the drop-in boundary for the hot path of projectchrono/DEM-Engine
+ * (kinematic-thread contact detection -> dynamic-thread contact force -> owner integration).
+ * In the reference that path is not behind a plugin ABI: it lives behind the C++ class
+ * deme::DEMSolver (src/DEM/API.h:50) whose Initialize()/DoDynamics() drive two worker
+ * threads (src/DEM/dT.cpp:2324, src/DEM/kT.cpp:218).  Each entry point below names the
+ * reference interface it replaces (file:line, relative to the reference tree).
+ *
+ * Conventions: every function returns 0 on success and a negative DEM_ERR_* code on failure
+ * (no exceptions cross the boundary); dem_last_error() returns a human readable message.
+ * All pointers are HOST memory owned by the caller; arrays follow the reference's SoA
+ * contract (src/DEM/Defines.h:269-373).  One context is driven by one CPU thread at a time.
+ * No torch / C++ types appear in any signature.
+ */
+#ifndef DEM_B200_H
+#define DEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DEM_B200_ABI_VERSION 1
+
+enum {
+    DEM_OK = 0,
+    DEM_ERR_INVALID = -1,  /* bad argument / call order */
+    DEM_ERR_CUDA = -2,     /* CUDA runtime failure (message has file:line) */
+    DEM_ERR_CAPACITY = -3, /* a device array overflowed and could not be grown */
+    DEM_ERR_VELOCITY = -4, /* max velocity exceeded errOutVel / non-finite state (kT.cpp:136-149) */
+    DEM_ERR_NO_GPU = -5    /* no CUDA device: there is NO CPU fallback */
+};
+
+/* contact type codes, src/DEM/Defines.h:74-82 */
+enum { DEM_CNT_NONE = 0, DEM_CNT_SPHERE_SPHERE = 1, DEM_CNT_SPHERE_MESH = 2, DEM_CNT_SPHERE_PLANE = 11,
+       DEM_CNT_SPHERE_PLATE = 12, DEM_CNT_SPHERE_CYL = 13 };
+/* analytical component types, src/DEM/Defines.h:68-72 */
+enum { DEM_ANAL_PLANE = 0, DEM_ANAL_PLATE = 1, DEM_ANAL_CYL_INF = 2 };
+/* TIME_INTEGRATOR, src/DEM/Defines.h:146 */
+enum { DEM_FORWARD_EULER = 0, DEM_CENTERED_DIFFERENCE = 1, DEM_EXTENDED_TAYLOR = 2 };
+/* FORCE_MODEL, src/DEM/Defines.h:150 */
+enum { DEM_HERTZIAN = 0, DEM_HERTZIAN_FRICTIONLESS = 1 };
+
+#define DEM_NUM_FAMILIES 256
+#define DEM_NUM_FAMILY_MASKS 32896 /* upper-triangular 256x256, src/kernel/DEMHelperKernels.cuh:57-62 */
+
+typedef struct DemCtx DemCtx;
+
+/* Replaces deme::DEMSimParams (src/DEM/Defines.h:194-265) + the SolverFlags that steer the hot path
+ * (src/DEM/Structs.h:482-531). */
+typedef struct DemSimParams {
+    uint32_t nvXp2, nvYp2, nvZp2; /* voxel-count bits per axis (figureOutNV, APIPrivate.cpp:373-487) */
+    uint32_t integrator;          /* DEM_FORWARD_EULER / CENTERED_DIFFERENCE / EXTENDED_TAYLOR */
+    uint32_t force_model;         /* DEM_HERTZIAN / DEM_HERTZIAN_FRICTIONLESS */
+    uint32_t cd_update_freq;      /* steps between contact-list rebuilds (SetCDUpdateFreq, API.h:107-113); >=1 */
+    double l;                     /* smallest length unit */
+    double voxelSize;             /* 2^16 * l */
+    float LBF[3];                 /* left-bottom-front corner of the world */
+    float G[3];                   /* gravitational acceleration */
+    float userBoxMin[3];
+    float userBoxMax[3];
+    float h;                      /* step size (float-rounded, Defines.h:240) */
+    float beta;                   /* >=0: fixed expand factor (SetExpandFactor(beta,true)); <0: velocity based margin */
+    float approxMaxVel;           /* SetMaxVelocity */
+    float expSafetyMulti;         /* SetExpandSafetyMultiplier */
+    float expSafetyAdder;         /* SetExpandSafetyAdder */
+    float errOutVel;              /* SetErrorOutVelocity */
+    uint32_t record_contact_forces; /* 0 == SetNoForceRecord() */
+    uint32_t pad_;
+} DemSimParams;
+
+/* Per-family motion prescription with numeric constants (SetFamilyFixed / SetFamilyPrescribedLinVel / AngVel /
+ * Position / AddFamilyPrescribedAcc with constant strings; what equipFamilyPrescribedMotions,
+ * APIPrivate.cpp:1601-1708, compiles into the integration kernel). */
+typedef struct DemPrescription {
+    uint8_t used;
+    uint8_t linVelPrescribed[3];
+    uint8_t rotVelPrescribed[3];
+    uint8_t linPosPrescribed[3];
+    uint8_t rotPosPrescribed;
+    uint8_t hasLinVel[3];
+    uint8_t hasRotVel[3];
+    uint8_t hasLinPos[3];
+    uint8_t hasAcc[3];
+    uint8_t hasAngAcc[3];
+    uint8_t pad_[2];
+    float linVel[3];
+    float rotVel[3];
+    float linPos[3];
+    float acc[3];
+    float angAcc[3];
+} DemPrescription;
+
+/* Replaces the timers/collaboration stats of ShowTimingStats / ShowThreadCollaborationStats
+ * (APIPublic.cpp:2215, :2481-2505) and GetNumContacts / GetAvgSphContacts. */
+typedef struct DemStats {
+    uint64_t n_steps;          /* steps taken since creation */
+    uint64_t n_rebuilds;       /* contact-list rebuilds */
+    uint64_t n_contacts_ss;    /* sphere-sphere candidates in the current list */
+    uint64_t n_contacts_sa;    /* sphere-analytical */
+    uint64_t n_contacts_st;    /* sphere-triangle */
+    uint64_t contact_capacity; /* per-list device capacity */
+    uint64_t kernel_launches;  /* kernels (own) launched or replayed from graphs since creation */
+    uint64_t device_bytes;     /* device memory held */
+    double sim_time;           /* GetSimTime */
+    float max_margin;          /* largest contact margin of the last rebuild */
+    float cell_size;           /* broad-phase cell edge of the last rebuild */
+    uint32_t n_cells[3];
+    uint32_t overflow;         /* !=0: a list overflowed (capacity was grown and the rebuild redone) */
+} DemStats;
+
+/* ---- host-side set-up arithmetic ---------------------------------------------------------------------- */
+/* DEMSolver::figureOutNV (APIPrivate.cpp:373-487): split 64 voxel bits, choose l. box_* is the target (enlarged) box. */
+int dem_host_figure_out_nv(const float box_min[3], const float box_max[3], uint32_t nv_p2[3], double* l,
+                           double* voxel_size);
+/* InstructBoxDomainDimension(x,y,z) (APIPublic.cpp:845-872). Outputs user box and 20%-enlarged target box. */
+int dem_host_box_domain(float x, float y, float z, float user_min[3], float user_max[3], float target_min[3],
+                        float target_max[3]);
+/* positionToVoxelID on the host (DEMHelperKernels.cuh:137-159), as dT::populateEntityArrays uses it (dT.cpp:638-1024). */
+int dem_host_encode_positions(const DemSimParams* p, const float* xyz_world, uint64_t n, uint64_t* voxelID,
+                              uint16_t* locX, uint16_t* locY, uint16_t* locZ);
+
+/* ---- life cycle: DEMSolver::DEMSolver / ~DEMSolver (APIPublic.cpp:23-92) ------------------------------- */
+int dem_ctx_create(DemCtx** out, int device);
+int dem_ctx_destroy(DemCtx* ctx);
+const char* dem_last_error(const DemCtx* ctx);
+int dem_abi_version(void);
+/* run on a caller-provided cudaStream_t (e.g. a torch stream) instead of the context's own stream */
+int dem_set_stream(DemCtx* ctx, void* cuda_stream);
+
+/* ---- Initialize(): flattened user input (APIPublic.cpp:2161-2213; dT::populateEntityArrays dT.cpp:638-1024) ---- */
+int dem_set_params(DemCtx* ctx, const DemSimParams* p); /* setSimParams, APIPrivate.cpp:1121 */
+/* clump component table + mass-property table (equipClumpTemplates / equipMassMoiVolume, APIPrivate.cpp:2028,1795) */
+int dem_upload_templates(DemCtx* ctx, uint32_t nComp, const float* radii, const float* relX, const float* relY,
+                         const float* relZ, uint32_t nMassProps, const float* mass, const float* moiX,
+                         const float* moiY, const float* moiZ);
+/* equipMaterials (APIPrivate.cpp:1877-2026): E,nu per material; CoR,mu,Crr nMat x nMat row-major */
+int dem_upload_materials(DemCtx* ctx, uint32_t nMat, const float* E, const float* nu, const float* CoR,
+                         const float* mu, const float* Crr);
+/* equipAnalGeoTemplates (APIPrivate.cpp:1724-1793) */
+int dem_upload_analytical(DemCtx* ctx, uint32_t nAnal, const uint32_t* objOwner, const uint8_t* objType,
+                          const uint16_t* objMaterial, const float* objNormal, const float* relPosX,
+                          const float* relPosY, const float* relPosZ, const float* rotX, const float* rotY,
+                          const float* rotZ, const float* size1, const float* size2, const float* size3,
+                          const float* objMass);
+/* family mask matrix (APIPrivate.cpp:815), extra margins, prescriptions (256 entries) */
+int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMargin, const DemPrescription* presc);
+/* owners: clumps, then analytical objects, then meshes (dT.cpp:638-1024) */
+int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, const uint16_t* locX,
+                      const uint16_t* locY, const uint16_t* locZ, const float* oriQw, const float* oriQx,
+                      const float* oriQy, const float* oriQz, const float* vX, const float* vY, const float* vZ,
+                      const float* omgBarX, const float* omgBarY, const float* omgBarZ, const uint8_t* familyID,
+                      const uint16_t* inertiaPropOffsets);
+int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClumpBody,
+                       const uint16_t* clumpComponentOffset, const uint16_t* sphereMaterialOffset);
+/* triangles of mesh owners (preprocessTriangleObjs; nodes in owner frame, xyz interleaved) */
+int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, const float* node1,
+                         const float* node2, const float* node3, const uint16_t* triMaterialOffset);
+/* allocateGPUArrays + initGPUArrays (dT.cpp:409, kT.cpp:579). contact_capacity==0 -> automatic */
+int dem_initialize(DemCtx* ctx, uint64_t contact_capacity);
+/* restart: SetExistingContacts / SetExistingContactWildcards (Structs.h:857-882, dT.cpp:849-881) */
+int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_t* idB, const uint8_t* type,
+                     const float* wildcards4 /* n x 4 row-major: delta_tan_xyz, delta_time */);
+
+/* ---- the hot loop ------------------------------------------------------------------------------------- */
+/* DoDynamics(t) / DoDynamicsThenSync(t) (APIPublic.cpp:2446-2479): takes the same number of steps as the reference's
+ * loop "for (double cycle = 0; cycle < t; cycle += (double)h)" (dT.cpp:2401) and blocks until they are done.
+ * t <= 0 only (re)builds the contact list (the dry run of DoDynamicsThenSync(0), dT.cpp:2393-2398). */
+int dem_do_dynamics(DemCtx* ctx, double t);
+/* DoStepDynamics() x n (API.h:1252-1263). Blocking. */
+int dem_step(DemCtx* ctx, uint64_t n_steps);
+/* enqueue n steps on the stream without waiting (dem_sync() later); lets callers time with their own events */
+int dem_step_async(DemCtx* ctx, uint64_t n_steps);
+int dem_sync(DemCtx* ctx);
+/* force a contact-list rebuild now (kT contactDetection(), DEMCubContactDetection.cu:38-1123) */
+int dem_rebuild_contacts(DemCtx* ctx);
+/* UpdateStepSize (API.h) */
+int dem_update_step_size(DemCtx* ctx, float h);
+
+/* ---- state access: trackers / writers read through these (dT.cpp:3062-3130) ---------------------------- */
+/* any output pointer may be NULL */
+int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* voxelID, uint16_t* locX,
+                             uint16_t* locY, uint16_t* locZ, float* oriQ_wxyz, float* vel_xyz, float* omg_xyz,
+                             float* acc_xyz, float* angacc_xyz, uint8_t* family);
+/* decoded world positions as the reference reports them (float, LBF added; dT.cpp:3062-3076) or in double */
+int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz_f32, double* xyz_f64);
+int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float* pos_xyz_world,
+                           const float* oriQ_wxyz, const float* vel_xyz, const float* omg_xyz,
+                           const uint8_t* family);
+/* contact list in the reference's order (type, idA, idB). Pass NULL arrays to only query the count. */
+int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n, uint32_t* idA, uint32_t* idB, uint8_t* type,
+                          float* wildcards4, float* force_xyz);
+int dem_get_stats(DemCtx* ctx, DemStats* out);
+
+/* reductions over clump owners (DEMInspector built-ins, AuxClasses.cpp:88-164) */
+enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_REDUCE_KINETIC_ENERGY = 3,
+       DEM_REDUCE_TOTAL_MASS = 4 };
+int dem_reduce(DemCtx* ctx, int kind, double* out);
+
+/* ---- measurement hooks (bench.py / ncu) ---------------------------------------------------------------- */
+/* Run n steps and return the mean device time per kernel class in microseconds, measured with CUDA events on the
+ * launching stream: [0]=contact force (all lists) [1]=integration [2]=rebuild (amortised per step) [3]=whole step */
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DEM_B200_H */

@@ -1,0 +1,187 @@
+"""Pins the CPU oracle (oracle/dem_oracle.c) against the reference's own kernel text compiled for the host
+(oracle/_ref/libdemref.so) -- bit for bit -- and against the committed golden vectors generated from it.
+
+There are no golden vectors or known-answer tests in the reference tree; what pins the oracle is
+(i) the reference's kernels executed here through the host shim and (ii) tests/golden/*.npz dumped from that.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle
+from pyapi import scenes
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+needs_ref = pytest.mark.skipif(pyoracle.ref() is None, reason="oracle/_ref/libdemref.so not built (no reference tree)")
+
+STATE = ["voxelID", "locX", "locY", "locZ", "oriQw", "oriQx", "oriQy", "oriQz", "vX", "vY", "vZ", "omgBarX", "omgBarY",
+         "omgBarZ", "aX", "aY", "aZ", "alphaX", "alphaY", "alphaZ"]
+
+
+def _scene(kind):
+    if kind == "clumps_full":
+        sc = scenes.config2_clumps(5, 5, 4, cd_update_freq=5, spacing=2.7, init_vel=(0.2, 0.1, -2.0))
+    elif kind == "clumps_roll":
+        sc = scenes.config2_clumps(4, 4, 3, cd_update_freq=5, spacing=2.7, Crr=0.05, init_vel=(0.3, 0.0, -2.0))
+    elif kind == "spheres_frictionless":
+        sc = scenes.config1_spheres(n_side=7, cd_update_freq=5, jitter=0.02)
+        sc.clump_vel[:] = (0.0, 0.0, -2.0)
+    elif kind == "cylinder":
+        sc = scenes.config2_clumps(4, 4, 3, cd_update_freq=5, spacing=2.7, init_vel=(1.5, 0.6, -2.0))
+        sc.bounding = "only_bottom"
+        sc.add_cylinder((0, 0, 0), (0, 0, 1), 0.04, 0, normal=0.0)
+    else:
+        raise KeyError(kind)
+    return sc
+
+
+def _assert_same_state(a, b):
+    for name in STATE:
+        x, y = getattr(a, name), getattr(b, name)
+        assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), name
+    assert a.nContacts == b.nContacts
+    n = a.nContacts
+    for k in range(4):
+        assert np.array_equal(a.contactWildcards[k][:n].view("u4"), b.contactWildcards[k][:n].view("u4")), "wildcard %d" % k
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder"])
+def test_step_bit_exact_vs_reference_kernels(built, kind):
+    f = scenes.flatten(_scene(kind))
+    a = pyoracle.world_from_flat(f)
+    b = a.copy()
+    nsteps = 4000
+    a.step(nsteps, cd_every=f.cd_update_freq)
+    b.step(nsteps, cd_every=f.cd_update_freq, use_ref=True)
+    assert a.nContacts > 0
+    # something physical must have happened: contacts with non-zero history or forces
+    assert np.abs(a.contactForces[: 3 * a.nContacts]).max() > 0
+    _assert_same_state(a, b)
+    n = a.nContacts
+    for name in ("contactForces", "contactTorque_convToForce", "contactPointGeometryA", "contactPointGeometryB"):
+        assert np.array_equal(getattr(a, name)[: 3 * n].view("u4"), getattr(b, name)[: 3 * n].view("u4")), name
+
+
+@needs_ref
+def test_codec_bit_exact(built):
+    import ctypes as C
+    f = scenes.flatten(_scene("clumps_full"))
+    w = pyoracle.world_from_flat(f)
+    rng = np.random.RandomState(1)
+    s = w.struct()
+    for _ in range(2000):
+        xyz = (rng.uniform(0.0, 0.1, 3)).astype("f8")
+        v1, v2 = C.c_uint64(), C.c_uint64()
+        l1, l2 = (C.c_uint16 * 3)(), (C.c_uint16 * 3)()
+        pyoracle.lib().orc_voxel_encode(C.byref(s), xyz.ctypes.data_as(C.c_void_p), C.byref(v1), l1)
+        pyoracle.ref().ref_voxel_encode(C.byref(s), xyz.ctypes.data_as(C.c_void_p), C.byref(v2), l2)
+        assert v1.value == v2.value and list(l1) == list(l2)
+    d1, d2 = np.zeros(3), np.zeros(3)
+    for o in range(0, w.nOwners, 7):
+        pyoracle.lib().orc_voxel_decode(C.byref(s), C.c_uint32(o), d1.ctypes.data_as(C.c_void_p))
+        pyoracle.ref().ref_voxel_decode(C.byref(s), C.c_uint32(o), d2.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(d1, d2)
+
+
+@needs_ref
+def test_margin_bit_exact(built):
+    f = scenes.flatten(_scene("clumps_full"))
+    a = pyoracle.world_from_flat(f)
+    rng = np.random.RandomState(2)
+    a.vX[:] = rng.normal(size=len(a.vX)).astype("f4")
+    a.vZ[:] = rng.normal(size=len(a.vZ)).astype("f4") * 3
+    b = a.copy()
+    a.compute_margins(20)
+    b.compute_margins(20, use_ref=True)
+    assert np.array_equal(a.marginSize.view("u4"), b.marginSize.view("u4"))
+    a.beta = b.beta = np.float32(1e-4)
+    a.compute_margins(20)
+    b.compute_margins(20, use_ref=True)
+    assert np.array_equal(a.marginSize.view("u4"), b.marginSize.view("u4"))
+
+
+@needs_ref
+def test_sphere_analytical_contacts_match_reference_bin_kernels(built):
+    """The oracle's sphere--analytical detection equals what getNumberOfBinsEachSphereTouches /
+    populateBinSphereTouchingPairs (DEMBinSphereKernels.cu) emit."""
+    import ctypes as C
+    f = scenes.flatten(_scene("cylinder"))
+    w = pyoracle.world_from_flat(f)
+    w.step(3000, cd_every=5)
+    w.compute_margins(5)
+    w.detect_contacts()
+    idA, idB, ct, _ = w.contacts()
+    sa = ct > 10
+    mine = sorted(zip(idA[sa].tolist(), idB[sa].tolist(), ct[sa].tolist()))
+    cap = 10 * w.nSpheres + 16
+    oS, oO, oT = np.zeros(cap, "u4"), np.zeros(cap, "u4"), np.zeros(cap, "u1")
+    s = w.struct()
+    n = pyoracle.ref().ref_sphere_anal_contacts(C.byref(s), C.c_double(0.02), C.c_uint32(64), C.c_uint32(64),
+                                                C.c_uint32(64), oS.ctypes.data_as(C.c_void_p),
+                                                oO.ctypes.data_as(C.c_void_p), oT.ctypes.data_as(C.c_void_p),
+                                                C.c_long(cap), None)
+    assert n >= 0
+    theirs = sorted(zip(oS[:n].tolist(), oO[:n].tolist(), oT[:n].tolist()))
+    assert len(mine) > 0 and mine == theirs
+
+
+@needs_ref
+def test_pair_acceptance_matches_calcContactPoint(built):
+    """Sphere--sphere acceptance of the oracle's broad phase == calcContactPoint (DEMContactKernels_SphereSphere.cu:57)."""
+    import ctypes as C
+    f = scenes.flatten(_scene("clumps_full"))
+    w = pyoracle.world_from_flat(f)
+    w.step(4000, cd_every=5)
+    w.compute_margins(5)
+    w.detect_contacts()
+    idA, idB, ct, _ = w.contacts()
+    ss = set(zip(idA[ct == 1].tolist(), idB[ct == 1].tolist()))
+    pos, rad = w.sphere_positions()
+    rinf = (rad + w.marginSize[w.ownerClumpBody[: w.nSpheres]]).astype("f4")
+    n = w.nSpheres
+    hits = set()
+    binid = C.c_uint32()
+    for a in range(n):
+        d = np.linalg.norm(pos[a + 1:] - pos[a], axis=1)
+        for b in (np.nonzero(d < 2.2 * rinf.max())[0] + a + 1):
+            if w.ownerClumpBody[a] == w.ownerClumpBody[b]:
+                continue
+            A, B = np.ascontiguousarray(pos[a]), np.ascontiguousarray(pos[b])
+            if pyoracle.ref().ref_calc_contact_point(C.c_double(0.05), C.c_uint32(100), C.c_uint32(100),
+                                                     A.ctypes.data_as(C.c_void_p), C.c_float(rinf[a]),
+                                                     B.ctypes.data_as(C.c_void_p), C.c_float(rinf[b]), C.c_float(0),
+                                                     C.c_float(0), C.byref(binid)):
+                hits.add((a, int(b)))
+    assert len(ss) > 0 and ss == hits
+
+
+GOLDEN_CASES = ["clumps_full", "spheres_frictionless"]
+
+
+@pytest.mark.parametrize("kind", GOLDEN_CASES)
+def test_oracle_reproduces_golden_vectors(built, kind):
+    """Golden trajectories dumped from the host-compiled reference kernels (tests/golden/make_golden.py)."""
+    path = os.path.join(GOLDEN, "golden_%s.npz" % kind)
+    g = np.load(path)
+    f = scenes.flatten(_scene(kind))
+    w = pyoracle.world_from_flat(f)
+    w.step(int(g["nsteps"]), cd_every=f.cd_update_freq)
+    for name in STATE:
+        assert np.array_equal(getattr(w, name)[: w.nOwners].view(np.uint8), g[name].view(np.uint8)), name
+    assert w.nContacts == int(g["nContacts"])
+    assert np.array_equal(w.idGeometryA[: w.nContacts], g["idGeometryA"])
+    assert np.array_equal(w.idGeometryB[: w.nContacts], g["idGeometryB"])
+
+
+def test_figure_out_nv_matches_product(built):
+    from pyapi import demb200
+    for box in [(1.0, 1.0, 1.0), (0.2, 0.2, 0.2), (1.5, 1.3, 1.1), (10.0, 1.0, 0.5), (0.3, 2.0, 0.7), (20, 20, 20)]:
+        umin, umax, tmin, tmax = pyoracle.box_domain(*box)
+        pmin, pmax, ptmin, ptmax = demb200.host_box_domain(*box)
+        assert np.array_equal(tmin, ptmin) and np.array_equal(tmax, ptmax) and np.array_equal(umin, pmin)
+        a = pyoracle.figure_out_nv(tmin, tmax)
+        b = demb200.host_figure_out_nv(tmin, tmax)
+        assert a[:3] == b[:3] and a[3] == b[3] and a[4] == b[4], (box, a, b)
+        assert sum(a[:3]) == 64
