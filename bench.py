@@ -1,0 +1,273 @@
+#!/usr/bin/env python3
+"""bench.py -- DEM steps/s (and grain-updates/s) of the B200-native stepping core on BASELINE.json's headline workload.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's own kernel text on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- 1M three-sphere clumps (data/clumps/3_clump.csv scaled to
+5 mm, Mixer-demo mass/MOI), Hertz-Mindlin with history, h = 5e-6, gravity-settled in a top-open box before timing.
+A "step" is one pass of the hot path: (amortised contact-list rebuild) + contact force + owner integration.
+
+Timing: W >= 3 untimed warm-up steps, then exactly K steps bracketed by a barrier + synchronize, CUDA events on the
+launching stream, max over ranks. The per-step working set (owner state 64 MB + contact stream ~0.5 GB) is larger than
+the 126 MB L2, so consecutive steps do not hit a warm L2 for the streamed arrays.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "dem-engine_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+
+def lattice_dims(n_clumps):
+    """nx*ny*nz ~= n_clumps with a bed about as deep as it is wide (100^3 for 1M)."""
+    n = max(1, int(round(n_clumps ** (1.0 / 3.0))))
+    nx = ny = n
+    nz = max(1, int(round(n_clumps / float(nx * ny))))
+    return nx, ny, nz
+
+
+def build_scene(n_clumps, cd_update_freq, spacing):
+    from pyapi import scenes
+    nx, ny, nz = lattice_dims(n_clumps)
+    sc = scenes.config2_clumps(nx, ny, nz, scale=0.005, h=5e-6, cd_update_freq=cd_update_freq, seed=4150, mu=0.2,
+                               Crr=0.0, spacing=spacing)
+    return sc, (nx, ny, nz)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [x.strip() for x in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def traffic_from_profiles():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get("k_force_ss_dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, budget_s=20.0):
+    """Times the reference's own kernel text (oracle/_ref, host-compiled) -- or the C port when _ref is absent -- on a
+    bounded sample of the workload. Returns (clump_updates_per_s, kind, cores, description, steps_run)."""
+    from oracle import pyoracle
+    from pyapi import scenes
+    sc, dims = build_scene(n_clumps, cd_update_freq, spacing)
+    f = scenes.flatten(sc)
+    w = pyoracle.world_from_flat(f)
+    use_ref = pyoracle.ref() is not None
+    w.step(settle_steps, cd_every=cd_update_freq, use_ref=use_ref)
+    t0 = time.perf_counter()
+    done = 0
+    chunk = max(1, min(steps, cd_update_freq))
+    while done < steps:
+        w.step(chunk, cd_every=cd_update_freq, use_ref=use_ref)
+        done += chunk
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    rate = done * f.nClumps / dt
+    return rate, ("reference" if use_ref else "port"), 1, (
+        "%d clumps (%dx%dx%d lattice of the same bed), %d steps after %d settling steps, single host thread; "
+        "value extrapolated linearly in clump count to the 1M-clump workload" % (f.nClumps, dims[0], dims[1], dims[2], done, settle_steps)), done, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=40)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--clumps", type=int, default=1000000)
+    ap.add_argument("--settle-steps", type=int, default=12000, help="untimed gravity-settling steps before warm-up")
+    ap.add_argument("--cd-update-freq", type=int, default=20)
+    ap.add_argument("--spacing", type=float, default=2.7, help="initial lattice spacing in units of the clump scale")
+    ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    metric, unit = "DEM steps/sec for 1M 3-sphere clumps (Hertz-Mindlin with history)", "steps/s"
+    workload = "C2: %d three-sphere clumps (3_clump.csv @5mm), gravity-settled bed in a top-open box, h=5e-6" % args.clumps
+
+    # ------------------------------------------------------------------------------------------------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, max(args.steps, 1), args.cd_update_freq,
+                                                             args.spacing, settle_steps=min(args.settle_steps, 2000),
+                                                             budget_s=60.0)
+        value = rate / float(args.clumps)
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
+                "steps": done, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 geometry)", "data": "synthetic",
+                "config": {"workload": workload, "cd_update_freq": args.cd_update_freq},
+                "grain_updates_per_s": rate,
+                "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    from pyapi import demb200, scenes
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # strong scaling: the bed is split into `world` slabs along x (multi-GPU)
+    n_local = args.clumps // world
+    sc, dims = build_scene(n_local, args.cd_update_freq, args.spacing)
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(local_rank)
+    stream = torch.cuda.Stream(device=local_rank)
+    eng.set_stream(stream.cuda_stream)
+    eng.load_flat(f)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        eng.step(args.settle_steps)
+        eng.step(args.warmup)
+        barrier()
+        launches0 = eng.stats().kernel_launches
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        eng.step_async(args.steps)
+        ev1.record(stream)
+        barrier()
+        sampler.stop_flag = True
+        ms = ev0.elapsed_time(ev1)
+        launches = eng.stats().kernel_launches - launches0
+        st = eng.stats()
+        # per-kernel device times (CUDA events on the launching stream), same state, right after the timed region
+        prof = eng.profile_steps(min(args.steps, 200))
+
+        # ---- e2e: through the public C-ABI calls with HOST buffers; every step uploads the step's host-side inputs
+        # (simulation parameters + the family prescription / mask tables a co-simulating caller updates) and reads the
+        # step's result metrics (max |v|, kinetic energy) back to the host.
+        h2d = 120 + 32896 + 1024 + 88 * 256
+        d2h = 16
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            eng.set_params(eng.params)
+            eng.update_families(f.familyMasks, f.familyExtraMarginSize, f.prescriptions)
+            eng.step(1)
+            eng.reduce(demb200.REDUCE_MAX_ABSV)
+            eng.reduce(demb200.REDUCE_KINETIC_ENERGY)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    value = args.steps / (ms / 1000.0)
+    n_total_clumps = f.nClumps * world
+    C_ss, C_sa = int(st.n_contacts_ss), int(st.n_contacts_sa)
+    peak, which = measured_peak()
+    # algorithmic bytes of the dominant kernel (k_force_ss), SURVEY.md 8(d): 41 B per candidate contact
+    # (9 ids + 16 history read + 16 history write) + 7 B per sphere + (57 read + 24 accumulate) B per owner
+    algo_bytes = 41.0 * C_ss + 7.0 * f.nSpheres + 81.0 * f.nOwners
+    ach = algo_bytes / (prof["force_ss_us"] * 1e-6) / 1e9 if prof["force_ss_us"] > 0 else 0.0
+    step_bytes = 41.0 * (C_ss + C_sa) + 7.0 * f.nSpheres + 218.0 * f.nOwners
+    line = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (f64 centre distance)", "data": "synthetic",
+        "config": {"workload": workload, "lattice": list(dims), "clumps_total": n_total_clumps,
+                   "spheres_per_gpu": int(f.nSpheres), "contacts_ss": C_ss, "contacts_sa": C_sa,
+                   "cd_update_freq": args.cd_update_freq, "settle_steps": args.settle_steps,
+                   "force_record": False, "l2": "per-step working set > 126 MB L2 (no flush needed)",
+                   "parallelism": "1 GPU" if world == 1 else "%d independent x-slabs (halo exchange not built yet)" % world},
+        "grain_updates_per_s": value * n_total_clumps,
+        "kernel_us": prof,
+        "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "k_force_ss", "achieved": ach, "peak": peak, "unit": "GB/s",
+                     "frac": ach / peak, "traffic": traffic_from_profiles(), "peak_source": which,
+                     "algorithmic_bytes_per_launch": algo_bytes},
+        "e2e": {"value": args.e2e_steps / (e2e_ms / 1000.0), "unit": unit, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, 200, args.cd_update_freq, args.spacing,
+                                                             settle_steps=1000, budget_s=20.0)
+        line["cpu_baseline"] = {"value": rate / float(args.clumps), "unit": unit, "cores": cores, "kind": kind,
+                                "sample": desc}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

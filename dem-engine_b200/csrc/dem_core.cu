@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -15,6 +16,8 @@
 #include "dem_kernels.h"
 
 using namespace demb;
+static_assert(sizeof(DemSimParams) == 120, "DemSimParams layout is part of the C ABI");
+static_assert(sizeof(DemPrescription) == 88 && sizeof(DemPrescription) == sizeof(Prescr), "DemPrescription layout");
 
 namespace {
 
@@ -101,8 +104,11 @@ struct DemCtx {
     uint64_t n_ss = 0, n_sa = 0;
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
-    int force_grid = 148 * 4;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    int ctas_per_sm = 3;
+    int blocked = 1;
+    bool keep_acc = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int sa_grid = 148;
 };
 
 namespace {
@@ -178,7 +184,8 @@ DevParams make_params(const DemCtx* c) {
     P.expSafetyAdder = s.expSafetyAdder;
     P.maxDrift = s.cd_update_freq;
     P.drift_h = s.h * (float)s.cd_update_freq;
-    P.state = c->d_state; P.wrench = c->d_wrench; P.acc_out = c->d_acc;
+    P.state = c->d_state; P.wrench = c->d_wrench; P.acc_out = c->keep_acc ? c->d_acc : nullptr;
+    P.blocked_partition = (uint32_t)c->blocked;
     P.sph = c->d_sph; P.comp = c->d_comp; P.massprop = c->d_massprop; P.matpair = c->d_matpair; P.anal = c->d_anal;
     P.familyMasks = c->d_masks; P.familyExtraMargin = c->d_extra; P.presc = c->d_presc;
     P.ss = as_list(c->ss[c->cur]);
@@ -233,7 +240,9 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
 }
 
 // one contact-list rebuild into the "other" buffers, then swap. Syncs once (reads the counts back).
-int rebuild(DemCtx* ctx) {
+int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
+    cudaEvent_t sev[8];
+    if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
     for (int attempt = 0; attempt < 8; attempt++) {
         DevParams P = make_params(ctx);
         CdParams C = make_cd(ctx);
@@ -242,10 +251,14 @@ int rebuild(DemCtx* ctx) {
         P.sa = as_list(ctx->sa[ctx->cur ^ 1]);
         cudaStream_t s = ctx->stream;
         CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 4, s));
+        if (stage_us) cudaEventRecord(sev[0], s);
         int launches = launch_cd_prepare(P, C, s);
+        if (stage_us) cudaEventRecord(sev[1], s);
         int sorted_buf = 0;
         launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
-        launches += launch_cd_sweep(P, C, sorted_buf, s);
+        if (stage_us) cudaEventRecord(sev[2], s);
+        launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);
+        if (stage_us) cudaEventRecord(sev[7], s);
         ctx->launches += launches;
         CK(cudaMemcpyAsync(ctx->h_pinned + 0, P.ss.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 1, P.sa.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
@@ -296,6 +309,14 @@ int rebuild(DemCtx* ctx) {
             ctx->capacity = newcap;
             continue;
         }
+        if (stage_us) {
+            // [0] margins+keys+histogram [1] radix sort [2] cell scan+gather [3] sweep count [4] offset scans
+            // [5] sweep fill (+history) [6] analytical fill + counts [7] whole rebuild on the device
+            for (int k = 0; k < 7; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
+            cudaEventElapsedTime(&stage_us[7], sev[0], sev[7]);
+            for (int k = 0; k < 8; k++) stage_us[k] *= 1000.f;
+            for (auto& e : sev) cudaEventDestroy(e);
+        }
         ctx->cur ^= 1;
         ctx->n_ss = ctx->h_pinned[0];
         ctx->n_sa = ctx->h_pinned[1];
@@ -313,8 +334,9 @@ int enqueue_step(DemCtx* ctx) {
         if (rc) return rc;
     }
     DevParams P = make_params(ctx);
-    launch_force(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->force_grid, ctx->stream,
-                 ctx->nAnal > 0);
+    launch_force_ss(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->num_sms, ctx->ctas_per_sm, ctx->stream);
+    if (ctx->nAnal > 0)
+        launch_force_sa(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
     launch_integrate(P, ctx->stream);
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
     ctx->n_steps++;
@@ -415,7 +437,9 @@ int dem_ctx_create(DemCtx** out, int device) {
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
     cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocDefault);
-    for (int k = 0; k < 4; k++) cudaEventCreate(&ctx->ev[k]);
+    if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
+    if (const char* e = getenv("DEMB_BLOCKED")) ctx->blocked = atoi(e) != 0;
+    for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
     *out = ctx;
     return DEM_OK;
 }
@@ -426,7 +450,7 @@ int dem_ctx_destroy(DemCtx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    for (int k = 0; k < 4; k++)
+    for (int k = 0; k < 5; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -689,7 +713,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     ctx->cur = 0;
 
     // grid-stride force kernels: a whole number of CTAs per SM
-    ctx->force_grid = ctx->num_sms * 8;
+    ctx->sa_grid = ctx->num_sms * 2;
     ctx->initialized = true;
     ctx->need_rebuild = true;
     ctx->steps_since_rebuild = 0;
@@ -807,6 +831,9 @@ int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* 
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
     std::vector<Wrench> ac;
     if (acc || angacc) {
+        // the per-owner {a, alpha} read-out costs 32 B/owner/step, so it is only written once somebody asks: this
+        // first query returns zeros, every later one the accelerations of the last step taken.
+        ctx->keep_acc = true;
         ac.resize(n);
         CK(cudaMemcpy(ac.data(), ctx->d_acc + first, sizeof(Wrench) * n, cudaMemcpyDeviceToHost));
     }
@@ -950,11 +977,29 @@ int dem_reduce(DemCtx* ctx, int kind, double* out) {
     return DEM_OK;
 }
 
-int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[4]) {
+int dem_set_option(DemCtx* ctx, const char* name, double value) {
+    if (!ctx || !name) return DEM_ERR_INVALID;
+    const std::string n(name);
+    if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
+    else if (n == "blocked_partition") ctx->blocked = value != 0.0;
+    else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
+    else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);
+    return DEM_OK;
+}
+
+int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    double acc[4] = {0, 0, 0, 0};
+    return rebuild(ctx, out_us);
+}
+
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
+    if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    double acc[5] = {0, 0, 0, 0, 0};
     cudaStream_t s = ctx->stream;
+    const int model = (int)ctx->sp.force_model;
+    const bool rec = ctx->sp.record_contact_forces != 0;
     for (uint64_t i = 0; i < n_steps; i++) {
         CK(cudaEventRecord(ctx->ev[0], s));
         if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
@@ -963,22 +1008,25 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[4]) {
         }
         CK(cudaEventRecord(ctx->ev[1], s));
         DevParams P = make_params(ctx);
-        launch_force(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->force_grid, s, ctx->nAnal > 0);
+        launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, s);
         CK(cudaEventRecord(ctx->ev[2], s));
-        launch_integrate(P, s);
+        if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
         CK(cudaEventRecord(ctx->ev[3], s));
+        launch_integrate(P, s);
+        CK(cudaEventRecord(ctx->ev[4], s));
         ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
         ctx->n_steps++;
         ctx->steps_since_rebuild++;
         ctx->sim_time += (double)ctx->sp.h;
-        CK(cudaEventSynchronize(ctx->ev[3]));
+        CK(cudaEventSynchronize(ctx->ev[4]));
         float ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); acc[0] += ms;
         CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); acc[1] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); acc[2] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[3])); acc[3] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); acc[2] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); acc[3] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4])); acc[4] += ms;
     }
-    for (int k = 0; k < 4; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;
+    for (int k = 0; k < 5; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;
     return DEM_OK;
 }
 

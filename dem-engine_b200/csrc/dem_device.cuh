@@ -103,6 +103,7 @@ struct DevParams {
     float beta, approxMaxVel, expSafetyMulti, expSafetyAdder;
     float drift_h;  // h * maxDrift as the reference forms it: (double)(..)*ts*maxDrift, evaluated per owner
     uint32_t maxDrift;
+    uint32_t blocked_partition;  // force kernel: contiguous slice per CTA (1) or grid-stride (0)
     // owners
     OwnerState* state;
     Wrench* wrench;

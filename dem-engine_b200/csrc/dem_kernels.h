@@ -34,13 +34,14 @@ struct CdParams {
     uint32_t* scan_tmp;   // block sums for the scans
 };
 
-void launch_force(const DevParams& P, int model, bool record, int grid, cudaStream_t s, bool have_sa);
+void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s);
+void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 void launch_integrate(const DevParams& P, cudaStream_t s);
 
 // rebuild stages; each returns the number of kernels it launched
 int launch_cd_prepare(const DevParams& P, const CdParams& C, cudaStream_t s);
 int launch_cd_sort(const DevParams& P, const CdParams& C, int key_bits, cudaStream_t s, int* out_buf);
-int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s);
+int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev = nullptr);
 int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* total, cudaStream_t s);
 int launch_reduce(const DevParams& P, int kind, double* d_out, cudaStream_t s);
 

@@ -509,7 +509,7 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, cudaStream_t s) {
     return launches;
 }
 
-int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s) {
+int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev) {
     int launches = 0;
     const uint32_t n = P.nSpheres;
     // cell histogram -> exclusive prefix (ncells+1 entries; scanning the full capacity keeps the launch shape static)
@@ -517,16 +517,21 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
     // totals live right behind the per-sphere offsets: cnt[n], saCnt[n]
     if (n) {
         k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(P, C, C.vals[sorted_buf]);
+        if (ev) cudaEventRecord(ev[0], s);
         k_sweep<false><<<(n + 127) / 128, 128, 0, s>>>(P, C, C.keys[sorted_buf]);
+        if (ev) cudaEventRecord(ev[1], s);
         launches += 2;
         launches += launch_scan_exclusive(C.cnt, n, C.scan_tmp, C.cnt + n, s);
         launches += launch_scan_exclusive(C.saCnt, n, C.scan_tmp, C.saCnt + n, s);
+        if (ev) cudaEventRecord(ev[2], s);
         k_sweep<true><<<(n + 127) / 128, 128, 0, s>>>(P, C, C.keys[sorted_buf]);
+        if (ev) cudaEventRecord(ev[3], s);
         k_sa_fill<<<(n + 255) / 256, 256, 0, s>>>(P, C);
         launches += 2;
     } else {
         cudaMemsetAsync(C.cnt, 0, sizeof(uint32_t), s);
         cudaMemsetAsync(C.saCnt, 0, sizeof(uint32_t), s);
+        if (ev) for (int k = 0; k < 4; k++) cudaEventRecord(ev[k], s);
     }
     k_finish_counts<<<1, 32, 0, s>>>(P, C, C.cnt + n, C.saCnt + n);
     launches++;

@@ -120,13 +120,29 @@ __device__ __forceinline__ void scatter_wrench(Wrench* __restrict__ wr, uint32_t
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// sphere--sphere contacts.  One thread per contact, grid-stride over a DEVICE-resident count (no host sync).
-template <int MODEL, bool RECORD>
-__global__ void __launch_bounds__(256) k_force_ss(const __grid_constant__ DevParams P) {
+// sphere--sphere contacts.  One thread per contact; the count is DEVICE-resident (no host sync).  Each CTA walks a
+// CONTIGUOUS slice of the (cell-ordered) contact list so that the owner records of spatially adjacent contacts are
+// re-used out of L1, and the next compiled record is prefetched while the current contact is evaluated.
+template <int MODEL, bool RECORD, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
     const uint32_t n = *P.ss.count;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
-        const uint4 ci = __ldcs(&P.ss.cinfo[c]);  // streaming: evict-first
+    uint32_t c, end, step;
+    if (P.blocked_partition) {
+        const uint32_t chunk = ((n + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
+        c = blockIdx.x * chunk + threadIdx.x;
+        end = min(n, (blockIdx.x + 1) * chunk);
+        step = 256;
+    } else {
+        c = blockIdx.x * blockDim.x + threadIdx.x;
+        end = n;
+        step = gridDim.x * blockDim.x;
+    }
+    uint4 ci = make_uint4(0, 0, 0, 0);
+    if (c < end) ci = __ldcs(&P.ss.cinfo[c]);  // streaming: evict-first
+    while (c < end) {
+        const uint32_t cn = c + step;
+        uint4 ci_next = make_uint4(0, 0, 0, 0);
+        if (cn < end) ci_next = __ldcs(&P.ss.cinfo[cn]);
         const uint32_t oA = ci.x, oB = ci.y;
         const bool alive = (ci.w >> 31) != 0u;
         float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -181,6 +197,8 @@ __global__ void __launch_bounds__(256) k_force_ss(const __grid_constant__ DevPar
             }
             if (RECORD) P.ss.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        ci = ci_next;
+        c = cn;
     }
 }
 
@@ -190,11 +208,19 @@ template <int MODEL, bool RECORD>
 __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevParams P) {
     const uint32_t n = *P.sa.count;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += stride) {
+        // every lane of the warp takes part in the B-side aggregation below, active or not
+        const bool active = c < n;
+        float wB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool touchB = false;
+        uint32_t oBkey = 0xffffffffu;
+        if (active) {
         const uint4 ci = P.sa.cinfo[c];
         const uint32_t oA = ci.x;
         const AnalObj ob = P.anal[ci.y];
         const uint32_t oB = ob.owner;
+        oBkey = oB;
         const bool alive = (ci.w >> 31) != 0u;
         float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODEL == 0 && alive) hist = P.sa.hist[c];
@@ -254,7 +280,17 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
             const MatPair mp = P.matpair[ci.w & 0xffffu];
             float3 force, troll;
             contact_model<MODEL>(mp, P.h, depth, nrm, cA, cB, A, B, rA, 1e15f, hist, force, troll);
-            scatter_wrench(P.wrench, oA, oB, force, troll, cA, cB, A.q, B.q);
+            {
+                const float3 FA = rotate_inv(force + troll, A.q);
+                const float3 TA = cross(cA, FA);
+                red_add_v4(&P.wrench[oA].f, force.x, force.y, force.z);
+                red_add_v4(&P.wrench[oA].t, TA.x, TA.y, TA.z);
+                const float3 FB = rotate_inv(f3(-1.f * (force.x + troll.x), -1.f * (force.y + troll.y), -1.f * (force.z + troll.z)), B.q);
+                const float3 TB = cross(cB, FB);
+                wB[0] = -force.x; wB[1] = -force.y; wB[2] = -force.z;
+                wB[3] = TB.x; wB[4] = TB.y; wB[5] = TB.z;
+                touchB = true;
+            }
             if (MODEL == 0) {
                 P.sa.hist[c] = hist;
                 if (!alive) P.sa.cinfo[c].w = ci.w | 0x80000000u;
@@ -266,6 +302,27 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
                 P.sa.cinfo[c].w = ci.w & 0x7fffffffu;
             }
             if (RECORD) P.sa.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        }  // active
+        // B side: the contacts of a warp almost always share ONE wall owner, so a per-contact reduction would
+        // serialise on a single L2 line. Reduce across the warp first, one vector reduction per distinct owner.
+        uint32_t todo = __ballot_sync(0xffffffffu, touchB);
+        while (todo) {
+            const int leader = __ffs(todo) - 1;
+            const uint32_t key = __shfl_sync(0xffffffffu, oBkey, leader);
+            const bool mine = touchB && (oBkey == key);
+            float v[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                v[k] = mine ? wB[k] : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+            }
+            if ((int)(threadIdx.x & 31) == leader) {
+                red_add_v4(&P.wrench[key].f, v[0], v[1], v[2]);
+                red_add_v4(&P.wrench[key].t, v[3], v[4], v[5]);
+            }
+            todo &= ~__ballot_sync(0xffffffffu, mine);
         }
     }
 }
@@ -383,22 +440,31 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-void launch_force(const DevParams& P, int model, bool record, int grid, cudaStream_t s, bool have_sa) {
+template <int MINB>
+static void launch_force_ss_t(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {
     const int block = 256;
-#define LAUNCH(K)                                   \
-    K<<<grid, block, 0, s>>>(P)
     if (model == DEM_HERTZIAN) {
-        if (record) { LAUNCH((k_force_ss<0, true>)); } else { LAUNCH((k_force_ss<0, false>)); }
-        if (have_sa) {
-            if (record) { LAUNCH((k_force_sa<0, true>)); } else { LAUNCH((k_force_sa<0, false>)); }
-        }
+        if (record) k_force_ss<0, true, MINB><<<grid, block, 0, s>>>(P); else k_force_ss<0, false, MINB><<<grid, block, 0, s>>>(P);
     } else {
-        if (record) { LAUNCH((k_force_ss<1, true>)); } else { LAUNCH((k_force_ss<1, false>)); }
-        if (have_sa) {
-            if (record) { LAUNCH((k_force_sa<1, true>)); } else { LAUNCH((k_force_sa<1, false>)); }
-        }
+        if (record) k_force_ss<1, true, MINB><<<grid, block, 0, s>>>(P); else k_force_ss<1, false, MINB><<<grid, block, 0, s>>>(P);
     }
-#undef LAUNCH
+}
+
+// ctas_per_sm CTAs per SM (2, 3 or 4 -- selects the register budget the kernel was compiled for)
+void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s) {
+    const int grid = num_sms * ctas_per_sm;
+    if (ctas_per_sm >= 4) launch_force_ss_t<4>(P, model, record, grid, s);
+    else if (ctas_per_sm == 3) launch_force_ss_t<3>(P, model, record, grid, s);
+    else launch_force_ss_t<2>(P, model, record, grid, s);
+}
+
+void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {
+    const int block = 256;
+    if (model == DEM_HERTZIAN) {
+        if (record) k_force_sa<0, true><<<grid, block, 0, s>>>(P); else k_force_sa<0, false><<<grid, block, 0, s>>>(P);
+    } else {
+        if (record) k_force_sa<1, true><<<grid, block, 0, s>>>(P); else k_force_sa<1, false><<<grid, block, 0, s>>>(P);
+    }
 }
 
 void launch_integrate(const DevParams& P, cudaStream_t s) {

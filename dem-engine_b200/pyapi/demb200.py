@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
-    "dem_get_stats", "dem_reduce", "dem_profile_steps",
+    "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
 ]
 
 
@@ -76,6 +76,7 @@ def load_library(path=None):
             getattr(_lib, name).argtypes = [C.c_void_p, C.c_uint64]
         _lib.dem_initialize.argtypes = [C.c_void_p, C.c_uint64]
         _lib.dem_update_step_size.argtypes = [C.c_void_p, C.c_float]
+        _lib.dem_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
     return _lib
 
 
@@ -253,7 +254,18 @@ class Engine:
         self._ck(self.lib.dem_reduce(self.ctx, int(kind), C.byref(out)))
         return out.value
 
+    def set_option(self, name, value):
+        self._ck(self.lib.dem_set_option(self.ctx, name.encode(), float(value)))
+
+    def profile_rebuild(self):
+        out = (C.c_float * 8)()
+        self._ck(self.lib.dem_profile_rebuild(self.ctx, out))
+        names = ["prep_us", "sort_us", "cellscan_gather_us", "sweep_count_us", "offset_scans_us", "sweep_fill_us",
+                 "sa_fill_us", "total_us"]
+        return dict(zip(names, [float(x) for x in out]))
+
     def profile_steps(self, n):
-        out = (C.c_float * 4)()
+        out = (C.c_float * 5)()
         self._ck(self.lib.dem_profile_steps(self.ctx, C.c_uint64(n), out))
-        return {"force_us": out[0], "integrate_us": out[1], "rebuild_us_per_step": out[2], "step_us": out[3]}
+        return {"force_ss_us": out[0], "force_sa_us": out[1], "integrate_us": out[2], "rebuild_us_per_step": out[3],
+                "step_us": out[4]}

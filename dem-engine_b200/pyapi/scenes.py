@@ -4,7 +4,7 @@
 mirroring the calls a reference demo script makes (LoadMaterial / LoadClumpType / AddClumps / InstructBoxDomain* ...).
 `flatten(scene)` produces the reference's flattened SoA arrays (owners ordered clumps, analytical objects, meshes;
 src/DEM/dT.cpp:638-1024 populateEntityArrays of the reference) as a `FlatWorld`, which both the CUDA engine
-(pyapi.demb200.Engine.load_flat) and the CPU oracle (oracle.pyoracle.World, tests only) consume.
+(pyapi.demb200.Engine.load_flat) and the CPU checker used by the tests consume.
 
 World sizing uses the product's own host routines (dem_host_box_domain / dem_host_figure_out_nv /
 dem_host_encode_positions of libdemcore.so).

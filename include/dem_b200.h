@@ -201,10 +201,19 @@ enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_
        DEM_REDUCE_TOTAL_MASS = 4 };
 int dem_reduce(DemCtx* ctx, int kind, double* out);
 
+/* execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
+ * "blocked_partition" (0/1), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */
+int dem_set_option(DemCtx* ctx, const char* name, double value);
+
 /* ---- measurement hooks (bench.py / ncu) ---------------------------------------------------------------- */
-/* Run n steps and return the mean device time per kernel class in microseconds, measured with CUDA events on the
- * launching stream: [0]=contact force (all lists) [1]=integration [2]=rebuild (amortised per step) [3]=whole step */
-int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[4]);
+/* Run n steps and return the mean device time per kernel in microseconds, measured with CUDA events on the
+ * launching stream: [0]=sphere-sphere force kernel [1]=sphere-analytical force kernel [2]=integration kernel
+ * [3]=contact rebuild amortised per step [4]=whole step */
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]);
+/* One contact-list rebuild with CUDA events between its stages (microseconds): [0] margins + cell keys + histogram
+ * [1] radix sort [2] cell-table scan + gather [3] sweep count [4] offset scans [5] sweep fill + history carry-over
+ * [6] analytical fill + counts [7] whole rebuild */
+int dem_profile_rebuild(DemCtx* ctx, float out_us[8]);
 
 #ifdef __cplusplus
 }

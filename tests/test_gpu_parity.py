@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA hot path (through the C ABI of include/dem_b200.h) against the CPU oracle on the same
+seeded inputs.  Integer / index work (contact candidates that are in physical touch, position codes after one step of
+identical forces) is compared exactly; floating-point state is compared to the stated tolerances:
+
+  * one step from identical state (no chaotic amplification):  |dv| <= 2e-5 * max|v| + 1e-7 m/s,
+    position code difference <= 2 sub-voxel units (the truncating encode can flip the last unit)
+  * N-step trajectories: a colliding granular bed amplifies ANY fp32 rounding difference exponentially (a 1-ulp
+    change of the initial velocities moves the oracle's own result by 1e-4 m after 3000 steps), so trajectories are
+    compared at checkpoints against the oracle's measured round-off sensitivity: the device may differ from the oracle
+    by at most 10x what the oracle differs from itself when its velocities are perturbed by 1e-6 relative (the size of
+    the per-step device/oracle difference established by the single-step test), plus 1e-7 m.
+"""
+import numpy as np
+import pytest
+
+from pyapi import demb200, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def _mk(kind):
+    from test_oracle_vs_ref import _scene
+    return _scene(kind)
+
+
+def _touching_pairs(w):
+    """Contacts of the oracle world that are in physical touch (non-zero force)."""
+    n = w.nContacts
+    F = w.contactForces[: 3 * n].reshape(-1, 3)
+    on = np.abs(F).max(1) > 0
+    return set(zip(w.idGeometryA[:n][on].tolist(), w.idGeometryB[:n][on].tolist(), w.contactType[:n][on].tolist()))
+
+
+def _vel(w, n):
+    return np.stack([w.vX, w.vY, w.vZ], 1)[:n]
+
+
+def _check_trajectory(eng, f, w, checkpoints, label):
+    """Step device and oracle side by side; at every checkpoint the device/oracle distance must stay within 10x the
+    oracle's own round-off sensitivity (see module docstring)."""
+    wp = w.copy()
+    for name in ("vX", "vY", "vZ", "omgBarX", "omgBarY", "omgBarZ"):
+        a = getattr(wp, name)
+        a[:] = (a.astype("f8") * (1.0 + 1e-6)).astype("f4")
+    nC = f.nClumps
+    done = 0
+    for cp in checkpoints:
+        eng.step(cp - done)
+        w.step(cp - done, cd_every=f.cd_update_freq)
+        wp.step(cp - done, cd_every=f.cd_update_freq)
+        done = cp
+        pw = w.positions_f64()[:nC]
+        sens_x = np.abs(wp.positions_f64()[:nC] - pw).max()
+        sens_v = np.abs(_vel(wp, nC) - _vel(w, nC)).max()
+        err_x = np.abs(eng.positions()[:nC] - pw).max()
+        err_v = np.abs(eng.owner_state()["vel"][:nC] - _vel(w, nC)).max()
+        print("%s step %d: |dx| %.2e (sensitivity %.2e)  |dv| %.2e (sensitivity %.2e)" % (label, cp, err_x, sens_x, err_v, sens_v))
+        assert err_x <= 10 * sens_x + 1e-7, (cp, err_x, sens_x)
+        assert err_v <= 10 * sens_v + 1e-5 * max(1.0, np.abs(_vel(w, nC)).max()), (cp, err_v, sens_v)
+
+
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder"])
+def test_trajectory_matches_oracle(built, kind):
+    po = _oracle()
+    f = scenes.flatten(_mk(kind))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    w = po.world_from_flat(f)
+    nsteps = 3000
+    _check_trajectory(eng, f, w, [500, 1000, 1500, 2000, 3000], kind)
+    st = eng.owner_state()
+    q = st["oriQ"][: f.nClumps]
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-5
+    # the device candidate list must contain every pair that is in physical touch in the device's own state
+    w2 = po.world_from_flat(f)
+    for name in ("voxelID", "locX", "locY", "locZ"):
+        getattr(w2, name)[: f.nOwners] = st[name]
+    for k, name in enumerate(("oriQw", "oriQx", "oriQy", "oriQz")):
+        getattr(w2, name)[: f.nOwners] = st["oriQ"][:, k]
+    w2.beta = np.float32(0.0)
+    w2.compute_margins(1)
+    w2.detect_contacts()
+    w2.calc_forces()
+    idA, idB, ct, wc = eng.contacts()
+    mine = set(zip(idA.tolist(), idB.tolist(), ct.tolist()))
+    touching = _touching_pairs(w2)
+    assert len(touching) > 0 and touching <= mine
+    assert eng.stats().n_rebuilds == nsteps // f.cd_update_freq
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", ["clumps_full", "spheres_frictionless", "cylinder"])
+def test_single_step_from_identical_state(built, kind):
+    """Advance the oracle into a contact-rich state, load that exact state (positions codes, velocities AND contact
+    history) into the device, then compare ONE step: no chaotic growth, so tolerances are at fp32 rounding level."""
+    po = _oracle()
+    f = scenes.flatten(_mk(kind))
+    w = po.world_from_flat(f)
+    w.step(3000 - (3000 % f.cd_update_freq), cd_every=f.cd_update_freq)
+    # copy oracle state into the flat arrays
+    for name in ("voxelID", "locX", "locY", "locZ", "oriQw", "oriQx", "oriQy", "oriQz", "vX", "vY", "vZ", "omgBarX",
+                 "omgBarY", "omgBarZ"):
+        getattr(f, name)[: f.nOwners] = getattr(w, name)[: f.nOwners]
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    n = w.nContacts
+    wc = np.stack([c[:n] for c in w.contactWildcards], 1)
+    eng.set_contacts(w.idGeometryA[:n], w.idGeometryB[:n], w.contactType[:n], wc)
+    eng.step(1)
+    w.step(1, cd_every=f.cd_update_freq)
+    st = eng.owner_state()
+    nC = f.nClumps
+    vw = np.stack([w.vX, w.vY, w.vZ], 1)[:nC]
+    ow = np.stack([w.omgBarX, w.omgBarY, w.omgBarZ], 1)[:nC]
+    vtol = 2e-5 * np.abs(vw).max() + 1e-7
+    print("%s single step: |dv| %.3e (tol %.3e), max|v| %.3f" % (kind, np.abs(st["vel"][:nC] - vw).max(), vtol, np.abs(vw).max()))
+    assert np.abs(st["vel"][:nC] - vw).max() <= vtol, (np.abs(st["vel"][:nC] - vw).max(), vtol)
+    otol = 2e-5 * max(np.abs(ow).max(), 1.0) + 1e-6
+    assert np.abs(st["omg"][:nC] - ow).max() <= otol, (np.abs(st["omg"][:nC] - ow).max(), otol)
+    # position codes: identical up to the last truncated unit
+    def ints(vox, lx, ly, lz):
+        vx = vox & np.uint64((1 << f.nvXp2) - 1)
+        vy = (vox >> np.uint64(f.nvXp2)) & np.uint64((1 << f.nvYp2) - 1)
+        vz = vox >> np.uint64(f.nvXp2 + f.nvYp2)
+        return np.stack([(vx.astype("i8") << 16) + lx, (vy.astype("i8") << 16) + ly, (vz.astype("i8") << 16) + lz], 1)
+    ig = ints(st["voxelID"][:nC], st["locX"][:nC].astype("i8"), st["locY"][:nC].astype("i8"), st["locZ"][:nC].astype("i8"))
+    iw = ints(w.voxelID[:nC], w.locX[:nC].astype("i8"), w.locY[:nC].astype("i8"), w.locZ[:nC].astype("i8"))
+    # one step moves an owner by v*h; a relative velocity error of 2e-5 on |v|<=3 m/s is 3e-10 m ~ tens of units of l
+    unit_tol = max(2, int(vtol * float(f.h) / f.l) + 2)
+    assert np.abs(ig - iw).max() <= unit_tol, (np.abs(ig - iw).max(), unit_tol)
+    # history of touching contacts carried and updated identically
+    idA, idB, ct, wcg = eng.contacts()
+    key = {(a, b, t): i for i, (a, b, t) in enumerate(zip(idA.tolist(), idB.tolist(), ct.tolist()))}
+    n = w.nContacts
+    wco = np.stack([c[:n] for c in w.contactWildcards], 1)
+    checked = 0
+    for i in range(n):
+        if np.abs(wco[i]).max() > 0:
+            j = key[(int(w.idGeometryA[i]), int(w.idGeometryB[i]), int(w.contactType[i]))]
+            assert np.allclose(wcg[j], wco[i], rtol=2e-4, atol=1e-9), (wcg[j], wco[i])
+            checked += 1
+    if f.force_model == demb200.HERTZIAN:
+        assert checked > 0
+    eng.close()
+
+
+def test_candidate_list_is_superset_of_brute_force(built):
+    """Broad phase: every pair of inflated spheres that overlaps (brute force O(N^2) in double) is in the device list."""
+    po = _oracle()
+    f = scenes.flatten(_mk("clumps_full"))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    eng.step(2000)
+    eng.rebuild_contacts()
+    st = eng.owner_state()
+    w = po.world_from_flat(f)
+    for name, key in (("voxelID", "voxelID"), ("locX", "locX"), ("locY", "locY"), ("locZ", "locZ")):
+        getattr(w, name)[: f.nOwners] = st[key]
+    for k, name in enumerate(("oriQw", "oriQx", "oriQy", "oriQz")):
+        getattr(w, name)[: f.nOwners] = st["oriQ"][:, k]
+    for k, name in enumerate(("vX", "vY", "vZ")):
+        getattr(w, name)[: f.nOwners] = st["vel"][:, k]
+    w.compute_margins(f.cd_update_freq)
+    w.detect_contacts()
+    oa, ob, ot, _ = w.contacts()
+    idA, idB, ct, _ = eng.contacts()
+    mine = set(zip(idA.tolist(), idB.tolist(), ct.tolist()))
+    theirs = set(zip(oa.tolist(), ob.tolist(), ot.tolist()))
+    assert len(theirs) > 50
+    assert theirs <= mine
+    # and not wildly larger (float slack only)
+    assert len(mine) <= len(theirs) + max(4, len(theirs) // 50)
+    eng.close()
+
+
+def test_empty_and_single_body_worlds(built):
+    # no clumps at all
+    sc = scenes.Scene()
+    sc.load_material(E=1e8, nu=0.3, CoR=0.5, mu=0.3, Crr=0.0)
+    sc.bounding = "all"
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    eng.step(5)
+    assert eng.stats().n_contacts_ss == 0
+    eng.close()
+    # one sphere in free fall: exact kinematics of the integrator
+    sc = scenes.Scene()
+    m = sc.load_material(E=1e8, nu=0.3, CoR=0.5, mu=0.3, Crr=0.0)
+    t = sc.load_sphere_type(1e-3, 0.01, m)
+    sc.add_clumps(t, [[0.0, 0.0, 0.2]])
+    sc.h = 1e-4
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    po = _oracle()
+    w = po.world_from_flat(f)
+    eng.step(100)
+    w.step(100, cd_every=f.cd_update_freq)
+    st = eng.owner_state()
+    assert st["vel"][0, 2] == w.vZ[0]
+    assert st["voxelID"][0] == w.voxelID[0] and st["locZ"][0] == w.locZ[0]
+    eng.close()
+
+
+def test_fixed_and_prescribed_families(built):
+    po = _oracle()
+    sc = _mk("clumps_full")
+    n = len(sc.clump_type)
+    fam = np.zeros(n, "u1")
+    fam[::7] = 3   # fixed family
+    fam[1::7] = 5  # prescribed linear velocity
+    sc.clump_family = fam
+    sc.fixed_families.append(3)
+    sc.prescribed[5] = dict(linvel=(0.1, None, -0.5), dictate=True)
+    sc.disabled_pairs.append((3, 5))
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    w = po.world_from_flat(f)
+    x0 = eng.positions()
+    _check_trajectory(eng, f, w, [500, 1000, 2000], "families")
+    x1 = eng.positions()
+    # fixed owners: no motion beyond the truncating re-encode of the reference (at most one length unit per step),
+    # and bit-identical to the oracle (no force arithmetic involved)
+    assert np.abs(x0[:n][fam == 3] - x1[:n][fam == 3]).max() <= 2000 * f.l
+    assert np.array_equal(x1[:n][fam == 3], w.positions_f64()[:n][fam == 3])
+    st = eng.owner_state()
+    assert np.all(st["vel"][:n][fam == 3] == 0)
+    assert np.all(st["vel"][:n][fam == 5][:, 0] == np.float32(0.1)) and np.all(st["vel"][:n][fam == 5][:, 2] == np.float32(-0.5))
+    idA, idB, ct, _ = eng.contacts()
+    own = f.ownerClumpBody
+    ss = ct == 1
+    fa, fb = fam[own[idA[ss]]], fam[own[idB[ss]]]
+    assert not np.any(((fa == 3) & (fb == 5)) | ((fa == 5) & (fb == 3)))
+    eng.close()
+
+
+def test_capacity_overflow_grows_list(built):
+    po = _oracle()
+    f = scenes.flatten(_mk("clumps_full"))
+    eng = demb200.Engine(0)
+    eng.load_flat(f, contact_capacity=16)
+    w = po.world_from_flat(f)
+    _check_trajectory(eng, f, w, [1000, 2000, 3000], "overflow")
+    s = eng.stats()
+    assert s.overflow > 0 and s.contact_capacity > 16
+    eng.close()
+
+
+def test_do_dynamics_step_count_and_reductions(built):
+    f = scenes.flatten(_mk("spheres_frictionless"))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    h = float(np.float32(f.h))
+    t = 250.5 * h
+    n_expected, cyc = 0, 0.0
+    while cyc < t:
+        n_expected += 1
+        cyc += h
+    eng.do_dynamics(t)
+    assert eng.stats().n_steps == n_expected
+    eng.do_dynamics(0.0)  # dry run only rebuilds
+    assert eng.stats().n_steps == n_expected
+    st = eng.owner_state()
+    nC = f.nClumps
+    absv = np.linalg.norm(st["vel"][:nC].astype("f8"), axis=1).max()
+    assert abs(eng.reduce(demb200.REDUCE_MAX_ABSV) - absv) < 1e-6 * max(absv, 1)
+    z = eng.positions()[:nC, 2]
+    assert abs(eng.reduce(demb200.REDUCE_MAX_Z) - z.max()) < 1e-12
+    assert abs(eng.reduce(demb200.REDUCE_MIN_Z) - z.min()) < 1e-12
+    mass = float(f.MassProperties[0]) * nC
+    assert abs(eng.reduce(demb200.REDUCE_TOTAL_MASS) - mass) < 1e-6 * mass
+    eng.close()
+
+
+def test_momentum_conservation_without_walls(built):
+    """Sum of internal forces is zero: with no gravity and no walls the total linear momentum is conserved."""
+    sc = scenes.config2_clumps(5, 5, 4, cd_update_freq=5, spacing=2.7)
+    sc.bounding = "none"
+    sc.G = (0, 0, 0)
+    rng = np.random.RandomState(3)
+    n = len(sc.clump_type)
+    c = sc.clump_xyz.mean(0)
+    sc.clump_vel = (-(sc.clump_xyz - c) * 40 + rng.normal(size=(n, 3)) * 0.05).astype("f4")  # implode
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    p0 = eng.owner_state()["vel"][:n].astype("f8").sum(0) * float(f.MassProperties[0])
+    eng.step(3000)
+    st = eng.owner_state()
+    p1 = st["vel"][:n].astype("f8").sum(0) * float(f.MassProperties[0])
+    assert eng.stats().n_contacts_ss > 0
+    scale = np.abs(st["vel"][:n]).sum() * float(f.MassProperties[0])
+    assert np.abs(p1 - p0).max() < 1e-4 * scale, (p0, p1, scale)
+    eng.close()
