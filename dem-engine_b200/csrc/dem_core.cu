@@ -86,9 +86,8 @@ struct DemCtx {
     uint32_t* d_vals[2] = {nullptr, nullptr};
     uint32_t* d_cellStart = nullptr;
     float4* d_sortedSph = nullptr;
-    uint2* d_sortedMeta = nullptr;
-    uint32_t* d_cnt = nullptr;
-    uint32_t* d_saCnt = nullptr;
+    uint4* d_sortedMeta = nullptr;
+    AnalWorld* d_analw = nullptr;
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
     uint32_t max_cells = 0;
@@ -100,12 +99,17 @@ struct DemCtx {
     uint64_t n_steps = 0, n_rebuilds = 0, launches = 0, device_bytes = 0;
     uint64_t steps_since_rebuild = 0;
     bool need_rebuild = true;
+    bool need_maxvel = true;  // velocities changed outside the integrator
+    int maxvel_slot = 0;
     double sim_time = 0.0;
     uint64_t n_ss = 0, n_sa = 0;
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
     int ctas_per_sm = 3;
-    int blocked = 1;
+    int blocked = 0;
+    int prefetch_mode = 1;
+    int fast_encode = 1;
+    int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     int sa_grid = 148;
@@ -183,14 +187,19 @@ DevParams make_params(const DemCtx* c) {
     P.beta = s.beta; P.approxMaxVel = s.approxMaxVel; P.expSafetyMulti = s.expSafetyMulti;
     P.expSafetyAdder = s.expSafetyAdder;
     P.maxDrift = s.cd_update_freq;
-    P.drift_h = s.h * (float)s.cd_update_freq;
     P.state = c->d_state; P.wrench = c->d_wrench; P.acc_out = c->keep_acc ? c->d_acc : nullptr;
     P.blocked_partition = (uint32_t)c->blocked;
+    P.prefetch_mode = (uint32_t)c->prefetch_mode;
+    P.fast_encode = (uint32_t)c->fast_encode;
+    P.inv_voxelSize = 1.0 / s.voxelSize;
     P.sph = c->d_sph; P.comp = c->d_comp; P.massprop = c->d_massprop; P.matpair = c->d_matpair; P.anal = c->d_anal;
     P.familyMasks = c->d_masks; P.familyExtraMargin = c->d_extra; P.presc = c->d_presc;
     P.ss = as_list(c->ss[c->cur]);
     P.sa = as_list(c->sa[c->cur]);
-    P.flags = c->d_flags; P.maxvel = c->d_maxvel;
+    P.flags = c->d_flags;
+    P.maxvel = c->d_maxvel + c->maxvel_slot;
+    P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
+    P.errOutVel = s.errOutVel;
     return P;
 }
 
@@ -209,7 +218,7 @@ CdParams make_cd(const DemCtx* c) {
     C.sphF = c->d_sphF;
     C.keys[0] = c->d_keys[0]; C.keys[1] = c->d_keys[1]; C.vals[0] = c->d_vals[0]; C.vals[1] = c->d_vals[1];
     C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedMeta = c->d_sortedMeta;
-    C.cnt = c->d_cnt; C.saCnt = c->d_saCnt;
+    C.analw = c->d_analw;
     C.oldss = as_list(c->ss[c->cur]);
     C.oldsa = as_list(c->sa[c->cur]);
     C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp;
@@ -222,8 +231,8 @@ void free_device(DemCtx* c) {
     dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce);
     for (int k = 0; k < 2; k++) { free_list(c->ss[k]); free_list(c->sa[k]); }
     dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
-    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_cnt);
-    dfree(c->d_saCnt); dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
+    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw);
+    dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
     c->device_bytes = 0;
 }
 
@@ -250,25 +259,31 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         P.ss = as_list(ctx->ss[ctx->cur ^ 1]);
         P.sa = as_list(ctx->sa[ctx->cur ^ 1]);
         cudaStream_t s = ctx->stream;
-        CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 4, s));
+        CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 3, s));  // [3] (velocity) is only cleared by the host
         if (stage_us) cudaEventRecord(sev[0], s);
-        int launches = launch_cd_prepare(P, C, s);
+        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, s);
         if (stage_us) cudaEventRecord(sev[1], s);
-        int sorted_buf = 0;
-        launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
+        int sorted_buf = -1;  // -1: counting sort inside the sweep stage
+        if (ctx->sort_mode == 0) launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
         if (stage_us) cudaEventRecord(sev[2], s);
-        launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);
+        launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);  // records sev[3..6]
         if (stage_us) cudaEventRecord(sev[7], s);
         ctx->launches += launches;
         CK(cudaMemcpyAsync(ctx->h_pinned + 0, P.ss.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 1, P.sa.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_flags, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 24, C.cnt + ctx->nSpheres, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 25, C.saCnt + ctx->nSpheres, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 24, P.ss.count + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->h_pinned + 25, P.sa.count + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         memcpy(&ctx->last_grid, ctx->h_pinned + 8, sizeof(GridInfo));
-        if (ctx->h_pinned[3] != 0) {
+        ctx->need_maxvel = false;
+        if (ctx->h_pinned[4] != 0)
+            return fail(ctx, DEM_ERR_CAPACITY, "a sphere has more than 40 forward contact candidates: geometry size "
+                        "ratios this large need a smaller contact margin (SetExpandSafetyAdder / SetCDUpdateFreq)");
+        if (ctx->h_pinned[5] != 0) {
+            const uint32_t zero = 0;
+            cudaMemcpy(ctx->d_flags + 3, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice);
             return fail(ctx, DEM_ERR_VELOCITY,
                         "an owner has a non-finite or too large velocity (max seen %.6g, limit %.6g) at t=%.9g",
                         ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
@@ -310,9 +325,10 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             continue;
         }
         if (stage_us) {
-            // [0] margins+keys+histogram [1] radix sort [2] cell scan+gather [3] sweep count [4] offset scans
-            // [5] sweep fill (+history) [6] analytical fill + counts [7] whole rebuild on the device
-            for (int k = 0; k < 7; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
+            // [0] margins+keys+histogram+analytical list [1] sort [2] cell-table scan [3] gather [4] sweep
+            // [5] counts [6] unused [7] whole rebuild on the device
+            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
+            stage_us[6] = 0.f;
             cudaEventElapsedTime(&stage_us[7], sev[0], sev[7]);
             for (int k = 0; k < 8; k++) stage_us[k] *= 1000.f;
             for (auto& e : sev) cudaEventDestroy(e);
@@ -338,6 +354,7 @@ int enqueue_step(DemCtx* ctx) {
     if (ctx->nAnal > 0)
         launch_force_sa(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
     launch_integrate(P, ctx->stream);
+    ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
     ctx->n_steps++;
     ctx->steps_since_rebuild++;
@@ -701,8 +718,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if ((rc = dalloc(ctx, &ctx->d_cellStart, (size_t)ctx->max_cells + 2))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_sortedSph, nS))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_sortedMeta, nS))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_cnt, (size_t)nS + 2))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_saCnt, (size_t)nS + 2))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_analw, ctx->h_anal.size()))) return rc;
     const size_t rs_blocks = ((size_t)nS + 4095) / 4096 + 1;
     if ((rc = dalloc(ctx, &ctx->d_rs_hist, 256 * rs_blocks))) return rc;
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
@@ -714,6 +730,9 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
 
     // grid-stride force kernels: a whole number of CTAs per SM
     ctx->sa_grid = ctx->num_sms * 2;
+    CK(cudaMemset(ctx->d_maxvel, 0, sizeof(float) * 4));
+    ctx->maxvel_slot = 0;
+    ctx->need_maxvel = true;
     ctx->initialized = true;
     ctx->need_rebuild = true;
     ctx->steps_since_rebuild = 0;
@@ -900,6 +919,7 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     }
     CK(cudaMemcpy(ctx->d_state + first, st.data(), sizeof(OwnerState) * n, cudaMemcpyHostToDevice));
     ctx->need_rebuild = true;
+    ctx->need_maxvel = true;
     return DEM_OK;
 }
 
@@ -928,11 +948,19 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
         for (uint64_t i = 0; i < m; i++) {
             Row r;
             r.a = pair[i].x; r.b = pair[i].y;
+            bool flip = false;
+            if (which == 0 && r.a > r.b) { std::swap(r.a, r.b); flip = true; }
             if (which == 0) r.t = DEM_CNT_SPHERE_SPHERE;
             else r.t = (ctx->h_anal[pair[i].y].type == DEM_ANAL_PLANE) ? DEM_CNT_SPHERE_PLANE : DEM_CNT_SPHERE_CYL;
             // history words of contacts that are not alive are stale by construction: report zeros
             r.h = (ci[i].w & 0x80000000u) ? hist[i] : make_float4(0, 0, 0, 0);
             r.f = frc[i];
+            if (flip) {
+                // the device lists a pair with the sphere that comes first in cell order as A; the reference reports
+                // the smaller sphere id as A. Swapping roles negates delta_tan and the force that "A feels".
+                r.h.x = -r.h.x; r.h.y = -r.h.y; r.h.z = -r.h.z;
+                r.f.x = -r.f.x; r.f.y = -r.f.y; r.f.z = -r.f.z;
+            }
             rows.push_back(r);
         }
     }
@@ -983,6 +1011,9 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
     else if (n == "blocked_partition") ctx->blocked = value != 0.0;
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
+    else if (n == "prefetch_mode") ctx->prefetch_mode = (int)value;
+    else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
+    else if (n == "sort_mode") ctx->sort_mode = (int)value;
     else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);
     return DEM_OK;
 }
@@ -1013,6 +1044,7 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
         if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
         CK(cudaEventRecord(ctx->ev[3], s));
         launch_integrate(P, s);
+        ctx->maxvel_slot ^= 1;
         CK(cudaEventRecord(ctx->ev[4], s));
         ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
         ctx->n_steps++;

@@ -101,9 +101,12 @@ struct DevParams {
     uint32_t nOwners, nSpheres, nAnal, nTri, nMat;
     // margin policy
     float beta, approxMaxVel, expSafetyMulti, expSafetyAdder;
-    float drift_h;  // h * maxDrift as the reference forms it: (double)(..)*ts*maxDrift, evaluated per owner
+    float errOutVel;
     uint32_t maxDrift;
     uint32_t blocked_partition;  // force kernel: contiguous slice per CTA (1) or grid-stride (0)
+    uint32_t prefetch_mode;      // force kernel: 0 none, 1 prefetch.global.L2, 2 prefetch.global.L1 of the next owners
+    uint32_t fast_encode;        // integrator: division-free position encode
+    double inv_voxelSize;
     // owners
     OwnerState* state;
     Wrench* wrench;
@@ -123,9 +126,10 @@ struct DevParams {
     const Prescr* presc;
     // contact lists
     ContactList ss, sa, st;
-    // status flags (device): [0] capacity overflow, [1] non-finite / too-fast owner, [2] cell overflow
+    // status flags (device): [0] capacity overflow, [1] non-finite / too-fast owner, [2] staging overflow in the sweep
     uint32_t* flags;
-    float* maxvel;  // device float: max |v| seen by the last margin pass
+    float* maxvel;       // device float: max |v| of the current state (kept up to date by the integrator)
+    float* maxvel_next;  // the slot the NEXT step will accumulate into (zeroed by this step's integrator)
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -181,6 +185,28 @@ __device__ __forceinline__ void pos_encode(OwnerPos& p, const DevParams& P, doub
     p.ly = (unsigned short)((Y - (double)ny * P.voxelSize) / P.l);
     p.lz = (unsigned short)((Z - (double)nz * P.voxelSize) / P.l);
     p.voxel = nx + (ny << P.nvXp2) + (nz << (P.nvXp2 + P.nvYp2));
+}
+
+// Same truncating encode without the six double-precision divisions: quotient by reciprocal multiply, then an exact
+// fused-multiply-add remainder corrects it to floor(X / voxelSize) and floor(rem / l). Identical to pos_encode except
+// when a quotient lies within one rounding error of an integer (where the reference's own rounded division decides).
+__device__ __forceinline__ void pos_encode_fast(OwnerPos& p, const DevParams& P, double X, double Y, double Z) {
+    const double c[3] = {X, Y, Z};
+    unsigned long long n[3];
+    unsigned int sub[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        long long q = (long long)(c[k] * P.inv_voxelSize);
+        double r = fma(-(double)q, P.voxelSize, c[k]);
+        if (r < 0.0) { q--; r += P.voxelSize; } else if (r >= P.voxelSize) { q++; r -= P.voxelSize; }
+        int sq = (int)(r * P.inv_l);
+        const double rr = fma(-(double)sq, P.l, r);
+        if (rr < 0.0) sq--; else if (rr >= P.l) sq++;
+        n[k] = (unsigned long long)q;
+        sub[k] = (unsigned int)min(max(sq, 0), 65535);
+    }
+    p.lx = (unsigned short)sub[0]; p.ly = (unsigned short)sub[1]; p.lz = (unsigned short)sub[2];
+    p.voxel = n[0] + (n[1] << P.nvXp2) + (n[2] << (P.nvXp2 + P.nvYp2));
 }
 
 __device__ __forceinline__ uint32_t mask_pair(uint32_t i, uint32_t j) {

@@ -12,6 +12,16 @@ struct GridInfo {
     float max_margin, maxvel;
 };
 
+// analytical component resolved to world space for one rebuild
+struct __align__(16) AnalWorld {
+    float px, py, pz;  // plane point / cylinder centre (LBF-relative)
+    float dx, dy, dz;  // plane normal / cylinder axis
+    float margin;      // margin of the owning body
+    float size1;
+    float normal_sign;
+    uint32_t type, family, material;
+};
+
 // scratch + in/out of one contact-list rebuild
 struct CdParams {
     GridInfo* grid;
@@ -26,9 +36,8 @@ struct CdParams {
     uint32_t* vals[2];
     uint32_t* cellStart;  // ncells+1 (histogram, then exclusive prefix)
     float4* sortedSph;
-    uint2* sortedMeta;    // {owner, sphere id}
-    uint32_t* cnt;        // per sorted sphere contact count / offsets (nSpheres+1)
-    uint32_t* saCnt;      // per sphere analytical contact count / offsets (nSpheres+1)
+    uint4* sortedMeta;    // {owner, sphere id, comp | material<<16, family}
+    AnalWorld* analw;
     ContactList oldss, oldsa;
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the scans
@@ -39,7 +48,7 @@ void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaS
 void launch_integrate(const DevParams& P, cudaStream_t s);
 
 // rebuild stages; each returns the number of kernels it launched
-int launch_cd_prepare(const DevParams& P, const CdParams& C, cudaStream_t s);
+int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, cudaStream_t s);
 int launch_cd_sort(const DevParams& P, const CdParams& C, int key_bits, cudaStream_t s, int* out_buf);
 int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev = nullptr);
 int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* total, cudaStream_t s);

@@ -1,14 +1,17 @@
 // kernels_cd.cu -- contact-list rebuild ("kinematic" work) for sm_100a, fully device-driven (no host round trips
 // between the stages):
-//   k_maxvel / k_grid_setup      max |v| -> margin -> broad-phase cell size and grid, decided ON the device
+//   k_maxvel / k_grid_setup      max |v| -> margin -> broad-phase cell size and grid, decided ON the device; also
+//                                resolves the analytical components (planes, cylinders) to world space once
 //   k_sphere_prep                per sphere: world position (fixed-point decode + rotated offset), inflated radius,
-//                                cell key + cell histogram, sphere--analytical candidate count
+//                                cell key + cell histogram; emits the sphere--analytical list (+history) directly
+//                                with warp-aggregated atomics
 //   radix sort (k_rs_*)          LSD, 8-bit digits, tile ranking with warp match + shared-memory staged coalesced scatter
 //   scan (k_scan_*)              exclusive prefix sums (cell table, per-sphere contact offsets, sort histograms)
 //   k_gather_sorted              cell-ordered float4 {x,y,z,r'} + {owner,id}
-//   k_sweep<FILL>                27-cell sweep over 9 contiguous rows; count pass + fill pass; the fill pass compiles the
-//                                per-contact record and carries the Hertz-Mindlin history over from the previous list
-//   k_sa_fill                    sphere--analytical list + history
+//   k_sweep                      ONE pass over the upper half of the 27-cell stencil (5 contiguous runs of the sorted array
+//                                instead of 9): distance test on the float4 stream first, accepted candidates staged per
+//                                thread, slots claimed with one warp-aggregated atomic, then the compiled per-contact
+//                                record is written and the Hertz-Mindlin history carried over from the previous list
 // Reference behaviour being reproduced: contactDetection(), src/algorithms/DEMCubContactDetection.cu:38-1123;
 // acceptance rule of src/kernel/DEMContactKernels_SphereSphere.cu:57-89,172-214 and DEMBinSphereKernels.cu:78-128;
 // margin of src/kernel/DEMMiscKernels.cu:37-69; history map of src/kernel/DEMHistoryMappingKernels.cu.
@@ -33,7 +36,7 @@ __global__ void k_maxvel(const __grid_constant__ DevParams P, float errOutVel) {
     if (o < P.nOwners) {
         const float4 v = P.state[o].vel;
         a = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-        if (!isfinite(a) || a > errOutVel) atomicOr(&P.flags[1], 1u);
+        if (!isfinite(a) || a > errOutVel) atomicOr(&P.flags[3], 1u);
         if (!isfinite(a)) a = 0.f;
     }
 #pragma unroll
@@ -71,68 +74,151 @@ __global__ void k_grid_setup(const __grid_constant__ DevParams P, const __grid_c
     *C.grid = g;
 }
 
-// sphere--analytical candidate test with inflated geometry (DEMBinSphereKernels.cu:78-128). Conservative in float.
-__device__ __forceinline__ bool sa_candidate(const DevParams& P, const AnalObj& ob, float3 sp /*LBF-rel*/, float rInfl,
-                                             uint32_t famS, bool any_mask) {
+// World-space analytical components of this rebuild (plane point / cylinder centre, direction, owner margin, family)
+__global__ void k_anal_prep(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= P.nAnal) return;
+    const AnalObj ob = P.anal[k];
     const OwnerState* sb = P.state + ob.owner;
     const OwnerPos pB = sb->pos;
-    if (any_mask && P.familyMasks[mask_pair(famS, pB.family)] != 0) return false;
     const float4 qB = sb->quat;
     const float4 vB = sb->vel;
-    const float mB = owner_margin(P, sqrtf(vB.x * vB.x + vB.y * vB.y + vB.z * vB.z), pB.family);
     double X, Y, Z;
     pos_decode(pB, P, X, Y, Z);
     const float3 rel = rotate(f3(ob.relx, ob.rely, ob.relz), qB);
     const float3 dir = rotate(f3(ob.rotx, ob.roty, ob.rotz), qB);
-    const float3 d = f3(sp.x - (float)(X + (double)rel.x), sp.y - (float)(Y + (double)rel.y),
-                        sp.z - (float)(Z + (double)rel.z));
-    const float thr = fminf(P.familyExtraMargin[famS], P.familyExtraMargin[pB.family]);
+    AnalWorld w;
+    w.px = (float)(X + (double)rel.x); w.py = (float)(Y + (double)rel.y); w.pz = (float)(Z + (double)rel.z);
+    w.dx = dir.x; w.dy = dir.y; w.dz = dir.z;
+    w.margin = owner_margin(P, sqrtf(vB.x * vB.x + vB.y * vB.y + vB.z * vB.z), pB.family);
+    w.size1 = ob.size1;
+    w.normal_sign = ob.normal_sign;
+    w.type = ob.type;
+    w.family = pB.family;
+    w.material = ob.material;
+    C.analw[k] = w;
+}
+
+// sphere--analytical candidate test with inflated geometry (DEMBinSphereKernels.cu:78-128). Conservative in float.
+__device__ __forceinline__ bool sa_candidate(const DevParams& P, const AnalWorld& w, float3 sp /*LBF-rel*/, float rInfl,
+                                             uint32_t famS, bool any_mask) {
+    if (any_mask && P.familyMasks[mask_pair(famS, w.family)] != 0) return false;
+    const float3 d = f3(sp.x - w.px, sp.y - w.py, sp.z - w.pz);
+    const float3 dir = f3(w.dx, w.dy, w.dz);
+    const float thr = fminf(P.familyExtraMargin[famS], P.familyExtraMargin[w.family]);
     const float slack = 1e-6f * (fabsf(sp.x) + fabsf(sp.y) + fabsf(sp.z) + 1.f);
     float depth;
-    if (ob.type == DEM_ANAL_PLANE) {
-        depth = rInfl + mB - dot(d, dir);
-    } else if (ob.type == DEM_ANAL_CYL_INF) {
+    if (w.type == DEM_ANAL_PLANE) {
+        depth = rInfl + w.margin - dot(d, dir);
+    } else if (w.type == DEM_ANAL_CYL_INF) {
         const float3 s2c = f3(-d.x, -d.y, -d.z);
         const float proj = dot(s2c, dir);
         const float3 radial = s2c - proj * dir;
-        const float cyl_rad = ob.size1 - ob.normal_sign * mB;
-        depth = rInfl - ob.normal_sign * (cyl_rad - length(radial));
+        const float cyl_rad = w.size1 - w.normal_sign * w.margin;
+        depth = rInfl - w.normal_sign * (cyl_rad - length(radial));
     } else {
         return false;
     }
     return depth + slack > thr;
 }
 
+// exclusive warp scan of a count + one atomic per warp on a global cursor: returns this lane's first slot
+__device__ __forceinline__ uint32_t warp_claim(uint32_t count, uint32_t* cursor) {
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = count;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - count;
+}
+
 __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ CdParams C) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nSpheres) return;
-    const GridInfo g = *C.grid;
-    const uint2 s = P.sph[i];
-    const OwnerState* st = P.state + s.x;
-    const OwnerPos pos = st->pos;
-    const float4 q = st->quat;
-    const float4 v = st->vel;
-    const float4 comp = __ldg(&P.comp[s.y & 0xffffu]);
-    const float margin = owner_margin(P, sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), pos.family);
-    double X, Y, Z;
-    pos_decode(pos, P, X, Y, Z);
-    const float3 rel = rotate(f3(comp.x, comp.y, comp.z), q);
-    const float3 sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
-    const float rInfl = comp.w + margin;
-    C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
-    int cx = (int)floorf(sp.x * g.inv_cs), cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
-    cx = min(max(cx, 0), (int)g.nbx - 1);
-    cy = min(max(cy, 0), (int)g.nby - 1);
-    cz = min(max(cz, 0), (int)g.nbz - 1);
-    const uint32_t key = (uint32_t)cx + g.nbx * ((uint32_t)cy + g.nby * (uint32_t)cz);
-    C.keys[0][i] = key;
-    C.vals[0][i] = i;
-    atomicAdd(&C.cellStart[key], 1u);
-    uint32_t nsa = 0;
-    for (uint32_t k = 0; k < P.nAnal; k++)
-        if (sa_candidate(P, P.anal[k], sp, rInfl, pos.family, C.any_mask != 0)) nsa++;
-    C.saCnt[i] = nsa;
+    const bool valid = i < P.nSpheres;
+    uint32_t nsa = 0, samask = 0;
+    float3 sp = f3(0.f, 0.f, 0.f);
+    uint2 s = make_uint2(0, 0);
+    uint32_t family = 0;
+    if (valid) {
+        const GridInfo g = *C.grid;
+        s = P.sph[i];
+        OwnerPos pos;
+        float4 q, v;
+        {
+            const float* base = reinterpret_cast<const float*>(P.state + s.x);
+            uint32_t a0, a1, a2, a3;
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                         : "l"(base));
+            pos.voxel = ((unsigned long long)a1 << 32) | a0;
+            pos.lx = (unsigned short)(a2 & 0xffffu); pos.ly = (unsigned short)(a2 >> 16);
+            pos.lz = (unsigned short)(a3 & 0xffffu); pos.family = (unsigned char)((a3 >> 16) & 0xffu);
+            pos.flags = 0;
+            v = __ldg(&P.state[s.x].vel);
+        }
+        family = pos.family;
+        const float4 comp = __ldg(&P.comp[s.y & 0xffffu]);
+        const float margin = owner_margin(P, sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), pos.family);
+        double X, Y, Z;
+        pos_decode(pos, P, X, Y, Z);
+        const float3 rel = rotate(f3(comp.x, comp.y, comp.z), q);
+        sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
+        const float rInfl = comp.w + margin;
+        C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
+        int cx = (int)floorf(sp.x * g.inv_cs), cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
+        cx = min(max(cx, 0), (int)g.nbx - 1);
+        cy = min(max(cy, 0), (int)g.nby - 1);
+        cz = min(max(cz, 0), (int)g.nbz - 1);
+        const uint32_t key = (uint32_t)cx + g.nbx * ((uint32_t)cy + g.nby * (uint32_t)cz);
+        C.keys[0][i] = key;
+        C.vals[0][i] = i;
+        // cell histogram; the arrival rank doubles as the slot of the counting sort (made deterministic afterwards)
+        C.vals[1][i] = atomicAdd(&C.cellStart[key], 1u);
+        // analytical candidates (at most 32 components are tracked per sphere in the bit mask; more fall back below)
+        for (uint32_t k = 0; k < P.nAnal; k++)
+            if (sa_candidate(P, C.analw[k], sp, rInfl, family, C.any_mask != 0)) {
+                if (k < 32) samask |= 1u << k;
+                nsa++;
+            }
+    }
+    if (P.nAnal == 0) return;
+    // ---- emit the sphere--analytical contacts of this warp into one contiguous run ----
+    uint32_t slot = warp_claim(nsa, P.sa.count);
+    if (!valid) return;
+    P.sa.seg_start[i] = slot;
+    P.sa.seg_count[i] = (slot + nsa <= C.capacity) ? nsa : (slot < C.capacity ? C.capacity - slot : 0u);
+    if (nsa == 0) return;
+    if (slot + nsa > C.capacity) atomicOr(&P.flags[0], 2u);
+    const uint32_t oldStart = C.oldsa.seg_start[i], oldCount = C.oldsa.seg_count[i];
+    for (uint32_t k = 0; k < P.nAnal; k++) {
+        bool hit;
+        if (k < 32) hit = (samask >> k) & 1u;
+        else hit = sa_candidate(P, C.analw[k], sp, C.sphF[i].w, family, C.any_mask != 0);
+        if (!hit) continue;
+        if (slot < C.capacity) {
+            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+            uint32_t alive = 0;
+            for (uint32_t t = 0; t < oldCount; t++) {
+                if (C.oldsa.pair[oldStart + t].y == k) {
+                    alive = C.oldsa.cinfo[oldStart + t].w & 0x80000000u;
+                    if (alive && C.oldsa.hist) h = C.oldsa.hist[oldStart + t];
+                    break;
+                }
+            }
+            const uint32_t matpair = (s.y >> 16) * P.nMat + C.analw[k].material;
+            P.sa.pair[slot] = make_uint2(i, k);
+            P.sa.cinfo[slot] = make_uint4(s.x, k, s.y & 0xffffu, matpair | alive);
+            if (P.sa.hist) P.sa.hist[slot] = h;
+        }
+        slot++;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -351,139 +437,147 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ D
     if (j >= P.nSpheres) return;
     const uint32_t i = vals[j];
     C.sortedSph[j] = C.sphF[i];
-    C.sortedMeta[j] = make_uint2(P.sph[i].x, i);
+    const uint2 s = P.sph[i];
+    uint32_t fam = 0;
+    if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
+    C.sortedMeta[j] = make_uint4(s.x, i, s.y, fam);  // {owner, sphere id, comp | material<<16, family}
 }
 
-// The 27-cell sweep.  Cells are x-fastest, so the 3 x-neighbours of a row are ONE contiguous run of the sorted
-// array: 9 runs per sphere, each delimited by two reads of the exclusive-prefix cell table.
-template <bool FILL>
+// ---- counting sort by cell (sort_mode 1): the histogram and its prefix exist anyway for the sweep ----
+__global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevParams P,
+                                                    const __grid_constant__ CdParams C) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.nSpheres) return;
+    C.keys[1][C.cellStart[C.keys[0][i]] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
+}
+
+// gather into cell order; inside a cell the spheres are ranked by sphere id, which makes the result identical to a
+// stable radix sort of (cell key, sphere id) no matter in which order the atomics arrived
+__global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant__ DevParams P,
+                                                          const __grid_constant__ CdParams C) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.nSpheres) return;
+    const uint32_t i = C.keys[1][j];
+    const uint32_t key = C.keys[0][i];
+    const uint32_t sb = C.cellStart[key], se = C.cellStart[key + 1];
+    uint32_t rank = 0;
+    for (uint32_t t = sb; t < se; t++) rank += (C.keys[1][t] < i) ? 1u : 0u;
+    const uint32_t dst = sb + rank;
+    C.sortedSph[dst] = C.sphF[i];
+    const uint2 s = P.sph[i];
+    uint32_t fam = 0;
+    if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
+    C.sortedMeta[dst] = make_uint4(s.x, i, s.y, fam);
+    C.vals[0][dst] = key;  // sorted keys for the sweep
+}
+
+constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half stencil)
+
+// The sweep.  Cells are x-fastest, so the x-neighbours of a row are ONE contiguous run of the cell-sorted array.
+// Each sphere looks only "forward" (upper half of the 27-cell stencil => 5 runs, the own row starting right behind
+// itself), so every pair is found exactly once by the sphere that comes first in the sorted order; that sphere is
+// geometry A of the contact.
 __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams P,
                                                const __grid_constant__ CdParams C,
                                                const uint32_t* __restrict__ keys) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.nSpheres) return;
-    const GridInfo g = *C.grid;
-    const float4 me = C.sortedSph[j];
-    const uint2 meta = C.sortedMeta[j];
-    const uint32_t key = keys[j];
-    const int cx = (int)(key % g.nbx);
-    const int cy = (int)((key / g.nbx) % g.nby);
-    const int cz = (int)(key / (g.nbx * g.nby));
-    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
-    const bool any_mask = C.any_mask != 0;
-    uint32_t famA = 0;
-    float extraA = 0.f;
-    if (any_mask || C.max_extra > 0.f) {
-        famA = P.state[meta.x].pos.family;
-        extraA = P.familyExtraMargin[famA];
-    }
+    const bool valid = j < P.nSpheres;
+    uint32_t acc[SWEEP_MAXC];
     uint32_t count = 0;
-    uint32_t out = 0, oldStart = 0, oldCount = 0, myComp = 0;
-    if (FILL) {
-        out = C.cnt[j];
-        oldStart = C.oldss.seg_start[meta.y];
-        oldCount = C.oldss.seg_count[meta.y];
-        myComp = P.sph[meta.y].y;
-    }
-    for (int dz = -1; dz <= 1; dz++) {
-        const int z = cz + dz;
-        if (z < 0 || z >= (int)g.nbz) continue;
-        for (int dy = -1; dy <= 1; dy++) {
-            const int y = cy + dy;
-            if (y < 0 || y >= (int)g.nby) continue;
+    uint4 meta = make_uint4(0, 0, 0, 0);
+    if (valid) {
+        const GridInfo g = *C.grid;
+        const float4 me = C.sortedSph[j];
+        meta = C.sortedMeta[j];
+        const uint32_t key = keys[j];
+        const int cx = (int)(key % g.nbx);
+        const int cy = (int)((key / g.nbx) % g.nby);
+        const int cz = (int)(key / (g.nbx * g.nby));
+        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
+        const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
+        const float extraA = fam_on ? P.familyExtraMargin[meta.w] : 0.f;
+#pragma unroll 1
+        for (int r = 0; r < 5; r++) {
+            // r=0: own row behind me; r=1: (dy=+1,dz=0); r=2..4: (dy=-1,0,+1; dz=+1)
+            const int dy = (r == 0) ? 0 : (r == 1 ? 1 : r - 3);
+            const int dz = (r < 2) ? 0 : 1;
+            const int y = cy + dy, z = cz + dz;
+            if (y < 0 || y >= (int)g.nby || z >= (int)g.nbz) continue;
             const uint32_t row = g.nbx * ((uint32_t)y + g.nby * (uint32_t)z);
-            const uint32_t qb = C.cellStart[row + x0], qe = C.cellStart[row + x1 + 1];
+            const uint32_t qb = (r == 0) ? j + 1 : C.cellStart[row + x0];
+            const uint32_t qe = C.cellStart[row + x1 + 1];
             for (uint32_t q = qb; q < qe; q++) {
-                const uint2 om = C.sortedMeta[q];
-                // A is the sphere with the smaller id (the reference emits ascending sphere ids within a bin)
-                if (om.y <= meta.y || om.x == meta.x) continue;
-                const float4 ot = C.sortedSph[q];
+                const float4 ot = __ldg(&C.sortedSph[q]);
                 const float dx = me.x - ot.x, dy2 = me.y - ot.y, dz2 = me.z - ot.z;
                 const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
                 const float R = me.w + ot.w;
                 // superset of the double-precision test d2 <= R^2 && R - d > min(extraA, extraB)
-                float Rt = R;
-                uint32_t famB = 0;
-                if (any_mask || C.max_extra > 0.f) {
-                    famB = P.state[om.x].pos.family;
-                    if (any_mask && P.familyMasks[mask_pair(famA, famB)] != 0) continue;
-                    Rt = R - fminf(extraA, P.familyExtraMargin[famB]);
+                if (d2 > R * R * 1.000001f + 1e-20f) continue;
+                const uint4 om = __ldg(&C.sortedMeta[q]);
+                if (om.x == meta.x) continue;  // same owner
+                if (fam_on) {
+                    if (C.any_mask && P.familyMasks[mask_pair(meta.w, om.w)] != 0) continue;
+                    const float Rt = R - fminf(extraA, P.familyExtraMargin[om.w]);
+                    if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
                 }
-                if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
-                if (FILL) {
-                    const uint32_t slot = out + count;
-                    if (slot < C.capacity) {
-                        const uint32_t compB = P.sph[om.y].y;
-                        const uint32_t nM = P.nMat;
-                        const uint32_t matpair = (myComp >> 16) * nM + (compB >> 16);
-                        // history carry-over: look (A,B) up in A's segment of the previous list
-                        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-                        uint32_t alive = 0;
-                        for (uint32_t t = 0; t < oldCount; t++) {
-                            if (C.oldss.pair[oldStart + t].y == om.y) {
-                                alive = C.oldss.cinfo[oldStart + t].w & 0x80000000u;
-                                if (alive && C.oldss.hist) h = C.oldss.hist[oldStart + t];
-                                break;
-                            }
-                        }
-                        P.ss.pair[slot] = make_uint2(meta.y, om.y);
-                        P.ss.cinfo[slot] =
-                            make_uint4(meta.x, om.x, (myComp & 0xffffu) | ((compB & 0xffffu) << 16), matpair | alive);
-                        if (P.ss.hist) P.ss.hist[slot] = h;
-                    }
-                }
+                if (count < SWEEP_MAXC) acc[count] = q;
                 count++;
             }
         }
+        if (count > SWEEP_MAXC) {
+            atomicOr(&P.flags[2], 1u);  // more forward contacts on one sphere than can be staged
+            count = SWEEP_MAXC;
+        }
     }
-    if (FILL) {
-        P.ss.seg_start[meta.y] = out;
-        P.ss.seg_count[meta.y] = (out + count <= C.capacity) ? count : (out < C.capacity ? C.capacity - out : 0u);
-    } else {
-        C.cnt[j] = count;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_sa_fill(const __grid_constant__ DevParams P,
-                                                 const __grid_constant__ CdParams C) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nSpheres) return;
-    const uint32_t out = C.saCnt[i], end = C.saCnt[i + 1];
-    P.sa.seg_start[i] = out;
-    P.sa.seg_count[i] = (end <= C.capacity) ? end - out : (out < C.capacity ? C.capacity - out : 0u);
-    if (end == out) return;
-    const float4 me = C.sphF[i];
-    const uint2 s = P.sph[i];
-    const uint32_t fam = P.state[s.x].pos.family;
-    const uint32_t oldStart = C.oldsa.seg_start[i], oldCount = C.oldsa.seg_count[i];
-    uint32_t k = 0;
-    for (uint32_t ob = 0; ob < P.nAnal; ob++) {
-        const AnalObj a = P.anal[ob];
-        if (!sa_candidate(P, a, f3(me.x, me.y, me.z), me.w, fam, C.any_mask != 0)) continue;
-        const uint32_t slot = out + k;
-        if (slot < C.capacity) {
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t alive = 0;
-            for (uint32_t t = 0; t < oldCount; t++) {
-                if (C.oldsa.pair[oldStart + t].y == ob) {
-                    alive = C.oldsa.cinfo[oldStart + t].w & 0x80000000u;
-                    if (alive && C.oldsa.hist) h = C.oldsa.hist[oldStart + t];
+    uint32_t slot = warp_claim(count, P.ss.count);
+    if (!valid) return;
+    P.ss.seg_start[meta.y] = slot;
+    P.ss.seg_count[meta.y] = (slot + count <= C.capacity) ? count : (slot < C.capacity ? C.capacity - slot : 0u);
+    if (count == 0) return;
+    if (slot + count > C.capacity) atomicOr(&P.flags[0], 1u);
+    const uint32_t oldStartA = C.oldss.seg_start[meta.y], oldCountA = C.oldss.seg_count[meta.y];
+    const uint32_t nM = P.nMat;
+    for (uint32_t k = 0; k < count; k++, slot++) {
+        if (slot >= C.capacity) break;
+        const uint4 om = __ldg(&C.sortedMeta[acc[k]]);
+        // history carry-over (DEMHistoryMappingKernels.cu): the pair may sit in the previous list as (A,B) or --
+        // when the two spheres swapped their order in the sorted array -- as (B,A); then delta_tan changes sign.
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t alive = 0;
+        bool found = false;
+        for (uint32_t t = 0; t < oldCountA; t++) {
+            if (C.oldss.pair[oldStartA + t].y == om.y) {
+                alive = C.oldss.cinfo[oldStartA + t].w & 0x80000000u;
+                if (alive && C.oldss.hist) h = C.oldss.hist[oldStartA + t];
+                found = true;
+                break;
+            }
+        }
+        if (!found) {
+            const uint32_t oldStartB = C.oldss.seg_start[om.y], oldCountB = C.oldss.seg_count[om.y];
+            for (uint32_t t = 0; t < oldCountB; t++) {
+                if (C.oldss.pair[oldStartB + t].y == meta.y) {
+                    alive = C.oldss.cinfo[oldStartB + t].w & 0x80000000u;
+                    if (alive && C.oldss.hist) {
+                        h = C.oldss.hist[oldStartB + t];
+                        h.x = -h.x; h.y = -h.y; h.z = -h.z;
+                    }
                     break;
                 }
             }
-            const uint32_t matpair = (s.y >> 16) * P.nMat + a.material;
-            P.sa.pair[slot] = make_uint2(i, ob);
-            P.sa.cinfo[slot] = make_uint4(s.x, ob, s.y & 0xffffu, matpair | alive);
-            if (P.sa.hist) P.sa.hist[slot] = h;
         }
-        k++;
+        const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
+        P.ss.pair[slot] = make_uint2(meta.y, om.y);
+        P.ss.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | alive);
+        if (P.ss.hist) P.ss.hist[slot] = h;
     }
 }
 
-__global__ void k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C,
-                                const uint32_t* __restrict__ ssTotal, const uint32_t* __restrict__ saTotal) {
+__global__ void k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t a = *ssTotal, b = *saTotal;
+        uint32_t a = *P.ss.count, b = *P.sa.count;
+        P.ss.count[1] = a;  // the unclamped demand, read back by the host to size a regrow
+        P.sa.count[1] = b;
         if (a > C.capacity) { atomicOr(&P.flags[0], 1u); a = C.capacity; }
         if (b > C.capacity) { atomicOr(&P.flags[0], 2u); b = C.capacity; }
         *P.ss.count = a;
@@ -492,16 +586,25 @@ __global__ void k_finish_counts(const __grid_constant__ DevParams P, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int launch_cd_prepare(const DevParams& P, const CdParams& C, cudaStream_t s) {
+int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, cudaStream_t s) {
     int launches = 0;
-    cudaMemsetAsync(P.maxvel, 0, sizeof(float), s);
-    if (P.nOwners) {
-        k_maxvel<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, 3.0e38f);
-        launches++;
+    if (need_maxvel) {
+        // velocities changed outside the integrator (initial state / host upload): recompute max |v|
+        cudaMemsetAsync(P.maxvel, 0, sizeof(float), s);
+        if (P.nOwners) {
+            k_maxvel<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, P.errOutVel);
+            launches++;
+        }
     }
     k_grid_setup<<<1, 32, 0, s>>>(P, C);
     launches++;
+    if (P.nAnal) {
+        k_anal_prep<<<(P.nAnal + 63) / 64, 64, 0, s>>>(P, C);
+        launches++;
+    }
     cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+    cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
+    cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
     if (P.nSpheres) {
         k_sphere_prep<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, C);
         launches++;
@@ -514,27 +617,25 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
     const uint32_t n = P.nSpheres;
     // cell histogram -> exclusive prefix (ncells+1 entries; scanning the full capacity keeps the launch shape static)
     launches += launch_scan_exclusive(C.cellStart, C.max_cells + 1, C.scan_tmp, nullptr, s);
-    // totals live right behind the per-sphere offsets: cnt[n], saCnt[n]
+    if (ev) cudaEventRecord(ev[0], s);
     if (n) {
-        k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(P, C, C.vals[sorted_buf]);
-        if (ev) cudaEventRecord(ev[0], s);
-        k_sweep<false><<<(n + 127) / 128, 128, 0, s>>>(P, C, C.keys[sorted_buf]);
+        if (sorted_buf < 0) {  // counting sort
+            k_cs_scatter<<<(n + 255) / 256, 256, 0, s>>>(P, C);
+            k_gather_sorted_cs<<<(n + 255) / 256, 256, 0, s>>>(P, C);
+            launches++;
+        } else {
+            k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(P, C, C.vals[sorted_buf]);
+        }
         if (ev) cudaEventRecord(ev[1], s);
+        k_sweep<<<(n + 127) / 128, 128, 0, s>>>(P, C, sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf]);
         launches += 2;
-        launches += launch_scan_exclusive(C.cnt, n, C.scan_tmp, C.cnt + n, s);
-        launches += launch_scan_exclusive(C.saCnt, n, C.scan_tmp, C.saCnt + n, s);
-        if (ev) cudaEventRecord(ev[2], s);
-        k_sweep<true><<<(n + 127) / 128, 128, 0, s>>>(P, C, C.keys[sorted_buf]);
-        if (ev) cudaEventRecord(ev[3], s);
-        k_sa_fill<<<(n + 255) / 256, 256, 0, s>>>(P, C);
-        launches += 2;
-    } else {
-        cudaMemsetAsync(C.cnt, 0, sizeof(uint32_t), s);
-        cudaMemsetAsync(C.saCnt, 0, sizeof(uint32_t), s);
-        if (ev) for (int k = 0; k < 4; k++) cudaEventRecord(ev[k], s);
+    } else if (ev) {
+        cudaEventRecord(ev[1], s);
     }
-    k_finish_counts<<<1, 32, 0, s>>>(P, C, C.cnt + n, C.saCnt + n);
+    if (ev) cudaEventRecord(ev[2], s);
+    k_finish_counts<<<1, 32, 0, s>>>(P, C);
     launches++;
+    if (ev) cudaEventRecord(ev[3], s);
     return launches;
 }
 

@@ -137,12 +137,25 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
         end = n;
         step = gridDim.x * blockDim.x;
     }
-    uint4 ci = make_uint4(0, 0, 0, 0);
+    // software pipeline: the compiled record is fetched two iterations ahead; as soon as a record has landed, the
+    // cache lines of its two owner records are pulled towards the SM (prefetch), so the dependent gather of the next
+    // iteration does not pay the full DRAM/L2 latency again.
+    uint4 ci = make_uint4(0, 0, 0, 0), ci_next = make_uint4(0, 0, 0, 0);
     if (c < end) ci = __ldcs(&P.ss.cinfo[c]);  // streaming: evict-first
+    if (c + step < end) ci_next = __ldcs(&P.ss.cinfo[c + step]);
     while (c < end) {
         const uint32_t cn = c + step;
-        uint4 ci_next = make_uint4(0, 0, 0, 0);
-        if (cn < end) ci_next = __ldcs(&P.ss.cinfo[cn]);
+        uint4 ci_next2 = make_uint4(0, 0, 0, 0);
+        if (cn + step < end) ci_next2 = __ldcs(&P.ss.cinfo[cn + step]);
+        if (cn < end && P.prefetch_mode) {
+            if (P.prefetch_mode == 1) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + ci_next.x));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + ci_next.y));
+            } else {
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.state + ci_next.x));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.state + ci_next.y));
+            }
+        }
         const uint32_t oA = ci.x, oB = ci.y;
         const bool alive = (ci.w >> 31) != 0u;
         float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -198,6 +211,7 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
             if (RECORD) P.ss.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         ci = ci_next;
+        ci_next = ci_next2;
         c = cn;
     }
 }
@@ -329,9 +343,7 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
 
 // ---------------------------------------------------------------------------------------------------------------
 // integrateOwners (DEMIntegrationKernels.cu:100-264). One thread per owner, 64-byte state in / out.
-__global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
-    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
-    if (o >= P.nOwners) return;
+__device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_t o) {
     OwnerPos pos;
     End e;
     load_owner(P.state, o, pos, e);
@@ -403,7 +415,7 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
         if (!LinP[k]) X[k] += (double)vp[k] * (double)h;
         X[k] -= (double)P.LBF[k];
     }
-    pos_encode(pos, P, X[0], X[1], X[2]);
+    if (P.fast_encode) pos_encode_fast(pos, P, X[0], X[1], X[2]); else pos_encode(pos, P, X[0], X[1], X[2]);
     float4 q = e.q;
     if (!RotP) {
         const float hh = P.half_h;
@@ -437,7 +449,25 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
     int4* wz = reinterpret_cast<int4*>(P.wrench + o);
     wz[0] = make_int4(0, 0, 0, 0);
     wz[1] = make_int4(0, 0, 0, 0);
+    return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
 }
+
+__global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
+    // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.
+    if (o == 0) *P.maxvel = 0.f;
+    float absv = 0.f;
+    if (o < P.nOwners) {
+        absv = integrate_one(P, o);
+        if (!isfinite(absv) || absv > P.errOutVel) atomicOr(&P.flags[3], 1u);
+        if (!isfinite(absv)) absv = 0.f;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) absv = fmaxf(absv, __shfl_xor_sync(0xffffffffu, absv, off));
+    if ((threadIdx.x & 31) == 0 && absv > 0.f) atomicMax(reinterpret_cast<int*>(P.maxvel_next), __float_as_int(absv));
+}
+
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int MINB>

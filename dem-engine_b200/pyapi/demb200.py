@@ -260,8 +260,7 @@ class Engine:
     def profile_rebuild(self):
         out = (C.c_float * 8)()
         self._ck(self.lib.dem_profile_rebuild(self.ctx, out))
-        names = ["prep_us", "sort_us", "cellscan_gather_us", "sweep_count_us", "offset_scans_us", "sweep_fill_us",
-                 "sa_fill_us", "total_us"]
+        names = ["prep_us", "sort_us", "cellscan_us", "gather_us", "sweep_us", "counts_us", "unused", "total_us"]
         return dict(zip(names, [float(x) for x in out]))
 
     def profile_steps(self, n):

@@ -210,9 +210,9 @@ int dem_set_option(DemCtx* ctx, const char* name, double value);
  * launching stream: [0]=sphere-sphere force kernel [1]=sphere-analytical force kernel [2]=integration kernel
  * [3]=contact rebuild amortised per step [4]=whole step */
 int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]);
-/* One contact-list rebuild with CUDA events between its stages (microseconds): [0] margins + cell keys + histogram
- * [1] radix sort [2] cell-table scan + gather [3] sweep count [4] offset scans [5] sweep fill + history carry-over
- * [6] analytical fill + counts [7] whole rebuild */
+/* One contact-list rebuild with CUDA events between its stages (microseconds): [0] margins + cell keys + histogram +
+ * sphere-analytical list [1] sort [2] cell-table scan [3] gather [4] sweep (+ history carry-over) [5] counts
+ * [6] unused [7] whole rebuild */
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]);
 
 #ifdef __cplusplus

@@ -29,17 +29,27 @@ eng.step(args.settle_steps)
 print("settled %d steps in %.1f s" % (args.settle_steps, time.time() - t0), flush=True)
 st = eng.stats()
 print("contacts ss %d sa %d cells %s cs %.5f margin %.6f" % (st.n_contacts_ss, st.n_contacts_sa, list(st.n_cells), st.cell_size, st.max_margin))
-for blocked in (1, 0):
-    for ctas in (2, 3, 4):
-        eng.set_option("blocked_partition", blocked)
-        eng.set_option("ctas_per_sm", ctas)
-        eng.profile_steps(20)
-        r = eng.profile_steps(args.steps)
-        print("blocked=%d ctas_per_sm=%d  %s" % (blocked, ctas, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
-eng.set_option("blocked_partition", 1)
+for fe in (0, 1):
+    eng.set_option("fast_encode", fe)
+    eng.profile_steps(20)
+    r = eng.profile_steps(args.steps)
+    print("fast_encode=%d  %s" % (fe, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
+for blocked in (0, 1):
+    for pf in (0, 1, 2):
+        for ctas in (2, 3):
+            eng.set_option("blocked_partition", blocked)
+            eng.set_option("ctas_per_sm", ctas)
+            eng.set_option("prefetch_mode", pf)
+            eng.profile_steps(20)
+            r = eng.profile_steps(args.steps)
+            print("blocked=%d prefetch=%d ctas_per_sm=%d  %s" % (blocked, pf, ctas, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
+eng.set_option("blocked_partition", 0)
 eng.set_option("ctas_per_sm", 3)
-for i in range(3):
-    print("rebuild", json.dumps({k: round(v, 1) for k, v in eng.profile_rebuild().items()}), flush=True)
+eng.set_option("prefetch_mode", 1)
+for sm in (0, 1):
+    eng.set_option("sort_mode", sm)
+    for i in range(2):
+        print("sort_mode", sm, "rebuild", json.dumps({k: round(v, 1) for k, v in eng.profile_rebuild().items()}), flush=True)
 t0 = time.time()
 eng.step(2000)
 print("2000 steps wall %.3f s -> %.1f steps/s" % (time.time() - t0, 2000 / (time.time() - t0)))
