@@ -52,6 +52,7 @@ struct DemCtx {
     std::vector<float> h_extra;
     std::vector<Prescr> h_presc;
     std::vector<OwnerState> h_state;
+    std::vector<float4> h_spin;
     std::vector<uint2> h_sph;
     std::vector<uint16_t> h_sph_comp, h_sph_mat;
     std::vector<uint32_t> h_sph_owner;
@@ -63,6 +64,7 @@ struct DemCtx {
 
     // device arrays
     OwnerState* d_state = nullptr;
+    float4* d_spin = nullptr;
     Wrench* d_wrench = nullptr;
     Wrench* d_acc = nullptr;
     uint2* d_sph = nullptr;
@@ -76,7 +78,9 @@ struct DemCtx {
     uint32_t* d_flags = nullptr;
     float* d_maxvel = nullptr;
     double* d_reduce = nullptr;
-    ListBuf ss[2], sa[2];
+    // contact lists [kind][buffer]: kind 0 = sphere-sphere in touch at the last rebuild, 1 = other sphere-sphere
+    // candidates, 2 = sphere-analytical; two buffers each (current / being rebuilt)
+    ListBuf lists[3][2];
     int cur = 0;  // index of the current list buffers
     uint64_t capacity = 0;
     // rebuild scratch
@@ -88,6 +92,7 @@ struct DemCtx {
     float4* d_sortedSph = nullptr;
     uint4* d_sortedMeta = nullptr;
     AnalWorld* d_analw = nullptr;
+    uint32_t* d_sortedPos = nullptr;
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
     uint32_t max_cells = 0;
@@ -102,12 +107,10 @@ struct DemCtx {
     bool need_maxvel = true;  // velocities changed outside the integrator
     int maxvel_slot = 0;
     double sim_time = 0.0;
-    uint64_t n_ss = 0, n_sa = 0;
+    uint64_t n_list[3] = {0, 0, 0};
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
-    int ctas_per_sm = 3;
-    int blocked = 0;
-    int prefetch_mode = 1;
+    int ctas_per_sm = 4;
     int fast_encode = 1;
     int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
@@ -116,6 +119,16 @@ struct DemCtx {
 };
 
 namespace {
+
+// applyOriQToVector3 on the host (reference DEMHelperKernels.cuh:161-173); q = {w,x,y,z}
+float3 host_rotate(float3 v, float4 q) {
+    const float w = q.x, x = q.y, y = q.z, z = q.w;
+    float3 r;
+    r.x = (2.0f * (w * w + x * x) - 1.0f) * v.x + (2.0f * (x * y - w * z)) * v.y + (2.0f * (x * z + w * y)) * v.z;
+    r.y = (2.0f * (x * y + w * z)) * v.x + (2.0f * (w * w + y * y) - 1.0f) * v.y + (2.0f * (y * z - w * x)) * v.z;
+    r.z = (2.0f * (x * z - w * y)) * v.x + (2.0f * (y * z + w * x)) * v.y + (2.0f * (w * w + z * z) - 1.0f) * v.z;
+    return r;
+}
 
 int fail(DemCtx* c, int code, const char* fmt, ...) {
     char buf[1024];
@@ -187,15 +200,14 @@ DevParams make_params(const DemCtx* c) {
     P.beta = s.beta; P.approxMaxVel = s.approxMaxVel; P.expSafetyMulti = s.expSafetyMulti;
     P.expSafetyAdder = s.expSafetyAdder;
     P.maxDrift = s.cd_update_freq;
-    P.state = c->d_state; P.wrench = c->d_wrench; P.acc_out = c->keep_acc ? c->d_acc : nullptr;
-    P.blocked_partition = (uint32_t)c->blocked;
-    P.prefetch_mode = (uint32_t)c->prefetch_mode;
+    P.state = c->d_state; P.spin = c->d_spin; P.wrench = c->d_wrench; P.acc_out = c->keep_acc ? c->d_acc : nullptr;
     P.fast_encode = (uint32_t)c->fast_encode;
     P.inv_voxelSize = 1.0 / s.voxelSize;
     P.sph = c->d_sph; P.comp = c->d_comp; P.massprop = c->d_massprop; P.matpair = c->d_matpair; P.anal = c->d_anal;
     P.familyMasks = c->d_masks; P.familyExtraMargin = c->d_extra; P.presc = c->d_presc;
-    P.ss = as_list(c->ss[c->cur]);
-    P.sa = as_list(c->sa[c->cur]);
+    P.ss = as_list(c->lists[0][c->cur]);
+    P.sn = as_list(c->lists[1][c->cur]);
+    P.sa = as_list(c->lists[2][c->cur]);
     P.flags = c->d_flags;
     P.maxvel = c->d_maxvel + c->maxvel_slot;
     P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
@@ -219,19 +231,22 @@ CdParams make_cd(const DemCtx* c) {
     C.keys[0] = c->d_keys[0]; C.keys[1] = c->d_keys[1]; C.vals[0] = c->d_vals[0]; C.vals[1] = c->d_vals[1];
     C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedMeta = c->d_sortedMeta;
     C.analw = c->d_analw;
-    C.oldss = as_list(c->ss[c->cur]);
-    C.oldsa = as_list(c->sa[c->cur]);
+    C.sortedPos = c->d_sortedPos;
+    C.oldss = as_list(c->lists[0][c->cur]);
+    C.oldsn = as_list(c->lists[1][c->cur]);
+    C.oldsa = as_list(c->lists[2][c->cur]);
     C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp;
     return C;
 }
 
 void free_device(DemCtx* c) {
-    dfree(c->d_state); dfree(c->d_wrench); dfree(c->d_acc); dfree(c->d_sph); dfree(c->d_comp); dfree(c->d_massprop);
+    dfree(c->d_state); dfree(c->d_spin); dfree(c->d_wrench); dfree(c->d_acc); dfree(c->d_sph); dfree(c->d_comp); dfree(c->d_massprop);
     dfree(c->d_matpair); dfree(c->d_anal); dfree(c->d_masks); dfree(c->d_extra); dfree(c->d_presc);
     dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce);
-    for (int k = 0; k < 2; k++) { free_list(c->ss[k]); free_list(c->sa[k]); }
+    for (int kind = 0; kind < 3; kind++)
+        for (int k = 0; k < 2; k++) free_list(c->lists[kind][k]);
     dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
-    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw);
+    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw); dfree(c->d_sortedPos);
     dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
     c->device_bytes = 0;
 }
@@ -240,10 +255,9 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
     const bool hist = ctx->sp.force_model == DEM_HERTZIAN;
     const bool rec = ctx->sp.record_contact_forces != 0;
     int rc;
-    for (int k = 0; k < 2; k++) {
-        if ((rc = alloc_list(ctx, ctx->ss[k], cap, ctx->nSpheres, hist, rec))) return rc;
-        if ((rc = alloc_list(ctx, ctx->sa[k], cap, ctx->nSpheres, hist, rec))) return rc;
-    }
+    for (int kind = 0; kind < 3; kind++)
+        for (int k = 0; k < 2; k++)
+            if ((rc = alloc_list(ctx, ctx->lists[kind][k], cap, ctx->nSpheres, hist, rec))) return rc;
     ctx->capacity = cap;
     return DEM_OK;
 }
@@ -255,9 +269,10 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
     for (int attempt = 0; attempt < 8; attempt++) {
         DevParams P = make_params(ctx);
         CdParams C = make_cd(ctx);
-        // the new list goes to the other buffer pair; the current one is the "old" list (history source)
-        P.ss = as_list(ctx->ss[ctx->cur ^ 1]);
-        P.sa = as_list(ctx->sa[ctx->cur ^ 1]);
+        // the new lists go to the other buffers; the current ones are the "old" lists (history source)
+        P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
+        P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
+        P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
         cudaStream_t s = ctx->stream;
         CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 3, s));  // [3] (velocity) is only cleared by the host
         if (stage_us) cudaEventRecord(sev[0], s);
@@ -269,12 +284,11 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);  // records sev[3..6]
         if (stage_us) cudaEventRecord(sev[7], s);
         ctx->launches += launches;
-        CK(cudaMemcpyAsync(ctx->h_pinned + 0, P.ss.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 1, P.sa.count, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        const ContactList* NL[3] = {&P.ss, &P.sn, &P.sa};
+        for (int kind = 0; kind < 3; kind++)  // {clamped count, demand}
+            CK(cudaMemcpyAsync(ctx->h_pinned + 32 + 2 * kind, NL[kind]->count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_flags, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 24, P.ss.count + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 25, P.sa.count + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         memcpy(&ctx->last_grid, ctx->h_pinned + 8, sizeof(GridInfo));
         ctx->need_maxvel = false;
@@ -289,38 +303,29 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
                         ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
         }
         if (ctx->h_pinned[2] != 0) {
-            // capacity overflow: grow both list pairs, keep the old list (history source) intact, redo
+            // capacity overflow: grow every list, keep the old lists (history source) intact, redo the rebuild
             ctx->overflow_seen++;
-            const uint64_t need = std::max<uint64_t>(ctx->h_pinned[24], ctx->h_pinned[25]);
+            uint64_t need = 0;
+            for (int kind = 0; kind < 3; kind++) need = std::max<uint64_t>(need, ctx->h_pinned[32 + 2 * kind + 1]);
             const uint64_t newcap = std::max<uint64_t>(need + need / 4 + 1024, ctx->capacity * 2);
             if (newcap > 0xfffffff0ull) return fail(ctx, DEM_ERR_CAPACITY, "contact list exceeds 2^32 entries");
-            // only the target buffers must grow for this attempt; the old buffers grow too so later swaps stay valid
-            ListBuf oldss = ctx->ss[ctx->cur], oldsa = ctx->sa[ctx->cur];
             const uint64_t oldcap = ctx->capacity;
             const bool hist = ctx->sp.force_model == DEM_HERTZIAN, rec = ctx->sp.record_contact_forces != 0;
-            free_list(ctx->ss[ctx->cur ^ 1]);
-            free_list(ctx->sa[ctx->cur ^ 1]);
-            int rc;
-            if ((rc = alloc_list(ctx, ctx->ss[ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
-            if ((rc = alloc_list(ctx, ctx->sa[ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
-            ListBuf nss, nsa;
-            if ((rc = alloc_list(ctx, nss, newcap, ctx->nSpheres, hist, rec))) return rc;
-            if ((rc = alloc_list(ctx, nsa, newcap, ctx->nSpheres, hist, rec))) return rc;
-            auto copy_list = [&](ListBuf& dst, const ListBuf& src) -> cudaError_t {
-                cudaError_t e;
-                if ((e = cudaMemcpy(dst.pair, src.pair, sizeof(uint2) * oldcap, cudaMemcpyDeviceToDevice))) return e;
-                if ((e = cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice))) return e;
-                if (src.hist && (e = cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice))) return e;
-                if ((e = cudaMemcpy(dst.seg_start, src.seg_start, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice))) return e;
-                if ((e = cudaMemcpy(dst.seg_count, src.seg_count, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice))) return e;
-                return cudaMemcpy(dst.count, src.count, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice);
-            };
-            CK(copy_list(nss, oldss));
-            CK(copy_list(nsa, oldsa));
-            free_list(oldss);
-            free_list(oldsa);
-            ctx->ss[ctx->cur] = nss;
-            ctx->sa[ctx->cur] = nsa;
+            for (int kind = 0; kind < 3; kind++) {
+                int rc;
+                free_list(ctx->lists[kind][ctx->cur ^ 1]);
+                if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
+                ListBuf src = ctx->lists[kind][ctx->cur], dst;
+                if ((rc = alloc_list(ctx, dst, newcap, ctx->nSpheres, hist, rec))) return rc;
+                CK(cudaMemcpy(dst.pair, src.pair, sizeof(uint2) * oldcap, cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice));
+                if (src.hist) CK(cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(dst.seg_start, src.seg_start, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(dst.seg_count, src.seg_count, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
+                CK(cudaMemcpy(dst.count, src.count, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
+                free_list(src);
+                ctx->lists[kind][ctx->cur] = dst;
+            }
             ctx->capacity = newcap;
             continue;
         }
@@ -334,8 +339,7 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             for (auto& e : sev) cudaEventDestroy(e);
         }
         ctx->cur ^= 1;
-        ctx->n_ss = ctx->h_pinned[0];
-        ctx->n_sa = ctx->h_pinned[1];
+        for (int kind = 0; kind < 3; kind++) ctx->n_list[kind] = ctx->h_pinned[32 + 2 * kind];
         ctx->n_rebuilds++;
         ctx->steps_since_rebuild = 0;
         ctx->need_rebuild = false;
@@ -455,7 +459,6 @@ int dem_ctx_create(DemCtx** out, int device) {
     ctx->num_sms = prop.multiProcessorCount;
     cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocDefault);
     if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
-    if (const char* e = getenv("DEMB_BLOCKED")) ctx->blocked = atoi(e) != 0;
     for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
     *out = ctx;
     return DEM_OK;
@@ -602,6 +605,7 @@ int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, co
         return DEM_ERR_INVALID;
     if (ctx->h_massprop.empty()) return fail(ctx, DEM_ERR_INVALID, "dem_upload_templates must precede dem_upload_owners");
     ctx->h_state.resize(nOwners);
+    ctx->h_spin.resize(nOwners);
     for (uint32_t o = 0; o < nOwners; o++) {
         OwnerState s;
         s.pos.voxel = voxelID[o];
@@ -616,8 +620,10 @@ int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, co
         uint32_t bits = inertiaPropOffsets[o];
         float fb;
         memcpy(&fb, &bits, 4);
-        s.omg = make_float4(omgBarX[o], omgBarY[o], omgBarZ[o], fb);
+        const float3 ww = host_rotate(make_float3(omgBarX[o], omgBarY[o], omgBarZ[o]), s.quat);
+        s.omg = make_float4(ww.x, ww.y, ww.z, 0.f);
         ctx->h_state[o] = s;
+        ctx->h_spin[o] = make_float4(omgBarX[o], omgBarY[o], omgBarZ[o], fb);
     }
     ctx->nOwners = nOwners;
     return DEM_OK;
@@ -670,6 +676,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     int rc;
     const uint32_t nO = ctx->nOwners, nS = ctx->nSpheres;
     if ((rc = dalloc(ctx, &ctx->d_state, nO))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_spin, nO))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_wrench, nO))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_acc, nO))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_sph, nS))) return rc;
@@ -685,6 +692,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if ((rc = dalloc(ctx, &ctx->d_reduce, 4))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_grid, 1))) return rc;
     CK(cudaMemcpy(ctx->d_state, ctx->h_state.data(), sizeof(OwnerState) * nO, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_spin, ctx->h_spin.data(), sizeof(float4) * nO, cudaMemcpyHostToDevice));
     CK(cudaMemset(ctx->d_wrench, 0, sizeof(Wrench) * std::max<size_t>(nO, 1)));
     CK(cudaMemset(ctx->d_acc, 0, sizeof(Wrench) * std::max<size_t>(nO, 1)));
     CK(cudaMemcpy(ctx->d_sph, ctx->h_sph.data(), sizeof(uint2) * nS, cudaMemcpyHostToDevice));
@@ -719,6 +727,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if ((rc = dalloc(ctx, &ctx->d_sortedSph, nS))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_sortedMeta, nS))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_analw, ctx->h_anal.size()))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sortedPos, nS))) return rc;
     const size_t rs_blocks = ((size_t)nS + 4095) / 4096 + 1;
     if ((rc = dalloc(ctx, &ctx->d_rs_hist, 256 * rs_blocks))) return rc;
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
@@ -736,7 +745,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     ctx->initialized = true;
     ctx->need_rebuild = true;
     ctx->steps_since_rebuild = 0;
-    ctx->n_ss = ctx->n_sa = 0;
+    ctx->n_list[0] = ctx->n_list[1] = ctx->n_list[2] = 0;
     return DEM_OK;
 }
 
@@ -773,7 +782,7 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
             count[idA[i]]++;
         }
         for (uint32_t s = 0, run = 0; s < nS; s++) { start[s] = run; run += count[s]; }
-        ListBuf& L = (which == 0) ? ctx->ss[ctx->cur] : ctx->sa[ctx->cur];
+        ListBuf& L = (which == 0) ? ctx->lists[0][ctx->cur] : ctx->lists[2][ctx->cur];
         const uint32_t cnt = (uint32_t)idx.size();
         CK(cudaMemcpy(L.pair, pair.data(), sizeof(uint2) * idx.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.cinfo, cinfo.data(), sizeof(uint4) * idx.size(), cudaMemcpyHostToDevice));
@@ -848,6 +857,11 @@ int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* 
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<OwnerState> st(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    std::vector<float4> sp;
+    if (omg) {
+        sp.resize(n);
+        CK(cudaMemcpy(sp.data(), ctx->d_spin + first, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    }
     std::vector<Wrench> ac;
     if (acc || angacc) {
         // the per-owner {a, alpha} read-out costs 32 B/owner/step, so it is only written once somebody asks: this
@@ -865,7 +879,7 @@ int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* 
         if (family) family[i] = s.pos.family;
         if (oriQ) { oriQ[4 * i] = s.quat.x; oriQ[4 * i + 1] = s.quat.y; oriQ[4 * i + 2] = s.quat.z; oriQ[4 * i + 3] = s.quat.w; }
         if (vel) { vel[3 * i] = s.vel.x; vel[3 * i + 1] = s.vel.y; vel[3 * i + 2] = s.vel.z; }
-        if (omg) { omg[3 * i] = s.omg.x; omg[3 * i + 1] = s.omg.y; omg[3 * i + 2] = s.omg.z; }
+        if (omg) { omg[3 * i] = sp[i].x; omg[3 * i + 1] = sp[i].y; omg[3 * i + 2] = sp[i].z; }
         if (acc) { acc[3 * i] = ac[i].f.x; acc[3 * i + 1] = ac[i].f.y; acc[3 * i + 2] = ac[i].f.z; }
         if (angacc) { angacc[3 * i] = ac[i].t.x; angacc[3 * i + 1] = ac[i].t.y; angacc[3 * i + 2] = ac[i].t.z; }
     }
@@ -903,7 +917,9 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     std::vector<OwnerState> st(n);
+    std::vector<float4> sp(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sp.data(), ctx->d_spin + first, sizeof(float4) * n, cudaMemcpyDeviceToHost));
     for (uint32_t i = 0; i < n; i++) {
         OwnerState& s = st[i];
         if (pos) {
@@ -914,10 +930,13 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
         }
         if (oriQ) s.quat = make_float4(oriQ[4 * i], oriQ[4 * i + 1], oriQ[4 * i + 2], oriQ[4 * i + 3]);
         if (vel) { s.vel.x = vel[3 * i]; s.vel.y = vel[3 * i + 1]; s.vel.z = vel[3 * i + 2]; }
-        if (omg) { s.omg.x = omg[3 * i]; s.omg.y = omg[3 * i + 1]; s.omg.z = omg[3 * i + 2]; }
+        if (omg) { sp[i].x = omg[3 * i]; sp[i].y = omg[3 * i + 1]; sp[i].z = omg[3 * i + 2]; }
         if (family) s.pos.family = family[i];
+        const float3 ww = host_rotate(make_float3(sp[i].x, sp[i].y, sp[i].z), s.quat);
+        s.omg = make_float4(ww.x, ww.y, ww.z, 0.f);
     }
     CK(cudaMemcpy(ctx->d_state + first, st.data(), sizeof(OwnerState) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_spin + first, sp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     ctx->need_rebuild = true;
     ctx->need_maxvel = true;
     return DEM_OK;
@@ -928,16 +947,17 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
     if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t nss = ctx->n_ss, nsa = ctx->n_sa, n = nss + nsa;
+    const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2];
     *n_out = n;
     if (!idA && !idB && !type && !wildcards4 && !force_xyz) return DEM_OK;
     if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
     struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; };
     std::vector<Row> rows;
     rows.reserve(n);
-    for (int which = 0; which < 2; which++) {
-        const ListBuf& L = which == 0 ? ctx->ss[ctx->cur] : ctx->sa[ctx->cur];
-        const uint64_t m = which == 0 ? nss : nsa;
+    for (int kind = 0; kind < 3; kind++) {
+        const ListBuf& L = ctx->lists[kind][ctx->cur];
+        const uint64_t m = ctx->n_list[kind];
+        const int which = (kind == 2) ? 1 : 0;
         std::vector<uint2> pair(m);
         std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0));
         CK(cudaMemcpy(pair.data(), L.pair, sizeof(uint2) * m, cudaMemcpyDeviceToHost));
@@ -983,7 +1003,8 @@ int dem_get_stats(DemCtx* ctx, DemStats* out) {
     if (!ctx || !out) return DEM_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     out->n_steps = ctx->n_steps; out->n_rebuilds = ctx->n_rebuilds;
-    out->n_contacts_ss = ctx->n_ss; out->n_contacts_sa = ctx->n_sa; out->n_contacts_st = 0;
+    out->n_contacts_ss = ctx->n_list[0] + ctx->n_list[1]; out->n_contacts_sa = ctx->n_list[2]; out->n_contacts_st = 0;
+    out->n_contacts_ss_touching = ctx->n_list[0];
     out->contact_capacity = ctx->capacity; out->kernel_launches = ctx->launches; out->device_bytes = ctx->device_bytes;
     out->sim_time = ctx->sim_time; out->max_margin = ctx->last_grid.max_margin; out->cell_size = ctx->last_grid.cs;
     out->n_cells[0] = ctx->last_grid.nbx; out->n_cells[1] = ctx->last_grid.nby; out->n_cells[2] = ctx->last_grid.nbz;
@@ -1009,9 +1030,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     if (!ctx || !name) return DEM_ERR_INVALID;
     const std::string n(name);
     if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
-    else if (n == "blocked_partition") ctx->blocked = value != 0.0;
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
-    else if (n == "prefetch_mode") ctx->prefetch_mode = (int)value;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
     else if (n == "sort_mode") ctx->sort_mode = (int)value;
     else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);

@@ -4,7 +4,8 @@
 //   owners  : four 16-byte records per owner, each fetched with ONE 128-bit load
 //             pos  {u64 voxelID; u16 locX,locY,locZ; u8 family; u8 flags}   (the reference's voxelID/locX/locY/locZ/
 //                   familyID arrays, src/DEM/Defines.h:272-280, packed)
-//             quat {w,x,y,z}     vel {vx,vy,vz,mass}     omg {wx,wy,wz, bits(inertiaPropOffset)}
+//             quat {w,x,y,z}     vel {vx,vy,vz,mass}     omg {WORLD-frame angular velocity, unused}
+//           + a 16-byte spin record {body-frame omgBar xyz, bits(inertiaPropOffset)} that only the integrator streams
 //           + one 32-byte wrench accumulator {Fx,Fy,Fz,0 | Tx,Ty,Tz,0} (force in world frame, torque in body frame),
 //             the target of 128-bit vector reductions (red.global.add.v4.f32, sm_90+).
 //   spheres : uint2 {owner, comp | material<<16}
@@ -29,7 +30,7 @@ struct __align__(64) OwnerState {
     OwnerPos pos;
     float4 quat;  // w,x,y,z
     float4 vel;   // vx,vy,vz, mass
-    float4 omg;   // body-frame angular velocity, w = bits(inertiaPropOffset)
+    float4 omg;   // WORLD-frame angular velocity R(q) omgBar (w unused); body-frame omgBar lives in DevParams::spin
 };
 static_assert(sizeof(OwnerState) == 64, "OwnerState must be 64 bytes");
 
@@ -103,12 +104,11 @@ struct DevParams {
     float beta, approxMaxVel, expSafetyMulti, expSafetyAdder;
     float errOutVel;
     uint32_t maxDrift;
-    uint32_t blocked_partition;  // force kernel: contiguous slice per CTA (1) or grid-stride (0)
-    uint32_t prefetch_mode;      // force kernel: 0 none, 1 prefetch.global.L2, 2 prefetch.global.L1 of the next owners
     uint32_t fast_encode;        // integrator: division-free position encode
     double inv_voxelSize;
     // owners
     OwnerState* state;
+    float4* spin;     // body-frame angular velocity omgBar xyz, w = bits(inertiaPropOffset)
     Wrench* wrench;
     Wrench* acc_out;  // optional per-owner {a, alpha} read-out (nullptr = off)
     // spheres / templates
@@ -124,8 +124,9 @@ struct DevParams {
     const uint8_t* familyMasks;
     const float* familyExtraMargin;
     const Prescr* presc;
-    // contact lists
-    ContactList ss, sa, st;
+    // contact lists: ss = sphere-sphere pairs in touch at the last rebuild, sn = the remaining sphere-sphere
+    // candidates, sa = sphere-analytical, st = sphere-triangle
+    ContactList ss, sn, sa, st;
     // status flags (device): [0] capacity overflow, [1] non-finite / too-fast owner, [2] staging overflow in the sweep
     uint32_t* flags;
     float* maxvel;       // device float: max |v| of the current state (kept up to date by the integrator)

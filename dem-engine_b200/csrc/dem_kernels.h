@@ -38,7 +38,8 @@ struct CdParams {
     float4* sortedSph;
     uint4* sortedMeta;    // {owner, sphere id, comp | material<<16, family}
     AnalWorld* analw;
-    ContactList oldss, oldsa;
+    uint32_t* sortedPos;  // sphere id -> position in the cell-sorted arrays
+    ContactList oldss, oldsn, oldsa;
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the scans
 };

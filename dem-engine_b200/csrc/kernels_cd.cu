@@ -441,6 +441,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ D
     uint32_t fam = 0;
     if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
     C.sortedMeta[j] = make_uint4(s.x, i, s.y, fam);  // {owner, sphere id, comp | material<<16, family}
+    C.sortedPos[i] = j;
 }
 
 // ---- counting sort by cell (sort_mode 1): the histogram and its prefix exist anyway for the sweep ----
@@ -469,6 +470,7 @@ __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant_
     if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
     C.sortedMeta[dst] = make_uint4(s.x, i, s.y, fam);
     C.vals[0][dst] = key;  // sorted keys for the sweep
+    C.sortedPos[i] = dst;
 }
 
 constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half stencil)
@@ -480,15 +482,19 @@ constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half s
 __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams P,
                                                const __grid_constant__ CdParams C,
                                                const uint32_t* __restrict__ keys) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = j < P.nSpheres;
-    uint32_t acc[SWEEP_MAXC];
-    uint32_t count = 0;
+    // One thread per sphere IN SPHERE-ID ORDER (clump by clump), so that the slots claimed below make the contact list
+    // owner-major: the force kernel then streams the A side and reduces it inside the warp.
+    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = sid < P.nSpheres;
+    const uint32_t j = valid ? C.sortedPos[sid] : 0u;
+    uint32_t acc[SWEEP_MAXC];  // staged candidates: sorted index, bit 31 = spheres overlap right now
+    uint32_t count = 0, countT = 0;
     uint4 meta = make_uint4(0, 0, 0, 0);
     if (valid) {
         const GridInfo g = *C.grid;
         const float4 me = C.sortedSph[j];
         meta = C.sortedMeta[j];
+        const float myMargin = me.w - __ldg(&P.comp[meta.z & 0xffffu]).w;
         const uint32_t key = keys[j];
         const int cx = (int)(key % g.nbx);
         const int cy = (int)((key / g.nbx) % g.nby);
@@ -520,68 +526,81 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
                     const float Rt = R - fminf(extraA, P.familyExtraMargin[om.w]);
                     if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
                 }
-                if (count < SWEEP_MAXC) acc[count] = q;
+                // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
+                const float Rtrue = R - myMargin - (ot.w - __ldg(&P.comp[om.z & 0xffffu]).w);
+                const uint32_t touching = (d2 < Rtrue * Rtrue) ? 0x80000000u : 0u;
+                if (count < SWEEP_MAXC) acc[count] = q | touching;
                 count++;
+                countT += touching >> 31;
             }
         }
         if (count > SWEEP_MAXC) {
             atomicOr(&P.flags[2], 1u);  // more forward contacts on one sphere than can be staged
             count = SWEEP_MAXC;
+            countT = 0;
+            for (uint32_t k = 0; k < count; k++) countT += acc[k] >> 31;
         }
     }
-    uint32_t slot = warp_claim(count, P.ss.count);
+    const uint32_t countN = count - countT;
+    uint32_t slotT = warp_claim(countT, P.ss.count);
+    uint32_t slotN = warp_claim(countN, P.sn.count);
     if (!valid) return;
-    P.ss.seg_start[meta.y] = slot;
-    P.ss.seg_count[meta.y] = (slot + count <= C.capacity) ? count : (slot < C.capacity ? C.capacity - slot : 0u);
+    P.ss.seg_start[meta.y] = slotT;
+    P.ss.seg_count[meta.y] = (slotT + countT <= C.capacity) ? countT : (slotT < C.capacity ? C.capacity - slotT : 0u);
+    P.sn.seg_start[meta.y] = slotN;
+    P.sn.seg_count[meta.y] = (slotN + countN <= C.capacity) ? countN : (slotN < C.capacity ? C.capacity - slotN : 0u);
     if (count == 0) return;
-    if (slot + count > C.capacity) atomicOr(&P.flags[0], 1u);
-    const uint32_t oldStartA = C.oldss.seg_start[meta.y], oldCountA = C.oldss.seg_count[meta.y];
+    if (slotT + countT > C.capacity) atomicOr(&P.flags[0], 1u);
+    if (slotN + countN > C.capacity) atomicOr(&P.flags[0], 4u);
     const uint32_t nM = P.nMat;
-    for (uint32_t k = 0; k < count; k++, slot++) {
-        if (slot >= C.capacity) break;
-        const uint4 om = __ldg(&C.sortedMeta[acc[k]]);
-        // history carry-over (DEMHistoryMappingKernels.cu): the pair may sit in the previous list as (A,B) or --
+    for (uint32_t k = 0; k < count; k++) {
+        const bool touching = (acc[k] >> 31) != 0u;
+        const uint4 om = __ldg(&C.sortedMeta[acc[k] & 0x7fffffffu]);
+        const ContactList& L = touching ? P.ss : P.sn;
+        const uint32_t slot = touching ? slotT++ : slotN++;
+        if (slot >= C.capacity) continue;
+        // history carry-over (DEMHistoryMappingKernels.cu): the pair may sit in either previous list as (A,B) or --
         // when the two spheres swapped their order in the sorted array -- as (B,A); then delta_tan changes sign.
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t alive = 0;
         bool found = false;
-        for (uint32_t t = 0; t < oldCountA; t++) {
-            if (C.oldss.pair[oldStartA + t].y == om.y) {
-                alive = C.oldss.cinfo[oldStartA + t].w & 0x80000000u;
-                if (alive && C.oldss.hist) h = C.oldss.hist[oldStartA + t];
-                found = true;
-                break;
-            }
-        }
-        if (!found) {
-            const uint32_t oldStartB = C.oldss.seg_start[om.y], oldCountB = C.oldss.seg_count[om.y];
-            for (uint32_t t = 0; t < oldCountB; t++) {
-                if (C.oldss.pair[oldStartB + t].y == meta.y) {
-                    alive = C.oldss.cinfo[oldStartB + t].w & 0x80000000u;
-                    if (alive && C.oldss.hist) {
-                        h = C.oldss.hist[oldStartB + t];
-                        h.x = -h.x; h.y = -h.y; h.z = -h.z;
+#pragma unroll 1
+        for (int pass = 0; pass < 4 && !found; pass++) {
+            const ContactList& O = ((pass & 1) == (touching ? 0 : 1)) ? C.oldss : C.oldsn;  // likelier list first
+            const bool flipped = pass >= 2;
+            const uint32_t a = flipped ? om.y : meta.y, b = flipped ? meta.y : om.y;
+            const uint32_t os = O.seg_start[a], oc = O.seg_count[a];
+            for (uint32_t t = 0; t < oc; t++) {
+                if (O.pair[os + t].y == b) {
+                    alive = O.cinfo[os + t].w & 0x80000000u;
+                    if (alive && O.hist) {
+                        h = O.hist[os + t];
+                        if (flipped) { h.x = -h.x; h.y = -h.y; h.z = -h.z; }
                     }
+                    found = true;
                     break;
                 }
             }
         }
         const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
-        P.ss.pair[slot] = make_uint2(meta.y, om.y);
-        P.ss.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | alive);
-        if (P.ss.hist) P.ss.hist[slot] = h;
+        L.pair[slot] = make_uint2(meta.y, om.y);
+        L.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | alive);
+        if (L.hist) L.hist[slot] = h;
     }
 }
 
 __global__ void k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t a = *P.ss.count, b = *P.sa.count;
+        uint32_t a = *P.ss.count, b = *P.sa.count, c = *P.sn.count;
         P.ss.count[1] = a;  // the unclamped demand, read back by the host to size a regrow
         P.sa.count[1] = b;
+        P.sn.count[1] = c;
         if (a > C.capacity) { atomicOr(&P.flags[0], 1u); a = C.capacity; }
         if (b > C.capacity) { atomicOr(&P.flags[0], 2u); b = C.capacity; }
+        if (c > C.capacity) { atomicOr(&P.flags[0], 4u); c = C.capacity; }
         *P.ss.count = a;
         *P.sa.count = b;
+        *P.sn.count = c;
     }
 }
 
@@ -604,6 +623,7 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, c
     }
     cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
     cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
+    cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
     cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
     if (P.nSpheres) {
         k_sphere_prep<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, C);
@@ -653,11 +673,11 @@ __global__ void k_reduce(const __grid_constant__ DevParams P, int kind, uint32_t
             pos_decode(st.pos, P, X, Y, Z);
             v = Z + (double)P.LBF[2];
         } else if (kind == DEM_REDUCE_KINETIC_ENERGY) {
-            const float4 mp = P.massprop[__float_as_uint(st.omg.w)];
+            const float4 sp = P.spin[o];
+            const float4 mp = P.massprop[__float_as_uint(sp.w)];
             v = 0.5 * (double)st.vel.w * ((double)st.vel.x * st.vel.x + (double)st.vel.y * st.vel.y +
                                          (double)st.vel.z * st.vel.z) +
-                0.5 * ((double)mp.y * st.omg.x * st.omg.x + (double)mp.z * st.omg.y * st.omg.y +
-                       (double)mp.w * st.omg.z * st.omg.z);
+                0.5 * ((double)mp.y * sp.x * sp.x + (double)mp.z * sp.y * sp.y + (double)mp.w * sp.z * sp.z);
         } else if (kind == DEM_REDUCE_TOTAL_MASS) {
             v = st.vel.w;
         }

@@ -4,7 +4,10 @@
 //   * the contact stream is a 128-bit compiled record + a 128-bit history word, the history word being touched only
 //     for contacts that are (or just stopped being) in physical touch,
 //   * owner wrenches are scattered with 128-bit vector reductions (REDG.E.ADD.F32x4) into a 32-byte accumulator that
-//     stays L2-resident.
+//     stays L2-resident,
+//   * the owner record carries the WORLD-frame angular velocity and the wrench accumulates the WORLD-frame torque, so a
+//     contact needs two quaternion rotations (the sphere offsets) instead of the reference's eight; the integrator
+//     rotates once per owner (R(w x c) = (Rw) x (Rc), sum_i R^T t_i = R^T sum_i t_i).
 // Reference behaviour being reproduced: src/kernel/DEMCalcForceKernels.cu:44-267 (calculateContactForces),
 // DEMCustomizablePolicies/FullHertzianForceModel.cu, FrictionlessHertzianForceModel.cu,
 // src/kernel/DEMCollectForceKernels_Compact.cu:13-102 (forceToAcc), src/kernel/DEMIntegrationKernels.cu:100-264.
@@ -15,9 +18,9 @@ namespace demb {
 // ---------------------------------------------------------------------------------------------------------------
 // gathered end point
 struct End {
-    float4 q;    // w,x,y,z
-    float3 v;    // linear velocity
-    float3 w;    // body-frame angular velocity (omgBar)
+    float4 q;   // w,x,y,z
+    float3 v;   // linear velocity
+    float3 ww;  // WORLD-frame angular velocity
     float mass;
 };
 
@@ -41,18 +44,19 @@ __device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, ui
     e.q = make_float4(q0, q1, q2, q3);
     e.v = f3(v0, v1, v2);
     e.mass = v3;
-    e.w = f3(w0, w1, w2);
+    e.ww = f3(w0, w1, w2);
 }
 
 // Hertz-Mindlin with history (MODEL 0) or frictionless Hertz (MODEL 1).
-//   depth > 0, n = unit normal B->A, cA/cB = contact point in the body frames of A/B.
+//   depth > 0, n = unit normal B->A, armA/armB = contact point minus owner position (world frame).
 // Returns force on A (world) and the torque-only rolling-resistance pseudo force.
 template <int MODEL>
-__device__ __forceinline__ void contact_model(const MatPair& mp, float h, float depth, float3 n, float3 cA, float3 cB,
-                                              const End& A, const End& B, float rA, float rB, float4& hist,
-                                              float3& force, float3& troll) {
-    const float3 rotVelCPA = rotate(cross(A.w, cA), A.q);
-    const float3 rotVelCPB = rotate(cross(B.w, cB), B.q);
+__device__ __forceinline__ void contact_model(const MatPair& mp, float h, float depth, float3 n, float3 armA,
+                                              float3 armB, const End& A, const End& B, float rA, float rB,
+                                              float4& hist, float3& force, float3& troll) {
+    // velocity of the contact point on each body: v + w x r  ( == v + R(omgBar x c_local) of the reference)
+    const float3 rotVelCPA = cross(A.ww, armA);
+    const float3 rotVelCPB = cross(B.ww, armB);
     const float3 velB2A = (A.v + rotVelCPA) - (B.v + rotVelCPB);
     const float projection = dot(velB2A, n);
     const float mass_eff = (A.mass * B.mass) / (A.mass + B.mass);
@@ -104,62 +108,32 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
     }
 }
 
-// scatter the wrench of one contact to both owners (forceToAcc semantics, but sums force / body-frame torque;
-// the division by mass / MOI happens once per owner in the integrator)
-__device__ __forceinline__ void scatter_wrench(Wrench* __restrict__ wr, uint32_t oA, uint32_t oB, float3 force,
-                                               float3 troll, float3 cA, float3 cB, float4 qA, float4 qB) {
-    const float3 FA = rotate_inv(force + troll, qA);
-    const float3 TA = cross(cA, FA);
-    red_add_v4(&wr[oA].f, force.x, force.y, force.z);
-    red_add_v4(&wr[oA].t, TA.x, TA.y, TA.z);
-    const float3 nf = f3(-force.x, -force.y, -force.z);
-    const float3 FB = rotate_inv(f3(-1.f * (force.x + troll.x), -1.f * (force.y + troll.y), -1.f * (force.z + troll.z)), qB);
-    const float3 TB = cross(cB, FB);
-    red_add_v4(&wr[oB].f, nf.x, nf.y, nf.z);
-    red_add_v4(&wr[oB].t, TB.x, TB.y, TB.z);
-}
-
 // ---------------------------------------------------------------------------------------------------------------
-// sphere--sphere contacts.  One thread per contact; the count is DEVICE-resident (no host sync).  Each CTA walks a
-// CONTIGUOUS slice of the (cell-ordered) contact list so that the owner records of spatially adjacent contacts are
-// re-used out of L1, and the next compiled record is prefetched while the current contact is evaluated.
+// sphere--sphere contacts.  One thread per contact over the virtual concatenation of the two sphere--sphere lists
+// (contacts in touch at the last rebuild first, mere candidates after them: warps are then homogeneous and the
+// candidates' warps skip the force model).  Counts are DEVICE-resident (no host sync).
 template <int MODEL, bool RECORD, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
-    const uint32_t n = *P.ss.count;
-    uint32_t c, end, step;
-    if (P.blocked_partition) {
-        const uint32_t chunk = ((n + gridDim.x - 1) / gridDim.x + 255u) & ~255u;
-        c = blockIdx.x * chunk + threadIdx.x;
-        end = min(n, (blockIdx.x + 1) * chunk);
-        step = 256;
-    } else {
-        c = blockIdx.x * blockDim.x + threadIdx.x;
-        end = n;
-        step = gridDim.x * blockDim.x;
-    }
-    // software pipeline: the compiled record is fetched two iterations ahead; as soon as a record has landed, the
-    // cache lines of its two owner records are pulled towards the SM (prefetch), so the dependent gather of the next
-    // iteration does not pay the full DRAM/L2 latency again.
-    uint4 ci = make_uint4(0, 0, 0, 0), ci_next = make_uint4(0, 0, 0, 0);
-    if (c < end) ci = __ldcs(&P.ss.cinfo[c]);  // streaming: evict-first
-    if (c + step < end) ci_next = __ldcs(&P.ss.cinfo[c + step]);
-    while (c < end) {
-        const uint32_t cn = c + step;
-        uint4 ci_next2 = make_uint4(0, 0, 0, 0);
-        if (cn + step < end) ci_next2 = __ldcs(&P.ss.cinfo[cn + step]);
-        if (cn < end && P.prefetch_mode) {
-            if (P.prefetch_mode == 1) {
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + ci_next.x));
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + ci_next.y));
-            } else {
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.state + ci_next.x));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(P.state + ci_next.y));
-            }
-        }
+    const uint32_t nT = *P.ss.count;
+    const uint32_t n = nT + *P.sn.count;
+    const uint32_t step = gridDim.x * blockDim.x;
+    const uint32_t nround = (n + 31u) & ~31u;  // whole warps take part in the A-side reduction
+    const int lane = threadIdx.x & 31;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += step) {
+        float wA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        uint32_t keyA = 0xffffffffu - (uint32_t)lane;  // never equal to a neighbour's key
+        bool touch = false;
+        if (c < n) {
+        const bool inT = c < nT;
+        const uint32_t idx = inT ? c : c - nT;
+        uint4* const cinfo = inT ? P.ss.cinfo : P.sn.cinfo;
+        float4* const histp = inT ? P.ss.hist : P.sn.hist;
+        const uint4 ci = __ldcs(&cinfo[idx]);  // streaming: evict-first
         const uint32_t oA = ci.x, oB = ci.y;
+        keyA = oA;
         const bool alive = (ci.w >> 31) != 0u;
         float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODEL == 0 && alive) hist = __ldcs(&P.ss.hist[c]);
+        if (MODEL == 0 && alive) hist = __ldcs(&histp[idx]);
         const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
         const float4 compB = __ldg(&P.comp[ci.z >> 16]);
         OwnerPos pA, pB;
@@ -187,32 +161,67 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
 
         if (depth > 0.f) {
             nrm = nrm * (1.f / mag);
-            // contact point = centre(B) + (rB - depth/2) n ; relative to each owner (float lever arms)
+            // contact point = centre(B) + (rB - depth/2) n ; lever arms from each owner (world frame)
             const float s = rB - 0.5f * depth;
-            const float3 cpB_w = relB + s * nrm;                                   // CP - ownerB
-            const float3 cpA_w = f3(relA.x - (float)dx, relA.y - (float)dy, relA.z - (float)dz) + s * nrm;  // CP - ownerA
-            const float3 cA = rotate_inv(cpA_w, A.q);
-            const float3 cB = rotate_inv(cpB_w, B.q);
+            const float3 armB = relB + s * nrm;
+            const float3 armA = f3(relA.x - (float)dx, relA.y - (float)dy, relA.z - (float)dz) + s * nrm;
             const MatPair mp = P.matpair[ci.w & 0xffffu];
             float3 force, troll;
-            contact_model<MODEL>(mp, P.h, depth, nrm, cA, cB, A, B, rA, rB, hist, force, troll);
-            scatter_wrench(P.wrench, oA, oB, force, troll, cA, cB, A.q, B.q);
+            contact_model<MODEL>(mp, P.h, depth, nrm, armA, armB, A, B, rA, rB, hist, force, troll);
+            // wrench scatter (forceToAcc semantics; force and WORLD-frame torque sums, divided by mass / rotated and
+            // divided by MOI once per owner in the integrator)
+            const float3 Ft = force + troll;
+            const float3 TA = cross(armA, Ft);
+            const float3 TB = cross(Ft, armB);  // armB x (-Ft)
+            wA[0] = force.x; wA[1] = force.y; wA[2] = force.z;
+            wA[3] = TA.x; wA[4] = TA.y; wA[5] = TA.z;
+            touch = true;
+            red_add_v4(&P.wrench[oB].f, -force.x, -force.y, -force.z);
+            red_add_v4(&P.wrench[oB].t, TB.x, TB.y, TB.z);
             if (MODEL == 0) {
-                __stcs(&P.ss.hist[c], hist);
-                if (!alive) P.ss.cinfo[c].w = ci.w | 0x80000000u;
+                __stcs(&histp[idx], hist);
+                if (!alive) cinfo[idx].w = ci.w | 0x80000000u;
             }
-            if (RECORD) P.ss.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+            if (RECORD) {
+                float4* const frc = inT ? P.ss.force : P.sn.force;
+                frc[idx] = make_float4(force.x, force.y, force.z, 0.f);
+            }
         } else {
             // not in touch: destroy history (FullHertzianForceModel.cu:129-136, DEMCalcForceKernels.cu:258-261)
             if (MODEL == 0 && alive) {
-                __stcs(&P.ss.hist[c], make_float4(0.f, 0.f, 0.f, 0.f));
-                P.ss.cinfo[c].w = ci.w & 0x7fffffffu;
+                __stcs(&histp[idx], make_float4(0.f, 0.f, 0.f, 0.f));
+                cinfo[idx].w = ci.w & 0x7fffffffu;
             }
-            if (RECORD) P.ss.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (RECORD) {
+                float4* const frc = inT ? P.ss.force : P.sn.force;
+                frc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
-        ci = ci_next;
-        ci_next = ci_next2;
-        c = cn;
+        }  // c < n
+        // A side: the list is owner-major, so the contacts of one owner sit in adjacent lanes. Segmented suffix sum over
+        // runs of equal owner, then ONE pair of vector reductions per run instead of one per contact.
+        if (__any_sync(0xffffffffu, touch)) {
+            // runs = maximal stretches of adjacent lanes with the same owner (robust to any key sequence)
+            const uint32_t kprev = __shfl_up_sync(0xffffffffu, keyA, 1);
+            const bool head = (lane == 0) || (kprev != keyA);
+            const uint32_t heads = __ballot_sync(0xffffffffu, head);
+            const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+            const int run_end = above ? lane + __ffs(above) : 32;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const bool take = lane + off < run_end;
+#pragma unroll
+                for (int k = 0; k < 6; k++) {
+                    const float up = __shfl_down_sync(0xffffffffu, wA[k], off);
+                    if (take) wA[k] += up;
+                }
+            }
+            const bool any_force = (wA[0] != 0.f) | (wA[1] != 0.f) | (wA[2] != 0.f) | (wA[3] != 0.f) | (wA[4] != 0.f) | (wA[5] != 0.f);
+            if (head && any_force) {
+                red_add_v4(&P.wrench[keyA].f, wA[0], wA[1], wA[2]);
+                red_add_v4(&P.wrench[keyA].t, wA[3], wA[4], wA[5]);
+            }
+        }
     }
 }
 
@@ -220,6 +229,18 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
 // sphere--analytical contacts (planes, infinite cylinders): checkSphereEntityOverlap, DEMHelperKernels.cuh:459-521
 template <int MODEL, bool RECORD>
 __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevParams P) {
+    // per-CTA accumulator for the (few) wall owners: a per-contact or even per-warp reduction would serialise on the
+    // single L2 line of the wall's wrench
+    __shared__ uint32_t tkey[8];
+    __shared__ float tval[8][6];
+    __shared__ int tcount;
+    if (threadIdx.x < 8) {
+        tkey[threadIdx.x] = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < 6; k++) tval[threadIdx.x][k] = 0.f;
+    }
+    if (threadIdx.x == 0) tcount = 0;
+    __syncthreads();
     const uint32_t n = *P.sa.count;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t nround = (n + 31u) & ~31u;
@@ -230,94 +251,89 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
         bool touchB = false;
         uint32_t oBkey = 0xffffffffu;
         if (active) {
-        const uint4 ci = P.sa.cinfo[c];
-        const uint32_t oA = ci.x;
-        const AnalObj ob = P.anal[ci.y];
-        const uint32_t oB = ob.owner;
-        oBkey = oB;
-        const bool alive = (ci.w >> 31) != 0u;
-        float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (MODEL == 0 && alive) hist = P.sa.hist[c];
-        const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
-        OwnerPos pA, pB;
-        End A, B;
-        load_owner(P.state, oA, pA, A);
-        load_owner(P.state, oB, pB, B);
-        B.mass = ob.mass;  // objMass (DEMCalcForceKernels.cu:198)
-        const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
-        const float3 relB = rotate(f3(ob.relx, ob.rely, ob.relz), B.q);
-        const float3 dirB = rotate(f3(ob.rotx, ob.roty, ob.rotz), B.q);
-        long long ax, ay, az, bx, by, bz;
-        pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
-        pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
-        // sphere centre minus entity point
-        const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
-        const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
-        const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
-        const float rA = compA.w;
-        float depth;
-        float3 nrm;
-        float3 cpA_w;  // CP - ownerA
-        if (ob.type == DEM_ANAL_PLANE) {
-            const float dist = (float)(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z);
-            depth = (float)((double)rA - (double)dist);
-            const float s = (float)((double)dist + ((double)rA - (double)dist) / 2.0);
-            nrm = dirB;
-            cpA_w = relA - s * dirB;
-        } else {  // DEM_ANAL_CYL_INF
-            // sph2cyl = B - A, minus its axial projection
-            const float proj = (float)(-(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z));
-            const double sx = -dx - (double)(proj * dirB.x);
-            const double sy = -dy - (double)(proj * dirB.y);
-            const double sz = -dz - (double)(proj * dirB.z);
-            const double dr = sqrt(sx * sx + sy * sy + sz * sz);
-            const float cyl_rad = ob.size1;
-            const double dep = (double)rA - (double)ob.normal_sign * ((double)cyl_rad - dr);
-            depth = (float)dep;
-            if (dr >= 1e-12) {
-                const double k = (double)ob.normal_sign / dr;
-                nrm = f3((float)(k * sx), (float)(k * sy), (float)(k * sz));
-                const float s = (float)((double)rA - dep / 2.0);
-                cpA_w = relA - s * nrm;
-            } else {
+            const uint4 ci = P.sa.cinfo[c];
+            const uint32_t oA = ci.x;
+            const AnalObj ob = P.anal[ci.y];
+            const uint32_t oB = ob.owner;
+            oBkey = oB;
+            const bool alive = (ci.w >> 31) != 0u;
+            float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODEL == 0 && alive) hist = P.sa.hist[c];
+            const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
+            OwnerPos pA, pB;
+            End A, B;
+            load_owner(P.state, oA, pA, A);
+            load_owner(P.state, oB, pB, B);
+            B.mass = ob.mass;  // objMass (DEMCalcForceKernels.cu:198)
+            const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
+            const float3 relB = rotate(f3(ob.relx, ob.rely, ob.relz), B.q);
+            const float3 dirB = rotate(f3(ob.rotx, ob.roty, ob.rotz), B.q);
+            long long ax, ay, az, bx, by, bz;
+            pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
+            pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
+            // sphere centre minus entity point
+            const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
+            const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
+            const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
+            const float rA = compA.w;
+            float depth;
+            float3 nrm;
+            float3 armA;  // CP - ownerA
+            if (ob.type == DEM_ANAL_PLANE) {
+                const float dist = (float)(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z);
+                depth = (float)((double)rA - (double)dist);
+                const float s = (float)((double)dist + ((double)rA - (double)dist) / 2.0);
                 nrm = dirB;
-                cpA_w = relA;
+                armA = relA - s * dirB;
+            } else {  // DEM_ANAL_CYL_INF
+                // sph2cyl = B - A, minus its axial projection
+                const float proj = (float)(-(dx * (double)dirB.x + dy * (double)dirB.y + dz * (double)dirB.z));
+                const double sx = -dx - (double)(proj * dirB.x);
+                const double sy = -dy - (double)(proj * dirB.y);
+                const double sz = -dz - (double)(proj * dirB.z);
+                const double dr = sqrt(sx * sx + sy * sy + sz * sz);
+                const float cyl_rad = ob.size1;
+                const double dep = (double)rA - (double)ob.normal_sign * ((double)cyl_rad - dr);
+                depth = (float)dep;
+                if (dr >= 1e-12) {
+                    const double k = (double)ob.normal_sign / dr;
+                    nrm = f3((float)(k * sx), (float)(k * sy), (float)(k * sz));
+                    const float s = (float)((double)rA - dep / 2.0);
+                    armA = relA - s * nrm;
+                } else {
+                    nrm = dirB;
+                    armA = relA;
+                }
             }
-        }
-        if (depth > 0.f) {
-            // CP - ownerB = (CP - ownerA) + (ownerA - ownerB)
-            const float3 cpB_w = f3((float)((double)cpA_w.x + (double)(ax - bx) * P.l),
-                                    (float)((double)cpA_w.y + (double)(ay - by) * P.l),
-                                    (float)((double)cpA_w.z + (double)(az - bz) * P.l));
-            const float3 cA = rotate_inv(cpA_w, A.q);
-            const float3 cB = rotate_inv(cpB_w, B.q);
-            const MatPair mp = P.matpair[ci.w & 0xffffu];
-            float3 force, troll;
-            contact_model<MODEL>(mp, P.h, depth, nrm, cA, cB, A, B, rA, 1e15f, hist, force, troll);
-            {
-                const float3 FA = rotate_inv(force + troll, A.q);
-                const float3 TA = cross(cA, FA);
+            if (depth > 0.f) {
+                // CP - ownerB = (CP - ownerA) + (ownerA - ownerB)
+                const float3 armB = f3((float)((double)armA.x + (double)(ax - bx) * P.l),
+                                       (float)((double)armA.y + (double)(ay - by) * P.l),
+                                       (float)((double)armA.z + (double)(az - bz) * P.l));
+                const MatPair mp = P.matpair[ci.w & 0xffffu];
+                float3 force, troll;
+                contact_model<MODEL>(mp, P.h, depth, nrm, armA, armB, A, B, rA, 1e15f, hist, force, troll);
+                const float3 Ft = force + troll;
+                const float3 TA = cross(armA, Ft);
+                const float3 TB = cross(Ft, armB);
                 red_add_v4(&P.wrench[oA].f, force.x, force.y, force.z);
                 red_add_v4(&P.wrench[oA].t, TA.x, TA.y, TA.z);
-                const float3 FB = rotate_inv(f3(-1.f * (force.x + troll.x), -1.f * (force.y + troll.y), -1.f * (force.z + troll.z)), B.q);
-                const float3 TB = cross(cB, FB);
                 wB[0] = -force.x; wB[1] = -force.y; wB[2] = -force.z;
                 wB[3] = TB.x; wB[4] = TB.y; wB[5] = TB.z;
                 touchB = true;
+                if (MODEL == 0) {
+                    P.sa.hist[c] = hist;
+                    if (!alive) P.sa.cinfo[c].w = ci.w | 0x80000000u;
+                }
+                if (RECORD) P.sa.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+            } else {
+                if (MODEL == 0 && alive) {
+                    P.sa.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    P.sa.cinfo[c].w = ci.w & 0x7fffffffu;
+                }
+                if (RECORD) P.sa.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (MODEL == 0) {
-                P.sa.hist[c] = hist;
-                if (!alive) P.sa.cinfo[c].w = ci.w | 0x80000000u;
-            }
-            if (RECORD) P.sa.force[c] = make_float4(force.x, force.y, force.z, 0.f);
-        } else {
-            if (MODEL == 0 && alive) {
-                P.sa.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                P.sa.cinfo[c].w = ci.w & 0x7fffffffu;
-            }
-            if (RECORD) P.sa.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        }  // active
         // B side: the contacts of a warp almost always share ONE wall owner, so a per-contact reduction would
         // serialise on a single L2 line. Reduce across the warp first, one vector reduction per distinct owner.
         uint32_t todo = __ballot_sync(0xffffffffu, touchB);
@@ -333,23 +349,52 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
                 for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
             }
             if ((int)(threadIdx.x & 31) == leader) {
-                red_add_v4(&P.wrench[key].f, v[0], v[1], v[2]);
-                red_add_v4(&P.wrench[key].t, v[3], v[4], v[5]);
+                int slot = -1;
+                const int cnt = min(tcount, 8);
+                for (int t = 0; t < cnt; t++)
+                    if (tkey[t] == key) { slot = t; break; }
+                if (slot < 0) {
+                    slot = atomicAdd(&tcount, 1);
+                    if (slot < 8) tkey[slot] = key;  // (a racing warp may append the same owner twice: harmless)
+                }
+                if (slot < 8) {
+#pragma unroll
+                    for (int k = 0; k < 6; k++) atomicAdd(&tval[slot][k], v[k]);
+                } else {
+                    red_add_v4(&P.wrench[key].f, v[0], v[1], v[2]);
+                    red_add_v4(&P.wrench[key].t, v[3], v[4], v[5]);
+                }
             }
             todo &= ~__ballot_sync(0xffffffffu, mine);
         }
     }
+    __syncthreads();
+    if (threadIdx.x < 8 && threadIdx.x < (unsigned)min(tcount, 8) && tkey[threadIdx.x] != 0xffffffffu) {
+        const float* v = tval[threadIdx.x];
+        red_add_v4(&P.wrench[tkey[threadIdx.x]].f, v[0], v[1], v[2]);
+        red_add_v4(&P.wrench[tkey[threadIdx.x]].t, v[3], v[4], v[5]);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// integrateOwners (DEMIntegrationKernels.cu:100-264). One thread per owner, 64-byte state in / out.
+// integrateOwners (DEMIntegrationKernels.cu:100-264). One thread per owner: 64-byte state + 16-byte body-frame spin
+// + 32-byte wrench in, state + spin out, wrench zeroed (prepareAccArrays, DEMPrepForceKernels.cu:14-37, fused).
+__device__ __forceinline__ void st_v8(void* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e),
+                 "f"(f), "f"(g), "f"(h)
+                 : "memory");
+}
+
 __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_t o) {
     OwnerPos pos;
     End e;
     load_owner(P.state, o, pos, e);
-    const float inertiaBits = P.state[o].omg.w;
-    const float4 mp = __ldg(&P.massprop[__float_as_uint(inertiaBits)]);
-    const Wrench wr = P.wrench[o];
+    const float4 spin = P.spin[o];  // body-frame angular velocity, w = bits(inertiaPropOffset)
+    const float4 mp = __ldg(&P.massprop[__float_as_uint(spin.w)]);
+    float wf[8];
+    asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(wf[0]), "=f"(wf[1]), "=f"(wf[2]), "=f"(wf[3]), "=f"(wf[4]), "=f"(wf[5]), "=f"(wf[6]), "=f"(wf[7])
+                 : "l"(P.wrench + o));
     const float h = P.h;
 
     bool LinVelP[3] = {false, false, false}, RotVelP[3] = {false, false, false}, LinP[3] = {false, false, false};
@@ -359,7 +404,7 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
     X[0] += (double)P.LBF[0];
     X[1] += (double)P.LBF[1];
     X[2] += (double)P.LBF[2];
-    float v[3] = {e.v.x, e.v.y, e.v.z}, w[3] = {e.w.x, e.w.y, e.w.z};
+    float v[3] = {e.v.x, e.v.y, e.v.z}, w[3] = {spin.x, spin.y, spin.z};
     float oldv[3] = {v[0], v[1], v[2]}, oldw[3] = {w[0], w[1], w[2]};
     float extra_acc[3] = {0.f, 0.f, 0.f}, extra_ang[3] = {0.f, 0.f, 0.f};
     const Prescr* pr = P.presc + pos.family;
@@ -377,9 +422,11 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
         }
         RotP = pr->rotPosPrescribed;
     }
-    // a = F/m, alpha = T/I (the reference accumulates F_i/m per contact; same sum up to rounding)
-    const float acc[3] = {wr.f.x / mp.x, wr.f.y / mp.x, wr.f.z / mp.x};
-    const float ang[3] = {wr.t.x / mp.y, wr.t.y / mp.z, wr.t.z / mp.w};
+    // a = F/m ; alpha = R^T T_world / I  (the reference accumulates F_i/m and R^T(c x F_i)/I per contact; same sums up
+    // to rounding)
+    const float acc[3] = {wf[0] / mp.x, wf[1] / mp.x, wf[2] / mp.x};
+    const float3 Tb = rotate_inv(f3(wf[4], wf[5], wf[6]), e.q);
+    const float ang[3] = {Tb.x / mp.y, Tb.y / mp.z, Tb.z / mp.w};
     float vup[3] = {0.f, 0.f, 0.f}, wup[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -428,27 +475,19 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
         const float len = sqrtf(Bq * Bq + Cq * Cq + Dq * Dq + Aq * Aq);
         q = make_float4(Aq / len, Bq / len, Cq / len, Dq / len);
     }
-    OwnerState out;
-    out.pos = pos;
-    out.quat = q;
-    out.vel = make_float4(v[0], v[1], v[2], e.mass);
-    out.omg = make_float4(w[0], w[1], w[2], inertiaBits);
-    int4* dst = reinterpret_cast<int4*>(P.state + o);
-    const int4* src = reinterpret_cast<const int4*>(&out);
-    dst[0] = src[0];
-    dst[1] = src[1];
-    dst[2] = src[2];
-    dst[3] = src[3];
+    // world-frame angular velocity of the NEW state for the next force evaluation
+    const float3 ww = rotate(f3(w[0], w[1], w[2]), q);
+    float* dst = reinterpret_cast<float*>(P.state + o);
+    const uint32_t p2 = (uint32_t)pos.lx | ((uint32_t)pos.ly << 16);
+    const uint32_t p3 = (uint32_t)pos.lz | ((uint32_t)pos.family << 16) | ((uint32_t)pos.flags << 24);
+    st_v8(dst, __uint_as_float((uint32_t)(pos.voxel & 0xffffffffull)), __uint_as_float((uint32_t)(pos.voxel >> 32)),
+          __uint_as_float(p2), __uint_as_float(p3), q.x, q.y, q.z, q.w);
+    st_v8(dst + 8, v[0], v[1], v[2], e.mass, ww.x, ww.y, ww.z, 0.f);
+    P.spin[o] = make_float4(w[0], w[1], w[2], spin.w);
     // per-owner acceleration read-out (ContactAcc / ContactAngAccLocal trackers), only when requested
-    if (P.acc_out) {
-        P.acc_out[o].f = make_float4(acc[0], acc[1], acc[2], 0.f);
-        P.acc_out[o].t = make_float4(ang[0], ang[1], ang[2], 0.f);
-    }
-    // consume the wrench: the accumulator is zero again for the next step's reductions (prepareAccArrays,
-    // DEMPrepForceKernels.cu:14-37, fused here)
-    int4* wz = reinterpret_cast<int4*>(P.wrench + o);
-    wz[0] = make_int4(0, 0, 0, 0);
-    wz[1] = make_int4(0, 0, 0, 0);
+    if (P.acc_out) st_v8(P.acc_out + o, acc[0], acc[1], acc[2], 0.f, ang[0], ang[1], ang[2], 0.f);
+    // consume the wrench: the accumulator is zero again for the next step's reductions
+    st_v8(P.wrench + o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
     return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
 }
 
@@ -467,7 +506,6 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
     for (int off = 16; off > 0; off >>= 1) absv = fmaxf(absv, __shfl_xor_sync(0xffffffffu, absv, off));
     if ((threadIdx.x & 31) == 0 && absv > 0.f) atomicMax(reinterpret_cast<int*>(P.maxvel_next), __float_as_int(absv));
 }
-
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int MINB>

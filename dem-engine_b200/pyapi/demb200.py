@@ -46,6 +46,7 @@ class DemStats(C.Structure):
         ("n_contacts_sa", C.c_uint64), ("n_contacts_st", C.c_uint64), ("contact_capacity", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64), ("sim_time", C.c_double),
         ("max_margin", C.c_float), ("cell_size", C.c_float), ("n_cells", C.c_uint32 * 3), ("overflow", C.c_uint32),
+        ("pad_", C.c_uint32), ("n_contacts_ss_touching", C.c_uint64),
     ]
 
 

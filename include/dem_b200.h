@@ -111,6 +111,8 @@ typedef struct DemStats {
     float cell_size;           /* broad-phase cell edge of the last rebuild */
     uint32_t n_cells[3];
     uint32_t overflow;         /* !=0: a list overflowed (capacity was grown and the rebuild redone) */
+    uint32_t pad_;
+    uint64_t n_contacts_ss_touching; /* sphere-sphere pairs that overlapped at the last rebuild */
 } DemStats;
 
 /* ---- host-side set-up arithmetic ---------------------------------------------------------------------- */
@@ -202,7 +204,7 @@ enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_
 int dem_reduce(DemCtx* ctx, int kind, double* out);
 
 /* execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
- * "blocked_partition" (0/1), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */
+ * "fast_encode" (0/1), "sort_mode" (0 radix sort, 1 counting sort; identical order), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */
 int dem_set_option(DemCtx* ctx, const char* name, double value);
 
 /* ---- measurement hooks (bench.py / ncu) ---------------------------------------------------------------- */

@@ -21,11 +21,13 @@ ap.add_argument("--settle-steps", type=int, default=12000)
 ap.add_argument("--steps", type=int, default=45)
 ap.add_argument("--cd-update-freq", type=int, default=20)
 ap.add_argument("--spacing", type=float, default=2.7)
+ap.add_argument("--ctas-per-sm", type=int, default=3)
 args = ap.parse_args()
 sc, dims = bench.build_scene(args.clumps, args.cd_update_freq, args.spacing)
 f = scenes.flatten(sc)
 eng = demb200.Engine(0)
 eng.load_flat(f)
+eng.set_option("ctas_per_sm", args.ctas_per_sm)
 eng.step(args.settle_steps)
 torch.cuda.synchronize()
 torch.cuda.profiler.start()

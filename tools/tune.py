@@ -25,27 +25,25 @@ f = scenes.flatten(sc)
 eng = demb200.Engine(0)
 eng.load_flat(f)
 t0 = time.time()
-eng.step(args.settle_steps)
+done = 0
+while done < args.settle_steps:
+    n = min(10000, args.settle_steps - done)
+    eng.step(n)
+    done += n
+    st = eng.stats()
+    print("  step %d: max|v| %.3f m/s  KE %.4e J  max z %.4f  ss %d (touching %d) sa %d  wall %.1f s" % (
+        done, eng.reduce(demb200.REDUCE_MAX_ABSV), eng.reduce(demb200.REDUCE_KINETIC_ENERGY),
+        eng.reduce(demb200.REDUCE_MAX_Z), st.n_contacts_ss, st.n_contacts_ss_touching, st.n_contacts_sa, time.time() - t0), flush=True)
 print("settled %d steps in %.1f s" % (args.settle_steps, time.time() - t0), flush=True)
 st = eng.stats()
 print("contacts ss %d sa %d cells %s cs %.5f margin %.6f" % (st.n_contacts_ss, st.n_contacts_sa, list(st.n_cells), st.cell_size, st.max_margin))
-for fe in (0, 1):
-    eng.set_option("fast_encode", fe)
+print("touching", st.n_contacts_ss_touching)
+for ctas in (2, 3, 4):
+    eng.set_option("ctas_per_sm", ctas)
     eng.profile_steps(20)
     r = eng.profile_steps(args.steps)
-    print("fast_encode=%d  %s" % (fe, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
-for blocked in (0, 1):
-    for pf in (0, 1, 2):
-        for ctas in (2, 3):
-            eng.set_option("blocked_partition", blocked)
-            eng.set_option("ctas_per_sm", ctas)
-            eng.set_option("prefetch_mode", pf)
-            eng.profile_steps(20)
-            r = eng.profile_steps(args.steps)
-            print("blocked=%d prefetch=%d ctas_per_sm=%d  %s" % (blocked, pf, ctas, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
-eng.set_option("blocked_partition", 0)
+    print("ctas_per_sm=%d  %s" % (ctas, json.dumps({k: round(v, 1) for k, v in r.items()})), flush=True)
 eng.set_option("ctas_per_sm", 3)
-eng.set_option("prefetch_mode", 1)
 for sm in (0, 1):
     eng.set_option("sort_mode", sm)
     for i in range(2):
