@@ -1,0 +1,994 @@
+// API.cpp -- implementation of the deme::DEMSolver facade over the C ABI of include/dem_b200.h.
+// Flattening follows DEMSolver::Initialize of the reference (src/DEM/APIPublic.cpp:2161-2213,
+// APIPrivate.cpp:119-1120, dT.cpp:638-1024): owners ordered clumps, then external objects; the world bounding box is
+// one extra external object appended at Initialize(); materials pairwise-averaged unless set explicitly.
+#include <DEM/API.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <sstream>
+
+#include "../../../include/dem_b200.h"
+
+namespace deme {
+
+namespace {
+std::string g_data_path = "";
+
+[[noreturn]] void fail(const std::string& msg) { throw std::runtime_error(msg); }
+
+bool parse_constant(const std::string& s, float& out) {
+    // "none" means unspecified; anything else must be a numeric constant (no runtime compilation of user code here)
+    std::string t;
+    for (char c : s)
+        if (!isspace((unsigned char)c)) t.push_back(c);
+    if (t.empty() || t == "none") return false;
+    char* end = nullptr;
+    const double v = std::strtod(t.c_str(), &end);
+    if (end == t.c_str() || *end != '\0')
+        fail("Prescription \"" + s + "\" is not a numeric constant. This B200-native core compiles its kernels ahead "
+             "of time; only constant prescriptions are supported.");
+    out = (float)v;
+    return true;
+}
+
+std::string upper(std::string s) {
+    for (auto& c : s) c = (char)toupper((unsigned char)c);
+    return s;
+}
+}  // namespace
+
+std::filesystem::path GET_DATA_PATH() {
+    if (!g_data_path.empty()) return std::filesystem::path(g_data_path);
+    if (const char* e = std::getenv("DEME_DATA_PATH")) return std::filesystem::path(e);
+    return std::filesystem::path("data");
+}
+std::filesystem::path GetDEMEDataFile(const std::string& relative) { return GET_DATA_PATH() / relative; }
+void SetDEMEDataPath(const std::string& path) { g_data_path = path; }
+
+// ---------------------------------------------------------------------------------------------------------------
+int DEMClumpTemplate::ReadComponentFromFile(const std::string filename, const std::string x_id, const std::string y_id,
+                                            const std::string z_id, const std::string r_id) {
+    std::ifstream f(filename);
+    if (!f) fail("Clump template file " + filename + " cannot be opened.");
+    std::string line;
+    std::getline(f, line);
+    std::vector<std::string> cols;
+    {
+        std::stringstream ss(line);
+        std::string c;
+        while (std::getline(ss, c, ',')) {
+            c.erase(std::remove_if(c.begin(), c.end(), [](unsigned char ch) { return isspace(ch); }), c.end());
+            cols.push_back(c);
+        }
+    }
+    auto col = [&](const std::string& id) {
+        auto it = std::find(cols.begin(), cols.end(), id);
+        if (it == cols.end()) fail("Column " + id + " not found in " + filename);
+        return (size_t)(it - cols.begin());
+    };
+    const size_t ix = col(x_id), iy = col(y_id), iz = col(z_id), ir = col(r_id);
+    radii.clear();
+    relPos.clear();
+    while (std::getline(f, line)) {
+        if (line.empty() || line[0] == '#') continue;
+        std::stringstream ss(line);
+        std::string c;
+        std::vector<float> v;
+        while (std::getline(ss, c, ',')) v.push_back((float)std::atof(c.c_str()));
+        if (v.size() <= std::max(std::max(ix, iy), std::max(iz, ir))) continue;
+        relPos.push_back(make_float3(v[ix], v[iy], v[iz]));
+        radii.push_back(v[ir]);
+    }
+    nComp = (unsigned int)radii.size();
+    return 0;
+}
+
+void DEMClumpTemplate::Scale(float s) {
+    if (!(s > 0)) fail("Scale: s must be positive");
+    for (auto& pos : relPos) pos *= s;
+    for (auto& rad : radii) rad *= s;
+    const double ps = (double)std::abs(s);
+    mass *= ps * ps * ps;
+    MOI *= ps * ps * ps * ps * ps;
+    volume *= ps * ps * ps;
+}
+
+DEMClumpBatch::DEMClumpBatch(size_t num) : nClumps(num) {
+    types.resize(num);
+    families.resize(num, 0);
+    vel.resize(num, make_float3(0, 0, 0));
+    angVel.resize(num, make_float3(0, 0, 0));
+    xyz.resize(num);
+    oriQ.resize(num, make_float4(0, 0, 0, 1));
+    obj_type = OWNER_TYPE::CLUMP;
+}
+void DEMClumpBatch::assertLength(size_t len, const std::string& name) const {
+    if (len != nClumps) {
+        std::stringstream ss;
+        ss << name << " input argument must have length " << nClumps << " (not " << len
+           << "), same as the number of clumps you originally added via AddClumps." << std::endl;
+        throw std::runtime_error(ss.str());
+    }
+}
+void DEMClumpBatch::SetTypes(const std::vector<std::shared_ptr<DEMClumpTemplate>>& input) { assertLength(input.size(), "SetTypes"); types = input; }
+void DEMClumpBatch::SetPos(const std::vector<float3>& input) { assertLength(input.size(), "SetPos"); xyz = input; }
+void DEMClumpBatch::SetVel(const std::vector<float3>& input) { assertLength(input.size(), "SetVel"); vel = input; }
+void DEMClumpBatch::SetAngVel(const std::vector<float3>& input) { assertLength(input.size(), "SetAngVel"); angVel = input; }
+void DEMClumpBatch::SetOriQ(const std::vector<float4>& input) { assertLength(input.size(), "SetOriQ"); oriQ = input; }
+void DEMClumpBatch::SetFamilies(const std::vector<unsigned int>& input) {
+    assertLength(input.size(), "SetFamilies");
+    for (unsigned int f : input)
+        if (f > 255) fail("A clump is instructed to have a family number larger than the max allowance 255");
+    families = input;
+    family_isSpecified = true;
+}
+
+void DEMExternObj::SetFamily(const unsigned int code) {
+    if (code > 255) fail("An external object is instructed to have a family number larger than the max allowance 255");
+    family_code = code;
+}
+void DEMExternObj::AddPlane(const float3 pos, const float3 normal, const std::shared_ptr<DEMMaterial>& material) {
+    comps.push_back({0, pos, normalize(normal), 0.f, 0.f, material});
+}
+void DEMExternObj::AddZCylinder(const float3 pos, const float rad, const std::shared_ptr<DEMMaterial>& material,
+                                const objNormal_t normal) {
+    comps.push_back({2, pos, make_float3(0, 0, 1), rad, normal ? 1.f : 0.f, material});
+}
+void DEMExternObj::AddCylinder(const float3 pos, const float3 axis, const float rad,
+                               const std::shared_ptr<DEMMaterial>& material, const objNormal_t normal) {
+    comps.push_back({2, pos, normalize(axis), rad, normal ? 1.f : 0.f, material});
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+DEMSolver::DEMSolver(unsigned int nGPUs) {
+    (void)nGPUs;
+    int device = 0;
+    if (const char* e = std::getenv("DEME_B200_DEVICE")) device = std::atoi(e);
+    const int rc = dem_ctx_create(&ctx, device);
+    if (rc != DEM_OK) fail("DEMSolver: no usable CUDA device (this core has no CPU fallback); dem_ctx_create returned " + std::to_string(rc));
+    m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
+}
+DEMSolver::DEMSolver(const std::vector<int>& gpu_ids) {
+    const int rc = dem_ctx_create(&ctx, gpu_ids.empty() ? 0 : gpu_ids[0]);
+    if (rc != DEM_OK) fail("DEMSolver: no usable CUDA device (this core has no CPU fallback)");
+    m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
+}
+DEMSolver::~DEMSolver() {
+    if (ctx) dem_ctx_destroy(ctx);
+}
+
+void DEMSolver::check(int rc, const char* what) const {
+    if (rc != DEM_OK) fail(std::string(what) + " failed: " + dem_last_error(ctx));
+}
+void DEMSolver::assertInit(const char* what) const {
+    if (!sys_initialized) fail(std::string(what) + " can only be called after Initialize().");
+}
+
+void DEMSolver::SetVerbosity(const std::string& verbose) {
+    const std::string u = upper(verbose);
+    if (u == "QUIET") verbosity = QUIET; else if (u == "ERROR") verbosity = ERR; else if (u == "WARNING") verbosity = WARNING;
+    else if (u == "INFO") verbosity = INFO; else if (u == "STEP_ANOMALY") verbosity = STEP_ANOMALY;
+    else if (u == "STEP_METRIC") verbosity = STEP_METRIC; else if (u == "DEBUG") verbosity = DEBUG;
+    else if (u == "STEP_DEBUG") verbosity = STEP_DEBUG;
+    else fail("Instruction " + verbose + " is unknown in SetVerbosity call.");
+}
+void DEMSolver::SetOutputContent(const std::vector<std::string>& content) {
+    unsigned int c = XYZ;
+    for (const auto& a : content) {
+        const std::string u = upper(a);
+        if (u == "XYZ") c |= XYZ; else if (u == "QUAT") c |= QUAT; else if (u == "ABSV") c |= ABSV; else if (u == "VEL") c |= VEL;
+        else if (u == "ANG_VEL") c |= ANG_VEL; else if (u == "ABS_ACC") c |= ABS_ACC; else if (u == "ACC") c |= ACC;
+        else if (u == "ANG_ACC") c |= ANG_ACC; else if (u == "FAMILY") c |= FAMILY; else if (u == "MAT") c |= MAT;
+        else fail("Instruction " + a + " is unknown in SetOutputContent call.");
+    }
+    m_out_content = c;
+}
+void DEMSolver::SetContactOutputContent(const std::vector<std::string>& content) {
+    unsigned int c = CNT_TYPE;
+    for (const auto& a : content) {
+        const std::string u = upper(a);
+        if (u == "CNT_TYPE") c |= CNT_TYPE; else if (u == "FORCE") c |= FORCE; else if (u == "POINT" || u == "CNT_POINT") c |= CNT_POINT;
+        else if (u == "COMPONENT") c |= COMPONENT; else if (u == "NORMAL") c |= NORMAL; else if (u == "TORQUE") c |= TORQUE;
+        else if (u == "CNT_WILDCARD") c |= CNT_WILDCARD; else if (u == "OWNER") c |= OWNER; else if (u == "GEO_ID") c |= GEO_ID;
+        else fail("Instruction " + a + " is unknown in SetContactOutputContent call.");
+    }
+    m_cnt_out_content = c;
+}
+
+void DEMSolver::InstructBoxDomainDimension(float x, float y, float z, const std::string& dir_exact) {
+    if (upper(dir_exact) != "NONE") fail("InstructBoxDomainDimension: an exact direction is not supported by this core.");
+    float umin[3], umax[3], tmin[3], tmax[3];
+    dem_host_box_domain(x, y, z, umin, umax, tmin, tmax);
+    m_user_box_min = make_float3(umin[0], umin[1], umin[2]);
+    m_user_box_max = make_float3(umax[0], umax[1], umax[2]);
+    m_target_box_min = make_float3(tmin[0], tmin[1], tmin[2]);
+    m_target_box_max = make_float3(tmax[0], tmax[1], tmax[2]);
+}
+void DEMSolver::InstructBoxDomainDimension(const std::pair<float, float>& x, const std::pair<float, float>& y,
+                                           const std::pair<float, float>& z, const std::string& dir_exact) {
+    if (upper(dir_exact) != "NONE") fail("InstructBoxDomainDimension: an exact direction is not supported by this core.");
+    // APIPublic.cpp:874-905: enlarge by 20 % about the user's box
+    m_user_box_min = make_float3(std::min(x.first, x.second), std::min(y.first, y.second), std::min(z.first, z.second));
+    m_user_box_max = make_float3(std::max(x.first, x.second), std::max(y.first, y.second), std::max(z.first, z.second));
+    const float3 sz = m_user_box_max - m_user_box_min;
+    const float3 enl = make_float3(sz.x * 0.2f / 2.f, sz.y * 0.2f / 2.f, sz.z * 0.2f / 2.f);
+    m_target_box_min = m_user_box_min - enl;
+    m_target_box_max = m_user_box_max + enl;
+}
+void DEMSolver::InstructBoxDomainBoundingBC(const std::string& inst, const std::shared_ptr<DEMMaterial>& mat) {
+    if (inst != "none" && inst != "all" && inst != "top_open" && inst != "only_bottom" && inst != "only_sides")
+        fail("Domain bounding BC instruction " + inst + " is unknown.");
+    m_user_add_bounding_box = inst;
+    m_bounding_box_material = mat;
+}
+
+void DEMSolver::SetCDUpdateFreq(int freq) {
+    // SetCDUpdateFreq(0) is the reference's lock-step mode: rebuild before every step
+    m_cd_update_freq = std::max(1, freq);
+}
+void DEMSolver::SetIntegrator(const std::string& intg) {
+    const std::string u = upper(intg);
+    if (u == "FORWARD_EULER") m_integrator = TIME_INTEGRATOR::FORWARD_EULER;
+    else if (u == "CENTERED_DIFFERENCE") m_integrator = TIME_INTEGRATOR::CENTERED_DIFFERENCE;
+    else if (u == "EXTENDED_TAYLOR") m_integrator = TIME_INTEGRATOR::EXTENDED_TAYLOR;
+    else fail("Integration type " + intg + " is unknown. Please select another via SetIntegrator.");
+}
+void DEMSolver::SetExpandFactor(float beta, bool fix) {
+    if (fix) m_expand_factor = beta;
+}
+void DEMSolver::UpdateStepSize(double ts) {
+    if (ts > 0) m_ts_size = ts;
+    if (sys_initialized) check(dem_update_step_size(ctx, (float)m_ts_size), "UpdateStepSize");
+}
+
+std::shared_ptr<DEMForceModel> DEMSolver::UseFrictionalHertzianModel() {
+    m_force_model = FORCE_MODEL::HERTZIAN;
+    return std::make_shared<DEMForceModel>(m_force_model);
+}
+std::shared_ptr<DEMForceModel> DEMSolver::UseFrictionlessHertzianModel() {
+    m_force_model = FORCE_MODEL::HERTZIAN_FRICTIONLESS;
+    return std::make_shared<DEMForceModel>(m_force_model);
+}
+std::shared_ptr<DEMForceModel> DEMSolver::DefineContactForceModel(const std::string&) {
+    fail("DefineContactForceModel: custom force-model source needs runtime compilation, which this ahead-of-time compiled "
+         "core does not have. Use UseFrictionalHertzianModel() or UseFrictionlessHertzianModel().");
+}
+std::shared_ptr<DEMForceModel> DEMSolver::ReadContactForceModel(const std::string&) {
+    fail("ReadContactForceModel: custom force-model source needs runtime compilation, which this ahead-of-time compiled "
+         "core does not have. Use UseFrictionalHertzianModel() or UseFrictionlessHertzianModel().");
+}
+
+std::shared_ptr<DEMMaterial> DEMSolver::LoadMaterial(const std::unordered_map<std::string, float>& mat_prop) {
+    auto m = std::make_shared<DEMMaterial>(mat_prop);
+    m->load_order = (unsigned int)m_loaded_materials.size();
+    m_loaded_materials.push_back(m);
+    return m;
+}
+void DEMSolver::SetMaterialPropertyPair(const std::string& name, const std::shared_ptr<DEMMaterial>& mat1,
+                                        const std::shared_ptr<DEMMaterial>& mat2, float val) {
+    m_pairwise_matprop[name][{mat1->load_order, mat2->load_order}] = val;
+}
+
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadClumpType(DEMClumpTemplate& clump) {
+    if (clump.mass <= 0 || length(clump.MOI) <= 0)
+        std::cerr << "WARNING! A type of clump is instructed to have near-zero mass or moment of inertia." << std::endl;
+    if (clump.radii.size() != clump.relPos.size() || clump.radii.size() != clump.materials.size())
+        fail("Arrays defining a clump topology type must all have the same length.");
+    auto p = std::make_shared<DEMClumpTemplate>(clump);
+    p->nComp = (unsigned int)clump.radii.size();
+    p->mark = (unsigned int)m_templates.size();
+    if (p->m_name == "NULL") {
+        char name[16];
+        snprintf(name, sizeof(name), "%04u", p->mark);
+        p->m_name = name;
+    }
+    m_templates.push_back(p);
+    return p;
+}
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadClumpType(float mass, float3 moi, const std::vector<float>& sp_radii,
+                                                           const std::vector<float3>& sp_locations_xyz,
+                                                           const std::vector<std::shared_ptr<DEMMaterial>>& sp_materials) {
+    DEMClumpTemplate c;
+    c.mass = mass; c.MOI = moi; c.radii = sp_radii; c.relPos = sp_locations_xyz; c.materials = sp_materials;
+    c.nComp = (unsigned int)sp_radii.size();
+    return LoadClumpType(c);
+}
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadClumpType(float mass, float3 moi, const std::vector<float>& sp_radii,
+                                                           const std::vector<float3>& sp_locations_xyz,
+                                                           const std::shared_ptr<DEMMaterial>& sp_material) {
+    return LoadClumpType(mass, moi, sp_radii, sp_locations_xyz,
+                         std::vector<std::shared_ptr<DEMMaterial>>(sp_radii.size(), sp_material));
+}
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadClumpType(float mass, float3 moi, const std::string filename,
+                                                           const std::vector<std::shared_ptr<DEMMaterial>>& sp_materials) {
+    DEMClumpTemplate c;
+    c.mass = mass; c.MOI = moi;
+    c.ReadComponentFromFile(filename);
+    c.materials = sp_materials;
+    return LoadClumpType(c);
+}
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadClumpType(float mass, float3 moi, const std::string filename,
+                                                           const std::shared_ptr<DEMMaterial>& sp_material) {
+    DEMClumpTemplate c;
+    c.mass = mass; c.MOI = moi;
+    c.ReadComponentFromFile(filename);
+    c.materials.assign(c.nComp, sp_material);
+    return LoadClumpType(c);
+}
+std::shared_ptr<DEMClumpTemplate> DEMSolver::LoadSphereType(float mass, float radius, const std::shared_ptr<DEMMaterial>& material) {
+    const float I = (float)(2.0 / 5.0 * mass * radius * radius);  // APIPublic.cpp LoadSphereType
+    return LoadClumpType(mass, make_float3(I, I, I), std::vector<float>(1, radius), std::vector<float3>(1, make_float3(0, 0, 0)),
+                         std::vector<std::shared_ptr<DEMMaterial>>(1, material));
+}
+
+std::shared_ptr<DEMClumpBatch> DEMSolver::AddClumps(DEMClumpBatch& input_batch) {
+    auto b = std::make_shared<DEMClumpBatch>(input_batch);
+    b->load_order = (unsigned int)m_cached_input_clump_batches.size();
+    size_t nsp = 0;
+    for (const auto& t : b->types) {
+        if (!t) fail("AddClumps: a clump has no template assigned.");
+        nsp += t->nComp;
+    }
+    b->nSpheres = nsp;
+    m_cached_input_clump_batches.push_back(b);
+    return b;
+}
+std::shared_ptr<DEMClumpBatch> DEMSolver::AddClumps(const std::vector<std::shared_ptr<DEMClumpTemplate>>& input_types,
+                                                    const std::vector<float3>& input_xyz) {
+    if (input_types.size() != input_xyz.size())
+        fail("Arrays in the call AddClumps must all have the same length.");
+    DEMClumpBatch b(input_xyz.size());
+    b.SetTypes(input_types);
+    b.SetPos(input_xyz);
+    return AddClumps(b);
+}
+std::shared_ptr<DEMExternObj> DEMSolver::AddExternalObject() {
+    auto o = std::make_shared<DEMExternObj>();
+    o->load_order = (unsigned int)m_cached_extern_objs.size();
+    m_cached_extern_objs.push_back(o);
+    return o;
+}
+std::shared_ptr<DEMExternObj> DEMSolver::AddBCPlane(const float3 pos, const float3 normal, const std::shared_ptr<DEMMaterial>& material) {
+    auto o = AddExternalObject();
+    o->SetFamily(RESERVED_FAMILY_NUM);
+    o->AddPlane(pos, normal, material);
+    return o;
+}
+
+std::shared_ptr<DEMInspector> DEMSolver::CreateInspector(const std::string& quantity) {
+    return std::make_shared<DEMInspector>(this, quantity);
+}
+
+void DEMSolver::DisableContactBetweenFamilies(unsigned int ID1, unsigned int ID2) {
+    if (ID1 > 255 || ID2 > 255) fail("Family numbers must not exceed 255.");
+    const unsigned i = std::min(ID1, ID2), j = std::max(ID1, ID2);
+    m_family_masks[(1 + j) * j / 2 + i] = 1;
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::EnableContactBetweenFamilies(unsigned int ID1, unsigned int ID2) {
+    if (ID1 > 255 || ID2 > 255) fail("Family numbers must not exceed 255.");
+    const unsigned i = std::min(ID1, ID2), j = std::max(ID1, ID2);
+    m_family_masks[(1 + j) * j / 2 + i] = 0;
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::SetFamilyFixed(unsigned int ID) {
+    if (ID > 255) fail("Family numbers must not exceed 255.");
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    for (int k = 0; k < 3; k++) {
+        p.linVelP[k] = p.rotVelP[k] = p.linPosP[k] = true;
+        p.hasLinVel[k] = p.hasRotVel[k] = true;
+        p.linVel[k] = p.rotVel[k] = 0.f;
+    }
+    p.rotPosP = true;
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::SetFamilyPrescribedLinVel(unsigned int ID, const std::string& velX, const std::string& velY,
+                                          const std::string& velZ, bool dictate) {
+    if (ID > 255) fail("Family numbers must not exceed 255.");
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    const std::string* s[3] = {&velX, &velY, &velZ};
+    for (int k = 0; k < 3; k++) {
+        float v;
+        if (parse_constant(*s[k], v)) { p.hasLinVel[k] = true; p.linVel[k] = v; p.linVelP[k] = dictate; }
+    }
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::SetFamilyPrescribedAngVel(unsigned int ID, const std::string& velX, const std::string& velY,
+                                          const std::string& velZ, bool dictate) {
+    if (ID > 255) fail("Family numbers must not exceed 255.");
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    const std::string* s[3] = {&velX, &velY, &velZ};
+    for (int k = 0; k < 3; k++) {
+        float v;
+        if (parse_constant(*s[k], v)) { p.hasRotVel[k] = true; p.rotVel[k] = v; p.rotVelP[k] = dictate; }
+    }
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::SetFamilyPrescribedPosition(unsigned int ID, const std::string& X, const std::string& Y,
+                                            const std::string& Z, bool dictate) {
+    if (ID > 255) fail("Family numbers must not exceed 255.");
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    const std::string* s[3] = {&X, &Y, &Z};
+    for (int k = 0; k < 3; k++) {
+        float v;
+        if (parse_constant(*s[k], v)) { p.hasLinPos[k] = true; p.linPos[k] = v; p.linPosP[k] = dictate; }
+    }
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::AddFamilyPrescribedAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z) {
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    const std::string* s[3] = {&X, &Y, &Z};
+    for (int k = 0; k < 3; k++) {
+        float v;
+        if (parse_constant(*s[k], v)) { p.hasAcc[k] = true; p.acc[k] = v; }
+    }
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z) {
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    const std::string* s[3] = {&X, &Y, &Z};
+    for (int k = 0; k < 3; k++) {
+        float v;
+        if (parse_constant(*s[k], v)) { p.hasAngAcc[k] = true; p.angAcc[k] = v; }
+    }
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::ChangeFamilyWhen(unsigned int, unsigned int, const std::string&) {
+    fail("ChangeFamilyWhen: condition strings need runtime compilation, which this ahead-of-time compiled core does "
+         "not have. Use ChangeFamily(ID_from, ID_to) between DoDynamics calls.");
+}
+void DEMSolver::SetFamilyExtraMargin(unsigned int N, float extra_size) {
+    if (N > 255) fail("Family numbers must not exceed 255.");
+    m_family_extra_margin[N] = extra_size;
+    if (sys_initialized) uploadFamilies();
+}
+
+void DEMSolver::uploadFamilies() {
+    std::vector<float> extra(DEM_NUM_FAMILIES, 0.f);
+    for (const auto& kv : m_family_extra_margin) extra[kv.first] = kv.second;
+    std::vector<DemPrescription> pr(DEM_NUM_FAMILIES);
+    memset(pr.data(), 0, sizeof(DemPrescription) * DEM_NUM_FAMILIES);
+    // the reserved family is always fixed (APIPublic.cpp:980-1011)
+    Prescription fixed;
+    fixed.used = true;
+    for (int k = 0; k < 3; k++) {
+        fixed.linVelP[k] = fixed.rotVelP[k] = fixed.linPosP[k] = true;
+        fixed.hasLinVel[k] = fixed.hasRotVel[k] = true;
+    }
+    fixed.rotPosP = true;
+    auto put = [&](unsigned fam, const Prescription& p) {
+        DemPrescription& d = pr[fam];
+        d.used = p.used;
+        for (int k = 0; k < 3; k++) {
+            d.linVelPrescribed[k] = p.linVelP[k]; d.rotVelPrescribed[k] = p.rotVelP[k]; d.linPosPrescribed[k] = p.linPosP[k];
+            d.hasLinVel[k] = p.hasLinVel[k]; d.hasRotVel[k] = p.hasRotVel[k]; d.hasLinPos[k] = p.hasLinPos[k];
+            d.hasAcc[k] = p.hasAcc[k]; d.hasAngAcc[k] = p.hasAngAcc[k];
+            d.linVel[k] = p.linVel[k]; d.rotVel[k] = p.rotVel[k]; d.linPos[k] = p.linPos[k];
+            d.acc[k] = p.acc[k]; d.angAcc[k] = p.angAcc[k];
+        }
+        d.rotPosPrescribed = p.rotPosP;
+    };
+    put(RESERVED_FAMILY_NUM, fixed);
+    for (const auto& kv : m_prescriptions) put(kv.first, kv.second);
+    check(dem_upload_families(ctx, m_family_masks.data(), extra.data(), pr.data()), "dem_upload_families");
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void DEMSolver::Initialize(bool dry_run) {
+    if (m_loaded_materials.empty()) fail("Before initializing the system, at least one material type should be loaded via LoadMaterial.");
+    if (m_ts_size <= 0.0) fail("Time step size is set to be " + std::to_string(m_ts_size) + ". Please supply a positive number via SetInitTimeStep.");
+
+    // ---- world sizing (figureOutNV) ----
+    DemSimParams sp;
+    memset(&sp, 0, sizeof(sp));
+    const float tmin[3] = {m_target_box_min.x, m_target_box_min.y, m_target_box_min.z};
+    const float tmax[3] = {m_target_box_max.x, m_target_box_max.y, m_target_box_max.z};
+    uint32_t nv[3];
+    dem_host_figure_out_nv(tmin, tmax, nv, &sp.l, &sp.voxelSize);
+    sp.nvXp2 = nv[0]; sp.nvYp2 = nv[1]; sp.nvZp2 = nv[2];
+    sp.integrator = (m_integrator == TIME_INTEGRATOR::FORWARD_EULER) ? DEM_FORWARD_EULER
+                    : (m_integrator == TIME_INTEGRATOR::CENTERED_DIFFERENCE) ? DEM_CENTERED_DIFFERENCE : DEM_EXTENDED_TAYLOR;
+    sp.force_model = (m_force_model == FORCE_MODEL::HERTZIAN_FRICTIONLESS) ? DEM_HERTZIAN_FRICTIONLESS : DEM_HERTZIAN;
+    sp.cd_update_freq = (uint32_t)m_cd_update_freq;
+    const float umin[3] = {m_user_box_min.x, m_user_box_min.y, m_user_box_min.z};
+    const float umax[3] = {m_user_box_max.x, m_user_box_max.y, m_user_box_max.z};
+    const float g[3] = {G.x, G.y, G.z};
+    for (int k = 0; k < 3; k++) { sp.LBF[k] = tmin[k]; sp.G[k] = g[k]; sp.userBoxMin[k] = umin[k]; sp.userBoxMax[k] = umax[k]; }
+    sp.h = (float)m_ts_size;
+    sp.beta = m_expand_factor;
+    sp.approxMaxVel = m_approx_max_vel;
+    sp.expSafetyMulti = m_expand_safety_multi;
+    sp.expSafetyAdder = m_expand_base_vel;
+    sp.errOutVel = threshold_error_out_vel;
+    sp.record_contact_forces = no_recording_contact_forces ? 0u : 1u;
+    check(dem_set_params(ctx, &sp), "dem_set_params");
+
+    // ---- world bounding box: one external object appended now (addWorldBoundingBox, APIPrivate.cpp:955-1014) ----
+    std::vector<std::shared_ptr<DEMExternObj>> ext = m_cached_extern_objs;
+    if (m_user_add_bounding_box != "none") {
+        const std::string& m = m_user_add_bounding_box;
+        const bool bottom = (m == "only_bottom" || m == "top_open" || m == "all");
+        const bool sides = (m == "only_sides" || m == "top_open" || m == "all");
+        const bool top = (m == "all");
+        auto box = std::make_shared<DEMExternObj>();
+        const float3 c = (m_user_box_min + m_user_box_max) / 2.f;
+        if (bottom) box->AddPlane(make_float3(c.x, c.y, m_user_box_min.z), make_float3(0, 0, 1), m_bounding_box_material);
+        if (sides) {
+            box->AddPlane(make_float3(m_user_box_min.x, c.y, c.z), make_float3(1, 0, 0), m_bounding_box_material);
+            box->AddPlane(make_float3(m_user_box_max.x, c.y, c.z), make_float3(-1, 0, 0), m_bounding_box_material);
+            box->AddPlane(make_float3(c.x, m_user_box_min.y, c.z), make_float3(0, 1, 0), m_bounding_box_material);
+            box->AddPlane(make_float3(c.x, m_user_box_max.y, c.z), make_float3(0, -1, 0), m_bounding_box_material);
+        }
+        if (top) box->AddPlane(make_float3(c.x, c.y, m_user_box_max.z), make_float3(0, 0, -1), m_bounding_box_material);
+        ext.push_back(box);
+    }
+
+    // ---- templates ----
+    std::vector<float> radii, relX, relY, relZ, mass, moiX, moiY, moiZ;
+    std::vector<uint32_t> comp_start;
+    std::vector<uint16_t> comp_mat;
+    for (const auto& t : m_templates) {
+        comp_start.push_back((uint32_t)radii.size());
+        for (size_t k = 0; k < t->radii.size(); k++) {
+            radii.push_back(t->radii[k]);
+            relX.push_back(t->relPos[k].x); relY.push_back(t->relPos[k].y); relZ.push_back(t->relPos[k].z);
+            comp_mat.push_back((uint16_t)t->materials[k]->load_order);
+        }
+        mass.push_back(t->mass); moiX.push_back(t->MOI.x); moiY.push_back(t->MOI.y); moiZ.push_back(t->MOI.z);
+    }
+    for (const auto& e : ext) { mass.push_back(e->mass); moiX.push_back(e->MOI.x); moiY.push_back(e->MOI.y); moiZ.push_back(e->MOI.z); }
+    check(dem_upload_templates(ctx, (uint32_t)radii.size(), radii.data(), relX.data(), relY.data(), relZ.data(),
+                               (uint32_t)mass.size(), mass.data(), moiX.data(), moiY.data(), moiZ.data()),
+          "dem_upload_templates");
+
+    // ---- materials (equipMaterials, APIPrivate.cpp:1877-2026) ----
+    const uint32_t nM = (uint32_t)m_loaded_materials.size();
+    std::vector<float> E(nM), nu(nM), CoR(nM * nM), mu(nM * nM), Crr(nM * nM);
+    auto prop = [&](uint32_t i, const char* name) {
+        const auto& mp = m_loaded_materials[i]->mat_prop;
+        auto it = mp.find(name);
+        return it == mp.end() ? 0.f : it->second;
+    };
+    for (uint32_t i = 0; i < nM; i++) { E[i] = prop(i, "E"); nu[i] = prop(i, "nu"); }
+    struct { const char* name; std::vector<float>* t; } pw[3] = {{"CoR", &CoR}, {"mu", &mu}, {"Crr", &Crr}};
+    for (auto& p : pw) {
+        for (uint32_t i = 0; i < nM; i++) (*p.t)[i * nM + i] = prop(i, p.name);
+        for (uint32_t i = 0; i < nM; i++)
+            for (uint32_t j = 0; j < nM; j++)
+                if (i != j) (*p.t)[i * nM + j] = (float)(((*p.t)[i * nM + i] + (*p.t)[j * nM + j]) / 2.);
+        auto it = m_pairwise_matprop.find(p.name);
+        if (it != m_pairwise_matprop.end())
+            for (const auto& kv : it->second) {
+                (*p.t)[kv.first.first * nM + kv.first.second] = kv.second;
+                (*p.t)[kv.first.second * nM + kv.first.first] = kv.second;
+            }
+    }
+    check(dem_upload_materials(ctx, nM, E.data(), nu.data(), CoR.data(), mu.data(), Crr.data()), "dem_upload_materials");
+
+    // ---- owners: clumps, then external objects ----
+    size_t nC = 0;
+    for (const auto& b : m_cached_input_clump_batches) nC += b->nClumps;
+    const size_t nE = ext.size(), nO = nC + nE;
+    std::vector<float> xyz(3 * nO), qw(nO), qx(nO), qy(nO), qz(nO), vx(nO), vy(nO), vz(nO), ox(nO), oy(nO), oz(nO);
+    std::vector<uint8_t> fam(nO);
+    std::vector<uint16_t> inertia(nO);
+    std::vector<uint32_t> sph_owner;
+    std::vector<uint16_t> sph_comp, sph_mat;
+    m_owner_mass.assign(nO, 0.f);
+    m_owner_moi.assign(nO, make_float3(0, 0, 0));
+    m_owner_type_mark.assign(nC, 0);
+    size_t o = 0;
+    bool out_of_box = false;
+    for (auto& b : m_cached_input_clump_batches) {
+        b->first_owner = (bodyID_t)o;
+        for (size_t j = 0; j < b->nClumps; j++, o++) {
+            const auto& t = b->types[j];
+            xyz[3 * o] = b->xyz[j].x; xyz[3 * o + 1] = b->xyz[j].y; xyz[3 * o + 2] = b->xyz[j].z;
+            if (b->xyz[j].x < m_user_box_min.x || b->xyz[j].x > m_user_box_max.x || b->xyz[j].y < m_user_box_min.y ||
+                b->xyz[j].y > m_user_box_max.y || b->xyz[j].z < m_user_box_min.z || b->xyz[j].z > m_user_box_max.z)
+                out_of_box = true;
+            qw[o] = b->oriQ[j].w; qx[o] = b->oriQ[j].x; qy[o] = b->oriQ[j].y; qz[o] = b->oriQ[j].z;
+            vx[o] = b->vel[j].x; vy[o] = b->vel[j].y; vz[o] = b->vel[j].z;
+            ox[o] = b->angVel[j].x; oy[o] = b->angVel[j].y; oz[o] = b->angVel[j].z;
+            fam[o] = (uint8_t)b->families[j];
+            inertia[o] = (uint16_t)t->mark;
+            m_owner_mass[o] = t->mass; m_owner_moi[o] = t->MOI; m_owner_type_mark[o] = t->mark;
+            for (unsigned int k = 0; k < t->nComp; k++) {
+                sph_owner.push_back((uint32_t)o);
+                sph_comp.push_back((uint16_t)(comp_start[t->mark] + k));
+                sph_mat.push_back(comp_mat[comp_start[t->mark] + k]);
+            }
+        }
+    }
+    if (out_of_box && verbosity >= WARNING)
+        std::cerr << "WARNING! At least one clump is initialized outside the user-specified box domain." << std::endl;
+    std::vector<uint32_t> objOwner;
+    std::vector<uint8_t> objType;
+    std::vector<uint16_t> objMat;
+    std::vector<float> objNormal, rpx, rpy, rpz, rtx, rty, rtz, s1, s2, s3, objMass;
+    for (size_t e = 0; e < nE; e++, o++) {
+        auto& ob = ext[e];
+        ob->owner = (bodyID_t)o;
+        xyz[3 * o] = ob->init_pos.x; xyz[3 * o + 1] = ob->init_pos.y; xyz[3 * o + 2] = ob->init_pos.z;
+        qw[o] = ob->init_oriQ.w; qx[o] = ob->init_oriQ.x; qy[o] = ob->init_oriQ.y; qz[o] = ob->init_oriQ.z;
+        fam[o] = (uint8_t)ob->family_code;
+        inertia[o] = (uint16_t)(m_templates.size() + e);
+        m_owner_mass[o] = ob->mass; m_owner_moi[o] = ob->MOI;
+        for (const auto& c : ob->comps) {
+            objOwner.push_back((uint32_t)o); objType.push_back((uint8_t)c.type);
+            objMat.push_back((uint16_t)c.material->load_order); objNormal.push_back(c.normal);
+            rpx.push_back(c.pos.x); rpy.push_back(c.pos.y); rpz.push_back(c.pos.z);
+            rtx.push_back(c.dir.x); rty.push_back(c.dir.y); rtz.push_back(c.dir.z);
+            s1.push_back(c.size1); s2.push_back(0.f); s3.push_back(0.f); objMass.push_back(ob->mass);
+        }
+    }
+    std::vector<uint64_t> voxel(nO);
+    std::vector<uint16_t> lx(nO), ly(nO), lz(nO);
+    dem_host_encode_positions(&sp, xyz.data(), nO, voxel.data(), lx.data(), ly.data(), lz.data());
+    check(dem_upload_analytical(ctx, (uint32_t)objOwner.size(), objOwner.data(), objType.data(), objMat.data(),
+                                objNormal.data(), rpx.data(), rpy.data(), rpz.data(), rtx.data(), rty.data(), rtz.data(),
+                                s1.data(), s2.data(), s3.data(), objMass.data()),
+          "dem_upload_analytical");
+    uploadFamilies();
+    check(dem_upload_owners(ctx, (uint32_t)nO, voxel.data(), lx.data(), ly.data(), lz.data(), qw.data(), qx.data(),
+                            qy.data(), qz.data(), vx.data(), vy.data(), vz.data(), ox.data(), oy.data(), oz.data(),
+                            fam.data(), inertia.data()),
+          "dem_upload_owners");
+    check(dem_upload_spheres(ctx, (uint32_t)sph_owner.size(), sph_owner.data(), sph_comp.data(), sph_mat.data()),
+          "dem_upload_spheres");
+    check(dem_upload_triangles(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_upload_triangles");
+    check(dem_initialize(ctx, 0), "dem_initialize");
+    nOwnerClumps = nC; nOwnerBodies = nO; nSpheres = sph_owner.size();
+    m_sphere_owner = sph_owner;
+    if (!m_trackers.empty()) check(dem_set_option(ctx, "keep_acc", 1.0), "dem_set_option");
+
+    // ---- restart: existing contacts + wildcards of the batches (Structs.h:857-882, dT.cpp:849-881) ----
+    {
+        std::vector<uint32_t> idA, idB;
+        std::vector<uint8_t> type;
+        std::vector<float> wc;
+        size_t sphere_base = 0;
+        for (const auto& b : m_cached_input_clump_batches) {
+            const size_t n = b->contact_pairs.size();
+            const char* names[4] = {"delta_tan_x", "delta_tan_y", "delta_tan_z", "delta_time"};
+            for (size_t i = 0; i < n; i++) {
+                idA.push_back((uint32_t)(sphere_base + b->contact_pairs[i].first));
+                idB.push_back((uint32_t)(sphere_base + b->contact_pairs[i].second));
+                type.push_back(DEM_CNT_SPHERE_SPHERE);
+                for (int k = 0; k < 4; k++) {
+                    auto it = b->contact_wildcards.find(names[k]);
+                    wc.push_back(it != b->contact_wildcards.end() && it->second.size() == n ? it->second[i] : 0.f);
+                }
+            }
+            sphere_base += b->nSpheres;
+        }
+        if (!idA.empty()) check(dem_set_contacts(ctx, idA.size(), idA.data(), idB.data(), type.data(), wc.data()), "dem_set_contacts");
+    }
+    sys_initialized = true;
+    if (verbosity >= INFO)
+        std::cout << "DEM core initialised: " << nC << " clumps, " << nSpheres << " spheres, " << objOwner.size()
+                  << " analytical components; l = " << sp.l << ", voxel bits " << sp.nvXp2 << "/" << sp.nvYp2 << "/"
+                  << sp.nvZp2 << std::endl;
+    // the reference's Initialize ends with a dry run that builds the first contact list (APIPublic.cpp:2207-2212)
+    if (dry_run) DoDynamicsThenSync(0.0);
+}
+
+void DEMSolver::UpdateClumps() {
+    fail("UpdateClumps: adding clumps to an initialised system is not built yet in this core; add all clumps before Initialize().");
+}
+void DEMSolver::ClearCache() {}
+
+void DEMSolver::DoDynamics(double thisCallDuration) {
+    assertInit("DoDynamics");
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    check(dem_do_dynamics(ctx, thisCallDuration), "DoDynamics");
+    m_wall_time_dynamics += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+}
+void DEMSolver::DoDynamicsThenSync(double thisCallDuration) { DoDynamics(thisCallDuration); }
+
+void DEMSolver::ChangeFamily(unsigned int ID_from, unsigned int ID_to) {
+    assertInit("ChangeFamily");
+    if (ID_from > 255 || ID_to > 255) fail("Family numbers must not exceed 255.");
+    std::vector<uint8_t> f(nOwnerBodies);
+    check(dem_download_owner_state(ctx, 0, (uint32_t)nOwnerBodies, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   nullptr, nullptr, nullptr, f.data()), "dem_download_owner_state");
+    for (auto& x : f)
+        if (x == ID_from) x = (uint8_t)ID_to;
+    check(dem_upload_owner_state(ctx, 0, (uint32_t)nOwnerBodies, nullptr, nullptr, nullptr, nullptr, f.data()), "dem_upload_owner_state");
+}
+
+size_t DEMSolver::GetNumContacts() const {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    return (size_t)(s.n_contacts_ss + s.n_contacts_sa + s.n_contacts_st);
+}
+float DEMSolver::GetAvgSphContacts() const {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    return nSpheres ? (float)((double)(s.n_contacts_ss + s.n_contacts_sa + s.n_contacts_st) / (double)nSpheres) : 0.f;
+}
+double DEMSolver::GetSimTime() const {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    return s.sim_time;
+}
+void DEMSolver::ShowThreadCollaborationStats() {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    std::cout << "Number of steps: " << s.n_steps << "\nNumber of contact-list rebuilds: " << s.n_rebuilds
+              << "\nAverage steps per rebuild: " << (s.n_rebuilds ? (double)s.n_steps / (double)s.n_rebuilds : 0.0)
+              << "\n(one in-order CUDA stream: no kT/dT hand-shake, no held-back steps)" << std::endl;
+}
+void DEMSolver::ShowTimingStats() {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    std::cout << "Wall time inside DoDynamics: " << m_wall_time_dynamics << " s for " << s.n_steps << " steps ("
+              << (m_wall_time_dynamics > 0 ? s.n_steps / m_wall_time_dynamics : 0.0) << " steps/s), " << s.kernel_launches
+              << " kernel launches" << std::endl;
+}
+void DEMSolver::ShowMemStats() const {
+    DemStats s;
+    dem_get_stats(ctx, &s);
+    std::cout << "Device memory held by the DEM core: " << s.device_bytes / (1024.0 * 1024.0) << " MiB" << std::endl;
+}
+
+// ---- raw owner access ----
+#define OWNER_GET(...)                                                                                      \
+    assertInit("owner query");                                                                              \
+    if (ownerID >= nOwnerBodies) fail("owner ID out of range");                                             \
+    check(dem_download_owner_state(ctx, ownerID, 1, __VA_ARGS__), "dem_download_owner_state")
+
+float3 DEMSolver::GetOwnerPosition(bodyID_t ownerID) const {
+    assertInit("owner query");
+    if (ownerID >= nOwnerBodies) fail("owner ID out of range");
+    float p[3];
+    check(dem_download_positions(ctx, ownerID, 1, p, nullptr), "dem_download_positions");
+    return make_float3(p[0], p[1], p[2]);
+}
+float3 DEMSolver::GetOwnerVelocity(bodyID_t ownerID) const {
+    float v[3];
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr, nullptr, nullptr);
+    return make_float3(v[0], v[1], v[2]);
+}
+float3 DEMSolver::GetOwnerAngVel(bodyID_t ownerID) const {
+    float v[3];
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr, nullptr);
+    return make_float3(v[0], v[1], v[2]);
+}
+float4 DEMSolver::GetOwnerOriQ(bodyID_t ownerID) const {
+    float q[4];
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, nullptr, nullptr, nullptr);
+    return make_float4(q[1], q[2], q[3], q[0]);  // core stores w,x,y,z; the API speaks x,y,z,w
+}
+float3 DEMSolver::GetOwnerAcc(bodyID_t ownerID) const {
+    float v[3];
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr);
+    return make_float3(v[0], v[1], v[2]);
+}
+float3 DEMSolver::GetOwnerAngAcc(bodyID_t ownerID) const {
+    float v[3];
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr);
+    return make_float3(v[0], v[1], v[2]);
+}
+unsigned int DEMSolver::GetOwnerFamily(bodyID_t ownerID) const {
+    uint8_t f;
+    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &f);
+    return f;
+}
+float DEMSolver::GetOwnerMass(bodyID_t ownerID) const { return m_owner_mass.at(ownerID); }
+float3 DEMSolver::GetOwnerMOI(bodyID_t ownerID) const { return m_owner_moi.at(ownerID); }
+void DEMSolver::SetOwnerPosition(bodyID_t ownerID, float3 pos) {
+    assertInit("SetOwnerPosition");
+    const float p[3] = {pos.x, pos.y, pos.z};
+    check(dem_upload_owner_state(ctx, ownerID, 1, p, nullptr, nullptr, nullptr, nullptr), "dem_upload_owner_state");
+}
+void DEMSolver::SetOwnerVelocity(bodyID_t ownerID, float3 vel) {
+    assertInit("SetOwnerVelocity");
+    const float p[3] = {vel.x, vel.y, vel.z};
+    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, p, nullptr, nullptr), "dem_upload_owner_state");
+}
+void DEMSolver::SetOwnerAngVel(bodyID_t ownerID, float3 angVel) {
+    assertInit("SetOwnerAngVel");
+    const float p[3] = {angVel.x, angVel.y, angVel.z};
+    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, nullptr, p, nullptr), "dem_upload_owner_state");
+}
+void DEMSolver::SetOwnerOriQ(bodyID_t ownerID, float4 oriQ) {
+    assertInit("SetOwnerOriQ");
+    const float q[4] = {oriQ.w, oriQ.x, oriQ.y, oriQ.z};
+    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, q, nullptr, nullptr, nullptr), "dem_upload_owner_state");
+}
+void DEMSolver::SetOwnerFamily(bodyID_t ownerID, unsigned int fam) {
+    assertInit("SetOwnerFamily");
+    const uint8_t f = (uint8_t)fam;
+    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, nullptr, nullptr, &f), "dem_upload_owner_state");
+}
+double DEMSolver::Reduce(int kind) const {
+    assertInit("inspector");
+    double out = 0;
+    check(dem_reduce(ctx, kind, &out), "dem_reduce");
+    return out;
+}
+
+// ---- trackers ----
+bodyID_t DEMTracker::first() {
+    if (obj->obj_type == OWNER_TYPE::CLUMP) return std::static_pointer_cast<DEMClumpBatch>(obj)->first_owner;
+    return std::static_pointer_cast<DEMExternObj>(obj)->owner;
+}
+size_t DEMTracker::count() {
+    if (obj->obj_type == OWNER_TYPE::CLUMP) return std::static_pointer_cast<DEMClumpBatch>(obj)->nClumps;
+    return 1;
+}
+bodyID_t DEMTracker::GetOwnerID(size_t offset) {
+    if (offset >= count()) fail("Tracker offset exceeds the number of owners it tracks.");
+    return first() + (bodyID_t)offset;
+}
+float3 DEMTracker::Pos(size_t offset) { return sys->GetOwnerPosition(GetOwnerID(offset)); }
+float3 DEMTracker::Vel(size_t offset) { return sys->GetOwnerVelocity(GetOwnerID(offset)); }
+float3 DEMTracker::AngVelLocal(size_t offset) { return sys->GetOwnerAngVel(GetOwnerID(offset)); }
+float3 DEMTracker::AngVelGlobal(size_t offset) {
+    const bodyID_t id = GetOwnerID(offset);
+    return Rotate(sys->GetOwnerAngVel(id), sys->GetOwnerOriQ(id));
+}
+float4 DEMTracker::OriQ(size_t offset) { return sys->GetOwnerOriQ(GetOwnerID(offset)); }
+float3 DEMTracker::ContactAcc(size_t offset) { return sys->GetOwnerAcc(GetOwnerID(offset)); }
+float3 DEMTracker::ContactAngAccLocal(size_t offset) { return sys->GetOwnerAngAcc(GetOwnerID(offset)); }
+float DEMTracker::Mass(size_t offset) { return sys->GetOwnerMass(GetOwnerID(offset)); }
+float3 DEMTracker::MOI(size_t offset) { return sys->GetOwnerMOI(GetOwnerID(offset)); }
+unsigned int DEMTracker::GetFamily(size_t offset) { return sys->GetOwnerFamily(GetOwnerID(offset)); }
+std::vector<float3> DEMTracker::Positions() {
+    std::vector<float3> out;
+    for (size_t i = 0; i < count(); i++) out.push_back(Pos(i));
+    return out;
+}
+std::vector<float3> DEMTracker::Velocities() {
+    std::vector<float3> out;
+    for (size_t i = 0; i < count(); i++) out.push_back(Vel(i));
+    return out;
+}
+void DEMTracker::SetPos(float3 pos, size_t offset) { sys->SetOwnerPosition(GetOwnerID(offset), pos); }
+void DEMTracker::SetVel(float3 vel, size_t offset) { sys->SetOwnerVelocity(GetOwnerID(offset), vel); }
+void DEMTracker::SetAngVel(float3 angVel, size_t offset) { sys->SetOwnerAngVel(GetOwnerID(offset), angVel); }
+void DEMTracker::SetOriQ(float4 oriQ, size_t offset) { sys->SetOwnerOriQ(GetOwnerID(offset), oriQ); }
+void DEMTracker::SetFamily(unsigned int fam_num, size_t offset) { sys->SetOwnerFamily(GetOwnerID(offset), fam_num); }
+
+// ---- inspectors ----
+DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(sim) {
+    if (quantity == "clump_max_z") kind = DEM_REDUCE_MAX_Z;
+    else if (quantity == "clump_min_z") kind = DEM_REDUCE_MIN_Z;
+    else if (quantity == "clump_max_absv" || quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;
+    else if (quantity == "clump_kinetic_energy") kind = DEM_REDUCE_KINETIC_ENERGY;
+    else if (quantity == "clump_mass") kind = DEM_REDUCE_TOTAL_MASS;
+    else fail("Inspector quantity " + quantity + " is not built into this core (available: clump_max_z, clump_min_z, "
+              "clump_max_absv, max_absv, clump_kinetic_energy, clump_mass).");
+}
+float DEMInspector::GetValue() { return (float)sys->Reduce(kind); }
+
+// ---- writers (dT.cpp:1254-1617): CSV only ----
+void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy) const {
+    assertInit("WriteClumpFile");
+    const uint32_t n = (uint32_t)nOwnerClumps;
+    std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n), w(3 * (size_t)n);
+    std::vector<uint8_t> fam(n);
+    check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), w.data(), nullptr,
+                                   nullptr, fam.data()), "dem_download_owner_state");
+    std::ofstream f(outfilename);
+    f << std::setprecision(accuracy);
+    f << "X,Y,Z";
+    if (m_out_content & QUAT) f << ",Qw,Qx,Qy,Qz";
+    f << ",clump_type";
+    if (m_out_content & ABSV) f << ",absv";
+    if (m_out_content & VEL) f << ",v_x,v_y,v_z";
+    if (m_out_content & ANG_VEL) f << ",w_x,w_y,w_z";
+    if (m_out_content & FAMILY) f << ",family";
+    f << "\n";
+    for (uint32_t i = 0; i < n; i++) {
+        f << pos[3 * i] << "," << pos[3 * i + 1] << "," << pos[3 * i + 2];
+        if (m_out_content & QUAT) f << "," << q[4 * i] << "," << q[4 * i + 1] << "," << q[4 * i + 2] << "," << q[4 * i + 3];
+        f << "," << m_templates[m_owner_type_mark[i]]->m_name;
+        if (m_out_content & ABSV) f << "," << std::sqrt(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+        if (m_out_content & VEL) f << "," << v[3 * i] << "," << v[3 * i + 1] << "," << v[3 * i + 2];
+        if (m_out_content & ANG_VEL) f << "," << w[3 * i] << "," << w[3 * i + 1] << "," << w[3 * i + 2];
+        if (m_out_content & FAMILY) f << "," << (unsigned)fam[i];
+        f << "\n";
+    }
+}
+void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const {
+    assertInit("WriteSphereFile");
+    const uint32_t n = (uint32_t)nOwnerClumps;
+    std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n);
+    check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), nullptr, nullptr,
+                                   nullptr, nullptr), "dem_download_owner_state");
+    std::ofstream f(outfilename);
+    f << "x,y,z,r";
+    if (m_out_content & ABSV) f << ",absv";
+    f << "\n";
+    for (uint32_t i = 0; i < n; i++) {
+        const auto& t = m_templates[m_owner_type_mark[i]];
+        const float4 quat = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);
+        for (unsigned int k = 0; k < t->nComp; k++) {
+            const float3 r = Rotate(t->relPos[k], quat);
+            f << pos[3 * i] + r.x << "," << pos[3 * i + 1] + r.y << "," << pos[3 * i + 2] + r.z << "," << t->radii[k];
+            if (m_out_content & ABSV) f << "," << std::sqrt(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+            f << "\n";
+        }
+    }
+}
+void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float force_thres) const {
+    assertInit("WriteContactFile");
+    uint64_t n = 0;
+    check(dem_download_contacts(ctx, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_download_contacts");
+    std::vector<uint32_t> a(n), b(n);
+    std::vector<uint8_t> t(n);
+    std::vector<float> wc(4 * n), fr(3 * n);
+    if (n) check(dem_download_contacts(ctx, n, &n, a.data(), b.data(), t.data(), wc.data(), fr.data()), "dem_download_contacts");
+    std::ofstream f(outfilename);
+    f << "contact_type,A,B,f_x,f_y,f_z,delta_tan_x,delta_tan_y,delta_tan_z,delta_time\n";
+    for (uint64_t i = 0; i < n; i++) {
+        const float fm = std::sqrt(fr[3 * i] * fr[3 * i] + fr[3 * i + 1] * fr[3 * i + 1] + fr[3 * i + 2] * fr[3 * i + 2]);
+        if (!no_recording_contact_forces && fm < force_thres) continue;
+        f << (t[i] == DEM_CNT_SPHERE_SPHERE ? "SS" : "SA") << "," << a[i] << "," << b[i] << "," << fr[3 * i] << "," << fr[3 * i + 1]
+          << "," << fr[3 * i + 2] << "," << wc[4 * i] << "," << wc[4 * i + 1] << "," << wc[4 * i + 2] << "," << wc[4 * i + 3] << "\n";
+    }
+}
+
+static std::vector<std::vector<std::string>> read_csv(const std::string& fn, std::vector<std::string>& header) {
+    std::ifstream f(fn);
+    if (!f) fail("File " + fn + " cannot be opened.");
+    std::string line;
+    std::getline(f, line);
+    std::stringstream hs(line);
+    std::string c;
+    while (std::getline(hs, c, ',')) header.push_back(c);
+    std::vector<std::vector<std::string>> rows;
+    while (std::getline(f, line)) {
+        if (line.empty()) continue;
+        std::stringstream ss(line);
+        std::vector<std::string> r;
+        while (std::getline(ss, c, ',')) r.push_back(c);
+        rows.push_back(r);
+    }
+    return rows;
+}
+std::unordered_map<std::string, std::vector<float3>> DEMSolver::ReadClumpXyzFromCsv(
+    const std::string& infilename, const std::string& clump_header, const std::string& x_header,
+    const std::string& y_header, const std::string& z_header) {
+    std::vector<std::string> h;
+    auto rows = read_csv(infilename, h);
+    auto col = [&](const std::string& id) { return (size_t)(std::find(h.begin(), h.end(), id) - h.begin()); };
+    const size_t ic = col(clump_header), ix = col(x_header), iy = col(y_header), iz = col(z_header);
+    if (std::max(std::max(ic, ix), std::max(iy, iz)) >= h.size()) fail("ReadClumpXyzFromCsv: a requested column is missing in " + infilename);
+    std::unordered_map<std::string, std::vector<float3>> out;
+    for (const auto& r : rows)
+        out[r[ic]].push_back(make_float3((float)atof(r[ix].c_str()), (float)atof(r[iy].c_str()), (float)atof(r[iz].c_str())));
+    return out;
+}
+std::unordered_map<std::string, std::vector<float4>> DEMSolver::ReadClumpQuatFromCsv(
+    const std::string& infilename, const std::string& clump_header, const std::string& qw_header,
+    const std::string& qx_header, const std::string& qy_header, const std::string& qz_header) {
+    std::vector<std::string> h;
+    auto rows = read_csv(infilename, h);
+    auto col = [&](const std::string& id) { return (size_t)(std::find(h.begin(), h.end(), id) - h.begin()); };
+    const size_t ic = col(clump_header), iw = col(qw_header), ix = col(qx_header), iy = col(qy_header), iz = col(qz_header);
+    if (std::max(std::max(ic, iw), std::max(ix, std::max(iy, iz))) >= h.size())
+        fail("ReadClumpQuatFromCsv: a requested column is missing in " + infilename);
+    std::unordered_map<std::string, std::vector<float4>> out;
+    for (const auto& r : rows)
+        out[r[ic]].push_back(make_float4((float)atof(r[ix].c_str()), (float)atof(r[iy].c_str()), (float)atof(r[iz].c_str()),
+                                         (float)atof(r[iw].c_str())));
+    return out;
+}
+
+}  // namespace deme

@@ -299,3 +299,39 @@ def test_momentum_conservation_without_walls(built):
     scale = np.abs(st["vel"][:n]).sum() * float(f.MassProperties[0])
     assert np.abs(p1 - p0).max() < 1e-4 * scale, (p0, p1, scale)
     eng.close()
+
+
+def test_cpp_facade_demo_scripts(built):
+    """The deme::DEMSolver facade (dem-engine_b200/host) drives the core from reference-style C++ demo scripts."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    host = os.path.join(root, "dem-engine_b200", "host")
+    subprocess.run(["make", "-C", host], check=True, stdout=subprocess.DEVNULL)
+    env = dict(os.environ, DEME_DATA_PATH=os.path.join(host, "data"))
+    out = subprocess.run([os.path.join(host, "demo", "DEMdemo_SphereCollide")], capture_output=True, text=True, env=env,
+                         timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    cor = float(out.stdout.split("CoR measured =")[1].split()[0])
+    # the same two-sphere collision through the oracle (the reference's Hertzian kernel gives e = 0.5035 for CoR = 0.6:
+    # its normal force is allowed to turn attractive at the end of the contact)
+    po = _oracle()
+    sc = scenes.Scene()
+    m = sc.load_material(E=1e8, nu=0.3, CoR=0.6, mu=0.0, Crr=0.0)
+    t = sc.load_sphere_type(11728., 1., m)
+    sc.add_clumps(t, [[-1.05, 0, 0]], vel=(1, 0, 0))
+    sc.add_clumps(t, [[1.05, 0, 0]], vel=(-1, 0, 0))
+    sc.box, sc.G, sc.h, sc.cd_update_freq, sc.approxMaxVel, sc.expSafetyAdder = (10, 10, 10), (0, 0, 0), 2e-5, 10, 3.0, 1.0
+    w = po.world_from_flat(scenes.flatten(sc))
+    w.step(5100, cd_every=10)
+    assert abs(cor - (w.vX[1] - w.vX[0]) / 2) < 2e-4, (out.stdout, w.vX[:2])
+    out = subprocess.run([os.path.join(host, "demo", "DEMdemo_ClumpBed"), "3"], capture_output=True, text=True, env=env,
+                         timeout=600, cwd="/tmp")
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "DEMdemo_ClumpBed exiting" in out.stdout
+    lines = [l for l in out.stdout.splitlines() if l.startswith("Frame")]
+    assert len(lines) == 3
+    lid = [float(l.split("lid z =")[1].split(",")[0]) for l in lines]
+    # the lid moves down at the prescribed 0.2 m/s: 1 mm per 0.005 s frame
+    assert abs((lid[0] - lid[1]) - 0.001) < 2e-5 and abs((lid[1] - lid[2]) - 0.001) < 2e-5, lid
+    assert "v_z = 0" in out.stdout.split("Lid after being fixed:")[1]
