@@ -104,6 +104,11 @@ def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, bu
     f = scenes.flatten(sc)
     w = pyoracle.world_from_flat(f)
     use_ref = pyoracle.ref() is not None
+    cores = os.cpu_count() or 1
+    if use_ref:
+        pyoracle.ref_set_threads(cores)
+    else:
+        cores = 1
     w.step(settle_steps, cd_every=cd_update_freq, use_ref=use_ref)
     t0 = time.perf_counter()
     done = 0
@@ -115,9 +120,10 @@ def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, bu
             break
     dt = time.perf_counter() - t0
     rate = done * f.nClumps / dt
-    return rate, ("reference" if use_ref else "port"), 1, (
-        "%d clumps (%dx%dx%d lattice of the same bed), %d steps after %d settling steps, single host thread; "
-        "value extrapolated linearly in clump count to the 1M-clump workload" % (f.nClumps, dims[0], dims[1], dims[2], done, settle_steps)), done, dt
+    return rate, ("reference" if use_ref else "port"), cores, (
+        "%d clumps (%dx%dx%d lattice of the same bed), %d steps after %d settling steps, the reference's own force / "
+        "accumulation / integration kernels on %d host threads (contact rebuild serial); value extrapolated linearly "
+        "in clump count to the 1M-clump workload" % (f.nClumps, dims[0], dims[1], dims[2], done, settle_steps, cores)), done, dt
 
 
 def main():
@@ -127,7 +133,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clumps", type=int, default=1000000)
-    ap.add_argument("--settle-steps", type=int, default=12000, help="untimed gravity-settling steps before warm-up")
+    ap.add_argument("--settle-steps", type=int, default=80000,
+                    help="untimed gravity-settling steps before warm-up (0.4 s of simulated time: the bed is at rest)")
     ap.add_argument("--cd-update-freq", type=int, default=20)
     ap.add_argument("--spacing", type=float, default=2.7, help="initial lattice spacing in units of the clump scale")
     ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
@@ -147,7 +154,7 @@ def main():
         if rank != 0:
             return 0
         rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, max(args.steps, 1), args.cd_update_freq,
-                                                             args.spacing, settle_steps=min(args.settle_steps, 2000),
+                                                             args.spacing, settle_steps=min(args.settle_steps, 4000),
                                                              budget_s=60.0)
         value = rate / float(args.clumps)
         line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
@@ -243,7 +250,7 @@ def main():
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (f64 centre distance)", "data": "synthetic",
         "config": {"workload": workload, "lattice": list(dims), "clumps_total": n_total_clumps,
-                   "spheres_per_gpu": int(f.nSpheres), "contacts_ss": C_ss, "contacts_sa": C_sa,
+                   "spheres_per_gpu": int(f.nSpheres), "contacts_ss": C_ss, "contacts_ss_touching": int(st.n_contacts_ss_touching), "contacts_sa": C_sa,
                    "cd_update_freq": args.cd_update_freq, "settle_steps": args.settle_steps,
                    "force_record": False, "l2": "per-step working set > 126 MB L2 (no flush needed)",
                    "parallelism": "1 GPU" if world == 1 else "%d independent x-slabs (halo exchange not built yet)" % world},
@@ -259,8 +266,8 @@ def main():
         "clocks": sampler.summary(),
     }
     if not args.no_cpu_baseline and world == 1:
-        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, 200, args.cd_update_freq, args.spacing,
-                                                             settle_steps=1000, budget_s=20.0)
+        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, 400, args.cd_update_freq, args.spacing,
+                                                             settle_steps=4000, budget_s=20.0)
         line["cpu_baseline"] = {"value": rate / float(args.clumps), "unit": unit, "cores": cores, "kind": kind,
                                 "sample": desc}
     print(json.dumps(line))

@@ -13,6 +13,9 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>  // types only: the library is bound with dlopen so that single-GPU use needs no NCCL at all
+
 #include "dem_kernels.h"
 
 using namespace demb;
@@ -20,6 +23,57 @@ static_assert(sizeof(DemSimParams) == 120, "DemSimParams layout is part of the C
 static_assert(sizeof(DemPrescription) == 88 && sizeof(DemPrescription) == sizeof(Prescr), "DemPrescription layout");
 
 namespace {
+
+// NCCL entry points, resolved at run time from the NCCL already loaded in the process (torch's) or the system one
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load() {
+        if (handle) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+        }
+        if (!handle) return false;
+#define NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(handle, name)); if (!field) return false;
+        NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        NCCL_SYM(CommDestroy, "ncclCommDestroy") NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv")
+        NCCL_SYM(AllReduce, "ncclAllReduce") NCCL_SYM(AllGather, "ncclAllGather") NCCL_SYM(GroupStart, "ncclGroupStart")
+        NCCL_SYM(GroupEnd, "ncclGroupEnd") NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+        return true;
+    }
+};
+NcclApi g_nccl;
+
+// domain decomposition state of one rank
+struct MgState {
+    bool on = false;
+    int rank = 0, world = 1;
+    ncclComm_t comm = nullptr;
+    float cut_lo = 0.f, cut_hi = 0.f;
+    uint8_t* d_flag = nullptr;
+    uint32_t* d_active_list = nullptr;
+    uint32_t* d_counts = nullptr;      // 8 words
+    uint32_t* d_allcounts = nullptr;   // world x 8 words
+    uint32_t* d_send_gid[2] = {nullptr, nullptr};
+    uint32_t* d_recv_gid[2] = {nullptr, nullptr};
+    void* d_sendbuf[2] = {nullptr, nullptr};
+    void* d_recvbuf[2] = {nullptr, nullptr};
+    uint32_t cap = 0;
+    uint32_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}, n_active = 0, n_own = 0;
+    uint64_t halo_bytes = 0;  // bytes sent per step by this rank
+};
 
 struct ListBuf {
     uint2* pair = nullptr;
@@ -115,6 +169,8 @@ struct DemCtx {
     int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    MgState mg;
+    float rclump = 0.f;
     int sa_grid = 148;
 };
 
@@ -209,6 +265,7 @@ DevParams make_params(const DemCtx* c) {
     P.sn = as_list(c->lists[1][c->cur]);
     P.sa = as_list(c->lists[2][c->cur]);
     P.flags = c->d_flags;
+    if (c->mg.on) { P.active = c->mg.d_flag; P.active_list = c->mg.d_active_list; P.nActive = c->mg.n_active; }
     P.maxvel = c->d_maxvel + c->maxvel_slot;
     P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
     P.errOutVel = s.errOutVel;
@@ -225,7 +282,7 @@ CdParams make_cd(const DemCtx* c) {
         const float e = 2.f * (c->sp.userBoxMin[k] - c->sp.LBF[k]) + (c->sp.userBoxMax[k] - c->sp.userBoxMin[k]);
         if (e > C.ext[k]) C.ext[k] = e;
     }
-    C.rmax = c->rmax; C.max_extra = c->max_extra; C.max_cells = c->max_cells; C.any_mask = c->any_mask;
+    C.rmax = c->rmax; C.rclump = c->rclump; C.max_extra = c->max_extra; C.max_cells = c->max_cells; C.any_mask = c->any_mask;
     C.capacity = (uint32_t)c->capacity;
     C.sphF = c->d_sphF;
     C.keys[0] = c->d_keys[0]; C.keys[1] = c->d_keys[1]; C.vals[0] = c->d_vals[0]; C.vals[1] = c->d_vals[1];
@@ -262,7 +319,83 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
     return DEM_OK;
 }
 
+#define NC(call)                                                                                                      \
+    do {                                                                                                              \
+        ncclResult_t r_ = (call);                                                                                     \
+        if (r_ != ncclSuccess)                                                                                        \
+            return fail(ctx, DEM_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
+    } while (0)
+
+MgParams make_mg(const DemCtx* c) {
+    MgParams M;
+    memset(&M, 0, sizeof(M));
+    const MgState& g = c->mg;
+    M.flag = g.d_flag; M.active_list = g.d_active_list; M.counts = g.d_counts;
+    M.send_gid[0] = g.d_send_gid[0]; M.send_gid[1] = g.d_send_gid[1];
+    M.send_cap = g.cap; M.nClumpOwners = c->nClumpOwners;
+    M.cut_lo = g.cut_lo; M.cut_hi = g.cut_hi; M.grid = c->d_grid;
+    M.has_left = g.rank > 0; M.has_right = g.rank < g.world - 1;
+    return M;
+}
+
+// send the {state, spin} records of my halo owners to both neighbours and scatter theirs into my global slots
+int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches) {
+    MgState& g = ctx->mg;
+    cudaStream_t s = ctx->stream;
+    for (int d = 0; d < 2; d++) *launches += launch_mg_pack(P, g.d_send_gid[d], g.n_send[d], g.d_sendbuf[d], s);
+    NC(g_nccl.GroupStart());
+    for (int d = 0; d < 2; d++) {
+        const int peer = g.rank + (d == 0 ? -1 : 1);
+        if (peer < 0 || peer >= g.world) continue;
+        if (g.n_send[d]) NC(g_nccl.Send(g.d_sendbuf[d], (size_t)g.n_send[d] * 80, ncclUint8, peer, g.comm, s));
+        if (g.n_recv[d]) NC(g_nccl.Recv(g.d_recvbuf[d], (size_t)g.n_recv[d] * 80, ncclUint8, peer, g.comm, s));
+    }
+    NC(g_nccl.GroupEnd());
+    for (int d = 0; d < 2; d++)
+        *launches += launch_mg_unpack(P, g.d_recv_gid[d], g.n_recv[d], g.d_recvbuf[d], flag_or_null, s);
+    return DEM_OK;
+}
+
+// at a rebuild: re-decide ownership, exchange the halo membership lists and the halo records, list the active owners
+int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches) {
+    MgState& g = ctx->mg;
+    cudaStream_t s = ctx->stream;
+    MgParams M = make_mg(ctx);
+    *launches += launch_mg_classify(P, M, s);
+    NC(g_nccl.AllGather(g.d_counts, g.d_allcounts, 8, ncclUint32, g.comm, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_allcounts, sizeof(uint32_t) * 8 * g.world, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint32_t* all = ctx->h_pinned + 40;
+    for (int r = 0; r < g.world; r++)
+        if (all[8 * r + 1] > g.cap || all[8 * r + 2] > g.cap)
+            return fail(ctx, DEM_ERR_CAPACITY, "halo of rank %d holds %u / %u owners, more than the buffer of %u", r,
+                        all[8 * r + 1], all[8 * r + 2], g.cap);
+    g.n_send[0] = all[8 * g.rank + 1];
+    g.n_send[1] = all[8 * g.rank + 2];
+    g.n_recv[0] = g.rank > 0 ? all[8 * (g.rank - 1) + 2] : 0;            // what my left neighbour sends to its right
+    g.n_recv[1] = g.rank < g.world - 1 ? all[8 * (g.rank + 1) + 1] : 0;  // what my right neighbour sends to its left
+    g.halo_bytes = ((uint64_t)g.n_send[0] + g.n_send[1]) * 80;
+    NC(g_nccl.GroupStart());
+    for (int d = 0; d < 2; d++) {
+        const int peer = g.rank + (d == 0 ? -1 : 1);
+        if (peer < 0 || peer >= g.world) continue;
+        if (g.n_send[d]) NC(g_nccl.Send(g.d_send_gid[d], g.n_send[d], ncclUint32, peer, g.comm, s));
+        if (g.n_recv[d]) NC(g_nccl.Recv(g.d_recv_gid[d], g.n_recv[d], ncclUint32, peer, g.comm, s));
+    }
+    NC(g_nccl.GroupEnd());
+    int rc = mg_halo_exchange(ctx, P, g.d_flag, launches);
+    if (rc) return rc;
+    *launches += launch_mg_active_list(P, M, s);
+    CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_counts, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    g.n_own = ctx->h_pinned[40];
+    g.n_active = ctx->h_pinned[43];
+    return DEM_OK;
+}
+
 // one contact-list rebuild into the "other" buffers, then swap. Syncs once (reads the counts back).
+int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches);
+
 int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
     cudaEvent_t sev[8];
     if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
@@ -276,7 +409,19 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         cudaStream_t s = ctx->stream;
         CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 3, s));  // [3] (velocity) is only cleared by the host
         if (stage_us) cudaEventRecord(sev[0], s);
-        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, s);
+        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, 0, s);
+        if (ctx->mg.on)  // the cell grid (hence the sorted order and the A/B roles) must be the same on every rank
+            NC(g_nccl.AllReduce(P.maxvel, P.maxvel, 1, ncclFloat32, ncclMax, ctx->mg.comm, s));
+        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 1, s);
+        if (ctx->mg.on) {
+            int rc = mg_redistribute(ctx, P, &launches);
+            if (rc) return rc;
+            P = make_params(ctx);  // nActive changed
+            P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
+            P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
+            P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
+        }
+        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 2, s);
         if (stage_us) cudaEventRecord(sev[1], s);
         int sorted_buf = -1;  // -1: counting sort inside the sweep stage
         if (ctx->sort_mode == 0) launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
@@ -287,6 +432,8 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         const ContactList* NL[3] = {&P.ss, &P.sn, &P.sa};
         for (int kind = 0; kind < 3; kind++)  // {clamped count, demand}
             CK(cudaMemcpyAsync(ctx->h_pinned + 32 + 2 * kind, NL[kind]->count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        if (ctx->mg.on)  // every rank must see the same verdict, or the ranks fall out of step inside NCCL
+            NC(g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclUint32, ncclMax, ctx->mg.comm, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_flags, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s));
         CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
@@ -302,6 +449,9 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
                         "an owner has a non-finite or too large velocity (max seen %.6g, limit %.6g) at t=%.9g",
                         ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
         }
+        if (ctx->h_pinned[2] != 0 && ctx->mg.on)
+            return fail(ctx, DEM_ERR_CAPACITY, "a contact list or halo buffer overflowed on some rank (flags %u); raise "
+                        "the contact capacity passed to dem_initialize", ctx->h_pinned[2]);
         if (ctx->h_pinned[2] != 0) {
             // capacity overflow: grow every list, keep the old lists (history source) intact, redo the rebuild
             ctx->overflow_seen++;
@@ -359,6 +509,12 @@ int enqueue_step(DemCtx* ctx) {
         launch_force_sa(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
     launch_integrate(P, ctx->stream);
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
+    if (ctx->mg.on) {
+        int l = 0;
+        int rc = mg_halo_exchange(ctx, P, nullptr, &l);
+        if (rc) return rc;
+        ctx->launches += l;
+    }
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
     ctx->n_steps++;
     ctx->steps_since_rebuild++;
@@ -457,7 +613,7 @@ int dem_ctx_create(DemCtx** out, int device) {
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
-    cudaHostAlloc((void**)&ctx->h_pinned, 64 * sizeof(uint32_t), cudaHostAllocDefault);
+    cudaHostAlloc((void**)&ctx->h_pinned, 256 * sizeof(uint32_t), cudaHostAllocDefault);
     if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
     for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
     *out = ctx;
@@ -468,6 +624,16 @@ int dem_ctx_destroy(DemCtx* ctx) {
     if (!ctx) return DEM_ERR_INVALID;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
+    {
+        MgState& g = ctx->mg;
+        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_counts); dfree(g.d_allcounts);
+        for (int d = 0; d < 2; d++) {
+            dfree(g.d_send_gid[d]); dfree(g.d_recv_gid[d]);
+            if (g.d_sendbuf[d]) cudaFree(g.d_sendbuf[d]);
+            if (g.d_recvbuf[d]) cudaFree(g.d_recvbuf[d]);
+        }
+    }
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int k = 0; k < 5; k++)
@@ -511,9 +677,11 @@ int dem_upload_templates(DemCtx* ctx, uint32_t nComp, const float* radii, const 
     if (nComp > 65535) return fail(ctx, DEM_ERR_INVALID, "more than 65535 distinct clump components");
     ctx->h_comp.resize(nComp);
     ctx->rmax = 0.f;
+    ctx->rclump = 0.f;
     for (uint32_t i = 0; i < nComp; i++) {
         ctx->h_comp[i] = make_float4(relX[i], relY[i], relZ[i], radii[i]);
         ctx->rmax = std::max(ctx->rmax, radii[i]);
+        ctx->rclump = std::max(ctx->rclump, std::sqrt(relX[i] * relX[i] + relY[i] * relY[i] + relZ[i] * relZ[i]) + radii[i]);
     }
     ctx->h_massprop.resize(nMassProps);
     for (uint32_t i = 0; i < nMassProps; i++) ctx->h_massprop[i] = make_float4(mass[i], moiX[i], moiY[i], moiZ[i]);
@@ -1026,6 +1194,79 @@ int dem_reduce(DemCtx* ctx, int kind, double* out) {
     return DEM_OK;
 }
 
+int dem_mgpu_unique_id(uint8_t out[128]) {
+    if (!out) return DEM_ERR_INVALID;
+    if (!g_nccl.load()) return DEM_ERR_INVALID;
+    ncclUniqueId id;
+    if (g_nccl.GetUniqueId(&id) != ncclSuccess) return DEM_ERR_CUDA;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    memcpy(out, &id, 128);
+    return DEM_OK;
+}
+
+int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, float* hi) {
+    if (!p || world < 1 || rank < 0 || rank >= world || !lo || !hi) return DEM_ERR_INVALID;
+    // equal-width slabs of the user's box along x, in LBF-relative coordinates; the end slabs extend to infinity
+    const double x0 = (double)p->userBoxMin[0] - (double)p->LBF[0], x1 = (double)p->userBoxMax[0] - (double)p->LBF[0];
+    const double w = (x1 - x0) / world;
+    *lo = (rank == 0) ? -3.0e38f : (float)(x0 + w * rank);
+    *hi = (rank == world - 1) ? 3.0e38f : (float)(x0 + w * (rank + 1));
+    return DEM_OK;
+}
+
+int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]) {
+    if (!ctx || !ctx->initialized || !unique_id || world < 1 || rank < 0 || rank >= world) return DEM_ERR_INVALID;
+    if (world == 1) return DEM_OK;
+    if (!g_nccl.load()) return fail(ctx, DEM_ERR_INVALID, "NCCL (libnccl.so.2) could not be loaded");
+    CK(cudaSetDevice(ctx->device));
+    MgState& g = ctx->mg;
+    g.rank = rank; g.world = world;
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    NC(g_nccl.CommInitRank(&g.comm, world, id, rank));
+    dem_host_slab_bounds(&ctx->sp, world, rank, &g.cut_lo, &g.cut_hi);
+    const uint32_t nO = ctx->nOwners;
+    // halo buffers: a quarter of the owners per side is far more than a slab's boundary layer ever holds
+    g.cap = std::max<uint32_t>(4096u, nO / (world > 2 ? 2u : 4u));
+    int rc;
+    if ((rc = dalloc(ctx, &g.d_flag, nO))) return rc;
+    if ((rc = dalloc(ctx, &g.d_active_list, nO))) return rc;
+    if ((rc = dalloc(ctx, &g.d_counts, 8))) return rc;
+    if ((rc = dalloc(ctx, &g.d_allcounts, 8 * (size_t)world))) return rc;
+    for (int d = 0; d < 2; d++) {
+        if ((rc = dalloc(ctx, &g.d_send_gid[d], g.cap))) return rc;
+        if ((rc = dalloc(ctx, &g.d_recv_gid[d], g.cap))) return rc;
+        CK(cudaMalloc(&g.d_sendbuf[d], (size_t)g.cap * 80));
+        CK(cudaMalloc(&g.d_recvbuf[d], (size_t)g.cap * 80));
+        ctx->device_bytes += 2 * (size_t)g.cap * 80;
+    }
+    // initial ownership from the uploaded positions: own inside my slab, unknown elsewhere (the first rebuild brings
+    // the ghosts in); replicated analytical owners are owned everywhere
+    std::vector<uint8_t> flag(nO, 0);
+    const DemSimParams& p = ctx->sp;
+    for (uint32_t o = 0; o < nO; o++) {
+        if (o >= ctx->nClumpOwners) { flag[o] = 1; continue; }
+        const OwnerPos& s = ctx->h_state[o].pos;
+        const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
+        const float x = (float)((double)vx * p.voxelSize + (double)s.lx * p.l);
+        flag[o] = (x >= g.cut_lo && x < g.cut_hi) ? 1 : 0;
+    }
+    CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
+    if (ctx->sort_mode != 1) ctx->sort_mode = 1;  // the radix path has no notion of inactive spheres
+    g.on = true;
+    ctx->need_rebuild = true;
+    ctx->need_maxvel = true;
+    return DEM_OK;
+}
+
+int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]) {
+    if (!ctx || !out) return DEM_ERR_INVALID;
+    const MgState& g = ctx->mg;
+    out[0] = g.n_own; out[1] = g.n_active; out[2] = g.n_send[0]; out[3] = g.n_send[1]; out[4] = g.halo_bytes;
+    out[5] = g.on ? (uint64_t)g.world : 1;
+    return DEM_OK;
+}
+
 int dem_set_option(DemCtx* ctx, const char* name, double value) {
     if (!ctx || !name) return DEM_ERR_INVALID;
     const std::string n(name);
@@ -1064,6 +1305,12 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
         CK(cudaEventRecord(ctx->ev[3], s));
         launch_integrate(P, s);
         ctx->maxvel_slot ^= 1;
+        if (ctx->mg.on) {
+            int l = 0;
+            int rc = mg_halo_exchange(ctx, P, nullptr, &l);
+            if (rc) return rc;
+            ctx->launches += l;
+        }
         CK(cudaEventRecord(ctx->ev[4], s));
         ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
         ctx->n_steps++;

@@ -111,6 +111,11 @@ struct DevParams {
     float4* spin;     // body-frame angular velocity omgBar xyz, w = bits(inertiaPropOffset)
     Wrench* wrench;
     Wrench* acc_out;  // optional per-owner {a, alpha} read-out (nullptr = off)
+    // domain decomposition (nullptr / 0 on a single GPU): per-owner activity flag (0 unknown, 1 own, 2 ghost) and the
+    // compact list of active owners the integrator walks
+    const uint8_t* active;
+    const uint32_t* active_list;
+    uint32_t nActive;
     // spheres / templates
     const uint2* sph;
     const float4* comp;      // {relx, rely, relz, radius}

@@ -10,6 +10,8 @@ struct GridInfo {
     float cs, inv_cs;
     uint32_t nbx, nby, nbz, ncells;
     float max_margin, maxvel;
+    float halo;  // domain decomposition: width of the ghost layer for this rebuild
+    float pad_;
 };
 
 // analytical component resolved to world space for one rebuild
@@ -27,6 +29,7 @@ struct CdParams {
     GridInfo* grid;
     float ext[3];        // extent of the binned region (target box size, LBF-relative)
     float rmax;          // largest template sphere radius
+    float rclump;        // upper bound of the circumscribed radius of any clump about its centre of mass
     float max_extra;     // largest family extra margin
     uint32_t max_cells;  // capacity of the cell table
     uint32_t any_mask;   // != 0 when any family pair is masked
@@ -44,12 +47,31 @@ struct CdParams {
     uint32_t* scan_tmp;   // block sums for the scans
 };
 
+// multi-GPU (slab decomposition) bookkeeping passed to the kernels of kernels_mgpu.cu
+struct MgParams {
+    uint8_t* flag;            // per global owner: 0 unknown here, 1 own, 2 ghost
+    uint32_t* active_list;    // compact list of active owners (own + ghost)
+    uint32_t* counts;         // device: [0] own [1] send-left [2] send-right [3] active
+    uint32_t* send_gid[2];    // own owners inside the halo of the left / right cut
+    uint32_t send_cap;
+    uint32_t nClumpOwners;    // owners >= this index are analytical / replicated
+    float cut_lo, cut_hi;     // my slab in LBF-relative x
+    const GridInfo* grid;     // halo width of this rebuild is grid->halo
+    int has_left, has_right;
+};
+
+int launch_mg_classify(const DevParams& P, const MgParams& M, cudaStream_t s);
+int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* buf, cudaStream_t s);
+int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s);
+int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s);
+
 void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s);
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 void launch_integrate(const DevParams& P, cudaStream_t s);
 
 // rebuild stages; each returns the number of kernels it launched
-int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, cudaStream_t s);
+// stage 0: max |v| (when stale); stage 1: grid + margin decision; stage 2: analytical prep, clears, sphere keys + SA list
+int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, int stage, cudaStream_t s);
 int launch_cd_sort(const DevParams& P, const CdParams& C, int key_bits, cudaStream_t s, int* out_buf);
 int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev = nullptr);
 int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* total, cudaStream_t s);

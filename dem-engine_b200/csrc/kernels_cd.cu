@@ -33,7 +33,7 @@ __device__ __forceinline__ float owner_margin(const DevParams& P, float absv, ui
 __global__ void k_maxvel(const __grid_constant__ DevParams P, float errOutVel) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     float a = 0.f;
-    if (o < P.nOwners) {
+    if (o < P.nOwners && (!P.active || P.active[o] != 0)) {
         const float4 v = P.state[o].vel;
         a = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
         if (!isfinite(a) || a > errOutVel) atomicOr(&P.flags[3], 1u);
@@ -71,6 +71,10 @@ __global__ void k_grid_setup(const __grid_constant__ DevParams P, const __grid_c
     g.ncells = nbx * nby * nbz;
     g.max_margin = margin;
     g.maxvel = vmax;
+    // ghost layer: two clumps can touch up to 2 (R_clump + margin) apart; one more margin on each side covers the
+    // distance an owner can travel before the next rebuild (that bound is what the margin is made of)
+    g.halo = 2.f * (C.rclump + margin) + 2.f * margin;
+    g.pad_ = 0.f;
     *C.grid = g;
 }
 
@@ -141,14 +145,23 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t count, uint32_t* cursor)
 __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ CdParams C) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < P.nSpheres;
+    bool valid = i < P.nSpheres;
     uint32_t nsa = 0, samask = 0;
     float3 sp = f3(0.f, 0.f, 0.f);
     uint2 s = make_uint2(0, 0);
     uint32_t family = 0;
     if (valid) {
-        const GridInfo g = *C.grid;
         s = P.sph[i];
+        if (P.active && P.active[s.x] == 0) {
+            // owner not held by this rank (domain decomposition): the sphere takes no part in this rebuild
+            C.keys[0][i] = 0xffffffffu;
+            P.sa.seg_start[i] = 0;
+            P.sa.seg_count[i] = 0;
+            valid = false;
+        }
+    }
+    if (valid) {
+        const GridInfo g = *C.grid;
         OwnerPos pos;
         float4 q, v;
         {
@@ -449,7 +462,9 @@ __global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevP
                                                     const __grid_constant__ CdParams C) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.nSpheres) return;
-    C.keys[1][C.cellStart[C.keys[0][i]] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
+    const uint32_t key = C.keys[0][i];
+    if (key == 0xffffffffu) return;  // inactive on this rank
+    C.keys[1][C.cellStart[key] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
 }
 
 // gather into cell order; inside a cell the spheres are ranked by sphere id, which makes the result identical to a
@@ -457,7 +472,7 @@ __global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevP
 __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant__ DevParams P,
                                                           const __grid_constant__ CdParams C) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.nSpheres) return;
+    if (j >= C.cellStart[C.max_cells]) return;  // number of active spheres (== nSpheres on a single GPU)
     const uint32_t i = C.keys[1][j];
     const uint32_t key = C.keys[0][i];
     const uint32_t sb = C.cellStart[key], se = C.cellStart[key + 1];
@@ -485,7 +500,13 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
     // One thread per sphere IN SPHERE-ID ORDER (clump by clump), so that the slots claimed below make the contact list
     // owner-major: the force kernel then streams the A side and reduces it inside the warp.
     const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = sid < P.nSpheres;
+    bool valid = sid < P.nSpheres;
+    if (valid && C.keys[0][sid] == 0xffffffffu) {
+        // inactive on this rank: leave empty segments behind so that later history look-ups find nothing stale
+        P.ss.seg_start[sid] = 0; P.ss.seg_count[sid] = 0;
+        P.sn.seg_start[sid] = 0; P.sn.seg_count[sid] = 0;
+        valid = false;
+    }
     const uint32_t j = valid ? C.sortedPos[sid] : 0u;
     uint32_t acc[SWEEP_MAXC];  // staged candidates: sorted index, bit 31 = spheres overlap right now
     uint32_t count = 0, countT = 0;
@@ -605,29 +626,33 @@ __global__ void k_finish_counts(const __grid_constant__ DevParams P, const __gri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, cudaStream_t s) {
+int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, int stage, cudaStream_t s) {
     int launches = 0;
-    if (need_maxvel) {
-        // velocities changed outside the integrator (initial state / host upload): recompute max |v|
-        cudaMemsetAsync(P.maxvel, 0, sizeof(float), s);
-        if (P.nOwners) {
-            k_maxvel<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, P.errOutVel);
+    if (stage == 0) {
+        if (need_maxvel) {
+            // velocities changed outside the integrator (initial state / host upload): recompute max |v|
+            cudaMemsetAsync(P.maxvel, 0, sizeof(float), s);
+            if (P.nOwners) {
+                k_maxvel<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, P.errOutVel);
+                launches++;
+            }
+        }
+    } else if (stage == 1) {
+        k_grid_setup<<<1, 32, 0, s>>>(P, C);
+        launches++;
+    } else {
+        if (P.nAnal) {
+            k_anal_prep<<<(P.nAnal + 63) / 64, 64, 0, s>>>(P, C);
             launches++;
         }
-    }
-    k_grid_setup<<<1, 32, 0, s>>>(P, C);
-    launches++;
-    if (P.nAnal) {
-        k_anal_prep<<<(P.nAnal + 63) / 64, 64, 0, s>>>(P, C);
-        launches++;
-    }
-    cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
-    cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
-    cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
-    cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
-    if (P.nSpheres) {
-        k_sphere_prep<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, C);
-        launches++;
+        cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+        cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
+        cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
+        cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
+        if (P.nSpheres) {
+            k_sphere_prep<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, C);
+            launches++;
+        }
     }
     return launches;
 }
@@ -664,7 +689,7 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
 __global__ void k_reduce(const __grid_constant__ DevParams P, int kind, uint32_t nClumps, double* out) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     double v = (kind == DEM_REDUCE_MIN_Z) ? 1e300 : ((kind == DEM_REDUCE_MAX_Z) ? -1e300 : 0.0);
-    if (o < nClumps) {
+    if (o < nClumps && (!P.active || P.active[o] == 1)) {
         const OwnerState st = P.state[o];
         if (kind == DEM_REDUCE_MAX_ABSV) {
             v = sqrtf(st.vel.x * st.vel.x + st.vel.y * st.vel.y + st.vel.z * st.vel.z);

@@ -492,13 +492,20 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
 }
 
 __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
-    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
     // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.
-    if (o == 0) *P.maxvel = 0.f;
+    if (t == 0) *P.maxvel = 0.f;
     float absv = 0.f;
-    if (o < P.nOwners) {
-        absv = integrate_one(P, o);
+    const uint32_t n = P.active_list ? P.nActive : P.nOwners;
+    if (t < n) {
+        const uint32_t o = P.active_list ? P.active_list[t] : t;
+        if (P.active && P.active[o] == 2) {
+            // ghost: its state arrives from the owning rank; only consume the (unused) wrench
+            st_v8(P.wrench + o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+        } else {
+            absv = integrate_one(P, o);
+        }
         if (!isfinite(absv) || absv > P.errOutVel) atomicOr(&P.flags[3], 1u);
         if (!isfinite(absv)) absv = 0.f;
     }
@@ -537,7 +544,8 @@ void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaS
 
 void launch_integrate(const DevParams& P, cudaStream_t s) {
     const int block = 256;
-    const int grid = (int)((P.nOwners + block - 1) / block);
+    const uint32_t n = P.active_list ? P.nActive : P.nOwners;
+    const int grid = (int)((n + block - 1) / block);
     if (grid > 0) k_integrate<<<grid, block, 0, s>>>(P);
 }
 

@@ -25,6 +25,7 @@ EXPORTED_SYMBOLS = [
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
+    "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
 ]
 
 
@@ -254,6 +255,24 @@ class Engine:
         out = C.c_double(0)
         self._ck(self.lib.dem_reduce(self.ctx, int(kind), C.byref(out)))
         return out.value
+
+    # ---- multi-GPU ----
+    @staticmethod
+    def mgpu_unique_id():
+        out = np.zeros(128, "u1")
+        rc = load_library().dem_mgpu_unique_id(_p(out))
+        if rc != 0:
+            raise DemError(rc, "dem_mgpu_unique_id failed (NCCL not loadable?)")
+        return out
+
+    def mgpu_init(self, rank, world, unique_id):
+        uid = np.ascontiguousarray(unique_id, "u1")
+        self._ck(self.lib.dem_mgpu_init(self.ctx, int(rank), int(world), _p(uid)))
+
+    def mgpu_info(self):
+        out = np.zeros(6, "u8")
+        self._ck(self.lib.dem_mgpu_info(self.ctx, _p(out)))
+        return dict(zip(["n_own", "n_active", "n_send_left", "n_send_right", "halo_bytes_per_step", "world"], out.tolist()))
 
     def set_option(self, name, value):
         self._ck(self.lib.dem_set_option(self.ctx, name.encode(), float(value)))

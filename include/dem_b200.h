@@ -203,6 +203,17 @@ enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_
        DEM_REDUCE_TOTAL_MASS = 4 };
 int dem_reduce(DemCtx* ctx, int kind, double* out);
 
+/* ---- multi-GPU: slab decomposition with ghost-owner halo exchange over NCCL (no counterpart in the reference, whose
+ * "multi-GPU" is the kT/dT thread pair of APIPublic.cpp:35-48).  One process and one context per GPU; every rank
+ * uploads the SAME complete input, then calls dem_mgpu_init with the id rank 0 created.  From then on each rank
+ * integrates the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step. */
+int dem_mgpu_unique_id(uint8_t out[128]);
+int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]);
+/* out: [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right [4] halo bytes sent per step [5] world */
+int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]);
+/* the x-slab (LBF-relative) of `rank` out of `world` */
+int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, float* hi);
+
 /* execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
  * "fast_encode" (0/1), "sort_mode" (0 radix sort, 1 counting sort; identical order), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */
 int dem_set_option(DemCtx* ctx, const char* name, double value);

@@ -136,7 +136,14 @@ def ref():
         _ref.ref_step.restype = C.c_int
         _ref.ref_sphere_anal_contacts.restype = C.c_long
         _ref.ref_calc_contact_point.restype = C.c_int
+        _ref.ref_set_threads(1)
     return _ref
+
+
+def ref_set_threads(n):
+    """Host threads the reference kernels are spread over (1 = serial, deterministic summation order)."""
+    if ref() is not None:
+        ref().ref_set_threads(int(n))
 
 
 def _ptr(a):

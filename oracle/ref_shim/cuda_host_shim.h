@@ -36,10 +36,21 @@ static thread_local ShimDim3 shim_blockIdx = {0, 0, 0}, shim_blockDim = {1, 1, 1
 
 static inline void __syncthreads() {}
 static inline void __threadfence() {}
+/* atomicAdd(float*): a real atomic (CAS loop) so that the harness may run the per-thread kernels on several host
+ * threads; with one thread it degenerates to a plain add in program order (used by the bit-exactness tests). */
 static inline float atomicAdd(float* addr, float v) {
-    float old = *addr;
-    *addr = old + v;
-    return old;
+    unsigned int* ia = reinterpret_cast<unsigned int*>(addr);
+    unsigned int old = __atomic_load_n(ia, __ATOMIC_RELAXED), assumed;
+    float fold;
+    do {
+        assumed = old;
+        __builtin_memcpy(&fold, &assumed, 4);
+        const float fnew = fold + v;
+        unsigned int inew;
+        __builtin_memcpy(&inew, &fnew, 4);
+        if (__atomic_compare_exchange_n(ia, &old, inew, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) break;
+    } while (true);
+    return fold;
 }
 static inline unsigned int atomicAdd(unsigned int* addr, unsigned int v) {
     unsigned int old = *addr;

@@ -161,10 +161,23 @@ void bind(OrcWorld* w, Bound& b) {
     k.ownerClumpBody = w->ownerClumpBody; k.clumpComponentOffset = b.comp8.data();
 }
 
+int g_threads = 1;
+
+/* one CUDA "thread" per index; indices are spread over g_threads host threads (OpenMP) */
 template <typename F>
 void launch(size_t n, unsigned block, F&& body) {
-    shim_blockDim.x = block;
-    for (size_t i = 0; i < n; i++) {
+    if (g_threads <= 1) {
+        shim_blockDim.x = block;
+        for (size_t i = 0; i < n; i++) {
+            shim_blockIdx.x = (unsigned)(i / block);
+            shim_threadIdx.x = (unsigned)(i % block);
+            body();
+        }
+        return;
+    }
+#pragma omp parallel for schedule(static) num_threads(g_threads)
+    for (long long i = 0; i < (long long)n; i++) {
+        shim_blockDim.x = block;
         shim_blockIdx.x = (unsigned)(i / block);
         shim_threadIdx.x = (unsigned)(i % block);
         body();
@@ -174,6 +187,9 @@ void launch(size_t n, unsigned block, F&& body) {
 }  // namespace
 
 extern "C" {
+
+/* number of host threads the kernels are spread over (1 = serial and deterministic) */
+void ref_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
 
 void ref_prepare_acc(OrcWorld* w) {
     Bound b; bind(w, b);
