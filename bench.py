@@ -178,14 +178,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # strong scaling: the bed is split into `world` slabs along x (multi-GPU)
-    n_local = args.clumps // world
-    sc, dims = build_scene(n_local, args.cd_update_freq, args.spacing)
+    # strong scaling: ONE bed of args.clumps clumps, split into `world` x-slabs with a ghost-owner halo exchange every
+    # step (multi-GPU). Every rank builds the same complete input; ownership follows positions.
+    sc, dims = build_scene(args.clumps, args.cd_update_freq, args.spacing)
     f = scenes.flatten(sc)
     eng = demb200.Engine(local_rank)
     stream = torch.cuda.Stream(device=local_rank)
     eng.set_stream(stream.cuda_stream)
-    eng.load_flat(f)
+    eng.load_flat(f, contact_capacity=0 if world == 1 else int(f.nSpheres) * 6 // world + 200000)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(demb200.Engine.mgpu_unique_id()).cuda())
+        dist.broadcast(uid, 0)
+        eng.mgpu_init(rank, world, uid.cpu().numpy())
 
     def barrier():
         if world > 1:
@@ -237,23 +243,28 @@ def main():
         return 0
 
     value = args.steps / (ms / 1000.0)
-    n_total_clumps = f.nClumps * world
+    n_total_clumps = f.nClumps
+    mg = eng.mgpu_info()
     C_ss, C_sa = int(st.n_contacts_ss), int(st.n_contacts_sa)
     peak, which = measured_peak()
     # algorithmic bytes of the dominant kernel (k_force_ss), SURVEY.md 8(d): 41 B per candidate contact
     # (9 ids + 16 history read + 16 history write) + 7 B per sphere + (57 read + 24 accumulate) B per owner
-    algo_bytes = 41.0 * C_ss + 7.0 * f.nSpheres + 81.0 * f.nOwners
+    n_own_local = mg["n_active"] if world > 1 else f.nOwners  # owners this rank actually touches
+    n_sph_local = 3 * n_own_local if world > 1 else f.nSpheres
+    algo_bytes = 41.0 * C_ss + 7.0 * n_sph_local + 81.0 * n_own_local
     ach = algo_bytes / (prof["force_ss_us"] * 1e-6) / 1e9 if prof["force_ss_us"] > 0 else 0.0
-    step_bytes = 41.0 * (C_ss + C_sa) + 7.0 * f.nSpheres + 218.0 * f.nOwners
+    step_bytes = 41.0 * (C_ss + C_sa) + 7.0 * n_sph_local + 218.0 * n_own_local
     line = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32 (f64 centre distance)", "data": "synthetic",
         "config": {"workload": workload, "lattice": list(dims), "clumps_total": n_total_clumps,
-                   "spheres_per_gpu": int(f.nSpheres), "contacts_ss": C_ss, "contacts_ss_touching": int(st.n_contacts_ss_touching), "contacts_sa": C_sa,
+                   "spheres_per_gpu": int(n_sph_local), "contacts_ss": C_ss, "contacts_ss_touching": int(st.n_contacts_ss_touching), "contacts_sa": C_sa,
                    "cd_update_freq": args.cd_update_freq, "settle_steps": args.settle_steps,
                    "force_record": False, "l2": "per-step working set > 126 MB L2 (no flush needed)",
-                   "parallelism": "1 GPU" if world == 1 else "%d independent x-slabs (halo exchange not built yet)" % world},
+                   "parallelism": "1 GPU" if world == 1 else
+                   "%d x-slabs, ghost-owner halo exchange per step over NCCL (rank 0: %d own + %d ghost owners, %d B sent per step)"
+                   % (world, mg["n_own"], mg["n_active"] - mg["n_own"], mg["halo_bytes_per_step"])},
         "grain_updates_per_s": value * n_total_clumps,
         "kernel_us": prof,
         "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,

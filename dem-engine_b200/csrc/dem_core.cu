@@ -663,9 +663,17 @@ int dem_set_params(DemCtx* ctx, const DemSimParams* p) {
     if (ctx->initialized && (p->force_model != ctx->sp.force_model ||
                              p->record_contact_forces != ctx->sp.record_contact_forces))
         return fail(ctx, DEM_ERR_INVALID, "force model / force record cannot change after dem_initialize");
+    // only what the contact margin / broad-phase grid depends on invalidates the current contact list
+    const DemSimParams& o = ctx->sp;
+    const bool list_stale = !ctx->params_set || p->h != o.h || p->beta != o.beta || p->approxMaxVel != o.approxMaxVel ||
+                            p->expSafetyMulti != o.expSafetyMulti || p->expSafetyAdder != o.expSafetyAdder ||
+                            p->cd_update_freq != o.cd_update_freq || p->l != o.l || p->nvXp2 != o.nvXp2 ||
+                            p->nvYp2 != o.nvYp2 || memcmp(p->LBF, o.LBF, sizeof(o.LBF)) != 0 ||
+                            memcmp(p->userBoxMin, o.userBoxMin, sizeof(o.userBoxMin)) != 0 ||
+                            memcmp(p->userBoxMax, o.userBoxMax, sizeof(o.userBoxMax)) != 0;
     ctx->sp = *p;
     ctx->params_set = true;
-    ctx->need_rebuild = true;
+    if (list_stale) ctx->need_rebuild = true;
     return DEM_OK;
 }
 
@@ -741,6 +749,8 @@ int dem_upload_analytical(DemCtx* ctx, uint32_t nAnal, const uint32_t* objOwner,
 
 int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMargin, const DemPrescription* presc) {
     if (!ctx) return DEM_ERR_INVALID;
+    const std::vector<uint8_t> old_masks = ctx->h_masks;
+    const std::vector<float> old_extra = ctx->h_extra;
     ctx->h_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
     ctx->h_extra.assign(DEM_NUM_FAMILIES, 0.f);
     ctx->h_presc.resize(DEM_NUM_FAMILIES);
@@ -758,7 +768,8 @@ int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMar
         CK(cudaMemcpyAsync(ctx->d_extra, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemcpyAsync(ctx->d_presc, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
-        ctx->need_rebuild = true;
+        // prescriptions act in the integrator only; the contact list depends on the masks and the extra margins
+        if (old_masks != ctx->h_masks || old_extra != ctx->h_extra) ctx->need_rebuild = true;
     }
     return DEM_OK;
 }
