@@ -170,13 +170,13 @@ def main():
     # ------------------------------------------------------------------------------------------------------------
     import torch
     import torch.distributed as dist
-    from pyapi import demb200, scenes
+    from pyapi import demb200, dist_util, scenes
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist_util.init("nccl", local_rank)
 
     # strong scaling: ONE bed of args.clumps clumps, split into `world` x-slabs with a ghost-owner halo exchange every
     # step (multi-GPU). Every rank builds the same complete input; ownership follows positions.
@@ -187,11 +187,7 @@ def main():
     eng.set_stream(stream.cuda_stream)
     eng.load_flat(f, contact_capacity=0 if world == 1 else int(f.nSpheres) * 6 // world + 200000)
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.from_numpy(demb200.Engine.mgpu_unique_id()).cuda())
-        dist.broadcast(uid, 0)
-        eng.mgpu_init(rank, world, uid.cpu().numpy())
+        eng.mgpu_init(rank, world, dist_util.share_bytes(demb200.Engine.mgpu_unique_id, 128, device="cuda"))
 
     def barrier():
         if world > 1:
@@ -233,10 +229,7 @@ def main():
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 
-    t = torch.tensor([ms, e2e_s * 1000.0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+    ms, e2e_ms = dist_util.max_over_ranks([ms, e2e_s * 1000.0], device="cuda")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

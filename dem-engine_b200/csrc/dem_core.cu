@@ -134,7 +134,7 @@ struct DemCtx {
     double* d_reduce = nullptr;
     // contact lists [kind][buffer]: kind 0 = sphere-sphere in touch at the last rebuild, 1 = other sphere-sphere
     // candidates, 2 = sphere-analytical; two buffers each (current / being rebuilt)
-    ListBuf lists[3][2];
+    ListBuf lists[4][2];  // [3] = sphere-triangle
     int cur = 0;  // index of the current list buffers
     uint64_t capacity = 0;
     // rebuild scratch
@@ -149,6 +149,14 @@ struct DemCtx {
     uint32_t* d_sortedPos = nullptr;
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
+    // triangles
+    float4* d_tri[3] = {nullptr, nullptr, nullptr};   // owner-frame nodes
+    uint2* d_tri_info = nullptr;
+    float4* d_triW[3] = {nullptr, nullptr, nullptr};  // world nodes of the last rebuild
+    uint32_t* d_triCellStart = nullptr;
+    uint32_t* d_triCellFill = nullptr;
+    uint32_t* d_triCellList = nullptr;
+    uint64_t tri_pair_cap = 0;
     uint32_t max_cells = 0;
     int key_bits = 8;
     // pinned read-back
@@ -161,7 +169,7 @@ struct DemCtx {
     bool need_maxvel = true;  // velocities changed outside the integrator
     int maxvel_slot = 0;
     double sim_time = 0.0;
-    uint64_t n_list[3] = {0, 0, 0};
+    uint64_t n_list[4] = {0, 0, 0, 0};
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
     int ctas_per_sm = 4;
@@ -264,6 +272,8 @@ DevParams make_params(const DemCtx* c) {
     P.ss = as_list(c->lists[0][c->cur]);
     P.sn = as_list(c->lists[1][c->cur]);
     P.sa = as_list(c->lists[2][c->cur]);
+    P.st = as_list(c->lists[3][c->cur]);
+    P.tri_n1 = c->d_tri[0]; P.tri_n2 = c->d_tri[1]; P.tri_n3 = c->d_tri[2]; P.tri_info = c->d_tri_info;
     P.flags = c->d_flags;
     if (c->mg.on) { P.active = c->mg.d_flag; P.active_list = c->mg.d_active_list; P.nActive = c->mg.n_active; }
     P.maxvel = c->d_maxvel + c->maxvel_slot;
@@ -292,6 +302,10 @@ CdParams make_cd(const DemCtx* c) {
     C.oldss = as_list(c->lists[0][c->cur]);
     C.oldsn = as_list(c->lists[1][c->cur]);
     C.oldsa = as_list(c->lists[2][c->cur]);
+    C.oldst = as_list(c->lists[3][c->cur]);
+    C.triW1 = c->d_triW[0]; C.triW2 = c->d_triW[1]; C.triW3 = c->d_triW[2];
+    C.triCellStart = c->d_triCellStart; C.triCellFill = c->d_triCellFill; C.triCellList = c->d_triCellList;
+    C.tri_pair_cap = (uint32_t)c->tri_pair_cap;
     C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp;
     return C;
 }
@@ -300,8 +314,10 @@ void free_device(DemCtx* c) {
     dfree(c->d_state); dfree(c->d_spin); dfree(c->d_wrench); dfree(c->d_acc); dfree(c->d_sph); dfree(c->d_comp); dfree(c->d_massprop);
     dfree(c->d_matpair); dfree(c->d_anal); dfree(c->d_masks); dfree(c->d_extra); dfree(c->d_presc);
     dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce);
-    for (int kind = 0; kind < 3; kind++)
+    for (int kind = 0; kind < 4; kind++)
         for (int k = 0; k < 2; k++) free_list(c->lists[kind][k]);
+    for (int k = 0; k < 3; k++) { dfree(c->d_tri[k]); dfree(c->d_triW[k]); }
+    dfree(c->d_tri_info); dfree(c->d_triCellStart); dfree(c->d_triCellFill); dfree(c->d_triCellList);
     dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
     dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw); dfree(c->d_sortedPos);
     dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
@@ -312,9 +328,9 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
     const bool hist = ctx->sp.force_model == DEM_HERTZIAN;
     const bool rec = ctx->sp.record_contact_forces != 0;
     int rc;
-    for (int kind = 0; kind < 3; kind++)
+    for (int kind = 0; kind < 4; kind++)
         for (int k = 0; k < 2; k++)
-            if ((rc = alloc_list(ctx, ctx->lists[kind][k], cap, ctx->nSpheres, hist, rec))) return rc;
+            if ((rc = alloc_list(ctx, ctx->lists[kind][k], (kind == 3 && ctx->nTri == 0) ? 1 : cap, ctx->nSpheres, hist, rec))) return rc;
     ctx->capacity = cap;
     return DEM_OK;
 }
@@ -406,6 +422,7 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
         P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
         P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
+        P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
         cudaStream_t s = ctx->stream;
         CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 3, s));  // [3] (velocity) is only cleared by the host
         if (stage_us) cudaEventRecord(sev[0], s);
@@ -420,8 +437,13 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
             P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
             P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
+            P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
         }
         launches += launch_cd_prepare(P, C, ctx->need_maxvel, 2, s);
+        launches += launch_cd_triangles(P, C, 0, s);  // triangle -> cell registration
+        launches += launch_cd_triangles(P, C, 1, s);  // per-sphere triangle candidates (+ history)
+        if (ctx->nTri)  // demand of the triangle--cell table
+            CK(cudaMemcpyAsync(ctx->h_pinned + 200, ctx->d_triCellStart + ctx->max_cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (stage_us) cudaEventRecord(sev[1], s);
         int sorted_buf = -1;  // -1: counting sort inside the sweep stage
         if (ctx->sort_mode == 0) launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
@@ -429,8 +451,8 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);  // records sev[3..6]
         if (stage_us) cudaEventRecord(sev[7], s);
         ctx->launches += launches;
-        const ContactList* NL[3] = {&P.ss, &P.sn, &P.sa};
-        for (int kind = 0; kind < 3; kind++)  // {clamped count, demand}
+        const ContactList* NL[4] = {&P.ss, &P.sn, &P.sa, &P.st};
+        for (int kind = 0; kind < 4; kind++)  // {clamped count, demand}
             CK(cudaMemcpyAsync(ctx->h_pinned + 32 + 2 * kind, NL[kind]->count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (ctx->mg.on)  // every rank must see the same verdict, or the ranks fall out of step inside NCCL
             NC(g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclUint32, ncclMax, ctx->mg.comm, s));
@@ -440,8 +462,9 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         memcpy(&ctx->last_grid, ctx->h_pinned + 8, sizeof(GridInfo));
         ctx->need_maxvel = false;
         if (ctx->h_pinned[4] != 0)
-            return fail(ctx, DEM_ERR_CAPACITY, "a sphere has more than 40 forward contact candidates: geometry size "
-                        "ratios this large need a smaller contact margin (SetExpandSafetyAdder / SetCDUpdateFreq)");
+            return fail(ctx, DEM_ERR_CAPACITY, "a sphere has more than 40 forward sphere or 24 triangle contact candidates: "
+                        "geometry size ratios this large need a smaller contact margin (SetExpandSafetyAdder / "
+                        "SetCDUpdateFreq) or a coarser mesh");
         if (ctx->h_pinned[5] != 0) {
             const uint32_t zero = 0;
             cudaMemcpy(ctx->d_flags + 3, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice);
@@ -452,16 +475,25 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
         if (ctx->h_pinned[2] != 0 && ctx->mg.on)
             return fail(ctx, DEM_ERR_CAPACITY, "a contact list or halo buffer overflowed on some rank (flags %u); raise "
                         "the contact capacity passed to dem_initialize", ctx->h_pinned[2]);
+        if ((ctx->h_pinned[2] & 16u) != 0) {
+            // the triangle--cell table was too small: it is scratch, so just regrow it and redo the rebuild
+            ctx->overflow_seen++;
+            dfree(ctx->d_triCellList);
+            ctx->tri_pair_cap = (uint64_t)ctx->h_pinned[200] + ctx->h_pinned[200] / 2 + 1024;
+            int rc = dalloc(ctx, &ctx->d_triCellList, ctx->tri_pair_cap);
+            if (rc) return rc;
+            continue;
+        }
         if (ctx->h_pinned[2] != 0) {
             // capacity overflow: grow every list, keep the old lists (history source) intact, redo the rebuild
             ctx->overflow_seen++;
             uint64_t need = 0;
-            for (int kind = 0; kind < 3; kind++) need = std::max<uint64_t>(need, ctx->h_pinned[32 + 2 * kind + 1]);
+            for (int kind = 0; kind < 4; kind++) need = std::max<uint64_t>(need, ctx->h_pinned[32 + 2 * kind + 1]);
             const uint64_t newcap = std::max<uint64_t>(need + need / 4 + 1024, ctx->capacity * 2);
             if (newcap > 0xfffffff0ull) return fail(ctx, DEM_ERR_CAPACITY, "contact list exceeds 2^32 entries");
             const uint64_t oldcap = ctx->capacity;
             const bool hist = ctx->sp.force_model == DEM_HERTZIAN, rec = ctx->sp.record_contact_forces != 0;
-            for (int kind = 0; kind < 3; kind++) {
+            for (int kind = 0; kind < (ctx->nTri ? 4 : 3); kind++) {
                 int rc;
                 free_list(ctx->lists[kind][ctx->cur ^ 1]);
                 if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
@@ -489,7 +521,7 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             for (auto& e : sev) cudaEventDestroy(e);
         }
         ctx->cur ^= 1;
-        for (int kind = 0; kind < 3; kind++) ctx->n_list[kind] = ctx->h_pinned[32 + 2 * kind];
+        for (int kind = 0; kind < 4; kind++) ctx->n_list[kind] = ctx->h_pinned[32 + 2 * kind];
         ctx->n_rebuilds++;
         ctx->steps_since_rebuild = 0;
         ctx->need_rebuild = false;
@@ -507,6 +539,8 @@ int enqueue_step(DemCtx* ctx) {
     launch_force_ss(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->num_sms, ctx->ctas_per_sm, ctx->stream);
     if (ctx->nAnal > 0)
         launch_force_sa(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
+    if (ctx->nTri > 0)
+        launch_force_st(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
     launch_integrate(P, ctx->stream);
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     if (ctx->mg.on) {
@@ -515,7 +549,7 @@ int enqueue_step(DemCtx* ctx) {
         if (rc) return rc;
         ctx->launches += l;
     }
-    ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
+    ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
     ctx->n_steps++;
     ctx->steps_since_rebuild++;
     ctx->sim_time += (double)ctx->sp.h;
@@ -830,10 +864,17 @@ int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClum
 
 int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, const float* node1, const float* node2,
                          const float* node3, const uint16_t* triMaterialOffset) {
-    if (!ctx) return DEM_ERR_INVALID;
-    if (nTri != 0) return fail(ctx, DEM_ERR_INVALID, "sphere--triangle contacts are not built yet (SURVEY.md 8 row a8)");
-    (void)ownerMesh; (void)node1; (void)node2; (void)node3; (void)triMaterialOffset;
-    ctx->nTri = 0;
+    // the flattened m_mesh_facet_owner / m_mesh_facets / material arrays of dT::populateEntityArrays (dT.cpp:960-1010)
+    if (!ctx || (nTri && (!ownerMesh || !node1 || !node2 || !node3 || !triMaterialOffset))) return DEM_ERR_INVALID;
+    ctx->h_tri1.resize(nTri); ctx->h_tri2.resize(nTri); ctx->h_tri3.resize(nTri); ctx->h_tri_info.resize(nTri);
+    for (uint32_t t = 0; t < nTri; t++) {
+        ctx->h_tri1[t] = make_float4(node1[3 * t], node1[3 * t + 1], node1[3 * t + 2], 0.f);
+        ctx->h_tri2[t] = make_float4(node2[3 * t], node2[3 * t + 1], node2[3 * t + 2], 0.f);
+        ctx->h_tri3[t] = make_float4(node3[3 * t], node3[3 * t + 1], node3[3 * t + 2], 0.f);
+        ctx->h_tri_info[t] = make_uint2(ownerMesh[t], (uint32_t)triMaterialOffset[t]);
+    }
+    ctx->nTri = nTri;
+    if (ctx->initialized) ctx->initialized = false;  // geometry changed: dem_initialize must run again
     return DEM_OK;
 }
 
@@ -850,6 +891,9 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     for (uint32_t i = 0; i < ctx->nAnal; i++)
         if (ctx->h_anal[i].owner >= ctx->nOwners || ctx->h_anal[i].material >= ctx->nMat)
             return fail(ctx, DEM_ERR_INVALID, "analytical component %u has a bad owner or material", i);
+    for (uint32_t i = 0; i < ctx->nTri; i++)
+        if (ctx->h_tri_info[i].x >= ctx->nOwners || ctx->h_tri_info[i].y >= ctx->nMat)
+            return fail(ctx, DEM_ERR_INVALID, "triangle %u has a bad owner or material", i);
     CK(cudaSetDevice(ctx->device));
     free_device(ctx);
     int rc;
@@ -912,6 +956,22 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
     if ((rc = dalloc(ctx, &ctx->d_scan_tmp, scan_n / 4096 + 2))) return rc;
 
+    if (ctx->nTri) {
+        const uint32_t nT = ctx->nTri;
+        const std::vector<float4>* src[3] = {&ctx->h_tri1, &ctx->h_tri2, &ctx->h_tri3};
+        for (int k = 0; k < 3; k++) {
+            if ((rc = dalloc(ctx, &ctx->d_tri[k], nT))) return rc;
+            if ((rc = dalloc(ctx, &ctx->d_triW[k], nT))) return rc;
+            CK(cudaMemcpy(ctx->d_tri[k], src[k]->data(), sizeof(float4) * nT, cudaMemcpyHostToDevice));
+        }
+        if ((rc = dalloc(ctx, &ctx->d_tri_info, nT))) return rc;
+        CK(cudaMemcpy(ctx->d_tri_info, ctx->h_tri_info.data(), sizeof(uint2) * nT, cudaMemcpyHostToDevice));
+        if ((rc = dalloc(ctx, &ctx->d_triCellStart, (size_t)ctx->max_cells + 2))) return rc;
+        if ((rc = dalloc(ctx, &ctx->d_triCellFill, (size_t)ctx->max_cells + 2))) return rc;
+        ctx->tri_pair_cap = (uint64_t)nT * 16 + 4096;
+        if ((rc = dalloc(ctx, &ctx->d_triCellList, ctx->tri_pair_cap))) return rc;
+    }
+
     uint64_t cap = contact_capacity ? contact_capacity : (uint64_t)nS * 8 + 1024;
     if ((rc = alloc_lists(ctx, cap))) return rc;
     ctx->cur = 0;
@@ -924,7 +984,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     ctx->initialized = true;
     ctx->need_rebuild = true;
     ctx->steps_since_rebuild = 0;
-    ctx->n_list[0] = ctx->n_list[1] = ctx->n_list[2] = 0;
+    for (auto& v : ctx->n_list) v = 0;
     return DEM_OK;
 }
 
@@ -937,12 +997,14 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
     CK(cudaSetDevice(ctx->device));
     // Build host-side "previous" lists grouped by sphere A so that the next rebuild carries the history over.
     const uint32_t nS = ctx->nSpheres;
-    for (int which = 0; which < 2; which++) {
+    for (int which = 0; which < 3; which++) {
+        if (which == 2 && ctx->nTri == 0) break;
         std::vector<uint64_t> idx;
         for (uint64_t i = 0; i < n; i++) {
             const bool is_ss = type[i] == DEM_CNT_SPHERE_SPHERE;
             const bool is_sa = type[i] > 10;
-            if ((which == 0 && is_ss) || (which == 1 && is_sa)) idx.push_back(i);
+            const bool is_st = type[i] == DEM_CNT_SPHERE_MESH;
+            if ((which == 0 && is_ss) || (which == 1 && is_sa) || (which == 2 && is_st)) idx.push_back(i);
         }
         std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return idA[a] < idA[b]; });
         std::vector<uint2> pair(idx.size());
@@ -961,7 +1023,7 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
             count[idA[i]]++;
         }
         for (uint32_t s = 0, run = 0; s < nS; s++) { start[s] = run; run += count[s]; }
-        ListBuf& L = (which == 0) ? ctx->lists[0][ctx->cur] : ctx->lists[2][ctx->cur];
+        ListBuf& L = (which == 0) ? ctx->lists[0][ctx->cur] : ctx->lists[which == 1 ? 2 : 3][ctx->cur];
         const uint32_t cnt = (uint32_t)idx.size();
         CK(cudaMemcpy(L.pair, pair.data(), sizeof(uint2) * idx.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.cinfo, cinfo.data(), sizeof(uint4) * idx.size(), cudaMemcpyHostToDevice));
@@ -1126,17 +1188,17 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
     if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2];
+    const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2] + ctx->n_list[3];
     *n_out = n;
     if (!idA && !idB && !type && !wildcards4 && !force_xyz) return DEM_OK;
     if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
     struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; };
     std::vector<Row> rows;
     rows.reserve(n);
-    for (int kind = 0; kind < 3; kind++) {
+    for (int kind = 0; kind < 4; kind++) {
         const ListBuf& L = ctx->lists[kind][ctx->cur];
         const uint64_t m = ctx->n_list[kind];
-        const int which = (kind == 2) ? 1 : 0;
+        const int which = (kind == 2) ? 1 : (kind == 3 ? 2 : 0);
         std::vector<uint2> pair(m);
         std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0));
         CK(cudaMemcpy(pair.data(), L.pair, sizeof(uint2) * m, cudaMemcpyDeviceToHost));
@@ -1150,6 +1212,7 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
             bool flip = false;
             if (which == 0 && r.a > r.b) { std::swap(r.a, r.b); flip = true; }
             if (which == 0) r.t = DEM_CNT_SPHERE_SPHERE;
+            else if (which == 2) r.t = DEM_CNT_SPHERE_MESH;
             else r.t = (ctx->h_anal[pair[i].y].type == DEM_ANAL_PLANE) ? DEM_CNT_SPHERE_PLANE : DEM_CNT_SPHERE_CYL;
             // history words of contacts that are not alive are stale by construction: report zeros
             r.h = (ci[i].w & 0x80000000u) ? hist[i] : make_float4(0, 0, 0, 0);
@@ -1182,7 +1245,7 @@ int dem_get_stats(DemCtx* ctx, DemStats* out) {
     if (!ctx || !out) return DEM_ERR_INVALID;
     memset(out, 0, sizeof(*out));
     out->n_steps = ctx->n_steps; out->n_rebuilds = ctx->n_rebuilds;
-    out->n_contacts_ss = ctx->n_list[0] + ctx->n_list[1]; out->n_contacts_sa = ctx->n_list[2]; out->n_contacts_st = 0;
+    out->n_contacts_ss = ctx->n_list[0] + ctx->n_list[1]; out->n_contacts_sa = ctx->n_list[2]; out->n_contacts_st = ctx->n_list[3];
     out->n_contacts_ss_touching = ctx->n_list[0];
     out->contact_capacity = ctx->capacity; out->kernel_launches = ctx->launches; out->device_bytes = ctx->device_bytes;
     out->sim_time = ctx->sim_time; out->max_margin = ctx->last_grid.max_margin; out->cell_size = ctx->last_grid.cs;
@@ -1222,6 +1285,31 @@ int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, 
     const double w = (x1 - x0) / world;
     *lo = (rank == 0) ? -3.0e38f : (float)(x0 + w * rank);
     *hi = (rank == world - 1) ? 3.0e38f : (float)(x0 + w * (rank + 1));
+    return DEM_OK;
+}
+
+int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float halo, uint64_t n, const uint64_t* voxelID,
+                              const uint16_t* locX, uint8_t* role, uint8_t* send) {
+    if (!p || world < 1 || rank < 0 || rank >= world || (n && (!voxelID || !locX || !role))) return DEM_ERR_INVALID;
+    float lo, hi;
+    dem_host_slab_bounds(p, world, rank, &lo, &hi);
+    const uint64_t xmask = (p->nvXp2 >= 64) ? ~0ull : ((1ull << p->nvXp2) - 1ull);
+    for (uint64_t i = 0; i < n; i++) {
+        // same arithmetic as the device (pos_decode, then float compare against the cuts: k_mg_classify)
+        const double X = (double)(voxelID[i] & xmask) * p->voxelSize + (double)locX[i] * p->l;
+        const float x = (float)X;
+        const bool own = (x >= lo) && (x < hi);
+        uint8_t r = 0, sd = 0;
+        if (own) {
+            r = 1;
+            if (rank > 0 && x < lo + halo) sd |= 1;
+            if (rank < world - 1 && x >= hi - halo) sd |= 2;
+        } else if ((rank > 0 && x < lo && x >= lo - halo) || (rank < world - 1 && x >= hi && x < hi + halo)) {
+            r = 2;
+        }
+        role[i] = r;
+        if (send) send[i] = sd;
+    }
     return DEM_OK;
 }
 

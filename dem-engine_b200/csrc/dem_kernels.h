@@ -42,7 +42,15 @@ struct CdParams {
     uint4* sortedMeta;    // {owner, sphere id, comp | material<<16, family}
     AnalWorld* analw;
     uint32_t* sortedPos;  // sphere id -> position in the cell-sorted arrays
-    ContactList oldss, oldsn, oldsa;
+    ContactList oldss, oldsn, oldsa, oldst;
+    // triangles (sphere--triangle broad phase)
+    float4* triW1;          // world-space nodes of this rebuild (LBF-relative, float); triW1.w = margin of the mesh owner
+    float4* triW2;
+    float4* triW3;
+    uint32_t* triCellStart; // per cell: triangles registered (histogram, then exclusive prefix), max_cells+1
+    uint32_t* triCellFill;  // per cell fill cursor
+    uint32_t* triCellList;  // triangle ids grouped by cell
+    uint32_t tri_pair_cap;
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the scans
 };
@@ -67,6 +75,8 @@ int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s)
 
 void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s);
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
+void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
+int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaStream_t s);
 void launch_integrate(const DevParams& P, cudaStream_t s);
 
 // rebuild stages; each returns the number of kernels it launched

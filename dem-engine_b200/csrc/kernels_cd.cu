@@ -488,6 +488,188 @@ __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant_
     C.sortedPos[i] = dst;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// sphere--triangle broad phase (replaces makeTriangleSandwich / bin--triangle pairs / per-bin sphere--triangle sweep,
+// DEMBinTriangleKernels.cu:22-221, DEMContactKernels_SphereTriangle.cu:116-427, and the host merge of
+// HostSideHelpers.hpp:176-193).  A triangle is registered in every cell that its bounding box, grown by the largest
+// inflated sphere radius plus its own margin, overlaps; a sphere then only looks at the triangles of its own cell.
+__device__ __forceinline__ void tri_cell_range(const GridInfo& g, const CdParams& C, float4 a, float4 b, float4 c,
+                                               int lo[3], int hi[3]) {
+    const float grow = C.rmax + g.max_margin + a.w + 1e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + 1.f);
+    const float mn[3] = {fminf(a.x, fminf(b.x, c.x)) - grow, fminf(a.y, fminf(b.y, c.y)) - grow, fminf(a.z, fminf(b.z, c.z)) - grow};
+    const float mx[3] = {fmaxf(a.x, fmaxf(b.x, c.x)) + grow, fmaxf(a.y, fmaxf(b.y, c.y)) + grow, fmaxf(a.z, fmaxf(b.z, c.z)) + grow};
+    const int nb[3] = {(int)g.nbx, (int)g.nby, (int)g.nbz};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        lo[k] = min(max((int)floorf(mn[k] * g.inv_cs), 0), nb[k] - 1);
+        hi[k] = min(max((int)floorf(mx[k] * g.inv_cs), 0), nb[k] - 1);
+    }
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_tri_cells(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.nTri) return;
+    const GridInfo g = *C.grid;
+    float4 a, b, c;
+    if (!FILL) {
+        const uint2 info = P.tri_info[t];
+        if (P.active && P.active[info.x] == 0) {  // mesh owner not held by this rank
+            C.triW1[t] = make_float4(0.f, 0.f, 0.f, -1.f);
+            return;
+        }
+        const OwnerState* sb = P.state + info.x;
+        const float4 q = sb->quat;
+        const float4 v = sb->vel;
+        double X, Y, Z;
+        pos_decode(sb->pos, P, X, Y, Z);
+        const float m = owner_margin(P, sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), sb->pos.family);
+        const float4 n1 = P.tri_n1[t], n2 = P.tri_n2[t], n3 = P.tri_n3[t];
+        const float3 r1 = rotate(f3(n1.x, n1.y, n1.z), q), r2 = rotate(f3(n2.x, n2.y, n2.z), q), r3 = rotate(f3(n3.x, n3.y, n3.z), q);
+        a = make_float4((float)(X + (double)r1.x), (float)(Y + (double)r1.y), (float)(Z + (double)r1.z), m);
+        b = make_float4((float)(X + (double)r2.x), (float)(Y + (double)r2.y), (float)(Z + (double)r2.z), 0.f);
+        c = make_float4((float)(X + (double)r3.x), (float)(Y + (double)r3.y), (float)(Z + (double)r3.z), 0.f);
+        C.triW1[t] = a; C.triW2[t] = b; C.triW3[t] = c;
+    } else {
+        a = C.triW1[t]; b = C.triW2[t]; c = C.triW3[t];
+        if (a.w < 0.f) return;
+    }
+    int lo[3], hi[3];
+    tri_cell_range(g, C, a, b, c, lo, hi);
+    for (int z = lo[2]; z <= hi[2]; z++)
+        for (int y = lo[1]; y <= hi[1]; y++)
+            for (int x = lo[0]; x <= hi[0]; x++) {
+                const uint32_t cell = (uint32_t)x + g.nbx * ((uint32_t)y + g.nby * (uint32_t)z);
+                if (!FILL) {
+                    atomicAdd(&C.triCellStart[cell], 1u);
+                } else {
+                    const uint32_t slot = C.triCellStart[cell] + atomicAdd(&C.triCellFill[cell], 1u);
+                    if (slot < C.tri_pair_cap) C.triCellList[slot] = t; else atomicOr(&P.flags[0], 16u);
+                }
+            }
+}
+
+// squared distance from point p to triangle (a,b,c): Ericson, Real-Time Collision Detection, p.141 (float, conservative use)
+__device__ __forceinline__ float tri_point_dist2(float3 a, float3 b, float3 c, float3 p) {
+    const float3 ab = b - a, ac = c - a, ap = p - a;
+    const float d1 = dot(ab, ap), d2 = dot(ac, ap);
+    float3 q;
+    if (d1 <= 0.f && d2 <= 0.f) q = a;
+    else {
+        const float3 bp = p - b;
+        const float d3 = dot(ab, bp), d4 = dot(ac, bp);
+        if (d3 >= 0.f && d4 <= d3) q = b;
+        else {
+            const float vc = d1 * d4 - d3 * d2;
+            if (vc <= 0.f && d1 >= 0.f && d3 <= 0.f) q = a + (d1 / (d1 - d3)) * ab;
+            else {
+                const float3 cp = p - c;
+                const float d5 = dot(ab, cp), d6 = dot(ac, cp);
+                if (d6 >= 0.f && d5 <= d6) q = c;
+                else {
+                    const float vb = d5 * d2 - d1 * d6;
+                    if (vb <= 0.f && d2 >= 0.f && d6 <= 0.f) q = a + (d2 / (d2 - d6)) * ac;
+                    else {
+                        const float va = d3 * d6 - d5 * d4;
+                        if (va <= 0.f && (d4 - d3) >= 0.f && (d5 - d6) >= 0.f) q = b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b);
+                        else {
+                            const float denom = 1.f / (va + vb + vc);
+                            q = a + (vb * denom) * ab + (vc * denom) * ac;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const float3 d = p - q;
+    return dot(d, d);
+}
+
+constexpr int ST_MAXC = 24;
+
+// per sphere (sphere-id order): candidates among the triangles registered in the sphere's own cell
+__global__ void __launch_bounds__(128) k_st_emit(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = sid < P.nSpheres;
+    uint32_t key = 0;
+    if (valid) {
+        key = C.keys[0][sid];
+        if (key == 0xffffffffu) {
+            P.st.seg_start[sid] = 0; P.st.seg_count[sid] = 0;
+            valid = false;
+        }
+    }
+    uint32_t acc[ST_MAXC];
+    uint32_t count = 0;
+    uint2 s = make_uint2(0, 0);
+    if (valid) {
+        s = P.sph[sid];
+        const float4 me = C.sphF[sid];
+        const uint32_t famS = P.state[s.x].pos.family;
+        const uint32_t tb = C.triCellStart[key], te = min(C.triCellStart[key + 1], C.tri_pair_cap);
+        for (uint32_t k = tb; k < te; k++) {
+            const uint32_t t = C.triCellList[k];
+            const float4 a = C.triW1[t], b = C.triW2[t], c = C.triW3[t];
+            const float R = me.w + a.w;
+            const float d2 = tri_point_dist2(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), f3(me.x, me.y, me.z));
+            if (d2 > R * R * 1.00001f + 1e-18f) continue;
+            if (C.any_mask) {
+                const uint32_t famT = P.state[P.tri_info[t].x].pos.family;
+                if (P.familyMasks[mask_pair(famS, famT)] != 0) continue;
+            }
+            if (count < ST_MAXC) acc[count] = t;
+            count++;
+        }
+        if (count > ST_MAXC) { atomicOr(&P.flags[2], 2u); count = ST_MAXC; }
+    }
+    uint32_t slot = warp_claim(count, P.st.count);
+    if (!valid) return;
+    P.st.seg_start[sid] = slot;
+    P.st.seg_count[sid] = (slot + count <= C.capacity) ? count : (slot < C.capacity ? C.capacity - slot : 0u);
+    if (count == 0) return;
+    if (slot + count > C.capacity) atomicOr(&P.flags[0], 32u);
+    const uint32_t oldStart = C.oldst.seg_start[sid], oldCount = C.oldst.seg_count[sid];
+    for (uint32_t k = 0; k < count; k++, slot++) {
+        if (slot >= C.capacity) break;
+        const uint32_t t = acc[k];
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t alive = 0;
+        for (uint32_t j = 0; j < oldCount; j++) {
+            if (C.oldst.pair[oldStart + j].y == t) {
+                alive = C.oldst.cinfo[oldStart + j].w & 0x80000000u;
+                if (alive && C.oldst.hist) h = C.oldst.hist[oldStart + j];
+                break;
+            }
+        }
+        const uint32_t matpair = (s.y >> 16) * P.nMat + P.tri_info[t].y;
+        P.st.pair[slot] = make_uint2(sid, t);
+        P.st.cinfo[slot] = make_uint4(s.x, t, s.y & 0xffffu, matpair | alive);
+        if (P.st.hist) P.st.hist[slot] = h;
+    }
+}
+
+// stage 0: world nodes + per-cell counts; stage 1: fill the per-cell triangle lists (after the scan) and emit the list
+int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaStream_t s) {
+    if (P.nTri == 0) {
+        if (stage == 0) cudaMemsetAsync(P.st.count, 0, sizeof(uint32_t) * 4, s);
+        return 0;
+    }
+    int launches = 0;
+    if (stage == 0) {
+        cudaMemsetAsync(P.st.count, 0, sizeof(uint32_t) * 4, s);
+        cudaMemsetAsync(C.triCellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+        cudaMemsetAsync(C.triCellFill, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+        k_tri_cells<false><<<(P.nTri + 127) / 128, 128, 0, s>>>(P, C);
+        launches += 1 + launch_scan_exclusive(C.triCellStart, C.max_cells + 1, C.scan_tmp, nullptr, s);
+        k_tri_cells<true><<<(P.nTri + 127) / 128, 128, 0, s>>>(P, C);
+        launches++;
+    } else if (P.nSpheres) {
+        k_st_emit<<<(P.nSpheres + 127) / 128, 128, 0, s>>>(P, C);
+        launches++;
+    }
+    return launches;
+}
+
 constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half stencil)
 
 // The sweep.  Cells are x-fastest, so the x-neighbours of a row are ONE contiguous run of the cell-sorted array.
@@ -612,10 +794,13 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
 
 __global__ void k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t a = *P.ss.count, b = *P.sa.count, c = *P.sn.count;
+        uint32_t a = *P.ss.count, b = *P.sa.count, c = *P.sn.count, d = *P.st.count;
         P.ss.count[1] = a;  // the unclamped demand, read back by the host to size a regrow
         P.sa.count[1] = b;
         P.sn.count[1] = c;
+        P.st.count[1] = d;
+        if (d > C.capacity) { atomicOr(&P.flags[0], 32u); d = C.capacity; }
+        *P.st.count = d;
         if (a > C.capacity) { atomicOr(&P.flags[0], 1u); a = C.capacity; }
         if (b > C.capacity) { atomicOr(&P.flags[0], 2u); b = C.capacity; }
         if (c > C.capacity) { atomicOr(&P.flags[0], 4u); c = C.capacity; }

@@ -226,21 +226,72 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Wrench of the few "wall" owners (analytical boundaries, meshes).  The contacts of a warp almost always share ONE such
+// owner, so a per-contact or even per-warp reduction would serialise on the single L2 line of its wrench: reduce across
+// the warp first, then into a per-CTA shared-memory table, and flush one vector reduction pair per owner per CTA.
+struct CtaWallAcc {
+    uint32_t key[8];
+    float val[8][6];
+    int count;
+};
+__device__ __forceinline__ void wall_init(CtaWallAcc& w) {
+    if (threadIdx.x < 8) {
+        w.key[threadIdx.x] = 0xffffffffu;
+#pragma unroll
+        for (int k = 0; k < 6; k++) w.val[threadIdx.x][k] = 0.f;
+    }
+    if (threadIdx.x == 0) w.count = 0;
+    __syncthreads();
+}
+// called by whole warps (inactive lanes pass touchB = false)
+__device__ __forceinline__ void wall_add(CtaWallAcc& w, const DevParams& P, bool touchB, uint32_t oBkey, const float wB[6]) {
+    uint32_t todo = __ballot_sync(0xffffffffu, touchB);
+    while (todo) {
+        const int leader = __ffs(todo) - 1;
+        const uint32_t key = __shfl_sync(0xffffffffu, oBkey, leader);
+        const bool mine = touchB && (oBkey == key);
+        float v[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) {
+            v[k] = mine ? wB[k] : 0.f;
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        }
+        if ((int)(threadIdx.x & 31) == leader) {
+            int slot = -1;
+            const int cnt = min(w.count, 8);
+            for (int t = 0; t < cnt; t++)
+                if (w.key[t] == key) { slot = t; break; }
+            if (slot < 0) {
+                slot = atomicAdd(&w.count, 1);
+                if (slot < 8) w.key[slot] = key;  // (a racing warp may append the same owner twice: harmless)
+            }
+            if (slot < 8) {
+#pragma unroll
+                for (int k = 0; k < 6; k++) atomicAdd(&w.val[slot][k], v[k]);
+            } else {
+                red_add_v4(&P.wrench[key].f, v[0], v[1], v[2]);
+                red_add_v4(&P.wrench[key].t, v[3], v[4], v[5]);
+            }
+        }
+        todo &= ~__ballot_sync(0xffffffffu, mine);
+    }
+}
+__device__ __forceinline__ void wall_flush(CtaWallAcc& w, const DevParams& P) {
+    __syncthreads();
+    if (threadIdx.x < 8 && threadIdx.x < (unsigned)min(w.count, 8) && w.key[threadIdx.x] != 0xffffffffu) {
+        const float* v = w.val[threadIdx.x];
+        red_add_v4(&P.wrench[w.key[threadIdx.x]].f, v[0], v[1], v[2]);
+        red_add_v4(&P.wrench[w.key[threadIdx.x]].t, v[3], v[4], v[5]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // sphere--analytical contacts (planes, infinite cylinders): checkSphereEntityOverlap, DEMHelperKernels.cuh:459-521
 template <int MODEL, bool RECORD>
 __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevParams P) {
-    // per-CTA accumulator for the (few) wall owners: a per-contact or even per-warp reduction would serialise on the
-    // single L2 line of the wall's wrench
-    __shared__ uint32_t tkey[8];
-    __shared__ float tval[8][6];
-    __shared__ int tcount;
-    if (threadIdx.x < 8) {
-        tkey[threadIdx.x] = 0xffffffffu;
-#pragma unroll
-        for (int k = 0; k < 6; k++) tval[threadIdx.x][k] = 0.f;
-    }
-    if (threadIdx.x == 0) tcount = 0;
-    __syncthreads();
+    __shared__ CtaWallAcc wall;
+    wall_init(wall);
     const uint32_t n = *P.sa.count;
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t nround = (n + 31u) & ~31u;
@@ -334,46 +385,137 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
                 if (RECORD) P.sa.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        // B side: the contacts of a warp almost always share ONE wall owner, so a per-contact reduction would
-        // serialise on a single L2 line. Reduce across the warp first, one vector reduction per distinct owner.
-        uint32_t todo = __ballot_sync(0xffffffffu, touchB);
-        while (todo) {
-            const int leader = __ffs(todo) - 1;
-            const uint32_t key = __shfl_sync(0xffffffffu, oBkey, leader);
-            const bool mine = touchB && (oBkey == key);
-            float v[6];
-#pragma unroll
-            for (int k = 0; k < 6; k++) {
-                v[k] = mine ? wB[k] : 0.f;
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], off);
+        wall_add(wall, P, touchB, oBkey, wB);
+    }
+    wall_flush(wall, P);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// sphere--triangle contacts: triangle_sphere_CD<double3,double> (DEMCollisionKernels.cu:15-156) inside
+// calculateContactForces (DEMCalcForceKernels.cu:134-177).  Everything is evaluated in the frame of owner A's position
+// (the integer owner difference is exact), the nodes being rotated in double by the float quaternion as the
+// reference's equipOwnerPosRot<double3> does.
+struct D3 { double x, y, z; };
+__device__ __forceinline__ D3 operator-(D3 a, D3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ D3 operator+(D3 a, D3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+__device__ __forceinline__ D3 operator*(D3 a, double s) { return {a.x * s, a.y * s, a.z * s}; }
+__device__ __forceinline__ double ddot(D3 a, D3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ D3 dcross(D3 a, D3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+__device__ __forceinline__ D3 rotate_d(float4 n, float4 q) {
+    const float w = q.x, x = q.y, y = q.z, z = q.w;
+    const double X = (double)n.x, Y = (double)n.y, Z = (double)n.z;
+    D3 r;
+    r.x = (double)(2.0f * (w * w + x * x) - 1.0f) * X + (double)(2.0f * (x * y - w * z)) * Y + (double)(2.0f * (x * z + w * y)) * Z;
+    r.y = (double)(2.0f * (x * y + w * z)) * X + (double)(2.0f * (w * w + y * y) - 1.0f) * Y + (double)(2.0f * (y * z - w * x)) * Z;
+    r.z = (double)(2.0f * (x * z - w * y)) * X + (double)(2.0f * (y * z + w * x)) * Y + (double)(2.0f * (w * w + z * z) - 1.0f) * Z;
+    return r;
+}
+// closest point of triangle ABC to P; returns true when it lies on an edge or vertex (snap_to_face)
+__device__ __forceinline__ bool snap_to_face(D3 A, D3 B, D3 C, D3 Pt, D3& res) {
+    const D3 AB = B - A, AC = C - A, AP = Pt - A;
+    const double d1 = ddot(AB, AP), d2 = ddot(AC, AP);
+    if (d1 <= 0. && d2 <= 0.) { res = A; return true; }
+    const D3 BP = Pt - B;
+    const double d3 = ddot(AB, BP), d4 = ddot(AC, BP);
+    if (d3 >= 0. && d4 <= d3) { res = B; return true; }
+    const double vc = d1 * d4 - d3 * d2;
+    if (vc <= 0. && d1 >= 0. && d3 <= 0.) { res = A + AB * (d1 / (d1 - d3)); return true; }
+    const D3 CP = Pt - C;
+    const double d5 = ddot(AB, CP), d6 = ddot(AC, CP);
+    if (d6 >= 0. && d5 <= d6) { res = C; return true; }
+    const double vb = d5 * d2 - d1 * d6;
+    if (vb <= 0. && d2 >= 0. && d6 <= 0.) { res = A + AC * (d2 / (d2 - d6)); return true; }
+    const double va = d3 * d6 - d5 * d4;
+    if (va <= 0. && (d4 - d3) >= 0. && (d5 - d6) >= 0.) { res = B + (C - B) * ((d4 - d3) / ((d4 - d3) + (d5 - d6))); return true; }
+    const double denom = 1.0 / (va + vb + vc);
+    res = (A + AB * (vb * denom)) + AC * (vc * denom);
+    return false;
+}
+
+template <int MODEL, bool RECORD>
+__global__ void __launch_bounds__(256) k_force_st(const __grid_constant__ DevParams P) {
+    __shared__ CtaWallAcc wall;
+    wall_init(wall);
+    const uint32_t n = *P.st.count;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += stride) {
+        const bool active = c < n;
+        float wB[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool touchB = false;
+        uint32_t oBkey = 0xffffffffu;
+        if (active) {
+            const uint4 ci = P.st.cinfo[c];
+            const uint32_t oA = ci.x, tri = ci.y;
+            const uint32_t oB = P.tri_info[tri].x;
+            oBkey = oB;
+            const bool alive = (ci.w >> 31) != 0u;
+            float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (MODEL == 0 && alive) hist = P.st.hist[c];
+            const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
+            OwnerPos pA, pB;
+            End A, B;
+            load_owner(P.state, oA, pA, A);
+            load_owner(P.state, oB, pB, B);
+            const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
+            long long ax, ay, az, bx, by, bz;
+            pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
+            pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
+            const D3 ownB = {(double)(bx - ax) * P.l, (double)(by - ay) * P.l, (double)(bz - az) * P.l};  // ownerB - ownerA
+            const D3 n1 = rotate_d(__ldg(&P.tri_n1[tri]), B.q) + ownB;
+            const D3 n2 = rotate_d(__ldg(&P.tri_n2[tri]), B.q) + ownB;
+            const D3 n3 = rotate_d(__ldg(&P.tri_n3[tri]), B.q) + ownB;
+            const D3 sp = {(double)relA.x, (double)relA.y, (double)relA.z};
+            const double radius = (double)compA.w;
+            D3 fn = dcross(n2 - n1, n3 - n1);
+            const double invLen = (double)(1.0f / sqrtf((float)ddot(fn, fn)));  // normalize(double3) is float precision
+            fn = fn * invLen;
+            const double hgt = ddot(sp - n1, fn);
+            D3 cp, nd;
+            double dpen;  // signed distance minus radius (negative = overlap)
+            bool in_contact;
+            if (!snap_to_face(n1, n2, n3, sp, cp)) {
+                dpen = hgt - radius;
+                nd = fn;
+                in_contact = !(hgt >= radius || hgt <= -radius);
+            } else {
+                const D3 d = sp - cp;
+                const double dist = sqrt(ddot(d, d));
+                dpen = dist - radius;
+                nd = d * (1.0 / dist);
+                in_contact = !(dpen >= 0. || hgt >= radius || hgt <= -radius);
             }
-            if ((int)(threadIdx.x & 31) == leader) {
-                int slot = -1;
-                const int cnt = min(tcount, 8);
-                for (int t = 0; t < cnt; t++)
-                    if (tkey[t] == key) { slot = t; break; }
-                if (slot < 0) {
-                    slot = atomicAdd(&tcount, 1);
-                    if (slot < 8) tkey[slot] = key;  // (a racing warp may append the same owner twice: harmless)
+            if (in_contact && dpen < 0.) {
+                const float3 nrm = f3((float)nd.x, (float)nd.y, (float)nd.z);
+                const float3 armA = f3((float)cp.x, (float)cp.y, (float)cp.z);
+                const float3 armB = f3((float)(cp.x - ownB.x), (float)(cp.y - ownB.y), (float)(cp.z - ownB.z));
+                const MatPair mp = P.matpair[ci.w & 0xffffu];
+                float3 force, troll;
+                contact_model<MODEL>(mp, P.h, (float)(-dpen), nrm, armA, armB, A, B, compA.w, 1e15f, hist, force, troll);
+                const float3 Ft = force + troll;
+                const float3 TA = cross(armA, Ft);
+                const float3 TB = cross(Ft, armB);
+                red_add_v4(&P.wrench[oA].f, force.x, force.y, force.z);
+                red_add_v4(&P.wrench[oA].t, TA.x, TA.y, TA.z);
+                wB[0] = -force.x; wB[1] = -force.y; wB[2] = -force.z;
+                wB[3] = TB.x; wB[4] = TB.y; wB[5] = TB.z;
+                touchB = true;
+                if (MODEL == 0) {
+                    P.st.hist[c] = hist;
+                    if (!alive) P.st.cinfo[c].w = ci.w | 0x80000000u;
                 }
-                if (slot < 8) {
-#pragma unroll
-                    for (int k = 0; k < 6; k++) atomicAdd(&tval[slot][k], v[k]);
-                } else {
-                    red_add_v4(&P.wrench[key].f, v[0], v[1], v[2]);
-                    red_add_v4(&P.wrench[key].t, v[3], v[4], v[5]);
+                if (RECORD) P.st.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+            } else {
+                if (MODEL == 0 && alive) {
+                    P.st.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    P.st.cinfo[c].w = ci.w & 0x7fffffffu;
                 }
+                if (RECORD) P.st.force[c] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            todo &= ~__ballot_sync(0xffffffffu, mine);
         }
+        wall_add(wall, P, touchB, oBkey, wB);
     }
-    __syncthreads();
-    if (threadIdx.x < 8 && threadIdx.x < (unsigned)min(tcount, 8) && tkey[threadIdx.x] != 0xffffffffu) {
-        const float* v = tval[threadIdx.x];
-        red_add_v4(&P.wrench[tkey[threadIdx.x]].f, v[0], v[1], v[2]);
-        red_add_v4(&P.wrench[tkey[threadIdx.x]].t, v[3], v[4], v[5]);
-    }
+    wall_flush(wall, P);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -459,7 +601,7 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
     }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        if (!LinP[k]) X[k] += (double)vp[k] * (double)h;
+        if (!LinP[k]) X[k] = __dadd_rn(X[k], __dmul_rn((double)vp[k], (double)h));
         X[k] -= (double)P.LBF[k];
     }
     if (P.fast_encode) pos_encode_fast(pos, P, X[0], X[1], X[2]); else pos_encode(pos, P, X[0], X[1], X[2]);
@@ -468,11 +610,15 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
         const float hh = P.half_h;
         const float b2 = hh * wp[0], c2 = hh * wp[1], d2 = hh * wp[2];
         const float a1 = q.x, b1 = q.y, c1 = q.z, d1 = q.w;
-        const float Aq = a1 - b1 * b2 - c1 * c2 - d1 * d2;
-        const float Bq = a1 * b2 + b1 + c1 * d2 - d1 * c2;
-        const float Cq = a1 * c2 - b1 * d2 + c1 + d1 * b2;
-        const float Dq = a1 * d2 + b1 * c2 - c1 * b2 + d1;
-        const float len = sqrtf(Bq * Bq + Cq * Cq + Dq * Dq + Aq * Aq);
+        // Hamilton product q * (1, ha) and renormalisation with every product and sum rounded separately (no FMA
+        // contraction), in the reference's association order (DEMHelperKernels.cuh:228-245): an owner with a
+        // prescribed spin then carries bit for bit the orientation the reference's arithmetic gives it -- one ulp of a
+        // float quaternion moves a facet of a 0.1 m drum by 1e-8 m, 0.1 % of a typical contact overlap.
+        const float Aq = __fsub_rn(__fsub_rn(__fsub_rn(a1, __fmul_rn(b1, b2)), __fmul_rn(c1, c2)), __fmul_rn(d1, d2));
+        const float Bq = __fsub_rn(__fadd_rn(__fadd_rn(__fmul_rn(a1, b2), b1), __fmul_rn(c1, d2)), __fmul_rn(d1, c2));
+        const float Cq = __fadd_rn(__fadd_rn(__fsub_rn(__fmul_rn(a1, c2), __fmul_rn(b1, d2)), c1), __fmul_rn(d1, b2));
+        const float Dq = __fadd_rn(__fsub_rn(__fadd_rn(__fmul_rn(a1, d2), __fmul_rn(b1, c2)), __fmul_rn(c1, b2)), d1);
+        const float len = sqrtf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Bq, Bq), __fmul_rn(Cq, Cq)), __fmul_rn(Dq, Dq)), __fmul_rn(Aq, Aq)));
         q = make_float4(Aq / len, Bq / len, Cq / len, Dq / len);
     }
     // world-frame angular velocity of the NEW state for the next force evaluation
@@ -539,6 +685,15 @@ void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaS
         if (record) k_force_sa<0, true><<<grid, block, 0, s>>>(P); else k_force_sa<0, false><<<grid, block, 0, s>>>(P);
     } else {
         if (record) k_force_sa<1, true><<<grid, block, 0, s>>>(P); else k_force_sa<1, false><<<grid, block, 0, s>>>(P);
+    }
+}
+
+void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {
+    const int block = 256;
+    if (model == DEM_HERTZIAN) {
+        if (record) k_force_st<0, true><<<grid, block, 0, s>>>(P); else k_force_st<0, false><<<grid, block, 0, s>>>(P);
+    } else {
+        if (record) k_force_st<1, true><<<grid, block, 0, s>>>(P); else k_force_st<1, false><<<grid, block, 0, s>>>(P);
     }
 }
 

@@ -159,6 +159,59 @@ class DEMExternObj : public DEMInitializer {
                      const objNormal_t normal = ENTITY_NORMAL_INWARD);
 };
 
+/// Triangle mesh owner (src/DEM/BdrsAndObjs.h:222-520). Vertices live in the mesh frame; facets are counter-clockwise
+/// (the right-hand-rule normal is the side that pushes spheres away).
+class DEMMeshConnected : public DEMInitializer {
+  public:
+    size_t nTri = 0;
+    std::vector<float3> m_vertices;
+    std::vector<float3> m_normals;
+    std::vector<float3> m_UV;
+    std::vector<int3> m_face_v_indices;
+    std::vector<int3> m_face_n_indices;
+    std::vector<int3> m_face_uv_indices;
+    std::vector<std::shared_ptr<DEMMaterial>> materials;
+    bool isMaterialSet = false;
+    unsigned int family_code = RESERVED_FAMILY_NUM;
+    float3 init_pos = make_float3(0, 0, 0);
+    float4 init_oriQ = make_float4(0, 0, 0, 1);
+    float mass = 1.f;
+    float3 MOI = make_float3(1.f, 1.f, 1.f);
+    std::string filename;
+    bodyID_t owner = 0;  // resolved at Initialize()
+
+    DEMMeshConnected() { obj_type = OWNER_TYPE::MESH; }
+    explicit DEMMeshConnected(const std::string& input_file) {
+        obj_type = OWNER_TYPE::MESH;
+        LoadWavefrontMesh(input_file);
+    }
+    DEMMeshConnected(const std::string& input_file, const std::shared_ptr<DEMMaterial>& mat) {
+        obj_type = OWNER_TYPE::MESH;
+        LoadWavefrontMesh(input_file);
+        SetMaterial(mat);
+    }
+    bool LoadWavefrontMesh(const std::string& input_file, bool load_normals = true, bool load_uv = false);
+    /// Build from raw arrays (vertices + vertex-index triples)
+    void SetGeometry(const std::vector<float3>& vertices, const std::vector<int3>& faces);
+    size_t GetNumTriangles() const { return nTri; }
+    size_t GetNumNodes() const { return m_vertices.size(); }
+    std::vector<float3>& GetCoordsVertices() { return m_vertices; }
+    std::vector<int3>& GetIndicesVertexes() { return m_face_v_indices; }
+    void Clear();
+    void SetMass(float m) { mass = m; }
+    void SetMOI(float3 moi) { MOI = moi; }
+    void SetFamily(unsigned int num) { family_code = num; }
+    void SetMaterial(const std::vector<std::shared_ptr<DEMMaterial>>& input);
+    void SetMaterial(const std::shared_ptr<DEMMaterial>& input) { SetMaterial(std::vector<std::shared_ptr<DEMMaterial>>(nTri, input)); }
+    void SetInitQuat(const float4 rotQ) { init_oriQ = rotQ; }
+    void SetInitPos(const float3 displ) { init_pos = displ; }
+    void InformCentroidPrincipal(float3 center, float4 prin_Q);
+    void Move(float3 vec, float4 rot_Q);
+    void Mirror(float3 plane_point, float3 plane_normal);
+    void Scale(float s);
+    void Scale(float3 s);
+};
+
 class DEMSolver;
 
 /// Tracker of one loaded object (a clump batch or an external object): src/DEM/AuxClasses.h:93-420
@@ -319,6 +372,13 @@ class DEMSolver {
     }
     std::shared_ptr<DEMExternObj> AddExternalObject();
     std::shared_ptr<DEMExternObj> AddBCPlane(const float3 pos, const float3 normal, const std::shared_ptr<DEMMaterial>& material);
+    std::shared_ptr<DEMMeshConnected> AddWavefrontMeshObject(const std::string& filename, const std::shared_ptr<DEMMaterial>& mat,
+                                                             bool load_normals = true, bool load_uv = false);
+    std::shared_ptr<DEMMeshConnected> AddWavefrontMeshObject(const std::string& filename, bool load_normals = true,
+                                                             bool load_uv = false);
+    std::shared_ptr<DEMMeshConnected> AddWavefrontMeshObject(DEMMeshConnected& mesh);
+    std::shared_ptr<DEMMeshConnected> AddMesh(DEMMeshConnected& mesh) { return AddWavefrontMeshObject(mesh); }
+    size_t GetNumMeshes() const { return m_cached_meshes.size(); }
 
     template <typename T>
     std::shared_ptr<DEMTracker> Track(const std::shared_ptr<T>& obj) {
@@ -360,7 +420,7 @@ class DEMSolver {
     void WriteSphereFile(const std::filesystem::path& outfilename) const;
     void WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy = 10) const;
     void WriteContactFile(const std::filesystem::path& outfilename, float force_thres = 1e-15) const;
-    void WriteMeshFile(const std::filesystem::path&) const {}
+    void WriteMeshFile(const std::filesystem::path& outfilename) const;  // legacy-ASCII VTK of all meshes, current pose
     static std::unordered_map<std::string, std::vector<float3>> ReadClumpXyzFromCsv(
         const std::string& infilename, const std::string& clump_header = "clump_type", const std::string& x_header = "X",
         const std::string& y_header = "Y", const std::string& z_header = "Z");
@@ -425,6 +485,7 @@ class DEMSolver {
     std::vector<std::shared_ptr<DEMClumpTemplate>> m_templates;
     std::vector<std::shared_ptr<DEMClumpBatch>> m_cached_input_clump_batches;
     std::vector<std::shared_ptr<DEMExternObj>> m_cached_extern_objs;
+    std::vector<std::shared_ptr<DEMMeshConnected>> m_cached_meshes;
     std::vector<std::shared_ptr<DEMTracker>> m_trackers;
     std::vector<std::pair<unsigned, unsigned>> m_input_no_contact_pairs;
     std::map<unsigned, Prescription> m_prescriptions;

@@ -24,7 +24,19 @@ class Sampler {
         m_size = make_float3(radius, radius, halfHeight);
         return Sample(1);
     }
+    /// Points in the x- / y-aligned cylinder of given radius and half height
+    std::vector<float3> SampleCylinderX(const float3& center, float radius, float halfHeight) {
+        m_center = center;
+        m_size = make_float3(halfHeight, radius, radius);
+        return Sample(2);
+    }
+    std::vector<float3> SampleCylinderY(const float3& center, float radius, float halfHeight) {
+        m_center = center;
+        m_size = make_float3(radius, halfHeight, radius);
+        return Sample(3);
+    }
     virtual void SetSeparation(float separation) { m_separation = separation; }
+    virtual float GetSeparation() const { return m_separation; }
 
   protected:
     virtual std::vector<float3> Sample(int volume) = 0;
@@ -33,6 +45,8 @@ class Sampler {
         const float fuzz = (m_size.x < 1) ? 1e-6f * m_size.x : 1e-6f;
         if (volume == 0)
             return std::fabs(v.x) <= m_size.x + fuzz && std::fabs(v.y) <= m_size.y + fuzz && std::fabs(v.z) <= m_size.z + fuzz;
+        if (volume == 2) return (v.y * v.y + v.z * v.z <= m_size.y * m_size.y) && std::fabs(v.x) <= m_size.x + fuzz;
+        if (volume == 3) return (v.x * v.x + v.z * v.z <= m_size.x * m_size.x) && std::fabs(v.y) <= m_size.y + fuzz;
         return (v.x * v.x + v.y * v.y <= m_size.x * m_size.x) && std::fabs(v.z) <= m_size.z + fuzz;
     }
     float m_separation;

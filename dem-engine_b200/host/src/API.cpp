@@ -360,6 +360,173 @@ std::shared_ptr<DEMExternObj> DEMSolver::AddBCPlane(const float3 pos, const floa
     return o;
 }
 
+// ---- DEMMeshConnected (src/DEM/BdrsAndObjs.h:222-520, src/DEM/BdrsAndObjs.cpp LoadWavefrontMesh) ----
+bool DEMMeshConnected::LoadWavefrontMesh(const std::string& input_file, bool load_normals, bool load_uv) {
+    std::ifstream in(input_file);
+    if (!in.is_open()) {
+        std::cerr << "Cannot open mesh file " << input_file << std::endl;
+        return false;
+    }
+    Clear();
+    filename = input_file;
+    std::string line;
+    // one face corner "v", "v/vt", "v//vn" or "v/vt/vn"; negative indices count from the end
+    auto corner = [&](const std::string& tok, int& v, int& vt, int& vn) {
+        v = vt = vn = 0;
+        size_t a = tok.find('/');
+        v = std::stoi(tok.substr(0, a));
+        if (a != std::string::npos) {
+            size_t b = tok.find('/', a + 1);
+            const std::string st = tok.substr(a + 1, b == std::string::npos ? std::string::npos : b - a - 1);
+            if (!st.empty()) vt = std::stoi(st);
+            if (b != std::string::npos && b + 1 < tok.size()) vn = std::stoi(tok.substr(b + 1));
+        }
+        if (v < 0) v = (int)m_vertices.size() + v + 1;
+        if (vt < 0) vt = (int)m_UV.size() + vt + 1;
+        if (vn < 0) vn = (int)m_normals.size() + vn + 1;
+    };
+    while (std::getline(in, line)) {
+        std::istringstream ss(line);
+        std::string tag;
+        if (!(ss >> tag)) continue;
+        if (tag == "v") {
+            float x, y, z;
+            ss >> x >> y >> z;
+            m_vertices.push_back(make_float3(x, y, z));
+        } else if (tag == "vn") {
+            float x, y, z;
+            ss >> x >> y >> z;
+            if (load_normals) m_normals.push_back(make_float3(x, y, z));
+        } else if (tag == "vt") {
+            float u = 0, v = 0;
+            ss >> u >> v;
+            if (load_uv) m_UV.push_back(make_float3(u, v, 0));
+        } else if (tag == "f") {
+            std::vector<int> vi, ti, ni;
+            std::string tok;
+            while (ss >> tok) {
+                int v, vt, vn;
+                corner(tok, v, vt, vn);
+                vi.push_back(v - 1); ti.push_back(vt - 1); ni.push_back(vn - 1);
+            }
+            for (size_t k = 1; k + 1 < vi.size(); k++) {  // fan triangulation of polygons
+                m_face_v_indices.push_back(make_int3(vi[0], vi[k], vi[k + 1]));
+                if (load_normals && ni[0] >= 0) m_face_n_indices.push_back(make_int3(ni[0], ni[k], ni[k + 1]));
+                if (load_uv && ti[0] >= 0) m_face_uv_indices.push_back(make_int3(ti[0], ti[k], ti[k + 1]));
+            }
+        }
+    }
+    for (const auto& fc : m_face_v_indices)
+        if (fc.x < 0 || fc.y < 0 || fc.z < 0 || (size_t)fc.x >= m_vertices.size() || (size_t)fc.y >= m_vertices.size() ||
+            (size_t)fc.z >= m_vertices.size())
+            fail("Mesh file " + input_file + " has a facet that refers to a vertex it does not define.");
+    nTri = m_face_v_indices.size();
+    return true;
+}
+void DEMMeshConnected::SetGeometry(const std::vector<float3>& vertices, const std::vector<int3>& faces) {
+    Clear();
+    m_vertices = vertices;
+    m_face_v_indices = faces;
+    for (const auto& fc : faces)
+        if (fc.x < 0 || fc.y < 0 || fc.z < 0 || (size_t)fc.x >= vertices.size() || (size_t)fc.y >= vertices.size() ||
+            (size_t)fc.z >= vertices.size())
+            fail("SetGeometry: a facet refers to a vertex that does not exist.");
+    nTri = faces.size();
+}
+void DEMMeshConnected::Clear() {
+    m_vertices.clear(); m_normals.clear(); m_UV.clear();
+    m_face_v_indices.clear(); m_face_n_indices.clear(); m_face_uv_indices.clear();
+    materials.clear(); isMaterialSet = false;
+    nTri = 0;
+}
+void DEMMeshConnected::SetMaterial(const std::vector<std::shared_ptr<DEMMaterial>>& input) {
+    if (input.size() != nTri) {
+        std::stringstream ss;
+        ss << "SetMaterial input argument must have length " << nTri << " (not " << input.size()
+           << "), same as the number of triangle facets in the mesh." << std::endl;
+        throw std::runtime_error(ss.str());
+    }
+    materials = input;
+    isMaterialSet = true;
+}
+// applyFrameTransformGlobalToLocal / LocalToGlobal, src/DEM/HostSideHelpers.hpp
+void DEMMeshConnected::InformCentroidPrincipal(float3 center, float4 prin_Q) {
+    const float4 inv = make_float4(-prin_Q.x, -prin_Q.y, -prin_Q.z, prin_Q.w);
+    for (auto& node : m_vertices) node = Rotate(node - center, inv);
+}
+void DEMMeshConnected::Move(float3 vec, float4 rot_Q) {
+    for (auto& node : m_vertices) node = Rotate(node, rot_Q) + vec;
+}
+void DEMMeshConnected::Mirror(float3 plane_point, float3 plane_normal) {
+    plane_normal = normalize(plane_normal);
+    for (auto& node : m_vertices) node += 2.f * dot(plane_point - node, plane_normal) * plane_normal;
+    for (auto& nrm : m_normals) nrm -= 2.f * dot(nrm, plane_normal) * plane_normal;
+    for (auto* faces : {&m_face_v_indices, &m_face_n_indices, &m_face_uv_indices})
+        for (auto& fc : *faces) std::swap(fc.y, fc.z);  // keep the winding outward after the reflection
+}
+void DEMMeshConnected::Scale(float s) {
+    if (!(s > 0.f)) fail("Scale: the scaling factor must be positive.");
+    for (auto& node : m_vertices) node *= s;
+    const double d = (double)s;
+    mass = (float)(mass * d * d * d);
+    MOI *= d * d * d * d * d;
+}
+void DEMMeshConnected::Scale(float3 s) {
+    if (!(s.x > 0.f && s.y > 0.f && s.z > 0.f)) fail("Scale: the scaling factors must be positive.");
+    for (auto& node : m_vertices) node = node * s;
+    const double prod = (double)s.x * (double)s.y * (double)s.z;
+    mass = (float)(mass * prod);
+    MOI.x = (float)(MOI.x * prod * s.x * s.x);
+    MOI.y = (float)(MOI.y * prod * s.y * s.y);
+    MOI.z = (float)(MOI.z * prod * s.z * s.z);
+}
+
+std::shared_ptr<DEMMeshConnected> DEMSolver::AddWavefrontMeshObject(DEMMeshConnected& mesh) {
+    if (mesh.GetNumTriangles() == 0 && verbosity >= WARNING)
+        std::cerr << "WARNING! It seems that a mesh contains 0 triangle facet at the time it is loaded." << std::endl;
+    if (sys_initialized) fail("AddWavefrontMeshObject: adding meshes to an initialised system is not supported; add them before Initialize().");
+    auto m = std::make_shared<DEMMeshConnected>(mesh);
+    m->load_order = (unsigned int)m_cached_meshes.size();
+    m_cached_meshes.push_back(m);
+    return m;
+}
+std::shared_ptr<DEMMeshConnected> DEMSolver::AddWavefrontMeshObject(const std::string& filename, const std::shared_ptr<DEMMaterial>& mat,
+                                                                    bool load_normals, bool load_uv) {
+    DEMMeshConnected mesh;
+    if (!mesh.LoadWavefrontMesh(filename, load_normals, load_uv)) fail("Failed to load in mesh file " + filename + ".");
+    mesh.SetMaterial(mat);
+    return AddWavefrontMeshObject(mesh);
+}
+std::shared_ptr<DEMMeshConnected> DEMSolver::AddWavefrontMeshObject(const std::string& filename, bool load_normals, bool load_uv) {
+    DEMMeshConnected mesh;
+    if (!mesh.LoadWavefrontMesh(filename, load_normals, load_uv)) fail("Failed to load in mesh file " + filename + ".");
+    return AddWavefrontMeshObject(mesh);
+}
+
+void DEMSolver::WriteMeshFile(const std::filesystem::path& outfilename) const {
+    assertInit("WriteMeshFile");
+    std::ofstream f(outfilename);
+    size_t nV = 0, nF = 0;
+    for (const auto& m : m_cached_meshes) { nV += m->m_vertices.size(); nF += m->nTri; }
+    f << "# vtk DataFile Version 2.0\nmeshes\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS " << nV << " float\n";
+    for (const auto& m : m_cached_meshes) {
+        const float3 p = GetOwnerPosition(m->owner);
+        const float4 q = GetOwnerOriQ(m->owner);
+        for (const auto& v : m->m_vertices) {
+            const float3 w = Rotate(v, q) + p;
+            f << w.x << " " << w.y << " " << w.z << "\n";
+        }
+    }
+    f << "CELLS " << nF << " " << 4 * nF << "\n";
+    size_t base = 0;
+    for (const auto& m : m_cached_meshes) {
+        for (const auto& fc : m->m_face_v_indices) f << "3 " << base + fc.x << " " << base + fc.y << " " << base + fc.z << "\n";
+        base += m->m_vertices.size();
+    }
+    f << "CELL_TYPES " << nF << "\n";
+    for (size_t i = 0; i < nF; i++) f << "5\n";
+}
+
 std::shared_ptr<DEMInspector> DEMSolver::CreateInspector(const std::string& quantity) {
     return std::make_shared<DEMInspector>(this, quantity);
 }
@@ -548,6 +715,7 @@ void DEMSolver::Initialize(bool dry_run) {
         mass.push_back(t->mass); moiX.push_back(t->MOI.x); moiY.push_back(t->MOI.y); moiZ.push_back(t->MOI.z);
     }
     for (const auto& e : ext) { mass.push_back(e->mass); moiX.push_back(e->MOI.x); moiY.push_back(e->MOI.y); moiZ.push_back(e->MOI.z); }
+    for (const auto& m : m_cached_meshes) { mass.push_back(m->mass); moiX.push_back(m->MOI.x); moiY.push_back(m->MOI.y); moiZ.push_back(m->MOI.z); }
     check(dem_upload_templates(ctx, (uint32_t)radii.size(), radii.data(), relX.data(), relY.data(), relZ.data(),
                                (uint32_t)mass.size(), mass.data(), moiX.data(), moiY.data(), moiZ.data()),
           "dem_upload_templates");
@@ -576,10 +744,10 @@ void DEMSolver::Initialize(bool dry_run) {
     }
     check(dem_upload_materials(ctx, nM, E.data(), nu.data(), CoR.data(), mu.data(), Crr.data()), "dem_upload_materials");
 
-    // ---- owners: clumps, then external objects ----
+    // ---- owners: clumps, then external objects, then meshes (dT.cpp:638-1024) ----
     size_t nC = 0;
     for (const auto& b : m_cached_input_clump_batches) nC += b->nClumps;
-    const size_t nE = ext.size(), nO = nC + nE;
+    const size_t nE = ext.size(), nMesh = m_cached_meshes.size(), nO = nC + nE + nMesh;
     std::vector<float> xyz(3 * nO), qw(nO), qx(nO), qy(nO), qz(nO), vx(nO), vy(nO), vz(nO), ox(nO), oy(nO), oz(nO);
     std::vector<uint8_t> fam(nO);
     std::vector<uint16_t> inertia(nO);
@@ -633,6 +801,29 @@ void DEMSolver::Initialize(bool dry_run) {
             s1.push_back(c.size1); s2.push_back(0.f); s3.push_back(0.f); objMass.push_back(ob->mass);
         }
     }
+    std::vector<uint32_t> triOwner;
+    std::vector<uint16_t> triMat;
+    std::vector<float> tn1, tn2, tn3;
+    for (size_t mi = 0; mi < nMesh; mi++, o++) {
+        auto& me = m_cached_meshes[mi];
+        if (me->nTri > 0 && !me->isMaterialSet)
+            fail("A meshed object is loaded but does not have associated material.\nPlease assign material to meshes via SetMaterial.");
+        me->owner = (bodyID_t)o;
+        xyz[3 * o] = me->init_pos.x; xyz[3 * o + 1] = me->init_pos.y; xyz[3 * o + 2] = me->init_pos.z;
+        qw[o] = me->init_oriQ.w; qx[o] = me->init_oriQ.x; qy[o] = me->init_oriQ.y; qz[o] = me->init_oriQ.z;
+        fam[o] = (uint8_t)me->family_code;
+        inertia[o] = (uint16_t)(m_templates.size() + nE + mi);
+        m_owner_mass[o] = me->mass; m_owner_moi[o] = me->MOI;
+        for (size_t t = 0; t < me->nTri; t++) {
+            const int3 fc = me->m_face_v_indices[t];
+            const float3 a = me->m_vertices[fc.x], b = me->m_vertices[fc.y], c = me->m_vertices[fc.z];
+            triOwner.push_back((uint32_t)o);
+            triMat.push_back((uint16_t)me->materials[t]->load_order);
+            tn1.insert(tn1.end(), {a.x, a.y, a.z});
+            tn2.insert(tn2.end(), {b.x, b.y, b.z});
+            tn3.insert(tn3.end(), {c.x, c.y, c.z});
+        }
+    }
     std::vector<uint64_t> voxel(nO);
     std::vector<uint16_t> lx(nO), ly(nO), lz(nO);
     dem_host_encode_positions(&sp, xyz.data(), nO, voxel.data(), lx.data(), ly.data(), lz.data());
@@ -647,7 +838,8 @@ void DEMSolver::Initialize(bool dry_run) {
           "dem_upload_owners");
     check(dem_upload_spheres(ctx, (uint32_t)sph_owner.size(), sph_owner.data(), sph_comp.data(), sph_mat.data()),
           "dem_upload_spheres");
-    check(dem_upload_triangles(ctx, 0, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_upload_triangles");
+    check(dem_upload_triangles(ctx, (uint32_t)triOwner.size(), triOwner.data(), tn1.data(), tn2.data(), tn3.data(), triMat.data()),
+          "dem_upload_triangles");
     check(dem_initialize(ctx, 0), "dem_initialize");
     nOwnerClumps = nC; nOwnerBodies = nO; nSpheres = sph_owner.size();
     m_sphere_owner = sph_owner;
@@ -823,6 +1015,7 @@ double DEMSolver::Reduce(int kind) const {
 // ---- trackers ----
 bodyID_t DEMTracker::first() {
     if (obj->obj_type == OWNER_TYPE::CLUMP) return std::static_pointer_cast<DEMClumpBatch>(obj)->first_owner;
+    if (obj->obj_type == OWNER_TYPE::MESH) return std::static_pointer_cast<DEMMeshConnected>(obj)->owner;
     return std::static_pointer_cast<DEMExternObj>(obj)->owner;
 }
 size_t DEMTracker::count() {

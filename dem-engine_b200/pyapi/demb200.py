@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "dem_abi_version", "dem_host_figure_out_nv", "dem_host_box_domain", "dem_host_encode_positions",
     "dem_ctx_create", "dem_ctx_destroy", "dem_last_error", "dem_set_stream", "dem_set_params",
     "dem_upload_templates", "dem_upload_materials", "dem_upload_analytical", "dem_upload_families",
-    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_initialize", "dem_set_contacts",
+    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
@@ -105,6 +105,43 @@ def host_box_domain(x, y, z):
     return out
 
 
+def params_from_flat(f):
+    """DemSimParams of a flattened scene (scenes.flatten)."""
+    p = DemSimParams()
+    p.nvXp2, p.nvYp2, p.nvZp2 = f.nvXp2, f.nvYp2, f.nvZp2
+    p.integrator, p.force_model, p.cd_update_freq = f.integrator, f.force_model, f.cd_update_freq
+    p.l, p.voxelSize = f.l, f.voxelSize
+    for k in range(3):
+        p.LBF[k], p.G[k] = float(f.LBF[k]), float(f.G[k])
+        p.userBoxMin[k], p.userBoxMax[k] = float(f.userBoxMin[k]), float(f.userBoxMax[k])
+    p.h, p.beta = float(f.h), float(f.beta)
+    p.approxMaxVel, p.expSafetyMulti, p.expSafetyAdder = float(f.approxMaxVel), float(f.expSafetyMulti), float(f.expSafetyAdder)
+    p.errOutVel = float(getattr(f, "errOutVel", 1e3))
+    p.record_contact_forces = int(getattr(f, "record_contact_forces", 0))
+    return p
+
+
+def host_slab_bounds(p, world, rank):
+    """x-slab (LBF-relative) of `rank`: dem_host_slab_bounds."""
+    lo, hi = C.c_float(), C.c_float()
+    rc = load_library().dem_host_slab_bounds(C.byref(p), int(world), int(rank), C.byref(lo), C.byref(hi))
+    assert rc == 0
+    return lo.value, hi.value
+
+
+def host_partition_owners(p, world, rank, halo, voxelID, locX):
+    """(role, send) per owner on `rank`: dem_host_partition_owners."""
+    voxelID = np.ascontiguousarray(voxelID, "u8")
+    locX = np.ascontiguousarray(locX, "u2")
+    n = len(voxelID)
+    role, send = np.zeros(n, "u1"), np.zeros(n, "u1")
+    lib = load_library()
+    lib.dem_host_partition_owners.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_uint64] + [C.c_void_p] * 4
+    rc = lib.dem_host_partition_owners(C.byref(p), int(world), int(rank), float(halo), n, _p(voxelID), _p(locX), _p(role), _p(send))
+    assert rc == 0
+    return role, send
+
+
 class DemError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("dem_b200 error %d: %s" % (code, msg))
@@ -147,17 +184,7 @@ class Engine:
 
     def load_flat(self, f, contact_capacity=0):
         """f: FlatWorld-like object (see scenes.flatten) with the reference's SoA arrays."""
-        p = DemSimParams()
-        p.nvXp2, p.nvYp2, p.nvZp2 = f.nvXp2, f.nvYp2, f.nvZp2
-        p.integrator, p.force_model, p.cd_update_freq = f.integrator, f.force_model, f.cd_update_freq
-        p.l, p.voxelSize = f.l, f.voxelSize
-        for k in range(3):
-            p.LBF[k], p.G[k] = float(f.LBF[k]), float(f.G[k])
-            p.userBoxMin[k], p.userBoxMax[k] = float(f.userBoxMin[k]), float(f.userBoxMax[k])
-        p.h, p.beta = float(f.h), float(f.beta)
-        p.approxMaxVel, p.expSafetyMulti, p.expSafetyAdder = float(f.approxMaxVel), float(f.expSafetyMulti), float(f.expSafetyAdder)
-        p.errOutVel = float(getattr(f, "errOutVel", 1e3))
-        p.record_contact_forces = int(getattr(f, "record_contact_forces", 0))
+        p = params_from_flat(f)
         self.set_params(p)
         lib = self.lib
         self._ck(lib.dem_upload_templates(self.ctx, C.c_uint32(f.nComp), _p(f.Radii), _p(f.CDRelPosX), _p(f.CDRelPosY),
@@ -177,6 +204,12 @@ class Engine:
                                        _p(f.inertiaPropOffsets)))
         self._ck(lib.dem_upload_spheres(self.ctx, C.c_uint32(f.nSpheres), _p(f.ownerClumpBody), _p(f.clumpComponentOffset),
                                         _p(f.sphereMaterialOffset)))
+        nTri = int(getattr(f, "nTri", 0))
+        if nTri:
+            self._ck(lib.dem_upload_triangles(self.ctx, C.c_uint32(nTri), _p(f.ownerMesh), _p(f.relPosNode1), _p(f.relPosNode2),
+                                              _p(f.relPosNode3), _p(f.triMaterialOffset)))
+        else:
+            self._ck(lib.dem_upload_triangles(self.ctx, C.c_uint32(0), None, None, None, None, None))
         self._ck(lib.dem_initialize(self.ctx, int(contact_capacity)))
         self.nOwners, self.nSpheres = int(f.nOwners), int(f.nSpheres)
 

@@ -37,6 +37,7 @@ class Scene:
         self.clump_omg = np.zeros((0, 3), "f4")
         self.clump_quat = np.zeros((0, 4), "f4")   # w,x,y,z
         self.clump_family = np.zeros(0, "u1")
+        self.meshes = []             # dicts family, mass, moi, pos, quat(wxyz), vel, omg, verts(n,3), faces(m,3), mat
         self.ext_objs = []           # dicts family, mass, moi, pos, quat(wxyz), comps=[dict(type,pos,dir,size1,normal,mat)]
         self.box = (1.0, 1.0, 1.0)
         self.bounding = "none"       # none | all | top_open | only_bottom | only_sides
@@ -100,6 +101,15 @@ class Scene:
         return len(self.ext_objs) - 1
 
 
+    def add_mesh(self, verts, faces, mat, mass=1.0, moi=(1.0, 1.0, 1.0), pos=(0, 0, 0), quat=(1, 0, 0, 0),
+                 family=RESERVED_FAMILY, vel=(0, 0, 0), omg=(0, 0, 0)):
+        """AddWavefrontMeshObject / AddMesh + SetInitPos/SetInitQuat/SetFamily/SetMass/SetMOI (API.h:629-655): vertices
+        in the mesh frame, counter-clockwise faces (right-hand-rule normal points at the contact side)."""
+        self.meshes.append(dict(verts=np.asarray(verts, "f4").reshape(-1, 3), faces=np.asarray(faces, "i8").reshape(-1, 3),
+                                mat=mat, mass=mass, moi=moi, pos=pos, quat=quat, family=family, vel=vel, omg=omg))
+        return len(self.meshes) - 1
+
+
 def _bounding_box_planes(scene, umin, umax):
     """addWorldBoundingBox, src/DEM/APIPrivate.cpp:955-1014 of the reference: ONE external object with up to 6 planes."""
     mode = scene.bounding
@@ -153,8 +163,9 @@ def flatten(scene):
     relarr = np.asarray(rel, "f4").reshape(-1, 3)
     f.CDRelPosX, f.CDRelPosY, f.CDRelPosZ = (np.ascontiguousarray(relarr[:, k]) for k in range(3))
     # mass properties: clump templates, then external objects (then meshes)
-    mass = [t["mass"] for t in scene.templates] + [e["mass"] for e in ext]
-    moi = [t["moi"] for t in scene.templates] + [e["moi"] for e in ext]
+    meshes = list(scene.meshes)
+    mass = [t["mass"] for t in scene.templates] + [e["mass"] for e in ext] + [m["mass"] for m in meshes]
+    moi = [t["moi"] for t in scene.templates] + [e["moi"] for e in ext] + [m["moi"] for m in meshes]
     f.nMassProps = len(mass)
     f.MassProperties = np.asarray(mass, "f4")
     moi = np.asarray(moi, "f4").reshape(-1, 3)
@@ -178,11 +189,13 @@ def flatten(scene):
                 t[i, j] = t[j, i] = np.float32(v)
         setattr(f, prop, np.ascontiguousarray(t.reshape(-1)))
 
-    # ---- owners: clumps, then analytical objects ----
-    nC, nE = len(scene.clump_type), len(ext)
-    f.nOwners = nC + nE
+    # ---- owners: clumps, then analytical objects, then meshes ----
+    nC, nE, nM = len(scene.clump_type), len(ext), len(meshes)
+    f.nOwners = nC + nE + nM
     f.nClumps = nC
-    xyz = np.concatenate([scene.clump_xyz, np.asarray([e["pos"] for e in ext], "f4").reshape(-1, 3)]).astype("f4")
+    f.nMeshes = nM
+    xyz = np.concatenate([scene.clump_xyz, np.asarray([e["pos"] for e in ext], "f4").reshape(-1, 3),
+                          np.asarray([m["pos"] for m in meshes], "f4").reshape(-1, 3)]).astype("f4")
     p = D.DemSimParams()
     p.nvXp2, p.nvYp2, p.nvZp2, p.l, p.voxelSize = f.nvXp2, f.nvYp2, f.nvZp2, f.l, f.voxelSize
     for k in range(3):
@@ -191,17 +204,19 @@ def flatten(scene):
     xyzc = np.ascontiguousarray(xyz)
     D.load_library().dem_host_encode_positions(C.byref(p), D._p(xyzc), C.c_uint64(f.nOwners), D._p(f.voxelID),
                                                D._p(f.locX), D._p(f.locY), D._p(f.locZ))
-    quat = np.concatenate([scene.clump_quat, np.asarray([e["quat"] for e in ext], "f4").reshape(-1, 4)]).astype("f4")
+    quat = np.concatenate([scene.clump_quat, np.asarray([e["quat"] for e in ext], "f4").reshape(-1, 4),
+                           np.asarray([m["quat"] for m in meshes], "f4").reshape(-1, 4)]).astype("f4")
     f.oriQw, f.oriQx, f.oriQy, f.oriQz = (np.ascontiguousarray(quat[:, k]) if len(quat) else np.zeros(1, "f4") for k in range(4))
-    vel = np.concatenate([scene.clump_vel, np.zeros((nE, 3), "f4")]).astype("f4")
-    omg = np.concatenate([scene.clump_omg, np.zeros((nE, 3), "f4")]).astype("f4")
+    vel = np.concatenate([scene.clump_vel, np.zeros((nE, 3), "f4"), np.asarray([m["vel"] for m in meshes], "f4").reshape(-1, 3)]).astype("f4")
+    omg = np.concatenate([scene.clump_omg, np.zeros((nE, 3), "f4"), np.asarray([m["omg"] for m in meshes], "f4").reshape(-1, 3)]).astype("f4")
     f.vX, f.vY, f.vZ = (np.ascontiguousarray(vel[:, k]) if len(vel) else np.zeros(1, "f4") for k in range(3))
     f.omgBarX, f.omgBarY, f.omgBarZ = (np.ascontiguousarray(omg[:, k]) if len(omg) else np.zeros(1, "f4") for k in range(3))
-    f.familyID = np.concatenate([scene.clump_family, np.asarray([e["family"] for e in ext], "u1")]).astype("u1")
+    f.familyID = np.concatenate([scene.clump_family, np.asarray([e["family"] for e in ext], "u1"),
+                                 np.asarray([m["family"] for m in meshes], "u1")]).astype("u1")
     if len(f.familyID) == 0:
         f.familyID = np.zeros(1, "u1")
     nT = len(scene.templates)
-    f.inertiaPropOffsets = np.concatenate([scene.clump_type.astype("u2"), (nT + np.arange(nE)).astype("u2")]).astype("u2")
+    f.inertiaPropOffsets = np.concatenate([scene.clump_type.astype("u2"), (nT + np.arange(nE + nM)).astype("u2")]).astype("u2")
     if len(f.inertiaPropOffsets) == 0:
         f.inertiaPropOffsets = np.zeros(1, "u2")
 
@@ -234,6 +249,14 @@ def flatten(scene):
     f.objSize3 = np.zeros(max(f.nAnal, 1), "f4")
     f.objMass = g(lambda o, c: ext[o - nC]["mass"], "f4")
 
+    # ---- triangles (dT.cpp:960-1010: facets of all meshes back to back, nodes in the mesh frame) ----
+    f.nTri = int(sum(len(m["faces"]) for m in meshes))
+    if f.nTri:
+        f.ownerMesh = np.concatenate([np.full(len(m["faces"]), nC + nE + i, "u4") for i, m in enumerate(meshes)]).astype("u4")
+        f.triMaterialOffset = np.concatenate([np.full(len(m["faces"]), m["mat"], "u2") for m in meshes]).astype("u2")
+        for k, name in enumerate(("relPosNode1", "relPosNode2", "relPosNode3")):
+            setattr(f, name, np.ascontiguousarray(np.concatenate([m["verts"][m["faces"][:, k]] for m in meshes]).astype("f4")))
+
     # ---- families ----
     f.familyMasks = np.zeros(D.PRESC_DTYPE.itemsize and 32896, "u1")
     for a, b in scene.disabled_pairs:
@@ -260,6 +283,41 @@ def flatten(scene):
                         pr[val][k] = d[key][k]
                         pr[flag][k] = dictate
     return f
+
+
+# -----------------------------------------------------------------------------------------------------------------
+# tessellated test geometry
+def plate_mesh(sx, sy, nx, ny, z=0.0):
+    """A flat plate [-sx/2,sx/2]x[-sy/2,sy/2] at height z, nx*ny*2 facets, normals +z."""
+    xs = np.linspace(-sx / 2, sx / 2, nx + 1, dtype="f8")
+    ys = np.linspace(-sy / 2, sy / 2, ny + 1, dtype="f8")
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    verts = np.stack([X.ravel(), Y.ravel(), np.full(X.size, z)], 1).astype("f4")
+    idx = lambda i, j: i * (ny + 1) + j
+    faces = []
+    for i in range(nx):
+        for j in range(ny):
+            a, b, c, d = idx(i, j), idx(i + 1, j), idx(i + 1, j + 1), idx(i, j + 1)
+            faces += [(a, b, c), (a, c, d)]
+    return verts, np.asarray(faces, "i8")
+
+
+def box_mesh(sx, sy, sz, n=1, inward=True):
+    """Closed box surface centred at the origin, each face n*n*2 facets; normals point inward (a container) or outward."""
+    V, F = [], []
+    half = np.array([sx, sy, sz], "f8") / 2
+    for axis in range(3):
+        for sign in (-1, 1):
+            u, v = [(1, 2), (2, 0), (0, 1)][axis]
+            pv, pf = plate_mesh(2 * half[u], 2 * half[v], n, n)
+            P = np.zeros((len(pv), 3))
+            P[:, u], P[:, v], P[:, axis] = pv[:, 0], pv[:, 1], sign * half[axis]
+            # plate normal is +axis (u x v = axis for the cyclic choice above)
+            want = -sign if inward else sign
+            ff = pf if want > 0 else pf[:, ::-1]
+            F.append(ff + sum(len(x) for x in V))
+            V.append(P)
+    return np.concatenate(V).astype("f4"), np.concatenate(F).astype("i8")
 
 
 # -----------------------------------------------------------------------------------------------------------------
@@ -352,4 +410,82 @@ def config2_clumps(nx, ny, nz, scale=0.005, h=5e-6, cd_update_freq=20, seed=4150
     s.h, s.G = h, (0, 0, -9.81)
     s.force_model = force_model
     s.cd_update_freq = cd_update_freq
+    return s
+
+
+def drum_mesh(radius, length, n_circ, n_axial, n_radial=None):
+    """Closed drum about the y axis, inward-facing facets: mantle n_circ x n_axial quads (2 facets each) and two caps
+    tessellated as n_radial rings.  Returns (verts, faces)."""
+    n_radial = n_radial or max(1, n_axial // 2)
+    th = 2.0 * np.pi * np.arange(n_circ) / n_circ
+    ring = np.stack([np.cos(th), np.zeros(n_circ), np.sin(th)], 1)
+    V, F = [], []
+    ys = np.linspace(-length / 2, length / 2, n_axial + 1)
+    for y in ys:
+        V.append(ring * radius + np.array([0.0, y, 0.0]))
+    idm = lambda a, c: a * n_circ + (c % n_circ)
+    for a in range(n_axial):
+        for c in range(n_circ):
+            p, q, r, s = idm(a, c), idm(a, c + 1), idm(a + 1, c + 1), idm(a + 1, c)
+            F += [(p, q, r), (p, r, s)]
+    base = (n_axial + 1) * n_circ
+    for side, y in ((0, -length / 2), (1, length / 2)):
+        start = base
+        for k in range(1, n_radial + 1):
+            V.append(ring * (radius * k / n_radial) + np.array([0.0, y, 0.0]))
+        V.append(np.array([[0.0, y, 0.0]]))
+        centre = start + n_radial * n_circ
+        idc = lambda k, c: start + (k - 1) * n_circ + (c % n_circ)
+        tri = []
+        for c in range(n_circ):
+            tri.append((centre, idc(1, c + 1), idc(1, c)))
+            for k in range(1, n_radial):
+                p, q, r, s = idc(k, c), idc(k, c + 1), idc(k + 1, c + 1), idc(k + 1, c)
+                tri += [(p, q, r), (p, r, s)]
+        tri = np.asarray(tri, "i8")
+        if side == 1:
+            tri = tri[:, ::-1]
+        F += tri.tolist()
+        base = centre + 1
+    return np.concatenate(V).astype("f4"), np.asarray(F, "i8")
+
+
+def config4_drum(n_clumps=500000, n_tri=50000, scale=0.004, h=5e-6, cd_update_freq=20, seed=7, omega=3.0, fill=0.45,
+                 spacing=2.9, init_vel=None):
+    """C4: polydisperse 3-sphere clumps (three sizes, 1 : 0.8 : 0.65) in a rotating drum made of ~n_tri facets; all wall
+    contacts go through the sphere--triangle path (no analytical boundary).  Hertz-Mindlin with history."""
+    s = Scene()
+    mat = s.load_material(E=1e8, nu=0.3, CoR=0.5, mu=0.4, Crr=0.0)
+    matw = s.load_material(E=2e8, nu=0.3, CoR=0.5, mu=0.6, Crr=0.0)
+    types = []
+    for k in (1.0, 0.8, 0.65):
+        sc = scale * k
+        types.append(s.load_clump_type(2.6e3 * CLUMP3_VOLUME * sc ** 3, np.array(CLUMP3_MOI) * 2.6e3 * sc ** 5,
+                                       CLUMP3[:, 3] * sc, CLUMP3[:, :3] * sc, mat))
+    sep = spacing * scale
+    # drum sized so that the requested number of lattice sites fills `fill` of its height
+    vol_site = sep ** 3 / math.sqrt(2.0)
+    vol = n_clumps * vol_site / fill
+    radius = (vol / (math.pi * 1.2)) ** (1.0 / 3.0)       # length = 1.2 R
+    length = 1.2 * radius
+    pts = hcp_box((0, 0, 0), (radius, length / 2 - 2.2 * scale, radius), sep)
+    rr = np.sqrt(pts[:, 0] ** 2 + pts[:, 2] ** 2)
+    pts = pts[rr < radius - 2.2 * scale]
+    pts = pts[np.argsort(pts[:, 2], kind="stable")][:n_clumps]     # the lowest sites
+    rng = np.random.RandomState(seed)
+    ty = np.asarray(types, "i4")[rng.randint(0, 3, len(pts))]
+    s.add_clumps(ty, pts, quat=random_unit_quats(len(pts), seed), vel=init_vel)
+    # facet count: mantle 2*nc*na + caps 2*nc*(2*nr-1), with na ~ nc*L/(2 pi R), nr ~ nc/(2 pi)
+    nc = max(12, int(round(math.sqrt(n_tri / (2 * 1.2 / (2 * math.pi) + 4 / (2 * math.pi))))))
+    na = max(1, int(round(nc * 1.2 / (2 * math.pi))))
+    nr = max(1, int(round(nc / (2 * math.pi))))
+    v, f = drum_mesh(radius, length, nc, na, nr)
+    s.add_mesh(v, f, mat=matw, mass=1.0, moi=(1, 1, 1), family=10)
+    s.prescribed[10] = dict(linvel=(0.0, 0.0, 0.0), angvel=(0.0, omega, 0.0))
+    d = 2.4 * radius
+    s.box = (d, 1.4 * length, d)
+    s.bounding = "none"
+    s.h, s.G = h, (0, 0, -9.81)
+    s.cd_update_freq = cd_update_freq
+    s.drum_radius, s.drum_length = radius, length
     return s

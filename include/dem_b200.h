@@ -213,6 +213,13 @@ int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]
 int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]);
 /* the x-slab (LBF-relative) of `rank` out of `world` */
 int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, float* hi);
+/* Host statement of the ownership rule the device applies at every rebuild: for each of the first n owners (clump
+ * owners; position codes as uploaded) role[i] = 1 if `rank` owns it (centre inside its slab), 2 if it is a ghost here
+ * (owned by a neighbour, within `halo` of the shared cut), 0 if this rank never sees it; send[i] bit 0 / bit 1 set when
+ * an owned owner must be sent to the left / right neighbour.  Both sides of a cut derive the same answer from the same
+ * position codes, so no negotiation is needed. */
+int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float halo, uint64_t n, const uint64_t* voxelID,
+                              const uint16_t* locX, uint8_t* role, uint8_t* send);
 
 /* execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
  * "fast_encode" (0/1), "sort_mode" (0 radix sort, 1 counting sort; identical order), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */

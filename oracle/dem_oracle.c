@@ -813,6 +813,51 @@ int orc_detect_contacts(OrcWorld* w) {
             if (t && depth > thr) PUSH(s, ob, (uint8_t)t);
         }
     }
+    /* sphere--triangle.  The reference sandwiches each facet between two offset copies, bins them and tests the
+     * inflated sphere against both copies with a one-sided test (src/kernel/DEMBinTriangleKernels.cu:22-221,
+     * src/kernel/DEMContactKernels_SphereTriangle.cu:196-262); which non-touching pairs that admits depends on its bin
+     * size.  What the force pass needs is every pair that can come within one radius of the facet before the next
+     * rebuild, so the restated rule is geometric: distance(centre, facet) < r + margin(sphere) + margin(mesh), less the
+     * smaller family extra margin (same shallow-contact drop as :238-247). */
+    for (uint32_t t = 0; t < w->nTri && nS > 0; t++) {
+        uint32_t oT = w->ownerMesh[t];
+        unsigned famT = w->familyID[oT];
+        double op[3];
+        orc_voxel_decode(w, oT, op);
+        float qw = w->oriQw[oT], qx = w->oriQx[oT], qy = w->oriQy[oT], qz = w->oriQz[oT];
+        d3 nd[3] = {{w->relPosNode1[3 * t], w->relPosNode1[3 * t + 1], w->relPosNode1[3 * t + 2]},
+                    {w->relPosNode2[3 * t], w->relPosNode2[3 * t + 1], w->relPosNode2[3 * t + 2]},
+                    {w->relPosNode3[3 * t], w->relPosNode3[3 * t + 1], w->relPosNode3[3 * t + 2]}};
+        double bl[3] = {1e300, 1e300, 1e300}, bh[3] = {-1e300, -1e300, -1e300};
+        for (int k = 0; k < 3; k++) {
+            quat_rotate_d(&nd[k].x, &nd[k].y, &nd[k].z, qw, qx, qy, qz);
+            nd[k].x += op[0]; nd[k].y += op[1]; nd[k].z += op[2];
+            const double c[3] = {nd[k].x, nd[k].y, nd[k].z};
+            for (int a = 0; a < 3; a++) {
+                if (c[a] < bl[a]) bl[a] = c[a];
+                if (c[a] > bh[a]) bh[a] = c[a];
+            }
+        }
+        const double mT = (double)w->marginSize[oT];
+        const double grow = (double)rmax + mT;
+        for (uint32_t sph = 0; sph < nS; sph++) {
+            const double* P = pos + 3 * sph;
+            if (P[0] < bl[0] - grow || P[0] > bh[0] + grow || P[1] < bl[1] - grow || P[1] > bh[1] + grow ||
+                P[2] < bl[2] - grow || P[2] > bh[2] + grow)
+                continue;
+            uint32_t oS = w->ownerClumpBody[sph];
+            if (oS == oT) continue;
+            unsigned famS = w->familyID[oS];
+            if (w->familyMasks[mask_pair(famS, famT)] != 0) continue;
+            d3 sp = {P[0], P[1], P[2]}, q;
+            snap_to_face(nd[0], nd[1], nd[2], sp, &q);
+            d3 dd = d3_sub(sp, q);
+            const double dist = sqrt(d3_dot(dd, dd));
+            float mA = w->familyExtraMarginSize[famS], mB = w->familyExtraMarginSize[famT];
+            const double am = (mA < mB) ? mA : mB;
+            if (((double)rad[sph] + mT) - dist > am) PUSH(sph, t, ORC_SPHERE_MESH);
+        }
+    }
 #undef PUSH
     free(pos); free(rad);
     qsort(keys, n, sizeof(CKey), ckey_cmp);

@@ -425,7 +425,8 @@ def material_tables(mats, pairs=None):
 
 def world_from_flat(f, contact_capacity=None):
     """Build an oracle World from the flattened arrays a scene produces (pyapi.scenes.flatten)."""
-    w = World(f.nOwners, f.nSpheres, f.nComp, f.nMassProps, f.nMat, f.nAnal, 0, contact_capacity)
+    nTri = int(getattr(f, "nTri", 0))
+    w = World(f.nOwners, f.nSpheres, f.nComp, f.nMassProps, f.nMat, f.nAnal, nTri, contact_capacity)
     for name in ("nvXp2", "nvYp2", "nvZp2", "l", "voxelSize", "integrator", "force_model"):
         setattr(w, name, getattr(f, name))
     w.LBF[:] = f.LBF
@@ -440,6 +441,10 @@ def world_from_flat(f, contact_capacity=None):
         for name, dt in arrs:
             if hasattr(f, name) and n > 0:
                 getattr(w, name)[:n] = np.asarray(getattr(f, name))[:n]
+    for name, dt in _TRI_ARRAYS:
+        if nTri:
+            src = np.asarray(getattr(f, name)).reshape(-1)
+            getattr(w, name)[:len(src)] = src
     for name in ("E", "nu", "CoR", "mu", "Crr"):
         getattr(w, name)[:] = getattr(f, name)
     w.familyMasks[:] = f.familyMasks

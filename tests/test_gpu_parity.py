@@ -64,7 +64,7 @@ def _check_trajectory(eng, f, w, checkpoints, label):
         assert err_v <= 10 * sens_v + 1e-5 * max(1.0, np.abs(_vel(w, nC)).max()), (cp, err_v, sens_v)
 
 
-@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder"])
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder", "mesh_tray"])
 def test_trajectory_matches_oracle(built, kind):
     po = _oracle()
     f = scenes.flatten(_mk(kind))
@@ -94,7 +94,7 @@ def test_trajectory_matches_oracle(built, kind):
     eng.close()
 
 
-@pytest.mark.parametrize("kind", ["clumps_full", "spheres_frictionless", "cylinder"])
+@pytest.mark.parametrize("kind", ["clumps_full", "spheres_frictionless", "cylinder", "mesh_tray"])
 def test_single_step_from_identical_state(built, kind):
     """Advance the oracle into a contact-rich state, load that exact state (positions codes, velocities AND contact
     history) into the device, then compare ONE step: no chaotic growth, so tolerances are at fp32 rounding level."""
@@ -149,10 +149,12 @@ def test_single_step_from_identical_state(built, kind):
     eng.close()
 
 
-def test_candidate_list_is_superset_of_brute_force(built):
-    """Broad phase: every pair of inflated spheres that overlaps (brute force O(N^2) in double) is in the device list."""
+@pytest.mark.parametrize("kind", ["clumps_full", "mesh_tray"])
+def test_candidate_list_is_superset_of_brute_force(built, kind):
+    """Broad phase: every pair of inflated spheres that overlaps (brute force O(N^2) in double), and every sphere within
+    its inflated radius of a facet, is in the device list."""
     po = _oracle()
-    f = scenes.flatten(_mk("clumps_full"))
+    f = scenes.flatten(_mk(kind))
     eng = demb200.Engine(0)
     eng.load_flat(f)
     eng.step(2000)
@@ -171,10 +173,61 @@ def test_candidate_list_is_superset_of_brute_force(built):
     idA, idB, ct, _ = eng.contacts()
     mine = set(zip(idA.tolist(), idB.tolist(), ct.tolist()))
     theirs = set(zip(oa.tolist(), ob.tolist(), ot.tolist()))
-    assert len(theirs) > 50
+    assert len(theirs) > (50 if kind == "clumps_full" else 20)
+    if kind == "mesh_tray":
+        assert sum(1 for t in theirs if t[2] == 2) > 5
     assert theirs <= mine
     # and not wildly larger (float slack only)
     assert len(mine) <= len(theirs) + max(4, len(theirs) // 50)
+    eng.close()
+
+
+def test_drum_config4_small_matches_oracle(built):
+    """BASELINE config 4 at oracle-sized scale: polydisperse clumps in a rotating drum of triangles."""
+    po = _oracle()
+    sc = scenes.config4_drum(2000, 1500, omega=6.0, init_vel=(0.2, 0.0, -1.0), cd_update_freq=10, spacing=2.7)
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    w = po.world_from_flat(f)
+    _check_trajectory(eng, f, w, [500, 1000, 1500, 2000, 2500], "drum")
+    st = eng.stats()
+    assert st.n_contacts_st > 20
+    n = w.nContacts
+    assert int((w.contactType[:n] == 2).sum()) > 20
+    # the drum itself follows its prescription exactly as the oracle's does
+    q = eng.owner_state()["oriQ"][f.nOwners - 1]
+    qo = np.array([w.oriQw[f.nOwners - 1], w.oriQx[f.nOwners - 1], w.oriQy[f.nOwners - 1], w.oriQz[f.nOwners - 1]])
+    assert np.abs(q - qo).max() < 1e-5
+    eng.close()
+
+
+def test_drum_config4_full_size_properties(built):
+    """BASELINE config 4 at full size (500k polydisperse clumps + ~50k facets): size-independent properties."""
+    sc = scenes.config4_drum(500000, 50000, omega=3.0, init_vel=(0.0, 0.0, -1.5), spacing=2.7)
+    f = scenes.flatten(sc)
+    assert f.nClumps == 500000 and 45000 <= f.nTri <= 55000
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    nsteps = 1200
+    eng.step(nsteps)
+    st = eng.stats()
+    assert st.n_contacts_st > 1000 and st.n_contacts_ss > 100000
+    pos = eng.positions()[: f.nClumps]
+    rad = np.sqrt(pos[:, 0] ** 2 + pos[:, 2] ** 2)
+    # nothing leaks through the facets: every clump centre stays inside the drum
+    assert rad.max() < sc.drum_radius and np.abs(pos[:, 1]).max() < sc.drum_length / 2
+    vel = eng.owner_state()["vel"][: f.nClumps]
+    assert np.isfinite(vel).all() and np.abs(vel).max() < 20.0
+    # grains next to the mantle have been stopped by it (they started at -1.5 m/s)
+    idA, idB, ct, wc = eng.contacts()
+    assert int((ct == 2).sum()) == st.n_contacts_st
+    tri_touch = np.unique(idA[(ct == 2) & (np.abs(wc).max(1) > 0)])
+    assert len(tri_touch) > 100
+    # the drum turned by omega * t about y
+    q = eng.owner_state()["oriQ"][f.nOwners - 1]
+    ang = 2 * np.arctan2(q[2], q[0])
+    assert abs(ang - 3.0 * nsteps * float(f.h)) < 1e-4
     eng.close()
 
 
@@ -329,6 +382,17 @@ def test_cpp_facade_demo_scripts(built):
                          timeout=600, cwd="/tmp")
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DEMdemo_ClumpBed exiting" in out.stdout
+    drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "3"], capture_output=True, text=True, env=env,
+                          timeout=600, cwd="/tmp")
+    assert drum.returncode == 0, drum.stdout + drum.stderr
+    assert "DEMdemo_MeshDrum exiting" in drum.stdout
+    dl = [l for l in drum.stdout.splitlines() if l.startswith("Frame")]
+    assert len(dl) == 3
+    for i, l in enumerate(dl):
+        assert float(l.split("max radial =")[1].split(",")[0]) < 0.1       # inside the drum mantle
+        assert float(l.split("max |y| =")[1].split(",")[0]) < 0.04          # between the caps
+        assert abs(float(l.split("drum angle =")[1].split(",")[0]) - 6.0 * 0.01 * (i + 1)) < 1e-3
+    assert int(dl[-1].split("contacts =")[1]) > 100
     lines = [l for l in out.stdout.splitlines() if l.startswith("Frame")]
     assert len(lines) == 3
     lid = [float(l.split("lid z =")[1].split(",")[0]) for l in lines]

@@ -31,6 +31,14 @@ def _scene(kind):
         sc = scenes.config2_clumps(4, 4, 3, cd_update_freq=5, spacing=2.7, init_vel=(1.5, 0.6, -2.0))
         sc.bounding = "only_bottom"
         sc.add_cylinder((0, 0, 0), (0, 0, 1), 0.04, 0, normal=0.0)
+    elif kind == "mesh_tray":
+        # clumps thrown into a tilted, spinning box made of triangles (sphere--triangle contacts)
+        sc = scenes.config2_clumps(4, 4, 3, cd_update_freq=5, spacing=2.7, init_vel=(0.3, 0.1, -2.0))
+        sc.bounding = "none"
+        lo, hi = sc.clump_xyz.min(0), sc.clump_xyz.max(0)
+        v, fc = scenes.box_mesh((hi[0] - lo[0]) * 1.6, (hi[1] - lo[1]) * 1.6, (hi[2] - lo[2]) * 2.2, n=3, inward=True)
+        sc.add_mesh(v, fc, mat=0, mass=1.0, moi=(1, 1, 1), pos=tuple((lo + hi) / 2), quat=(0.9950042, 0.0998334, 0, 0), family=10)
+        sc.prescribed[10] = dict(linvel=(0.0, 0.0, 0.0), angvel=(0.0, 0.0, 2.0))
     else:
         raise KeyError(kind)
     return sc
@@ -47,7 +55,7 @@ def _assert_same_state(a, b):
 
 
 @needs_ref
-@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder"])
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder", "mesh_tray"])
 def test_step_bit_exact_vs_reference_kernels(built, kind):
     f = scenes.flatten(_scene(kind))
     a = pyoracle.world_from_flat(f)
@@ -157,7 +165,7 @@ def test_pair_acceptance_matches_calcContactPoint(built):
     assert len(ss) > 0 and ss == hits
 
 
-GOLDEN_CASES = ["clumps_full", "spheres_frictionless"]
+GOLDEN_CASES = ["clumps_full", "spheres_frictionless", "mesh_tray"]
 
 
 @pytest.mark.parametrize("kind", GOLDEN_CASES)
