@@ -91,6 +91,9 @@ struct DemCtx {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = true;
+    cudaStream_t side = nullptr;   // wall / mesh contact kernels run here, next to the sphere--sphere kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int overlap_walls = 1;
     int num_sms = 148;
     std::string err;
     bool initialized = false;
@@ -180,6 +183,7 @@ struct DemCtx {
     MgState mg;
     float rclump = 0.f;
     int sa_grid = 148;
+    int last_sorted_buf = 0;
 };
 
 namespace {
@@ -446,7 +450,7 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             CK(cudaMemcpyAsync(ctx->h_pinned + 200, ctx->d_triCellStart + ctx->max_cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
         if (stage_us) cudaEventRecord(sev[1], s);
         int sorted_buf = -1;  // -1: counting sort inside the sweep stage
-        if (ctx->sort_mode == 0) launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf);
+        if (ctx->sort_mode == 0) { launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf); ctx->last_sorted_buf = sorted_buf; }
         if (stage_us) cudaEventRecord(sev[2], s);
         launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);  // records sev[3..6]
         if (stage_us) cudaEventRecord(sev[7], s);
@@ -536,11 +540,28 @@ int enqueue_step(DemCtx* ctx) {
         if (rc) return rc;
     }
     DevParams P = make_params(ctx);
-    launch_force_ss(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->num_sms, ctx->ctas_per_sm, ctx->stream);
-    if (ctx->nAnal > 0)
-        launch_force_sa(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
-    if (ctx->nTri > 0)
-        launch_force_st(P, (int)ctx->sp.force_model, ctx->sp.record_contact_forces != 0, ctx->sa_grid, ctx->stream);
+    const int model = (int)ctx->sp.force_model;
+    const bool rec = ctx->sp.record_contact_forces != 0;
+    const bool walls = ctx->nAnal > 0 || ctx->nTri > 0;
+    // The wall / mesh contact kernels are small (tens of thousands of contacts: latency, not bandwidth) and only meet
+    // the sphere--sphere kernel in the wrench accumulator (atomic reductions): run them beside it on a second stream.
+    cudaStream_t ws = (walls && ctx->overlap_walls && ctx->side) ? ctx->side : ctx->stream;
+    if (ws != ctx->stream) {
+        CK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+        CK(cudaStreamWaitEvent(ws, ctx->ev_fork, 0));
+    }
+    if (ws != ctx->stream) {  // first, so that they are resident before the persistent kernel fills the SMs
+        if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, ws);
+        if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, ws);
+        CK(cudaEventRecord(ctx->ev_join, ws));
+    }
+    launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->stream);
+    if (ws == ctx->stream) {
+        if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, ws);
+        if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, ws);
+    } else {
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    }
     launch_integrate(P, ctx->stream);
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     if (ctx->mg.on) {
@@ -650,6 +671,9 @@ int dem_ctx_create(DemCtx** out, int device) {
     cudaHostAlloc((void**)&ctx->h_pinned, 256 * sizeof(uint32_t), cudaHostAllocDefault);
     if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
     for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
+    cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     *out = ctx;
     return DEM_OK;
 }
@@ -668,6 +692,9 @@ int dem_ctx_destroy(DemCtx* ctx) {
             if (g.d_recvbuf[d]) cudaFree(g.d_recvbuf[d]);
         }
     }
+    if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (int k = 0; k < 5; k++)
@@ -1373,6 +1400,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
     else if (n == "sort_mode") ctx->sort_mode = (int)value;
+    else if (n == "overlap_walls") ctx->overlap_walls = value != 0.0;
     else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);
     return DEM_OK;
 }
@@ -1381,6 +1409,30 @@ int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     return rebuild(ctx, out_us);
+}
+
+int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uint64_t* n_out) {
+    if (!ctx || !ctx->initialized || !what || !out || !n_out) return DEM_ERR_INVALID;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const std::string w(what);
+    const void* src = nullptr;
+    uint64_t avail = 0;
+    const uint64_t nS = ctx->nSpheres;
+    if (w == "sphere_keys") { src = ctx->d_keys[0]; avail = nS; }
+    else if (w == "sorted_keys") { src = (ctx->sort_mode == 1) ? ctx->d_vals[0] : ctx->d_keys[ctx->last_sorted_buf]; avail = nS; }
+    else if (w == "sphere_pos") { src = ctx->d_sphF; avail = nS * 4; }
+    else if (w == "sorted_ids") {
+        // second word of the 16-byte sorted meta record
+        const uint64_t m = std::min<uint64_t>(n, nS);
+        if (m) CK(cudaMemcpy2D(out, 4, reinterpret_cast<const char*>(ctx->d_sortedMeta) + 4, 16, 4, m, cudaMemcpyDeviceToHost));
+        *n_out = m;
+        return DEM_OK;
+    } else return fail(ctx, DEM_ERR_INVALID, "dem_debug_download: unknown array '%s'", what);
+    const uint64_t m = std::min<uint64_t>(n, avail);
+    if (m && src) CK(cudaMemcpy(out, src, m * 4, cudaMemcpyDeviceToHost));
+    *n_out = m;
+    return DEM_OK;
 }
 
 int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
@@ -1401,6 +1453,7 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
         launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, s);
         CK(cudaEventRecord(ctx->ev[2], s));
         if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
+        if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
         CK(cudaEventRecord(ctx->ev[3], s));
         launch_integrate(P, s);
         ctx->maxvel_slot ^= 1;
@@ -1411,7 +1464,7 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
             ctx->launches += l;
         }
         CK(cudaEventRecord(ctx->ev[4], s));
-        ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0);
+        ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
         ctx->n_steps++;
         ctx->steps_since_rebuild++;
         ctx->sim_time += (double)ctx->sp.h;

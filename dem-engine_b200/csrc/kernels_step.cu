@@ -655,9 +655,15 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
         if (!isfinite(absv) || absv > P.errOutVel) atomicOr(&P.flags[3], 1u);
         if (!isfinite(absv)) absv = 0.f;
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) absv = fmaxf(absv, __shfl_xor_sync(0xffffffffu, absv, off));
-    if ((threadIdx.x & 31) == 0 && absv > 0.f) atomicMax(reinterpret_cast<int*>(P.maxvel_next), __float_as_int(absv));
+    // non-negative floats order like their bit patterns: integer max in the warp (REDUX), then in the CTA, then ONE
+    // atomic per CTA (a per-warp atomic on a single address serialises 30k updates in L2)
+    __shared__ int s_max;
+    if (threadIdx.x == 0) s_max = 0;
+    __syncthreads();
+    const int wv = __reduce_max_sync(0xffffffffu, __float_as_int(absv));
+    if ((threadIdx.x & 31) == 0 && wv > 0) atomicMax(&s_max, wv);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_max > 0) atomicMax(reinterpret_cast<int*>(P.maxvel_next), s_max);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

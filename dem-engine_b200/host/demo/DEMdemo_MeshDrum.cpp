@@ -91,7 +91,7 @@ int main(int argc, char** argv) {
     auto max_v = DEMSim.CreateInspector("clump_max_absv");
     auto tracker = DEMSim.Track(particles);
     for (int i = 0; i < frames; i++) {
-        DEMSim.DoDynamicsThenSync(0.01);
+        DEMSim.DoDynamicsThenSync(0.02);
         float rmax = 0.f, ymax = 0.f;
         for (const auto& p : tracker->Positions()) {
             rmax = std::max(rmax, std::sqrt(p.x * p.x + p.z * p.z));

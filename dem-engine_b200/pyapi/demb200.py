@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "dem_abi_version", "dem_host_figure_out_nv", "dem_host_box_domain", "dem_host_encode_positions",
     "dem_ctx_create", "dem_ctx_destroy", "dem_last_error", "dem_set_stream", "dem_set_params",
     "dem_upload_templates", "dem_upload_materials", "dem_upload_analytical", "dem_upload_families",
-    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_initialize", "dem_set_contacts",
+    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
@@ -288,6 +288,17 @@ class Engine:
         out = C.c_double(0)
         self._ck(self.lib.dem_reduce(self.ctx, int(kind), C.byref(out)))
         return out.value
+
+    def debug_download(self, what, n=None):
+        """Raw device scratch of the last rebuild / step (dem_debug_download)."""
+        dt = "f4" if what == "sphere_pos" else "u4"
+        if n is None:
+            n = 4 * self.nSpheres if what == "sphere_pos" else self.nSpheres
+        out = np.zeros(max(int(n), 1), dt)
+        got = C.c_uint64()
+        self.lib.dem_debug_download.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_uint64, C.c_void_p]
+        self._ck(self.lib.dem_debug_download(self.ctx, what.encode(), _p(out), int(n), C.byref(got)))
+        return out[: got.value]
 
     # ---- multi-GPU ----
     @staticmethod

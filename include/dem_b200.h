@@ -235,6 +235,13 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]);
  * [6] unused [7] whole rebuild */
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]);
 
+/* Raw views of device scratch of the LAST rebuild / step, for tests and tools (synchronises).  `what`:
+ *   "sphere_keys" u32[nSpheres]  cell key of each sphere (0xffffffff = not held by this rank)
+ *   "sorted_keys" u32[nSpheres]  cell keys in sorted order      "sorted_ids" u32[nSpheres]  sphere ids in sorted order
+ *   "sphere_pos"  f32[4*nSpheres] LBF-relative centre + inflated radius
+ * Copies min(n, available) elements and returns the number copied in *n_out. */
+int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uint64_t* n_out);
+
 #ifdef __cplusplus
 }
 #endif

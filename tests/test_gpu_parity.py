@@ -382,16 +382,16 @@ def test_cpp_facade_demo_scripts(built):
                          timeout=600, cwd="/tmp")
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DEMdemo_ClumpBed exiting" in out.stdout
-    drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "3"], capture_output=True, text=True, env=env,
+    drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "5"], capture_output=True, text=True, env=env,
                           timeout=600, cwd="/tmp")
     assert drum.returncode == 0, drum.stdout + drum.stderr
     assert "DEMdemo_MeshDrum exiting" in drum.stdout
     dl = [l for l in drum.stdout.splitlines() if l.startswith("Frame")]
-    assert len(dl) == 3
+    assert len(dl) == 5
     for i, l in enumerate(dl):
         assert float(l.split("max radial =")[1].split(",")[0]) < 0.1       # inside the drum mantle
         assert float(l.split("max |y| =")[1].split(",")[0]) < 0.04          # between the caps
-        assert abs(float(l.split("drum angle =")[1].split(",")[0]) - 6.0 * 0.01 * (i + 1)) < 1e-3
+        assert abs(float(l.split("drum angle =")[1].split(",")[0]) - 6.0 * 0.02 * (i + 1)) < 1e-3
     assert int(dl[-1].split("contacts =")[1]) > 100
     lines = [l for l in out.stdout.splitlines() if l.startswith("Frame")]
     assert len(lines) == 3
