@@ -256,8 +256,9 @@ def main():
                    "cd_update_freq": args.cd_update_freq, "settle_steps": args.settle_steps,
                    "force_record": False, "l2": "per-step working set > 126 MB L2 (no flush needed)",
                    "parallelism": "1 GPU" if world == 1 else
-                   "%d x-slabs, ghost-owner halo exchange per step over NCCL (rank 0: %d own + %d ghost owners, %d B sent per step)"
-                   % (world, mg["n_own"], mg["n_active"] - mg["n_own"], mg["halo_bytes_per_step"])},
+                   "%d x-slabs, ghost-owner halo exchange per step over %s (rank 0: %d own + %d ghost owners, %d B sent per step)"
+                   % (world, "NVLink peer stores + flags" if mg.get("peer_memory_exchange") else "ncclSend/ncclRecv",
+                      mg["n_own"], mg["n_active"] - mg["n_own"], mg["halo_bytes_per_step"])},
         "grain_updates_per_s": value * n_total_clumps,
         "kernel_us": prof,
         "step_algorithmic_GBps": step_bytes / (ms / args.steps * 1e-3) / 1e9,

@@ -73,6 +73,12 @@ struct MgState {
     uint32_t cap = 0;
     uint32_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}, n_active = 0, n_own = 0;
     uint64_t halo_bytes = 0;  // bytes sent per step by this rank
+    // peer-memory exchange (see kernels_mgpu.cu): one allocation [flags: 256 B][recv: dir x parity x cap x 80 B]
+    bool p2p = false;
+    char* p2p_block = nullptr;
+    char* peer_block[2] = {nullptr, nullptr};  // the neighbours' blocks mapped into this process
+    uint32_t* d_block_counter = nullptr;
+    uint64_t epoch = 0;
 };
 
 struct ListBuf {
@@ -362,6 +368,31 @@ MgParams make_mg(const DemCtx* c) {
 int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches) {
     MgState& g = ctx->mg;
     cudaStream_t s = ctx->stream;
+    if (g.p2p && !flag_or_null) {
+        // per-step path: stores into the neighbours' memory + flags, no library call
+        MgP2P X;
+        memset(&X, 0, sizeof(X));
+        g.epoch++;
+        const size_t half = (size_t)g.cap * 80, par = (size_t)(g.epoch & 1);
+        for (int d = 0; d < 2; d++) {
+            const int peer = g.rank + (d == 0 ? -1 : 1);
+            X.has[d] = (peer >= 0 && peer < g.world) ? 1 : 0;
+            X.send_gid[d] = g.d_send_gid[d]; X.recv_gid[d] = g.d_recv_gid[d];
+            X.n_send[d] = g.n_send[d]; X.n_recv[d] = g.n_recv[d];
+            // my records for the neighbour in direction d arrive there as "from direction 1-d"
+            if (X.has[d]) {
+                X.peer_recv[d] = reinterpret_cast<int4*>(g.peer_block[d] + 256 + ((size_t)(1 - d) * 2 + par) * half);
+                X.peer_flag[d] = reinterpret_cast<unsigned long long*>(g.peer_block[d]) + (1 - d);
+            }
+            X.my_recv[d] = reinterpret_cast<const int4*>(g.p2p_block + 256 + ((size_t)d * 2 + par) * half);
+            X.my_flag[d] = reinterpret_cast<unsigned long long*>(g.p2p_block) + d;
+        }
+        X.epoch = g.epoch;
+        X.block_counter = g.d_block_counter;
+        *launches += launch_mg_push(P, X, s);
+        *launches += launch_mg_pull(P, X, s);
+        return DEM_OK;
+    }
     for (int d = 0; d < 2; d++) *launches += launch_mg_pack(P, g.d_send_gid[d], g.n_send[d], g.d_sendbuf[d], s);
     NC(g_nccl.GroupStart());
     for (int d = 0; d < 2; d++) {
@@ -685,7 +716,10 @@ int dem_ctx_destroy(DemCtx* ctx) {
     if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
     {
         MgState& g = ctx->mg;
-        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_counts); dfree(g.d_allcounts);
+        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
+        for (int d = 0; d < 2; d++)
+            if (g.peer_block[d]) cudaIpcCloseMemHandle(g.peer_block[d]);
+        if (g.p2p_block) cudaFree(g.p2p_block);
         for (int d = 0; d < 2; d++) {
             dfree(g.d_send_gid[d]); dfree(g.d_recv_gid[d]);
             if (g.d_sendbuf[d]) cudaFree(g.d_sendbuf[d]);
@@ -1378,6 +1412,57 @@ int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]
         flag[o] = (x >= g.cut_lo && x < g.cut_hi) ? 1 : 0;
     }
     CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
+    // ---- peer-memory exchange: map the neighbours' receive blocks (falls back to ncclSend/ncclRecv if that fails) ----
+    {
+        const size_t block_bytes = 256 + 4 * (size_t)g.cap * 80;
+        CK(cudaMalloc((void**)&g.p2p_block, block_bytes));
+        CK(cudaMemset(g.p2p_block, 0, block_bytes));
+        ctx->device_bytes += block_bytes;
+        if ((rc = dalloc(ctx, &g.d_block_counter, 4))) return rc;
+        CK(cudaMemset(g.d_block_counter, 0, 16));
+        cudaIpcMemHandle_t mine;
+        bool ok = cudaIpcGetMemHandle(&mine, g.p2p_block) == cudaSuccess;
+        if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+        // all-gather {handle, ok} over the communicator we already have
+        const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
+        std::vector<char> h_all(rec * world), h_me(rec, 0);
+        memcpy(h_me.data(), &mine, sizeof(mine));
+        h_me[sizeof(mine)] = ok ? 1 : 0;
+        char *d_me = nullptr, *d_all = nullptr;
+        CK(cudaMalloc((void**)&d_me, rec));
+        CK(cudaMalloc((void**)&d_all, rec * world));
+        CK(cudaMemcpy(d_me, h_me.data(), rec, cudaMemcpyHostToDevice));
+        NC(g_nccl.AllGather(d_me, d_all, rec, ncclUint8, g.comm, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpy(h_all.data(), d_all, rec * world, cudaMemcpyDeviceToHost));
+        cudaFree(d_me); cudaFree(d_all);
+        bool all_ok = getenv("DEM_B200_NO_P2P") == nullptr;
+        for (int r = 0; r < world; r++) all_ok = all_ok && h_all[rec * r + sizeof(mine)] == 1;
+        for (int d = 0; d < 2 && all_ok; d++) {
+            const int peer = rank + (d == 0 ? -1 : 1);
+            if (peer < 0 || peer >= world) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, h_all.data() + rec * peer, sizeof(h));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                all_ok = false;
+            }
+            g.peer_block[d] = (char*)ptr;
+        }
+        // every rank must take the same path: agree on the verdict
+        int* d_ok = nullptr;
+        CK(cudaMalloc((void**)&d_ok, sizeof(int)));
+        const int mine_ok = all_ok ? 1 : 0;
+        CK(cudaMemcpy(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
+        NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, g.comm, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        int verdict = 0;
+        CK(cudaMemcpy(&verdict, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+        cudaFree(d_ok);
+        g.p2p = verdict == 1;
+        g.epoch = 0;
+    }
     if (ctx->sort_mode != 1) ctx->sort_mode = 1;  // the radix path has no notion of inactive spheres
     g.on = true;
     ctx->need_rebuild = true;
@@ -1389,7 +1474,7 @@ int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]) {
     if (!ctx || !out) return DEM_ERR_INVALID;
     const MgState& g = ctx->mg;
     out[0] = g.n_own; out[1] = g.n_active; out[2] = g.n_send[0]; out[3] = g.n_send[1]; out[4] = g.halo_bytes;
-    out[5] = g.on ? (uint64_t)g.world : 1;
+    out[5] = (g.on ? (uint64_t)g.world : 1) | (g.p2p ? (1ull << 32) : 0ull);  // bit 32: peer-memory exchange in use
     return DEM_OK;
 }
 

@@ -73,6 +73,22 @@ int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* bu
 int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s);
 int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s);
 
+// per-step halo exchange through peer memory (NVLink stores into the neighbour's receive buffer + a flag)
+struct MgP2P {
+    const uint32_t* send_gid[2];   // my halo owners for the left / right neighbour
+    const uint32_t* recv_gid[2];   // the owners the left / right neighbour sends me
+    uint32_t n_send[2], n_recv[2];
+    int4* peer_recv[2];            // where my records for the left / right neighbour go (in THEIR memory, this epoch's half)
+    unsigned long long* peer_flag[2];  // their "data of epoch e has arrived" word for my direction
+    const int4* my_recv[2];        // where the left / right neighbour's records arrive (my memory, this epoch's half)
+    unsigned long long* my_flag[2];
+    unsigned long long epoch;      // 1, 2, 3, ... one per exchange
+    uint32_t* block_counter;       // last-block detection of the push kernel
+    int has[2];                    // neighbour present on the left / right
+};
+int launch_mg_push(const DevParams& P, const MgP2P& X, cudaStream_t s);
+int launch_mg_pull(const DevParams& P, const MgP2P& X, cudaStream_t s);
+
 void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s);
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaStream_t s);

@@ -93,6 +93,84 @@ __global__ void __launch_bounds__(256) k_mg_active_list(const __grid_constant__ 
     warp_append(own, &M.counts[0]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Per-step exchange without a library call: every rank stores the {state, spin} records of its halo owners straight into
+// the neighbour's receive buffer over NVLink (peer memory mapped with cudaIpc*), then publishes the epoch number in the
+// neighbour's flag word; the neighbour's pull kernel waits for that word and scatters the records into its global
+// slots.  Receive buffers are double buffered by epoch parity: a rank can run at most one exchange ahead of its
+// neighbour (it cannot finish pull(e) before the neighbour has pushed epoch e), so the half written in epoch e+1 is
+// the one the neighbour finished reading in epoch e-1.
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__global__ void __launch_bounds__(256) k_mg_push(const __grid_constant__ DevParams P, const __grid_constant__ MgP2P X) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n0 = X.n_send[0] * 5u, n1 = X.n_send[1] * 5u;
+    if (t < n0 + n1) {
+        const int d = t < n0 ? 0 : 1;
+        const uint32_t u = d == 0 ? t : t - n0;
+        const uint32_t i = u / 5u, part = u - i * 5u;
+        const uint32_t g = X.send_gid[d][i];
+        const int4* src = (part < 4) ? reinterpret_cast<const int4*>(P.state + g) + part
+                                     : reinterpret_cast<const int4*>(P.spin + g);
+        X.peer_recv[d][(size_t)i * 5u + part] = *src;
+    }
+    // publish: all stores of this grid, then the flag (last block to arrive does it)
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(X.block_counter, 1u);
+        if (done == gridDim.x - 1) {
+            *X.block_counter = 0;
+            __threadfence_system();
+            if (X.has[0]) st_release_sys(X.peer_flag[0], X.epoch);
+            if (X.has[1]) st_release_sys(X.peer_flag[1], X.epoch);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevParams P, const __grid_constant__ MgP2P X) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        for (int d = 0; d < 2; d++) {
+            if (!X.has[d]) continue;
+            while (ld_acquire_sys(X.my_flag[d]) < X.epoch) {
+                if (clock64() - t0 > 20000000000ll) {  // ~10 s: the neighbour is gone; report instead of hanging
+                    atomicOr(&P.flags[0], 64u);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t n0 = X.n_recv[0] * 5u, n1 = X.n_recv[1] * 5u;
+    if (t >= n0 + n1) return;
+    const int d = t < n0 ? 0 : 1;
+    const uint32_t u = d == 0 ? t : t - n0;
+    const uint32_t i = u / 5u, part = u - i * 5u;
+    const uint32_t g = X.recv_gid[d][i];
+    int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + g) + part : reinterpret_cast<int4*>(P.spin + g);
+    *dst = __ldcg(&X.my_recv[d][(size_t)i * 5u + part]);  // written by the peer: never through this SM's L1
+}
+
+int launch_mg_push(const DevParams& P, const MgP2P& X, cudaStream_t s) {
+    const uint32_t n = (X.n_send[0] + X.n_send[1]) * 5u;
+    k_mg_push<<<(n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s>>>(P, X);
+    return 1;
+}
+int launch_mg_pull(const DevParams& P, const MgP2P& X, cudaStream_t s) {
+    const uint32_t n = (X.n_recv[0] + X.n_recv[1]) * 5u;
+    k_mg_pull<<<(n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s>>>(P, X);
+    return 1;
+}
+
 int launch_mg_classify(const DevParams& P, const MgParams& M, cudaStream_t s) {
     cudaMemsetAsync(M.counts, 0, sizeof(uint32_t) * 8, s);
     if (P.nOwners) k_mg_classify<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, M);

@@ -316,7 +316,10 @@ class Engine:
     def mgpu_info(self):
         out = np.zeros(6, "u8")
         self._ck(self.lib.dem_mgpu_info(self.ctx, _p(out)))
-        return dict(zip(["n_own", "n_active", "n_send_left", "n_send_right", "halo_bytes_per_step", "world"], out.tolist()))
+        d = dict(zip(["n_own", "n_active", "n_send_left", "n_send_right", "halo_bytes_per_step", "world"], out.tolist()))
+        d["peer_memory_exchange"] = bool(d["world"] >> 32)
+        d["world"] &= 0xffffffff
+        return d
 
     def set_option(self, name, value):
         self._ck(self.lib.dem_set_option(self.ctx, name.encode(), float(value)))

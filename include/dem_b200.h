@@ -209,7 +209,9 @@ int dem_reduce(DemCtx* ctx, int kind, double* out);
  * integrates the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step. */
 int dem_mgpu_unique_id(uint8_t out[128]);
 int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]);
-/* out: [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right [4] halo bytes sent per step [5] world */
+/* out: [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right [4] halo bytes sent per step
+ * [5] world size in the low 32 bits; bit 32 set when the per-step exchange goes through peer memory (NVLink stores +
+ * flags) instead of ncclSend/ncclRecv */
 int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]);
 /* the x-slab (LBF-relative) of `rank` out of `world` */
 int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, float* hi);

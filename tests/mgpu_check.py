@@ -104,6 +104,7 @@ def main():
     res = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(res, 0)
     if rank == 0:
+        print("exchange:", "NVLink peer stores + flags" if eng.mgpu_info()["peer_memory_exchange"] else "ncclSend/ncclRecv", flush=True)
         print("MGPU_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(res.item()) == 1 else 1)
