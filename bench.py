@@ -126,6 +126,50 @@ def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, bu
         "in clump count to the 1M-clump workload" % (f.nClumps, dims[0], dims[1], dims[2], done, settle_steps, cores)), done, dt
 
 
+def run_c5(args, rank, local_rank, world):
+    """BASELINE configs[4]: 5M monodisperse spheres, binning + sort only.  The spheres are pre-partitioned into x-slabs,
+    one per GPU; there is no exchange in steady state, so the ranks run independently (no data-path collective)."""
+    import torch
+    from pyapi import demb200, dist_util, scenes
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist_util.init("nccl", local_rank)
+    sc = scenes.config5_spheres(args.spheres, x_range=(rank / world, (rank + 1) / world))
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(local_rank)
+    eng.load_flat(f, contact_capacity=1024)
+    eng.profile_binning(max(args.warmup, 3))
+    if world > 1:
+        torch.distributed.barrier()
+    torch.cuda.synchronize()
+    reps = max(args.steps // 10, 10)
+    t = eng.profile_binning(reps)
+    (us,) = dist_util.max_over_ranks([t["total_us"]], device="cuda")
+    n_local = int(f.nSpheres)
+    n_total = int(dist_util.gather_counts([n_local], device="cuda").sum()) if world > 1 else n_local
+    if rank == 0:
+        peak, which = measured_peak()
+        algo = 96.0 * n_local  # SURVEY.md 8(d): 16 N position read + 8 N key/value write + 8 N (2p+1) sort traffic, p = 4
+        line = {"metric": "sphere-keys/s, binning + sort only (5M monodisperse spheres)", "value": n_total / (us * 1e-6),
+                "unit": "keys/s", "n_gpus": args.gpus, "steps": reps, "warmup": max(args.warmup, 3), "ms_per_step": us / 1000.0,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 keys (f64 position decode)",
+                "data": "synthetic",
+                "config": {"workload": "C5: %d spheres r=1mm uniform random at 50%% packing, binning + sort only" % n_total,
+                           "spheres_per_gpu": n_local, "cells": [int(v) for v in eng.stats().n_cells],
+                           "parallelism": "1 GPU" if world == 1 else "%d pre-partitioned x-slabs, no exchange" % world},
+                "kernel_us": t,
+                "roofline": {"bound": "hbm", "kernel": "keys + counting sort + gather", "achieved": algo / (us * 1e-6) / 1e9,
+                             "peak": peak, "unit": "GB/s", "frac": algo / (us * 1e-6) / 1e9 / peak, "traffic": None,
+                             "peak_source": which, "algorithmic_bytes_per_launch": algo},
+                "gpu_launches": int(eng.stats().kernel_launches)}
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -140,6 +184,9 @@ def main():
     ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
+                    help="c2: the headline bed (default); c5: 5M-sphere binning + sort stress case (BASELINE configs[4])")
+    ap.add_argument("--spheres", type=int, default=5000000, help="c5: total number of spheres")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -171,6 +218,9 @@ def main():
     import torch
     import torch.distributed as dist
     from pyapi import demb200, dist_util, scenes
+
+    if args.workload == "c5":
+        return run_c5(args, rank, local_rank, world)
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")

@@ -1496,6 +1496,41 @@ int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
     return rebuild(ctx, out_us);
 }
 
+int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]) {
+    if (!ctx || !ctx->initialized || !out_us || repeats == 0) return DEM_ERR_INVALID;
+    if (ctx->mg.on) return fail(ctx, DEM_ERR_INVALID, "dem_profile_binning: single-device contexts only (shard the spheres, one context per GPU)");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    double acc[3] = {0, 0, 0};
+    for (uint32_t r = 0; r < repeats; r++) {
+        DevParams P = make_params(ctx);
+        CdParams C = make_cd(ctx);
+        // scratch lists: the other buffers (the analytical list is emitted by the key pass)
+        P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]); P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
+        P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]); P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
+        CK(cudaEventRecord(ctx->ev[0], s));
+        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, 0, s);
+        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 1, s);
+        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 2, s);
+        CK(cudaEventRecord(ctx->ev[1], s));
+        int sorted_buf = -1;
+        if (ctx->sort_mode == 0) { launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf); ctx->last_sorted_buf = sorted_buf; }
+        launches += launch_cd_sweep(P, C, sorted_buf, s, nullptr, /*sort_only*/ true);
+        CK(cudaEventRecord(ctx->ev[2], s));
+        CK(cudaEventSynchronize(ctx->ev[2]));
+        ctx->launches += launches;
+        ctx->need_maxvel = false;
+        float ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); acc[0] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); acc[1] += ms;
+        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[2])); acc[2] += ms;
+    }
+    CK(cudaMemcpy(&ctx->last_grid, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 3; k++) out_us[k] = (float)(acc[k] * 1000.0 / repeats);
+    ctx->need_rebuild = true;  // the scratch of the real lists was reused
+    return DEM_OK;
+}
+
 int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uint64_t* n_out) {
     if (!ctx || !ctx->initialized || !what || !out || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));

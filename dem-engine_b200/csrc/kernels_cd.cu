@@ -842,7 +842,7 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, i
     return launches;
 }
 
-int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev) {
+int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev, bool sort_only) {
     int launches = 0;
     const uint32_t n = P.nSpheres;
     // cell histogram -> exclusive prefix (ncells+1 entries; scanning the full capacity keeps the launch shape static)
@@ -857,6 +857,7 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
             k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(P, C, C.vals[sorted_buf]);
         }
         if (ev) cudaEventRecord(ev[1], s);
+        if (sort_only) return launches + 1;
         k_sweep<<<(n + 127) / 128, 128, 0, s>>>(P, C, sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf]);
         launches += 2;
     } else if (ev) {

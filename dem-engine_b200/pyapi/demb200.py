@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "dem_abi_version", "dem_host_figure_out_nv", "dem_host_box_domain", "dem_host_encode_positions",
     "dem_ctx_create", "dem_ctx_destroy", "dem_last_error", "dem_set_stream", "dem_set_params",
     "dem_upload_templates", "dem_upload_materials", "dem_upload_analytical", "dem_upload_families",
-    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_initialize", "dem_set_contacts",
+    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
@@ -288,6 +288,11 @@ class Engine:
         out = C.c_double(0)
         self._ck(self.lib.dem_reduce(self.ctx, int(kind), C.byref(out)))
         return out.value
+
+    def profile_binning(self, repeats=10):
+        out = (C.c_float * 3)()
+        self._ck(self.lib.dem_profile_binning(self.ctx, int(repeats), out))
+        return {"keys_us": out[0], "sort_us": out[1], "total_us": out[2]}
 
     def debug_download(self, what, n=None):
         """Raw device scratch of the last rebuild / step (dem_debug_download)."""

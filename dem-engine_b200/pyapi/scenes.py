@@ -489,3 +489,25 @@ def config4_drum(n_clumps=500000, n_tri=50000, scale=0.004, h=5e-6, cd_update_fr
     s.cd_update_freq = cd_update_freq
     s.drum_radius, s.drum_length = radius, length
     return s
+
+
+def config5_spheres(n=5000000, r=0.001, packing=0.5, seed=11, x_range=None):
+    """C5: n monodisperse spheres (r = 1 mm) uniformly random in a cubic box at 50 % packing -- the neighbour-search
+    stress case (binning + sort only: the spheres overlap at random, no forces are evaluated).  `x_range=(a, b)` keeps
+    only the spheres whose x/box fraction lies in [a, b): the pre-partitioned share of one GPU."""
+    s = Scene()
+    mat = s.load_material(E=1e8, nu=0.3, CoR=0.6, mu=0.0, Crr=0.0)
+    t = s.load_sphere_type(2500.0 * 4.0 / 3.0 * math.pi * r ** 3, r, mat)
+    side = (n * 4.0 / 3.0 * math.pi * r ** 3 / packing) ** (1.0 / 3.0)
+    rng = np.random.RandomState(seed)
+    pts = (rng.uniform(-0.5, 0.5, (n, 3)) * side).astype("f4")
+    if x_range is not None:
+        frac = pts[:, 0] / side + 0.5
+        pts = pts[(frac >= x_range[0]) & (frac < x_range[1])]
+    s.add_clumps(t, pts)
+    s.box = (side * 1.02, side * 1.02, side * 1.02)
+    s.bounding = "none"
+    s.h, s.G = 2e-6, (0, 0, -9.81)
+    s.force_model = D.HERTZIAN_FRICTIONLESS
+    s.cd_update_freq = 20
+    return s

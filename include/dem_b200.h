@@ -237,6 +237,12 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]);
  * [6] unused [7] whole rebuild */
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]);
 
+/* Binning + sort only (the neighbour-search stress case): `repeats` times { margins, sphere world positions, cell keys,
+ * cell histogram ; sort into (cell, sphere id) order ; gather of the sorted sphere stream }, no sweep.  Mean device time
+ * in microseconds: [0] positions + keys + histogram [1] sort (+ gather) [2] both.  Leaves the sorted arrays behind for
+ * dem_debug_download. */
+int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]);
+
 /* Raw views of device scratch of the LAST rebuild / step, for tests and tools (synchronises).  `what`:
  *   "sphere_keys" u32[nSpheres]  cell key of each sphere (0xffffffff = not held by this rank)
  *   "sorted_keys" u32[nSpheres]  cell keys in sorted order      "sorted_ids" u32[nSpheres]  sphere ids in sorted order

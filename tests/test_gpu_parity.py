@@ -231,6 +231,41 @@ def test_drum_config4_full_size_properties(built):
     eng.close()
 
 
+def test_config5_binning_and_sort_bit_exact(built):
+    """BASELINE config 5 (5M random spheres, binning + sort only): integer work, compared bit for bit with numpy --
+    cell keys from the sphere positions, and the sorted order == a stable sort by (cell key, sphere id)."""
+    n = 5000000
+    f = scenes.flatten(scenes.config5_spheres(n))
+    eng = demb200.Engine(0)
+    eng.load_flat(f, contact_capacity=1024)   # no contact list is built
+    for mode in (1, 0):                        # counting sort, LSD radix sort: same order
+        eng.set_option("sort_mode", mode)
+        t = eng.profile_binning(3)
+        assert t["total_us"] > 0
+        st = eng.stats()
+        pos = eng.debug_download("sphere_pos").reshape(-1, 4)
+        keys = eng.debug_download("sphere_keys")
+        skeys = eng.debug_download("sorted_keys")
+        sids = eng.debug_download("sorted_ids")
+        assert len(keys) == n == len(skeys) == len(sids)
+        # positions: decode of the fixed-point code (double), cast to float
+        vx = (f.voxelID[:n] & np.uint64((1 << f.nvXp2) - 1)).astype("f8")
+        x = (vx * f.voxelSize + f.locX[:n].astype("f8") * f.l).astype("f4")
+        assert np.array_equal(pos[:, 0], x)
+        # keys: floor(pos * (1/cs)) per axis in float, clamped, linearised
+        inv = np.float32(1.0) / np.float32(st.cell_size)
+        nb = [int(v) for v in st.n_cells]
+        c = [np.clip(np.floor(pos[:, k] * inv).astype("i8"), 0, nb[k] - 1) for k in range(3)]
+        ref_keys = (c[0] + nb[0] * (c[1] + nb[1] * c[2])).astype("u4")
+        if mode == 1:  # (the radix passes ping-pong through the key buffer: only the counting sort leaves it intact)
+            assert np.array_equal(keys, ref_keys)
+        # sorted order: stable sort by key (ties by sphere id)
+        order = np.argsort(ref_keys, kind="stable").astype("u4")
+        assert np.array_equal(sids, order)
+        assert np.array_equal(skeys, ref_keys[order])
+    eng.close()
+
+
 def test_empty_and_single_body_worlds(built):
     # no clumps at all
     sc = scenes.Scene()
