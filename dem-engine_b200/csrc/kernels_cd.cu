@@ -693,11 +693,13 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
     uint32_t acc[SWEEP_MAXC];  // staged candidates: sorted index, bit 31 = spheres overlap right now
     uint32_t count = 0, countT = 0;
     uint4 meta = make_uint4(0, 0, 0, 0);
+    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+    float myMargin = 0.f;
     if (valid) {
         const GridInfo g = *C.grid;
-        const float4 me = C.sortedSph[j];
+        me = C.sortedSph[j];
         meta = C.sortedMeta[j];
-        const float myMargin = me.w - __ldg(&P.comp[meta.z & 0xffffu]).w;
+        myMargin = me.w - __ldg(&P.comp[meta.z & 0xffffu]).w;
         const uint32_t key = keys[j];
         const int cx = (int)(key % g.nbx);
         const int cy = (int)((key / g.nbx) % g.nby);
@@ -705,44 +707,75 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
         const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
         const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
         const float extraA = fam_on ? P.familyExtraMargin[meta.w] : 0.f;
-#pragma unroll 1
+        // ---- the five runs of the half stencil: all ten bounds are fetched before any of them is used ----
+        uint32_t qb[5], qe[5];
+#pragma unroll
         for (int r = 0; r < 5; r++) {
             // r=0: own row behind me; r=1: (dy=+1,dz=0); r=2..4: (dy=-1,0,+1; dz=+1)
             const int dy = (r == 0) ? 0 : (r == 1 ? 1 : r - 3);
             const int dz = (r < 2) ? 0 : 1;
             const int y = cy + dy, z = cz + dz;
-            if (y < 0 || y >= (int)g.nby || z >= (int)g.nbz) continue;
-            const uint32_t row = g.nbx * ((uint32_t)y + g.nby * (uint32_t)z);
-            const uint32_t qb = (r == 0) ? j + 1 : C.cellStart[row + x0];
-            const uint32_t qe = C.cellStart[row + x1 + 1];
-            for (uint32_t q = qb; q < qe; q++) {
-                const float4 ot = __ldg(&C.sortedSph[q]);
-                const float dx = me.x - ot.x, dy2 = me.y - ot.y, dz2 = me.z - ot.z;
-                const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
-                const float R = me.w + ot.w;
-                // superset of the double-precision test d2 <= R^2 && R - d > min(extraA, extraB)
-                if (d2 > R * R * 1.000001f + 1e-20f) continue;
-                const uint4 om = __ldg(&C.sortedMeta[q]);
-                if (om.x == meta.x) continue;  // same owner
-                if (fam_on) {
-                    if (C.any_mask && P.familyMasks[mask_pair(meta.w, om.w)] != 0) continue;
-                    const float Rt = R - fminf(extraA, P.familyExtraMargin[om.w]);
-                    if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
+            const bool ok = !(y < 0 || y >= (int)g.nby || z >= (int)g.nbz);
+            const uint32_t row = ok ? g.nbx * ((uint32_t)y + g.nby * (uint32_t)z) : 0u;
+            qb[r] = (r == 0) ? j + 1 : (ok ? __ldg(&C.cellStart[row + x0]) : 0u);
+            qe[r] = ok ? __ldg(&C.cellStart[row + x1 + 1]) : 0u;
+        }
+        // ---- distance test, four candidates in flight at a time (independent 16-byte loads of the sorted stream) ----
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            for (uint32_t q = qb[r]; q < qe[r]; q += 4) {
+                float4 ot[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) ot[u] = __ldg(&C.sortedSph[min(q + u, qe[r] - 1u)]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (q + u >= qe[r]) break;
+                    const float dx = me.x - ot[u].x, dy2 = me.y - ot[u].y, dz2 = me.z - ot[u].z;
+                    const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                    const float R = me.w + ot[u].w;
+                    // superset of the double-precision test d2 <= R^2 && R - d > min(extraA, extraB)
+                    if (d2 > R * R * 1.000001f + 1e-20f) continue;
+                    if (count < SWEEP_MAXC) acc[count] = q + u;
+                    count++;
                 }
-                // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
-                const float Rtrue = R - myMargin - (ot.w - __ldg(&P.comp[om.z & 0xffffu]).w);
-                const uint32_t touching = (d2 < Rtrue * Rtrue) ? 0x80000000u : 0u;
-                if (count < SWEEP_MAXC) acc[count] = q | touching;
-                count++;
-                countT += touching >> 31;
             }
         }
         if (count > SWEEP_MAXC) {
-            atomicOr(&P.flags[2], 1u);  // more forward contacts on one sphere than can be staged
+            atomicOr(&P.flags[2], 1u);  // more neighbours within reach of one sphere than can be staged
             count = SWEEP_MAXC;
-            countT = 0;
-            for (uint32_t k = 0; k < count; k++) countT += acc[k] >> 31;
         }
+        // ---- owner / family filter and "in touch right now?" on the staged few (their records, four at a time) ----
+        uint32_t kept = 0;
+        for (uint32_t k0 = 0; k0 < count; k0 += 4) {
+            uint4 om[4];
+            float4 ot[4];
+            uint32_t qq[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                qq[u] = acc[min(k0 + u, count - 1u)];
+                om[u] = __ldg(&C.sortedMeta[qq[u]]);
+                ot[u] = __ldg(&C.sortedSph[qq[u]]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (k0 + u >= count) break;
+                if (om[u].x == meta.x) continue;  // same owner
+                const float dx = me.x - ot[u].x, dy2 = me.y - ot[u].y, dz2 = me.z - ot[u].z;
+                const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
+                const float R = me.w + ot[u].w;
+                if (fam_on) {
+                    if (C.any_mask && P.familyMasks[mask_pair(meta.w, om[u].w)] != 0) continue;
+                    const float Rt = R - fminf(extraA, P.familyExtraMargin[om[u].w]);
+                    if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
+                }
+                // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
+                const float Rtrue = R - myMargin - (ot[u].w - __ldg(&P.comp[om[u].z & 0xffffu]).w);
+                const uint32_t touching = (d2 < Rtrue * Rtrue) ? 0x80000000u : 0u;
+                acc[kept++] = qq[u] | touching;  // (kept <= k0 + u: never overtakes the read position)
+                countT += touching >> 31;
+            }
+        }
+        count = kept;
     }
     const uint32_t countN = count - countT;
     uint32_t slotT = warp_claim(countT, P.ss.count);
@@ -767,6 +800,17 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t alive = 0;
         bool found = false;
+        if (!touching) {
+            // A candidate that is clearly apart at these very positions (float positions: allow for their rounding)
+            // would have its history destroyed by the force pass that follows this rebuild (no overlap => wildcards
+            // zeroed, DEMCalcForceKernels.cu:258-261): it carries none over, so there is nothing to look up or write.
+            const float4 ot = __ldg(&C.sortedSph[acc[k] & 0x7fffffffu]);
+            const float dx = me.x - ot.x, dy = me.y - ot.y, dz = me.z - ot.z;
+            const float Rtrue = (me.w - myMargin) + __ldg(&P.comp[om.z & 0xffffu]).w;
+            const float slack = 3e-7f * (fabsf(me.x) + fabsf(me.y) + fabsf(me.z)) + 1e-8f;
+            found = sqrtf(dx * dx + dy * dy + dz * dz) * 0.999999f - Rtrue * 1.000001f - slack > 0.f;
+        }
+        const bool no_history = found;
 #pragma unroll 1
         for (int pass = 0; pass < 4 && !found; pass++) {
             const ContactList& O = ((pass & 1) == (touching ? 0 : 1)) ? C.oldss : C.oldsn;  // likelier list first
@@ -788,7 +832,7 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
         const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
         L.pair[slot] = make_uint2(meta.y, om.y);
         L.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | alive);
-        if (L.hist) L.hist[slot] = h;
+        if (L.hist && !no_history) L.hist[slot] = h;  // (a contact that is not alive never has its history word read)
     }
 }
 
