@@ -184,6 +184,8 @@ def main():
     ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--profile-window", action="store_true",
+                    help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
                     help="c2: the headline bed (default); c5: 5M-sphere binning + sort stress case (BASELINE configs[4])")
     ap.add_argument("--spheres", type=int, default=5000000, help="c5: total number of spheres")
@@ -252,10 +254,14 @@ def main():
         sampler = ClockSampler(local_rank)
         sampler.start()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if args.profile_window:
+            torch.cuda.profiler.start()
         ev0.record(stream)
         eng.step_async(args.steps)
         ev1.record(stream)
         barrier()
+        if args.profile_window:
+            torch.cuda.profiler.stop()
         sampler.stop_flag = True
         ms = ev0.elapsed_time(ev1)
         launches = eng.stats().kernel_launches - launches0
