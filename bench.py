@@ -45,37 +45,73 @@ def build_scene(n_clumps, cd_update_freq, spacing):
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock / throttle reasons during the timed region through NVML (a query takes ~0.1 ms, so even a
+    timed region of a few tens of milliseconds is sampled many times); falls back to polling nvidia-smi."""
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_s=0.002):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.period, self.samples, self.stop_flag = index, period_s, [], False
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = index
+            try:
+                ids = [int(x) for x in vis.split(",") if x.strip() != ""]
+                if ids and index < len(ids):
+                    phys = ids[index]
+            except ValueError:
+                pass
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+        except Exception:
+            self.nv = None
+
+    def _sample_nvml(self):
+        nv = self.nv
+        sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+            r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        reasons = []
+        for name, bit in (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown),
+                          ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown),
+                          ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap)):
+            if r & bit:
+                reasons.append(name)
+        return sm, reasons
+
+    def _sample_smi(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                             capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        self.sm_max = float(parts[1])
+        reasons = [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[2:6]) if v.lower().startswith("active")]
+        return float(parts[0]), reasons
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [x.strip() for x in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self.samples.append(self._sample_nvml() if self.nv else self._sample_smi())
             except Exception:
                 pass
-            time.sleep(0.1)
+            time.sleep(self.period)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": sorted(reasons),
-                "samples": len(sm)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[1]})
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": getattr(self, "sm_max", None), "reasons": reasons,
+                "samples": len(sm), "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def measured_peak():
@@ -173,7 +209,7 @@ def run_c5(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=40)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--clumps", type=int, default=1000000)
@@ -183,7 +219,7 @@ def main():
     ap.add_argument("--spacing", type=float, default=2.7, help="initial lattice spacing in units of the clump scale")
     ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--profile-window", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],

@@ -182,6 +182,7 @@ struct DemCtx {
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
     int ctas_per_sm = 4;
+    int fast_math = 1;  // sphere--sphere force kernel: MUFU reciprocal / rsqrt instead of IEEE division / sqrt
     int fast_encode = 1;
     int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
@@ -586,7 +587,7 @@ int enqueue_step(DemCtx* ctx) {
         if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, ws);
         CK(cudaEventRecord(ctx->ev_join, ws));
     }
-    launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->stream);
+    launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->fast_math != 0, ctx->stream);
     if (ws == ctx->stream) {
         if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, ws);
         if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, ws);
@@ -701,6 +702,7 @@ int dem_ctx_create(DemCtx** out, int device) {
     ctx->num_sms = prop.multiProcessorCount;
     cudaHostAlloc((void**)&ctx->h_pinned, 256 * sizeof(uint32_t), cudaHostAllocDefault);
     if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
+    if (const char* e = getenv("DEMB_FAST_MATH")) ctx->fast_math = atoi(e);
     for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
@@ -1482,6 +1484,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     if (!ctx || !name) return DEM_ERR_INVALID;
     const std::string n(name);
     if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
+    else if (n == "fast_math") ctx->fast_math = value != 0.0;
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
     else if (n == "sort_mode") ctx->sort_mode = (int)value;
@@ -1570,7 +1573,7 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
         }
         CK(cudaEventRecord(ctx->ev[1], s));
         DevParams P = make_params(ctx);
-        launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, s);
+        launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->fast_math != 0, s);
         CK(cudaEventRecord(ctx->ev[2], s));
         if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
         if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);

@@ -89,7 +89,7 @@ struct MgP2P {
 int launch_mg_push(const DevParams& P, const MgP2P& X, cudaStream_t s);
 int launch_mg_pull(const DevParams& P, const MgP2P& X, cudaStream_t s);
 
-void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s);
+void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, bool fast, cudaStream_t s);
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaStream_t s);

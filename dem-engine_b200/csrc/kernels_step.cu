@@ -47,10 +47,21 @@ __device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, ui
     e.ww = f3(w0, w1, w2);
 }
 
+// Division / square root of the force model.  FAST = one MUFU (reciprocal / reciprocal square root, 1 ulp) and a
+// multiply instead of the IEEE-rounded sequences (8-12 instructions and a branch each): -100 of ~1100 SASS
+// instructions, -3 % kernel time; the difference (<= 2 ulp of a force term) is far inside the fp32 parity tolerance
+// (tests/test_gpu_parity.py runs both).  FAST = false reproduces the reference's correctly rounded operators.
+template <bool FAST>
+__device__ __forceinline__ float fdiv(float a, float b) { return FAST ? __fdividef(a, b) : a / b; }
+template <bool FAST>
+__device__ __forceinline__ float fsqrt(float a) { return FAST ? a * rsqrtf(fmaxf(a, 1e-37f)) : sqrtf(a); }
+template <bool FAST>
+__device__ __forceinline__ float flength(float3 a) { return fsqrt<FAST>(dot(a, a)); }
+
 // Hertz-Mindlin with history (MODEL 0) or frictionless Hertz (MODEL 1).
 //   depth > 0, n = unit normal B->A, armA/armB = contact point minus owner position (world frame).
 // Returns force on A (world) and the torque-only rolling-resistance pseudo force.
-template <int MODEL>
+template <int MODEL, bool FAST = false>
 __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float depth, float3 n, float3 armA,
                                               float3 armB, const End& A, const End& B, float rA, float rB,
                                               float4& hist, float3& force, float3& troll) {
@@ -59,11 +70,11 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
     const float3 rotVelCPB = cross(B.ww, armB);
     const float3 velB2A = (A.v + rotVelCPA) - (B.v + rotVelCPB);
     const float projection = dot(velB2A, n);
-    const float mass_eff = (A.mass * B.mass) / (A.mass + B.mass);
-    const float sqrt_Rd = sqrtf(depth * ((rA * rB) / (rA + rB)));
+    const float mass_eff = fdiv<FAST>(A.mass * B.mass, A.mass + B.mass);
+    const float sqrt_Rd = fsqrt<FAST>(depth * fdiv<FAST>(rA * rB, rA + rB));
     const float Sn = 2.f * mp.E_cnt * sqrt_Rd;
     const float k_n = 0.6666666666666666f * Sn;
-    const float gamma_n = 1.825741858350554f * mp.beta * sqrtf(Sn * mass_eff);
+    const float gamma_n = 1.825741858350554f * mp.beta * fsqrt<FAST>(Sn * mass_eff);
     force = (k_n * depth + gamma_n * projection) * n;
     troll = f3(0.f, 0.f, 0.f);
     if (MODEL == 0) {
@@ -90,14 +101,14 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
         }
         if (mp.mu > 0.f) {
             const float kt = 8.f * mp.G_cnt * sqrt_Rd;
-            const float gt = -1.825741858350554f * mp.beta * sqrtf(mass_eff * kt);
+            const float gt = -1.825741858350554f * mp.beta * fsqrt<FAST>(mass_eff * kt);
             float3 tf = (-kt) * delta_tan - gt * vrel_tan;
-            const float ft = length(tf);
+            const float ft = flength<FAST>(tf);
             if (ft > 1e-12f) {
-                const float ft_max = length(force) * mp.mu;
+                const float ft_max = flength<FAST>(force) * mp.mu;
                 if (ft > ft_max) {
-                    tf = (ft_max / ft) * tf;
-                    delta_tan = (tf + gt * vrel_tan) * (1.f / (-kt));
+                    tf = fdiv<FAST>(ft_max, ft) * tf;
+                    delta_tan = (tf + gt * vrel_tan) * fdiv<FAST>(1.f, -kt);
                 }
             } else {
                 tf = f3(0.f, 0.f, 0.f);
@@ -112,7 +123,7 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
 // sphere--sphere contacts.  One thread per contact over the virtual concatenation of the two sphere--sphere lists
 // (contacts in touch at the last rebuild first, mere candidates after them: warps are then homogeneous and the
 // candidates' warps skip the force model).  Counts are DEVICE-resident (no host sync).
-template <int MODEL, bool RECORD, int MINB>
+template <int MODEL, bool RECORD, int MINB, bool FAST>
 __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
     const uint32_t nT = *P.ss.count;
     const uint32_t n = nT + *P.sn.count;
@@ -155,19 +166,21 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
         const float rA = compA.w, rB = compB.w;
         const double R = (double)rA + (double)rB;
         float3 nrm = f3((float)dx, (float)dy, (float)dz);
-        const float mag = sqrtf(dot(nrm, nrm));
+        const float mag2 = dot(nrm, nrm);
+        const float imag = FAST ? rsqrtf(fmaxf(mag2, 1e-37f)) : 0.f;
+        const float mag = FAST ? mag2 * imag : sqrtf(mag2);
         // overlap = R - |d| = (R^2 - d^2) / (R + |d|): numerator in double, the rest in float
-        const float depth = (float)(R * R - d2) / ((float)R + mag);
+        const float depth = fdiv<FAST>((float)(R * R - d2), (float)R + mag);
 
         if (depth > 0.f) {
-            nrm = nrm * (1.f / mag);
+            nrm = nrm * (FAST ? imag : 1.f / mag);
             // contact point = centre(B) + (rB - depth/2) n ; lever arms from each owner (world frame)
             const float s = rB - 0.5f * depth;
             const float3 armB = relB + s * nrm;
             const float3 armA = f3(relA.x - (float)dx, relA.y - (float)dy, relA.z - (float)dz) + s * nrm;
             const MatPair mp = P.matpair[ci.w & 0xffffu];
             float3 force, troll;
-            contact_model<MODEL>(mp, P.h, depth, nrm, armA, armB, A, B, rA, rB, hist, force, troll);
+            contact_model<MODEL, FAST>(mp, P.h, depth, nrm, armA, armB, A, B, rA, rB, hist, force, troll);
             // wrench scatter (forceToAcc semantics; force and WORLD-frame torque sums, divided by mass / rotated and
             // divided by MOI once per owner in the integrator)
             const float3 Ft = force + troll;
@@ -667,22 +680,28 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int MINB>
+template <int MINB, bool FAST>
 static void launch_force_ss_t(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {
     const int block = 256;
     if (model == DEM_HERTZIAN) {
-        if (record) k_force_ss<0, true, MINB><<<grid, block, 0, s>>>(P); else k_force_ss<0, false, MINB><<<grid, block, 0, s>>>(P);
+        if (record) k_force_ss<0, true, MINB, FAST><<<grid, block, 0, s>>>(P); else k_force_ss<0, false, MINB, FAST><<<grid, block, 0, s>>>(P);
     } else {
-        if (record) k_force_ss<1, true, MINB><<<grid, block, 0, s>>>(P); else k_force_ss<1, false, MINB><<<grid, block, 0, s>>>(P);
+        if (record) k_force_ss<1, true, MINB, FAST><<<grid, block, 0, s>>>(P); else k_force_ss<1, false, MINB, FAST><<<grid, block, 0, s>>>(P);
     }
 }
 
 // ctas_per_sm CTAs per SM (2, 3 or 4 -- selects the register budget the kernel was compiled for)
-void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, cudaStream_t s) {
+void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, int ctas_per_sm, bool fast, cudaStream_t s) {
     const int grid = num_sms * ctas_per_sm;
-    if (ctas_per_sm >= 4) launch_force_ss_t<4>(P, model, record, grid, s);
-    else if (ctas_per_sm == 3) launch_force_ss_t<3>(P, model, record, grid, s);
-    else launch_force_ss_t<2>(P, model, record, grid, s);
+    if (fast) {
+        if (ctas_per_sm >= 4) launch_force_ss_t<4, true>(P, model, record, grid, s);
+        else if (ctas_per_sm == 3) launch_force_ss_t<3, true>(P, model, record, grid, s);
+        else launch_force_ss_t<2, true>(P, model, record, grid, s);
+    } else {
+        if (ctas_per_sm >= 4) launch_force_ss_t<4, false>(P, model, record, grid, s);
+        else if (ctas_per_sm == 3) launch_force_ss_t<3, false>(P, model, record, grid, s);
+        else launch_force_ss_t<2, false>(P, model, record, grid, s);
+    }
 }
 
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {

@@ -94,10 +94,13 @@ def test_trajectory_matches_oracle(built, kind):
     eng.close()
 
 
+@pytest.mark.parametrize("fast_math", [1, 0])
 @pytest.mark.parametrize("kind", ["clumps_full", "spheres_frictionless", "cylinder", "mesh_tray"])
-def test_single_step_from_identical_state(built, kind):
+def test_single_step_from_identical_state(built, kind, fast_math):
     """Advance the oracle into a contact-rich state, load that exact state (positions codes, velocities AND contact
-    history) into the device, then compare ONE step: no chaotic growth, so tolerances are at fp32 rounding level."""
+    history) into the device, then compare ONE step: no chaotic growth, so tolerances are at fp32 rounding level.
+    Both arithmetic modes of the sphere--sphere force kernel (fast_math = 1: MUFU reciprocal / rsqrt, the default;
+    0: IEEE division / sqrt as the reference compiles them) must meet the same tolerance."""
     po = _oracle()
     f = scenes.flatten(_mk(kind))
     w = po.world_from_flat(f)
@@ -107,6 +110,7 @@ def test_single_step_from_identical_state(built, kind):
                  "omgBarY", "omgBarZ"):
         getattr(f, name)[: f.nOwners] = getattr(w, name)[: f.nOwners]
     eng = demb200.Engine(0)
+    eng.set_option("fast_math", fast_math)
     eng.load_flat(f)
     n = w.nContacts
     wc = np.stack([c[:n] for c in w.contactWildcards], 1)
@@ -118,7 +122,7 @@ def test_single_step_from_identical_state(built, kind):
     vw = np.stack([w.vX, w.vY, w.vZ], 1)[:nC]
     ow = np.stack([w.omgBarX, w.omgBarY, w.omgBarZ], 1)[:nC]
     vtol = 2e-5 * np.abs(vw).max() + 1e-7
-    print("%s single step: |dv| %.3e (tol %.3e), max|v| %.3f" % (kind, np.abs(st["vel"][:nC] - vw).max(), vtol, np.abs(vw).max()))
+    print("%s fast_math=%d single step: |dv| %.3e (tol %.3e), max|v| %.3f" % (kind, fast_math, np.abs(st["vel"][:nC] - vw).max(), vtol, np.abs(vw).max()))
     assert np.abs(st["vel"][:nC] - vw).max() <= vtol, (np.abs(st["vel"][:nC] - vw).max(), vtol)
     otol = 2e-5 * max(np.abs(ow).max(), 1.0) + 1e-6
     assert np.abs(st["omg"][:nC] - ow).max() <= otol, (np.abs(st["omg"][:nC] - ow).max(), otol)
