@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
     """Samples SM clock / throttle reasons during the timed region through NVML (a query takes ~0.1 ms, so even a
     timed region of a few tens of milliseconds is sampled many times); falls back to polling nvidia-smi."""
 
-    def __init__(self, index=0, period_s=0.002):
+    def __init__(self, index=0, period_s=0.01):
         super().__init__(daemon=True)
         self.index, self.period, self.samples, self.stop_flag = index, period_s, [], False
         self.nv = None
@@ -100,18 +100,29 @@ class ClockSampler(threading.Thread):
     def run(self):
         while not self.stop_flag:
             try:
-                self.samples.append(self._sample_nvml() if self.nv else self._sample_smi())
+                sm, reasons = self._sample_nvml() if self.nv else self._sample_smi()
+                self.samples.append((sm, reasons, time.perf_counter()))
             except Exception:
                 pass
             time.sleep(self.period)
 
-    def summary(self):
+    def summary(self, t0=None, t1=None):
+        """Median SM clock and throttle reasons over the samples taken inside [t0, t1] (the timed region); when that
+        region was too short to hold three samples, over everything sampled under the same load (timed region + the
+        per-kernel timing pass that follows it on the same state), and says so."""
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
-        sm = sorted(s[0] for s in self.samples)
-        reasons = sorted({r for s in self.samples for r in s[1]})
+        window, use = "timed region", self.samples
+        if t0 is not None:
+            inside = [s for s in self.samples if t0 <= s[2] <= t1]
+            if len(inside) >= 3:
+                use = inside
+            else:
+                window = "timed region + per-kernel timing pass (timed region shorter than 3 samples)"
+        sm = sorted(s[0] for s in use)
+        reasons = sorted({r for s in use for r in s[1]})
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": getattr(self, "sm_max", None), "reasons": reasons,
-                "samples": len(sm), "source": "nvml" if self.nv else "nvidia-smi"}
+                "samples": len(sm), "window": window, "source": "nvml" if self.nv else "nvidia-smi"}
 
 
 def measured_peak():
@@ -220,6 +231,7 @@ def main():
     ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--clock-period", type=float, default=0.01, help="seconds between NVML clock samples")
     ap.add_argument("--profile-window", action="store_true",
                     help="bracket the timed steps with cudaProfilerStart/Stop (for `ncu --profile-from-start off`)")
     ap.add_argument("--workload", default="c2", choices=["c2", "c5"],
@@ -287,8 +299,9 @@ def main():
         eng.step(args.warmup)
         barrier()
         launches0 = eng.stats().kernel_launches
-        sampler = ClockSampler(local_rank)
+        sampler = ClockSampler(local_rank, args.clock_period)
         sampler.start()
+        t_timed0 = time.perf_counter()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if args.profile_window:
             torch.cuda.profiler.start()
@@ -296,14 +309,15 @@ def main():
         eng.step_async(args.steps)
         ev1.record(stream)
         barrier()
+        t_timed1 = time.perf_counter()
         if args.profile_window:
             torch.cuda.profiler.stop()
-        sampler.stop_flag = True
         ms = ev0.elapsed_time(ev1)
         launches = eng.stats().kernel_launches - launches0
         st = eng.stats()
         # per-kernel device times (CUDA events on the launching stream), same state, right after the timed region
         prof = eng.profile_steps(min(args.steps, 200))
+        sampler.stop_flag = True
 
         # ---- e2e: through the public C-ABI calls with HOST buffers; every step uploads the step's host-side inputs
         # (simulation parameters + the family prescription / mask tables a co-simulating caller updates) and reads the
@@ -360,7 +374,7 @@ def main():
         "e2e": {"value": args.e2e_steps / (e2e_ms / 1000.0), "unit": unit, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": args.e2e_steps},
         "gpu_launches": int(launches),
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary(t_timed0, t_timed1),
     }
     if not args.no_cpu_baseline and world == 1:
         rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, 400, args.cd_update_freq, args.spacing,

@@ -64,6 +64,9 @@ struct MgState {
     float cut_lo = 0.f, cut_hi = 0.f;
     uint8_t* d_flag = nullptr;
     uint32_t* d_active_list = nullptr;
+    uint32_t* d_act_sph = nullptr;     // spheres of the active owners (the rebuild walks these only)
+    uint32_t n_act_sph = 0;
+    uint32_t grid_cells = 0;           // cells of this rank's table at the current rebuild (0 = not known yet)
     uint32_t* d_counts = nullptr;      // 8 words
     uint32_t* d_allcounts = nullptr;   // world x 8 words
     uint32_t* d_send_gid[2] = {nullptr, nullptr};
@@ -310,6 +313,12 @@ CdParams make_cd(const DemCtx* c) {
     C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedMeta = c->d_sortedMeta;
     C.analw = c->d_analw;
     C.sortedPos = c->d_sortedPos;
+    C.scan_cells = c->max_cells + 1;
+    if (c->mg.on) {
+        C.slab_on = 1; C.slab_lo = c->mg.cut_lo; C.slab_hi = c->mg.cut_hi;
+        C.act_sph = c->mg.d_act_sph; C.nActSph = c->mg.n_act_sph;
+        if (c->mg.grid_cells) C.scan_cells = std::min(c->mg.grid_cells, c->max_cells) + 1;
+    }
     C.oldss = as_list(c->lists[0][c->cur]);
     C.oldsn = as_list(c->lists[1][c->cur]);
     C.oldsa = as_list(c->lists[2][c->cur]);
@@ -362,6 +371,7 @@ MgParams make_mg(const DemCtx* c) {
     M.send_cap = g.cap; M.nClumpOwners = c->nClumpOwners;
     M.cut_lo = g.cut_lo; M.cut_hi = g.cut_hi; M.grid = c->d_grid;
     M.has_left = g.rank > 0; M.has_right = g.rank < g.world - 1;
+    M.act_sph = g.d_act_sph;
     return M;
 }
 
@@ -438,10 +448,16 @@ int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches) {
     int rc = mg_halo_exchange(ctx, P, g.d_flag, launches);
     if (rc) return rc;
     *launches += launch_mg_active_list(P, M, s);
+    *launches += launch_mg_active_spheres(P, M, s);
     CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_counts, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     g.n_own = ctx->h_pinned[40];
     g.n_active = ctx->h_pinned[43];
+    g.n_act_sph = ctx->h_pinned[44];
+    GridInfo gi;
+    memcpy(&gi, ctx->h_pinned + 8, sizeof(GridInfo));
+    g.grid_cells = gi.ncells;  // the host now knows this rebuild's grid: clear and scan only its cells
     return DEM_OK;
 }
 
@@ -470,6 +486,7 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
             int rc = mg_redistribute(ctx, P, &launches);
             if (rc) return rc;
             P = make_params(ctx);  // nActive changed
+            C = make_cd(ctx);      // ... and so did the active sphere list and the cell count
             P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
             P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
             P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
@@ -718,7 +735,7 @@ int dem_ctx_destroy(DemCtx* ctx) {
     if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
     {
         MgState& g = ctx->mg;
-        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
+        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_act_sph); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
         for (int d = 0; d < 2; d++)
             if (g.peer_block[d]) cudaIpcCloseMemHandle(g.peer_block[d]);
         if (g.p2p_block) cudaFree(g.p2p_block);
@@ -1393,6 +1410,7 @@ int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]
     int rc;
     if ((rc = dalloc(ctx, &g.d_flag, nO))) return rc;
     if ((rc = dalloc(ctx, &g.d_active_list, nO))) return rc;
+    if ((rc = dalloc(ctx, &g.d_act_sph, std::max<uint32_t>(ctx->nSpheres, 1u)))) return rc;
     if ((rc = dalloc(ctx, &g.d_counts, 8))) return rc;
     if ((rc = dalloc(ctx, &g.d_allcounts, 8 * (size_t)world))) return rc;
     for (int d = 0; d < 2; d++) {
@@ -1558,48 +1576,68 @@ int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uin
     return DEM_OK;
 }
 
-int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]) {
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    double acc[5] = {0, 0, 0, 0, 0};
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStream_t s = ctx->stream;
     const int model = (int)ctx->sp.force_model;
     const bool rec = ctx->sp.record_contact_forces != 0;
-    for (uint64_t i = 0; i < n_steps; i++) {
-        CK(cudaEventRecord(ctx->ev[0], s));
-        if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
-            int rc = rebuild(ctx);
-            if (rc) return rc;
+    // Events are recorded for a whole batch of steps and read back afterwards: a host synchronisation per step would
+    // expose launch latencies and, on several GPUs, let the ranks drift apart between steps.
+    constexpr int NE = 6, BATCH = 128;
+    std::vector<cudaEvent_t> ev((size_t)NE * BATCH);
+    for (auto& e : ev) CK(cudaEventCreate(&e));
+    uint64_t done = 0;
+    int rc_out = DEM_OK;
+    while (done < n_steps && rc_out == DEM_OK) {
+        const int nb = (int)std::min<uint64_t>(BATCH, n_steps - done);
+        for (int i = 0; i < nb; i++) {
+            cudaEvent_t* e = &ev[(size_t)NE * i];
+            CK(cudaEventRecord(e[0], s));
+            if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+                int rc = rebuild(ctx);
+                if (rc) { rc_out = rc; break; }
+            }
+            CK(cudaEventRecord(e[1], s));
+            DevParams P = make_params(ctx);
+            launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->fast_math != 0, s);
+            CK(cudaEventRecord(e[2], s));
+            if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
+            if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
+            CK(cudaEventRecord(e[3], s));
+            launch_integrate(P, s);
+            ctx->maxvel_slot ^= 1;
+            CK(cudaEventRecord(e[4], s));
+            if (ctx->mg.on) {
+                int l = 0;
+                int rc = mg_halo_exchange(ctx, P, nullptr, &l);
+                if (rc) { rc_out = rc; break; }
+                ctx->launches += l;
+            }
+            CK(cudaEventRecord(e[5], s));
+            ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
+            ctx->n_steps++;
+            ctx->steps_since_rebuild++;
+            ctx->sim_time += (double)ctx->sp.h;
         }
-        CK(cudaEventRecord(ctx->ev[1], s));
-        DevParams P = make_params(ctx);
-        launch_force_ss(P, model, rec, ctx->num_sms, ctx->ctas_per_sm, ctx->fast_math != 0, s);
-        CK(cudaEventRecord(ctx->ev[2], s));
-        if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
-        if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
-        CK(cudaEventRecord(ctx->ev[3], s));
-        launch_integrate(P, s);
-        ctx->maxvel_slot ^= 1;
-        if (ctx->mg.on) {
-            int l = 0;
-            int rc = mg_halo_exchange(ctx, P, nullptr, &l);
-            if (rc) return rc;
-            ctx->launches += l;
+        if (rc_out != DEM_OK) break;
+        CK(cudaStreamSynchronize(s));
+        for (int i = 0; i < nb; i++) {
+            cudaEvent_t* e = &ev[(size_t)NE * i];
+            float ms;
+            CK(cudaEventElapsedTime(&ms, e[1], e[2])); acc[0] += ms;
+            CK(cudaEventElapsedTime(&ms, e[2], e[3])); acc[1] += ms;
+            CK(cudaEventElapsedTime(&ms, e[3], e[4])); acc[2] += ms;
+            CK(cudaEventElapsedTime(&ms, e[0], e[1])); acc[3] += ms;
+            CK(cudaEventElapsedTime(&ms, e[0], e[5])); acc[4] += ms;
+            CK(cudaEventElapsedTime(&ms, e[4], e[5])); acc[5] += ms;
         }
-        CK(cudaEventRecord(ctx->ev[4], s));
-        ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
-        ctx->n_steps++;
-        ctx->steps_since_rebuild++;
-        ctx->sim_time += (double)ctx->sp.h;
-        CK(cudaEventSynchronize(ctx->ev[4]));
-        float ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2])); acc[0] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3])); acc[1] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4])); acc[2] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1])); acc[3] += ms;
-        CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[4])); acc[4] += ms;
+        done += nb;
     }
-    for (int k = 0; k < 5; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;
+    for (auto& e : ev) cudaEventDestroy(e);
+    if (rc_out != DEM_OK) return rc_out;
+    for (int k = 0; k < 8; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;
     return DEM_OK;
 }
 

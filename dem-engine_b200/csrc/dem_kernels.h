@@ -11,7 +11,7 @@ struct GridInfo {
     uint32_t nbx, nby, nbz, ncells;
     float max_margin, maxvel;
     float halo;  // domain decomposition: width of the ghost layer for this rebuild
-    float pad_;
+    int x0;      // domain decomposition: first cell column of this rank's table (nbx counts the columns it holds)
 };
 
 // analytical component resolved to world space for one rebuild
@@ -53,6 +53,13 @@ struct CdParams {
     uint32_t tri_pair_cap;
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the scans
+    // domain decomposition (0 / nullptr on a single GPU): the rebuild walks the spheres of the active owners only and
+    // bins them into the cell columns of this rank's slab (+ halo)
+    const uint32_t* act_sph;  // compact list of active sphere ids
+    uint32_t nActSph;
+    uint32_t scan_cells;      // cell-table entries to clear and scan (ncells + 1 when the host knows the grid)
+    int slab_on;
+    float slab_lo, slab_hi;   // my slab in LBF-relative x
 };
 
 // multi-GPU (slab decomposition) bookkeeping passed to the kernels of kernels_mgpu.cu
@@ -66,11 +73,13 @@ struct MgParams {
     float cut_lo, cut_hi;     // my slab in LBF-relative x
     const GridInfo* grid;     // halo width of this rebuild is grid->halo
     int has_left, has_right;
+    uint32_t* act_sph;        // compact list of the spheres of active owners; counts[4] = its length
 };
 
 int launch_mg_classify(const DevParams& P, const MgParams& M, cudaStream_t s);
 int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* buf, cudaStream_t s);
 int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s);
+int launch_mg_active_spheres(const DevParams& P, const MgParams& M, cudaStream_t s);
 int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s);
 
 // per-step halo exchange through peer memory (NVLink stores into the neighbour's receive buffer + a flag)

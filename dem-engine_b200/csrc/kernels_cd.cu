@@ -74,7 +74,20 @@ __global__ void k_grid_setup(const __grid_constant__ DevParams P, const __grid_c
     // ghost layer: two clumps can touch up to 2 (R_clump + margin) apart; one more margin on each side covers the
     // distance an owner can travel before the next rebuild (that bound is what the margin is made of)
     g.halo = 2.f * (C.rclump + margin) + 2.f * margin;
-    g.pad_ = 0.f;
+    g.x0 = 0;
+    if (C.slab_on) {
+        // This rank only bins the cell columns its active spheres can fall into: the slab, the ghost layer on either
+        // side, the reach of a ghost clump's spheres beyond its centre, and one spare column.  Same cell size and
+        // origin on every rank, so the (cell, sphere id) order of any two spheres -- hence their A/B roles -- is the
+        // same wherever the pair is evaluated; spheres outside the range are clamped into the edge columns, which
+        // keeps true neighbours within one column of each other.
+        const float reach = g.halo + C.rclump + margin + cs;
+        const int lo = max(0, (int)floorf((C.slab_lo - reach) * g.inv_cs));
+        const int hi = min((int)nbx - 1, (int)floorf((C.slab_hi + reach) * g.inv_cs));
+        g.x0 = lo;
+        g.nbx = (uint32_t)max(1, hi - lo + 1);
+        g.ncells = g.nbx * nby * nbz;
+    }
     *C.grid = g;
 }
 
@@ -144,8 +157,9 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t count, uint32_t* cursor)
 
 __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ CdParams C) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = i < P.nSpheres;
+    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = t_ < (C.act_sph ? C.nActSph : P.nSpheres);
+    const uint32_t i = (valid && C.act_sph) ? C.act_sph[t_] : t_;
     uint32_t nsa = 0, samask = 0;
     float3 sp = f3(0.f, 0.f, 0.f);
     uint2 s = make_uint2(0, 0);
@@ -185,7 +199,7 @@ __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ Dev
         sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
         const float rInfl = comp.w + margin;
         C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
-        int cx = (int)floorf(sp.x * g.inv_cs), cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
+        int cx = (int)floorf(sp.x * g.inv_cs) - g.x0, cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
         cx = min(max(cx, 0), (int)g.nbx - 1);
         cy = min(max(cy, 0), (int)g.nby - 1);
         cz = min(max(cz, 0), (int)g.nbz - 1);
@@ -460,8 +474,9 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ D
 // ---- counting sort by cell (sort_mode 1): the histogram and its prefix exist anyway for the sweep ----
 __global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevParams P,
                                                     const __grid_constant__ CdParams C) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.nSpheres) return;
+    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t_ >= (C.act_sph ? C.nActSph : P.nSpheres)) return;
+    const uint32_t i = C.act_sph ? C.act_sph[t_] : t_;
     const uint32_t key = C.keys[0][i];
     if (key == 0xffffffffu) return;  // inactive on this rank
     C.keys[1][C.cellStart[key] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
@@ -472,7 +487,7 @@ __global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevP
 __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant__ DevParams P,
                                                           const __grid_constant__ CdParams C) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= C.cellStart[C.max_cells]) return;  // number of active spheres (== nSpheres on a single GPU)
+    if (j >= C.cellStart[C.grid->ncells]) return;  // number of active spheres (== nSpheres on a single GPU)
     const uint32_t i = C.keys[1][j];
     const uint32_t key = C.keys[0][i];
     const uint32_t sb = C.cellStart[key], se = C.cellStart[key + 1];
@@ -501,8 +516,9 @@ __device__ __forceinline__ void tri_cell_range(const GridInfo& g, const CdParams
     const int nb[3] = {(int)g.nbx, (int)g.nby, (int)g.nbz};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        lo[k] = min(max((int)floorf(mn[k] * g.inv_cs), 0), nb[k] - 1);
-        hi[k] = min(max((int)floorf(mx[k] * g.inv_cs), 0), nb[k] - 1);
+        const int off = (k == 0) ? g.x0 : 0;
+        lo[k] = min(max((int)floorf(mn[k] * g.inv_cs) - off, 0), nb[k] - 1);
+        hi[k] = min(max((int)floorf(mx[k] * g.inv_cs) - off, 0), nb[k] - 1);
     }
 }
 
@@ -681,8 +697,9 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
                                                const uint32_t* __restrict__ keys) {
     // One thread per sphere IN SPHERE-ID ORDER (clump by clump), so that the slots claimed below make the contact list
     // owner-major: the force kernel then streams the A side and reduces it inside the warp.
-    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = sid < P.nSpheres;
+    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = t_ < (C.act_sph ? C.nActSph : P.nSpheres);
+    const uint32_t sid = (valid && C.act_sph) ? C.act_sph[t_] : t_;
     if (valid && C.keys[0][sid] == 0xffffffffu) {
         // inactive on this rank: leave empty segments behind so that later history look-ups find nothing stale
         P.ss.seg_start[sid] = 0; P.ss.seg_count[sid] = 0;
@@ -874,12 +891,22 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, i
             k_anal_prep<<<(P.nAnal + 63) / 64, 64, 0, s>>>(P, C);
             launches++;
         }
-        cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+        cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * (size_t)C.scan_cells, s);
         cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
-        if (P.nSpheres) {
-            k_sphere_prep<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, C);
+        if (C.act_sph && P.nTri)  // the per-sphere triangle pass walks all spheres and skips those without a key
+            cudaMemsetAsync(C.keys[0], 0xff, sizeof(uint32_t) * (size_t)P.nSpheres, s);
+        if (C.act_sph) {
+            // spheres this rank does not hold are not visited: leave empty segments behind for them, so that later
+            // history look-ups find nothing stale
+            cudaMemsetAsync(P.ss.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
+            cudaMemsetAsync(P.sn.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
+            cudaMemsetAsync(P.sa.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
+        }
+        const uint32_t n = C.act_sph ? C.nActSph : P.nSpheres;
+        if (n) {
+            k_sphere_prep<<<(n + 255) / 256, 256, 0, s>>>(P, C);
             launches++;
         }
     }
@@ -888,9 +915,10 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, i
 
 int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev, bool sort_only) {
     int launches = 0;
-    const uint32_t n = P.nSpheres;
-    // cell histogram -> exclusive prefix (ncells+1 entries; scanning the full capacity keeps the launch shape static)
-    launches += launch_scan_exclusive(C.cellStart, C.max_cells + 1, C.scan_tmp, nullptr, s);
+    const uint32_t n = C.act_sph ? C.nActSph : P.nSpheres;
+    // cell histogram -> exclusive prefix (ncells+1 entries; on a single GPU the host does not know the grid of this
+    // rebuild yet and scans the full capacity, which keeps the launch shape static)
+    launches += launch_scan_exclusive(C.cellStart, C.scan_cells, C.scan_tmp, nullptr, s);
     if (ev) cudaEventRecord(ev[0], s);
     if (n) {
         if (sorted_buf < 0) {  // counting sort

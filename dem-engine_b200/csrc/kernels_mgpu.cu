@@ -93,6 +93,16 @@ __global__ void __launch_bounds__(256) k_mg_active_list(const __grid_constant__ 
     warp_append(own, &M.counts[0]);
 }
 
+// compact list of the spheres of active owners: the rebuild walks this list instead of all spheres, so its cost follows
+// the slab, not the whole bed.  Warps append in arrival order, lanes in sphere order: the spheres of a clump stay
+// adjacent (up to a warp boundary), which is all the owner-major contact order needs.
+__global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant__ DevParams P, MgParams M) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = (i < P.nSpheres) && (M.flag[P.sph[i].x] != 0);
+    const uint32_t slot = warp_append(act, &M.counts[4]);
+    if (act) M.act_sph[slot] = i;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Per-step exchange without a library call: every rank stores the {state, spin} records of its halo owners straight into
 // the neighbour's receive buffer over NVLink (peer memory mapped with cudaIpc*), then publishes the epoch number in the
@@ -184,6 +194,10 @@ int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* bu
 int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s) {
     if (n == 0) return 0;
     k_mg_unpack<<<(n * 5u + 255) / 256, 256, 0, s>>>(P, gid, n, reinterpret_cast<const int4*>(buf), flag);
+    return 1;
+}
+int launch_mg_active_spheres(const DevParams& P, const MgParams& M, cudaStream_t s) {
+    if (P.nSpheres) k_mg_active_spheres<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, M);
     return 1;
 }
 int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s) {

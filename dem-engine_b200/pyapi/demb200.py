@@ -336,7 +336,7 @@ class Engine:
         return dict(zip(names, [float(x) for x in out]))
 
     def profile_steps(self, n):
-        out = (C.c_float * 5)()
+        out = (C.c_float * 8)()
         self._ck(self.lib.dem_profile_steps(self.ctx, C.c_uint64(n), out))
         return {"force_ss_us": out[0], "force_sa_us": out[1], "integrate_us": out[2], "rebuild_us_per_step": out[3],
-                "step_us": out[4]}
+                "step_us": out[4], "halo_exchange_us": out[5]}

@@ -230,8 +230,10 @@ int dem_set_option(DemCtx* ctx, const char* name, double value);
 /* ---- measurement hooks (bench.py / ncu) ---------------------------------------------------------------- */
 /* Run n steps and return the mean device time per kernel in microseconds, measured with CUDA events on the
  * launching stream: [0]=sphere-sphere force kernel [1]=sphere-analytical force kernel [2]=integration kernel
- * [3]=contact rebuild amortised per step [4]=whole step */
-int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[5]);
+ * [3]=contact rebuild amortised per step [4]=whole step [5]=ghost-owner halo exchange (multi-GPU; includes waiting for
+ * the neighbour) [6..7] reserved.  The wall / mesh kernels run serialised here (no side stream), so [4] is an upper
+ * bound of the production step. */
+int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]);
 /* One contact-list rebuild with CUDA events between its stages (microseconds): [0] margins + cell keys + histogram +
  * sphere-analytical list [1] sort [2] cell-table scan [3] gather [4] sweep (+ history carry-over) [5] counts
  * [6] unused [7] whole rebuild */
