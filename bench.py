@@ -322,16 +322,15 @@ def main():
         # ---- e2e: through the public C-ABI calls with HOST buffers; every step uploads the step's host-side inputs
         # (simulation parameters + the family prescription / mask tables a co-simulating caller updates) and reads the
         # step's result metrics (max |v|, kinetic energy) back to the host.
-        h2d = 120 + 32896 + 1024 + 88 * 256
-        d2h = 16
+        h2d = 56576 + 40  # family blob (masks 32896 padded to 33024 + 1024 + 88*256) + neutral elements of the reductions
+        d2h = 40          # five doubles of dem_reduce_many
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             eng.set_params(eng.params)
             eng.update_families(f.familyMasks, f.familyExtraMarginSize, f.prescriptions)
-            eng.step(1)
-            eng.reduce(demb200.REDUCE_MAX_ABSV)
-            eng.reduce(demb200.REDUCE_KINETIC_ENERGY)
+            eng.step_async(1)
+            eng.reduce_many((demb200.REDUCE_MAX_ABSV, demb200.REDUCE_KINETIC_ENERGY))  # synchronises
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
 

@@ -138,12 +138,18 @@ struct DemCtx {
     float4* d_massprop = nullptr;
     MatPair* d_matpair = nullptr;
     AnalObj* d_anal = nullptr;
+    // family tables live in one device blob [masks | extra margins | prescriptions] refreshed with ONE copy from a
+    // pinned staging buffer (a co-simulating caller re-sends them every step)
+    char* d_famblob = nullptr;
+    char* h_famblob = nullptr;        // pinned
+    cudaEvent_t ev_fam = nullptr;     // completion of the last staged upload
     uint8_t* d_masks = nullptr;
     float* d_extra = nullptr;
     Prescr* d_presc = nullptr;
     uint32_t* d_flags = nullptr;
     float* d_maxvel = nullptr;
     double* d_reduce = nullptr;
+    double* d_reduce_many = nullptr;
     // contact lists [kind][buffer]: kind 0 = sphere-sphere in touch at the last rebuild, 1 = other sphere-sphere
     // candidates, 2 = sphere-analytical; two buffers each (current / being rebuilt)
     ListBuf lists[4][2];  // [3] = sphere-triangle
@@ -332,8 +338,8 @@ CdParams make_cd(const DemCtx* c) {
 
 void free_device(DemCtx* c) {
     dfree(c->d_state); dfree(c->d_spin); dfree(c->d_wrench); dfree(c->d_acc); dfree(c->d_sph); dfree(c->d_comp); dfree(c->d_massprop);
-    dfree(c->d_matpair); dfree(c->d_anal); dfree(c->d_masks); dfree(c->d_extra); dfree(c->d_presc);
-    dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce);
+    dfree(c->d_matpair); dfree(c->d_anal); dfree(c->d_famblob); c->d_masks = nullptr; c->d_extra = nullptr; c->d_presc = nullptr;
+    dfree(c->d_flags); dfree(c->d_maxvel); dfree(c->d_reduce); dfree(c->d_reduce_many);
     for (int kind = 0; kind < 4; kind++)
         for (int k = 0; k < 2; k++) free_list(c->lists[kind][k]);
     for (int k = 0; k < 3; k++) { dfree(c->d_tri[k]); dfree(c->d_triW[k]); }
@@ -342,6 +348,28 @@ void free_device(DemCtx* c) {
     dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw); dfree(c->d_sortedPos);
     dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
     c->device_bytes = 0;
+}
+
+constexpr size_t FAM_OFF_MASKS = 0;
+constexpr size_t FAM_OFF_EXTRA = (DEM_NUM_FAMILY_MASKS + 255) / 256 * 256;
+constexpr size_t FAM_OFF_PRESC = FAM_OFF_EXTRA + sizeof(float) * DEM_NUM_FAMILIES;
+constexpr size_t FAM_BLOB_BYTES = FAM_OFF_PRESC + sizeof(Prescr) * DEM_NUM_FAMILIES;
+
+// host tables -> pinned staging -> device blob, one asynchronous copy on the compute stream
+int stage_families(DemCtx* ctx) {
+    if (!ctx->h_famblob) {
+        CK(cudaHostAlloc((void**)&ctx->h_famblob, FAM_BLOB_BYTES, cudaHostAllocDefault));
+        memset(ctx->h_famblob, 0, FAM_BLOB_BYTES);
+        CK(cudaEventCreateWithFlags(&ctx->ev_fam, cudaEventDisableTiming));
+    } else {
+        CK(cudaEventSynchronize(ctx->ev_fam));  // the previous upload has left the staging buffer
+    }
+    memcpy(ctx->h_famblob + FAM_OFF_MASKS, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS);
+    memcpy(ctx->h_famblob + FAM_OFF_EXTRA, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES);
+    memcpy(ctx->h_famblob + FAM_OFF_PRESC, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES);
+    CK(cudaMemcpyAsync(ctx->d_famblob, ctx->h_famblob, FAM_BLOB_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_fam, ctx->stream));
+    return DEM_OK;
 }
 
 int alloc_lists(DemCtx* ctx, uint64_t cap) {
@@ -750,6 +778,8 @@ int dem_ctx_destroy(DemCtx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->h_famblob) cudaFreeHost(ctx->h_famblob);
+    if (ctx->ev_fam) cudaEventDestroy(ctx->ev_fam);
     for (int k = 0; k < 5; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -878,10 +908,9 @@ int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMar
     for (float e : ctx->h_extra) ctx->max_extra = std::max(ctx->max_extra, e);
     if (ctx->initialized) {
         cudaSetDevice(ctx->device);
-        CK(cudaMemcpyAsync(ctx->d_masks, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_extra, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ctx->d_presc, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        // stream-ordered: the tables change between the steps already enqueued and the ones enqueued after this call
+        int rcf = stage_families(ctx);
+        if (rcf) return rcf;
         // prescriptions act in the integrator only; the contact list depends on the masks and the extra margins
         if (old_masks != ctx->h_masks || old_extra != ctx->h_extra) ctx->need_rebuild = true;
     }
@@ -987,12 +1016,14 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if ((rc = dalloc(ctx, &ctx->d_massprop, ctx->h_massprop.size()))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_matpair, ctx->h_matpair.size()))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_anal, ctx->h_anal.size()))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_masks, DEM_NUM_FAMILY_MASKS))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_extra, DEM_NUM_FAMILIES))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_presc, DEM_NUM_FAMILIES))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_famblob, FAM_BLOB_BYTES))) return rc;
+    ctx->d_masks = reinterpret_cast<uint8_t*>(ctx->d_famblob + FAM_OFF_MASKS);
+    ctx->d_extra = reinterpret_cast<float*>(ctx->d_famblob + FAM_OFF_EXTRA);
+    ctx->d_presc = reinterpret_cast<Prescr*>(ctx->d_famblob + FAM_OFF_PRESC);
     if ((rc = dalloc(ctx, &ctx->d_flags, 4))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_maxvel, 4))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_reduce, 4))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_reduce_many, 8))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_grid, 1))) return rc;
     CK(cudaMemcpy(ctx->d_state, ctx->h_state.data(), sizeof(OwnerState) * nO, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_spin, ctx->h_spin.data(), sizeof(float4) * nO, cudaMemcpyHostToDevice));
@@ -1003,9 +1034,11 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     CK(cudaMemcpy(ctx->d_massprop, ctx->h_massprop.data(), sizeof(float4) * ctx->h_massprop.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_matpair, ctx->h_matpair.data(), sizeof(MatPair) * ctx->h_matpair.size(), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ctx->d_anal, ctx->h_anal.data(), sizeof(AnalObj) * ctx->h_anal.size(), cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_masks, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_extra, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_presc, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES, cudaMemcpyHostToDevice));
+    {
+        int rcf = stage_families(ctx);
+        if (rcf) return rcf;
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
     CK(cudaMemset(ctx->d_flags, 0, sizeof(uint32_t) * 4));
 
     // broad-phase sizing: the smallest cell the device may ever pick bounds the cell table and the sort key width
@@ -1345,6 +1378,24 @@ int dem_reduce(DemCtx* ctx, int kind, double* out) {
     ctx->launches += launch_reduce(P, kind, ctx->d_reduce, ctx->stream);
     CK(cudaMemcpyAsync(out, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return DEM_OK;
+}
+
+int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]) {
+    if (!ctx || !ctx->initialized || !out) return DEM_ERR_INVALID;
+    if (kind_mask == 0 || kind_mask >= (1u << 5)) return fail(ctx, DEM_ERR_INVALID, "unknown reduction in mask");
+    CK(cudaSetDevice(ctx->device));
+    double* hp = reinterpret_cast<double*>(ctx->h_pinned + 112);  // pinned scratch: words 112..131
+    const double init[5] = {0.0, -1e300, 1e300, 0.0, 0.0};
+    memcpy(hp, init, sizeof(init));
+    CK(cudaMemcpyAsync(ctx->d_reduce_many, hp, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    DevParams P = make_params(ctx);
+    P.nOwners = ctx->nClumpOwners;
+    ctx->launches += launch_reduce_many(P, kind_mask, ctx->d_reduce_many, ctx->stream);
+    CK(cudaMemcpyAsync(hp + 5, ctx->d_reduce_many, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 5; k++)
+        if (kind_mask & (1u << k)) out[k] = hp[5 + k];
     return DEM_OK;
 }
 

@@ -112,5 +112,6 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
                     bool sort_only = false);
 int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* total, cudaStream_t s);
 int launch_reduce(const DevParams& P, int kind, double* d_out, cudaStream_t s);
+int launch_reduce_many(const DevParams& P, uint32_t mask, double* d_out, cudaStream_t s);
 
 }  // namespace demb

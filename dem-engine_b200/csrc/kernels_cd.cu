@@ -990,6 +990,73 @@ __global__ void k_reduce(const __grid_constant__ DevParams P, int kind, uint32_t
     }
 }
 
+// All five reductions in ONE pass over the owners (a caller that polls several inspectors per frame pays for the 80-byte
+// owner stream once): per-thread values -> warp shuffle -> shared memory -> one atomic per CTA and quantity.
+// out[kind] must hold the neutral element of each reduction on entry.
+__device__ __forceinline__ void atomic_minmax_double(double* out, double v, bool is_max) {
+    unsigned long long* addr = reinterpret_cast<unsigned long long*>(out);
+    unsigned long long old = *addr, assumed;
+    do {
+        assumed = old;
+        const double cur = __longlong_as_double((long long)assumed);
+        const double nv = is_max ? fmax(cur, v) : fmin(cur, v);
+        if (nv == cur) break;
+        old = atomicCAS(addr, assumed, (unsigned long long)__double_as_longlong(nv));
+    } while (assumed != old);
+}
+
+__global__ void __launch_bounds__(256) k_reduce_many(const __grid_constant__ DevParams P, uint32_t mask, uint32_t nClumps,
+                                                     double* out) {
+    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    double v[5] = {0.0, -1e300, 1e300, 0.0, 0.0};
+    if (o < nClumps && (!P.active || P.active[o] == 1)) {
+        const OwnerState st = P.state[o];
+        v[DEM_REDUCE_MAX_ABSV] = sqrtf(st.vel.x * st.vel.x + st.vel.y * st.vel.y + st.vel.z * st.vel.z);
+        if (mask & ((1u << DEM_REDUCE_MAX_Z) | (1u << DEM_REDUCE_MIN_Z))) {
+            double X, Y, Z;
+            pos_decode(st.pos, P, X, Y, Z);
+            v[DEM_REDUCE_MAX_Z] = v[DEM_REDUCE_MIN_Z] = Z + (double)P.LBF[2];
+        }
+        if (mask & (1u << DEM_REDUCE_KINETIC_ENERGY)) {
+            const float4 sp = P.spin[o];
+            const float4 mp = P.massprop[__float_as_uint(sp.w)];
+            v[DEM_REDUCE_KINETIC_ENERGY] =
+                0.5 * (double)st.vel.w * ((double)st.vel.x * st.vel.x + (double)st.vel.y * st.vel.y + (double)st.vel.z * st.vel.z) +
+                0.5 * ((double)mp.y * sp.x * sp.x + (double)mp.z * sp.y * sp.y + (double)mp.w * sp.z * sp.z);
+        }
+        v[DEM_REDUCE_TOTAL_MASS] = st.vel.w;
+    }
+    __shared__ double sh[5][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        if (!(mask & (1u << k))) continue;
+        const bool is_max = (k == DEM_REDUCE_MAX_ABSV || k == DEM_REDUCE_MAX_Z), is_min = (k == DEM_REDUCE_MIN_Z);
+        double x = v[k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double t = __shfl_xor_sync(0xffffffffu, x, off);
+            x = is_max ? fmax(x, t) : (is_min ? fmin(x, t) : x + t);
+        }
+        if (lane == 0) sh[k][warp] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x < 5 && (mask & (1u << threadIdx.x))) {
+        const int k = threadIdx.x;
+        const bool is_max = (k == DEM_REDUCE_MAX_ABSV || k == DEM_REDUCE_MAX_Z), is_min = (k == DEM_REDUCE_MIN_Z);
+        double x = sh[k][0];
+        for (int w = 1; w < 8; w++) x = is_max ? fmax(x, sh[k][w]) : (is_min ? fmin(x, sh[k][w]) : x + sh[k][w]);
+        if (is_max || is_min) atomic_minmax_double(out + k, x, is_max); else atomicAdd(out + k, x);
+    }
+}
+
+int launch_reduce_many(const DevParams& P, uint32_t mask, double* d_out, cudaStream_t s) {
+    const uint32_t n = P.nOwners;
+    if (n == 0) return 0;
+    k_reduce_many<<<(n + 255) / 256, 256, 0, s>>>(P, mask, n, d_out);
+    return 1;
+}
+
 int launch_reduce(const DevParams& P, int kind, double* d_out, cudaStream_t s) {
     // clump owners are the owners that have spheres: the caller passes nOwners restricted to clumps via P.nOwners
     const uint32_t n = P.nOwners;

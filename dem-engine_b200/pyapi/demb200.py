@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
-    "dem_get_stats", "dem_reduce", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
+    "dem_get_stats", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
 ]
 
@@ -288,6 +288,15 @@ class Engine:
         out = C.c_double(0)
         self._ck(self.lib.dem_reduce(self.ctx, int(kind), C.byref(out)))
         return out.value
+
+    def reduce_many(self, kinds):
+        """Several reductions in one pass and one read-back (dem_reduce_many); returns {kind: value}."""
+        mask = 0
+        for k in kinds:
+            mask |= 1 << int(k)
+        out = (C.c_double * 5)()
+        self._ck(self.lib.dem_reduce_many(self.ctx, C.c_uint32(mask), out))
+        return {int(k): out[int(k)] for k in kinds}
 
     def profile_binning(self, repeats=10):
         out = (C.c_float * 3)()

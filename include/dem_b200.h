@@ -202,6 +202,10 @@ int dem_get_stats(DemCtx* ctx, DemStats* out);
 enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_REDUCE_KINETIC_ENERGY = 3,
        DEM_REDUCE_TOTAL_MASS = 4 };
 int dem_reduce(DemCtx* ctx, int kind, double* out);
+/* Several reductions in one pass over the owners and one read-back: bit k of kind_mask selects DEM_REDUCE_<k>;
+ * out[k] receives it (entries of unselected kinds are left untouched). What a caller polling several inspectors per
+ * frame (DEMInspector::GetValue in a loop, e.g. DEMdemo_Mixer.cpp:130-140) should use. */
+int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]);
 
 /* ---- multi-GPU: slab decomposition with ghost-owner halo exchange over NCCL (no counterpart in the reference, whose
  * "multi-GPU" is the kT/dT thread pair of APIPublic.cpp:35-48).  One process and one context per GPU; every rank

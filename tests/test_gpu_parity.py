@@ -371,6 +371,23 @@ def test_do_dynamics_step_count_and_reductions(built):
     eng.close()
 
 
+def test_reduce_many_matches_single_reductions(built):
+    """dem_reduce_many (one pass, one read-back) returns what the individual dem_reduce calls return."""
+    f = scenes.flatten(_mk("clumps_full"))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    eng.step(300)
+    kinds = (demb200.REDUCE_MAX_ABSV, demb200.REDUCE_MAX_Z, demb200.REDUCE_MIN_Z, demb200.REDUCE_KINETIC_ENERGY,
+             demb200.REDUCE_TOTAL_MASS)
+    many = eng.reduce_many(kinds)
+    for k in kinds:
+        one = eng.reduce(k)
+        assert many[k] == pytest.approx(one, rel=1e-9, abs=1e-300), (k, many[k], one)
+    sub = eng.reduce_many((demb200.REDUCE_KINETIC_ENERGY,))
+    assert sub[demb200.REDUCE_KINETIC_ENERGY] == pytest.approx(many[demb200.REDUCE_KINETIC_ENERGY], rel=1e-9)
+    eng.close()
+
+
 def test_momentum_conservation_without_walls(built):
     """Sum of internal forces is zero: with no gravity and no walls the total linear momentum is conserved."""
     sc = scenes.config2_clumps(5, 5, 4, cd_update_freq=5, spacing=2.7)
