@@ -687,6 +687,7 @@ int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaSt
 }
 
 constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half stencil)
+constexpr uint32_t CINFO_NO_HISTORY = 0x40000000u;  // sweep -> k_history: this contact carries no history over
 
 // The sweep.  Cells are x-fastest, so the x-neighbours of a row are ONE contiguous run of the cell-sorted array.
 // Each sphere looks only "forward" (upper half of the 27-cell stencil => 5 runs, the own row starting right behind
@@ -812,11 +813,9 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
         const ContactList& L = touching ? P.ss : P.sn;
         const uint32_t slot = touching ? slotT++ : slotN++;
         if (slot >= C.capacity) continue;
-        // history carry-over (DEMHistoryMappingKernels.cu): the pair may sit in either previous list as (A,B) or --
-        // when the two spheres swapped their order in the sorted array -- as (B,A); then delta_tan changes sign.
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t alive = 0;
-        bool found = false;
+        // The history carry-over is NOT done here: per sphere it is a doubly nested search of very uneven length (the
+        // warp would run at 5-9 active lanes of 32); k_history does it with one thread per emitted contact instead.
+        uint32_t skip = 0;
         if (!touching) {
             // A candidate that is clearly apart at these very positions (float positions: allow for their rounding)
             // would have its history destroyed by the force pass that follows this rebuild (no overlap => wildcards
@@ -825,14 +824,40 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
             const float dx = me.x - ot.x, dy = me.y - ot.y, dz = me.z - ot.z;
             const float Rtrue = (me.w - myMargin) + __ldg(&P.comp[om.z & 0xffffu]).w;
             const float slack = 3e-7f * (fabsf(me.x) + fabsf(me.y) + fabsf(me.z)) + 1e-8f;
-            found = sqrtf(dx * dx + dy * dy + dz * dz) * 0.999999f - Rtrue * 1.000001f - slack > 0.f;
+            if (sqrtf(dx * dx + dy * dy + dz * dz) * 0.999999f - Rtrue * 1.000001f - slack > 0.f) skip = CINFO_NO_HISTORY;
         }
-        const bool no_history = found;
+        const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
+        L.pair[slot] = make_uint2(meta.y, om.y);
+        L.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | skip);
+    }
+}
+
+// History carry-over (DEMHistoryMappingKernels.cu), one thread per contact of the two new sphere--sphere lists: the pair
+// may sit in either previous list as (A,B) or -- when the two spheres swapped their order in the sorted array -- as
+// (B,A); then delta_tan changes sign.  Adjacent threads hold the contacts of the same sphere A (the lists are
+// sphere-major), so their segment look-ups coalesce.
+__global__ void __launch_bounds__(256) k_history(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    const uint32_t nT = min(*P.ss.count, C.capacity);
+    const uint32_t n = nT + min(*P.sn.count, C.capacity);
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
+        const bool touching = c < nT;
+        const ContactList& L = touching ? P.ss : P.sn;
+        const uint32_t slot = touching ? c : c - nT;
+        const uint32_t w = L.cinfo[slot].w;
+        if (w & CINFO_NO_HISTORY) {  // (a contact that is not alive never has its history word read)
+            L.cinfo[slot].w = w & ~CINFO_NO_HISTORY;
+            continue;
+        }
+        const uint2 pr = L.pair[slot];
+        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t alive = 0;
+        bool found = false;
 #pragma unroll 1
         for (int pass = 0; pass < 4 && !found; pass++) {
             const ContactList& O = ((pass & 1) == (touching ? 0 : 1)) ? C.oldss : C.oldsn;  // likelier list first
             const bool flipped = pass >= 2;
-            const uint32_t a = flipped ? om.y : meta.y, b = flipped ? meta.y : om.y;
+            const uint32_t a = flipped ? pr.y : pr.x, b = flipped ? pr.x : pr.y;
             const uint32_t os = O.seg_start[a], oc = O.seg_count[a];
             for (uint32_t t = 0; t < oc; t++) {
                 if (O.pair[os + t].y == b) {
@@ -846,10 +871,8 @@ __global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams
                 }
             }
         }
-        const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
-        L.pair[slot] = make_uint2(meta.y, om.y);
-        L.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | alive);
-        if (L.hist && !no_history) L.hist[slot] = h;  // (a contact that is not alive never has its history word read)
+        if (alive) L.cinfo[slot].w = w | alive;
+        if (L.hist) L.hist[slot] = h;
     }
 }
 
@@ -931,7 +954,8 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaS
         if (ev) cudaEventRecord(ev[1], s);
         if (sort_only) return launches + 1;
         k_sweep<<<(n + 127) / 128, 128, 0, s>>>(P, C, sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf]);
-        launches += 2;
+        k_history<<<148 * 8, 256, 0, s>>>(P, C);
+        launches += 3;
     } else if (ev) {
         cudaEventRecord(ev[1], s);
     }
