@@ -493,6 +493,19 @@ class DEMSolver {
     std::vector<uint8_t> m_family_masks;
 
     size_t nOwnerClumps = 0, nOwnerBodies = 0, nSpheres = 0;
+    // state of the already initialised owners carried over by UpdateClumps (empty otherwise)
+    struct CarriedState {
+        size_t nClumps = 0, nBodies = 0, nBatches = 0;
+        std::vector<uint64_t> voxel;
+        std::vector<uint16_t> lx, ly, lz;
+        std::vector<float> quat, vel, omg;
+        std::vector<uint8_t> fam;
+        std::vector<uint32_t> idA, idB;
+        std::vector<uint8_t> ctype;
+        std::vector<float> wildcards;
+    };
+    CarriedState m_carry;
+    size_t m_n_init_batches = 0;
     std::vector<float> m_owner_mass;
     std::vector<float3> m_owner_moi;
     std::vector<unsigned int> m_owner_type_mark;  // clump template mark per clump owner

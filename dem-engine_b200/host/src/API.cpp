@@ -827,6 +827,21 @@ void DEMSolver::Initialize(bool dry_run) {
     std::vector<uint64_t> voxel(nO);
     std::vector<uint16_t> lx(nO), ly(nO), lz(nO);
     dem_host_encode_positions(&sp, xyz.data(), nO, voxel.data(), lx.data(), ly.data(), lz.data());
+    if (m_carry.nBodies) {
+        // UpdateClumps: the owners that were already in the simulation keep their exact state (position codes,
+        // orientation, velocities, family). Old clumps keep their indices; the external objects and meshes move up
+        // behind the newly added clumps.
+        if (nE + nMesh != m_carry.nBodies - m_carry.nClumps || nC < m_carry.nClumps)
+            fail("UpdateClumps: only clumps can be added to an initialised system.");
+        for (size_t i = 0; i < m_carry.nBodies; i++) {
+            const size_t j = (i < m_carry.nClumps) ? i : i - m_carry.nClumps + nC;
+            voxel[j] = m_carry.voxel[i]; lx[j] = m_carry.lx[i]; ly[j] = m_carry.ly[i]; lz[j] = m_carry.lz[i];
+            qw[j] = m_carry.quat[4 * i]; qx[j] = m_carry.quat[4 * i + 1]; qy[j] = m_carry.quat[4 * i + 2]; qz[j] = m_carry.quat[4 * i + 3];
+            vx[j] = m_carry.vel[3 * i]; vy[j] = m_carry.vel[3 * i + 1]; vz[j] = m_carry.vel[3 * i + 2];
+            ox[j] = m_carry.omg[3 * i]; oy[j] = m_carry.omg[3 * i + 1]; oz[j] = m_carry.omg[3 * i + 2];
+            fam[j] = m_carry.fam[i];
+        }
+    }
     check(dem_upload_analytical(ctx, (uint32_t)objOwner.size(), objOwner.data(), objType.data(), objMat.data(),
                                 objNormal.data(), rpx.data(), rpy.data(), rpz.data(), rtx.data(), rty.data(), rtz.data(),
                                 s1.data(), s2.data(), s3.data(), objMass.data()),
@@ -850,9 +865,13 @@ void DEMSolver::Initialize(bool dry_run) {
         std::vector<uint32_t> idA, idB;
         std::vector<uint8_t> type;
         std::vector<float> wc;
-        size_t sphere_base = 0;
+        size_t sphere_base = 0, batch_no = 0;
+        if (m_carry.nBodies) {  // UpdateClumps: the contacts (and their history) of the running simulation
+            idA = m_carry.idA; idB = m_carry.idB; type = m_carry.ctype; wc = m_carry.wildcards;
+        }
         for (const auto& b : m_cached_input_clump_batches) {
-            const size_t n = b->contact_pairs.size();
+            // (the contact pairs of batches that were already initialised went in then and have evolved since)
+            const size_t n = (batch_no++ < m_carry.nBatches) ? 0 : b->contact_pairs.size();
             const char* names[4] = {"delta_tan_x", "delta_tan_y", "delta_tan_z", "delta_time"};
             for (size_t i = 0; i < n; i++) {
                 idA.push_back((uint32_t)(sphere_base + b->contact_pairs[i].first));
@@ -868,6 +887,7 @@ void DEMSolver::Initialize(bool dry_run) {
         if (!idA.empty()) check(dem_set_contacts(ctx, idA.size(), idA.data(), idB.data(), type.data(), wc.data()), "dem_set_contacts");
     }
     sys_initialized = true;
+    m_n_init_batches = m_cached_input_clump_batches.size();
     if (verbosity >= INFO)
         std::cout << "DEM core initialised: " << nC << " clumps, " << nSpheres << " spheres, " << objOwner.size()
                   << " analytical components; l = " << sp.l << ", voxel bits " << sp.nvXp2 << "/" << sp.nvYp2 << "/"
@@ -876,8 +896,31 @@ void DEMSolver::Initialize(bool dry_run) {
     if (dry_run) DoDynamicsThenSync(0.0);
 }
 
+// UpdateClumps (APIPublic.cpp:2347-2390): clumps added with AddClumps after Initialize() join the running simulation.
+// The flattened arrays are rebuilt and uploaded again; owners that were already there keep their exact device state and
+// the contact list keeps its history (dem_set_contacts). New clumps are numbered right behind the existing clumps (the
+// reference numbers them behind ALL existing owners; objects are addressed through their handles here, so only the raw
+// owner ids of external objects / meshes differ).
 void DEMSolver::UpdateClumps() {
-    fail("UpdateClumps: adding clumps to an initialised system is not built yet in this core; add all clumps before Initialize().");
+    assertInit("UpdateClumps");
+    if (m_cached_input_clump_batches.size() == m_n_init_batches) {
+        if (verbosity >= WARNING) std::cerr << "WARNING! UpdateClumps is called, but no new clumps were added since the last initialization." << std::endl;
+        return;
+    }
+    CarriedState& c = m_carry;
+    c.nClumps = nOwnerClumps; c.nBodies = nOwnerBodies; c.nBatches = m_n_init_batches;
+    const size_t n = nOwnerBodies;
+    c.voxel.resize(n); c.lx.resize(n); c.ly.resize(n); c.lz.resize(n);
+    c.quat.resize(4 * n); c.vel.resize(3 * n); c.omg.resize(3 * n); c.fam.resize(n);
+    check(dem_download_owner_state(ctx, 0, (uint32_t)n, c.voxel.data(), c.lx.data(), c.ly.data(), c.lz.data(), c.quat.data(),
+                                   c.vel.data(), c.omg.data(), nullptr, nullptr, c.fam.data()), "dem_download_owner_state");
+    uint64_t nc = 0;
+    check(dem_download_contacts(ctx, 0, &nc, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_download_contacts");
+    c.idA.resize(nc); c.idB.resize(nc); c.ctype.resize(nc); c.wildcards.resize(4 * nc);
+    if (nc) check(dem_download_contacts(ctx, nc, &nc, c.idA.data(), c.idB.data(), c.ctype.data(), c.wildcards.data(), nullptr), "dem_download_contacts");
+    Initialize(false);
+    c = CarriedState();
+    DoDynamicsThenSync(0.0);  // the contact list now includes the newcomers
 }
 void DEMSolver::ClearCache() {}
 

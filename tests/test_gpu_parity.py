@@ -438,6 +438,25 @@ def test_cpp_facade_demo_scripts(built):
                          timeout=600, cwd="/tmp")
     assert out.returncode == 0, out.stdout + out.stderr
     assert "DEMdemo_ClumpBed exiting" in out.stdout
+    # AddClumps + UpdateClumps on a running simulation: the clumps already there keep their exact state and contacts
+    fill = subprocess.run([os.path.join(host, "demo", "DEMdemo_FillInBatches"), "3"], capture_output=True, text=True,
+                          env=env, timeout=600, cwd="/tmp")
+    assert fill.returncode == 0, fill.stdout + fill.stderr
+    assert "DEMdemo_FillInBatches exiting" in fill.stdout
+    fl = [l for l in fill.stdout.splitlines() if l.startswith("Batch")]
+    assert len(fl) == 3
+    counts = [int(l.split("clumps =")[1].split(",")[0]) for l in fl]
+    assert counts[0] < counts[1] < counts[2] and (counts[1] - counts[0]) == (counts[2] - counts[1])
+    for l in fl:
+        assert float(l.split("first batch moved =")[1].split(",")[0]) == 0.0    # position codes carried over exactly
+        assert float(l.split("dv =")[1].split(",")[0]) == 0.0
+        cb, ca = l.split("contacts before/after =")[1].split(",")[0].split("/")
+        # the list (touching pairs and candidates, with history) survives the update; the rebuild that follows it may
+        # prune a candidate or add the newcomers' pairs
+        assert int(ca) >= 0.98 * int(cb)
+    assert int(fl[-1].split("contacts before/after =")[1].split("/")[0]) > 100
+    t = [float(l.split("t =")[1]) for l in fl]
+    assert abs(t[0] - 0.05) < 1e-4 and abs(t[2] - 0.15) < 1e-4                  # simulated time keeps running
     drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "5"], capture_output=True, text=True, env=env,
                           timeout=600, cwd="/tmp")
     assert drum.returncode == 0, drum.stdout + drum.stderr
