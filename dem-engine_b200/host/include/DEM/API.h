@@ -428,6 +428,20 @@ class DEMSolver {
         const std::string& infilename, const std::string& clump_header = "clump_type", const std::string& qw_header = "Qw",
         const std::string& qx_header = "Qx", const std::string& qy_header = "Qy", const std::string& qz_header = "Qz");
 
+    static std::unordered_map<std::string, std::vector<float3>> ReadClumpVelFromCsv(const std::string& infilename) {
+        return ReadClumpXyzFromCsv(infilename, "clump_type", "v_x", "v_y", "v_z");
+    }
+    static std::unordered_map<std::string, std::vector<float3>> ReadClumpAngVelFromCsv(const std::string& infilename) {
+        return ReadClumpXyzFromCsv(infilename, "clump_type", "w_x", "w_y", "w_z");
+    }
+    /// All contact pairs (geometry ids) of one contact type from a contact file (API.h:1190-1211 of the reference)
+    static std::vector<std::pair<bodyID_t, bodyID_t>> ReadContactPairsFromCsv(
+        const std::string& infilename, const std::string& cntType = "SS", const std::string& cntColName = "contact_type",
+        const std::string& first_name = "geoA", const std::string& second_name = "geoB");
+    /// All contact wildcards (every column that is not a standard contact-file column) of one contact type
+    static std::unordered_map<std::string, std::vector<float>> ReadContactWildcardsFromCsv(
+        const std::string& infilename, const std::string& cntType = "SS", const std::string& cntColName = "contact_type");
+
     // raw owner access used by trackers (src/DEM/dT.cpp:3062-3130)
     float3 GetOwnerPosition(bodyID_t ownerID) const;
     float3 GetOwnerVelocity(bodyID_t ownerID) const;
@@ -509,7 +523,7 @@ class DEMSolver {
     std::vector<float> m_owner_mass;
     std::vector<float3> m_owner_moi;
     std::vector<unsigned int> m_owner_type_mark;  // clump template mark per clump owner
-    std::vector<unsigned int> m_sphere_owner;
+    std::vector<unsigned int> m_sphere_owner, m_tri_owner, m_anal_owner;
     double m_wall_time_dynamics = 0.0;
 };
 

@@ -3,6 +3,7 @@
 // APIPrivate.cpp:119-1120, dT.cpp:638-1024): owners ordered clumps, then external objects; the world bounding box is
 // one extra external object appended at Initialize(); materials pairwise-averaged unless set explicitly.
 #include <DEM/API.h>
+#include <set>
 
 #include <algorithm>
 #include <chrono>
@@ -858,6 +859,8 @@ void DEMSolver::Initialize(bool dry_run) {
     check(dem_initialize(ctx, 0), "dem_initialize");
     nOwnerClumps = nC; nOwnerBodies = nO; nSpheres = sph_owner.size();
     m_sphere_owner = sph_owner;
+    m_tri_owner = triOwner;
+    m_anal_owner = objOwner;
     if (!m_trackers.empty()) check(dem_set_option(ctx, "keep_acc", 1.0), "dem_set_option");
 
     // ---- restart: existing contacts + wildcards of the batches (Structs.h:857-882, dT.cpp:849-881) ----
@@ -1171,11 +1174,20 @@ void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float
     std::vector<float> wc(4 * n), fr(3 * n);
     if (n) check(dem_download_contacts(ctx, n, &n, a.data(), b.data(), t.data(), wc.data(), fr.data()), "dem_download_contacts");
     std::ofstream f(outfilename);
-    f << "contact_type,A,B,f_x,f_y,f_z,delta_tan_x,delta_tan_y,delta_tan_z,delta_time\n";
+    // columns as the reference writes them (dT.cpp:1700-1936): owners A/B, geometry ids geoA/geoB (sphere id; component
+    // or facet id on the B side of SA / SM contacts), force on A, then the wildcards
+    f << std::setprecision(9);
+    f << "contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x,delta_tan_y,delta_tan_z,delta_time\n";
     for (uint64_t i = 0; i < n; i++) {
         const float fm = std::sqrt(fr[3 * i] * fr[3 * i] + fr[3 * i + 1] * fr[3 * i + 1] + fr[3 * i + 2] * fr[3 * i + 2]);
         if (!no_recording_contact_forces && fm < force_thres) continue;
-        f << (t[i] == DEM_CNT_SPHERE_SPHERE ? "SS" : "SA") << "," << a[i] << "," << b[i] << "," << fr[3 * i] << "," << fr[3 * i + 1]
+        const char* tn = (t[i] == DEM_CNT_SPHERE_SPHERE) ? "SS" : (t[i] == DEM_CNT_SPHERE_MESH ? "SM" : "SA");
+        const unsigned int oa = m_sphere_owner[a[i]];
+        unsigned int ob = 0;
+        if (t[i] == DEM_CNT_SPHERE_SPHERE) ob = m_sphere_owner[b[i]];
+        else if (t[i] == DEM_CNT_SPHERE_MESH) ob = b[i] < m_tri_owner.size() ? m_tri_owner[b[i]] : 0;
+        else ob = b[i] < m_anal_owner.size() ? m_anal_owner[b[i]] : 0;
+        f << tn << "," << oa << "," << ob << "," << a[i] << "," << b[i] << "," << fr[3 * i] << "," << fr[3 * i + 1]
           << "," << fr[3 * i + 2] << "," << wc[4 * i] << "," << wc[4 * i + 1] << "," << wc[4 * i + 2] << "," << wc[4 * i + 3] << "\n";
     }
 }
@@ -1224,6 +1236,42 @@ std::unordered_map<std::string, std::vector<float4>> DEMSolver::ReadClumpQuatFro
     for (const auto& r : rows)
         out[r[ic]].push_back(make_float4((float)atof(r[ix].c_str()), (float)atof(r[iy].c_str()), (float)atof(r[iz].c_str()),
                                          (float)atof(r[iw].c_str())));
+    return out;
+}
+
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::ReadContactPairsFromCsv(const std::string& infilename,
+                                                                            const std::string& cntType,
+                                                                            const std::string& cntColName,
+                                                                            const std::string& first_name,
+                                                                            const std::string& second_name) {
+    std::vector<std::string> h;
+    auto rows = read_csv(infilename, h);
+    auto col = [&](const std::string& id) { return (size_t)(std::find(h.begin(), h.end(), id) - h.begin()); };
+    const size_t it = col(cntColName), ia = col(first_name), ib = col(second_name);
+    if (std::max(it, std::max(ia, ib)) >= h.size()) fail("ReadContactPairsFromCsv: a requested column is missing in " + infilename);
+    std::vector<std::pair<bodyID_t, bodyID_t>> pairs;
+    for (const auto& r : rows)
+        if (r[it] == cntType) pairs.emplace_back((bodyID_t)std::stoul(r[ia]), (bodyID_t)std::stoul(r[ib]));
+    return pairs;
+}
+std::unordered_map<std::string, std::vector<float>> DEMSolver::ReadContactWildcardsFromCsv(const std::string& infilename,
+                                                                                         const std::string& cntType,
+                                                                                         const std::string& cntColName) {
+    // every column that is not one of the standard contact-file columns is a wildcard (Structs.h:79-87 of the reference)
+    static const std::set<std::string> known = {"A", "B", "compA", "compB", "geoA", "geoB", "nameA", "nameB", "contact_type",
+                                                "f_x", "f_y", "f_z", "torque_x", "torque_y", "torque_z", "n_x", "n_y", "n_z",
+                                                "X", "Y", "Z", "SS", "SA", "SM"};
+    std::vector<std::string> h;
+    auto rows = read_csv(infilename, h);
+    const size_t it = (size_t)(std::find(h.begin(), h.end(), cntColName) - h.begin());
+    if (it >= h.size()) fail("ReadContactWildcardsFromCsv: column " + cntColName + " is missing in " + infilename);
+    std::unordered_map<std::string, std::vector<float>> out;
+    for (size_t c = 0; c < h.size(); c++) {
+        if (known.count(h[c])) continue;
+        auto& v = out[h[c]];
+        for (const auto& r : rows)
+            if (r[it] == cntType) v.push_back((float)atof(r[c].c_str()));
+    }
     return out;
 }
 

@@ -457,6 +457,19 @@ def test_cpp_facade_demo_scripts(built):
     assert int(fl[-1].split("contacts before/after =")[1].split("/")[0]) > 100
     t = [float(l.split("t =")[1]) for l in fl]
     assert abs(t[0] - 0.05) < 1e-4 and abs(t[2] - 0.15) < 1e-4                  # simulated time keeps running
+    # checkpoint / restart through the clump file + contact file (history wildcards) written and read by the facade
+    rs = subprocess.run([os.path.join(host, "demo", "DEMdemo_Restart")], capture_output=True, text=True, env=env,
+                        timeout=600, cwd="/tmp")
+    assert rs.returncode == 0, rs.stdout + rs.stderr
+    assert "DEMdemo_Restart exiting" in rs.stdout
+    assert int(rs.stdout.split("contact pairs read =")[1].split(",")[0]) > 100
+    assert int(rs.stdout.split("wildcard columns =")[1].split()[0]) == 4
+    dx_with = float(rs.stdout.split("restart with history   : max |dx| =")[1].split(",")[0])
+    dx_without = float(rs.stdout.split("restart without history: max |dx| =")[1].split(",")[0])
+    # positions go through 9-digit text and float; the frictional history makes the restart follow the original run
+    assert dx_with < 3e-4 and dx_with < dx_without, rs.stdout
+    with open("/tmp/DemoOutput_Restart/contacts.csv") as fh:
+        assert fh.readline().strip().startswith("contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x")
     drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "5"], capture_output=True, text=True, env=env,
                           timeout=600, cwd="/tmp")
     assert drum.returncode == 0, drum.stdout + drum.stderr
