@@ -92,6 +92,7 @@ struct ListBuf {
     uint32_t* seg_count = nullptr;
     uint32_t* count = nullptr;
     float4* force = nullptr;
+    float4* cpoint = nullptr;
 };
 
 }  // namespace
@@ -250,6 +251,7 @@ int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, 
     if ((rc = dalloc(ctx, &L.cinfo, cap))) return rc;
     if (hist && (rc = dalloc(ctx, &L.hist, cap))) return rc;
     if (force && (rc = dalloc(ctx, &L.force, cap))) return rc;
+    if (force && (rc = dalloc(ctx, &L.cpoint, cap))) return rc;
     if ((rc = dalloc(ctx, &L.seg_start, (size_t)nSph + 1))) return rc;
     if ((rc = dalloc(ctx, &L.seg_count, (size_t)nSph + 1))) return rc;
     if ((rc = dalloc(ctx, &L.count, 4))) return rc;
@@ -259,14 +261,14 @@ int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, 
     return DEM_OK;
 }
 void free_list(ListBuf& L) {
-    dfree(L.pair); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.seg_start); dfree(L.seg_count);
+    dfree(L.pair); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.cpoint); dfree(L.seg_start); dfree(L.seg_count);
     dfree(L.count);
 }
 
 ContactList as_list(const ListBuf& L) {
     ContactList c;
     c.pair = L.pair; c.cinfo = L.cinfo; c.hist = L.hist; c.seg_start = L.seg_start; c.seg_count = L.seg_count;
-    c.count = L.count; c.force = L.force;
+    c.count = L.count; c.force = L.force; c.cpoint = L.cpoint;
     return c;
 }
 
@@ -1298,14 +1300,19 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
 
 int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB, uint8_t* type,
                           float* wildcards4, float* force_xyz) {
+    return dem_download_contact_records(ctx, capacity, n_out, idA, idB, type, wildcards4, force_xyz, nullptr);
+}
+
+int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB,
+                                 uint8_t* type, float* wildcards4, float* force_xyz, float* point_xyz) {
     if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2] + ctx->n_list[3];
     *n_out = n;
-    if (!idA && !idB && !type && !wildcards4 && !force_xyz) return DEM_OK;
+    if (!idA && !idB && !type && !wildcards4 && !force_xyz && !point_xyz) return DEM_OK;
     if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
-    struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; };
+    struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; float4 p; };
     std::vector<Row> rows;
     rows.reserve(n);
     for (int kind = 0; kind < 4; kind++) {
@@ -1313,10 +1320,11 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
         const uint64_t m = ctx->n_list[kind];
         const int which = (kind == 2) ? 1 : (kind == 3 ? 2 : 0);
         std::vector<uint2> pair(m);
-        std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0));
+        std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0)), cpt(m, make_float4(0, 0, 0, 0));
         CK(cudaMemcpy(pair.data(), L.pair, sizeof(uint2) * m, cudaMemcpyDeviceToHost));
         if (L.hist) CK(cudaMemcpy(hist.data(), L.hist, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         if (L.force) CK(cudaMemcpy(frc.data(), L.force, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        if (L.cpoint && point_xyz) CK(cudaMemcpy(cpt.data(), L.cpoint, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         std::vector<uint4> ci(m);
         CK(cudaMemcpy(ci.data(), L.cinfo, sizeof(uint4) * m, cudaMemcpyDeviceToHost));
         for (uint64_t i = 0; i < m; i++) {
@@ -1330,6 +1338,7 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
             // history words of contacts that are not alive are stale by construction: report zeros
             r.h = (ci[i].w & 0x80000000u) ? hist[i] : make_float4(0, 0, 0, 0);
             r.f = frc[i];
+            r.p = cpt[i];
             if (flip) {
                 // the device lists a pair with the sphere that comes first in cell order as A; the reference reports
                 // the smaller sphere id as A. Swapping roles negates delta_tan and the force that "A feels".
@@ -1350,6 +1359,11 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
         if (type) type[i] = rows[i].t;
         if (wildcards4) { wildcards4[4 * i] = rows[i].h.x; wildcards4[4 * i + 1] = rows[i].h.y; wildcards4[4 * i + 2] = rows[i].h.z; wildcards4[4 * i + 3] = rows[i].h.w; }
         if (force_xyz) { force_xyz[3 * i] = rows[i].f.x; force_xyz[3 * i + 1] = rows[i].f.y; force_xyz[3 * i + 2] = rows[i].f.z; }
+        if (point_xyz) {  // world frame: the record is LBF-relative
+            point_xyz[3 * i] = rows[i].p.x + ctx->sp.LBF[0];
+            point_xyz[3 * i + 1] = rows[i].p.y + ctx->sp.LBF[1];
+            point_xyz[3 * i + 2] = rows[i].p.z + ctx->sp.LBF[2];
+        }
     }
     return DEM_OK;
 }

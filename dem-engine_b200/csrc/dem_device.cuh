@@ -87,6 +87,7 @@ struct ContactList {
     uint32_t* seg_count; // per sphere A: number of contacts of A
     uint32_t* count;     // device-resident number of contacts
     float4* force;       // optional per-contact force record (xyz) -- nullptr when SetNoForceRecord
+    float4* cpoint;      // ... and the contact point (world frame, LBF-relative) the force acts at
 };
 
 // Everything a kernel needs, passed by value (__grid_constant__)

@@ -47,6 +47,13 @@ __device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, ui
     e.ww = f3(w0, w1, w2);
 }
 
+// contact point in the world frame (LBF-relative), for the per-contact record: owner A's position + lever arm
+__device__ __forceinline__ float4 contact_point_world(const DevParams& P, const OwnerPos& pA, float3 armA) {
+    double X, Y, Z;
+    pos_decode(pA, P, X, Y, Z);
+    return make_float4((float)(X + (double)armA.x), (float)(Y + (double)armA.y), (float)(Z + (double)armA.z), 0.f);
+}
+
 // Division / square root of the force model.  FAST = one MUFU (reciprocal / reciprocal square root, 1 ulp) and a
 // multiply instead of the IEEE-rounded sequences (8-12 instructions and a branch each): -100 of ~1100 SASS
 // instructions, -3 % kernel time; the difference (<= 2 ulp of a force term) is far inside the fp32 parity tolerance
@@ -197,7 +204,9 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
             }
             if (RECORD) {
                 float4* const frc = inT ? P.ss.force : P.sn.force;
+                float4* const cpt = inT ? P.ss.cpoint : P.sn.cpoint;
                 frc[idx] = make_float4(force.x, force.y, force.z, 0.f);
+                cpt[idx] = contact_point_world(P, pA, armA);
             }
         } else {
             // not in touch: destroy history (FullHertzianForceModel.cu:129-136, DEMCalcForceKernels.cu:258-261)
@@ -389,7 +398,10 @@ __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevPar
                     P.sa.hist[c] = hist;
                     if (!alive) P.sa.cinfo[c].w = ci.w | 0x80000000u;
                 }
-                if (RECORD) P.sa.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+                if (RECORD) {
+                    P.sa.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+                    P.sa.cpoint[c] = contact_point_world(P, pA, armA);
+                }
             } else {
                 if (MODEL == 0 && alive) {
                     P.sa.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -517,7 +529,10 @@ __global__ void __launch_bounds__(256) k_force_st(const __grid_constant__ DevPar
                     P.st.hist[c] = hist;
                     if (!alive) P.st.cinfo[c].w = ci.w | 0x80000000u;
                 }
-                if (RECORD) P.st.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+                if (RECORD) {
+                    P.st.force[c] = make_float4(force.x, force.y, force.z, 0.f);
+                    P.st.cpoint[c] = contact_point_world(P, pA, armA);
+                }
             } else {
                 if (MODEL == 0 && alive) {
                     P.st.hist[c] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -61,6 +61,23 @@ int main(int argc, char** argv) {
     }
     DEMSim.DoDynamicsThenSync(0.05);
     printf("Final: clumps = %zu, max z = %.5f, t = %.4f\n", DEMSim.GetNumClumps(), max_z->GetValue(), DEMSim.GetSimTime());
+    // contact queries: every listed pair (owner ids, sorted by A), and the force pairs acting on the first batch
+    const auto all_pairs = DEMSim.GetContacts();
+    const auto clump_pairs = DEMSim.GetClumpContacts();
+    bool sorted = true;
+    for (size_t i = 1; i < all_pairs.size(); i++) sorted = sorted && all_pairs[i - 1].first <= all_pairs[i].first;
+    std::vector<float3> points, forces;
+    const size_t nf = tracker->GetContactForcesForAll(points, forces);
+    float3 sum = make_float3(0, 0, 0);
+    float zmin = 1e30f, zmax = -1e30f;
+    for (size_t i = 0; i < nf; i++) {
+        sum = sum + forces[i];
+        zmin = std::min(zmin, points[i].z);
+        zmax = std::max(zmax, points[i].z);
+    }
+    printf("Contacts: listed = %zu (GetNumContacts %zu), clump-clump = %zu, sorted = %d; force pairs on first batch = %zu, "
+           "sum fz = %.4f, point z range = [%.4f, %.4f]\n",
+           all_pairs.size(), DEMSim.GetNumContacts(), clump_pairs.size(), (int)sorted, nf, sum.z, zmin, zmax);
     std::cout << "DEMdemo_FillInBatches exiting..." << std::endl;
     return 0;
 }

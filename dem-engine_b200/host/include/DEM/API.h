@@ -231,6 +231,9 @@ class DEMTracker {
     unsigned int GetFamily(size_t offset = 0);
     std::vector<float3> Positions();
     std::vector<float3> Velocities();
+    /// Contact points and forces (global frame) acting on the tracked owner at `offset` / on all tracked owners
+    size_t GetContactForces(std::vector<float3>& points, std::vector<float3>& forces, size_t offset = 0);
+    size_t GetContactForcesForAll(std::vector<float3>& points, std::vector<float3>& forces);
     void SetPos(float3 pos, size_t offset = 0);
     void SetVel(float3 vel, size_t offset = 0);
     void SetAngVel(float3 angVel, size_t offset = 0);
@@ -442,6 +445,17 @@ class DEMSolver {
     static std::unordered_map<std::string, std::vector<float>> ReadContactWildcardsFromCsv(
         const std::string& infilename, const std::string& cntType = "SS", const std::string& cntColName = "contact_type");
 
+    // ---- contact queries (API.h:500-570, 912-940 of the reference). GetContacts-like methods report POTENTIAL contacts
+    // (every listed pair, like WriteContactFileIncludingPotentialPairs); owner-id pairs sorted by the A owner.
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetContacts() const;
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetContacts(const std::set<family_t>& family_to_include) const;
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetClumpContacts() const;
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetClumpContacts(const std::set<family_t>& family_to_include) const;
+    /// Every force pair (contact point in the world frame, force on the queried owner) that concerns one of the owners;
+    /// a contact between two listed owners is reported once, for the A side. Needs the force record (default on).
+    size_t GetOwnerContactForces(const std::vector<bodyID_t>& ownerIDs, std::vector<float3>& points,
+                                 std::vector<float3>& forces) const;
+
     // raw owner access used by trackers (src/DEM/dT.cpp:3062-3130)
     float3 GetOwnerPosition(bodyID_t ownerID) const;
     float3 GetOwnerVelocity(bodyID_t ownerID) const;
@@ -524,6 +538,8 @@ class DEMSolver {
     std::vector<float3> m_owner_moi;
     std::vector<unsigned int> m_owner_type_mark;  // clump template mark per clump owner
     std::vector<unsigned int> m_sphere_owner, m_tri_owner, m_anal_owner;
+    bodyID_t geoOwner(uint32_t geo, uint8_t type, bool sideB) const;
+    std::vector<std::pair<bodyID_t, bodyID_t>> contactOwnerPairs(bool clumps_only, const std::set<family_t>* fams) const;
     double m_wall_time_dynamics = 0.0;
 };
 

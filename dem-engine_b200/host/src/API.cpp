@@ -1239,6 +1239,84 @@ std::unordered_map<std::string, std::vector<float4>> DEMSolver::ReadClumpQuatFro
     return out;
 }
 
+// ---- contact queries ----
+namespace {
+struct ContactRows {
+    std::vector<uint32_t> a, b;
+    std::vector<uint8_t> t;
+    std::vector<float> force, point;
+};
+}  // namespace
+static ContactRows download_rows(DemCtx* ctx, bool with_record) {
+    ContactRows r;
+    uint64_t n = 0;
+    if (dem_download_contacts(ctx, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr) != DEM_OK) fail(dem_last_error(ctx));
+    r.a.resize(n); r.b.resize(n); r.t.resize(n);
+    if (with_record) { r.force.resize(3 * n); r.point.resize(3 * n); }
+    if (n && dem_download_contact_records(ctx, n, &n, r.a.data(), r.b.data(), r.t.data(), nullptr,
+                                          with_record ? r.force.data() : nullptr, with_record ? r.point.data() : nullptr) != DEM_OK)
+        fail(dem_last_error(ctx));
+    return r;
+}
+bodyID_t DEMSolver::geoOwner(uint32_t geo, uint8_t type, bool sideB) const {
+    if (!sideB || type == DEM_CNT_SPHERE_SPHERE) return m_sphere_owner.at(geo);
+    if (type == DEM_CNT_SPHERE_MESH) return m_tri_owner.at(geo);
+    return m_anal_owner.at(geo);
+}
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::contactOwnerPairs(bool clumps_only, const std::set<family_t>* fams) const {
+    assertInit("GetContacts");
+    const ContactRows r = download_rows(ctx, false);
+    std::vector<uint8_t> fam;
+    if (fams) {
+        fam.resize(nOwnerBodies);
+        check(dem_download_owner_state(ctx, 0, (uint32_t)nOwnerBodies, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                       nullptr, nullptr, nullptr, fam.data()), "dem_download_owner_state");
+    }
+    std::vector<std::pair<bodyID_t, bodyID_t>> out;
+    for (size_t i = 0; i < r.a.size(); i++) {
+        if (clumps_only && r.t[i] != DEM_CNT_SPHERE_SPHERE) continue;
+        const bodyID_t oa = geoOwner(r.a[i], r.t[i], false), ob = geoOwner(r.b[i], r.t[i], true);
+        if (fams && (!fams->count(fam[oa]) || !fams->count(fam[ob]))) continue;
+        out.emplace_back(oa, ob);
+    }
+    std::stable_sort(out.begin(), out.end(), [](const auto& x, const auto& y) { return x.first < y.first; });
+    return out;
+}
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetContacts() const { return contactOwnerPairs(false, nullptr); }
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetContacts(const std::set<family_t>& f) const { return contactOwnerPairs(false, &f); }
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetClumpContacts() const { return contactOwnerPairs(true, nullptr); }
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetClumpContacts(const std::set<family_t>& f) const { return contactOwnerPairs(true, &f); }
+
+size_t DEMSolver::GetOwnerContactForces(const std::vector<bodyID_t>& ownerIDs, std::vector<float3>& points,
+                                        std::vector<float3>& forces) const {
+    assertInit("GetOwnerContactForces");
+    if (no_recording_contact_forces)
+        fail("GetOwnerContactForces needs the per-contact force record; do not call SetNoForceRecord() if you query contact forces.");
+    const std::set<bodyID_t> want(ownerIDs.begin(), ownerIDs.end());
+    const ContactRows r = download_rows(ctx, true);
+    points.clear();
+    forces.clear();
+    for (size_t i = 0; i < r.a.size(); i++) {
+        const float3 F = make_float3(r.force[3 * i], r.force[3 * i + 1], r.force[3 * i + 2]);
+        if (length(F) < 1e-15f) continue;  // DEME_TINY_FLOAT: only contacts that produce force
+        const bodyID_t oa = geoOwner(r.a[i], r.t[i], false), ob = geoOwner(r.b[i], r.t[i], true);
+        const bool forA = want.count(oa) != 0;
+        if (!forA && !want.count(ob)) continue;
+        points.push_back(make_float3(r.point[3 * i], r.point[3 * i + 1], r.point[3 * i + 2]));
+        forces.push_back(forA ? F : F * -1.f);
+    }
+    return points.size();
+}
+size_t DEMTracker::GetContactForces(std::vector<float3>& points, std::vector<float3>& forces, size_t offset) {
+    return sys->GetOwnerContactForces({GetOwnerID(offset)}, points, forces);
+}
+size_t DEMTracker::GetContactForcesForAll(std::vector<float3>& points, std::vector<float3>& forces) {
+    std::vector<bodyID_t> ids;
+    const size_t n = (obj->obj_type == OWNER_TYPE::CLUMP) ? std::static_pointer_cast<DEMClumpBatch>(obj)->GetNumClumps() : 1;
+    for (size_t i = 0; i < n; i++) ids.push_back(GetOwnerID(i));
+    return sys->GetOwnerContactForces(ids, points, forces);
+}
+
 std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::ReadContactPairsFromCsv(const std::string& infilename,
                                                                             const std::string& cntType,
                                                                             const std::string& cntColName,

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
-    "dem_get_stats", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
+    "dem_get_stats", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
 ]
 
@@ -278,6 +278,18 @@ class Engine:
             self._ck(self.lib.dem_download_contacts(self.ctx, C.c_uint64(m), C.byref(n), _p(idA), _p(idB), _p(ct), _p(wc),
                                                     _p(fr) if with_force else None))
         return (idA, idB, ct, wc, fr) if with_force else (idA, idB, ct, wc)
+
+    def contact_records(self):
+        """(idA, idB, type, wildcards, force on A, contact point in the world frame) of every listed contact."""
+        n = C.c_uint64(0)
+        self._ck(self.lib.dem_download_contacts(self.ctx, C.c_uint64(0), C.byref(n), None, None, None, None, None))
+        m = int(n.value)
+        idA, idB, ct = np.zeros(m, "u4"), np.zeros(m, "u4"), np.zeros(m, "u1")
+        wc, fr, pt = np.zeros((m, 4), "f4"), np.zeros((m, 3), "f4"), np.zeros((m, 3), "f4")
+        if m:
+            self._ck(self.lib.dem_download_contact_records(self.ctx, C.c_uint64(m), C.byref(n), _p(idA), _p(idB), _p(ct),
+                                                           _p(wc), _p(fr), _p(pt)))
+        return idA, idB, ct, wc, fr, pt
 
     def stats(self):
         s = DemStats()

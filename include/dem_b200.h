@@ -196,6 +196,11 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
 /* contact list in the reference's order (type, idA, idB). Pass NULL arrays to only query the count. */
 int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n, uint32_t* idA, uint32_t* idB, uint8_t* type,
                           float* wildcards4, float* force_xyz);
+/* the same rows plus the contact point (world frame) each force acts at -- the per-contact record behind
+ * GetOwnerContactForces / DEMTracker::GetContactForces (dT.cpp:2740-2791, DEMDynamicMisc.cu:14-100) and the contact
+ * file's point columns. Needs record_contact_forces; the point is the one of the last force evaluation. */
+int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n, uint32_t* idA, uint32_t* idB,
+                                 uint8_t* type, float* wildcards4, float* force_xyz, float* point_xyz);
 int dem_get_stats(DemCtx* ctx, DemStats* out);
 
 /* reductions over clump owners (DEMInspector built-ins, AuxClasses.cpp:88-164) */

@@ -371,6 +371,70 @@ def test_do_dynamics_step_count_and_reductions(built):
     eng.close()
 
 
+@pytest.mark.parametrize("kind", ["clumps_full", "mesh_tray"])
+def test_contact_force_records_match_oracle(built, kind):
+    """The per-contact record behind GetOwnerContactForces / the contact file (force on A and the contact point in the
+    world frame, reference: contactForces + contactPointGeometryA, DEMCalcForceKernels.cu:240-256) against the oracle,
+    one step from identical state.  A contact force is k * depth^1.5 with depths of 1e-6..1e-5 m between bodies whose
+    float sphere offsets carry 1e-9 m of rounding, so a single shallow contact may differ by a few 1e-4 relative; the
+    tolerances are: every contact |dF| <= 2e-3 |F| + 1e-6 N, median relative |dF| <= 5e-5, |dP| <= 1e-6 m (the record is
+    float, LBF-relative)."""
+    po = _oracle()
+    f = scenes.flatten(_mk(kind))
+    f.record_contact_forces = 1
+    w = po.world_from_flat(f)
+    w.step(3000 - (3000 % f.cd_update_freq), cd_every=f.cd_update_freq)
+    for name in ("voxelID", "locX", "locY", "locZ", "oriQw", "oriQx", "oriQy", "oriQz", "vX", "vY", "vZ", "omgBarX",
+                 "omgBarY", "omgBarZ"):
+        getattr(f, name)[: f.nOwners] = getattr(w, name)[: f.nOwners]
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    n = w.nContacts
+    wc = np.stack([c[:n] for c in w.contactWildcards], 1)
+    eng.set_contacts(w.idGeometryA[:n], w.idGeometryB[:n], w.contactType[:n], wc)
+    x_old = w.positions_f64().copy()
+    q_old = np.stack([w.oriQw, w.oriQx, w.oriQy, w.oriQz], 1)[: f.nOwners].astype("f8").copy()
+    eng.step(1)
+    w.step(1, cd_every=f.cd_update_freq)
+    idA, idB, ct, wcg, fr, pt = eng.contact_records()
+    key = {(a, b, t): i for i, (a, b, t) in enumerate(zip(idA.tolist(), idB.tolist(), ct.tolist()))}
+    n = w.nContacts
+    F = w.contactForces[: 3 * n].reshape(-1, 3)
+    locA = w.contactPointGeometryA[: 3 * n].reshape(-1, 3).astype("f8")
+    own = np.asarray(f.ownerClumpBody)
+
+    def rot(v, q):  # applyOriQToVector3, q = (w, x, y, z)
+        qw, qx, qy, qz = q
+        return np.array([
+            (2 * (qw * qw + qx * qx) - 1) * v[0] + 2 * (qx * qy - qw * qz) * v[1] + 2 * (qx * qz + qw * qy) * v[2],
+            2 * (qx * qy + qw * qz) * v[0] + (2 * (qw * qw + qy * qy) - 1) * v[1] + 2 * (qy * qz - qw * qx) * v[2],
+            2 * (qx * qz - qw * qy) * v[0] + 2 * (qy * qz + qw * qx) * v[1] + (2 * (qw * qw + qz * qz) - 1) * v[2]])
+
+    checked = 0
+    worstF = worstP = 0.0
+    rel = []
+    for i in range(n):
+        if np.abs(F[i]).max() == 0:
+            continue
+        j = key[(int(w.idGeometryA[i]), int(w.idGeometryB[i]), int(w.contactType[i]))]
+        oa = int(own[int(w.idGeometryA[i])])
+        p_ref = x_old[oa] + rot(locA[i], q_old[oa])
+        dF = np.abs(fr[j].astype("f8") - F[i]).max()
+        dP = np.abs(pt[j].astype("f8") - p_ref).max()
+        worstF, worstP = max(worstF, dF / (np.abs(F[i]).max() + 1e-30)), max(worstP, dP)
+        rel.append(dF / (np.abs(F[i]).max() + 1e-30))
+        assert dF <= 2e-3 * np.abs(F[i]).max() + 1e-6, (i, fr[j], F[i])
+        assert dP <= 1e-6, (i, pt[j], p_ref)
+        checked += 1
+    print("%s: %d contact records checked, worst relative |dF| %.2e, worst |dP| %.2e m" % (kind, checked, worstF, worstP))
+    assert checked > (20 if kind == "clumps_full" else 3), checked
+    assert np.median(rel) <= 5e-5, np.median(rel)
+    # contacts without force report zero force
+    quiet = [key[k] for k in key if np.abs(fr[key[k]]).max() == 0]
+    assert len(quiet) + checked <= len(idA)
+    eng.close()
+
+
 def test_reduce_many_matches_single_reductions(built):
     """dem_reduce_many (one pass, one read-back) returns what the individual dem_reduce calls return."""
     f = scenes.flatten(_mk("clumps_full"))
@@ -457,6 +521,14 @@ def test_cpp_facade_demo_scripts(built):
     assert int(fl[-1].split("contacts before/after =")[1].split("/")[0]) > 100
     t = [float(l.split("t =")[1]) for l in fl]
     assert abs(t[0] - 0.05) < 1e-4 and abs(t[2] - 0.15) < 1e-4                  # simulated time keeps running
+    # contact queries of the facade (GetContacts / GetClumpContacts / DEMTracker::GetContactForcesForAll)
+    cl = [l for l in fill.stdout.splitlines() if l.startswith("Contacts:")][0]
+    listed = int(cl.split("listed =")[1].split()[0])
+    assert listed == int(cl.split("GetNumContacts")[1].split(")")[0]) and listed > 100
+    assert 0 < int(cl.split("clump-clump =")[1].split(",")[0]) <= listed and "sorted = 1" in cl
+    assert int(cl.split("force pairs on first batch =")[1].split(",")[0]) > 50
+    z0, z1 = [float(v) for v in cl.split("point z range = [")[1].split("]")[0].split(",")]
+    assert -0.6 - 1e-3 <= z0 <= z1 < 0.0                                        # contact points lie in the pile
     # checkpoint / restart through the clump file + contact file (history wildcards) written and read by the facade
     rs = subprocess.run([os.path.join(host, "demo", "DEMdemo_Restart")], capture_output=True, text=True, env=env,
                         timeout=600, cwd="/tmp")
