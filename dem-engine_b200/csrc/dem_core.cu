@@ -82,6 +82,8 @@ struct MgState {
     char* peer_block[2] = {nullptr, nullptr};  // the neighbours' blocks mapped into this process
     uint32_t* d_block_counter = nullptr;
     uint64_t epoch = 0;
+    int32_t* d_send_slot[2] = {nullptr, nullptr};  // per owner: slot in the left / right neighbour's buffer or -1
+    bool fuse_push = true;                         // the integrator stores the halo records itself (no push kernel)
 };
 
 struct ListBuf {
@@ -405,31 +407,61 @@ MgParams make_mg(const DemCtx* c) {
     return M;
 }
 
+int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches);
+
+// the next epoch of the peer-memory exchange: where my records go, where the neighbours' arrive
+MgP2P mg_next_epoch(DemCtx* ctx) {
+    MgState& g = ctx->mg;
+    MgP2P X;
+    memset(&X, 0, sizeof(X));
+    g.epoch++;
+    const size_t half = (size_t)g.cap * 80, par = (size_t)(g.epoch & 1);
+    for (int d = 0; d < 2; d++) {
+        const int peer = g.rank + (d == 0 ? -1 : 1);
+        X.has[d] = (peer >= 0 && peer < g.world) ? 1 : 0;
+        X.send_gid[d] = g.d_send_gid[d]; X.recv_gid[d] = g.d_recv_gid[d];
+        X.n_send[d] = g.n_send[d]; X.n_recv[d] = g.n_recv[d];
+        // my records for the neighbour in direction d arrive there as "from direction 1-d"
+        if (X.has[d]) {
+            X.peer_recv[d] = reinterpret_cast<int4*>(g.peer_block[d] + 256 + ((size_t)(1 - d) * 2 + par) * half);
+            X.peer_flag[d] = reinterpret_cast<unsigned long long*>(g.peer_block[d]) + (1 - d);
+        }
+        X.my_recv[d] = reinterpret_cast<const int4*>(g.p2p_block + 256 + ((size_t)d * 2 + par) * half);
+        X.my_flag[d] = reinterpret_cast<unsigned long long*>(g.p2p_block) + d;
+    }
+    X.epoch = g.epoch;
+    X.block_counter = g.d_block_counter;
+    return X;
+}
+
+// integration + per-step halo exchange.  With peer memory the integrator itself stores the halo records into the
+// neighbours' buffers (fused push); k_mg_pull, next in the stream, publishes the epoch to the neighbours, waits for
+// theirs and scatters what they stored here.
+int integrate_and_exchange(DemCtx* ctx, DevParams& P, int* launches) {
+    MgState& g = ctx->mg;
+    if (g.on && g.p2p && g.fuse_push) {
+        MgP2P X = mg_next_epoch(ctx);
+        X.publish = 1;
+        for (int d = 0; d < 2; d++) {
+            P.send_slot[d] = g.d_send_slot[d];
+            P.peer_recv[d] = X.peer_recv[d];
+        }
+        launch_integrate(P, ctx->stream);
+        *launches += launch_mg_pull(P, X, ctx->stream);
+        return DEM_OK;
+    }
+    launch_integrate(P, ctx->stream);
+    if (g.on) return mg_halo_exchange(ctx, P, nullptr, launches);
+    return DEM_OK;
+}
+
 // send the {state, spin} records of my halo owners to both neighbours and scatter theirs into my global slots
 int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches) {
     MgState& g = ctx->mg;
     cudaStream_t s = ctx->stream;
     if (g.p2p && !flag_or_null) {
         // per-step path: stores into the neighbours' memory + flags, no library call
-        MgP2P X;
-        memset(&X, 0, sizeof(X));
-        g.epoch++;
-        const size_t half = (size_t)g.cap * 80, par = (size_t)(g.epoch & 1);
-        for (int d = 0; d < 2; d++) {
-            const int peer = g.rank + (d == 0 ? -1 : 1);
-            X.has[d] = (peer >= 0 && peer < g.world) ? 1 : 0;
-            X.send_gid[d] = g.d_send_gid[d]; X.recv_gid[d] = g.d_recv_gid[d];
-            X.n_send[d] = g.n_send[d]; X.n_recv[d] = g.n_recv[d];
-            // my records for the neighbour in direction d arrive there as "from direction 1-d"
-            if (X.has[d]) {
-                X.peer_recv[d] = reinterpret_cast<int4*>(g.peer_block[d] + 256 + ((size_t)(1 - d) * 2 + par) * half);
-                X.peer_flag[d] = reinterpret_cast<unsigned long long*>(g.peer_block[d]) + (1 - d);
-            }
-            X.my_recv[d] = reinterpret_cast<const int4*>(g.p2p_block + 256 + ((size_t)d * 2 + par) * half);
-            X.my_flag[d] = reinterpret_cast<unsigned long long*>(g.p2p_block) + d;
-        }
-        X.epoch = g.epoch;
-        X.block_counter = g.d_block_counter;
+        const MgP2P X = mg_next_epoch(ctx);
         *launches += launch_mg_push(P, X, s);
         *launches += launch_mg_pull(P, X, s);
         return DEM_OK;
@@ -477,6 +509,7 @@ int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches) {
     NC(g_nccl.GroupEnd());
     int rc = mg_halo_exchange(ctx, P, g.d_flag, launches);
     if (rc) return rc;
+    for (int d = 0; d < 2; d++) *launches += launch_mg_send_map(g.d_send_gid[d], g.n_send[d], g.d_send_slot[d], ctx->nOwners, s);
     *launches += launch_mg_active_list(P, M, s);
     *launches += launch_mg_active_spheres(P, M, s);
     CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_counts, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
@@ -641,14 +674,13 @@ int enqueue_step(DemCtx* ctx) {
     } else {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
-    launch_integrate(P, ctx->stream);
-    ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
-    if (ctx->mg.on) {
+    {
         int l = 0;
-        int rc = mg_halo_exchange(ctx, P, nullptr, &l);
+        int rc = integrate_and_exchange(ctx, P, &l);
         if (rc) return rc;
         ctx->launches += l;
     }
+    ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
     ctx->n_steps++;
     ctx->steps_since_rebuild++;
@@ -765,7 +797,7 @@ int dem_ctx_destroy(DemCtx* ctx) {
     if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
     {
         MgState& g = ctx->mg;
-        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_act_sph); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
+        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_act_sph); dfree(g.d_send_slot[0]); dfree(g.d_send_slot[1]); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
         for (int d = 0; d < 2; d++)
             if (g.peer_block[d]) cudaIpcCloseMemHandle(g.peer_block[d]);
         if (g.p2p_block) cudaFree(g.p2p_block);
@@ -1476,6 +1508,11 @@ int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]
     if ((rc = dalloc(ctx, &g.d_flag, nO))) return rc;
     if ((rc = dalloc(ctx, &g.d_active_list, nO))) return rc;
     if ((rc = dalloc(ctx, &g.d_act_sph, std::max<uint32_t>(ctx->nSpheres, 1u)))) return rc;
+    for (int d = 0; d < 2; d++) {
+        if ((rc = dalloc(ctx, &g.d_send_slot[d], std::max<uint32_t>(nO, 1u)))) return rc;
+        CK(cudaMemset(g.d_send_slot[d], 0xff, sizeof(int32_t) * std::max<uint32_t>(nO, 1u)));
+    }
+    if (getenv("DEM_B200_NO_FUSED_PUSH")) g.fuse_push = false;
     if ((rc = dalloc(ctx, &g.d_counts, 8))) return rc;
     if ((rc = dalloc(ctx, &g.d_allcounts, 8 * (size_t)world))) return rc;
     for (int d = 0; d < 2; d++) {
@@ -1671,14 +1708,28 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
             if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
             if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
             CK(cudaEventRecord(e[3], s));
-            launch_integrate(P, s);
-            ctx->maxvel_slot ^= 1;
-            CK(cudaEventRecord(e[4], s));
-            if (ctx->mg.on) {
-                int l = 0;
-                int rc = mg_halo_exchange(ctx, P, nullptr, &l);
-                if (rc) { rc_out = rc; break; }
-                ctx->launches += l;
+            if (ctx->mg.on && ctx->mg.p2p && ctx->mg.fuse_push) {
+                // fused push: the integrator and the exchange cannot be timed apart; [5] is the pull (incl. waiting)
+                MgP2P X = mg_next_epoch(ctx);
+                X.publish = 1;
+                for (int d = 0; d < 2; d++) {
+                    P.send_slot[d] = ctx->mg.d_send_slot[d];
+                    P.peer_recv[d] = X.peer_recv[d];
+                }
+                launch_integrate(P, s);
+                ctx->maxvel_slot ^= 1;
+                CK(cudaEventRecord(e[4], s));
+                ctx->launches += launch_mg_pull(P, X, s);
+            } else {
+                launch_integrate(P, s);
+                ctx->maxvel_slot ^= 1;
+                CK(cudaEventRecord(e[4], s));
+                if (ctx->mg.on) {
+                    int l = 0;
+                    int rc = mg_halo_exchange(ctx, P, nullptr, &l);
+                    if (rc) { rc_out = rc; break; }
+                    ctx->launches += l;
+                }
             }
             CK(cudaEventRecord(e[5], s));
             ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);

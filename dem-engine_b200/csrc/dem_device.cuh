@@ -117,6 +117,11 @@ struct DevParams {
     const uint8_t* active;
     const uint32_t* active_list;
     uint32_t nActive;
+    // ... and the per-step halo push fused into the integrator: per owner the slot of its {state, spin} record in the
+    // left / right neighbour's receive buffer (-1 = not in that halo; nullptr = no fused push) and the neighbours'
+    // buffers (this epoch's half, in THEIR memory)
+    const int32_t* send_slot[2];
+    int4* peer_recv[2];
     // spheres / templates
     const uint2* sph;
     const float4* comp;      // {relx, rely, relz, radius}

@@ -79,6 +79,7 @@ struct MgParams {
 int launch_mg_classify(const DevParams& P, const MgParams& M, cudaStream_t s);
 int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* buf, cudaStream_t s);
 int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s);
+int launch_mg_send_map(const uint32_t* gid, uint32_t n, int32_t* slot, uint32_t nOwners, cudaStream_t s);
 int launch_mg_active_spheres(const DevParams& P, const MgParams& M, cudaStream_t s);
 int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s);
 
@@ -94,6 +95,7 @@ struct MgP2P {
     unsigned long long epoch;      // 1, 2, 3, ... one per exchange
     uint32_t* block_counter;       // last-block detection of the push kernel
     int has[2];                    // neighbour present on the left / right
+    int publish;                   // k_mg_pull publishes my epoch first (the integrator stored the records: fused push)
 };
 int launch_mg_push(const DevParams& P, const MgP2P& X, cudaStream_t s);
 int launch_mg_pull(const DevParams& P, const MgP2P& X, cudaStream_t s);

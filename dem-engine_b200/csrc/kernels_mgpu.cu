@@ -146,6 +146,13 @@ __global__ void __launch_bounds__(256) k_mg_push(const __grid_constant__ DevPara
 }
 
 __global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevParams P, const __grid_constant__ MgP2P X) {
+    if (X.publish && blockIdx.x == 0 && threadIdx.x == 0) {
+        // fused push: the integrator (the previous kernel in this stream) stored my halo records into the neighbours'
+        // buffers; tell them the epoch is complete BEFORE waiting for theirs (no rank waits for another's wait)
+        __threadfence_system();
+        if (X.has[0]) st_release_sys(X.peer_flag[0], X.epoch);
+        if (X.has[1]) st_release_sys(X.peer_flag[1], X.epoch);
+    }
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         for (int d = 0; d < 2; d++) {
@@ -196,6 +203,17 @@ int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const 
     k_mg_unpack<<<(n * 5u + 255) / 256, 256, 0, s>>>(P, gid, n, reinterpret_cast<const int4*>(buf), flag);
     return 1;
 }
+// owner id -> slot in the neighbour's receive buffer (the integrator's fused push looks its owners up here)
+__global__ void __launch_bounds__(256) k_mg_send_map(const uint32_t* __restrict__ gid, uint32_t n, int32_t* __restrict__ slot) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) slot[gid[i]] = (int32_t)i;
+}
+int launch_mg_send_map(const uint32_t* gid, uint32_t n, int32_t* slot, uint32_t nOwners, cudaStream_t s) {
+    cudaMemsetAsync(slot, 0xff, sizeof(int32_t) * (size_t)nOwners, s);
+    if (n) k_mg_send_map<<<(n + 255) / 256, 256, 0, s>>>(gid, n, slot);
+    return 1;
+}
+
 int launch_mg_active_spheres(const DevParams& P, const MgParams& M, cudaStream_t s) {
     if (P.nSpheres) k_mg_active_spheres<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, M);
     return 1;

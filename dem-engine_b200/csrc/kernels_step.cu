@@ -658,6 +658,25 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
           __uint_as_float(p2), __uint_as_float(p3), q.x, q.y, q.z, q.w);
     st_v8(dst + 8, v[0], v[1], v[2], e.mass, ww.x, ww.y, ww.z, 0.f);
     P.spin[o] = make_float4(w[0], w[1], w[2], spin.w);
+    // multi-GPU: an own owner inside a neighbour's halo goes straight into that neighbour's receive buffer over NVLink
+    // (the record layout of k_mg_push: four 16-byte words of state, one of spin).  No fence here: the stores are
+    // complete when this kernel is, and k_mg_pull -- next in the stream -- publishes the epoch to the neighbours.
+    if (P.send_slot[0]) {
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            const int32_t slot = P.send_slot[d][o];
+            if (slot >= 0) {
+                // 80-byte records are only 16-byte aligned: five 128-bit stores
+                float4* r = reinterpret_cast<float4*>(P.peer_recv[d] + (size_t)slot * 5u);
+                r[0] = make_float4(__uint_as_float((uint32_t)(pos.voxel & 0xffffffffull)),
+                                   __uint_as_float((uint32_t)(pos.voxel >> 32)), __uint_as_float(p2), __uint_as_float(p3));
+                r[1] = q;
+                r[2] = make_float4(v[0], v[1], v[2], e.mass);
+                r[3] = make_float4(ww.x, ww.y, ww.z, 0.f);
+                r[4] = make_float4(w[0], w[1], w[2], spin.w);
+            }
+        }
+    }
     // per-owner acceleration read-out (ContactAcc / ContactAngAccLocal trackers), only when requested
     if (P.acc_out) st_v8(P.acc_out + o, acc[0], acc[1], acc[2], 0.f, ang[0], ang[1], ang[2], 0.f);
     // consume the wrench: the accumulator is zero again for the next step's reductions
