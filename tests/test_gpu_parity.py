@@ -206,6 +206,77 @@ def test_drum_config4_small_matches_oracle(built):
     eng.close()
 
 
+def test_config2_full_size_properties(built):
+    """BASELINE config 2 at FULL size (1M three-sphere clumps, Hertz-Mindlin with history), size-independent properties:
+      * no touching pair is missing: every pair of spheres of different clumps that overlaps RIGHT NOW (k-d tree over a
+        slab of the bed, positions recomputed in double on the host) is in the device's contact list, although the
+        list was built up to cd_update_freq - 1 steps earlier (that is what the margin is for);
+      * history is non-zero only for listed contacts whose spheres overlap or overlapped (alive => in the list), and
+        the pairs are unique;
+      * orientations stay unit quaternions, the state stays finite, nothing leaves the box;
+      * the bed loses energy (CoR < 1, friction) apart from what gravity feeds in."""
+    from scipy.spatial import cKDTree
+    sc = scenes.config2_clumps(100, 100, 100, scale=0.005, h=5e-6, cd_update_freq=20, seed=4150, mu=0.2, Crr=0.0, spacing=2.7)
+    n = len(sc.clump_type)
+    rng = np.random.RandomState(3)
+    sc.clump_vel = (rng.normal(size=(n, 3)) * 0.8 + np.array([0.0, 0.0, -1.0])).astype("f4")
+    f = scenes.flatten(sc)
+    assert f.nClumps == 1000000 and f.nSpheres == 3000000
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    ke0 = eng.reduce(demb200.REDUCE_KINETIC_ENERGY)
+    nsteps = 2010                      # ends 10 steps after a rebuild: the list in use is 10 steps old
+    eng.step(nsteps)
+    st = eng.stats()
+    assert st.n_contacts_ss_touching > 100000, st.n_contacts_ss_touching
+    own = eng.owner_state()
+    q = own["oriQ"][: f.nClumps].astype("f8")
+    assert np.isfinite(own["vel"]).all() and np.isfinite(q).all()
+    assert np.abs(np.sqrt((q * q).sum(1)) - 1.0).max() < 1e-5
+    pos = eng.positions()[: f.nClumps]
+    lo, hi = np.asarray(f.userBoxMin, "f8"), np.asarray(f.userBoxMax, "f8")
+    assert (pos[:, :2] > lo[:2] - 1e-3).all() and (pos[:, :2] < hi[:2] + 1e-3).all() and (pos[:, 2] > lo[2] - 1e-3).all()
+    # work done by gravity is bounded by m g * (fall of the centre of mass); the bed must not have gained more than that
+    ke1 = eng.reduce(demb200.REDUCE_KINETIC_ENERGY)
+    m = float(f.MassProperties[0]) if np.ndim(f.MassProperties) == 1 else float(np.asarray(f.MassProperties).ravel()[0])
+    z0 = np.asarray(sc.clump_xyz, "f8")[:, 2]
+    fed = m * 9.81 * float((z0 - pos[:, 2]).sum())
+    assert ke1 < ke0 + max(fed, 0.0) + 1e-9 * ke0, (ke0, ke1, fed)
+
+    # ---- sphere centres in double for a slab of the bed ----
+    sel = np.nonzero(np.abs(pos[:, 0] - np.median(pos[:, 0])) < 0.03)[0]      # ~45 k clumps
+    qw, qx, qy, qz = (q[sel, k] for k in range(4))
+    rel = np.stack([np.asarray(f.CDRelPosX, "f8"), np.asarray(f.CDRelPosY, "f8"), np.asarray(f.CDRelPosZ, "f8")], 1)[:3]
+    rad = np.asarray(f.Radii, "f8")[:3]
+    centres, sph_id = [], []
+    for k in range(3):
+        v = rel[k]
+        rx = (2 * (qw * qw + qx * qx) - 1) * v[0] + 2 * (qx * qy - qw * qz) * v[1] + 2 * (qx * qz + qw * qy) * v[2]
+        ry = 2 * (qx * qy + qw * qz) * v[0] + (2 * (qw * qw + qy * qy) - 1) * v[1] + 2 * (qy * qz - qw * qx) * v[2]
+        rz = 2 * (qx * qz - qw * qy) * v[0] + 2 * (qy * qz + qw * qx) * v[1] + (2 * (qw * qw + qz * qz) - 1) * v[2]
+        centres.append(pos[sel] + np.stack([rx, ry, rz], 1))
+        sph_id.append(3 * sel + k)
+    centres, sph_id = np.concatenate(centres), np.concatenate(sph_id)
+    r_of = np.tile(rad, 1)[sph_id % 3]
+    tree = cKDTree(centres)
+    cand = tree.query_pairs(2.0 * rad.max(), output_type="ndarray")
+    d = np.linalg.norm(centres[cand[:, 0]] - centres[cand[:, 1]], axis=1)
+    touching = (d < r_of[cand[:, 0]] + r_of[cand[:, 1]] - 1e-9) & (sph_id[cand[:, 0]] // 3 != sph_id[cand[:, 1]] // 3)
+    a, b = sph_id[cand[touching, 0]], sph_id[cand[touching, 1]]
+    a, b = np.minimum(a, b).astype("u8"), np.maximum(a, b).astype("u8")
+    brute = np.unique(a * np.uint64(1 << 32) + b)
+    assert len(brute) > 2000, len(brute)
+    idA, idB, ct, wc = eng.contacts()
+    ss = ct == 1
+    listed = idA[ss].astype("u8") * np.uint64(1 << 32) + idB[ss].astype("u8")
+    assert len(np.unique(listed)) == len(listed)                                 # every pair listed once
+    missing = np.setdiff1d(brute, listed)
+    print("config 2 full size: %d touching pairs in the slab (k-d tree), %d listed pairs in all, %d missing" % (
+        len(brute), len(listed), len(missing)))
+    assert len(missing) == 0
+    eng.close()
+
+
 def test_drum_config4_full_size_properties(built):
     """BASELINE config 4 at full size (500k polydisperse clumps + ~50k facets): size-independent properties."""
     sc = scenes.config4_drum(500000, 50000, omega=3.0, init_vel=(0.0, 0.0, -1.5), spacing=2.7)
