@@ -193,6 +193,16 @@ struct DemCtx {
     uint64_t n_list[4] = {0, 0, 0, 0};
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
+    // CUDA graph of one whole contact-list cycle (cd_update_freq steps) for launch-bound scenes: [list buffer][max|v| slot]
+    struct CycleGraph {
+        cudaGraphExec_t exec = nullptr;
+        DevParams P0;        // the parameters the captured kernels were launched with (first step): validity check
+        uint32_t L = 0;      // steps in the graph
+        int cfg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    };
+    CycleGraph graphs[2][2];
+    int use_graph = 2;       // 0 off, 1 on, 2 auto (on for scenes small enough to be launch-bound)
+    uint64_t graph_launches = 0;
     int ctas_per_sm = 4;
     int fast_math = 1;  // sphere--sphere force kernel: MUFU reciprocal / rsqrt instead of IEEE division / sqrt
     int fast_encode = 1;
@@ -646,11 +656,8 @@ int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
     return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
 }
 
-int enqueue_step(DemCtx* ctx) {
-    if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
-        int rc = rebuild(ctx);
-        if (rc) return rc;
-    }
+// the kernels of ONE step on ctx->stream (+ side stream); flips the max|v| slot. No bookkeeping, no rebuild.
+int launch_step(DemCtx* ctx) {
     DevParams P = make_params(ctx);
     const int model = (int)ctx->sp.force_model;
     const bool rec = ctx->sp.record_contact_forces != 0;
@@ -682,9 +689,92 @@ int enqueue_step(DemCtx* ctx) {
     }
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
+    return DEM_OK;
+}
+
+int enqueue_step(DemCtx* ctx) {
+    if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+        int rc = rebuild(ctx);
+        if (rc) return rc;
+    }
+    int rc = launch_step(ctx);
+    if (rc) return rc;
     ctx->n_steps++;
     ctx->steps_since_rebuild++;
     ctx->sim_time += (double)ctx->sp.h;
+    return DEM_OK;
+}
+
+// ---- CUDA graph of one contact-list cycle -------------------------------------------------------------------------
+// Between two rebuilds every step launches the same kernels with the same parameters (only the max|v| slot alternates),
+// so a scene whose step is shorter than the host's launch path (three to four launches, two event records and two
+// stream waits: ~20 us) is launch bound.  The whole cycle of cd_update_freq steps is captured once per contact-list
+// buffer and replayed with ONE cudaGraphLaunch; it stays valid for as long as the kernel parameters are byte-identical.
+void graph_config(const DemCtx* ctx, int cfg[8]) {
+    cfg[0] = (int)ctx->sp.force_model; cfg[1] = (int)ctx->sp.record_contact_forces; cfg[2] = ctx->ctas_per_sm;
+    cfg[3] = ctx->fast_math; cfg[4] = ctx->overlap_walls; cfg[5] = (int)ctx->nAnal; cfg[6] = (int)ctx->nTri; cfg[7] = ctx->sa_grid;
+}
+bool graph_wanted(const DemCtx* ctx) {
+    if (ctx->mg.on || ctx->use_graph == 0) return false;
+    if (ctx->use_graph == 1) return true;
+    return ctx->nSpheres <= 262144u;  // beyond that a step outlasts its launches
+}
+void graph_drop(DemCtx* ctx) {
+    for (auto& row : ctx->graphs)
+        for (auto& g : row) {
+            if (g.exec) cudaGraphExecDestroy(g.exec);
+            g.exec = nullptr;
+            g.L = 0;
+        }
+}
+// run one full cycle (L = cd_update_freq steps, starting right after a rebuild) through the graph; returns DEM_OK and
+// sets *done on success, leaves *done false when the caller should fall back to plain launches
+int run_cycle_graph(DemCtx* ctx, bool* done) {
+    *done = false;
+    const uint32_t L = ctx->sp.cd_update_freq;
+    DemCtx::CycleGraph& G = ctx->graphs[ctx->cur][ctx->maxvel_slot];
+    const DevParams P = make_params(ctx);
+    int cfg[8];
+    graph_config(ctx, cfg);
+    if (G.exec && (G.L != L || memcmp(&G.P0, &P, sizeof(P)) != 0 || memcmp(G.cfg, cfg, sizeof(cfg)) != 0)) {
+        cudaGraphExecDestroy(G.exec);
+        G.exec = nullptr;
+    }
+    if (!G.exec) {
+        const int slot0 = ctx->maxvel_slot;
+        const uint64_t launches0 = ctx->launches;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            ctx->use_graph = 0;
+            return DEM_OK;
+        }
+        int rc = DEM_OK;
+        for (uint32_t i = 0; i < L && rc == DEM_OK; i++) rc = launch_step(ctx);
+        const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        ctx->maxvel_slot = slot0;
+        ctx->launches = launches0;
+        if (rc != DEM_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            G.exec = nullptr;
+            ctx->use_graph = 0;  // not worth retrying every cycle
+            ctx->err.clear();
+            return DEM_OK;
+        }
+        cudaGraphDestroy(graph);
+        G.P0 = P;
+        G.L = L;
+        memcpy(G.cfg, cfg, sizeof(cfg));
+    }
+    CK(cudaGraphLaunch(G.exec, ctx->stream));
+    ctx->graph_launches++;
+    ctx->maxvel_slot ^= (int)(L & 1u);
+    ctx->launches += (uint64_t)L * (2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0));
+    ctx->n_steps += L;
+    ctx->steps_since_rebuild += L;
+    for (uint32_t i = 0; i < L; i++) ctx->sim_time += (double)ctx->sp.h;
+    *done = true;
     return DEM_OK;
 }
 
@@ -807,6 +897,7 @@ int dem_ctx_destroy(DemCtx* ctx) {
             if (g.d_recvbuf[d]) cudaFree(g.d_recvbuf[d]);
         }
     }
+    graph_drop(ctx);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
@@ -827,6 +918,7 @@ int dem_set_stream(DemCtx* ctx, void* cuda_stream) {
     if (!ctx) return DEM_ERR_INVALID;
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    graph_drop(ctx);
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
     return DEM_OK;
@@ -1195,9 +1287,24 @@ int dem_rebuild_contacts(DemCtx* ctx) {
 int dem_step_async(DemCtx* ctx, uint64_t n_steps) {
     if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
     CK(cudaSetDevice(ctx->device));
-    for (uint64_t i = 0; i < n_steps; i++) {
+    uint64_t i = 0;
+    while (i < n_steps) {
+        if (graph_wanted(ctx) && n_steps - i >= ctx->sp.cd_update_freq && ctx->sp.cd_update_freq >= 2) {
+            // a whole contact-list cycle ahead: rebuild now if one is due, then replay the cycle's graph
+            if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+                int rc = rebuild(ctx);
+                if (rc) return rc;
+            }
+            if (ctx->steps_since_rebuild == 0) {
+                bool done = false;
+                int rc = run_cycle_graph(ctx, &done);
+                if (rc) return rc;
+                if (done) { i += ctx->sp.cd_update_freq; continue; }
+            }
+        }
         int rc = enqueue_step(ctx);
         if (rc) return rc;
+        i++;
     }
     CK(cudaGetLastError());
     return DEM_OK;
@@ -1605,6 +1712,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     const std::string n(name);
     if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
     else if (n == "fast_math") ctx->fast_math = value != 0.0;
+    else if (n == "use_graph") { ctx->use_graph = (int)value; if (ctx->use_graph == 0) graph_drop(ctx); }
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
     else if (n == "sort_mode") ctx->sort_mode = (int)value;

@@ -65,6 +65,8 @@ int main() {
     pB->SetExistingContactWildcards(wildcards);
     auto trB = B.Track(pB);
     B.Initialize();
+    // what the restarted solver now holds (every listed pair): the test compares it with contacts.csv entry by entry
+    B.WriteContactFile(dir / "contacts_restarted.csv", -1.0f);
 
     // ---- a third one restarted WITHOUT the contact history, for scale ----
     std::shared_ptr<DEMMaterial> mat3;

