@@ -1,0 +1,51 @@
+"""CPU-only: the facade's checkpoint readers (ReadClump*FromCsv, ReadContactPairsFromCsv,
+ReadContactWildcardsFromCsv -- reference API.h:1124-1250) parse the files the facade / the reference write."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "dem-engine_b200", "host")
+
+
+def test_checkpoint_readers_round_trip(built, tmp_path):
+    subprocess.run(["make", "-C", HOST], check=True, stdout=subprocess.DEVNULL)
+    exe = str(tmp_path / "csv_readers_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "host", "csv_readers_check.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "dem-engine_b200"), "-ldeme_b200", "-ldemcore",
+                    "-Wl,-rpath," + os.path.join(ROOT, "dem-engine_b200")], check=True)
+    rng = np.random.RandomState(5)
+    n = 7
+    types = ["three_sphere" if i % 3 else "ball" for i in range(n)]
+    cols = rng.normal(size=(n, 13)).astype("f4")
+    clumps = tmp_path / "clumps.csv"
+    with open(clumps, "w") as f:
+        # the column order of WriteClumpFile (XYZ, QUAT, clump_type, VEL, ANG_VEL, FAMILY)
+        f.write("X,Y,Z,Qw,Qx,Qy,Qz,clump_type,v_x,v_y,v_z,w_x,w_y,w_z,family\n")
+        for i in range(n):
+            c = cols[i]
+            f.write(",".join("%.9g" % v for v in c[:7]) + "," + types[i] + "," + ",".join("%.9g" % v for v in c[7:]) + ",0\n")
+    contacts = tmp_path / "contacts.csv"
+    rows = [("SS", 0, 2, 1, 7, rng.normal(size=7).astype("f4")), ("SA", 1, 9, 4, 0, rng.normal(size=7).astype("f4")),
+            ("SS", 1, 3, 5, 11, rng.normal(size=7).astype("f4")), ("SM", 2, 10, 8, 3, rng.normal(size=7).astype("f4"))]
+    with open(contacts, "w") as f:
+        f.write("contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x,delta_tan_y,delta_tan_z,delta_time\n")
+        for t, a, b, ga, gb, v in rows:
+            f.write("%s,%d,%d,%d,%d," % (t, a, b, ga, gb) + ",".join("%.9g" % x for x in v) + "\n")
+    out = subprocess.run([exe, str(clumps), str(contacts)], capture_output=True, text=True, check=True).stdout.splitlines()
+    got = {}
+    for line in out:
+        p = line.split()
+        if p[0] == "clump":
+            got.setdefault(p[1], []).append([float(x) for x in p[3:]])
+    for name in ("three_sphere", "ball"):
+        want = cols[[i for i in range(n) if types[i] == name]]
+        assert np.allclose(np.array(got[name], "f4"), want, rtol=1e-6, atol=0), name
+    assert "pairs 2 wildcards 4" in out and "sa_pairs 1" in out
+    pr = [l.split() for l in out if l.startswith("pair ")]
+    ss = [r for r in rows if r[0] == "SS"]
+    for l, r in zip(pr, ss):
+        assert (int(l[1]), int(l[2])) == (r[3], r[4])                       # geometry ids, not owner ids
+        assert np.allclose([float(x) for x in l[3:]], r[5][3:], rtol=1e-6)   # the four history wildcards
