@@ -1,7 +1,11 @@
 // DEM/utils/Samplers.hpp -- point samplers demo scripts use to generate input
-// (counterpart of src/DEM/utils/Samplers.hpp of the reference: HCPSampler :498-533, GridSampler :536-573).
+// (counterpart of src/DEM/utils/Samplers.hpp of the reference: PDSampler :271-467, HCPSampler :498-533,
+// GridSampler :536-573, DEMCylSurfSampler :616-641).
 #pragma once
 #include <cmath>
+#include <cstdint>
+#include <random>
+#include <unordered_map>
 #include <vector>
 
 #include "../HostSideHelpers.hpp"
@@ -104,6 +108,106 @@ class GridSampler : public Sampler {
 };
 
 /// DEMBoxGridSampler(BoxCenter, HalfDims, GridSizeX, GridSizeY, GridSizeZ)
+// Poisson-disk sampler: a maximal random set of points no two of which are closer than the separation (what
+// DEMdemo_BallDrop / Repose / Centrifuge use to fill a volume without a lattice).  Dart throwing with a background grid
+// (cell = separation / sqrt(3), so a cell holds at most one point): every accepted point spawns up to
+// `pointsPerIteration` candidates in the shell [separation, 2 separation] around it; a candidate is kept if it lies in
+// the volume and no point of the 5x5x5 cell neighbourhood is too close.  Seeded with 0 like the reference's
+// (Samplers.hpp:279-281), so a script generates the same cloud every run.
+class PDSampler : public Sampler {
+  public:
+    explicit PDSampler(float separation, int pointsPerIteration = 30)
+        : Sampler(separation), m_ppi(pointsPerIteration), m_rng(0) {}
+    void SetRandomEngineSeed(unsigned int seed) { m_rng.seed(seed); }
+
+  protected:
+    std::vector<float3> Sample(int volume) override {
+        std::vector<float3> pts;
+        const float r = m_separation;
+        if (!(r > 0.f)) return pts;
+        const float cell = r / std::sqrt(3.0f);
+        // bounding box of the volume (half extents per axis)
+        const float3 half = (volume == 1)   ? make_float3(m_size.x, m_size.x, m_size.z)
+                            : (volume == 2) ? make_float3(m_size.x, m_size.y, m_size.y)
+                            : (volume == 3) ? make_float3(m_size.x, m_size.y, m_size.x)
+                                            : m_size;
+        const float3 lo = m_center - half;
+        auto key = [&](const float3& p) -> uint64_t {
+            const uint64_t ix = (uint64_t)std::floor((p.x - lo.x) / cell + 2.f), iy = (uint64_t)std::floor((p.y - lo.y) / cell + 2.f),
+                           iz = (uint64_t)std::floor((p.z - lo.z) / cell + 2.f);
+            return ix | (iy << 21) | (iz << 42);
+        };
+        std::unordered_map<uint64_t, uint32_t> grid;
+        auto too_close = [&](const float3& p) {
+            const uint64_t k = key(p);
+            const int64_t ix = (int64_t)(k & 0x1fffff), iy = (int64_t)((k >> 21) & 0x1fffff), iz = (int64_t)(k >> 42);
+            for (int64_t dz = -2; dz <= 2; dz++)
+                for (int64_t dy = -2; dy <= 2; dy++)
+                    for (int64_t dx = -2; dx <= 2; dx++) {
+                        const int64_t x = ix + dx, y = iy + dy, z = iz + dz;
+                        if (x < 0 || y < 0 || z < 0) continue;
+                        auto it = grid.find((uint64_t)x | ((uint64_t)y << 21) | ((uint64_t)z << 42));
+                        if (it == grid.end()) continue;
+                        const float3 d = pts[it->second] - p;
+                        if (dot(d, d) < r * r) return true;
+                    }
+            return false;
+        };
+        std::uniform_real_distribution<float> U(0.f, 1.f);
+        // first point: the centre of the volume (always inside)
+        pts.push_back(m_center);
+        grid[key(m_center)] = 0;
+        std::vector<uint32_t> active(1, 0u);
+        while (!active.empty()) {
+            const size_t pick = (size_t)(U(m_rng) * (float)active.size()) % active.size();
+            const float3 base = pts[active[pick]];
+            bool spawned = false;
+            for (int t = 0; t < m_ppi; t++) {
+                // uniform direction, radius uniform in volume over the shell [r, 2r]
+                const float cz = 2.f * U(m_rng) - 1.f, phi = 6.2831853f * U(m_rng);
+                const float sz = std::sqrt(std::max(0.f, 1.f - cz * cz));
+                const float rad = r * std::cbrt(1.f + 7.f * U(m_rng));
+                const float3 c = base + make_float3(sz * std::cos(phi), sz * std::sin(phi), cz) * rad;
+                if (!accept(volume, c) || too_close(c)) continue;
+                grid[key(c)] = (uint32_t)pts.size();
+                active.push_back((uint32_t)pts.size());
+                pts.push_back(c);
+                spawned = true;
+            }
+            if (!spawned) {
+                active[pick] = active.back();
+                active.pop_back();
+            }
+        }
+        return pts;
+    }
+
+  private:
+    int m_ppi;
+    std::mt19937 m_rng;
+};
+
+/// Points on the mantle of a cylinder, rows along the axis spaced `spacing * ParticleRad` apart (a shell of particles
+/// that resembles a cylindrical surface; Samplers.hpp:616-641 of the reference)
+inline std::vector<float3> DEMCylSurfSampler(float3 CylCenter, float3 CylAxis, float CylRad, float CylHeight,
+                                             float ParticleRad, float spacing = 1.2f) {
+    std::vector<float3> points;
+    const float step = spacing * ParticleRad;
+    const unsigned int rows = (unsigned int)(2.0 * 3.14159265358979323846 * CylRad / step);
+    if (rows == 0 || !(step > 0.f)) return points;
+    const float3 a = normalize(CylAxis);
+    // any unit vector perpendicular to the axis, and the one completing the frame
+    const float3 helper = (std::fabs(a.x) < 0.9f) ? make_float3(1, 0, 0) : make_float3(0, 1, 0);
+    const float3 u = normalize(cross(a, helper)), v = cross(a, u);
+    for (unsigned int i = 0; i < rows; i++) {
+        const float ang = 6.28318530717958647692f * (float)i / (float)rows;
+        const float3 radial = u * std::cos(ang) + v * std::sin(ang);
+        const float3 start = CylCenter + a * (CylHeight / 2.f) + radial * CylRad;
+        for (float d = 0.f; d <= CylHeight; d += step) points.push_back(start - a * d);
+    }
+    return points;
+}
+
 inline std::vector<float3> DEMBoxGridSampler(float3 BoxCenter, float3 HalfDims, float GridSizeX, float GridSizeY = -1.0,
                                              float GridSizeZ = -1.0) {
     if (GridSizeY < 0) GridSizeY = GridSizeX;

@@ -49,3 +49,46 @@ def test_checkpoint_readers_round_trip(built, tmp_path):
     for l, r in zip(pr, ss):
         assert (int(l[1]), int(l[2])) == (r[3], r[4])                       # geometry ids, not owner ids
         assert np.allclose([float(x) for x in l[3:]], r[5][3:], rtol=1e-6)   # the four history wildcards
+
+
+def test_point_samplers(built, tmp_path):
+    """Samplers the demo scripts generate their input with (reference src/DEM/utils/Samplers.hpp): Poisson-disk
+    (minimum distance respected, maximal, reproducible), HCP / grid lattices, cylinder-surface shell."""
+    from scipy.spatial import cKDTree
+    exe = str(tmp_path / "samplers_check")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "host", "samplers_check.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "dem-engine_b200"), "-ldeme_b200", "-ldemcore",
+                    "-Wl,-rpath," + os.path.join(ROOT, "dem-engine_b200")], check=True)
+    lines = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines()
+    sets, i = {}, 0
+    while i < len(lines):
+        name, n = lines[i].split()
+        n = int(n)
+        sets[name] = np.array([[float(x) for x in l.split()] for l in lines[i + 1:i + 1 + n]], "f8").reshape(n, 3)
+        i += 1 + n
+
+    def min_dist(p):
+        d, _ = cKDTree(p).query(p, k=2)
+        return d[:, 1].min()
+
+    pd = sets["pd_box"]
+    c, h = np.array([0.1, -0.2, 0.3]), np.array([0.5, 0.4, 0.3])
+    assert (np.abs(pd - c) <= h + 1e-6).all()
+    assert min_dist(pd) >= 0.05 * (1 - 1e-5)
+    # maximal: random probes inside the box all have a sample within the separation (a few per mille may sit in a gap
+    # the dart throwing did not reach); density of a maximal Poisson-disk set is 0.65-0.9 points per separation^3
+    probes = c + (np.random.RandomState(0).rand(4000, 3) * 2 - 1) * (h - 0.05)
+    d, _ = cKDTree(pd).query(probes)
+    assert (d < 0.05).mean() > 0.99
+    dens = len(pd) * 0.05 ** 3 / np.prod(2 * h)
+    assert 0.5 < dens < 1.0, dens
+    assert np.array_equal(pd, sets["pd_box_again"])                       # seeded with 0: reproducible
+    cyl = sets["pd_cylz"]
+    assert (np.hypot(cyl[:, 0], cyl[:, 1]) <= 0.3 + 1e-6).all() and (np.abs(cyl[:, 2]) <= 0.2 + 1e-6).all()
+    assert min_dist(cyl) >= 0.04 * (1 - 1e-5) and len(cyl) > 1000
+    assert abs(min_dist(sets["hcp_box"]) - 0.05) < 1e-5 and abs(min_dist(sets["grid_box"]) - 0.05) < 1e-5
+    assert len(sets["hcp_box"]) > len(sets["grid_box"])                    # HCP packs denser than the cubic grid
+    shell = sets["cyl_surf"]
+    assert np.allclose(np.hypot(shell[:, 0], shell[:, 1]), 0.5, atol=1e-5)
+    assert shell[:, 2].min() >= 0.5 - 1e-5 and shell[:, 2].max() <= 1.5 + 1e-5 and len(shell) > 1000
