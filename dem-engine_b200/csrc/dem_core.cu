@@ -1113,6 +1113,28 @@ int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, 
     return DEM_OK;
 }
 
+int dem_update_triangle_nodes(DemCtx* ctx, uint32_t first, uint32_t n, const float* node1, const float* node2,
+                              const float* node3) {
+    // SetTriNodeRelPos / UpdateTriNodeRelPos (API.h:489-491, dT.cpp:3135-3158): the facets' owner-frame node positions
+    // change (a deforming mesh driven by a co-simulated FEA solver); the mesh owner's pose is untouched
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if (n == 0) return DEM_OK;
+    if (!node1 || !node2 || !node3) return DEM_ERR_INVALID;
+    if ((uint64_t)first + n > ctx->nTri) return fail(ctx, DEM_ERR_INVALID, "triangle range out of bounds");
+    CK(cudaSetDevice(ctx->device));
+    std::vector<float4>* dst[3] = {&ctx->h_tri1, &ctx->h_tri2, &ctx->h_tri3};
+    const float* src[3] = {node1, node2, node3};
+    for (int k = 0; k < 3; k++) {
+        for (uint32_t t = 0; t < n; t++)
+            (*dst[k])[first + t] = make_float4(src[k][3 * t], src[k][3 * t + 1], src[k][3 * t + 2], 0.f);
+        // stream-ordered: steps already enqueued see the old shape, steps enqueued after this call the new one
+        CK(cudaMemcpyAsync(ctx->d_tri[k] + first, dst[k]->data() + first, sizeof(float4) * n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));  // (the host vectors may be modified again right away)
+    ctx->need_rebuild = true;                // sphere--facet candidates were found for the old shape
+    return DEM_OK;
+}
+
 int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if (!ctx) return DEM_ERR_INVALID;
     if (!ctx->params_set) return fail(ctx, DEM_ERR_INVALID, "dem_set_params must precede dem_initialize");

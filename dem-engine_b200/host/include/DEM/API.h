@@ -164,6 +164,7 @@ class DEMExternObj : public DEMInitializer {
 class DEMMeshConnected : public DEMInitializer {
   public:
     size_t nTri = 0;
+    size_t tri_first = 0;  // id of this mesh's first facet in the flattened facet arrays (set by Initialize)
     std::vector<float3> m_vertices;
     std::vector<float3> m_normals;
     std::vector<float3> m_UV;
@@ -231,6 +232,12 @@ class DEMTracker {
     unsigned int GetFamily(size_t offset = 0);
     std::vector<float3> Positions();
     std::vector<float3> Velocities();
+    /// Deforming mesh (AuxClasses.h:288-313 of the reference): replace / displace the tracked mesh's nodes (mesh frame;
+    /// one entry per node), read the nodes back in the global frame, get the mesh handle
+    void UpdateMesh(const std::vector<float3>& new_nodes);
+    void UpdateMeshByIncrement(const std::vector<float3>& deformation);
+    std::vector<float3> GetMeshNodesGlobal();
+    std::shared_ptr<DEMMeshConnected> GetMesh();
     /// Contact points and forces (global frame) acting on the tracked owner at `offset` / on all tracked owners
     size_t GetContactForces(std::vector<float3>& points, std::vector<float3>& forces, size_t offset = 0);
     size_t GetContactForcesForAll(std::vector<float3>& points, std::vector<float3>& forces);
@@ -444,6 +451,12 @@ class DEMSolver {
     /// All contact wildcards (every column that is not a standard contact-file column) of one contact type
     static std::unordered_map<std::string, std::vector<float>> ReadContactWildcardsFromCsv(
         const std::string& infilename, const std::string& cntType = "SS", const std::string& cntColName = "contact_type");
+
+    // ---- deforming meshes (API.h:489-498 of the reference): new / incremented node positions in the mesh frame
+    void SetTriNodeRelPos(size_t owner, size_t triID, const std::vector<float3>& new_nodes);
+    void UpdateTriNodeRelPos(size_t owner, size_t triID, const std::vector<float3>& updates);
+    std::vector<float3> GetMeshNodesGlobal(bodyID_t ownerID);
+    std::shared_ptr<DEMMeshConnected> GetCachedMesh(bodyID_t ownerID);
 
     // ---- contact queries (API.h:500-570, 912-940 of the reference). GetContacts-like methods report POTENTIAL contacts
     // (every listed pair, like WriteContactFileIncludingPotentialPairs); owner-id pairs sorted by the A owner.

@@ -810,6 +810,7 @@ void DEMSolver::Initialize(bool dry_run) {
         if (me->nTri > 0 && !me->isMaterialSet)
             fail("A meshed object is loaded but does not have associated material.\nPlease assign material to meshes via SetMaterial.");
         me->owner = (bodyID_t)o;
+        me->tri_first = triOwner.size();
         xyz[3 * o] = me->init_pos.x; xyz[3 * o + 1] = me->init_pos.y; xyz[3 * o + 2] = me->init_pos.z;
         qw[o] = me->init_oriQ.w; qx[o] = me->init_oriQ.x; qy[o] = me->init_oriQ.y; qz[o] = me->init_oriQ.z;
         fam[o] = (uint8_t)me->family_code;
@@ -1238,6 +1239,66 @@ std::unordered_map<std::string, std::vector<float4>> DEMSolver::ReadClumpQuatFro
                                          (float)atof(r[iw].c_str())));
     return out;
 }
+
+// ---- deforming meshes ----
+std::shared_ptr<DEMMeshConnected> DEMSolver::GetCachedMesh(bodyID_t ownerID) {
+    for (auto& m : m_cached_meshes)
+        if (m->owner == ownerID) return m;
+    fail("Owner " + std::to_string(ownerID) + " is not a mesh.");
+}
+void DEMSolver::SetTriNodeRelPos(size_t owner, size_t triID, const std::vector<float3>& new_nodes) {
+    assertInit("SetTriNodeRelPos");
+    auto me = GetCachedMesh((bodyID_t)owner);
+    if (new_nodes.size() != me->m_vertices.size())
+        fail("SetTriNodeRelPos: the mesh has " + std::to_string(me->m_vertices.size()) + " nodes, but " +
+             std::to_string(new_nodes.size()) + " new node positions were given.");
+    if (triID != me->tri_first) fail("SetTriNodeRelPos: triID must be the id of the mesh's first facet.");
+    me->m_vertices = new_nodes;
+    std::vector<float> n1, n2, n3;
+    n1.reserve(3 * me->nTri); n2.reserve(3 * me->nTri); n3.reserve(3 * me->nTri);
+    for (size_t t = 0; t < me->nTri; t++) {
+        const int3 fc = me->m_face_v_indices[t];
+        const float3 a = new_nodes[fc.x], b = new_nodes[fc.y], c = new_nodes[fc.z];
+        n1.insert(n1.end(), {a.x, a.y, a.z});
+        n2.insert(n2.end(), {b.x, b.y, b.z});
+        n3.insert(n3.end(), {c.x, c.y, c.z});
+    }
+    check(dem_update_triangle_nodes(ctx, (uint32_t)me->tri_first, (uint32_t)me->nTri, n1.data(), n2.data(), n3.data()),
+          "dem_update_triangle_nodes");
+}
+void DEMSolver::UpdateTriNodeRelPos(size_t owner, size_t triID, const std::vector<float3>& updates) {
+    assertInit("UpdateTriNodeRelPos");
+    auto me = GetCachedMesh((bodyID_t)owner);
+    if (updates.size() != me->m_vertices.size())
+        fail("UpdateTriNodeRelPos: the mesh has " + std::to_string(me->m_vertices.size()) + " nodes, but " +
+             std::to_string(updates.size()) + " increments were given.");
+    std::vector<float3> moved = me->m_vertices;
+    for (size_t i = 0; i < moved.size(); i++) moved[i] += updates[i];
+    SetTriNodeRelPos(owner, triID, moved);
+}
+std::vector<float3> DEMSolver::GetMeshNodesGlobal(bodyID_t ownerID) {
+    assertInit("GetMeshNodesGlobal");
+    auto me = GetCachedMesh(ownerID);
+    const float3 pos = GetOwnerPosition(ownerID);
+    const float4 q = GetOwnerOriQ(ownerID);
+    std::vector<float3> out(me->m_vertices.size());
+    for (size_t i = 0; i < out.size(); i++) out[i] = Rotate(me->m_vertices[i], q) + pos;
+    return out;
+}
+static std::shared_ptr<DEMMeshConnected> tracked_mesh(const std::shared_ptr<DEMInitializer>& obj, const char* what) {
+    if (obj->obj_type != OWNER_TYPE::MESH) fail(std::string(what) + " is only callable when this tracker is tracking a mesh.");
+    return std::static_pointer_cast<DEMMeshConnected>(obj);
+}
+void DEMTracker::UpdateMesh(const std::vector<float3>& new_nodes) {
+    auto me = tracked_mesh(obj, "UpdateMesh");
+    sys->SetTriNodeRelPos(me->owner, me->tri_first, new_nodes);
+}
+void DEMTracker::UpdateMeshByIncrement(const std::vector<float3>& deformation) {
+    auto me = tracked_mesh(obj, "UpdateMeshByIncrement");
+    sys->UpdateTriNodeRelPos(me->owner, me->tri_first, deformation);
+}
+std::vector<float3> DEMTracker::GetMeshNodesGlobal() { return sys->GetMeshNodesGlobal(tracked_mesh(obj, "GetMeshNodesGlobal")->owner); }
+std::shared_ptr<DEMMeshConnected> DEMTracker::GetMesh() { return tracked_mesh(obj, "GetMesh"); }
 
 // ---- contact queries ----
 namespace {

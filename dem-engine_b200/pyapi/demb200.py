@@ -21,7 +21,7 @@ EXPORTED_SYMBOLS = [
     "dem_abi_version", "dem_host_figure_out_nv", "dem_host_box_domain", "dem_host_encode_positions",
     "dem_ctx_create", "dem_ctx_destroy", "dem_last_error", "dem_set_stream", "dem_set_params",
     "dem_upload_templates", "dem_upload_materials", "dem_upload_analytical", "dem_upload_families",
-    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
+    "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_update_triangle_nodes", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
@@ -218,6 +218,11 @@ class Engine:
         ctype = np.ascontiguousarray(ctype, "u1")
         wc = None if wildcards4 is None else np.ascontiguousarray(wildcards4, "f4")
         self._ck(self.lib.dem_set_contacts(self.ctx, C.c_uint64(len(idA)), _p(idA), _p(idB), _p(ctype), _p(wc)))
+
+    def update_triangle_nodes(self, first, n1, n2, n3):
+        """New owner-frame node positions (n x 3 each) of the facets starting at `first` (deforming mesh)."""
+        n1, n2, n3 = (np.ascontiguousarray(a, "f4").reshape(-1, 3) for a in (n1, n2, n3))
+        self._ck(self.lib.dem_update_triangle_nodes(self.ctx, C.c_uint32(first), C.c_uint32(len(n1)), _p(n1), _p(n2), _p(n3)))
 
     def update_families(self, masks, extra, presc):
         presc = np.ascontiguousarray(presc)

@@ -162,6 +162,13 @@ int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClum
 /* triangles of mesh owners (preprocessTriangleObjs; nodes in owner frame, xyz interleaved) */
 int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, const float* node1,
                          const float* node2, const float* node3, const uint16_t* triMaterialOffset);
+/* Deforming mesh: new owner-frame node positions of the facets [first, first+n) (3 floats per node, one array per
+ * facet corner). Replaces SetTriNodeRelPos / UpdateTriNodeRelPos (src/DEM/API.h:489-491, dT.cpp:3135-3158), what
+ * DEMTracker::UpdateMesh / UpdateMeshByIncrement call (AuxClasses.cpp:681-693). Stream-ordered; the contact list is
+ * rebuilt before the next step. */
+int dem_update_triangle_nodes(DemCtx* ctx, uint32_t first, uint32_t n, const float* node1, const float* node2,
+                              const float* node3);
+
 /* allocateGPUArrays + initGPUArrays (dT.cpp:409, kT.cpp:579). contact_capacity==0 -> automatic */
 int dem_initialize(DemCtx* ctx, uint64_t contact_capacity);
 /* restart: SetExistingContacts / SetExistingContactWildcards (Structs.h:857-882, dT.cpp:849-881) */

@@ -186,6 +186,47 @@ def test_candidate_list_is_superset_of_brute_force(built, kind):
     eng.close()
 
 
+def test_deforming_mesh_matches_oracle(built):
+    """Deformable-mesh node update (dem_update_triangle_nodes; SetTriNodeRelPos, reference API.h:489-491): the spinning
+    box of facets around the clumps shrinks by 3 % in mid-run, identically on the device and in the oracle; the
+    trajectories must keep agreeing (same yardstick as test_trajectory_matches_oracle), the facets must have pushed
+    the clumps inwards, and the update must reject a bad range."""
+    po = _oracle()
+    f = scenes.flatten(_mk("mesh_tray"))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    w = po.world_from_flat(f)
+    wp = w.copy()  # the oracle with velocities perturbed by 1e-6: the round-off sensitivity yardstick (module docstring)
+    for name in ("vX", "vY", "vZ", "omgBarX", "omgBarY", "omgBarZ"):
+        a = getattr(wp, name)
+        a[:] = (a.astype("f8") * (1.0 + 1e-6)).astype("f4")
+    nC = f.nClumps
+    nodes = [np.asarray(getattr(f, k), "f4").reshape(-1, 3) * np.float32(0.97) for k in ("relPosNode1", "relPosNode2", "relPosNode3")]
+    done, r0 = 0, None
+    for cp in (500, 1000, 1250, 1500, 2000):
+        eng.step(cp - done)
+        w.step(cp - done, cd_every=f.cd_update_freq)
+        wp.step(cp - done, cd_every=f.cd_update_freq)
+        done = cp
+        pw = w.positions_f64()[:nC]
+        sens_x = np.abs(wp.positions_f64()[:nC] - pw).max()
+        err_x = np.abs(eng.positions()[:nC] - pw).max()
+        print("deforming mesh step %d: |dx| %.2e (sensitivity %.2e)" % (cp, err_x, sens_x))
+        assert err_x <= 10 * sens_x + 1e-7, (cp, err_x, sens_x)
+        if cp == 1000:  # (a multiple of cd_update_freq: device and oracle both rebuild their lists at the next step)
+            r0 = np.abs(eng.positions()[:nC] - eng.positions()[f.nOwners - 1]).max()
+            eng.update_triangle_nodes(0, *nodes)
+            for world in (w, wp):
+                for k, n in zip(("relPosNode1", "relPosNode2", "relPosNode3"), nodes):
+                    getattr(world, k)[: 3 * f.nTri] = n.ravel()
+    assert eng.stats().n_contacts_st > 5
+    r1 = np.abs(eng.positions()[:nC] - eng.positions()[f.nOwners - 1]).max()
+    print("deforming mesh: farthest clump from the box centre %.5f -> %.5f m" % (r0, r1))
+    with pytest.raises(demb200.DemError):
+        eng.update_triangle_nodes(f.nTri - 1, nodes[0][:2], nodes[1][:2], nodes[2][:2])
+    eng.close()
+
+
 def test_drum_config4_small_matches_oracle(built):
     """BASELINE config 4 at oracle-sized scale: polydisperse clumps in a rotating drum of triangles."""
     po = _oracle()
