@@ -1,16 +1,19 @@
 // dem_device.cuh -- device data layout and math helpers of the B200-native DEM core.
 //
 // HBM layout (see DESIGN.md "Data layout"):
-//   owners  : four 16-byte records per owner, each fetched with ONE 128-bit load
-//             pos  {u64 voxelID; u16 locX,locY,locZ; u8 family; u8 flags}   (the reference's voxelID/locX/locY/locZ/
-//                   familyID arrays, src/DEM/Defines.h:272-280, packed)
-//             quat {w,x,y,z}     vel {vx,vy,vz,mass}     omg {WORLD-frame angular velocity, unused}
+//   owners  : one 64-byte record per owner, fetched with TWO 256-bit loads (one per 32-byte sector)
+//             sector 0: pos  {u64 voxelID; u16 locX,locY,locZ; u8 family; u8 flags}   (the reference's voxelID / locX /
+//                            locY / locZ / familyID arrays, src/DEM/Defines.h:272-280, packed) + quat {w,x,y,z}
+//             sector 1: vel {vx,vy,vz,mass} + omg {WORLD-frame angular velocity, unused}
 //           + a 16-byte spin record {body-frame omgBar xyz, bits(inertiaPropOffset)} that only the integrator streams
-//           + one 32-byte wrench accumulator {Fx,Fy,Fz,0 | Tx,Ty,Tz,0} (force in world frame, torque in body frame),
-//             the target of 128-bit vector reductions (red.global.add.v4.f32, sm_90+).
+//           + one 32-byte wrench accumulator {Fx,Fy,Fz,0 | Tx,Ty,Tz,0}, force AND torque in the world frame (the
+//             integrator rotates the summed torque into the body frame once per owner), the target of 128-bit vector
+//             reductions (red.global.add.v4.f32, sm_90+).
 //   spheres : uint2 {owner, comp | material<<16}
-//   contacts: uint2 {geoA, geoB} + float4 history {delta_tan_xyz, delta_time} per list (sphere-sphere,
-//             sphere-analytical, sphere-triangle are separate lists, so no per-contact type byte is stored).
+//   contacts: four lists (sphere-sphere in touch, sphere-sphere candidates, sphere-analytical, sphere-triangle: no
+//             per-contact type byte), each a compiled 16-byte record {ownerA, ownerB|obj, compA|compB<<16,
+//             matpair|alive<<31} + float4 history {delta_tan_xyz, delta_time} (+ uint2 {geoA, geoB} for the rebuild, and
+//             the optional force / contact-point record).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -36,7 +39,7 @@ static_assert(sizeof(OwnerState) == 64, "OwnerState must be 64 bytes");
 
 struct __align__(32) Wrench {
     float4 f;  // world-frame force sum
-    float4 t;  // body-frame torque sum
+    float4 t;  // world-frame torque sum
 };
 
 // per material pair, precomputed on the host exactly as matProxy2ContactParam<float> and the beta expression of
