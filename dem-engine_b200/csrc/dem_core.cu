@@ -1622,6 +1622,10 @@ int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float 
 int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]) {
     if (!ctx || !ctx->initialized || !unique_id || world < 1 || rank < 0 || rank >= world) return DEM_ERR_INVALID;
     if (world == 1) return DEM_OK;
+    // Wall owners (analytical boundaries) are replicated on every rank, which is exact while they are fixed or follow a
+    // prescribed motion; a mesh additionally needs its facets partitioned with the slabs, which is not built yet.
+    if (ctx->nTri > 0)
+        return fail(ctx, DEM_ERR_INVALID, "the slab decomposition does not cover triangle meshes yet: run scenes with meshes on one GPU");
     if (!g_nccl.load()) return fail(ctx, DEM_ERR_INVALID, "NCCL (libnccl.so.2) could not be loaded");
     CK(cudaSetDevice(ctx->device));
     MgState& g = ctx->mg;

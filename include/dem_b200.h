@@ -222,7 +222,10 @@ int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]);
 /* ---- multi-GPU: slab decomposition with ghost-owner halo exchange over NCCL (no counterpart in the reference, whose
  * "multi-GPU" is the kT/dT thread pair of APIPublic.cpp:35-48).  One process and one context per GPU; every rank
  * uploads the SAME complete input, then calls dem_mgpu_init with the id rank 0 created.  From then on each rank
- * integrates the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step. */
+ * integrates the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step
+ * (NVLink peer stores + flags when the GPUs can map each other's memory, ncclSend/ncclRecv otherwise).  Wall owners
+ * (analytical boundaries) are replicated: exact while they are fixed or prescribed.  Scenes with triangle meshes are
+ * refused (DEM_ERR_INVALID): their facets are not partitioned yet. */
 int dem_mgpu_unique_id(uint8_t out[128]);
 int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]);
 /* out: [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right [4] halo bytes sent per step
