@@ -29,6 +29,8 @@
 
 struct DemCtx;
 
+#include "utils/Expression.hpp"
+
 namespace deme {
 
 typedef unsigned int bodyID_t;
@@ -411,6 +413,8 @@ class DEMSolver {
     void AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z);
     void ChangeFamily(unsigned int ID_from, unsigned int ID_to);
     void ChangeFamilyWhen(unsigned int, unsigned int, const std::string&);
+    /// Value of a prescription string at time t (what the integrator will be given); exposed for scripts and tests
+    static double EvaluatePrescription(const std::string& expression, double t) { return TimeExpression(expression).Eval(t); }
     void SetFamilyExtraMargin(unsigned int N, float extra_size);
 
     void Initialize(bool dry_run = true);
@@ -495,7 +499,16 @@ class DEMSolver {
         bool hasLinVel[3] = {false, false, false}, hasRotVel[3] = {false, false, false}, hasLinPos[3] = {false, false, false};
         bool hasAcc[3] = {false, false, false}, hasAngAcc[3] = {false, false, false};
         float linVel[3] = {0, 0, 0}, rotVel[3] = {0, 0, 0}, linPos[3] = {0, 0, 0}, acc[3] = {0, 0, 0}, angAcc[3] = {0, 0, 0};
+        // time-dependent components (nullptr = constant): re-evaluated before every step (DEM/utils/Expression.hpp)
+        std::shared_ptr<TimeExpression> eLinVel[3], eRotVel[3], eLinPos[3], eAcc[3], eAngAcc[3];
+        bool TimeDependent() const {
+            for (int k = 0; k < 3; k++)
+                if (eLinVel[k] || eRotVel[k] || eLinPos[k] || eAcc[k] || eAngAcc[k]) return true;
+            return false;
+        }
     };
+    bool anyTimeDependentPrescription() const;
+    double simTimeOrZero() const;
     void check(int rc, const char* what) const;
     void uploadFamilies();
     void assertInit(const char* what) const;

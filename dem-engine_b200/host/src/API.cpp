@@ -22,18 +22,17 @@ std::string g_data_path = "";
 
 [[noreturn]] void fail(const std::string& msg) { throw std::runtime_error(msg); }
 
-bool parse_constant(const std::string& s, float& out) {
-    // "none" means unspecified; anything else must be a numeric constant (no runtime compilation of user code here)
+// "none" means unspecified. Anything else is an expression of the simulation time t (DEM/utils/Expression.hpp): a
+// constant is folded here; a time-dependent one is kept in `expr` and re-evaluated before every step.
+bool parse_prescription(const std::string& s, double t_now, float& out, std::shared_ptr<TimeExpression>& expr) {
     std::string t;
     for (char c : s)
         if (!isspace((unsigned char)c)) t.push_back(c);
+    expr.reset();
     if (t.empty() || t == "none") return false;
-    char* end = nullptr;
-    const double v = std::strtod(t.c_str(), &end);
-    if (end == t.c_str() || *end != '\0')
-        fail("Prescription \"" + s + "\" is not a numeric constant. This B200-native core compiles its kernels ahead "
-             "of time; only constant prescriptions are supported.");
-    out = (float)v;
+    auto e = std::make_shared<TimeExpression>(s);
+    out = (float)e->Eval(t_now);
+    if (!e->IsConstant()) expr = e;
     return true;
 }
 
@@ -564,7 +563,7 @@ void DEMSolver::SetFamilyPrescribedLinVel(unsigned int ID, const std::string& ve
     const std::string* s[3] = {&velX, &velY, &velZ};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_constant(*s[k], v)) { p.hasLinVel[k] = true; p.linVel[k] = v; p.linVelP[k] = dictate; }
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinVel[k])) { p.hasLinVel[k] = true; p.linVel[k] = v; p.linVelP[k] = dictate; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -576,7 +575,7 @@ void DEMSolver::SetFamilyPrescribedAngVel(unsigned int ID, const std::string& ve
     const std::string* s[3] = {&velX, &velY, &velZ};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_constant(*s[k], v)) { p.hasRotVel[k] = true; p.rotVel[k] = v; p.rotVelP[k] = dictate; }
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eRotVel[k])) { p.hasRotVel[k] = true; p.rotVel[k] = v; p.rotVelP[k] = dictate; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -588,7 +587,7 @@ void DEMSolver::SetFamilyPrescribedPosition(unsigned int ID, const std::string& 
     const std::string* s[3] = {&X, &Y, &Z};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_constant(*s[k], v)) { p.hasLinPos[k] = true; p.linPos[k] = v; p.linPosP[k] = dictate; }
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinPos[k])) { p.hasLinPos[k] = true; p.linPos[k] = v; p.linPosP[k] = dictate; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -598,7 +597,7 @@ void DEMSolver::AddFamilyPrescribedAcc(unsigned int ID, const std::string& X, co
     const std::string* s[3] = {&X, &Y, &Z};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_constant(*s[k], v)) { p.hasAcc[k] = true; p.acc[k] = v; }
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eAcc[k])) { p.hasAcc[k] = true; p.acc[k] = v; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -608,7 +607,7 @@ void DEMSolver::AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X,
     const std::string* s[3] = {&X, &Y, &Z};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_constant(*s[k], v)) { p.hasAngAcc[k] = true; p.angAcc[k] = v; }
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eAngAcc[k])) { p.hasAngAcc[k] = true; p.angAcc[k] = v; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -648,6 +647,19 @@ void DEMSolver::uploadFamilies() {
         d.rotPosPrescribed = p.rotPosP;
     };
     put(RESERVED_FAMILY_NUM, fixed);
+    // time-dependent components take their value at the time the next step starts from (the reference hands the
+    // integrator simParams->timeElapsed, which it advances after the step: dT.cpp:2463)
+    const double t_now = simTimeOrZero();
+    for (auto& kv : m_prescriptions) {
+        Prescription& p = kv.second;
+        for (int k = 0; k < 3; k++) {
+            if (p.eLinVel[k]) p.linVel[k] = (float)p.eLinVel[k]->Eval(t_now);
+            if (p.eRotVel[k]) p.rotVel[k] = (float)p.eRotVel[k]->Eval(t_now);
+            if (p.eLinPos[k]) p.linPos[k] = (float)p.eLinPos[k]->Eval(t_now);
+            if (p.eAcc[k]) p.acc[k] = (float)p.eAcc[k]->Eval(t_now);
+            if (p.eAngAcc[k]) p.angAcc[k] = (float)p.eAngAcc[k]->Eval(t_now);
+        }
+    }
     for (const auto& kv : m_prescriptions) put(kv.first, kv.second);
     check(dem_upload_families(ctx, m_family_masks.data(), extra.data(), pr.data()), "dem_upload_families");
 }
@@ -928,9 +940,28 @@ void DEMSolver::UpdateClumps() {
 }
 void DEMSolver::ClearCache() {}
 
+bool DEMSolver::anyTimeDependentPrescription() const {
+    for (const auto& kv : m_prescriptions)
+        if (kv.second.TimeDependent()) return true;
+    return false;
+}
+double DEMSolver::simTimeOrZero() const { return sys_initialized ? GetSimTime() : 0.0; }
+
 void DEMSolver::DoDynamics(double thisCallDuration) {
     assertInit("DoDynamics");
     const auto t0 = std::chrono::high_resolution_clock::now();
+    if (thisCallDuration > 0.0 && anyTimeDependentPrescription()) {
+        // prescriptions that depend on t: refresh the family tables before every step (one stream-ordered 56 KB copy,
+        // no synchronisation), same step count as the reference's loop (dT.cpp:2401)
+        const double h = (double)(float)m_ts_size;
+        uint64_t n = 0;
+        for (double cycle = 0.0; cycle < thisCallDuration; cycle += h) n++;
+        for (uint64_t i = 0; i < n; i++) {
+            uploadFamilies();
+            check(dem_step_async(ctx, 1), "DoDynamics");
+        }
+        check(dem_sync(ctx), "DoDynamics");
+    } else
     check(dem_do_dynamics(ctx, thisCallDuration), "DoDynamics");
     m_wall_time_dynamics += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
 }

@@ -679,6 +679,18 @@ def test_cpp_facade_demo_scripts(built):
     assert dropped <= max(3, len(orig) // 25), (dropped, len(orig))
     with open("/tmp/DemoOutput_Restart/contacts.csv") as fh:
         assert fh.readline().strip().startswith("contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x")
+    # prescribed motion given as expressions of t (parsed and evaluated by the facade, refreshed before every step)
+    sh = subprocess.run([os.path.join(host, "demo", "DEMdemo_Shaker")], capture_output=True, text=True, env=env,
+                        timeout=600, cwd="/tmp")
+    assert sh.returncode == 0, sh.stdout + sh.stderr
+    assert "DEMdemo_Shaker exiting" in sh.stdout
+    frames = [l for l in sh.stdout.splitlines() if l.startswith("Frame")]
+    assert len(frames) == 4
+    for l in frames:
+        got = [float(v) for v in l.split("plate = (")[1].split(")")[0].split(",")]
+        exp = [float(v) for v in l.split("expected = (")[1].split(")")[0].split(",")]
+        assert np.abs(np.array(got) - np.array(exp)).max() < 2e-7, l        # float position read-out of a 0.1 m value
+    assert abs(float(frames[-1].split("plate = (")[1].split(",")[0]) - 0.5 * 0.006) < 5e-5   # the drift started at t = 4 ms
     drum = subprocess.run([os.path.join(host, "demo", "DEMdemo_MeshDrum"), "5"], capture_output=True, text=True, env=env,
                           timeout=600, cwd="/tmp")
     assert drum.returncode == 0, drum.stdout + drum.stderr

@@ -92,3 +92,41 @@ def test_point_samplers(built, tmp_path):
     shell = sets["cyl_surf"]
     assert np.allclose(np.hypot(shell[:, 0], shell[:, 1]), 0.5, atol=1e-5)
     assert shell[:, 2].min() >= 0.5 - 1e-5 and shell[:, 2].max() <= 1.5 + 1e-5 and len(shell) > 1000
+
+
+def test_prescription_expression_parser(tmp_path):
+    """Prescription strings (expressions of t as the reference's demos write them) parsed and evaluated by the facade's
+    TimeExpression, against Python's own evaluation of the same formulas."""
+    import math
+    exe = str(tmp_path / "expression_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(HOST, "include"),
+                    os.path.join(ROOT, "tests", "host", "expression_check.cpp"), "-o", exe], check=True)
+    cases = [  # (C expression, python expression or None for a syntax error, is constant)
+        ("0.04 * sin(200 * t)", "0.04 * math.sin(200 * t)", False),
+        ("-3.14 / 4", "-3.14 / 4", True),
+        ("(t > 1.0) ? 2.0 * sin(5.0 * deme::PI * (t - 1.0)) : 0", "(2.0 * math.sin(5.0 * math.pi * (t - 1.0))) if t > 1.0 else 0.0", False),
+        ("1.0f + pow(t, 2) - fmin(t, 0.5) * 3", "1.0 + t ** 2 - min(t, 0.5) * 3", False),
+        ("2 - 3 - 4 * 2 / 8", "2 - 3 - 4 * 2 / 8", True),
+        ("-(1 + 2) * -t", "-(1 + 2) * -t", False),
+        ("t >= 0.5 && t < 1.5 ? 1 : 0", "1.0 if (t >= 0.5 and t < 1.5) else 0.0", False),
+        ("!(t < 1) || t == 0.5", "1.0 if ((not (t < 1)) or t == 0.5) else 0.0", False),
+        ("std::sqrt(fabs(t - 1)) + exp(-t) + atan2(t, 2) + erf(t)", "math.sqrt(abs(t - 1)) + math.exp(-t) + math.atan2(t, 2) + math.erf(t)", False),
+        ("(float)3 / 2 + M_PI", "1.5 + math.pi", True),
+        ("to_the_moon(t)", None, False),
+        ("1 +", None, False),
+        ("(1 + 2", None, False),
+    ]
+    src = tmp_path / "expr.txt"
+    src.write_text("\n".join(c[0] for c in cases) + "\n")
+    times = [0.0, 0.5, 1.3, 2.75]
+    out = subprocess.run([exe, str(src)] + [repr(t) for t in times], capture_output=True, text=True, check=True).stdout.splitlines()
+    assert len(out) == len(cases)
+    for (cexpr, pyexpr, const), line in zip(cases, out):
+        if pyexpr is None:
+            assert line == "ERROR", (cexpr, line)
+            continue
+        p = line.split()
+        assert int(p[0]) == int(const), cexpr
+        for t, v in zip(times, p[1:]):
+            want = float(eval(pyexpr, {"math": math, "t": t, "min": min, "abs": abs}))
+            assert abs(float(v) - want) <= 1e-12 * max(1.0, abs(want)), (cexpr, t, v, want)
