@@ -1358,6 +1358,12 @@ int dem_do_dynamics(DemCtx* ctx, double t) {
     return dem_step(ctx, n);
 }
 
+int dem_set_sim_time(DemCtx* ctx, double t) {
+    if (!ctx) return DEM_ERR_INVALID;
+    ctx->sim_time = t;  // host-side clock only (the kernels never see it): SetSimTime, dT.cpp:2709-2713
+    return DEM_OK;
+}
+
 int dem_update_step_size(DemCtx* ctx, float h) {
     if (!ctx || !(h > 0)) return DEM_ERR_INVALID;
     ctx->sp.h = h;

@@ -78,6 +78,13 @@ int main(int argc, char** argv) {
     printf("Contacts: listed = %zu (GetNumContacts %zu), clump-clump = %zu, sorted = %d; force pairs on first batch = %zu, "
            "sum fz = %.4f, point z range = [%.4f, %.4f]\n",
            all_pairs.size(), DEMSim.GetNumContacts(), clump_pairs.size(), (int)sorted, nf, sum.z, zmin, zmax);
+    // solver read-outs: broad-phase grid, margin, memory, neighbours of one clump, the simulated-time clock
+    const double t_end = DEMSim.GetSimTime();
+    DEMSim.SetSimTime(1.5);
+    printf("Solver: bin size = %.6f, bins = %zu, margin = %.6f, device MB = %.1f, clump 0 touches %zu clumps, "
+           "time %.4f -> %.4f\n", DEMSim.GetBinSize(), DEMSim.GetBinNum(), DEMSim.GetExpandFactor(),
+           DEMSim.GetDeviceMemUsageDynamic() / 1048576.0, DEMSim.GetOwnerContactClumps(0).size(), t_end, DEMSim.GetSimTime());
+    DEMSim.WriteContactFileIncludingPotentialPairs("DemoOutput_FillInBatches_contacts.csv");
     std::cout << "DEMdemo_FillInBatches exiting..." << std::endl;
     return 0;
 }

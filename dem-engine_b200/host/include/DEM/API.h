@@ -308,6 +308,16 @@ class DEMSolver {
     size_t GetNumContacts() const;
     float GetAvgSphContacts() const;
     double GetSimTime() const;
+    void SetSimTime(double time);
+    /// Broad-phase cell size and cell count of the last contact-list rebuild (the reference's bin size / number of bins)
+    double GetBinSize() const;
+    size_t GetBinNum() const;
+    /// The contact margin currently added to every sphere radius (largest over the owners)
+    float GetExpandFactor() const;
+    size_t GetDeviceMemUsageDynamic() const;
+    size_t GetDeviceMemUsageKinematic() const { return 0; }  // one context does both jobs here
+    /// Owner ids of the clumps in (potential) contact with the given owner
+    std::vector<bodyID_t> GetOwnerContactClumps(bodyID_t ownerID) const;
     float GetUpdateFreq() const { return (float)m_cd_update_freq; }
     bool GetInitStatus() const { return sys_initialized; }
 
@@ -409,6 +419,22 @@ class DEMSolver {
                                    const std::string& velZ, bool dictate = true);
     void SetFamilyPrescribedPosition(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z,
                                      bool dictate = true);
+    // "dictated, value left to the user" forms (API.h:712-786 of the reference): the listed components are no longer
+    // influenced by contact forces; the user sets them through trackers
+    void SetFamilyPrescribedLinVel(unsigned int ID) { markPrescribed(ID, 0, 7); }
+    void SetFamilyPrescribedLinVelX(unsigned int ID) { markPrescribed(ID, 0, 1); }
+    void SetFamilyPrescribedLinVelY(unsigned int ID) { markPrescribed(ID, 0, 2); }
+    void SetFamilyPrescribedLinVelZ(unsigned int ID) { markPrescribed(ID, 0, 4); }
+    void SetFamilyPrescribedAngVel(unsigned int ID) { markPrescribed(ID, 1, 7); }
+    void SetFamilyPrescribedAngVelX(unsigned int ID) { markPrescribed(ID, 1, 1); }
+    void SetFamilyPrescribedAngVelY(unsigned int ID) { markPrescribed(ID, 1, 2); }
+    void SetFamilyPrescribedAngVelZ(unsigned int ID) { markPrescribed(ID, 1, 4); }
+    void SetFamilyPrescribedPosition(unsigned int ID) { markPrescribed(ID, 2, 7); }
+    void SetFamilyPrescribedPositionX(unsigned int ID) { markPrescribed(ID, 2, 1); }
+    void SetFamilyPrescribedPositionY(unsigned int ID) { markPrescribed(ID, 2, 2); }
+    void SetFamilyPrescribedPositionZ(unsigned int ID) { markPrescribed(ID, 2, 4); }
+    void SetFamilyPrescribedQuaternion(unsigned int ID) { markPrescribed(ID, 3, 7); }
+    void SetFamilyPrescribedQuaternion(unsigned int ID, const std::string& q_formula, bool dictate = true);
     void AddFamilyPrescribedAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z);
     void AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z);
     void ChangeFamily(unsigned int ID_from, unsigned int ID_to);
@@ -434,7 +460,17 @@ class DEMSolver {
     void WriteSphereFile(const std::filesystem::path& outfilename) const;
     void WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy = 10) const;
     void WriteContactFile(const std::filesystem::path& outfilename, float force_thres = 1e-15) const;
-    void WriteMeshFile(const std::filesystem::path& outfilename) const;  // legacy-ASCII VTK of all meshes, current pose
+    void WriteMeshFile(const std::filesystem::path& outfilename) const;
+    void WriteContactFileIncludingPotentialPairs(const std::filesystem::path& outfilename) const { WriteContactFile(outfilename, -1.0f); }
+    void SetContactOutputFormat(OUTPUT_FORMAT) {}
+    void SetContactOutputFormat(const std::string&) {}
+    /// Clumps of this family are left out of the clump / sphere files
+    void DisableFamilyOutput(unsigned int ID) { m_no_output_families.insert((family_t)ID); }
+    static std::unordered_map<std::string, std::vector<float3>> ReadClumpFloat3FromCsv(
+        const std::string& infilename, const std::string& x_header, const std::string& y_header, const std::string& z_header,
+        const std::string& clump_header = "clump_type") {
+        return ReadClumpXyzFromCsv(infilename, clump_header, x_header, y_header, z_header);
+    }  // legacy-ASCII VTK of all meshes, current pose
     static std::unordered_map<std::string, std::vector<float3>> ReadClumpXyzFromCsv(
         const std::string& infilename, const std::string& clump_header = "clump_type", const std::string& x_header = "X",
         const std::string& y_header = "Y", const std::string& z_header = "Z");
@@ -508,6 +544,8 @@ class DEMSolver {
         }
     };
     bool anyTimeDependentPrescription() const;
+    void markPrescribed(unsigned int ID, int what, int axes);
+    std::set<family_t> m_no_output_families;
     double simTimeOrZero() const;
     void check(int rc, const char* what) const;
     void uploadFamilies();

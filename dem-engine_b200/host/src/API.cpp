@@ -611,6 +611,29 @@ void DEMSolver::AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X,
     }
     if (sys_initialized) uploadFamilies();
 }
+void DEMSolver::markPrescribed(unsigned int ID, int what, int axes) {
+    if (ID > 255) fail("Family numbers must not exceed 255.");
+    Prescription& p = m_prescriptions[ID];
+    p.used = true;
+    for (int k = 0; k < 3; k++) {
+        if (!(axes & (1 << k))) continue;
+        if (what == 0) p.linVelP[k] = true;
+        else if (what == 1) p.rotVelP[k] = true;
+        else if (what == 2) p.linPosP[k] = true;
+    }
+    if (what == 3) p.rotPosP = true;
+    if (sys_initialized) uploadFamilies();
+}
+void DEMSolver::SetFamilyPrescribedQuaternion(unsigned int ID, const std::string& q_formula, bool dictate) {
+    std::string t;
+    for (char c : q_formula)
+        if (!isspace((unsigned char)c)) t.push_back(c);
+    if (!t.empty() && t != "none")
+        fail("SetFamilyPrescribedQuaternion: a quaternion FORMULA is C++ code the reference compiles at run time; this "
+             "ahead-of-time compiled core only supports the dictated form (no formula): set the orientation through a "
+             "tracker, or prescribe the angular velocity instead.");
+    if (dictate) markPrescribed(ID, 3, 7);
+}
 void DEMSolver::ChangeFamilyWhen(unsigned int, unsigned int, const std::string&) {
     fail("ChangeFamilyWhen: condition strings need runtime compilation, which this ahead-of-time compiled core does "
          "not have. Use ChangeFamily(ID_from, ID_to) between DoDynamics calls.");
@@ -988,6 +1011,35 @@ float DEMSolver::GetAvgSphContacts() const {
     dem_get_stats(ctx, &s);
     return nSpheres ? (float)((double)(s.n_contacts_ss + s.n_contacts_sa + s.n_contacts_st) / (double)nSpheres) : 0.f;
 }
+void DEMSolver::SetSimTime(double time) { check(dem_set_sim_time(ctx, time), "dem_set_sim_time"); }
+double DEMSolver::GetBinSize() const {
+    DemStats st;
+    check(dem_get_stats(ctx, &st), "dem_get_stats");
+    return st.cell_size;
+}
+size_t DEMSolver::GetBinNum() const {
+    DemStats st;
+    check(dem_get_stats(ctx, &st), "dem_get_stats");
+    return (size_t)st.n_cells[0] * st.n_cells[1] * st.n_cells[2];
+}
+float DEMSolver::GetExpandFactor() const {
+    DemStats st;
+    check(dem_get_stats(ctx, &st), "dem_get_stats");
+    return st.max_margin;
+}
+size_t DEMSolver::GetDeviceMemUsageDynamic() const {
+    DemStats st;
+    check(dem_get_stats(ctx, &st), "dem_get_stats");
+    return (size_t)st.device_bytes;
+}
+std::vector<bodyID_t> DEMSolver::GetOwnerContactClumps(bodyID_t ownerID) const {
+    std::vector<bodyID_t> out;
+    for (const auto& pr : GetClumpContacts()) {
+        if (pr.first == ownerID) out.push_back(pr.second);
+        else if (pr.second == ownerID) out.push_back(pr.first);
+    }
+    return out;
+}
 double DEMSolver::GetSimTime() const {
     DemStats s;
     dem_get_stats(ctx, &s);
@@ -1165,6 +1217,7 @@ void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigne
     if (m_out_content & FAMILY) f << ",family";
     f << "\n";
     for (uint32_t i = 0; i < n; i++) {
+        if (m_no_output_families.count(fam[i])) continue;  // DisableFamilyOutput
         f << pos[3 * i] << "," << pos[3 * i + 1] << "," << pos[3 * i + 2];
         if (m_out_content & QUAT) f << "," << q[4 * i] << "," << q[4 * i + 1] << "," << q[4 * i + 2] << "," << q[4 * i + 3];
         f << "," << m_templates[m_owner_type_mark[i]]->m_name;
@@ -1180,13 +1233,15 @@ void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const 
     const uint32_t n = (uint32_t)nOwnerClumps;
     std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n);
     check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
+    std::vector<uint8_t> fam(n);
     check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), nullptr, nullptr,
-                                   nullptr, nullptr), "dem_download_owner_state");
+                                   nullptr, fam.data()), "dem_download_owner_state");
     std::ofstream f(outfilename);
     f << "x,y,z,r";
     if (m_out_content & ABSV) f << ",absv";
     f << "\n";
     for (uint32_t i = 0; i < n; i++) {
+        if (m_no_output_families.count(fam[i])) continue;  // DisableFamilyOutput
         const auto& t = m_templates[m_owner_type_mark[i]];
         const float4 quat = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);
         for (unsigned int k = 0; k < t->nComp; k++) {

@@ -24,7 +24,7 @@ EXPORTED_SYMBOLS = [
     "dem_upload_owners", "dem_upload_spheres", "dem_upload_triangles", "dem_update_triangle_nodes", "dem_host_partition_owners", "dem_debug_download", "dem_profile_binning", "dem_initialize", "dem_set_contacts",
     "dem_do_dynamics", "dem_step", "dem_step_async", "dem_sync", "dem_rebuild_contacts", "dem_update_step_size",
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
-    "dem_get_stats", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
+    "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
 ]
 
@@ -73,6 +73,7 @@ def load_library(path=None):
         _lib.dem_last_error.restype = C.c_char_p
         _lib.dem_last_error.argtypes = [C.c_void_p]
         _lib.dem_do_dynamics.argtypes = [C.c_void_p, C.c_double]
+        _lib.dem_set_sim_time.argtypes = [C.c_void_p, C.c_double]
         _lib.dem_host_box_domain.argtypes = [C.c_float, C.c_float, C.c_float] + [C.c_void_p] * 4
         for name in ("dem_step", "dem_step_async"):
             getattr(_lib, name).argtypes = [C.c_void_p, C.c_uint64]

@@ -188,6 +188,8 @@ int dem_sync(DemCtx* ctx);
 /* force a contact-list rebuild now (kT contactDetection(), DEMCubContactDetection.cu:38-1123) */
 int dem_rebuild_contacts(DemCtx* ctx);
 /* UpdateStepSize (API.h) */
+/* SetSimTime (API.h:117, dT.cpp:2709-2713): the simulated-time clock reported by dem_get_stats */
+int dem_set_sim_time(DemCtx* ctx, double t);
 int dem_update_step_size(DemCtx* ctx, float h);
 
 /* ---- state access: trackers / writers read through these (dT.cpp:3062-3130) ---------------------------- */

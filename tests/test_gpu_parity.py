@@ -641,6 +641,13 @@ def test_cpp_facade_demo_scripts(built):
     assert int(cl.split("force pairs on first batch =")[1].split(",")[0]) > 50
     z0, z1 = [float(v) for v in cl.split("point z range = [")[1].split("]")[0].split(",")]
     assert -0.6 - 1e-3 <= z0 <= z1 < 0.0                                        # contact points lie in the pile
+    sl = [l for l in fill.stdout.splitlines() if l.startswith("Solver:")][0]
+    bin_size, margin = float(sl.split("bin size =")[1].split(",")[0]), float(sl.split("margin =")[1].split(",")[0])
+    assert 0.016 < bin_size < 0.03 and 0 < margin < 0.002 and int(sl.split("bins =")[1].split(",")[0]) > 1000
+    assert float(sl.split("device MB =")[1].split(",")[0]) > 1.0 and int(sl.split("touches")[1].split()[0]) >= 1
+    assert sl.strip().endswith("-> 1.5000")                                      # SetSimTime
+    with open("/tmp/DemoOutput_FillInBatches_contacts.csv") as fh:
+        assert sum(1 for _ in fh) - 1 == listed                                  # potential pairs included
     # checkpoint / restart through the clump file + contact file (history wildcards) written and read by the facade
     rs = subprocess.run([os.path.join(host, "demo", "DEMdemo_Restart")], capture_output=True, text=True, env=env,
                         timeout=600, cwd="/tmp")
