@@ -85,6 +85,19 @@ int main(int argc, char** argv) {
            "time %.4f -> %.4f\n", DEMSim.GetBinSize(), DEMSim.GetBinNum(), DEMSim.GetExpandFactor(),
            DEMSim.GetDeviceMemUsageDynamic() / 1048576.0, DEMSim.GetOwnerContactClumps(0).size(), t_end, DEMSim.GetSimTime());
     DEMSim.WriteContactFileIncludingPotentialPairs("DemoOutput_FillInBatches_contacts.csv");
+    // freeze the bottom of the pile: clumps below a height join a fixed family, and stop moving
+    DEMSim.SetFamilyFixed(5);
+    const size_t frozen = DEMSim.ChangeClumpFamily(5, {-1., 1.}, {-1., 1.}, {-1., -0.55});
+    DEMSim.DoDynamicsThenSync(0.002);
+    float vmax_frozen = 0.f;
+    size_t in_family = 0;
+    const std::vector<float3> vel_all = tracker->Velocities();
+    for (size_t i = 0; i < n_first; i++)
+        if (tracker->GetFamily(i) == 5) {
+            in_family++;
+            vmax_frozen = std::max(vmax_frozen, length(vel_all[i]));
+        }
+    printf("Frozen: %zu clumps changed family, %zu of the first batch among them, their max |v| = %.3e\n", frozen, in_family, vmax_frozen);
     std::cout << "DEMdemo_FillInBatches exiting..." << std::endl;
     return 0;
 }

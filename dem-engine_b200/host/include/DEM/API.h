@@ -438,6 +438,12 @@ class DEMSolver {
     void AddFamilyPrescribedAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z);
     void AddFamilyPrescribedAngAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z);
     void ChangeFamily(unsigned int ID_from, unsigned int ID_to);
+    /// Change the family of the clumps whose centre lies in a box region (API.h:1030-1043 of the reference); only
+    /// clumps currently in one of `orig_fam` are touched when that set is not empty. Returns the number changed.
+    size_t ChangeClumpFamily(unsigned int fam_num, const std::pair<double, double>& X = std::pair<double, double>(-1e30, 1e30),
+                             const std::pair<double, double>& Y = std::pair<double, double>(-1e30, 1e30),
+                             const std::pair<double, double>& Z = std::pair<double, double>(-1e30, 1e30),
+                             const std::set<unsigned int>& orig_fam = std::set<unsigned int>());
     void ChangeFamilyWhen(unsigned int, unsigned int, const std::string&);
     /// Value of a prescription string at time t (what the integrator will be given); exposed for scripts and tests
     static double EvaluatePrescription(const std::string& expression, double t) { return TimeExpression(expression).Eval(t); }

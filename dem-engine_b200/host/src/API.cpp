@@ -1001,6 +1001,28 @@ void DEMSolver::ChangeFamily(unsigned int ID_from, unsigned int ID_to) {
     check(dem_upload_owner_state(ctx, 0, (uint32_t)nOwnerBodies, nullptr, nullptr, nullptr, nullptr, f.data()), "dem_upload_owner_state");
 }
 
+size_t DEMSolver::ChangeClumpFamily(unsigned int fam_num, const std::pair<double, double>& X, const std::pair<double, double>& Y,
+                                    const std::pair<double, double>& Z, const std::set<unsigned int>& orig_fam) {
+    assertInit("ChangeClumpFamily");
+    if (fam_num > 255) fail("Family numbers must not exceed 255.");
+    const uint32_t n = (uint32_t)nOwnerClumps;
+    std::vector<float> pos(3 * (size_t)n);
+    std::vector<uint8_t> f(n);
+    check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   f.data()), "dem_download_owner_state");
+    size_t changed = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const float x = pos[3 * i], y = pos[3 * i + 1], z = pos[3 * i + 2];
+        if (x < X.first || x > X.second || y < Y.first || y > Y.second || z < Z.first || z > Z.second) continue;
+        if (!orig_fam.empty() && !orig_fam.count(f[i])) continue;
+        if (f[i] != (uint8_t)fam_num) changed++;
+        f[i] = (uint8_t)fam_num;
+    }
+    if (changed) check(dem_upload_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, f.data()), "dem_upload_owner_state");
+    return changed;
+}
+
 size_t DEMSolver::GetNumContacts() const {
     DemStats s;
     dem_get_stats(ctx, &s);

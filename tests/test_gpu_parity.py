@@ -646,6 +646,9 @@ def test_cpp_facade_demo_scripts(built):
     assert 0.016 < bin_size < 0.03 and 0 < margin < 0.002 and int(sl.split("bins =")[1].split(",")[0]) > 1000
     assert float(sl.split("device MB =")[1].split(",")[0]) > 1.0 and int(sl.split("touches")[1].split()[0]) >= 1
     assert sl.strip().endswith("-> 1.5000")                                      # SetSimTime
+    fz = [l for l in fill.stdout.splitlines() if l.startswith("Frozen:")][0]   # ChangeClumpFamily + SetFamilyFixed
+    assert int(fz.split()[1]) > 10 and int(fz.split("family,")[1].split()[0]) > 0
+    assert float(fz.split("max |v| =")[1]) == 0.0
     with open("/tmp/DemoOutput_FillInBatches_contacts.csv") as fh:
         assert sum(1 for _ in fh) - 1 == listed                                  # potential pairs included
     # checkpoint / restart through the clump file + contact file (history wildcards) written and read by the facade
