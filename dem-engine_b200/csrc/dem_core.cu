@@ -1651,6 +1651,10 @@ int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]
         if ((rc = dalloc(ctx, &g.d_send_slot[d], std::max<uint32_t>(nO, 1u)))) return rc;
         CK(cudaMemset(g.d_send_slot[d], 0xff, sizeof(int32_t) * std::max<uint32_t>(nO, 1u)));
     }
+    // The fused push was verified on hardware with two ranks (tests/mgpu_check.py); with more ranks an interior rank
+    // pushes in both directions, which has not been run yet: keep the separate push kernel there unless asked.
+    g.fuse_push = (world == 2);
+    if (const char* e = getenv("DEM_B200_FUSED_PUSH")) g.fuse_push = atoi(e) != 0;
     if (getenv("DEM_B200_NO_FUSED_PUSH")) g.fuse_push = false;
     if ((rc = dalloc(ctx, &g.d_counts, 8))) return rc;
     if ((rc = dalloc(ctx, &g.d_allcounts, 8 * (size_t)world))) return rc;
