@@ -17,11 +17,11 @@ from pyapi import demb200, scenes  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--clumps", type=int, default=1000000)
-ap.add_argument("--settle-steps", type=int, default=12000)
+ap.add_argument("--settle-steps", type=int, default=80000)
 ap.add_argument("--steps", type=int, default=45)
 ap.add_argument("--cd-update-freq", type=int, default=20)
 ap.add_argument("--spacing", type=float, default=2.7)
-ap.add_argument("--ctas-per-sm", type=int, default=3)
+ap.add_argument("--ctas-per-sm", type=int, default=4)
 args = ap.parse_args()
 sc, dims = bench.build_scene(args.clumps, args.cd_update_freq, args.spacing)
 f = scenes.flatten(sc)
