@@ -130,3 +130,51 @@ def test_prescription_expression_parser(tmp_path):
         for t, v in zip(times, p[1:]):
             want = float(eval(pyexpr, {"math": math, "t": t, "min": min, "abs": abs}))
             assert abs(float(v) - want) <= 1e-12 * max(1.0, abs(want)), (cexpr, t, v, want)
+
+
+def test_wavefront_mesh_loading_and_transforms(built, tmp_path):
+    """DEMMeshConnected on the host (reference BdrsAndObjs.h:222-520): OBJ loading incl. quads and v/vt/vn corners,
+    Scale (mass ~ s^3, MOI ~ s^5), Move (rotate, then translate), Mirror (reflect and flip the winding)."""
+    exe = str(tmp_path / "mesh_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "host", "mesh_check.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "dem-engine_b200"), "-ldeme_b200", "-ldemcore",
+                    "-Wl,-rpath," + os.path.join(ROOT, "dem-engine_b200")], check=True)
+    obj = tmp_path / "shape.obj"
+    obj.write_text("# a unit square (one quad) and a triangle above it\n"
+                   "v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 0.5 0.5 1\n"
+                   "vn 0 0 1\nvt 0 0\n"
+                   "f 1/1/1 2/1/1 3/1/1 4/1/1\n"
+                   "f 1//1 2//1 5//1\n"
+                   "f -3 -2 -1\n")
+    out = subprocess.run([exe, str(obj)], capture_output=True, text=True, check=True).stdout.splitlines()
+    sets, cur = {}, None
+    for l in out:
+        p = l.split()
+        if p[0] in ("loaded", "scaled", "moved", "mirrored"):
+            cur = p[0]
+            sets[cur] = dict(nv=int(p[1]), nt=int(p[2]), mass=float(p[4]), moi=[float(x) for x in p[6:9]], v=[], f=[])
+        elif p[0] == "v":
+            sets[cur]["v"].append([float(x) for x in p[1:]])
+        elif p[0] == "f":
+            sets[cur]["f"].append([int(x) for x in p[1:]])
+    assert "missing 0" in out
+    L = sets["loaded"]
+    assert L["nv"] == 5 and L["nt"] == 4                       # the quad became two triangles
+    V = np.array(L["v"])
+    F = np.array(L["f"])
+    assert F.min() == 0 and F.max() == 4                       # zero-based
+    assert [2, 3, 4] in F.tolist()                             # negative indices count from the end
+    tri_area = lambda v, f: 0.5 * np.linalg.norm(np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]]), axis=1)
+    assert np.isclose(tri_area(V, F)[:2].sum(), 1.0)          # the two halves of the unit square
+    S = sets["scaled"]
+    assert np.allclose(np.array(S["v"]), 2 * V) and np.isclose(S["mass"], 2 * 8) and np.allclose(S["moi"], np.array([1, 2, 3]) * 32)
+    M = np.array(sets["moved"]["v"])
+    want = np.stack([-V[:, 1], V[:, 0], V[:, 2]], 1) + np.array([1, 2, 3])   # 90 degrees about z, then the shift
+    assert np.allclose(M, want, atol=1e-6)
+    R = sets["mirrored"]
+    assert np.allclose(np.array(R["v"]), V * np.array([-1, 1, 1]))
+    n0 = np.cross(V[F[:, 1]] - V[F[:, 0]], V[F[:, 2]] - V[F[:, 0]])
+    Rv, Rf = np.array(R["v"]), np.array(R["f"])
+    n1 = np.cross(Rv[Rf[:, 1]] - Rv[Rf[:, 0]], Rv[Rf[:, 2]] - Rv[Rf[:, 0]])
+    assert np.allclose(n1, n0 * np.array([-1, 1, 1]))          # normals are reflected, not inverted
