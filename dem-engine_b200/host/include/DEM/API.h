@@ -10,6 +10,7 @@
 // family-change conditions) throw with a clear message.
 #pragma once
 
+#include <algorithm>
 #include <cstdint>
 #include <filesystem>
 #include <iostream>
