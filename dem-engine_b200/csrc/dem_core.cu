@@ -3,14 +3,21 @@
 // (dT workerThread src/DEM/dT.cpp:2324-2479, kT workerThread src/DEM/kT.cpp:218-320) and their
 // cudaMemcpy mailbox hand-shake (dT.cpp:1989-2038, kT.cpp:193-216) with ONE in-order stream: the rebuild runs on the
 // same GPU right before the force kernel that first uses the list, so the list is never stale by more than
-// cd_update_freq steps and no peer copies exist.  There is no CPU fallback: without a device every entry point fails.
+// cd_update_freq steps and no peer copies exist.  The host never waits inside a rebuild: every count and flag stays on
+// the device, the rebuild's last kernel leaves a status record in pinned memory, and the host reads that record one
+// cycle later (right before it enqueues the next rebuild).  A rebuild that could not hold its result poisons the
+// context on the device -- every later kernel returns at once -- and the host, when it finds out, grows the arrays,
+// rolls its own bookkeeping back to that rebuild and replays.  There is no CPU fallback: without a device every entry
+// point fails.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <dlfcn.h>
@@ -24,18 +31,15 @@ static_assert(sizeof(DemPrescription) == 88 && sizeof(DemPrescription) == sizeof
 
 namespace {
 
-// NCCL entry points, resolved at run time from the NCCL already loaded in the process (torch's) or the system one
+// NCCL entry points, resolved at run time from the NCCL already loaded in the process (torch's) or the system one.
+// Used ONLY to bootstrap the multi-process decomposition (all-gather of the cudaIpc handles of the peer blocks); every
+// exchange after that is device-driven over the peer-mapped blocks (kernels_mgpu.cu).
 struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*GroupStart)() = nullptr;
-    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool load() {
         if (handle) return true;
@@ -47,47 +51,38 @@ struct NcclApi {
         if (!handle) return false;
 #define NCCL_SYM(field, name) field = reinterpret_cast<decltype(field)>(dlsym(handle, name)); if (!field) return false;
         NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank")
-        NCCL_SYM(CommDestroy, "ncclCommDestroy") NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv")
-        NCCL_SYM(AllReduce, "ncclAllReduce") NCCL_SYM(AllGather, "ncclAllGather") NCCL_SYM(GroupStart, "ncclGroupStart")
-        NCCL_SYM(GroupEnd, "ncclGroupEnd") NCCL_SYM(GetErrorString, "ncclGetErrorString")
+        NCCL_SYM(CommDestroy, "ncclCommDestroy") NCCL_SYM(AllGather, "ncclAllGather")
+        NCCL_SYM(GetErrorString, "ncclGetErrorString")
 #undef NCCL_SYM
         return true;
     }
 };
 NcclApi g_nccl;
 
-// domain decomposition state of one rank
+// domain decomposition state of one rank (device side: MgDev, dem_device.cuh)
 struct MgState {
     bool on = false;
+    bool local = false;  // all ranks are contexts of THIS process (peer access) instead of one process per GPU (cudaIpc)
     int rank = 0, world = 1;
     ncclComm_t comm = nullptr;
     float cut_lo = 0.f, cut_hi = 0.f;
-    uint8_t* d_flag = nullptr;
-    uint32_t* d_active_list = nullptr;
-    uint32_t* d_act_sph = nullptr;     // spheres of the active owners (the rebuild walks these only)
-    uint32_t n_act_sph = 0;
-    uint32_t grid_cells = 0;           // cells of this rank's table at the current rebuild (0 = not known yet)
-    uint32_t* d_counts = nullptr;      // 8 words
-    uint32_t* d_allcounts = nullptr;   // world x 8 words
-    uint32_t* d_send_gid[2] = {nullptr, nullptr};
-    uint32_t* d_recv_gid[2] = {nullptr, nullptr};
-    void* d_sendbuf[2] = {nullptr, nullptr};
-    void* d_recvbuf[2] = {nullptr, nullptr};
     uint32_t cap = 0;
-    uint32_t n_send[2] = {0, 0}, n_recv[2] = {0, 0}, n_active = 0, n_own = 0;
-    uint64_t halo_bytes = 0;  // bytes sent per step by this rank
-    // peer-memory exchange (see kernels_mgpu.cu): one allocation [flags: 256 B][recv: dir x parity x cap x 80 B]
-    bool p2p = false;
-    char* p2p_block = nullptr;
-    char* peer_block[2] = {nullptr, nullptr};  // the neighbours' blocks mapped into this process
-    uint32_t* d_block_counter = nullptr;
-    uint64_t epoch = 0;
-    int32_t* d_send_slot[2] = {nullptr, nullptr};  // per owner: slot in the left / right neighbour's buffer or -1
-    bool fuse_push = true;                         // the integrator stores the halo records itself (no push kernel)
+    char* my_block = nullptr;
+    char* peer_block[MG_MAX_WORLD] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool peer_ipc[MG_MAX_WORLD] = {false, false, false, false, false, false, false, false};
+    unsigned long long* d_ctrs = nullptr;  // [0] epoch [1] mail counter [2..3] block counters (as u32)
+    uint8_t* d_flag = nullptr;
+    uint32_t* d_active_list[2] = {nullptr, nullptr};
+    uint32_t* d_counts = nullptr;  // [2 parities][8]
+    uint32_t* d_send_gid[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    int32_t* d_send_slot[2] = {nullptr, nullptr};
+    uint32_t* d_act_sph = nullptr;
+    uint2* d_owner_sph = nullptr;
+    uint32_t last[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // counts of the last confirmed rebuild (RebuildStatus::mg)
 };
 
 struct ListBuf {
-    uint2* pair = nullptr;
+    uint32_t* idB = nullptr;
     uint4* cinfo = nullptr;
     float4* hist = nullptr;
     uint32_t* seg_start = nullptr;
@@ -95,6 +90,17 @@ struct ListBuf {
     uint32_t* count = nullptr;
     float4* force = nullptr;
     float4* cpoint = nullptr;
+};
+
+// host bookkeeping at the moment a rebuild was enqueued: what the host returns to when that rebuild turns out to
+// have failed on the device
+struct PendingRebuild {
+    bool valid = false;
+    uint32_t seq = 0;
+    uint64_t n_steps = 0, steps_since = 0, n_rebuilds = 0;
+    double sim_time = 0.0;
+    int cur = 0, maxvel_slot = 0;
+    bool need_maxvel = false;
 };
 
 }  // namespace
@@ -123,8 +129,6 @@ struct DemCtx {
     std::vector<OwnerState> h_state;
     std::vector<float4> h_spin;
     std::vector<uint2> h_sph;
-    std::vector<uint16_t> h_sph_comp, h_sph_mat;
-    std::vector<uint32_t> h_sph_owner;
     std::vector<float4> h_tri1, h_tri2, h_tri3;
     std::vector<uint2> h_tri_info;
     uint32_t nOwners = 0, nSpheres = 0, nAnal = 0, nTri = 0, nClumpOwners = 0;
@@ -142,20 +146,22 @@ struct DemCtx {
     MatPair* d_matpair = nullptr;
     AnalObj* d_anal = nullptr;
     // family tables live in one device blob [masks | extra margins | prescriptions] refreshed with ONE copy from a
-    // pinned staging buffer (a co-simulating caller re-sends them every step)
+    // pinned staging buffer (a co-simulating caller re-sends them every step); two staging buffers alternate so that
+    // the host only ever waits for the upload before the previous one
     char* d_famblob = nullptr;
-    char* h_famblob = nullptr;        // pinned
-    cudaEvent_t ev_fam = nullptr;     // completion of the last staged upload
+    char* h_famblob[2] = {nullptr, nullptr};  // pinned
+    cudaEvent_t ev_fam[2] = {nullptr, nullptr};
+    int fam_slot = 0;
     uint8_t* d_masks = nullptr;
     float* d_extra = nullptr;
     Prescr* d_presc = nullptr;
-    uint32_t* d_flags = nullptr;
+    uint32_t* d_flags = nullptr;   // DEM_NUM_FLAGS status words (DEM_FLAG_*)
     float* d_maxvel = nullptr;
     double* d_reduce = nullptr;
     double* d_reduce_many = nullptr;
     // contact lists [kind][buffer]: kind 0 = sphere-sphere in touch at the last rebuild, 1 = other sphere-sphere
-    // candidates, 2 = sphere-analytical; two buffers each (current / being rebuilt)
-    ListBuf lists[4][2];  // [3] = sphere-triangle
+    // candidates, 2 = sphere-analytical, 3 = sphere-triangle; two buffers each (current / being rebuilt)
+    ListBuf lists[4][2];
     int cur = 0;  // index of the current list buffers
     uint64_t capacity = 0;
     // rebuild scratch
@@ -165,11 +171,13 @@ struct DemCtx {
     uint32_t* d_vals[2] = {nullptr, nullptr};
     uint32_t* d_cellStart = nullptr;
     float4* d_sortedSph = nullptr;
+    uint2* d_sortedAux = nullptr;
     uint4* d_sortedMeta = nullptr;
     AnalWorld* d_analw = nullptr;
-    uint32_t* d_sortedPos = nullptr;
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
+    unsigned long long* d_scan_desc = nullptr;
+    uint32_t* d_idA[2] = {nullptr, nullptr};  // sphere A of every new sphere--sphere contact (fill pass -> history pass)
     // triangles
     float4* d_tri[3] = {nullptr, nullptr, nullptr};   // owner-frame nodes
     uint2* d_tri_info = nullptr;
@@ -180,11 +188,14 @@ struct DemCtx {
     uint64_t tri_pair_cap = 0;
     uint32_t max_cells = 0;
     int key_bits = 8;
-    // pinned read-back
-    uint32_t* h_pinned = nullptr;  // [0]=ssCount [1]=saCount [2..4]=flags, [8..] GridInfo
+    // pinned host memory
+    uint32_t* h_pinned = nullptr;        // 256 words of read-back scratch (reductions at words 112..131)
+    RebuildStatus* h_status = nullptr;   // ring of REBUILD_STATUS_SLOTS records written by k_finish_counts (mapped)
+    RebuildStatus* d_status = nullptr;   // the device's view of it
 
     // bookkeeping
     uint64_t n_steps = 0, n_rebuilds = 0, launches = 0, device_bytes = 0;
+    uint64_t steps_target = 0;  // steps asked for so far (n_steps falls behind it while a failed rebuild is replayed)
     uint64_t steps_since_rebuild = 0;
     bool need_rebuild = true;
     bool need_maxvel = true;  // velocities changed outside the integrator
@@ -193,15 +204,21 @@ struct DemCtx {
     uint64_t n_list[4] = {0, 0, 0, 0};
     GridInfo last_grid{};
     uint32_t overflow_seen = 0;
-    // CUDA graph of one whole contact-list cycle (cd_update_freq steps) for launch-bound scenes: [list buffer][max|v| slot]
+    uint32_t seq_host = 0;    // rebuilds enqueued so far == DEM_FLAG_SEQ on the device once they have run
+    PendingRebuild pending;
+    // adaptive update frequency (UseAdaptiveUpdateFreq, src/DEM/dT.h:721-752): 0 = fixed at sp.cd_update_freq
+    int adaptive_freq = 0;
+    // CUDA graph of one whole contact-list cycle (rebuild + cd_update_freq steps): [list buffer][max|v| slot]
     struct CycleGraph {
         cudaGraphExec_t exec = nullptr;
-        DevParams P0;        // the parameters the captured kernels were launched with (first step): validity check
+        DevParams P0;        // the parameters the captured kernels were launched with: validity check
+        CdParams C0;
         uint32_t L = 0;      // steps in the graph
-        int cfg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int cfg[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        uint64_t launches = 0;
     };
     CycleGraph graphs[2][2];
-    int use_graph = 2;       // 0 off, 1 on, 2 auto (on for scenes small enough to be launch-bound)
+    int use_graph = 2;       // 0 off, 1 on, 2 auto (on for scenes small enough to be launch-bound and on several GPUs)
     uint64_t graph_launches = 0;
     int ctas_per_sm = 4;
     int fast_math = 1;  // sphere--sphere force kernel: MUFU reciprocal / rsqrt instead of IEEE division / sqrt
@@ -259,7 +276,7 @@ void dfree(T*& p) {
 
 int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, bool force) {
     int rc;
-    if ((rc = dalloc(ctx, &L.pair, cap))) return rc;
+    if ((rc = dalloc(ctx, &L.idB, cap))) return rc;
     if ((rc = dalloc(ctx, &L.cinfo, cap))) return rc;
     if (hist && (rc = dalloc(ctx, &L.hist, cap))) return rc;
     if (force && (rc = dalloc(ctx, &L.force, cap))) return rc;
@@ -270,18 +287,51 @@ int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, 
     CK(cudaMemset(L.seg_start, 0, sizeof(uint32_t) * ((size_t)nSph + 1)));
     CK(cudaMemset(L.seg_count, 0, sizeof(uint32_t) * ((size_t)nSph + 1)));
     CK(cudaMemset(L.count, 0, sizeof(uint32_t) * 4));
+    // the record of a contact that no force kernel has visited yet reads as zero force at the origin
+    if (force) {
+        CK(cudaMemset(L.force, 0, sizeof(float4) * std::max<uint64_t>(cap, 1)));
+        CK(cudaMemset(L.cpoint, 0, sizeof(float4) * std::max<uint64_t>(cap, 1)));
+    }
     return DEM_OK;
 }
 void free_list(ListBuf& L) {
-    dfree(L.pair); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.cpoint); dfree(L.seg_start); dfree(L.seg_count);
+    dfree(L.idB); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.cpoint); dfree(L.seg_start); dfree(L.seg_count);
     dfree(L.count);
 }
 
 ContactList as_list(const ListBuf& L) {
     ContactList c;
-    c.pair = L.pair; c.cinfo = L.cinfo; c.hist = L.hist; c.seg_start = L.seg_start; c.seg_count = L.seg_count;
+    c.idB = L.idB; c.cinfo = L.cinfo; c.hist = L.hist; c.seg_start = L.seg_start; c.seg_count = L.seg_count;
     c.count = L.count; c.force = L.force; c.cpoint = L.cpoint;
     return c;
+}
+
+MgDev make_mgdev(const DemCtx* c) {
+    MgDev M;
+    memset(&M, 0, sizeof(M));
+    const MgState& g = c->mg;
+    M.world = 1;
+    if (!g.on) return M;
+    M.rank = g.rank; M.world = g.world;
+    M.has[0] = g.rank > 0; M.has[1] = g.rank < g.world - 1;
+    M.my_block = g.my_block;
+    for (int r = 0; r < g.world; r++) M.peer_block[r] = g.peer_block[r];
+    M.cap = g.cap;
+    M.epoch = g.d_ctrs;
+    M.mail_ctr = g.d_ctrs + 1;
+    M.block_ctr = reinterpret_cast<uint32_t*>(g.d_ctrs + 2);
+    M.flag = g.d_flag;
+    for (int p = 0; p < 2; p++) {
+        M.active_list[p] = g.d_active_list[p];
+        M.counts[p] = g.d_counts + 8 * p;
+        for (int d = 0; d < 2; d++) M.send_gid[p][d] = g.d_send_gid[p][d];
+    }
+    for (int d = 0; d < 2; d++) M.send_slot[d] = g.d_send_slot[d];
+    M.act_sph = g.d_act_sph;
+    M.owner_sph = g.d_owner_sph;
+    M.cut_lo = g.cut_lo; M.cut_hi = g.cut_hi;
+    M.nClumpOwners = c->nClumpOwners;
+    return M;
 }
 
 DevParams make_params(const DemCtx* c) {
@@ -309,13 +359,29 @@ DevParams make_params(const DemCtx* c) {
     P.st = as_list(c->lists[3][c->cur]);
     P.tri_n1 = c->d_tri[0]; P.tri_n2 = c->d_tri[1]; P.tri_n3 = c->d_tri[2]; P.tri_info = c->d_tri_info;
     P.flags = c->d_flags;
-    if (c->mg.on) { P.active = c->mg.d_flag; P.active_list = c->mg.d_active_list; P.nActive = c->mg.n_active; }
+    if (c->mg.on) {
+        const MgState& g = c->mg;
+        P.active = g.d_flag;
+        P.active_list = g.d_active_list[c->cur];
+        P.nActivePtr = g.d_counts + 8 * c->cur + 3;
+        for (int d = 0; d < 2; d++) {
+            const int peer = g.rank + (d == 0 ? -1 : 1);
+            P.send_slot[d] = g.d_send_slot[d];
+            // my records for the neighbour in direction d arrive there as "from direction 1-d"
+            P.peer_rec[d] = (peer >= 0 && peer < g.world)
+                                ? reinterpret_cast<int4*>(g.peer_block[peer] + mg_off_rec(g.cap, 1 - d, 0))
+                                : nullptr;
+        }
+        P.rec_half_int4 = g.cap * 5u;
+        P.epoch = g.d_ctrs;
+    }
     P.maxvel = c->d_maxvel + c->maxvel_slot;
     P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
     P.errOutVel = s.errOutVel;
     return P;
 }
 
+// rebuild parameters: the new lists go to the buffers cur^1, the current ones are the "old" lists (history source)
 CdParams make_cd(const DemCtx* c) {
     CdParams C;
     memset(&C, 0, sizeof(C));
@@ -330,14 +396,12 @@ CdParams make_cd(const DemCtx* c) {
     C.capacity = (uint32_t)c->capacity;
     C.sphF = c->d_sphF;
     C.keys[0] = c->d_keys[0]; C.keys[1] = c->d_keys[1]; C.vals[0] = c->d_vals[0]; C.vals[1] = c->d_vals[1];
-    C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedMeta = c->d_sortedMeta;
+    C.cellStart = c->d_cellStart; C.sortedSph = c->d_sortedSph; C.sortedAux = c->d_sortedAux; C.sortedMeta = c->d_sortedMeta;
     C.analw = c->d_analw;
-    C.sortedPos = c->d_sortedPos;
-    C.scan_cells = c->max_cells + 1;
     if (c->mg.on) {
         C.slab_on = 1; C.slab_lo = c->mg.cut_lo; C.slab_hi = c->mg.cut_hi;
-        C.act_sph = c->mg.d_act_sph; C.nActSph = c->mg.n_act_sph;
-        if (c->mg.grid_cells) C.scan_cells = std::min(c->mg.grid_cells, c->max_cells) + 1;
+        C.act_sph = c->mg.d_act_sph;
+        C.act_count = c->mg.d_counts + 8 * (c->cur ^ 1) + 4;
     }
     C.oldss = as_list(c->lists[0][c->cur]);
     C.oldsn = as_list(c->lists[1][c->cur]);
@@ -346,7 +410,9 @@ CdParams make_cd(const DemCtx* c) {
     C.triW1 = c->d_triW[0]; C.triW2 = c->d_triW[1]; C.triW3 = c->d_triW[2];
     C.triCellStart = c->d_triCellStart; C.triCellFill = c->d_triCellFill; C.triCellList = c->d_triCellList;
     C.tri_pair_cap = (uint32_t)c->tri_pair_cap;
-    C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp;
+    C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp; C.scan_desc = c->d_scan_desc;
+    C.idA_ss = c->d_idA[0]; C.idA_sn = c->d_idA[1];
+    C.status = c->d_status;
     return C;
 }
 
@@ -359,9 +425,25 @@ void free_device(DemCtx* c) {
     for (int k = 0; k < 3; k++) { dfree(c->d_tri[k]); dfree(c->d_triW[k]); }
     dfree(c->d_tri_info); dfree(c->d_triCellStart); dfree(c->d_triCellFill); dfree(c->d_triCellList);
     dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
-    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedMeta); dfree(c->d_analw); dfree(c->d_sortedPos);
-    dfree(c->d_rs_hist); dfree(c->d_scan_tmp);
+    dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedAux); dfree(c->d_sortedMeta); dfree(c->d_analw);
+    dfree(c->d_rs_hist); dfree(c->d_scan_tmp); dfree(c->d_scan_desc); dfree(c->d_idA[0]); dfree(c->d_idA[1]);
     c->device_bytes = 0;
+}
+
+void free_mg(DemCtx* c) {
+    MgState& g = c->mg;
+    dfree(g.d_flag); dfree(g.d_active_list[0]); dfree(g.d_active_list[1]); dfree(g.d_act_sph); dfree(g.d_owner_sph);
+    dfree(g.d_send_slot[0]); dfree(g.d_send_slot[1]); dfree(g.d_counts); dfree(g.d_ctrs);
+    for (int p = 0; p < 2; p++)
+        for (int d = 0; d < 2; d++) dfree(g.d_send_gid[p][d]);
+    for (int r = 0; r < (int)MG_MAX_WORLD; r++) {
+        if (g.peer_block[r] && g.peer_ipc[r]) cudaIpcCloseMemHandle(g.peer_block[r]);
+        g.peer_block[r] = nullptr;
+        g.peer_ipc[r] = false;
+    }
+    if (g.my_block) cudaFree(g.my_block);
+    g.my_block = nullptr;
+    g.on = false;
 }
 
 constexpr size_t FAM_OFF_MASKS = 0;
@@ -369,20 +451,23 @@ constexpr size_t FAM_OFF_EXTRA = (DEM_NUM_FAMILY_MASKS + 255) / 256 * 256;
 constexpr size_t FAM_OFF_PRESC = FAM_OFF_EXTRA + sizeof(float) * DEM_NUM_FAMILIES;
 constexpr size_t FAM_BLOB_BYTES = FAM_OFF_PRESC + sizeof(Prescr) * DEM_NUM_FAMILIES;
 
-// host tables -> pinned staging -> device blob, one asynchronous copy on the compute stream
+// host tables -> pinned staging -> device blob, one asynchronous copy on the compute stream.  Two staging buffers
+// alternate: the host waits for the upload before the previous one, which has long left its buffer.
 int stage_families(DemCtx* ctx) {
-    if (!ctx->h_famblob) {
-        CK(cudaHostAlloc((void**)&ctx->h_famblob, FAM_BLOB_BYTES, cudaHostAllocDefault));
-        memset(ctx->h_famblob, 0, FAM_BLOB_BYTES);
-        CK(cudaEventCreateWithFlags(&ctx->ev_fam, cudaEventDisableTiming));
+    const int k = ctx->fam_slot;
+    ctx->fam_slot ^= 1;
+    if (!ctx->h_famblob[k]) {
+        CK(cudaHostAlloc((void**)&ctx->h_famblob[k], FAM_BLOB_BYTES, cudaHostAllocDefault));
+        memset(ctx->h_famblob[k], 0, FAM_BLOB_BYTES);
+        CK(cudaEventCreateWithFlags(&ctx->ev_fam[k], cudaEventDisableTiming));
     } else {
-        CK(cudaEventSynchronize(ctx->ev_fam));  // the previous upload has left the staging buffer
+        CK(cudaEventSynchronize(ctx->ev_fam[k]));  // the upload before the previous one has left this buffer
     }
-    memcpy(ctx->h_famblob + FAM_OFF_MASKS, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS);
-    memcpy(ctx->h_famblob + FAM_OFF_EXTRA, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES);
-    memcpy(ctx->h_famblob + FAM_OFF_PRESC, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES);
-    CK(cudaMemcpyAsync(ctx->d_famblob, ctx->h_famblob, FAM_BLOB_BYTES, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaEventRecord(ctx->ev_fam, ctx->stream));
+    memcpy(ctx->h_famblob[k] + FAM_OFF_MASKS, ctx->h_masks.data(), DEM_NUM_FAMILY_MASKS);
+    memcpy(ctx->h_famblob[k] + FAM_OFF_EXTRA, ctx->h_extra.data(), sizeof(float) * DEM_NUM_FAMILIES);
+    memcpy(ctx->h_famblob[k] + FAM_OFF_PRESC, ctx->h_presc.data(), sizeof(Prescr) * DEM_NUM_FAMILIES);
+    CK(cudaMemcpyAsync(ctx->d_famblob, ctx->h_famblob[k], FAM_BLOB_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_fam[k], ctx->stream));
     return DEM_OK;
 }
 
@@ -393,6 +478,8 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
     for (int kind = 0; kind < 4; kind++)
         for (int k = 0; k < 2; k++)
             if ((rc = alloc_list(ctx, ctx->lists[kind][k], (kind == 3 && ctx->nTri == 0) ? 1 : cap, ctx->nSpheres, hist, rec))) return rc;
+    for (int k = 0; k < 2; k++)
+        if ((rc = dalloc(ctx, &ctx->d_idA[k], cap))) return rc;
     ctx->capacity = cap;
     return DEM_OK;
 }
@@ -404,254 +491,203 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
             return fail(ctx, DEM_ERR_CUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__, g_nccl.GetErrorString(r_)); \
     } while (0)
 
-MgParams make_mg(const DemCtx* c) {
-    MgParams M;
-    memset(&M, 0, sizeof(M));
-    const MgState& g = c->mg;
-    M.flag = g.d_flag; M.active_list = g.d_active_list; M.counts = g.d_counts;
-    M.send_gid[0] = g.d_send_gid[0]; M.send_gid[1] = g.d_send_gid[1];
-    M.send_cap = g.cap; M.nClumpOwners = c->nClumpOwners;
-    M.cut_lo = g.cut_lo; M.cut_hi = g.cut_hi; M.grid = c->d_grid;
-    M.has_left = g.rank > 0; M.has_right = g.rank < g.world - 1;
-    M.act_sph = g.d_act_sph;
-    return M;
-}
+void graph_drop(DemCtx* ctx);
 
-int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches);
-
-// the next epoch of the peer-memory exchange: where my records go, where the neighbours' arrive
-MgP2P mg_next_epoch(DemCtx* ctx) {
-    MgState& g = ctx->mg;
-    MgP2P X;
-    memset(&X, 0, sizeof(X));
-    g.epoch++;
-    const size_t half = (size_t)g.cap * 80, par = (size_t)(g.epoch & 1);
-    for (int d = 0; d < 2; d++) {
-        const int peer = g.rank + (d == 0 ? -1 : 1);
-        X.has[d] = (peer >= 0 && peer < g.world) ? 1 : 0;
-        X.send_gid[d] = g.d_send_gid[d]; X.recv_gid[d] = g.d_recv_gid[d];
-        X.n_send[d] = g.n_send[d]; X.n_recv[d] = g.n_recv[d];
-        // my records for the neighbour in direction d arrive there as "from direction 1-d"
-        if (X.has[d]) {
-            X.peer_recv[d] = reinterpret_cast<int4*>(g.peer_block[d] + 256 + ((size_t)(1 - d) * 2 + par) * half);
-            X.peer_flag[d] = reinterpret_cast<unsigned long long*>(g.peer_block[d]) + (1 - d);
-        }
-        X.my_recv[d] = reinterpret_cast<const int4*>(g.p2p_block + 256 + ((size_t)d * 2 + par) * half);
-        X.my_flag[d] = reinterpret_cast<unsigned long long*>(g.p2p_block) + d;
+// Grow every contact list to `newcap` entries, keeping the contents of the CURRENT lists (the history source of the
+// next rebuild).  Host-synchronous; only called with the stream idle.
+int grow_lists(DemCtx* ctx, uint64_t newcap) {
+    if (newcap > 0xfffffff0ull) return fail(ctx, DEM_ERR_CAPACITY, "contact list exceeds 2^32 entries");
+    const uint64_t oldcap = ctx->capacity;
+    const bool hist = ctx->sp.force_model == DEM_HERTZIAN, rec = ctx->sp.record_contact_forces != 0;
+    for (int kind = 0; kind < (ctx->nTri ? 4 : 3); kind++) {
+        int rc;
+        free_list(ctx->lists[kind][ctx->cur ^ 1]);
+        if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
+        ListBuf src = ctx->lists[kind][ctx->cur], dst;
+        if ((rc = alloc_list(ctx, dst, newcap, ctx->nSpheres, hist, rec))) return rc;
+        CK(cudaMemcpy(dst.idB, src.idB, sizeof(uint32_t) * oldcap, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice));
+        if (src.hist) CK(cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
+        if (src.force) CK(cudaMemcpy(dst.force, src.force, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
+        if (src.cpoint) CK(cudaMemcpy(dst.cpoint, src.cpoint, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(dst.seg_start, src.seg_start, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(dst.seg_count, src.seg_count, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
+        CK(cudaMemcpy(dst.count, src.count, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
+        free_list(src);
+        ctx->lists[kind][ctx->cur] = dst;
     }
-    X.epoch = g.epoch;
-    X.block_counter = g.d_block_counter;
-    return X;
-}
-
-// integration + per-step halo exchange.  With peer memory the integrator itself stores the halo records into the
-// neighbours' buffers (fused push); k_mg_pull, next in the stream, publishes the epoch to the neighbours, waits for
-// theirs and scatters what they stored here.
-int integrate_and_exchange(DemCtx* ctx, DevParams& P, int* launches) {
-    MgState& g = ctx->mg;
-    if (g.on && g.p2p && g.fuse_push) {
-        MgP2P X = mg_next_epoch(ctx);
-        X.publish = 1;
-        for (int d = 0; d < 2; d++) {
-            P.send_slot[d] = g.d_send_slot[d];
-            P.peer_recv[d] = X.peer_recv[d];
-        }
-        launch_integrate(P, ctx->stream);
-        *launches += launch_mg_pull(P, X, ctx->stream);
-        return DEM_OK;
+    for (int k = 0; k < 2; k++) {
+        dfree(ctx->d_idA[k]);
+        int rc = dalloc(ctx, &ctx->d_idA[k], newcap);
+        if (rc) return rc;
     }
-    launch_integrate(P, ctx->stream);
-    if (g.on) return mg_halo_exchange(ctx, P, nullptr, launches);
+    ctx->capacity = newcap;
+    graph_drop(ctx);
     return DEM_OK;
 }
 
-// send the {state, spin} records of my halo owners to both neighbours and scatter theirs into my global slots
-int mg_halo_exchange(DemCtx* ctx, const DevParams& P, uint8_t* flag_or_null, int* launches) {
-    MgState& g = ctx->mg;
+// ---- the rebuild, host side ---------------------------------------------------------------------------------------
+// All kernels of ONE contact-list rebuild into the buffers cur^1, on ctx->stream; nothing here waits for the device.
+// Returns the number of kernels launched.  sev (optional, 8 events) brackets the stages for dem_profile_rebuild.
+int launch_rebuild_kernels(DemCtx* ctx, cudaEvent_t* sev) {
+    DevParams P = make_params(ctx);
+    const CdParams C = make_cd(ctx);
+    const int par = ctx->cur ^ 1;
+    P.ss = as_list(ctx->lists[0][par]);
+    P.sn = as_list(ctx->lists[1][par]);
+    P.sa = as_list(ctx->lists[2][par]);
+    P.st = as_list(ctx->lists[3][par]);
     cudaStream_t s = ctx->stream;
-    if (g.p2p && !flag_or_null) {
-        // per-step path: stores into the neighbours' memory + flags, no library call
-        const MgP2P X = mg_next_epoch(ctx);
-        *launches += launch_mg_push(P, X, s);
-        *launches += launch_mg_pull(P, X, s);
-        return DEM_OK;
-    }
-    for (int d = 0; d < 2; d++) *launches += launch_mg_pack(P, g.d_send_gid[d], g.n_send[d], g.d_sendbuf[d], s);
-    NC(g_nccl.GroupStart());
-    for (int d = 0; d < 2; d++) {
-        const int peer = g.rank + (d == 0 ? -1 : 1);
-        if (peer < 0 || peer >= g.world) continue;
-        if (g.n_send[d]) NC(g_nccl.Send(g.d_sendbuf[d], (size_t)g.n_send[d] * 80, ncclUint8, peer, g.comm, s));
-        if (g.n_recv[d]) NC(g_nccl.Recv(g.d_recvbuf[d], (size_t)g.n_recv[d] * 80, ncclUint8, peer, g.comm, s));
-    }
-    NC(g_nccl.GroupEnd());
-    for (int d = 0; d < 2; d++)
-        *launches += launch_mg_unpack(P, g.d_recv_gid[d], g.n_recv[d], g.d_recvbuf[d], flag_or_null, s);
-    return DEM_OK;
+    const MgDev M = make_mgdev(ctx);
+    const MgDev* Mp = ctx->mg.on ? &M : nullptr;
+    int launches = launch_zero_u32(ctx->d_flags, 2, ctx->d_flags, ctx->num_sms, s);  // capacity bits + triangle demand
+    if (sev) cudaEventRecord(sev[0], s);
+    launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 0, ctx->num_sms, s);
+    launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 1, ctx->num_sms, s);
+    if (ctx->mg.on) launches += launch_mg_redistribute(P, M, ctx->d_grid, par, ctx->num_sms, s);
+    launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 2, ctx->num_sms, s);
+    launches += launch_cd_triangles(P, C, 0, ctx->num_sms, s);  // triangle -> cell registration
+    launches += launch_cd_triangles(P, C, 1, ctx->num_sms, s);  // per-sphere triangle candidates (+ history)
+    if (sev) cudaEventRecord(sev[1], s);
+    int sorted_buf = -1;  // -1: counting sort inside the sweep stage
+    if (ctx->sort_mode == 0) { launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf); ctx->last_sorted_buf = sorted_buf; }
+    if (sev) cudaEventRecord(sev[2], s);
+    launches += launch_cd_sweep(P, C, Mp, par, sorted_buf, ctx->num_sms, s, sev ? sev + 3 : nullptr);  // records sev[3..6]
+    if (sev) cudaEventRecord(sev[7], s);
+    return launches;
 }
 
-// at a rebuild: re-decide ownership, exchange the halo membership lists and the halo records, list the active owners
-int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches) {
-    MgState& g = ctx->mg;
-    cudaStream_t s = ctx->stream;
-    MgParams M = make_mg(ctx);
-    *launches += launch_mg_classify(P, M, s);
-    NC(g_nccl.AllGather(g.d_counts, g.d_allcounts, 8, ncclUint32, g.comm, s));
-    CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_allcounts, sizeof(uint32_t) * 8 * g.world, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    const uint32_t* all = ctx->h_pinned + 40;
-    for (int r = 0; r < g.world; r++)
-        if (all[8 * r + 1] > g.cap || all[8 * r + 2] > g.cap)
-            return fail(ctx, DEM_ERR_CAPACITY, "halo of rank %d holds %u / %u owners, more than the buffer of %u", r,
-                        all[8 * r + 1], all[8 * r + 2], g.cap);
-    g.n_send[0] = all[8 * g.rank + 1];
-    g.n_send[1] = all[8 * g.rank + 2];
-    g.n_recv[0] = g.rank > 0 ? all[8 * (g.rank - 1) + 2] : 0;            // what my left neighbour sends to its right
-    g.n_recv[1] = g.rank < g.world - 1 ? all[8 * (g.rank + 1) + 1] : 0;  // what my right neighbour sends to its left
-    g.halo_bytes = ((uint64_t)g.n_send[0] + g.n_send[1]) * 80;
-    NC(g_nccl.GroupStart());
-    for (int d = 0; d < 2; d++) {
-        const int peer = g.rank + (d == 0 ? -1 : 1);
-        if (peer < 0 || peer >= g.world) continue;
-        if (g.n_send[d]) NC(g_nccl.Send(g.d_send_gid[d], g.n_send[d], ncclUint32, peer, g.comm, s));
-        if (g.n_recv[d]) NC(g_nccl.Recv(g.d_recv_gid[d], g.n_recv[d], ncclUint32, peer, g.comm, s));
-    }
-    NC(g_nccl.GroupEnd());
-    int rc = mg_halo_exchange(ctx, P, g.d_flag, launches);
-    if (rc) return rc;
-    for (int d = 0; d < 2; d++) *launches += launch_mg_send_map(g.d_send_gid[d], g.n_send[d], g.d_send_slot[d], ctx->nOwners, s);
-    *launches += launch_mg_active_list(P, M, s);
-    *launches += launch_mg_active_spheres(P, M, s);
-    CK(cudaMemcpyAsync(ctx->h_pinned + 40, g.d_counts, sizeof(uint32_t) * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    g.n_own = ctx->h_pinned[40];
-    g.n_active = ctx->h_pinned[43];
-    g.n_act_sph = ctx->h_pinned[44];
-    GridInfo gi;
-    memcpy(&gi, ctx->h_pinned + 8, sizeof(GridInfo));
-    g.grid_cells = gi.ncells;  // the host now knows this rebuild's grid: clear and scan only its cells
-    return DEM_OK;
+// host bookkeeping of a rebuild that has just been enqueued (plain launches or as the head of a cycle graph)
+void note_rebuild_enqueued(DemCtx* ctx) {
+    PendingRebuild& p = ctx->pending;
+    p.valid = true;
+    p.seq = ++ctx->seq_host;
+    p.n_steps = ctx->n_steps; p.steps_since = ctx->steps_since_rebuild; p.n_rebuilds = ctx->n_rebuilds;
+    p.sim_time = ctx->sim_time;
+    p.cur = ctx->cur; p.maxvel_slot = ctx->maxvel_slot; p.need_maxvel = ctx->need_maxvel;
+    ctx->cur ^= 1;
+    ctx->n_rebuilds++;
+    ctx->steps_since_rebuild = 0;
+    ctx->need_rebuild = false;
+    ctx->need_maxvel = false;
 }
 
-// one contact-list rebuild into the "other" buffers, then swap. Syncs once (reads the counts back).
-int mg_redistribute(DemCtx* ctx, const DevParams& P, int* launches);
-
-int rebuild(DemCtx* ctx, float* stage_us = nullptr) {
-    cudaEvent_t sev[8];
-    if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
-    for (int attempt = 0; attempt < 8; attempt++) {
-        DevParams P = make_params(ctx);
-        CdParams C = make_cd(ctx);
-        // the new lists go to the other buffers; the current ones are the "old" lists (history source)
-        P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
-        P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
-        P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
-        P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
-        cudaStream_t s = ctx->stream;
-        CK(cudaMemsetAsync(ctx->d_flags, 0, sizeof(uint32_t) * 3, s));  // [3] (velocity) is only cleared by the host
-        if (stage_us) cudaEventRecord(sev[0], s);
-        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, 0, s);
-        if (ctx->mg.on)  // the cell grid (hence the sorted order and the A/B roles) must be the same on every rank
-            NC(g_nccl.AllReduce(P.maxvel, P.maxvel, 1, ncclFloat32, ncclMax, ctx->mg.comm, s));
-        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 1, s);
-        if (ctx->mg.on) {
-            int rc = mg_redistribute(ctx, P, &launches);
-            if (rc) return rc;
-            P = make_params(ctx);  // nActive changed
-            C = make_cd(ctx);      // ... and so did the active sphere list and the cell count
-            P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]);
-            P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
-            P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]);
-            P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
+// Wait for the status record of the pending rebuild and act on it.  *rolled_back = true: the rebuild had overflowed, the
+// arrays were grown and the host state is back where that rebuild was enqueued (need_rebuild set): the caller replays.
+int confirm_rebuild(DemCtx* ctx, bool* rolled_back) {
+    if (rolled_back) *rolled_back = false;
+    PendingRebuild& p = ctx->pending;
+    if (!p.valid) return DEM_OK;
+    volatile RebuildStatus* st = ctx->h_status + (p.seq % REBUILD_STATUS_SLOTS);
+    {
+        // k_finish_counts writes seq last, after a system fence: spin on the pinned word (works for plain launches and
+        // for graph replays alike; an event could not be waited on from inside a captured cycle)
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned spins = 0;
+        while (st->seq != p.seq) {
+            if ((++spins & 0x3ffu) == 0) {
+                const cudaError_t q = cudaStreamQuery(ctx->stream);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail(ctx, DEM_ERR_CUDA, "the device failed during a contact-list rebuild: %s", cudaGetErrorString(q));
+                if (q == cudaSuccess && st->seq != p.seq)
+                    return fail(ctx, DEM_ERR_CUDA, "rebuild %u finished without leaving its status record (found %u)", p.seq, st->seq);
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(120))
+                    return fail(ctx, DEM_ERR_CUDA, "timed out waiting for contact-list rebuild %u", p.seq);
+                std::this_thread::yield();
+            }
         }
-        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 2, s);
-        launches += launch_cd_triangles(P, C, 0, s);  // triangle -> cell registration
-        launches += launch_cd_triangles(P, C, 1, s);  // per-sphere triangle candidates (+ history)
-        if (ctx->nTri)  // demand of the triangle--cell table
-            CK(cudaMemcpyAsync(ctx->h_pinned + 200, ctx->d_triCellStart + ctx->max_cells, sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (stage_us) cudaEventRecord(sev[1], s);
-        int sorted_buf = -1;  // -1: counting sort inside the sweep stage
-        if (ctx->sort_mode == 0) { launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf); ctx->last_sorted_buf = sorted_buf; }
-        if (stage_us) cudaEventRecord(sev[2], s);
-        launches += launch_cd_sweep(P, C, sorted_buf, s, stage_us ? sev + 3 : nullptr);  // records sev[3..6]
-        if (stage_us) cudaEventRecord(sev[7], s);
-        ctx->launches += launches;
-        const ContactList* NL[4] = {&P.ss, &P.sn, &P.sa, &P.st};
-        for (int kind = 0; kind < 4; kind++)  // {clamped count, demand}
-            CK(cudaMemcpyAsync(ctx->h_pinned + 32 + 2 * kind, NL[kind]->count, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        if (ctx->mg.on)  // every rank must see the same verdict, or the ranks fall out of step inside NCCL
-            NC(g_nccl.AllReduce(ctx->d_flags, ctx->d_flags, 4, ncclUint32, ncclMax, ctx->mg.comm, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 2, ctx->d_flags, sizeof(uint32_t) * 4, cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_grid, sizeof(GridInfo), cudaMemcpyDeviceToHost, s));
-        CK(cudaStreamSynchronize(s));
-        memcpy(&ctx->last_grid, ctx->h_pinned + 8, sizeof(GridInfo));
-        ctx->need_maxvel = false;
-        if (ctx->h_pinned[4] != 0)
-            return fail(ctx, DEM_ERR_CAPACITY, "a sphere has more than 40 forward sphere or 24 triangle contact candidates: "
-                        "geometry size ratios this large need a smaller contact margin (SetExpandSafetyAdder / "
-                        "SetCDUpdateFreq) or a coarser mesh");
-        if (ctx->h_pinned[5] != 0) {
-            const uint32_t zero = 0;
-            cudaMemcpy(ctx->d_flags + 3, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice);
-            return fail(ctx, DEM_ERR_VELOCITY,
-                        "an owner has a non-finite or too large velocity (max seen %.6g, limit %.6g) at t=%.9g",
-                        ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
-        }
-        if (ctx->h_pinned[2] != 0 && ctx->mg.on)
-            return fail(ctx, DEM_ERR_CAPACITY, "a contact list or halo buffer overflowed on some rank (flags %u); raise "
-                        "the contact capacity passed to dem_initialize", ctx->h_pinned[2]);
-        if ((ctx->h_pinned[2] & 16u) != 0) {
-            // the triangle--cell table was too small: it is scratch, so just regrow it and redo the rebuild
-            ctx->overflow_seen++;
+    }
+    RebuildStatus r;
+    memcpy(&r, const_cast<RebuildStatus*>(st), sizeof(r));
+    p.valid = false;
+    if (r.haloflags & 64u)
+        return fail(ctx, DEM_ERR_CUDA, "multi-GPU: a neighbouring rank stopped answering (halo exchange timed out)");
+    if (r.poison != 0u) {
+        // ---- the rebuild could not hold its result: every kernel after it was a no-op.  Drain, grow, roll back. ----
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->side) CK(cudaStreamSynchronize(ctx->side));
+        ctx->overflow_seen++;
+        ctx->n_steps = p.n_steps; ctx->steps_since_rebuild = p.steps_since; ctx->n_rebuilds = p.n_rebuilds;
+        ctx->sim_time = p.sim_time; ctx->cur = p.cur; ctx->maxvel_slot = p.maxvel_slot; ctx->need_maxvel = p.need_maxvel;
+        ctx->need_rebuild = true;
+        if (r.capflags & 8u)
+            return fail(ctx, DEM_ERR_CAPACITY, "multi-GPU: the halo of a rank holds more owners than its buffer of %u; "
+                        "use fewer ranks or a wider domain", ctx->mg.cap);
+        if (r.capflags & 16u) {
+            // the triangle--cell table was too small: it is scratch, so just regrow it
             dfree(ctx->d_triCellList);
-            ctx->tri_pair_cap = (uint64_t)ctx->h_pinned[200] + ctx->h_pinned[200] / 2 + 1024;
+            ctx->tri_pair_cap = (uint64_t)r.tri_demand + r.tri_demand / 2 + 1024;
             int rc = dalloc(ctx, &ctx->d_triCellList, ctx->tri_pair_cap);
             if (rc) return rc;
-            continue;
+            graph_drop(ctx);
         }
-        if (ctx->h_pinned[2] != 0) {
-            // capacity overflow: grow every list, keep the old lists (history source) intact, redo the rebuild
-            ctx->overflow_seen++;
+        if (r.capflags & ~(8u | 16u)) {
             uint64_t need = 0;
-            for (int kind = 0; kind < 4; kind++) need = std::max<uint64_t>(need, ctx->h_pinned[32 + 2 * kind + 1]);
-            const uint64_t newcap = std::max<uint64_t>(need + need / 4 + 1024, ctx->capacity * 2);
-            if (newcap > 0xfffffff0ull) return fail(ctx, DEM_ERR_CAPACITY, "contact list exceeds 2^32 entries");
-            const uint64_t oldcap = ctx->capacity;
-            const bool hist = ctx->sp.force_model == DEM_HERTZIAN, rec = ctx->sp.record_contact_forces != 0;
-            for (int kind = 0; kind < (ctx->nTri ? 4 : 3); kind++) {
-                int rc;
-                free_list(ctx->lists[kind][ctx->cur ^ 1]);
-                if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
-                ListBuf src = ctx->lists[kind][ctx->cur], dst;
-                if ((rc = alloc_list(ctx, dst, newcap, ctx->nSpheres, hist, rec))) return rc;
-                CK(cudaMemcpy(dst.pair, src.pair, sizeof(uint2) * oldcap, cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice));
-                if (src.hist) CK(cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(dst.seg_start, src.seg_start, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(dst.seg_count, src.seg_count, sizeof(uint32_t) * ((size_t)ctx->nSpheres + 1), cudaMemcpyDeviceToDevice));
-                CK(cudaMemcpy(dst.count, src.count, sizeof(uint32_t) * 4, cudaMemcpyDeviceToDevice));
-                free_list(src);
-                ctx->lists[kind][ctx->cur] = dst;
+            for (int kind = 0; kind < 4; kind++) need = std::max<uint64_t>(need, r.demand[kind]);
+            // (on several GPUs the rank that overflowed may be another one: grow anyway, all ranks replay together)
+            const uint64_t newcap = std::max<uint64_t>(need + need / 4 + 1024, need > ctx->capacity ? ctx->capacity * 2 : ctx->capacity);
+            if (newcap > ctx->capacity) {
+                int rc = grow_lists(ctx, newcap);
+                if (rc) return rc;
             }
-            ctx->capacity = newcap;
-            continue;
         }
-        if (stage_us) {
-            // [0] margins+keys+histogram+analytical list [1] sort [2] cell-table scan [3] gather [4] sweep
-            // [5] counts [6] unused [7] whole rebuild on the device
-            for (int k = 0; k < 6; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
-            stage_us[6] = 0.f;
-            cudaEventElapsedTime(&stage_us[7], sev[0], sev[7]);
-            for (int k = 0; k < 8; k++) stage_us[k] *= 1000.f;
-            for (auto& e : sev) cudaEventDestroy(e);
-        }
-        ctx->cur ^= 1;
-        for (int kind = 0; kind < 4; kind++) ctx->n_list[kind] = ctx->h_pinned[32 + 2 * kind];
-        ctx->n_rebuilds++;
-        ctx->steps_since_rebuild = 0;
-        ctx->need_rebuild = false;
+        uint32_t zeros[DEM_NUM_FLAGS] = {0, 0, 0, 0, 0, 0, 0, 0};
+        zeros[DEM_FLAG_SEQ] = ctx->seq_host;
+        zeros[DEM_FLAG_VELOCITY] = r.velflag;
+        CK(cudaMemcpy(ctx->d_flags, zeros, sizeof(zeros), cudaMemcpyHostToDevice));
+        if (rolled_back) *rolled_back = true;
         return DEM_OK;
+    }
+    for (int kind = 0; kind < 4; kind++) ctx->n_list[kind] = r.count[kind];
+    ctx->last_grid = r.grid;
+    if (ctx->mg.on) memcpy(ctx->mg.last, r.mg, sizeof(r.mg));
+    if (r.velflag != 0u) {
+        const uint32_t zero = 0;
+        cudaMemcpyAsync(ctx->d_flags + DEM_FLAG_VELOCITY, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        return fail(ctx, DEM_ERR_VELOCITY, "an owner has a non-finite or too large velocity (max seen %.6g, limit %.6g) at t=%.9g",
+                    ctx->last_grid.maxvel, ctx->sp.errOutVel, ctx->sim_time);
+    }
+    return DEM_OK;
+}
+
+// enqueue one rebuild with plain launches.  Confirms the previous one first (at most one rebuild is ever unconfirmed:
+// its status slot and the buffers it read from stay untouched until then); when that turns into a roll-back nothing is
+// enqueued and the caller's loop re-evaluates.
+int enqueue_rebuild(DemCtx* ctx, float* stage_us = nullptr) {
+    bool rolled = false;
+    int rc = confirm_rebuild(ctx, &rolled);
+    if (rc) return rc;
+    if (rolled && !stage_us) return DEM_OK;
+    cudaEvent_t sev[8];
+    if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
+    ctx->launches += launch_rebuild_kernels(ctx, stage_us ? sev : nullptr);
+    note_rebuild_enqueued(ctx);
+    if (stage_us) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        // [0] margins+keys+histogram+analytical list [1] sort [2] cell-table scan [3] gather [4] sweep
+        // [5] counts [6] unused [7] whole rebuild on the device
+        for (int k = 0; k < 6; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
+        stage_us[6] = 0.f;
+        cudaEventElapsedTime(&stage_us[7], sev[0], sev[7]);
+        for (int k = 0; k < 8; k++) stage_us[k] *= 1000.f;
+        for (auto& e : sev) cudaEventDestroy(e);
+    }
+    CK(cudaGetLastError());
+    return DEM_OK;
+}
+
+// a rebuild NOW, confirmed before returning (dry run of DoDynamicsThenSync(0), dem_rebuild_contacts, profiling)
+int rebuild_blocking(DemCtx* ctx, float* stage_us = nullptr) {
+    for (int attempt = 0; attempt < 8; attempt++) {
+        ctx->need_rebuild = true;
+        int rc = enqueue_rebuild(ctx, stage_us);
+        if (rc) return rc;
+        if (!ctx->pending.valid) continue;  // the PREVIOUS rebuild had to be rolled back: go again
+        bool rolled = false;
+        rc = confirm_rebuild(ctx, &rolled);
+        if (rc) return rc;
+        if (!rolled) return DEM_OK;
     }
     return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
 }
@@ -681,42 +717,36 @@ int launch_step(DemCtx* ctx) {
     } else {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
-    {
-        int l = 0;
-        int rc = integrate_and_exchange(ctx, P, &l);
-        if (rc) return rc;
-        ctx->launches += l;
-    }
+    // integration; on several GPUs the integrator itself stores the halo records into the neighbours' buffers and
+    // k_mg_pull, next in the stream, publishes the exchange number, waits for theirs and scatters what they stored here
+    launch_integrate(P, ctx->num_sms, ctx->stream);
+    if (ctx->mg.on) ctx->launches += launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, ctx->stream);
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
     return DEM_OK;
 }
 
-int enqueue_step(DemCtx* ctx) {
-    if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
-        int rc = rebuild(ctx);
-        if (rc) return rc;
-    }
-    int rc = launch_step(ctx);
-    if (rc) return rc;
-    ctx->n_steps++;
-    ctx->steps_since_rebuild++;
-    ctx->sim_time += (double)ctx->sp.h;
-    return DEM_OK;
+void note_steps_enqueued(DemCtx* ctx, uint64_t n) {
+    ctx->n_steps += n;
+    ctx->steps_since_rebuild += n;
+    for (uint64_t i = 0; i < n; i++) ctx->sim_time += (double)ctx->sp.h;
 }
 
 // ---- CUDA graph of one contact-list cycle -------------------------------------------------------------------------
-// Between two rebuilds every step launches the same kernels with the same parameters (only the max|v| slot alternates),
-// so a scene whose step is shorter than the host's launch path (three to four launches, two event records and two
-// stream waits: ~20 us) is launch bound.  The whole cycle of cd_update_freq steps is captured once per contact-list
-// buffer and replayed with ONE cudaGraphLaunch; it stays valid for as long as the kernel parameters are byte-identical.
-void graph_config(const DemCtx* ctx, int cfg[8]) {
+// A cycle -- the rebuild and the cd_update_freq steps that use its lists -- launches the same kernels with the same
+// parameters every time (all counts, the grid, exchange numbers live in device memory; only the list buffer and the
+// max|v| slot alternate), so a scene whose step is shorter than the host's launch path (three to five launches, two
+// event records and two stream waits: ~20 us), or a decomposed run whose ranks must not drift apart, is captured once per
+// (list buffer, max|v| slot) and replayed with ONE cudaGraphLaunch; the graph stays valid for as long as the kernel
+// parameters are byte-identical.
+void graph_config(const DemCtx* ctx, int cfg[10]) {
     cfg[0] = (int)ctx->sp.force_model; cfg[1] = (int)ctx->sp.record_contact_forces; cfg[2] = ctx->ctas_per_sm;
     cfg[3] = ctx->fast_math; cfg[4] = ctx->overlap_walls; cfg[5] = (int)ctx->nAnal; cfg[6] = (int)ctx->nTri; cfg[7] = ctx->sa_grid;
+    cfg[8] = ctx->sort_mode; cfg[9] = ctx->key_bits;
 }
 bool graph_wanted(const DemCtx* ctx) {
-    if (ctx->mg.on || ctx->use_graph == 0) return false;
-    if (ctx->use_graph == 1) return true;
+    if (ctx->use_graph == 0) return false;
+    if (ctx->use_graph == 1 || ctx->mg.on) return true;
     return ctx->nSpheres <= 262144u;  // beyond that a step outlasts its launches
 }
 void graph_drop(DemCtx* ctx) {
@@ -727,21 +757,27 @@ void graph_drop(DemCtx* ctx) {
             g.L = 0;
         }
 }
-// run one full cycle (L = cd_update_freq steps, starting right after a rebuild) through the graph; returns DEM_OK and
-// sets *done on success, leaves *done false when the caller should fall back to plain launches
+// run one full cycle (the due rebuild + L = cd_update_freq steps) through the graph; sets *done on success, leaves it
+// false when the caller should fall back to plain launches (or re-evaluate after a roll-back)
 int run_cycle_graph(DemCtx* ctx, bool* done) {
     *done = false;
+    bool rolled = false;
+    int rc = confirm_rebuild(ctx, &rolled);
+    if (rc) return rc;
+    if (rolled || ctx->need_maxvel) return DEM_OK;
     const uint32_t L = ctx->sp.cd_update_freq;
     DemCtx::CycleGraph& G = ctx->graphs[ctx->cur][ctx->maxvel_slot];
     const DevParams P = make_params(ctx);
-    int cfg[8];
+    const CdParams C = make_cd(ctx);
+    int cfg[10];
     graph_config(ctx, cfg);
-    if (G.exec && (G.L != L || memcmp(&G.P0, &P, sizeof(P)) != 0 || memcmp(G.cfg, cfg, sizeof(cfg)) != 0)) {
+    if (G.exec && (G.L != L || memcmp(&G.P0, &P, sizeof(P)) != 0 || memcmp(&G.C0, &C, sizeof(C)) != 0 ||
+                   memcmp(G.cfg, cfg, sizeof(cfg)) != 0)) {
         cudaGraphExecDestroy(G.exec);
         G.exec = nullptr;
     }
     if (!G.exec) {
-        const int slot0 = ctx->maxvel_slot;
+        const int slot0 = ctx->maxvel_slot, cur0 = ctx->cur;
         const uint64_t launches0 = ctx->launches;
         cudaGraph_t graph = nullptr;
         if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
@@ -749,10 +785,14 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
             ctx->use_graph = 0;
             return DEM_OK;
         }
-        int rc = DEM_OK;
+        ctx->launches += launch_rebuild_kernels(ctx, nullptr);
+        ctx->cur ^= 1;
+        rc = DEM_OK;
         for (uint32_t i = 0; i < L && rc == DEM_OK; i++) rc = launch_step(ctx);
         const cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        G.launches = ctx->launches - launches0;
         ctx->maxvel_slot = slot0;
+        ctx->cur = cur0;
         ctx->launches = launches0;
         if (rc != DEM_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&G.exec, graph, 0) != cudaSuccess) {
             cudaGetLastError();
@@ -764,22 +804,63 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
         }
         cudaGraphDestroy(graph);
         G.P0 = P;
+        G.C0 = C;
         G.L = L;
         memcpy(G.cfg, cfg, sizeof(cfg));
     }
     CK(cudaGraphLaunch(G.exec, ctx->stream));
     ctx->graph_launches++;
+    ctx->launches += G.launches;
+    note_rebuild_enqueued(ctx);
     ctx->maxvel_slot ^= (int)(L & 1u);
-    ctx->launches += (uint64_t)L * (2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0));
-    ctx->n_steps += L;
-    ctx->steps_since_rebuild += L;
-    for (uint32_t i = 0; i < L; i++) ctx->sim_time += (double)ctx->sp.h;
+    note_steps_enqueued(ctx, L);
     *done = true;
     return DEM_OK;
 }
 
+// enqueue steps until n_steps has caught up with steps_target; never waits for the device except to confirm the
+// rebuild before the one being enqueued
+int pump(DemCtx* ctx) {
+    while (ctx->n_steps < ctx->steps_target) {
+        const uint32_t L = ctx->sp.cd_update_freq;
+        if (ctx->need_rebuild || ctx->steps_since_rebuild >= L) {
+            if (graph_wanted(ctx) && !ctx->need_maxvel && L >= 2 && ctx->steps_target - ctx->n_steps >= L) {
+                bool done = false;
+                int rc = run_cycle_graph(ctx, &done);
+                if (rc) return rc;
+                if (done) continue;
+                if (!ctx->need_rebuild && ctx->steps_since_rebuild < L) continue;
+            }
+            const uint64_t before = ctx->seq_host;
+            int rc = enqueue_rebuild(ctx);
+            if (rc) return rc;
+            if (ctx->seq_host == before) continue;  // rolled back instead: re-evaluate
+        }
+        int rc = launch_step(ctx);
+        if (rc) return rc;
+        note_steps_enqueued(ctx, 1);
+    }
+    CK(cudaGetLastError());
+    return DEM_OK;
+}
+
+// wait for everything enqueued, confirm the last rebuild, replay what a failed rebuild dropped
+int settle(DemCtx* ctx) {
+    for (int attempt = 0; attempt < 16; attempt++) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        bool rolled = false;
+        int rc = confirm_rebuild(ctx, &rolled);
+        if (rc) return rc;
+        if (ctx->n_steps >= ctx->steps_target) return DEM_OK;
+        rc = pump(ctx);
+        if (rc) return rc;
+    }
+    return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
+}
+
 }  // namespace
 
+// ===============================================================================================================
 // ===============================================================================================================
 extern "C" {
 
@@ -870,6 +951,14 @@ int dem_ctx_create(DemCtx** out, int device) {
     cudaGetDeviceProperties(&prop, device);
     ctx->num_sms = prop.multiProcessorCount;
     cudaHostAlloc((void**)&ctx->h_pinned, 256 * sizeof(uint32_t), cudaHostAllocDefault);
+    // status ring of the rebuilds: written by the device (k_finish_counts), polled by the host
+    if (cudaHostAlloc((void**)&ctx->h_status, sizeof(RebuildStatus) * REBUILD_STATUS_SLOTS, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&ctx->d_status, ctx->h_status, 0) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return DEM_ERR_CUDA;
+    }
+    memset(ctx->h_status, 0, sizeof(RebuildStatus) * REBUILD_STATUS_SLOTS);
     if (const char* e = getenv("DEMB_CTAS_PER_SM")) ctx->ctas_per_sm = std::max(2, std::min(4, atoi(e)));
     if (const char* e = getenv("DEMB_FAST_MATH")) ctx->fast_math = atoi(e);
     for (int k = 0; k < 5; k++) cudaEventCreate(&ctx->ev[k]);
@@ -885,26 +974,18 @@ int dem_ctx_destroy(DemCtx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
-    {
-        MgState& g = ctx->mg;
-        dfree(g.d_flag); dfree(g.d_active_list); dfree(g.d_act_sph); dfree(g.d_send_slot[0]); dfree(g.d_send_slot[1]); dfree(g.d_counts); dfree(g.d_allcounts); dfree(g.d_block_counter);
-        for (int d = 0; d < 2; d++)
-            if (g.peer_block[d]) cudaIpcCloseMemHandle(g.peer_block[d]);
-        if (g.p2p_block) cudaFree(g.p2p_block);
-        for (int d = 0; d < 2; d++) {
-            dfree(g.d_send_gid[d]); dfree(g.d_recv_gid[d]);
-            if (g.d_sendbuf[d]) cudaFree(g.d_sendbuf[d]);
-            if (g.d_recvbuf[d]) cudaFree(g.d_recvbuf[d]);
-        }
-    }
+    free_mg(ctx);
     graph_drop(ctx);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
-    if (ctx->h_famblob) cudaFreeHost(ctx->h_famblob);
-    if (ctx->ev_fam) cudaEventDestroy(ctx->ev_fam);
+    if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    for (int k = 0; k < 2; k++) {
+        if (ctx->h_famblob[k]) cudaFreeHost(ctx->h_famblob[k]);
+        if (ctx->ev_fam[k]) cudaEventDestroy(ctx->ev_fam[k]);
+    }
     for (int k = 0; k < 5; k++)
         if (ctx->ev[k]) cudaEventDestroy(ctx->ev[k]);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -1152,6 +1233,8 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
         if (ctx->h_tri_info[i].x >= ctx->nOwners || ctx->h_tri_info[i].y >= ctx->nMat)
             return fail(ctx, DEM_ERR_INVALID, "triangle %u has a bad owner or material", i);
     CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    free_mg(ctx);  // (a re-initialised context is a single-GPU context again)
     free_device(ctx);
     int rc;
     const uint32_t nO = ctx->nOwners, nS = ctx->nSpheres;
@@ -1168,7 +1251,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     ctx->d_masks = reinterpret_cast<uint8_t*>(ctx->d_famblob + FAM_OFF_MASKS);
     ctx->d_extra = reinterpret_cast<float*>(ctx->d_famblob + FAM_OFF_EXTRA);
     ctx->d_presc = reinterpret_cast<Prescr*>(ctx->d_famblob + FAM_OFF_PRESC);
-    if ((rc = dalloc(ctx, &ctx->d_flags, 4))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_flags, DEM_NUM_FLAGS))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_maxvel, 4))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_reduce, 4))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_reduce_many, 8))) return rc;
@@ -1187,7 +1270,12 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
         if (rcf) return rcf;
         CK(cudaStreamSynchronize(ctx->stream));
     }
-    CK(cudaMemset(ctx->d_flags, 0, sizeof(uint32_t) * 4));
+    CK(cudaMemset(ctx->d_flags, 0, sizeof(uint32_t) * DEM_NUM_FLAGS));
+    memset(ctx->h_status, 0, sizeof(RebuildStatus) * REBUILD_STATUS_SLOTS);
+    ctx->seq_host = 0;
+    ctx->pending = PendingRebuild();
+    ctx->steps_target = ctx->n_steps;
+    graph_drop(ctx);
 
     // broad-phase sizing: the smallest cell the device may ever pick bounds the cell table and the sort key width
     {
@@ -1208,14 +1296,18 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
         if ((rc = dalloc(ctx, &ctx->d_vals[k], nS))) return rc;
     }
     if ((rc = dalloc(ctx, &ctx->d_cellStart, (size_t)ctx->max_cells + 2))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_sortedSph, nS))) return rc;
+    // (+2: the sweep stages these streams with 16-byte bulk copies that may start / end one entry outside a run)
+    if ((rc = dalloc(ctx, &ctx->d_sortedSph, (size_t)nS + 2))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_sortedAux, (size_t)nS + 2))) return rc;
+    CK(cudaMemset(ctx->d_sortedSph, 0, sizeof(float4) * ((size_t)nS + 2)));
+    CK(cudaMemset(ctx->d_sortedAux, 0, sizeof(uint2) * ((size_t)nS + 2)));
     if ((rc = dalloc(ctx, &ctx->d_sortedMeta, nS))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_analw, ctx->h_anal.size()))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_sortedPos, nS))) return rc;
     const size_t rs_blocks = ((size_t)nS + 4095) / 4096 + 1;
     if ((rc = dalloc(ctx, &ctx->d_rs_hist, 256 * rs_blocks))) return rc;
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
     if ((rc = dalloc(ctx, &ctx->d_scan_tmp, scan_n / 4096 + 2))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_scan_desc, scan_n / 4096 + 8))) return rc;
 
     if (ctx->nTri) {
         const uint32_t nT = ctx->nTri;
@@ -1253,13 +1345,15 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
                      const float* wildcards4) {
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if (n && (!idA || !idB || !type)) return DEM_ERR_INVALID;
-    if (n > ctx->capacity) return fail(ctx, DEM_ERR_CAPACITY, "dem_set_contacts: %llu contacts exceed capacity %llu",
-                                       (unsigned long long)n, (unsigned long long)ctx->capacity);
     CK(cudaSetDevice(ctx->device));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
+    if (n > ctx->capacity) {
+        int rc = grow_lists(ctx, n + n / 4 + 1024);
+        if (rc) return rc;
+    }
     // Build host-side "previous" lists grouped by sphere A so that the next rebuild carries the history over.
     const uint32_t nS = ctx->nSpheres;
     for (int which = 0; which < 3; which++) {
-        if (which == 2 && ctx->nTri == 0) break;
         std::vector<uint64_t> idx;
         for (uint64_t i = 0; i < n; i++) {
             const bool is_ss = type[i] == DEM_CNT_SPHERE_SPHERE;
@@ -1267,15 +1361,16 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
             const bool is_st = type[i] == DEM_CNT_SPHERE_MESH;
             if ((which == 0 && is_ss) || (which == 1 && is_sa) || (which == 2 && is_st)) idx.push_back(i);
         }
+        if (which == 2 && ctx->nTri == 0) break;
         std::stable_sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return idA[a] < idA[b]; });
-        std::vector<uint2> pair(idx.size());
+        std::vector<uint32_t> gb(idx.size());
         std::vector<uint4> cinfo(idx.size());
         std::vector<float4> hist(idx.size());
         std::vector<uint32_t> start(nS + 1, 0), count(nS + 1, 0);
         for (size_t k = 0; k < idx.size(); k++) {
             const uint64_t i = idx[k];
             if (idA[i] >= nS) return fail(ctx, DEM_ERR_INVALID, "contact %llu: bad geometry A", (unsigned long long)i);
-            pair[k] = make_uint2(idA[i], idB[i]);
+            gb[k] = idB[i];
             float4 h = make_float4(0, 0, 0, 0);
             if (wildcards4) h = make_float4(wildcards4[4 * i], wildcards4[4 * i + 1], wildcards4[4 * i + 2], wildcards4[4 * i + 3]);
             hist[k] = h;
@@ -1283,19 +1378,24 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
             cinfo[k] = make_uint4(0, 0, 0, alive ? 0x80000000u : 0u);
             count[idA[i]]++;
         }
-        for (uint32_t s = 0, run = 0; s < nS; s++) { start[s] = run; run += count[s]; }
+        for (uint32_t sp = 0, run = 0; sp < nS; sp++) { start[sp] = run; run += count[sp]; }
         ListBuf& L = (which == 0) ? ctx->lists[0][ctx->cur] : ctx->lists[which == 1 ? 2 : 3][ctx->cur];
-        const uint32_t cnt = (uint32_t)idx.size();
-        CK(cudaMemcpy(L.pair, pair.data(), sizeof(uint2) * idx.size(), cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(L.idB, gb.data(), sizeof(uint32_t) * idx.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.cinfo, cinfo.data(), sizeof(uint4) * idx.size(), cudaMemcpyHostToDevice));
         if (L.hist) CK(cudaMemcpy(L.hist, hist.data(), sizeof(float4) * idx.size(), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.seg_start, start.data(), sizeof(uint32_t) * (nS + 1), cudaMemcpyHostToDevice));
         CK(cudaMemcpy(L.seg_count, count.data(), sizeof(uint32_t) * (nS + 1), cudaMemcpyHostToDevice));
         // the old list is only a history source: its count is not used by force kernels until the rebuild swaps
-        const uint32_t zero = 0;
-        (void)cnt;
-        CK(cudaMemcpy(L.count, &zero, sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CK(cudaMemset(L.count, 0, sizeof(uint32_t) * 4));
     }
+    // the sphere--sphere candidate list of the same buffer holds no restored contact: leave nothing stale behind for
+    // the history search to match first
+    {
+        ListBuf& L = ctx->lists[1][ctx->cur];
+        CK(cudaMemset(L.seg_count, 0, sizeof(uint32_t) * ((size_t)nS + 1)));
+        CK(cudaMemset(L.count, 0, sizeof(uint32_t) * 4));
+    }
+    for (auto& v : ctx->n_list) v = 0;
     ctx->need_rebuild = true;
     return DEM_OK;
 }
@@ -1303,40 +1403,26 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
 int dem_rebuild_contacts(DemCtx* ctx) {
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    return rebuild(ctx);
+    int rc = settle(ctx);
+    if (rc) return rc;
+    return rebuild_blocking(ctx);
 }
 
 int dem_step_async(DemCtx* ctx, uint64_t n_steps) {
     if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
     CK(cudaSetDevice(ctx->device));
-    uint64_t i = 0;
-    while (i < n_steps) {
-        if (graph_wanted(ctx) && n_steps - i >= ctx->sp.cd_update_freq && ctx->sp.cd_update_freq >= 2) {
-            // a whole contact-list cycle ahead: rebuild now if one is due, then replay the cycle's graph
-            if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
-                int rc = rebuild(ctx);
-                if (rc) return rc;
-            }
-            if (ctx->steps_since_rebuild == 0) {
-                bool done = false;
-                int rc = run_cycle_graph(ctx, &done);
-                if (rc) return rc;
-                if (done) { i += ctx->sp.cd_update_freq; continue; }
-            }
-        }
-        int rc = enqueue_step(ctx);
-        if (rc) return rc;
-        i++;
-    }
-    CK(cudaGetLastError());
-    return DEM_OK;
+    ctx->steps_target = ctx->n_steps + n_steps;
+    return pump(ctx);
 }
 
 int dem_sync(DemCtx* ctx) {
     if (!ctx) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return DEM_OK;
+    if (!ctx->initialized) {
+        CK(cudaStreamSynchronize(ctx->stream));
+        return DEM_OK;
+    }
+    return settle(ctx);
 }
 
 int dem_step(DemCtx* ctx, uint64_t n_steps) {
@@ -1377,7 +1463,7 @@ int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* 
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
     std::vector<float4> sp;
@@ -1413,7 +1499,7 @@ int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz32
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
     const DemSimParams& p = ctx->sp;
@@ -1438,7 +1524,7 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     std::vector<float4> sp(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
@@ -1474,7 +1560,7 @@ int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out
                                  uint8_t* type, float* wildcards4, float* force_xyz, float* point_xyz) {
     if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2] + ctx->n_list[3];
     *n_out = n;
     if (!idA && !idB && !type && !wildcards4 && !force_xyz && !point_xyz) return DEM_OK;
@@ -1486,9 +1572,18 @@ int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out
         const ListBuf& L = ctx->lists[kind][ctx->cur];
         const uint64_t m = ctx->n_list[kind];
         const int which = (kind == 2) ? 1 : (kind == 3 ? 2 : 0);
-        std::vector<uint2> pair(m);
+        // geometry A of a contact is the sphere whose segment it lies in
+        std::vector<uint2> pair(m, make_uint2(0xffffffffu, 0u));
+        {
+            std::vector<uint32_t> gb(m), ss(ctx->nSpheres), sc(ctx->nSpheres);
+            CK(cudaMemcpy(gb.data(), L.idB, sizeof(uint32_t) * m, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(ss.data(), L.seg_start, sizeof(uint32_t) * ctx->nSpheres, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(sc.data(), L.seg_count, sizeof(uint32_t) * ctx->nSpheres, cudaMemcpyDeviceToHost));
+            for (uint64_t i = 0; i < m; i++) pair[i].y = gb[i];
+            for (uint32_t sp = 0; sp < ctx->nSpheres; sp++)
+                for (uint32_t k = 0; k < sc[sp] && (uint64_t)ss[sp] + k < m; k++) pair[(size_t)ss[sp] + k].x = sp;
+        }
         std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0)), cpt(m, make_float4(0, 0, 0, 0));
-        CK(cudaMemcpy(pair.data(), L.pair, sizeof(uint2) * m, cudaMemcpyDeviceToHost));
         if (L.hist) CK(cudaMemcpy(hist.data(), L.hist, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         if (L.force) CK(cudaMemcpy(frc.data(), L.force, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         if (L.cpoint && point_xyz) CK(cudaMemcpy(cpt.data(), L.cpoint, sizeof(float4) * m, cudaMemcpyDeviceToHost));
@@ -1625,121 +1720,266 @@ int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float 
     return DEM_OK;
 }
 
-int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]) {
-    if (!ctx || !ctx->initialized || !unique_id || world < 1 || rank < 0 || rank >= world) return DEM_ERR_INVALID;
-    if (world == 1) return DEM_OK;
-    // Wall owners (analytical boundaries) are replicated on every rank, which is exact while they are fixed or follow a
-    // prescribed motion; a mesh additionally needs its facets partitioned with the slabs, which is not built yet.
-    if (ctx->nTri > 0)
-        return fail(ctx, DEM_ERR_INVALID, "the slab decomposition does not cover triangle meshes yet: run scenes with meshes on one GPU");
-    if (!g_nccl.load()) return fail(ctx, DEM_ERR_INVALID, "NCCL (libnccl.so.2) could not be loaded");
+} // extern "C"
+
+namespace {
+
+// Everything of the decomposition that does not depend on how the peers' blocks get mapped: slab, buffers, the initial
+// ownership.  Leaves g.my_block allocated and zeroed; the caller fills g.peer_block[] and switches g.on.
+int mg_prepare(DemCtx* ctx, int rank, int world) {
+    if (world > (int)MG_MAX_WORLD) return fail(ctx, DEM_ERR_INVALID, "at most %u ranks (GPUs of one box)", MG_MAX_WORLD);
+    // Wall and mesh owners are replicated on every rank and feel only the contacts of that rank's slab: exact as long as
+    // their motion does not depend on the forces on them, i.e. while they are fixed or fully prescribed.
+    for (uint32_t o = ctx->nClumpOwners; o < ctx->nOwners; o++) {
+        const Prescr& pr = ctx->h_presc[ctx->h_state[o].pos.family];
+        bool ok = pr.used != 0;
+        for (int k = 0; k < 3; k++) ok = ok && (pr.linVelPrescribed[k] || pr.linPosPrescribed[k]) && (pr.rotVelPrescribed[k] || pr.rotPosPrescribed);
+        if (!ok)
+            return fail(ctx, DEM_ERR_INVALID, "owner %u (an analytical object or a mesh, family %u) moves freely: on several "
+                        "GPUs such owners must be fixed or follow a fully prescribed motion", o, (unsigned)ctx->h_state[o].pos.family);
+    }
     CK(cudaSetDevice(ctx->device));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
+    free_mg(ctx);
     MgState& g = ctx->mg;
     g.rank = rank; g.world = world;
-    ncclUniqueId id;
-    memcpy(&id, unique_id, 128);
-    NC(g_nccl.CommInitRank(&g.comm, world, id, rank));
     dem_host_slab_bounds(&ctx->sp, world, rank, &g.cut_lo, &g.cut_hi);
-    const uint32_t nO = ctx->nOwners;
+    const uint32_t nO = ctx->nOwners, nS = ctx->nSpheres;
     // halo buffers: a quarter of the owners per side is far more than a slab's boundary layer ever holds
     g.cap = std::max<uint32_t>(4096u, nO / (world > 2 ? 2u : 4u));
     int rc;
     if ((rc = dalloc(ctx, &g.d_flag, nO))) return rc;
-    if ((rc = dalloc(ctx, &g.d_active_list, nO))) return rc;
-    if ((rc = dalloc(ctx, &g.d_act_sph, std::max<uint32_t>(ctx->nSpheres, 1u)))) return rc;
+    for (int p = 0; p < 2; p++) {
+        if ((rc = dalloc(ctx, &g.d_active_list[p], nO))) return rc;
+        for (int d = 0; d < 2; d++)
+            if ((rc = dalloc(ctx, &g.d_send_gid[p][d], g.cap))) return rc;
+    }
+    if ((rc = dalloc(ctx, &g.d_act_sph, std::max<uint32_t>(nS, 1u)))) return rc;
     for (int d = 0; d < 2; d++) {
         if ((rc = dalloc(ctx, &g.d_send_slot[d], std::max<uint32_t>(nO, 1u)))) return rc;
         CK(cudaMemset(g.d_send_slot[d], 0xff, sizeof(int32_t) * std::max<uint32_t>(nO, 1u)));
     }
-    // The fused push was verified on hardware with two ranks (tests/mgpu_check.py); with more ranks an interior rank
-    // pushes in both directions, which has not been run yet: keep the separate push kernel there unless asked.
-    g.fuse_push = (world == 2);
-    if (const char* e = getenv("DEM_B200_FUSED_PUSH")) g.fuse_push = atoi(e) != 0;
-    if (getenv("DEM_B200_NO_FUSED_PUSH")) g.fuse_push = false;
-    if ((rc = dalloc(ctx, &g.d_counts, 8))) return rc;
-    if ((rc = dalloc(ctx, &g.d_allcounts, 8 * (size_t)world))) return rc;
-    for (int d = 0; d < 2; d++) {
-        if ((rc = dalloc(ctx, &g.d_send_gid[d], g.cap))) return rc;
-        if ((rc = dalloc(ctx, &g.d_recv_gid[d], g.cap))) return rc;
-        CK(cudaMalloc(&g.d_sendbuf[d], (size_t)g.cap * 80));
-        CK(cudaMalloc(&g.d_recvbuf[d], (size_t)g.cap * 80));
-        ctx->device_bytes += 2 * (size_t)g.cap * 80;
+    if ((rc = dalloc(ctx, &g.d_counts, 16))) return rc;
+    if ((rc = dalloc(ctx, &g.d_ctrs, 4))) return rc;
+    CK(cudaMemset(g.d_counts, 0, sizeof(uint32_t) * 16));
+    CK(cudaMemset(g.d_ctrs, 0, sizeof(unsigned long long) * 4));
+    // per owner {first sphere, number of spheres} when the spheres of every owner are contiguous (they are as the
+    // reference flattens clumps, dT.cpp:638-1024): the rebuild then lists the active spheres without a pass over all
+    {
+        std::vector<uint2> os(nO, make_uint2(0u, 0u));
+        bool contiguous = true;
+        for (uint32_t i = 0; i < nS && contiguous; i++) {
+            const uint32_t o = ctx->h_sph[i].x;
+            if (os[o].y == 0) os[o].x = i;
+            else if (os[o].x + os[o].y != i) contiguous = false;
+            os[o].y++;
+        }
+        if (contiguous) {
+            if ((rc = dalloc(ctx, &g.d_owner_sph, nO))) return rc;
+            CK(cudaMemcpy(g.d_owner_sph, os.data(), sizeof(uint2) * nO, cudaMemcpyHostToDevice));
+        }
     }
     // initial ownership from the uploaded positions: own inside my slab, unknown elsewhere (the first rebuild brings
-    // the ghosts in); replicated analytical owners are owned everywhere
-    std::vector<uint8_t> flag(nO, 0);
-    const DemSimParams& p = ctx->sp;
-    for (uint32_t o = 0; o < nO; o++) {
-        if (o >= ctx->nClumpOwners) { flag[o] = 1; continue; }
-        const OwnerPos& s = ctx->h_state[o].pos;
-        const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
-        const float x = (float)((double)vx * p.voxelSize + (double)s.lx * p.l);
-        flag[o] = (x >= g.cut_lo && x < g.cut_hi) ? 1 : 0;
-    }
-    CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
-    // ---- peer-memory exchange: map the neighbours' receive blocks (falls back to ncclSend/ncclRecv if that fails) ----
+    // the ghosts in); replicated analytical / mesh owners are owned everywhere.  The "previous cycle's active list" the
+    // first rebuild walks is the list of these own owners.
     {
-        const size_t block_bytes = 256 + 4 * (size_t)g.cap * 80;
-        CK(cudaMalloc((void**)&g.p2p_block, block_bytes));
-        CK(cudaMemset(g.p2p_block, 0, block_bytes));
-        ctx->device_bytes += block_bytes;
-        if ((rc = dalloc(ctx, &g.d_block_counter, 4))) return rc;
-        CK(cudaMemset(g.d_block_counter, 0, 16));
-        cudaIpcMemHandle_t mine;
-        bool ok = cudaIpcGetMemHandle(&mine, g.p2p_block) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
-        // all-gather {handle, ok} over the communicator we already have
-        const size_t rec = sizeof(cudaIpcMemHandle_t) + 8;
-        std::vector<char> h_all(rec * world), h_me(rec, 0);
-        memcpy(h_me.data(), &mine, sizeof(mine));
-        h_me[sizeof(mine)] = ok ? 1 : 0;
-        char *d_me = nullptr, *d_all = nullptr;
-        CK(cudaMalloc((void**)&d_me, rec));
-        CK(cudaMalloc((void**)&d_all, rec * world));
-        CK(cudaMemcpy(d_me, h_me.data(), rec, cudaMemcpyHostToDevice));
-        NC(g_nccl.AllGather(d_me, d_all, rec, ncclUint8, g.comm, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        CK(cudaMemcpy(h_all.data(), d_all, rec * world, cudaMemcpyDeviceToHost));
-        cudaFree(d_me); cudaFree(d_all);
-        bool all_ok = getenv("DEM_B200_NO_P2P") == nullptr;
-        for (int r = 0; r < world; r++) all_ok = all_ok && h_all[rec * r + sizeof(mine)] == 1;
-        for (int d = 0; d < 2 && all_ok; d++) {
-            const int peer = rank + (d == 0 ? -1 : 1);
-            if (peer < 0 || peer >= world) continue;
-            cudaIpcMemHandle_t h;
-            memcpy(&h, h_all.data() + rec * peer, sizeof(h));
-            void* ptr = nullptr;
-            if (cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                cudaGetLastError();
-                all_ok = false;
+        std::vector<uint8_t> flag(nO, 0);
+        std::vector<uint32_t> act;
+        const DemSimParams& p = ctx->sp;
+        // (what the device holds now, not what was uploaded: the context may have stepped on one GPU before)
+        std::vector<OwnerState> st(nO);
+        CK(cudaMemcpy(st.data(), ctx->d_state, sizeof(OwnerState) * nO, cudaMemcpyDeviceToHost));
+        for (uint32_t o = 0; o < nO; o++) {
+            bool own = true;
+            if (o < ctx->nClumpOwners) {
+                const OwnerPos& s = st[o].pos;
+                const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
+                const float x = (float)((double)vx * p.voxelSize + (double)s.lx * p.l);
+                own = (x >= g.cut_lo && x < g.cut_hi);
             }
-            g.peer_block[d] = (char*)ptr;
+            flag[o] = own ? 1 : 0;
+            if (own) act.push_back(o);
         }
-        // every rank must take the same path: agree on the verdict
-        int* d_ok = nullptr;
-        CK(cudaMalloc((void**)&d_ok, sizeof(int)));
-        const int mine_ok = all_ok ? 1 : 0;
-        CK(cudaMemcpy(d_ok, &mine_ok, sizeof(int), cudaMemcpyHostToDevice));
-        NC(g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt32, ncclMin, g.comm, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
-        int verdict = 0;
-        CK(cudaMemcpy(&verdict, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
-        cudaFree(d_ok);
-        g.p2p = verdict == 1;
-        g.epoch = 0;
+        CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
+        const int prev = ctx->cur;  // the first rebuild builds parity cur^1 and walks the list of parity cur
+        CK(cudaMemcpy(g.d_active_list[prev], act.data(), sizeof(uint32_t) * act.size(), cudaMemcpyHostToDevice));
+        uint32_t cnt[8] = {0, 0, 0, (uint32_t)act.size(), 0, 0, 0, 0};
+        CK(cudaMemcpy(g.d_counts + 8 * prev, cnt, sizeof(cnt), cudaMemcpyHostToDevice));
     }
-    if (ctx->sort_mode != 1) ctx->sort_mode = 1;  // the radix path has no notion of inactive spheres
-    g.on = true;
+    const size_t block_bytes = mg_block_bytes(g.cap);
+    CK(cudaMalloc((void**)&g.my_block, block_bytes));
+    CK(cudaMemset(g.my_block, 0, block_bytes));
+    ctx->device_bytes += block_bytes;
+    return DEM_OK;
+}
+
+void mg_switch_on(DemCtx* ctx) {
+    ctx->sort_mode = 1;  // the radix path has no notion of inactive spheres
+    ctx->mg.on = true;
     ctx->need_rebuild = true;
     ctx->need_maxvel = true;
+    graph_drop(ctx);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]) {
+    if (!ctx || !ctx->initialized || !unique_id || world < 1 || rank < 0 || rank >= world) return DEM_ERR_INVALID;
+    if (world == 1) return DEM_OK;
+    if (!g_nccl.load()) return fail(ctx, DEM_ERR_INVALID, "NCCL (libnccl.so.2) could not be loaded");
+    int rc = mg_prepare(ctx, rank, world);
+    if (rc) return rc;
+    MgState& g = ctx->mg;
+    g.local = false;
+    // bootstrap: NCCL carries the cudaIpc handles of the peer blocks once; nothing after this goes through a library
+    ncclUniqueId id;
+    memcpy(&id, unique_id, 128);
+    NC(g_nccl.CommInitRank(&g.comm, world, id, rank));
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, g.my_block));
+    const size_t rec = sizeof(cudaIpcMemHandle_t);
+    std::vector<char> h_all(rec * world);
+    char *d_me = nullptr, *d_all = nullptr;
+    CK(cudaMalloc((void**)&d_me, rec));
+    CK(cudaMalloc((void**)&d_all, rec * world));
+    CK(cudaMemcpy(d_me, &mine, rec, cudaMemcpyHostToDevice));
+    NC(g_nccl.AllGather(d_me, d_all, rec, ncclUint8, g.comm, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(h_all.data(), d_all, rec * world, cudaMemcpyDeviceToHost));
+    cudaFree(d_me); cudaFree(d_all);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { g.peer_block[r] = g.my_block; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, h_all.data() + rec * r, sizeof(h));
+        void* ptr = nullptr;
+        const cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, DEM_ERR_CUDA, "rank %d cannot map the exchange block of rank %d (%s): the decomposition needs "
+                        "peer access between the GPUs (NVLink / NVSwitch)", rank, r, cudaGetErrorString(e));
+        }
+        g.peer_block[r] = (char*)ptr;
+        g.peer_ipc[r] = true;
+    }
+    mg_switch_on(ctx);
+    return DEM_OK;
+}
+
+/* All ranks are contexts of THIS process, one per GPU: the blocks are mapped with cudaDeviceEnablePeerAccess.  Contexts
+ * of a local group must be stepped together through dem_group_step / dem_group_sync (their kernels wait for each other
+ * on the device). */
+int dem_mgpu_init_local(DemCtx** ctxs, int world) {
+    if (!ctxs || world < 1) return DEM_ERR_INVALID;
+    if (world == 1) return DEM_OK;
+    for (int r = 0; r < world; r++)
+        if (!ctxs[r] || !ctxs[r]->initialized) return DEM_ERR_INVALID;
+    for (int r = 0; r < world; r++) {
+        DemCtx* ctx = ctxs[r];
+        int rc = mg_prepare(ctx, r, world);
+        if (rc) return rc;
+        ctx->mg.local = true;
+        for (int q = 0; q < world; q++) {
+            if (q == r || ctxs[q]->device == ctx->device) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[q]->device));
+            if (!can) return fail(ctx, DEM_ERR_CUDA, "GPU %d cannot access GPU %d's memory", ctx->device, ctxs[q]->device);
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return fail(ctx, DEM_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", ctx->device, ctxs[q]->device, cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    }
+    for (int r = 0; r < world; r++) {
+        for (int q = 0; q < world; q++) ctxs[r]->mg.peer_block[q] = ctxs[q]->mg.my_block;
+        mg_switch_on(ctxs[r]);
+    }
+    return DEM_OK;
+}
+
+/* n steps on every context of a local group, cycle by cycle across the ranks so that no rank's host-side wait can come
+ * before the work its peers' kernels are waiting for has been enqueued.  dem_group_sync blocks until all are done. */
+int dem_group_step_async(DemCtx** ctxs, int world, uint64_t n_steps) {
+    if (!ctxs || world < 1) return DEM_ERR_INVALID;
+    for (int r = 0; r < world; r++) {
+        if (!ctxs[r] || !ctxs[r]->initialized) return DEM_ERR_INVALID;
+        ctxs[r]->steps_target = ctxs[r]->n_steps + n_steps;
+    }
+    for (;;) {
+        bool busy = false;
+        for (int r = 0; r < world; r++) {
+            DemCtx* ctx = ctxs[r];
+            if (ctx->n_steps >= ctx->steps_target) continue;
+            busy = true;
+            CK(cudaSetDevice(ctx->device));
+            // one cycle's worth: up to the next rebuild boundary
+            const uint64_t target = ctx->steps_target;
+            const uint64_t L = ctx->sp.cd_update_freq;
+            const uint64_t room = (ctx->need_rebuild || ctx->steps_since_rebuild >= L) ? L : L - ctx->steps_since_rebuild;
+            ctx->steps_target = std::min<uint64_t>(target, ctx->n_steps + room);
+            const int rc = pump(ctx);
+            ctx->steps_target = target;
+            if (rc) return rc;
+        }
+        if (!busy) break;
+    }
+    return DEM_OK;
+}
+
+int dem_group_sync(DemCtx** ctxs, int world) {
+    if (!ctxs || world < 1) return DEM_ERR_INVALID;
+    for (int attempt = 0; attempt < 16; attempt++) {
+        bool again = false;
+        for (int r = 0; r < world; r++) {
+            DemCtx* ctx = ctxs[r];
+            CK(cudaSetDevice(ctx->device));
+            CK(cudaStreamSynchronize(ctx->stream));
+            bool rolled = false;
+            const int rc = confirm_rebuild(ctx, &rolled);
+            if (rc) return rc;
+            again = again || rolled || ctx->n_steps < ctx->steps_target;
+        }
+        if (!again) return DEM_OK;
+        // a rebuild overflowed (on every rank alike: the verdict is agreed on the device): replay together
+        uint64_t left = 0;
+        for (int r = 0; r < world; r++) left = std::max<uint64_t>(left, ctxs[r]->steps_target - ctxs[r]->n_steps);
+        const int rc = dem_group_step_async(ctxs, world, left);
+        if (rc) return rc;
+    }
+    return DEM_ERR_CAPACITY;
+}
+
+/* After dem_group_sync: copy into ctxs[0] the records of the clump owners the other ranks own, so that ctxs[0] holds the
+ * merged state of the whole system for trackers / writers / inspectors. */
+int dem_group_gather(DemCtx** ctxs, int world) {
+    if (!ctxs || world < 1 || !ctxs[0]) return DEM_ERR_INVALID;
+    DemCtx* ctx = ctxs[0];
+    if (world == 1 || !ctx->mg.on) return DEM_OK;
+    CK(cudaSetDevice(ctx->device));
+    const DevParams P = make_params(ctx);
+    for (int r = 1; r < world; r++)
+        ctx->launches += launch_mg_gather_owned(P, ctxs[r]->d_state, ctxs[r]->d_spin, ctxs[r]->mg.d_flag, ctx->nClumpOwners, ctx->stream);
+    CK(cudaStreamSynchronize(ctx->stream));
+    return DEM_OK;
+}
+
+/* device-side barrier over the ranks, enqueued on the stream: what a benchmark puts right before its first timing event
+ * so that the timed region starts with all GPUs level */
+int dem_mgpu_barrier(DemCtx* ctx) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if (!ctx->mg.on) return DEM_OK;
+    CK(cudaSetDevice(ctx->device));
+    ctx->launches += launch_mg_barrier(make_params(ctx), make_mgdev(ctx), ctx->stream);
     return DEM_OK;
 }
 
 int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]) {
     if (!ctx || !out) return DEM_ERR_INVALID;
     const MgState& g = ctx->mg;
-    out[0] = g.n_own; out[1] = g.n_active; out[2] = g.n_send[0]; out[3] = g.n_send[1]; out[4] = g.halo_bytes;
-    out[5] = (g.on ? (uint64_t)g.world : 1) | (g.p2p ? (1ull << 32) : 0ull);  // bit 32: peer-memory exchange in use
+    out[0] = g.last[0]; out[1] = g.last[3]; out[2] = g.last[1]; out[3] = g.last[2];
+    out[4] = ((uint64_t)g.last[1] + g.last[2]) * 80;
+    out[5] = (g.on ? (uint64_t)g.world : 1) | (g.on ? (1ull << 32) : 0ull);  // bit 32: exchange through peer memory
     return DEM_OK;
 }
 
@@ -1760,13 +2000,16 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    return rebuild(ctx, out_us);
+    int rc = settle(ctx);
+    if (rc) return rc;
+    return rebuild_blocking(ctx, out_us);
 }
 
 int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]) {
     if (!ctx || !ctx->initialized || !out_us || repeats == 0) return DEM_ERR_INVALID;
     if (ctx->mg.on) return fail(ctx, DEM_ERR_INVALID, "dem_profile_binning: single-device contexts only (shard the spheres, one context per GPU)");
     CK(cudaSetDevice(ctx->device));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     cudaStream_t s = ctx->stream;
     double acc[3] = {0, 0, 0};
     for (uint32_t r = 0; r < repeats; r++) {
@@ -1776,13 +2019,13 @@ int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]) {
         P.ss = as_list(ctx->lists[0][ctx->cur ^ 1]); P.sn = as_list(ctx->lists[1][ctx->cur ^ 1]);
         P.sa = as_list(ctx->lists[2][ctx->cur ^ 1]); P.st = as_list(ctx->lists[3][ctx->cur ^ 1]);
         CK(cudaEventRecord(ctx->ev[0], s));
-        int launches = launch_cd_prepare(P, C, ctx->need_maxvel, 0, s);
-        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 1, s);
-        launches += launch_cd_prepare(P, C, ctx->need_maxvel, 2, s);
+        int launches = launch_cd_prepare(P, C, nullptr, ctx->need_maxvel, 0, ctx->num_sms, s);
+        launches += launch_cd_prepare(P, C, nullptr, ctx->need_maxvel, 1, ctx->num_sms, s);
+        launches += launch_cd_prepare(P, C, nullptr, ctx->need_maxvel, 2, ctx->num_sms, s);
         CK(cudaEventRecord(ctx->ev[1], s));
         int sorted_buf = -1;
         if (ctx->sort_mode == 0) { launches += launch_cd_sort(P, C, ctx->key_bits, s, &sorted_buf); ctx->last_sorted_buf = sorted_buf; }
-        launches += launch_cd_sweep(P, C, sorted_buf, s, nullptr, /*sort_only*/ true);
+        launches += launch_cd_sweep(P, C, nullptr, ctx->cur ^ 1, sorted_buf, ctx->num_sms, s, nullptr, /*sort_only*/ true);
         CK(cudaEventRecord(ctx->ev[2], s));
         CK(cudaEventSynchronize(ctx->ev[2]));
         ctx->launches += launches;
@@ -1801,7 +2044,7 @@ int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]) {
 int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uint64_t* n_out) {
     if (!ctx || !ctx->initialized || !what || !out || !n_out) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     const std::string w(what);
     const void* src = nullptr;
     uint64_t avail = 0;
@@ -1825,6 +2068,7 @@ int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uin
 int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
     CK(cudaSetDevice(ctx->device));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     cudaStream_t s = ctx->stream;
     const int model = (int)ctx->sp.force_model;
@@ -1838,12 +2082,15 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
     int rc_out = DEM_OK;
     while (done < n_steps && rc_out == DEM_OK) {
         const int nb = (int)std::min<uint64_t>(BATCH, n_steps - done);
+        int got = 0;
         for (int i = 0; i < nb; i++) {
             cudaEvent_t* e = &ev[(size_t)NE * i];
             CK(cudaEventRecord(e[0], s));
             if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
-                int rc = rebuild(ctx);
+                const uint32_t before = ctx->seq_host;
+                int rc = enqueue_rebuild(ctx);
                 if (rc) { rc_out = rc; break; }
+                if (ctx->seq_host == before) break;  // an earlier rebuild was rolled back: start the batch over
             }
             CK(cudaEventRecord(e[1], s));
             DevParams P = make_params(ctx);
@@ -1852,38 +2099,22 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
             if (ctx->nAnal > 0) launch_force_sa(P, model, rec, ctx->sa_grid, s);
             if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
             CK(cudaEventRecord(e[3], s));
-            if (ctx->mg.on && ctx->mg.p2p && ctx->mg.fuse_push) {
-                // fused push: the integrator and the exchange cannot be timed apart; [5] is the pull (incl. waiting)
-                MgP2P X = mg_next_epoch(ctx);
-                X.publish = 1;
-                for (int d = 0; d < 2; d++) {
-                    P.send_slot[d] = ctx->mg.d_send_slot[d];
-                    P.peer_recv[d] = X.peer_recv[d];
-                }
-                launch_integrate(P, s);
-                ctx->maxvel_slot ^= 1;
-                CK(cudaEventRecord(e[4], s));
-                ctx->launches += launch_mg_pull(P, X, s);
-            } else {
-                launch_integrate(P, s);
-                ctx->maxvel_slot ^= 1;
-                CK(cudaEventRecord(e[4], s));
-                if (ctx->mg.on) {
-                    int l = 0;
-                    int rc = mg_halo_exchange(ctx, P, nullptr, &l);
-                    if (rc) { rc_out = rc; break; }
-                    ctx->launches += l;
-                }
-            }
+            // (on several GPUs the integrator also stores the halo records; [5] is the pull, including the wait)
+            launch_integrate(P, ctx->num_sms, s);
+            ctx->maxvel_slot ^= 1;
+            CK(cudaEventRecord(e[4], s));
+            if (ctx->mg.on) ctx->launches += launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, s);
             CK(cudaEventRecord(e[5], s));
             ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
-            ctx->n_steps++;
-            ctx->steps_since_rebuild++;
-            ctx->sim_time += (double)ctx->sp.h;
+            note_steps_enqueued(ctx, 1);
+            got++;
         }
         if (rc_out != DEM_OK) break;
-        CK(cudaStreamSynchronize(s));
-        for (int i = 0; i < nb; i++) {
+        const uint64_t steps_before = ctx->n_steps;
+        ctx->steps_target = ctx->n_steps;
+        { int rcs = settle(ctx); if (rcs) { rc_out = rcs; break; } }
+        if (ctx->n_steps != steps_before) continue;  // rolled back inside the batch: its timings are void
+        for (int i = 0; i < got; i++) {
             cudaEvent_t* e = &ev[(size_t)NE * i];
             float ms;
             CK(cudaEventElapsedTime(&ms, e[1], e[2])); acc[0] += ms;
@@ -1893,8 +2124,9 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
             CK(cudaEventElapsedTime(&ms, e[0], e[5])); acc[4] += ms;
             CK(cudaEventElapsedTime(&ms, e[4], e[5])); acc[5] += ms;
         }
-        done += nb;
+        done += got;
     }
+    ctx->steps_target = ctx->n_steps;
     for (auto& e : ev) cudaEventDestroy(e);
     if (rc_out != DEM_OK) return rc_out;
     for (int k = 0; k < 8; k++) out_us[k] = n_steps ? (float)(acc[k] * 1000.0 / (double)n_steps) : 0.f;

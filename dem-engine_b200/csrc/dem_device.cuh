@@ -81,17 +81,68 @@ struct Prescr {  // == DemPrescription (88 bytes)
 };
 static_assert(sizeof(Prescr) == 88, "Prescr must match DemPrescription");
 
-// one contact list
+// one contact list.  Geometry A of a contact is the sphere whose segment [seg_start, seg_start + seg_count) it lies in.
 struct ContactList {
-    uint2* pair;         // {geoA, geoB}: sphere ids (geoB = analytical component / triangle id for the other lists)
+    uint32_t* idB;       // geometry B: sphere id (analytical component / triangle id for the other lists)
     uint4* cinfo;        // compiled record {ownerA, ownerB|objID, compA | compB<<16, matpair | alive<<31}
     float4* hist;        // delta_tan_xyz, delta_time
     uint32_t* seg_start; // per sphere A: first contact of A in this list
     uint32_t* seg_count; // per sphere A: number of contacts of A
-    uint32_t* count;     // device-resident number of contacts
+    uint32_t* count;     // device-resident number of contacts: [0] clamped to the capacity, [1] demand
     float4* force;       // optional per-contact force record (xyz) -- nullptr when SetNoForceRecord
     float4* cpoint;      // ... and the contact point (world frame, LBF-relative) the force acts at
 };
+
+// status words of a context (DevParams::flags)
+enum {
+    DEM_FLAG_CAPACITY = 0,  // bit mask: which list / table overflowed in the last rebuild
+    DEM_FLAG_TRI_DEMAND = 1,  // entries the triangle--cell table would have needed
+    DEM_FLAG_HALO = 2,      // multi-GPU: a halo buffer overflowed / a neighbour stopped answering
+    DEM_FLAG_VELOCITY = 3,  // an owner has a non-finite or too large velocity
+    DEM_FLAG_POISON = 4,    // != 0: a rebuild failed; every kernel of every later step / rebuild is a no-op until the
+                            // host has grown the lists and cleared it (value = sequence number of the failed rebuild)
+    DEM_FLAG_SEQ = 5,       // rebuilds finished so far (device-side counter: graph replays carry no host arguments)
+    DEM_NUM_FLAGS = 8
+};
+constexpr uint32_t CINFO_NO_HISTORY = 0x40000000u;  // sweep -> k_history: this contact carries no history over
+
+// Multi-GPU (slab decomposition) state as the kernels see it.  Everything that changes from step to step or rebuild
+// to rebuild lives in DEVICE memory (epoch counters, counts, lists), so that the same parameter block -- hence the same
+// CUDA graph -- serves every step and every rebuild.  Layout of a rank's peer-visible block (mapped by all ranks):
+//   [0, 1024)                      header: see the MG_* offsets below
+//   MG_OFF_GID  + ((par*2 + dir) * cap) * 4      halo membership lists written by the neighbour in direction dir
+//   MG_OFF_REC  + ((dir*2 + half) * cap) * 80    {state, spin} records written by the neighbour in direction dir
+constexpr uint32_t MG_MAX_WORLD = 8;
+constexpr uint32_t MG_HDR_STEP_FLAG = 0;      // u64[2]: neighbour `dir` has completed exchange number e
+constexpr uint32_t MG_HDR_RECV_COUNT = 16;    // u32[2 par][2 dir]: owners the neighbour sends me during this cycle
+constexpr uint32_t MG_HDR_MAIL = 64;          // all-gather mailbox: [2 parity][8 ranks] x {u64 seq, u32 val[2]}
+constexpr uint32_t MG_HDR_BYTES = 1024;
+struct MgDev {
+    int rank, world;
+    int has[2];                       // neighbour present on the left / right
+    char* my_block;
+    char* peer_block[MG_MAX_WORLD];   // every rank's block (peer_block[rank] == my_block)
+    uint32_t cap;                     // owners per halo list
+    unsigned long long* epoch;        // exchanges (per-step and per-rebuild alike) completed so far
+    unsigned long long* mail_ctr;     // all-gathers completed so far
+    uint32_t* block_ctr;              // [0] pull kernel, [1] push kernel: last-block detection
+    uint8_t* flag;                    // per global owner: 0 unknown here, 1 own, 2 ghost
+    uint32_t* active_list[2];         // [par] compact list of active owners (own + ghost) of the cycle with parity par
+    uint32_t* counts[2];              // [par] {own, send-left, send-right, active, active spheres, -, -, -}
+    uint32_t* send_gid[2][2];         // [par][dir] own owners inside the halo of the left / right cut
+    int32_t* send_slot[2];            // [dir] per owner: slot in that neighbour's receive buffer, or -1
+    uint32_t* act_sph;                // spheres of the active owners (the rebuild walks these only)
+    const uint2* owner_sph;           // per owner {first sphere, number of spheres} (nullptr: not contiguous)
+    float cut_lo, cut_hi;             // my slab in LBF-relative x
+    uint32_t nClumpOwners;            // owners >= this index are analytical / mesh owners, replicated on every rank
+};
+__host__ __device__ __forceinline__ size_t mg_off_gid(uint32_t cap, int par, int dir) {
+    return (size_t)MG_HDR_BYTES + ((size_t)(par * 2 + dir) * cap) * 4u;
+}
+__host__ __device__ __forceinline__ size_t mg_off_rec(uint32_t cap, int dir, int half) {
+    return (size_t)MG_HDR_BYTES + (size_t)4u * cap * 4u + ((size_t)(dir * 2 + half) * cap) * 80u;
+}
+__host__ __device__ __forceinline__ size_t mg_block_bytes(uint32_t cap) { return mg_off_rec(cap, 2, 0); }
 
 // Everything a kernel needs, passed by value (__grid_constant__)
 struct DevParams {
@@ -115,16 +166,18 @@ struct DevParams {
     float4* spin;     // body-frame angular velocity omgBar xyz, w = bits(inertiaPropOffset)
     Wrench* wrench;
     Wrench* acc_out;  // optional per-owner {a, alpha} read-out (nullptr = off)
-    // domain decomposition (nullptr / 0 on a single GPU): per-owner activity flag (0 unknown, 1 own, 2 ghost) and the
-    // compact list of active owners the integrator walks
+    // domain decomposition (nullptr on a single GPU): per-owner activity flag (0 unknown, 1 own, 2 ghost), the
+    // compact list of active owners the integrator walks and its DEVICE-resident length
     const uint8_t* active;
     const uint32_t* active_list;
-    uint32_t nActive;
+    const uint32_t* nActivePtr;
     // ... and the per-step halo push fused into the integrator: per owner the slot of its {state, spin} record in the
-    // left / right neighbour's receive buffer (-1 = not in that halo; nullptr = no fused push) and the neighbours'
-    // buffers (this epoch's half, in THEIR memory)
+    // left / right neighbour's receive buffer (-1 = not in that halo; nullptr = no fused push), the neighbours' record
+    // areas for my direction (both epoch halves, in THEIR memory) and the exchange counter that selects the half
     const int32_t* send_slot[2];
-    int4* peer_recv[2];
+    int4* peer_rec[2];
+    uint32_t rec_half_int4;             // int4 words per epoch half (cap * 5)
+    const unsigned long long* epoch;
     // spheres / templates
     const uint2* sph;
     const float4* comp;      // {relx, rely, relz, radius}
@@ -141,7 +194,7 @@ struct DevParams {
     // contact lists: ss = sphere-sphere pairs in touch at the last rebuild, sn = the remaining sphere-sphere
     // candidates, sa = sphere-analytical, st = sphere-triangle
     ContactList ss, sn, sa, st;
-    // status flags (device): [0] capacity overflow, [1] non-finite / too-fast owner, [2] staging overflow in the sweep
+    // status words (device), indexed by DEM_FLAG_*
     uint32_t* flags;
     float* maxvel;       // device float: max |v| of the current state (kept up to date by the integrator)
     float* maxvel_next;  // the slot the NEXT step will accumulate into (zeroed by this step's integrator)
@@ -233,6 +286,46 @@ __device__ __forceinline__ uint32_t mask_pair(uint32_t i, uint32_t j) {
 __device__ __forceinline__ void red_add_v4(float4* addr, float x, float y, float z) {
     asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(0.0f)
                  : "memory");
+}
+
+// ---- system-scope flag words (peer memory over NVLink) ----
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+constexpr long long MG_SPIN_TIMEOUT_CYCLES = 20000000000ll;  // ~10 s: the peer is gone; report instead of hanging
+
+// All-gather of two 32-bit words over the ranks through the peer-mapped mailboxes, called by ONE full warp: lane r
+// (r < world) stores this rank's words into rank r's mailbox and then waits for rank r's words in its own.  On return
+// lane r holds rank r's words in (o0, o1); lanes >= world hold this rank's own.  Two mailbox sets alternate with the
+// all-gather number: a rank cannot start all-gather m+2 before every rank has finished reading all-gather m.
+__device__ __forceinline__ void mg_allgather(const MgDev& M, uint32_t v0, uint32_t v1, uint32_t& o0, uint32_t& o1,
+                                             uint32_t* flags) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long m = *M.mail_ctr + 1ull;
+    __syncwarp();
+    o0 = v0; o1 = v1;
+    if (lane < M.world) {
+        char* slot = M.peer_block[lane] + MG_HDR_MAIL + ((size_t)(m & 1ull) * MG_MAX_WORLD + (size_t)M.rank) * 16u;
+        asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + 8), "r"(v0), "r"(v1) : "memory");
+        st_release_sys(reinterpret_cast<unsigned long long*>(slot), m);
+        const char* mine = M.my_block + MG_HDR_MAIL + ((size_t)(m & 1ull) * MG_MAX_WORLD + (size_t)lane) * 16u;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (ld_acquire_sys(reinterpret_cast<const unsigned long long*>(mine)) < m) {
+            if (clock64() - t0 > MG_SPIN_TIMEOUT_CYCLES) { atomicOr(&flags[DEM_FLAG_HALO], 64u); ok = false; break; }
+        }
+        if (ok) {
+            const uint2 r = __ldcg(reinterpret_cast<const uint2*>(mine + 8));
+            o0 = r.x; o1 = r.y;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) *M.mail_ctr = m;
 }
 
 template <typename T>

@@ -1,21 +1,28 @@
-// kernels_cd.cu -- contact-list rebuild ("kinematic" work) for sm_100a, fully device-driven (no host round trips
-// between the stages):
-//   k_maxvel / k_grid_setup      max |v| -> margin -> broad-phase cell size and grid, decided ON the device; also
-//                                resolves the analytical components (planes, cylinders) to world space once
+// kernels_cd.cu -- contact-list rebuild ("kinematic" work) for sm_100a, fully device-driven: no host round trip between
+// the stages and none at the end -- every count, the grid and every flag stay on the device; the last kernel leaves a
+// status record in pinned host memory that the host reads once it knows the rebuild to be complete.  All kernels are
+// grid-stride over DEVICE-resident counts, so the same launch parameters -- hence the same CUDA graph -- serve every
+// rebuild.  A rebuild that cannot hold its result (a list or table overflowed) sets the poison word: every later kernel
+// of this context returns at once, so the state freezes at the failed rebuild until the host has grown the arrays.
+//   k_maxvel / k_grid_setup      max |v| (all-gathered over the ranks) -> margin -> broad-phase cell size and grid
+//   k_anal_prep                  resolves the analytical components (planes, cylinders) to world space once
 //   k_sphere_prep                per sphere: world position (fixed-point decode + rotated offset), inflated radius,
 //                                cell key + cell histogram; emits the sphere--analytical list (+history) directly
 //                                with warp-aggregated atomics
-//   radix sort (k_rs_*)          LSD, 8-bit digits, tile ranking with warp match + shared-memory staged coalesced scatter
-//   scan (k_scan_*)              exclusive prefix sums (cell table, per-sphere contact offsets, sort histograms)
-//   k_gather_sorted              cell-ordered float4 {x,y,z,r'} + {owner,id}
-//   k_sweep                      ONE pass over the upper half of the 27-cell stencil (5 contiguous runs of the sorted array
-//                                instead of 9): distance test on the float4 stream first, accepted candidates staged per
-//                                thread, slots claimed with one warp-aggregated atomic, then the compiled per-contact
-//                                record is written and the Hertz-Mindlin history carried over from the previous list
+//   k_scan_lookback              single-pass exclusive prefix sums with decoupled look-back (cell table, per-sphere
+//                                contact offsets)
+//   k_cs_scatter / k_gather_sorted_cs   counting sort into (cell, sphere id) order; radix sort (k_rs_*) as alternative
+//   k_sweep_tma<COUNT|FILL>      kernels_sweep.cu: TMA-staged pair sweep over the upper half of the 27-cell stencil
+//   k_history                    Hertz-Mindlin history carried over from the previous lists
+//   k_tri_cells / k_st_emit      sphere--triangle broad phase
+//   k_finish_counts              clamps, overflow -> poison (agreed over the ranks), status record
 // Reference behaviour being reproduced: contactDetection(), src/algorithms/DEMCubContactDetection.cu:38-1123;
 // acceptance rule of src/kernel/DEMContactKernels_SphereSphere.cu:57-89,172-214 and DEMBinSphereKernels.cu:78-128;
 // margin of src/kernel/DEMMiscKernels.cu:37-69; history map of src/kernel/DEMHistoryMappingKernels.cu.
 // The candidate list is a SUPERSET of the reference's (the force kernel re-tests true overlap), so physics is identical.
+#include <algorithm>
+#include <cstring>
+
 #include "dem_kernels.h"
 
 namespace demb {
@@ -31,22 +38,37 @@ __device__ __forceinline__ float owner_margin(const DevParams& P, float absv, ui
 }
 
 __global__ void k_maxvel(const __grid_constant__ DevParams P, float errOutVel) {
-    const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = P.active_list ? *P.nActivePtr : P.nOwners;
     float a = 0.f;
-    if (o < P.nOwners && (!P.active || P.active[o] != 0)) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t o = P.active_list ? P.active_list[t] : t;
         const float4 v = P.state[o].vel;
-        a = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-        if (!isfinite(a) || a > errOutVel) atomicOr(&P.flags[3], 1u);
-        if (!isfinite(a)) a = 0.f;
+        float b = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
+        if (!isfinite(b) || b > errOutVel) atomicOr(&P.flags[DEM_FLAG_VELOCITY], 1u);
+        if (!isfinite(b)) b = 0.f;
+        a = fmaxf(a, b);
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, off));
     if ((threadIdx.x & 31) == 0 && a > 0.f) atomicMax(reinterpret_cast<int*>(P.maxvel), __float_as_int(a));
 }
 
-__global__ void k_grid_setup(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float vmax = *P.maxvel;
+// one warp: all-gather of max |v| over the ranks (the cell grid, hence the sorted order and the A/B roles of a pair,
+// must be the same on every rank), then lane 0 decides the grid
+__global__ void __launch_bounds__(32) k_grid_setup(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C,
+                                                   const __grid_constant__ MgDev M) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    float vmax = *P.maxvel;
+    if (M.world > 1) {
+        uint32_t o0, o1;
+        mg_allgather(M, __float_as_uint(vmax), 0u, o0, o1, P.flags);
+        vmax = __uint_as_float(o0);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, off));
+        if (threadIdx.x == 0) *P.maxvel = vmax;
+    }
+    if (threadIdx.x != 0) return;
     float margin;
     if (P.beta >= 0.f) {
         margin = P.beta + C.max_extra;
@@ -93,6 +115,7 @@ __global__ void k_grid_setup(const __grid_constant__ DevParams P, const __grid_c
 
 // World-space analytical components of this rebuild (plane point / cylinder centre, direction, owner margin, family)
 __global__ void k_anal_prep(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= P.nAnal) return;
     const AnalObj ob = P.anal[k];
@@ -157,95 +180,103 @@ __device__ __forceinline__ uint32_t warp_claim(uint32_t count, uint32_t* cursor)
 
 __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ DevParams P,
                                                      const __grid_constant__ CdParams C) {
-    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t_ < (C.act_sph ? C.nActSph : P.nSpheres);
-    const uint32_t i = (valid && C.act_sph) ? C.act_sph[t_] : t_;
-    uint32_t nsa = 0, samask = 0;
-    float3 sp = f3(0.f, 0.f, 0.f);
-    uint2 s = make_uint2(0, 0);
-    uint32_t family = 0;
-    if (valid) {
-        s = P.sph[i];
-        if (P.active && P.active[s.x] == 0) {
-            // owner not held by this rank (domain decomposition): the sphere takes no part in this rebuild
-            C.keys[0][i] = 0xffffffffu;
-            P.sa.seg_start[i] = 0;
-            P.sa.seg_count[i] = 0;
-            valid = false;
-        }
-    }
-    if (valid) {
-        const GridInfo g = *C.grid;
-        OwnerPos pos;
-        float4 q, v;
-        {
-            const float* base = reinterpret_cast<const float*>(P.state + s.x);
-            uint32_t a0, a1, a2, a3;
-            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
-                         : "l"(base));
-            pos.voxel = ((unsigned long long)a1 << 32) | a0;
-            pos.lx = (unsigned short)(a2 & 0xffffu); pos.ly = (unsigned short)(a2 >> 16);
-            pos.lz = (unsigned short)(a3 & 0xffffu); pos.family = (unsigned char)((a3 >> 16) & 0xffu);
-            pos.flags = 0;
-            v = __ldg(&P.state[s.x].vel);
-        }
-        family = pos.family;
-        const float4 comp = __ldg(&P.comp[s.y & 0xffffu]);
-        const float margin = owner_margin(P, sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), pos.family);
-        double X, Y, Z;
-        pos_decode(pos, P, X, Y, Z);
-        const float3 rel = rotate(f3(comp.x, comp.y, comp.z), q);
-        sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
-        const float rInfl = comp.w + margin;
-        C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
-        int cx = (int)floorf(sp.x * g.inv_cs) - g.x0, cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
-        cx = min(max(cx, 0), (int)g.nbx - 1);
-        cy = min(max(cy, 0), (int)g.nby - 1);
-        cz = min(max(cz, 0), (int)g.nbz - 1);
-        const uint32_t key = (uint32_t)cx + g.nbx * ((uint32_t)cy + g.nby * (uint32_t)cz);
-        C.keys[0][i] = key;
-        C.vals[0][i] = i;
-        // cell histogram; the arrival rank doubles as the slot of the counting sort (made deterministic afterwards)
-        C.vals[1][i] = atomicAdd(&C.cellStart[key], 1u);
-        // analytical candidates (at most 32 components are tracked per sphere in the bit mask; more fall back below)
-        for (uint32_t k = 0; k < P.nAnal; k++)
-            if (sa_candidate(P, C.analw[k], sp, rInfl, family, C.any_mask != 0)) {
-                if (k < 32) samask |= 1u << k;
-                nsa++;
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = C.act_sph ? *C.act_count : P.nSpheres;
+    const uint32_t nround = (n + 31u) & ~31u;  // whole warps take part in the slot claim
+    const GridInfo g = *C.grid;
+    for (uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < nround; t_ += gridDim.x * blockDim.x) {
+        const bool valid = t_ < n;
+        const uint32_t i = (valid && C.act_sph) ? C.act_sph[t_] : t_;
+        uint32_t nsa = 0, samask = 0;
+        float3 sp = f3(0.f, 0.f, 0.f);
+        uint2 s = make_uint2(0, 0);
+        uint32_t family = 0;
+        float rInfl = 0.f;
+        if (valid) {
+            s = P.sph[i];
+            OwnerPos pos;
+            float4 q, v;
+            {
+                const float* base = reinterpret_cast<const float*>(P.state + s.x);
+                uint32_t a0, a1, a2, a3;
+                asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=f"(q.x), "=f"(q.y), "=f"(q.z), "=f"(q.w)
+                             : "l"(base));
+                pos.voxel = ((unsigned long long)a1 << 32) | a0;
+                pos.lx = (unsigned short)(a2 & 0xffffu); pos.ly = (unsigned short)(a2 >> 16);
+                pos.lz = (unsigned short)(a3 & 0xffffu); pos.family = (unsigned char)((a3 >> 16) & 0xffu);
+                pos.flags = 0;
+                v = __ldg(&P.state[s.x].vel);
             }
-    }
-    if (P.nAnal == 0) return;
-    // ---- emit the sphere--analytical contacts of this warp into one contiguous run ----
-    uint32_t slot = warp_claim(nsa, P.sa.count);
-    if (!valid) return;
-    P.sa.seg_start[i] = slot;
-    P.sa.seg_count[i] = (slot + nsa <= C.capacity) ? nsa : (slot < C.capacity ? C.capacity - slot : 0u);
-    if (nsa == 0) return;
-    if (slot + nsa > C.capacity) atomicOr(&P.flags[0], 2u);
-    const uint32_t oldStart = C.oldsa.seg_start[i], oldCount = C.oldsa.seg_count[i];
-    for (uint32_t k = 0; k < P.nAnal; k++) {
-        bool hit;
-        if (k < 32) hit = (samask >> k) & 1u;
-        else hit = sa_candidate(P, C.analw[k], sp, C.sphF[i].w, family, C.any_mask != 0);
-        if (!hit) continue;
-        if (slot < C.capacity) {
-            float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-            uint32_t alive = 0;
-            for (uint32_t t = 0; t < oldCount; t++) {
-                if (C.oldsa.pair[oldStart + t].y == k) {
-                    alive = C.oldsa.cinfo[oldStart + t].w & 0x80000000u;
-                    if (alive && C.oldsa.hist) h = C.oldsa.hist[oldStart + t];
-                    break;
+            family = pos.family;
+            const float4 comp = __ldg(&P.comp[s.y & 0xffffu]);
+            const float margin = owner_margin(P, sqrtf(v.x * v.x + v.y * v.y + v.z * v.z), pos.family);
+            double X, Y, Z;
+            pos_decode(pos, P, X, Y, Z);
+            const float3 rel = rotate(f3(comp.x, comp.y, comp.z), q);
+            sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
+            rInfl = comp.w + margin;
+            C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
+            int cx = (int)floorf(sp.x * g.inv_cs) - g.x0, cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
+            cx = min(max(cx, 0), (int)g.nbx - 1);
+            cy = min(max(cy, 0), (int)g.nby - 1);
+            cz = min(max(cz, 0), (int)g.nbz - 1);
+            const uint32_t key = (uint32_t)cx + g.nbx * ((uint32_t)cy + g.nby * (uint32_t)cz);
+            C.keys[0][i] = key;
+            C.vals[0][i] = i;
+            // cell histogram; the arrival rank doubles as the slot of the counting sort (made deterministic afterwards)
+            C.vals[1][i] = atomicAdd(&C.cellStart[key], 1u);
+            // analytical candidates (at most 32 components are tracked per sphere in the bit mask; more fall back below)
+            for (uint32_t k = 0; k < P.nAnal; k++)
+                if (sa_candidate(P, C.analw[k], sp, rInfl, family, C.any_mask != 0)) {
+                    if (k < 32) samask |= 1u << k;
+                    nsa++;
                 }
-            }
-            const uint32_t matpair = (s.y >> 16) * P.nMat + C.analw[k].material;
-            P.sa.pair[slot] = make_uint2(i, k);
-            P.sa.cinfo[slot] = make_uint4(s.x, k, s.y & 0xffffu, matpair | alive);
-            if (P.sa.hist) P.sa.hist[slot] = h;
         }
-        slot++;
+        if (P.nAnal == 0) continue;
+        // ---- emit the sphere--analytical contacts of this warp into one contiguous run ----
+        uint32_t slot = warp_claim(nsa, P.sa.count);
+        if (!valid) continue;
+        P.sa.seg_start[i] = slot;
+        P.sa.seg_count[i] = (slot + nsa <= C.capacity) ? nsa : (slot < C.capacity ? C.capacity - slot : 0u);
+        if (nsa == 0) continue;
+        if (slot + nsa > C.capacity) atomicOr(&P.flags[DEM_FLAG_CAPACITY], 2u);
+        const uint32_t oldStart = C.oldsa.seg_start[i], oldCount = C.oldsa.seg_count[i];
+        for (uint32_t k = 0; k < P.nAnal; k++) {
+            bool hit;
+            if (k < 32) hit = (samask >> k) & 1u;
+            else hit = sa_candidate(P, C.analw[k], sp, rInfl, family, C.any_mask != 0);
+            if (!hit) continue;
+            if (slot < C.capacity) {
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t alive = 0;
+                for (uint32_t t = 0; t < oldCount; t++) {
+                    if (C.oldsa.idB[oldStart + t] == k) {
+                        alive = C.oldsa.cinfo[oldStart + t].w & 0x80000000u;
+                        if (alive && C.oldsa.hist) h = C.oldsa.hist[oldStart + t];
+                        break;
+                    }
+                }
+                const uint32_t matpair = (s.y >> 16) * P.nMat + C.analw[k].material;
+                P.sa.idB[slot] = k;
+                P.sa.cinfo[slot] = make_uint4(s.x, k, s.y & 0xffffu, matpair | alive);
+                if (P.sa.hist) P.sa.hist[slot] = h;
+            }
+            slot++;
+        }
     }
+}
+
+// zero a u32 range unless the context is poisoned (a memset node cannot be made conditional)
+__global__ void __launch_bounds__(256) k_zero_u32(uint32_t* __restrict__ p, size_t n, const uint32_t* __restrict__ flags) {
+    if (flags[DEM_FLAG_POISON]) return;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0u;
+}
+int launch_zero_u32(uint32_t* p, size_t n, const uint32_t* flags, int num_sms, cudaStream_t s) {
+    if (n == 0) return 0;
+    const int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)num_sms * 8);
+    k_zero_u32<<<grid, 256, 0, s>>>(p, n, flags);
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -342,6 +373,105 @@ int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* t
     k_scan_top<<<1, 1024, 0, s>>>(tmp, nblk, total);
     k_scan_apply<<<nblk, SC_THREADS, 0, s>>>(data, n, tmp);
     return 3;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Single-pass exclusive scan with decoupled look-back (Merrill & Garland): tiles are handed out by an atomic counter
+// (so a tile's predecessors are always already running), each tile publishes its aggregate, resolves its prefix from
+// the descriptors behind it and publishes the inclusive prefix.  One pass over the data instead of the three of the
+// sums / top / apply scheme; the length is read from device memory.
+//   descriptor = value | state << 32   (state 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix)
+constexpr int LB_THREADS = 256;
+constexpr int LB_ITEMS = 16;
+constexpr int LB_TILE = LB_THREADS * LB_ITEMS;
+
+__global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in, uint32_t* out,
+                                                              const uint32_t* __restrict__ n_ptr, uint32_t n_add,
+                                                              unsigned long long* desc, uint32_t* total_out,
+                                                              const uint32_t* __restrict__ flags) {
+    if (flags[DEM_FLAG_POISON]) return;
+    __shared__ uint32_t sm[33];
+    __shared__ uint32_t s_tile, s_prefix;
+    const uint32_t n = (n_ptr ? *n_ptr : 0u) + n_add;
+    const uint32_t ntiles = (n + LB_TILE - 1) / LB_TILE;
+    uint32_t* tile_ctr = reinterpret_cast<uint32_t*>(desc);
+    volatile unsigned long long* D = desc + 1;
+    if (n == 0) {
+        if (blockIdx.x == 0 && threadIdx.x == 0 && total_out) *total_out = 0u;
+        return;
+    }
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(tile_ctr, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) break;
+        const uint32_t base = tile * LB_TILE + threadIdx.x * LB_ITEMS;
+        uint32_t v[LB_ITEMS];
+        uint32_t acc = 0;
+        if (base + LB_ITEMS <= n) {
+            const uint4* src = reinterpret_cast<const uint4*>(in + base);
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS / 4; k++) {
+                const uint4 q = src[k];
+                v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS; k++) v[k] = (base + k < n) ? in[base + k] : 0u;
+        }
+#pragma unroll
+        for (int k = 0; k < LB_ITEMS; k++) acc += v[k];
+        uint32_t total;
+        uint32_t ex = block_exclusive_scan(acc, sm, total);
+        if (threadIdx.x == 0) {
+            uint32_t prefix = 0;
+            if (tile == 0) {
+                D[0] = (unsigned long long)total | (2ull << 32);
+            } else {
+                D[tile] = (unsigned long long)total | (1ull << 32);
+                __threadfence();
+                for (int p = (int)tile - 1; p >= 0; p--) {
+                    unsigned long long d;
+                    do { d = D[p]; } while ((d >> 32) == 0ull);
+                    prefix += (uint32_t)d;
+                    if ((d >> 32) == 2ull) break;
+                }
+                D[tile] = (unsigned long long)(prefix + total) | (2ull << 32);
+            }
+            s_prefix = prefix;
+            if (tile == ntiles - 1 && total_out) *total_out = prefix + total;
+        }
+        __syncthreads();
+        ex += s_prefix;
+        if (base + LB_ITEMS <= n) {
+            uint4* dst = reinterpret_cast<uint4*>(out + base);
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS / 4; k++) {
+                uint4 q;
+                q.x = ex; ex += v[4 * k];
+                q.y = ex; ex += v[4 * k + 1];
+                q.z = ex; ex += v[4 * k + 2];
+                q.w = ex; ex += v[4 * k + 3];
+                dst[k] = q;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS; k++) {
+                if (base + k < n) out[base + k] = ex;
+                ex += v[k];
+            }
+        }
+        __syncthreads();  // s_tile / s_prefix are rewritten by the next round
+    }
+}
+
+int launch_scan_lookback(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_add, uint32_t n_max,
+                         unsigned long long* desc, uint32_t* total, const uint32_t* flags, int num_sms, cudaStream_t s) {
+    const uint32_t max_tiles = (n_max + LB_TILE - 1) / LB_TILE;
+    cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * ((size_t)max_tiles + 2), s);
+    const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>(max_tiles, (uint32_t)num_sms * 4u));
+    k_scan_lookback<<<grid, LB_THREADS, 0, s>>>(in, out, n_ptr, n_add, desc, total, flags);
+    return 1;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -457,9 +587,11 @@ int launch_cd_sort(const DevParams& P, const CdParams& C, int key_bits, cudaStre
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// radix-sort path (single GPU, sort_mode 0): gather into the sorted order the sort produced
 __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ DevParams P,
                                                        const __grid_constant__ CdParams C,
                                                        const uint32_t* __restrict__ vals) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= P.nSpheres) return;
     const uint32_t i = vals[j];
@@ -468,39 +600,43 @@ __global__ void __launch_bounds__(256) k_gather_sorted(const __grid_constant__ D
     uint32_t fam = 0;
     if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
     C.sortedMeta[j] = make_uint4(s.x, i, s.y, fam);  // {owner, sphere id, comp | material<<16, family}
-    C.sortedPos[i] = j;
+    C.sortedAux[j] = make_uint2(s.x, __float_as_uint(__ldg(&P.comp[s.y & 0xffffu]).w));
 }
 
 // ---- counting sort by cell (sort_mode 1): the histogram and its prefix exist anyway for the sweep ----
 __global__ void __launch_bounds__(256) k_cs_scatter(const __grid_constant__ DevParams P,
                                                     const __grid_constant__ CdParams C) {
-    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t_ >= (C.act_sph ? C.nActSph : P.nSpheres)) return;
-    const uint32_t i = C.act_sph ? C.act_sph[t_] : t_;
-    const uint32_t key = C.keys[0][i];
-    if (key == 0xffffffffu) return;  // inactive on this rank
-    C.keys[1][C.cellStart[key] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = C.act_sph ? *C.act_count : P.nSpheres;
+    for (uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < n; t_ += gridDim.x * blockDim.x) {
+        const uint32_t i = C.act_sph ? C.act_sph[t_] : t_;
+        const uint32_t key = C.keys[0][i];
+        C.keys[1][C.cellStart[key] + C.vals[1][i]] = i;  // arrival order inside the cell (non-deterministic)
+    }
 }
 
 // gather into cell order; inside a cell the spheres are ranked by sphere id, which makes the result identical to a
 // stable radix sort of (cell key, sphere id) no matter in which order the atomics arrived
 __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant__ DevParams P,
                                                           const __grid_constant__ CdParams C) {
-    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= C.cellStart[C.grid->ncells]) return;  // number of active spheres (== nSpheres on a single GPU)
-    const uint32_t i = C.keys[1][j];
-    const uint32_t key = C.keys[0][i];
-    const uint32_t sb = C.cellStart[key], se = C.cellStart[key + 1];
-    uint32_t rank = 0;
-    for (uint32_t t = sb; t < se; t++) rank += (C.keys[1][t] < i) ? 1u : 0u;
-    const uint32_t dst = sb + rank;
-    C.sortedSph[dst] = C.sphF[i];
-    const uint2 s = P.sph[i];
-    uint32_t fam = 0;
-    if (C.any_mask != 0 || C.max_extra > 0.f) fam = P.state[s.x].pos.family;
-    C.sortedMeta[dst] = make_uint4(s.x, i, s.y, fam);
-    C.vals[0][dst] = key;  // sorted keys for the sweep
-    C.sortedPos[i] = dst;
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = C.cellStart[C.grid->ncells];  // number of active spheres (== nSpheres on a single GPU)
+    const bool need_fam = C.any_mask != 0 || C.max_extra > 0.f;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t i = C.keys[1][j];
+        const uint32_t key = C.keys[0][i];
+        const uint32_t sb = C.cellStart[key], se = C.cellStart[key + 1];
+        uint32_t rank = 0;
+        for (uint32_t t = sb; t < se; t++) rank += (C.keys[1][t] < i) ? 1u : 0u;
+        const uint32_t dst = sb + rank;
+        C.sortedSph[dst] = C.sphF[i];
+        const uint2 s = P.sph[i];
+        uint32_t fam = 0;
+        if (need_fam) fam = P.state[s.x].pos.family;
+        C.sortedMeta[dst] = make_uint4(s.x, i, s.y, fam);
+        C.sortedAux[dst] = make_uint2(s.x, __float_as_uint(__ldg(&P.comp[s.y & 0xffffu]).w));
+        C.vals[0][dst] = key;  // sorted keys for the sweep
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -508,32 +644,36 @@ __global__ void __launch_bounds__(256) k_gather_sorted_cs(const __grid_constant_
 // DEMBinTriangleKernels.cu:22-221, DEMContactKernels_SphereTriangle.cu:116-427, and the host merge of
 // HostSideHelpers.hpp:176-193).  A triangle is registered in every cell that its bounding box, grown by the largest
 // inflated sphere radius plus its own margin, overlaps; a sphere then only looks at the triangles of its own cell.
-__device__ __forceinline__ void tri_cell_range(const GridInfo& g, const CdParams& C, float4 a, float4 b, float4 c,
+// Returns false when the facet lies entirely outside the cell columns this rank bins (domain decomposition: every rank
+// holds all facets of the replicated mesh owners but registers only those that can meet its slab).
+__device__ __forceinline__ bool tri_cell_range(const GridInfo& g, const CdParams& C, float4 a, float4 b, float4 c,
                                                int lo[3], int hi[3]) {
     const float grow = C.rmax + g.max_margin + a.w + 1e-6f * (fabsf(a.x) + fabsf(a.y) + fabsf(a.z) + 1.f);
     const float mn[3] = {fminf(a.x, fminf(b.x, c.x)) - grow, fminf(a.y, fminf(b.y, c.y)) - grow, fminf(a.z, fminf(b.z, c.z)) - grow};
     const float mx[3] = {fmaxf(a.x, fmaxf(b.x, c.x)) + grow, fmaxf(a.y, fmaxf(b.y, c.y)) + grow, fmaxf(a.z, fmaxf(b.z, c.z)) + grow};
     const int nb[3] = {(int)g.nbx, (int)g.nby, (int)g.nbz};
+    if (C.slab_on) {
+        const int xl = (int)floorf(mn[0] * g.inv_cs) - g.x0, xh = (int)floorf(mx[0] * g.inv_cs) - g.x0;
+        if (xh < 0 || xl > nb[0] - 1) return false;
+    }
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int off = (k == 0) ? g.x0 : 0;
         lo[k] = min(max((int)floorf(mn[k] * g.inv_cs) - off, 0), nb[k] - 1);
         hi[k] = min(max((int)floorf(mx[k] * g.inv_cs) - off, 0), nb[k] - 1);
     }
+    return true;
 }
 
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_tri_cells(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.nTri) return;
     const GridInfo g = *C.grid;
     float4 a, b, c;
     if (!FILL) {
         const uint2 info = P.tri_info[t];
-        if (P.active && P.active[info.x] == 0) {  // mesh owner not held by this rank
-            C.triW1[t] = make_float4(0.f, 0.f, 0.f, -1.f);
-            return;
-        }
         const OwnerState* sb = P.state + info.x;
         const float4 q = sb->quat;
         const float4 v = sb->vel;
@@ -548,10 +688,9 @@ __global__ void __launch_bounds__(128) k_tri_cells(const __grid_constant__ DevPa
         C.triW1[t] = a; C.triW2[t] = b; C.triW3[t] = c;
     } else {
         a = C.triW1[t]; b = C.triW2[t]; c = C.triW3[t];
-        if (a.w < 0.f) return;
     }
     int lo[3], hi[3];
-    tri_cell_range(g, C, a, b, c, lo, hi);
+    if (!tri_cell_range(g, C, a, b, c, lo, hi)) return;
     for (int z = lo[2]; z <= hi[2]; z++)
         for (int y = lo[1]; y <= hi[1]; y++)
             for (int x = lo[0]; x <= hi[0]; x++) {
@@ -560,7 +699,7 @@ __global__ void __launch_bounds__(128) k_tri_cells(const __grid_constant__ DevPa
                     atomicAdd(&C.triCellStart[cell], 1u);
                 } else {
                     const uint32_t slot = C.triCellStart[cell] + atomicAdd(&C.triCellFill[cell], 1u);
-                    if (slot < C.tri_pair_cap) C.triCellList[slot] = t; else atomicOr(&P.flags[0], 16u);
+                    if (slot < C.tri_pair_cap) C.triCellList[slot] = t; else atomicOr(&P.flags[DEM_FLAG_CAPACITY], 16u);
                 }
             }
 }
@@ -601,71 +740,73 @@ __device__ __forceinline__ float tri_point_dist2(float3 a, float3 b, float3 c, f
     return dot(d, d);
 }
 
-constexpr int ST_MAXC = 24;
-
-// per sphere (sphere-id order): candidates among the triangles registered in the sphere's own cell
-__global__ void __launch_bounds__(128) k_st_emit(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
-    const uint32_t sid = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = sid < P.nSpheres;
-    uint32_t key = 0;
-    if (valid) {
-        key = C.keys[0][sid];
-        if (key == 0xffffffffu) {
-            P.st.seg_start[sid] = 0; P.st.seg_count[sid] = 0;
-            valid = false;
-        }
+// is triangle t a contact candidate of the sphere `me` (inflated radius in .w, family famS)?
+__device__ __forceinline__ bool st_candidate(const DevParams& P, const CdParams& C, float4 me, uint32_t famS, uint32_t t) {
+    const float4 a = C.triW1[t], b = C.triW2[t], c = C.triW3[t];
+    const float R = me.w + a.w;
+    const float d2 = tri_point_dist2(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), f3(me.x, me.y, me.z));
+    if (d2 > R * R * 1.00001f + 1e-18f) return false;
+    if (C.any_mask) {
+        const uint32_t famT = P.state[P.tri_info[t].x].pos.family;
+        if (P.familyMasks[mask_pair(famS, famT)] != 0) return false;
     }
-    uint32_t acc[ST_MAXC];
-    uint32_t count = 0;
-    uint2 s = make_uint2(0, 0);
-    if (valid) {
-        s = P.sph[sid];
-        const float4 me = C.sphF[sid];
-        const uint32_t famS = P.state[s.x].pos.family;
-        const uint32_t tb = C.triCellStart[key], te = min(C.triCellStart[key + 1], C.tri_pair_cap);
+    return true;
+}
+
+// per sphere (sphere-id order): candidates among the triangles registered in the sphere's own cell.  Two passes over
+// the cell's triangle list -- count, claim a run of slots with one warp-aggregated atomic, test again and write -- so
+// there is no cap on the number of facets a sphere may touch (a mesh finer than the grains is legal).
+__global__ void __launch_bounds__(128) k_st_emit(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = C.act_sph ? *C.act_count : P.nSpheres;
+    const uint32_t nround = (n + 31u) & ~31u;
+    for (uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x; t_ < nround; t_ += gridDim.x * blockDim.x) {
+        const bool valid = t_ < n;
+        const uint32_t sid = (valid && C.act_sph) ? C.act_sph[t_] : t_;
+        uint32_t count = 0, tb = 0, te = 0, famS = 0;
+        uint2 s = make_uint2(0, 0);
+        float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) {
+            const uint32_t key = C.keys[0][sid];
+            s = P.sph[sid];
+            me = C.sphF[sid];
+            famS = P.state[s.x].pos.family;
+            tb = C.triCellStart[key];
+            te = min(C.triCellStart[key + 1], C.tri_pair_cap);
+            for (uint32_t k = tb; k < te; k++) count += st_candidate(P, C, me, famS, C.triCellList[k]) ? 1u : 0u;
+        }
+        uint32_t slot = warp_claim(count, P.st.count);
+        if (!valid) continue;
+        P.st.seg_start[sid] = slot;
+        P.st.seg_count[sid] = (slot + count <= C.capacity) ? count : (slot < C.capacity ? C.capacity - slot : 0u);
+        if (count == 0) continue;
+        if (slot + count > C.capacity) atomicOr(&P.flags[DEM_FLAG_CAPACITY], 32u);
+        const uint32_t oldStart = C.oldst.seg_start[sid], oldCount = C.oldst.seg_count[sid];
         for (uint32_t k = tb; k < te; k++) {
             const uint32_t t = C.triCellList[k];
-            const float4 a = C.triW1[t], b = C.triW2[t], c = C.triW3[t];
-            const float R = me.w + a.w;
-            const float d2 = tri_point_dist2(f3(a.x, a.y, a.z), f3(b.x, b.y, b.z), f3(c.x, c.y, c.z), f3(me.x, me.y, me.z));
-            if (d2 > R * R * 1.00001f + 1e-18f) continue;
-            if (C.any_mask) {
-                const uint32_t famT = P.state[P.tri_info[t].x].pos.family;
-                if (P.familyMasks[mask_pair(famS, famT)] != 0) continue;
+            if (!st_candidate(P, C, me, famS, t)) continue;
+            if (slot < C.capacity) {
+                float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
+                uint32_t alive = 0;
+                for (uint32_t j = 0; j < oldCount; j++) {
+                    if (C.oldst.idB[oldStart + j] == t) {
+                        alive = C.oldst.cinfo[oldStart + j].w & 0x80000000u;
+                        if (alive && C.oldst.hist) h = C.oldst.hist[oldStart + j];
+                        break;
+                    }
+                }
+                const uint32_t matpair = (s.y >> 16) * P.nMat + P.tri_info[t].y;
+                P.st.idB[slot] = t;
+                P.st.cinfo[slot] = make_uint4(s.x, t, s.y & 0xffffu, matpair | alive);
+                if (P.st.hist) P.st.hist[slot] = h;
             }
-            if (count < ST_MAXC) acc[count] = t;
-            count++;
+            slot++;
         }
-        if (count > ST_MAXC) { atomicOr(&P.flags[2], 2u); count = ST_MAXC; }
-    }
-    uint32_t slot = warp_claim(count, P.st.count);
-    if (!valid) return;
-    P.st.seg_start[sid] = slot;
-    P.st.seg_count[sid] = (slot + count <= C.capacity) ? count : (slot < C.capacity ? C.capacity - slot : 0u);
-    if (count == 0) return;
-    if (slot + count > C.capacity) atomicOr(&P.flags[0], 32u);
-    const uint32_t oldStart = C.oldst.seg_start[sid], oldCount = C.oldst.seg_count[sid];
-    for (uint32_t k = 0; k < count; k++, slot++) {
-        if (slot >= C.capacity) break;
-        const uint32_t t = acc[k];
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
-        uint32_t alive = 0;
-        for (uint32_t j = 0; j < oldCount; j++) {
-            if (C.oldst.pair[oldStart + j].y == t) {
-                alive = C.oldst.cinfo[oldStart + j].w & 0x80000000u;
-                if (alive && C.oldst.hist) h = C.oldst.hist[oldStart + j];
-                break;
-            }
-        }
-        const uint32_t matpair = (s.y >> 16) * P.nMat + P.tri_info[t].y;
-        P.st.pair[slot] = make_uint2(sid, t);
-        P.st.cinfo[slot] = make_uint4(s.x, t, s.y & 0xffffu, matpair | alive);
-        if (P.st.hist) P.st.hist[slot] = h;
     }
 }
 
-// stage 0: world nodes + per-cell counts; stage 1: fill the per-cell triangle lists (after the scan) and emit the list
-int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaStream_t s) {
+// stage 0: world nodes + per-cell counts + fill of the per-cell triangle lists; stage 1: the sphere--triangle list
+int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, int num_sms, cudaStream_t s) {
     if (P.nTri == 0) {
         if (stage == 0) cudaMemsetAsync(P.st.count, 0, sizeof(uint32_t) * 4, s);
         return 0;
@@ -673,172 +814,30 @@ int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, cudaSt
     int launches = 0;
     if (stage == 0) {
         cudaMemsetAsync(P.st.count, 0, sizeof(uint32_t) * 4, s);
-        cudaMemsetAsync(C.triCellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
-        cudaMemsetAsync(C.triCellFill, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 1), s);
+        cudaMemsetAsync(C.triCellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 2), s);
+        cudaMemsetAsync(C.triCellFill, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 2), s);
         k_tri_cells<false><<<(P.nTri + 127) / 128, 128, 0, s>>>(P, C);
-        launches += 1 + launch_scan_exclusive(C.triCellStart, C.max_cells + 1, C.scan_tmp, nullptr, s);
+        launches += 1 + launch_scan_lookback(C.triCellStart, C.triCellStart, &C.grid->ncells, 1u, C.max_cells + 1, C.scan_desc,
+                                             nullptr, P.flags, num_sms, s);
         k_tri_cells<true><<<(P.nTri + 127) / 128, 128, 0, s>>>(P, C);
         launches++;
     } else if (P.nSpheres) {
-        k_st_emit<<<(P.nSpheres + 127) / 128, 128, 0, s>>>(P, C);
+        const int grid = (int)std::min<uint32_t>((P.nSpheres + 127) / 128, (uint32_t)num_sms * 16u);
+        k_st_emit<<<grid, 128, 0, s>>>(P, C);
         launches++;
     }
     return launches;
 }
 
-constexpr int SWEEP_MAXC = 40;  // accepted candidates staged per sphere (half stencil)
-constexpr uint32_t CINFO_NO_HISTORY = 0x40000000u;  // sweep -> k_history: this contact carries no history over
-
-// The sweep.  Cells are x-fastest, so the x-neighbours of a row are ONE contiguous run of the cell-sorted array.
-// Each sphere looks only "forward" (upper half of the 27-cell stencil => 5 runs, the own row starting right behind
-// itself), so every pair is found exactly once by the sphere that comes first in the sorted order; that sphere is
-// geometry A of the contact.
-__global__ void __launch_bounds__(128) k_sweep(const __grid_constant__ DevParams P,
-                                               const __grid_constant__ CdParams C,
-                                               const uint32_t* __restrict__ keys) {
-    // One thread per sphere IN SPHERE-ID ORDER (clump by clump), so that the slots claimed below make the contact list
-    // owner-major: the force kernel then streams the A side and reduces it inside the warp.
-    const uint32_t t_ = blockIdx.x * blockDim.x + threadIdx.x;
-    bool valid = t_ < (C.act_sph ? C.nActSph : P.nSpheres);
-    const uint32_t sid = (valid && C.act_sph) ? C.act_sph[t_] : t_;
-    if (valid && C.keys[0][sid] == 0xffffffffu) {
-        // inactive on this rank: leave empty segments behind so that later history look-ups find nothing stale
-        P.ss.seg_start[sid] = 0; P.ss.seg_count[sid] = 0;
-        P.sn.seg_start[sid] = 0; P.sn.seg_count[sid] = 0;
-        valid = false;
-    }
-    const uint32_t j = valid ? C.sortedPos[sid] : 0u;
-    uint32_t acc[SWEEP_MAXC];  // staged candidates: sorted index, bit 31 = spheres overlap right now
-    uint32_t count = 0, countT = 0;
-    uint4 meta = make_uint4(0, 0, 0, 0);
-    float4 me = make_float4(0.f, 0.f, 0.f, 0.f);
-    float myMargin = 0.f;
-    if (valid) {
-        const GridInfo g = *C.grid;
-        me = C.sortedSph[j];
-        meta = C.sortedMeta[j];
-        myMargin = me.w - __ldg(&P.comp[meta.z & 0xffffu]).w;
-        const uint32_t key = keys[j];
-        const int cx = (int)(key % g.nbx);
-        const int cy = (int)((key / g.nbx) % g.nby);
-        const int cz = (int)(key / (g.nbx * g.nby));
-        const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
-        const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
-        const float extraA = fam_on ? P.familyExtraMargin[meta.w] : 0.f;
-        // ---- the five runs of the half stencil: all ten bounds are fetched before any of them is used ----
-        uint32_t qb[5], qe[5];
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            // r=0: own row behind me; r=1: (dy=+1,dz=0); r=2..4: (dy=-1,0,+1; dz=+1)
-            const int dy = (r == 0) ? 0 : (r == 1 ? 1 : r - 3);
-            const int dz = (r < 2) ? 0 : 1;
-            const int y = cy + dy, z = cz + dz;
-            const bool ok = !(y < 0 || y >= (int)g.nby || z >= (int)g.nbz);
-            const uint32_t row = ok ? g.nbx * ((uint32_t)y + g.nby * (uint32_t)z) : 0u;
-            qb[r] = (r == 0) ? j + 1 : (ok ? __ldg(&C.cellStart[row + x0]) : 0u);
-            qe[r] = ok ? __ldg(&C.cellStart[row + x1 + 1]) : 0u;
-        }
-        // ---- distance test, four candidates in flight at a time (independent 16-byte loads of the sorted stream) ----
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            for (uint32_t q = qb[r]; q < qe[r]; q += 4) {
-                float4 ot[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) ot[u] = __ldg(&C.sortedSph[min(q + u, qe[r] - 1u)]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (q + u >= qe[r]) break;
-                    const float dx = me.x - ot[u].x, dy2 = me.y - ot[u].y, dz2 = me.z - ot[u].z;
-                    const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
-                    const float R = me.w + ot[u].w;
-                    // superset of the double-precision test d2 <= R^2 && R - d > min(extraA, extraB)
-                    if (d2 > R * R * 1.000001f + 1e-20f) continue;
-                    if (count < SWEEP_MAXC) acc[count] = q + u;
-                    count++;
-                }
-            }
-        }
-        if (count > SWEEP_MAXC) {
-            atomicOr(&P.flags[2], 1u);  // more neighbours within reach of one sphere than can be staged
-            count = SWEEP_MAXC;
-        }
-        // ---- owner / family filter and "in touch right now?" on the staged few (their records, four at a time) ----
-        uint32_t kept = 0;
-        for (uint32_t k0 = 0; k0 < count; k0 += 4) {
-            uint4 om[4];
-            float4 ot[4];
-            uint32_t qq[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                qq[u] = acc[min(k0 + u, count - 1u)];
-                om[u] = __ldg(&C.sortedMeta[qq[u]]);
-                ot[u] = __ldg(&C.sortedSph[qq[u]]);
-            }
-#pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (k0 + u >= count) break;
-                if (om[u].x == meta.x) continue;  // same owner
-                const float dx = me.x - ot[u].x, dy2 = me.y - ot[u].y, dz2 = me.z - ot[u].z;
-                const float d2 = dx * dx + dy2 * dy2 + dz2 * dz2;
-                const float R = me.w + ot[u].w;
-                if (fam_on) {
-                    if (C.any_mask && P.familyMasks[mask_pair(meta.w, om[u].w)] != 0) continue;
-                    const float Rt = R - fminf(extraA, P.familyExtraMargin[om[u].w]);
-                    if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
-                }
-                // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
-                const float Rtrue = R - myMargin - (ot[u].w - __ldg(&P.comp[om[u].z & 0xffffu]).w);
-                const uint32_t touching = (d2 < Rtrue * Rtrue) ? 0x80000000u : 0u;
-                acc[kept++] = qq[u] | touching;  // (kept <= k0 + u: never overtakes the read position)
-                countT += touching >> 31;
-            }
-        }
-        count = kept;
-    }
-    const uint32_t countN = count - countT;
-    uint32_t slotT = warp_claim(countT, P.ss.count);
-    uint32_t slotN = warp_claim(countN, P.sn.count);
-    if (!valid) return;
-    P.ss.seg_start[meta.y] = slotT;
-    P.ss.seg_count[meta.y] = (slotT + countT <= C.capacity) ? countT : (slotT < C.capacity ? C.capacity - slotT : 0u);
-    P.sn.seg_start[meta.y] = slotN;
-    P.sn.seg_count[meta.y] = (slotN + countN <= C.capacity) ? countN : (slotN < C.capacity ? C.capacity - slotN : 0u);
-    if (count == 0) return;
-    if (slotT + countT > C.capacity) atomicOr(&P.flags[0], 1u);
-    if (slotN + countN > C.capacity) atomicOr(&P.flags[0], 4u);
-    const uint32_t nM = P.nMat;
-    for (uint32_t k = 0; k < count; k++) {
-        const bool touching = (acc[k] >> 31) != 0u;
-        const uint4 om = __ldg(&C.sortedMeta[acc[k] & 0x7fffffffu]);
-        const ContactList& L = touching ? P.ss : P.sn;
-        const uint32_t slot = touching ? slotT++ : slotN++;
-        if (slot >= C.capacity) continue;
-        // The history carry-over is NOT done here: per sphere it is a doubly nested search of very uneven length (the
-        // warp would run at 5-9 active lanes of 32); k_history does it with one thread per emitted contact instead.
-        uint32_t skip = 0;
-        if (!touching) {
-            // A candidate that is clearly apart at these very positions (float positions: allow for their rounding)
-            // would have its history destroyed by the force pass that follows this rebuild (no overlap => wildcards
-            // zeroed, DEMCalcForceKernels.cu:258-261): it carries none over, so there is nothing to look up or write.
-            const float4 ot = __ldg(&C.sortedSph[acc[k] & 0x7fffffffu]);
-            const float dx = me.x - ot.x, dy = me.y - ot.y, dz = me.z - ot.z;
-            const float Rtrue = (me.w - myMargin) + __ldg(&P.comp[om.z & 0xffffu]).w;
-            const float slack = 3e-7f * (fabsf(me.x) + fabsf(me.y) + fabsf(me.z)) + 1e-8f;
-            if (sqrtf(dx * dx + dy * dy + dz * dz) * 0.999999f - Rtrue * 1.000001f - slack > 0.f) skip = CINFO_NO_HISTORY;
-        }
-        const uint32_t matpair = (meta.z >> 16) * nM + (om.z >> 16);
-        L.pair[slot] = make_uint2(meta.y, om.y);
-        L.cinfo[slot] = make_uint4(meta.x, om.x, (meta.z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | skip);
-    }
-}
-
 // History carry-over (DEMHistoryMappingKernels.cu), one thread per contact of the two new sphere--sphere lists: the pair
 // may sit in either previous list as (A,B) or -- when the two spheres swapped their order in the sorted array -- as
 // (B,A); then delta_tan changes sign.  Adjacent threads hold the contacts of the same sphere A (the lists are
-// sphere-major), so their segment look-ups coalesce.
+// sphere-major), so their segment look-ups coalesce.  Sphere A of a contact comes from the scratch array the fill pass
+// of the sweep left behind (the lists themselves only keep geometry B: A is implied by the segment table).
 __global__ void __launch_bounds__(256) k_history(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
-    const uint32_t nT = min(*P.ss.count, C.capacity);
-    const uint32_t n = nT + min(*P.sn.count, C.capacity);
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t nT = min(P.ss.count[0], C.capacity);
+    const uint32_t n = nT + min(P.sn.count[0], C.capacity);
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += stride) {
         const bool touching = c < nT;
@@ -849,7 +848,8 @@ __global__ void __launch_bounds__(256) k_history(const __grid_constant__ DevPara
             L.cinfo[slot].w = w & ~CINFO_NO_HISTORY;
             continue;
         }
-        const uint2 pr = L.pair[slot];
+        const uint32_t sidA = (touching ? C.idA_ss : C.idA_sn)[slot];
+        const uint32_t sidB = L.idB[slot];
         float4 h = make_float4(0.f, 0.f, 0.f, 0.f);
         uint32_t alive = 0;
         bool found = false;
@@ -857,10 +857,10 @@ __global__ void __launch_bounds__(256) k_history(const __grid_constant__ DevPara
         for (int pass = 0; pass < 4 && !found; pass++) {
             const ContactList& O = ((pass & 1) == (touching ? 0 : 1)) ? C.oldss : C.oldsn;  // likelier list first
             const bool flipped = pass >= 2;
-            const uint32_t a = flipped ? pr.y : pr.x, b = flipped ? pr.x : pr.y;
+            const uint32_t a = flipped ? sidB : sidA, b = flipped ? sidA : sidB;
             const uint32_t os = O.seg_start[a], oc = O.seg_count[a];
             for (uint32_t t = 0; t < oc; t++) {
-                if (O.pair[os + t].y == b) {
+                if (O.idB[os + t] == b) {
                     alive = O.cinfo[os + t].w & 0x80000000u;
                     if (alive && O.hist) {
                         h = O.hist[os + t];
@@ -876,92 +876,169 @@ __global__ void __launch_bounds__(256) k_history(const __grid_constant__ DevPara
     }
 }
 
-__global__ void k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t a = *P.ss.count, b = *P.sa.count, c = *P.sn.count, d = *P.st.count;
-        P.ss.count[1] = a;  // the unclamped demand, read back by the host to size a regrow
-        P.sa.count[1] = b;
-        P.sn.count[1] = c;
-        P.st.count[1] = d;
-        if (d > C.capacity) { atomicOr(&P.flags[0], 32u); d = C.capacity; }
-        *P.st.count = d;
-        if (a > C.capacity) { atomicOr(&P.flags[0], 1u); a = C.capacity; }
-        if (b > C.capacity) { atomicOr(&P.flags[0], 2u); b = C.capacity; }
-        if (c > C.capacity) { atomicOr(&P.flags[0], 4u); c = C.capacity; }
-        *P.ss.count = a;
-        *P.sa.count = b;
-        *P.sn.count = c;
+// Last kernel of a rebuild (one warp): clamp the counts, agree on the verdict over the ranks, poison the context when a
+// list or table overflowed anywhere, and leave the status record for the host.
+__global__ void __launch_bounds__(32) k_finish_counts(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C,
+                                                      const __grid_constant__ MgDev M, int par) {
+    const int lane = threadIdx.x;
+    const uint32_t seq = P.flags[DEM_FLAG_SEQ] + 1u;
+    uint32_t poison = P.flags[DEM_FLAG_POISON];
+    uint32_t cnt[4] = {0, 0, 0, 0}, dem[4] = {0, 0, 0, 0};
+    uint32_t tri_demand = 0;
+    if (poison == 0u) {
+        if (lane == 0) {
+            const ContactList* L[4] = {&P.ss, &P.sn, &P.sa, &P.st};
+            const uint32_t bit[4] = {1u, 4u, 2u, 32u};
+            for (int k = 0; k < 4; k++) {
+                dem[k] = L[k]->count[0];
+                cnt[k] = min(dem[k], C.capacity);
+                if (dem[k] > C.capacity) atomicOr(&P.flags[DEM_FLAG_CAPACITY], bit[k]);
+                L[k]->count[0] = cnt[k];
+                L[k]->count[1] = dem[k];
+            }
+            if (P.nTri) {
+                tri_demand = C.triCellStart[C.grid->ncells];
+                if (tri_demand > C.tri_pair_cap) atomicOr(&P.flags[DEM_FLAG_CAPACITY], 16u);
+                P.flags[DEM_FLAG_TRI_DEMAND] = tri_demand;
+            }
+            __threadfence();
+        }
+        __syncwarp();
+        uint32_t cap = P.flags[DEM_FLAG_CAPACITY] | ((P.flags[DEM_FLAG_HALO] & 8u) ? 8u : 0u);
+        uint32_t vel = P.flags[DEM_FLAG_VELOCITY];
+        if (M.world > 1) {
+            // every rank must reach the same verdict, or they fall out of step with each other
+            uint32_t o0, o1;
+            mg_allgather(M, cap, vel, o0, o1, P.flags);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                o0 |= __shfl_xor_sync(0xffffffffu, o0, off);
+                o1 |= __shfl_xor_sync(0xffffffffu, o1, off);
+            }
+            cap = o0;
+            vel = o1;
+            if (lane == 0 && vel) P.flags[DEM_FLAG_VELOCITY] = vel;
+        }
+        if (cap) poison = seq;
+        if (lane == 0) {
+            if (poison) P.flags[DEM_FLAG_POISON] = poison;
+            RebuildStatus* st = C.status + (seq % REBUILD_STATUS_SLOTS);
+            st->poison = poison;
+            st->capflags = cap;
+            st->velflag = vel;
+            st->haloflags = P.flags[DEM_FLAG_HALO];
+            st->tri_demand = tri_demand;
+            for (int k = 0; k < 4; k++) { st->count[k] = cnt[k]; st->demand[k] = dem[k]; }
+            st->grid = *C.grid;
+            for (int k = 0; k < 8; k++) st->mg[k] = (M.world > 1) ? M.counts[par][k] : 0u;
+            if (M.world > 1) {
+                const uint32_t* rc = reinterpret_cast<const uint32_t*>(M.my_block + MG_HDR_RECV_COUNT) + par * 2;
+                st->mg[5] = rc[0]; st->mg[6] = rc[1];
+            }
+            __threadfence_system();
+            st->seq = seq;
+        }
+    } else if (lane == 0) {
+        RebuildStatus* st = C.status + (seq % REBUILD_STATUS_SLOTS);
+        st->poison = poison;
+        st->capflags = 0; st->velflag = P.flags[DEM_FLAG_VELOCITY]; st->haloflags = P.flags[DEM_FLAG_HALO];
+        __threadfence_system();
+        st->seq = seq;
     }
+    if (lane == 0) P.flags[DEM_FLAG_SEQ] = seq;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-int launch_cd_prepare(const DevParams& P, const CdParams& C, bool need_maxvel, int stage, cudaStream_t s) {
+static int gs_grid(uint32_t n, int threads, int num_sms, int per_sm) {
+    return (int)std::max<uint32_t>(1u, std::min<uint32_t>((n + threads - 1) / threads, (uint32_t)(num_sms * per_sm)));
+}
+
+int launch_cd_prepare(const DevParams& P, const CdParams& C, const MgDev* M, bool need_maxvel, int stage, int num_sms,
+                      cudaStream_t s) {
     int launches = 0;
     if (stage == 0) {
         if (need_maxvel) {
             // velocities changed outside the integrator (initial state / host upload): recompute max |v|
             cudaMemsetAsync(P.maxvel, 0, sizeof(float), s);
             if (P.nOwners) {
-                k_maxvel<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, P.errOutVel);
+                k_maxvel<<<gs_grid(P.nOwners, 256, num_sms, 8), 256, 0, s>>>(P, P.errOutVel);
                 launches++;
             }
         }
     } else if (stage == 1) {
-        k_grid_setup<<<1, 32, 0, s>>>(P, C);
+        MgDev single;
+        memset(&single, 0, sizeof(single));
+        single.world = 1;
+        k_grid_setup<<<1, 32, 0, s>>>(P, C, M ? *M : single);
         launches++;
     } else {
         if (P.nAnal) {
             k_anal_prep<<<(P.nAnal + 63) / 64, 64, 0, s>>>(P, C);
             launches++;
         }
-        cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * (size_t)C.scan_cells, s);
+        cudaMemsetAsync(C.cellStart, 0, sizeof(uint32_t) * ((size_t)C.max_cells + 2), s);  // scratch
+        // (the count words of the lists being built; under poison the lists they belong to are not looked at)
         cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
-        if (C.act_sph && P.nTri)  // the per-sphere triangle pass walks all spheres and skips those without a key
-            cudaMemsetAsync(C.keys[0], 0xff, sizeof(uint32_t) * (size_t)P.nSpheres, s);
         if (C.act_sph) {
             // spheres this rank does not hold are not visited: leave empty segments behind for them, so that later
             // history look-ups find nothing stale
-            cudaMemsetAsync(P.ss.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
-            cudaMemsetAsync(P.sn.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
-            cudaMemsetAsync(P.sa.seg_count, 0, sizeof(uint32_t) * ((size_t)P.nSpheres + 1), s);
+            launches += launch_zero_u32(P.ss.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
+            launches += launch_zero_u32(P.sn.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
+            launches += launch_zero_u32(P.sa.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
+            if (P.nTri) launches += launch_zero_u32(P.st.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
         }
-        const uint32_t n = C.act_sph ? C.nActSph : P.nSpheres;
-        if (n) {
-            k_sphere_prep<<<(n + 255) / 256, 256, 0, s>>>(P, C);
+        if (P.nSpheres) {
+            k_sphere_prep<<<gs_grid(P.nSpheres, 256, num_sms, 8), 256, 0, s>>>(P, C);
             launches++;
         }
     }
     return launches;
 }
 
-int launch_cd_sweep(const DevParams& P, const CdParams& C, int sorted_buf, cudaStream_t s, cudaEvent_t* ev, bool sort_only) {
+int launch_cd_sweep(const DevParams& P, const CdParams& C, const MgDev* M, int par, int sorted_buf, int num_sms,
+                    cudaStream_t s, cudaEvent_t* ev, bool sort_only) {
     int launches = 0;
-    const uint32_t n = C.act_sph ? C.nActSph : P.nSpheres;
-    // cell histogram -> exclusive prefix (ncells+1 entries; on a single GPU the host does not know the grid of this
-    // rebuild yet and scans the full capacity, which keeps the launch shape static)
-    launches += launch_scan_exclusive(C.cellStart, C.scan_cells, C.scan_tmp, nullptr, s);
+    const uint32_t n = P.nSpheres;
+    // cell histogram -> exclusive prefix over the ncells+1 entries of THIS rebuild's grid (device-resident length)
+    launches += launch_scan_lookback(C.cellStart, C.cellStart, &C.grid->ncells, 1u, C.max_cells + 1, C.scan_desc, nullptr,
+                                     P.flags, num_sms, s);
     if (ev) cudaEventRecord(ev[0], s);
     if (n) {
         if (sorted_buf < 0) {  // counting sort
-            k_cs_scatter<<<(n + 255) / 256, 256, 0, s>>>(P, C);
-            k_gather_sorted_cs<<<(n + 255) / 256, 256, 0, s>>>(P, C);
-            launches++;
+            k_cs_scatter<<<gs_grid(n, 256, num_sms, 8), 256, 0, s>>>(P, C);
+            k_gather_sorted_cs<<<gs_grid(n, 256, num_sms, 8), 256, 0, s>>>(P, C);
+            launches += 2;
         } else {
             k_gather_sorted<<<(n + 255) / 256, 256, 0, s>>>(P, C, C.vals[sorted_buf]);
+            launches++;
         }
         if (ev) cudaEventRecord(ev[1], s);
-        if (sort_only) return launches + 1;
-        k_sweep<<<(n + 127) / 128, 128, 0, s>>>(P, C, sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf]);
-        k_history<<<148 * 8, 256, 0, s>>>(P, C);
-        launches += 3;
+        if (!sort_only) {
+            const uint32_t* keys = sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf];
+            const int grid = gs_grid(n, 128, num_sms, 8);
+            launch_sweep_count(P, C, keys, grid, s);
+            launches += 1 + launch_scan_lookback(P.ss.seg_count, P.ss.seg_start, nullptr, n, n, C.scan_desc, P.ss.count, P.flags, num_sms, s);
+            launches += launch_scan_lookback(P.sn.seg_count, P.sn.seg_start, nullptr, n, n, C.scan_desc, P.sn.count, P.flags, num_sms, s);
+            launch_sweep_fill(P, C, keys, grid, s);
+            launches++;
+            if (P.ss.hist) {  // (a history-less force model has nothing to carry over)
+                k_history<<<num_sms * 8, 256, 0, s>>>(P, C);
+                launches++;
+            }
+        }
     } else if (ev) {
         cudaEventRecord(ev[1], s);
     }
     if (ev) cudaEventRecord(ev[2], s);
-    k_finish_counts<<<1, 32, 0, s>>>(P, C);
-    launches++;
+    if (!sort_only) {
+        MgDev single;
+        memset(&single, 0, sizeof(single));
+        single.world = 1;
+        k_finish_counts<<<1, 32, 0, s>>>(P, C, M ? *M : single, par);
+        launches++;
+    }
     if (ev) cudaEventRecord(ev[3], s);
     return launches;
 }

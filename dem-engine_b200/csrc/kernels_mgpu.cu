@@ -4,15 +4,24 @@
 // Every rank keeps GLOBALLY indexed owner arrays (1M owners x 112 B is nothing next to 180 GB of HBM), so an owner
 // never changes its index; what changes is who integrates it.  Rank r owns the owners whose centre lies in its
 // x-slab and additionally holds exact copies ("ghosts") of the neighbours' owners within the halo width of a cut.
-//   * per step   : own owners inside the halo are packed (state 64 B + spin 16 B) and sent to the neighbour, which
-//                  scatters them into the same global slots -- ncclSend/ncclRecv pairs grouped on the compute stream;
-//   * per rebuild: ownership is re-decided from positions by the same rule on both sides of a cut (the data is an
-//                  exact copy, so both sides agree without talking), the halo membership lists are exchanged, and the
-//                  ordinary rebuild runs over the active (own + ghost) spheres only.
+// EVERYTHING here is device-driven over peer-mapped memory (NVLink stores + system-scope flag words): no library call,
+// no host synchronisation, and no host-side argument changes from one step or rebuild to the next -- exchange numbers
+// and all counts live in device memory -- so whole steps and whole rebuilds replay as CUDA graphs on every rank.
+//   * per step   : the integrator stores the {state, spin} record (80 B) of each own owner inside a halo straight into
+//                  the neighbour's receive buffer; k_mg_pull publishes the exchange number to the neighbours, waits for
+//                  theirs and scatters what they stored here into the same global slots;
+//   * per rebuild: max |v| is all-gathered through per-rank mailboxes (same cell grid everywhere), ownership is
+//                  re-decided from positions by the same rule on both sides of a cut (the data is an exact copy, so
+//                  both sides agree without talking) walking only the owners this rank already holds, the halo
+//                  membership lists + records + counts are pushed to the neighbours, and the ordinary rebuild runs over
+//                  the active (own + ghost) spheres only; its verdict (overflow -> poison) is all-gathered too.
 // Contacts across a cut are evaluated on BOTH ranks from identical inputs (same roles, same arithmetic), each rank
 // applying the wrench to its own owners only: no reverse force exchange, and the contact history stays identical on
 // both sides.  Ghost--ghost contacts inside the halo are evaluated too (history only) so that an owner that later
 // crosses the cut finds the history of all its contacts already present on the rank that takes it over.
+// Wall and mesh owners are replicated ("owned" everywhere): exact while they are fixed or follow a prescribed motion.
+#include <algorithm>
+
 #include "dem_kernels.h"
 
 namespace demb {
@@ -27,199 +36,279 @@ __device__ __forceinline__ uint32_t warp_append(bool pred, uint32_t* cursor) {
     base = __shfl_sync(0xffffffffu, base, leader);
     return pred ? base + __popc(m & ((1u << lane) - 1u)) : 0xffffffffu;
 }
+__device__ __forceinline__ uint32_t warp_claim_n(uint32_t count, uint32_t* cursor) {
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = count;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(cursor, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - count;
+}
 
-// Re-decide ownership from positions and list the own owners that sit in the halo of either cut.
-//   flag[g]: 0 unknown here, 1 own, 2 ghost.   counts: [0] own, [1] send-left, [2] send-right
-__global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ DevParams P, MgParams M) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    bool own = false, toL = false, toR = false;
-    if (g < P.nOwners) {
-        const uint8_t f = M.flag[g];
-        if (f != 0) {
+__device__ __forceinline__ unsigned long long* mg_flag(char* block, int dir) {
+    return reinterpret_cast<unsigned long long*>(block + MG_HDR_STEP_FLAG) + dir;
+}
+__device__ __forceinline__ uint32_t* mg_recv_count(char* block, int par, int dir) {
+    return reinterpret_cast<uint32_t*>(block + MG_HDR_RECV_COUNT) + par * 2 + dir;
+}
+
+// ---- rebuild, step 1: forget the slots of the previous halo lists (both parities: the other one may hold the lists of
+// a failed attempt), so that the slot map only needs touching where it changes ----
+__global__ void __launch_bounds__(256) k_mg_unmap(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    for (int par = 0; par < 2; par++)
+        for (int d = 0; d < 2; d++) {
+            const uint32_t n = min(M.counts[par][1 + d], M.cap);
+            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+                M.send_slot[d][M.send_gid[par][d][i]] = -1;
+        }
+}
+
+// ---- step 2: re-decide ownership from positions, walking the owners of the previous cycle's active list only; own
+// owners go to the new active list, those inside the halo of a cut additionally to that cut's send list ----
+//   flag[g]: 0 unknown here, 1 own, 2 ghost.   counts[par]: [0] own, [1] send-left, [2] send-right, [3] active
+__global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M,
+                                                     const GridInfo* __restrict__ grid, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = M.counts[par ^ 1][3];
+    const uint32_t nround = (n + 31u) & ~31u;
+    const float halo = grid->halo;
+    uint32_t* cnt = M.counts[par];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+        bool own = false, toL = false, toR = false;
+        uint32_t g = 0;
+        if (t < n) {
+            g = M.active_list[par ^ 1][t];
             if (g >= M.nClumpOwners) {
-                own = true;  // boundary / analytical owners are replicated and "owned" everywhere
+                own = true;  // boundary / analytical / mesh owners are replicated and "owned" everywhere
             } else {
                 double X, Y, Z;
                 pos_decode(P.state[g].pos, P, X, Y, Z);
                 const float x = (float)X;  // LBF-relative
                 own = (x >= M.cut_lo) && (x < M.cut_hi);
                 if (own) {
-                    const float halo = M.grid->halo;
-                    toL = M.has_left && (x < M.cut_lo + halo);
-                    toR = M.has_right && (x >= M.cut_hi - halo);
+                    toL = M.has[0] && (x < M.cut_lo + halo);
+                    toR = M.has[1] && (x >= M.cut_hi - halo);
                 }
             }
+            M.flag[g] = own ? 1 : 0;  // ghosts are re-flagged when the neighbour's list arrives
         }
-        M.flag[g] = own ? 1 : 0;  // ghosts are re-flagged when the neighbour's list arrives
+        const uint32_t sa = warp_append(own, &cnt[3]);
+        if (own) M.active_list[par][sa] = g;
+        warp_append(own && g < M.nClumpOwners, &cnt[0]);
+        const uint32_t sl = warp_append(toL, &cnt[1]);
+        const uint32_t sr = warp_append(toR, &cnt[2]);
+        if (toL && sl < M.cap) { M.send_gid[par][0][sl] = g; M.send_slot[0][g] = (int32_t)sl; }
+        if (toR && sr < M.cap) { M.send_gid[par][1][sr] = g; M.send_slot[1][g] = (int32_t)sr; }
+        if ((toL && sl >= M.cap) || (toR && sr >= M.cap)) atomicOr(&P.flags[DEM_FLAG_HALO], 8u);
     }
-    const uint32_t sl = warp_append(toL, &M.counts[1]);
-    const uint32_t sr = warp_append(toR, &M.counts[2]);
-    if (toL && sl < M.send_cap) M.send_gid[0][sl] = g;
-    if (toR && sr < M.send_cap) M.send_gid[1][sr] = g;
-    if ((toL && sl >= M.send_cap) || (toR && sr >= M.send_cap)) atomicOr(&P.flags[0], 8u);
 }
 
-// gather {state, spin} of the listed owners into a contiguous send buffer (80 B per owner)
-__global__ void __launch_bounds__(256) k_mg_pack(const __grid_constant__ DevParams P, const uint32_t* __restrict__ gid,
-                                                 uint32_t n, int4* __restrict__ buf) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * 5u) return;
-    const uint32_t i = t / 5u, part = t - i * 5u;
-    const uint32_t g = gid[i];
-    const int4* src = (part < 4) ? reinterpret_cast<const int4*>(P.state + g) + part
-                                 : reinterpret_cast<const int4*>(P.spin + g);
-    buf[(size_t)i * 5u + part] = *src;
-}
-
-// scatter received {state, spin} into the global slots and (at a rebuild) flag them as ghosts
-__global__ void __launch_bounds__(256) k_mg_unpack(const __grid_constant__ DevParams P, const uint32_t* __restrict__ gid,
-                                                   uint32_t n, const int4* __restrict__ buf, uint8_t* flag) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * 5u) return;
-    const uint32_t i = t / 5u, part = t - i * 5u;
-    const uint32_t g = gid[i];
-    int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + g) + part : reinterpret_cast<int4*>(P.spin + g);
-    *dst = buf[(size_t)i * 5u + part];
-    if (flag && part == 0) flag[g] = 2;
-}
-
-// compact list of the active owners (own and ghost) for the integrator
-__global__ void __launch_bounds__(256) k_mg_active_list(const __grid_constant__ DevParams P, MgParams M) {
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = (g < P.nOwners) && (M.flag[g] != 0);
-    const uint32_t slot = warp_append(act, &M.counts[3]);
-    if (act) M.active_list[slot] = g;
-    const bool own = act && M.flag[g] == 1;
-    warp_append(own, &M.counts[0]);
-}
-
-// compact list of the spheres of active owners: the rebuild walks this list instead of all spheres, so its cost follows
-// the slab, not the whole bed.  Warps append in arrival order, lanes in sphere order: the spheres of a clump stay
-// adjacent (up to a warp boundary), which is all the owner-major contact order needs.
-__global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant__ DevParams P, MgParams M) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool act = (i < P.nSpheres) && (M.flag[P.sph[i].x] != 0);
-    const uint32_t slot = warp_append(act, &M.counts[4]);
-    if (act) M.act_sph[slot] = i;
-}
-
-// ---------------------------------------------------------------------------------------------------------------
-// Per-step exchange without a library call: every rank stores the {state, spin} records of its halo owners straight into
-// the neighbour's receive buffer over NVLink (peer memory mapped with cudaIpc*), then publishes the epoch number in the
-// neighbour's flag word; the neighbour's pull kernel waits for that word and scatters the records into its global
-// slots.  Receive buffers are double buffered by epoch parity: a rank can run at most one exchange ahead of its
-// neighbour (it cannot finish pull(e) before the neighbour has pushed epoch e), so the half written in epoch e+1 is
-// the one the neighbour finished reading in epoch e-1.
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(256) k_mg_push(const __grid_constant__ DevParams P, const __grid_constant__ MgP2P X) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n0 = X.n_send[0] * 5u, n1 = X.n_send[1] * 5u;
-    if (t < n0 + n1) {
-        const int d = t < n0 ? 0 : 1;
-        const uint32_t u = d == 0 ? t : t - n0;
-        const uint32_t i = u / 5u, part = u - i * 5u;
-        const uint32_t g = X.send_gid[d][i];
-        const int4* src = (part < 4) ? reinterpret_cast<const int4*>(P.state + g) + part
-                                     : reinterpret_cast<const int4*>(P.spin + g);
-        X.peer_recv[d][(size_t)i * 5u + part] = *src;
+// ---- step 3: push the membership lists, their records and their lengths into the neighbours' blocks, then publish the
+// exchange number (last block to finish) ----
+__global__ void __launch_bounds__(256) k_mg_push_full(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const unsigned long long e = *M.epoch + 1ull;
+    const int half = (int)(e & 1ull);
+    for (int d = 0; d < 2; d++) {
+        if (!M.has[d]) continue;
+        char* peer = M.peer_block[M.rank + (d == 0 ? -1 : 1)];
+        const uint32_t n = min(M.counts[par][1 + d], M.cap);
+        uint32_t* pg = reinterpret_cast<uint32_t*>(peer + mg_off_gid(M.cap, par, 1 - d));
+        int4* pr = reinterpret_cast<int4*>(peer + mg_off_rec(M.cap, 1 - d, half));
+        const uint32_t* gid = M.send_gid[par][d];
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 5u; t += gridDim.x * blockDim.x) {
+            const uint32_t i = t / 5u, part = t - i * 5u;
+            const uint32_t g = gid[i];
+            const int4* src = (part < 4) ? reinterpret_cast<const int4*>(P.state + g) + part
+                                         : reinterpret_cast<const int4*>(P.spin + g);
+            pr[(size_t)i * 5u + part] = *src;
+            if (part == 0) pg[i] = g;
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) *mg_recv_count(peer, par, 1 - d) = n;
     }
     // publish: all stores of this grid, then the flag (last block to arrive does it)
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t done = atomicAdd(X.block_counter, 1u);
+        const uint32_t done = atomicAdd(&M.block_ctr[1], 1u);
         if (done == gridDim.x - 1) {
-            *X.block_counter = 0;
+            M.block_ctr[1] = 0;
             __threadfence_system();
-            if (X.has[0]) st_release_sys(X.peer_flag[0], X.epoch);
-            if (X.has[1]) st_release_sys(X.peer_flag[1], X.epoch);
+            for (int d = 0; d < 2; d++)
+                if (M.has[d]) st_release_sys(mg_flag(M.peer_block[M.rank + (d == 0 ? -1 : 1)], 1 - d), e);
         }
     }
 }
 
-__global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevParams P, const __grid_constant__ MgP2P X) {
-    if (X.publish && blockIdx.x == 0 && threadIdx.x == 0) {
-        // fused push: the integrator (the previous kernel in this stream) stored my halo records into the neighbours'
-        // buffers; tell them the epoch is complete BEFORE waiting for theirs (no rank waits for another's wait)
-        __threadfence_system();
-        if (X.has[0]) st_release_sys(X.peer_flag[0], X.epoch);
-        if (X.has[1]) st_release_sys(X.peer_flag[1], X.epoch);
-    }
-    if (threadIdx.x == 0) {
-        const long long t0 = clock64();
-        for (int d = 0; d < 2; d++) {
-            if (!X.has[d]) continue;
-            while (ld_acquire_sys(X.my_flag[d]) < X.epoch) {
-                if (clock64() - t0 > 20000000000ll) {  // ~10 s: the neighbour is gone; report instead of hanging
-                    atomicOr(&P.flags[0], 64u);
-                    break;
-                }
+// wait until both neighbours have published exchange e (called by one thread per block)
+__device__ __forceinline__ void mg_wait_neighbours(const DevParams& P, const MgDev& M, unsigned long long e) {
+    const long long t0 = clock64();
+    for (int d = 0; d < 2; d++) {
+        if (!M.has[d]) continue;
+        while (ld_acquire_sys(mg_flag(M.my_block, d)) < e) {
+            if (clock64() - t0 > MG_SPIN_TIMEOUT_CYCLES) {
+                atomicOr(&P.flags[DEM_FLAG_HALO], 64u);
+                break;
             }
         }
     }
+}
+// the last block to finish advances the exchange counter (every block read it before taking part)
+__device__ __forceinline__ void mg_finish_exchange(const MgDev& M, unsigned long long e) {
     __syncthreads();
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t n0 = X.n_recv[0] * 5u, n1 = X.n_recv[1] * 5u;
-    if (t >= n0 + n1) return;
-    const int d = t < n0 ? 0 : 1;
-    const uint32_t u = d == 0 ? t : t - n0;
-    const uint32_t i = u / 5u, part = u - i * 5u;
-    const uint32_t g = X.recv_gid[d][i];
-    int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + g) + part : reinterpret_cast<int4*>(P.spin + g);
-    *dst = __ldcg(&X.my_recv[d][(size_t)i * 5u + part]);  // written by the peer: never through this SM's L1
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const uint32_t done = atomicAdd(&M.block_ctr[0], 1u);
+        if (done == gridDim.x - 1) {
+            M.block_ctr[0] = 0;
+            *M.epoch = e;
+        }
+    }
 }
 
-int launch_mg_push(const DevParams& P, const MgP2P& X, cudaStream_t s) {
-    const uint32_t n = (X.n_send[0] + X.n_send[1]) * 5u;
-    k_mg_push<<<(n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s>>>(P, X);
-    return 1;
+// ---- step 4: take in the neighbours' lists: scatter the records, flag the owners as ghosts, append them to the new
+// active list ----
+__global__ void __launch_bounds__(256) k_mg_pull_full(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const unsigned long long e = *M.epoch + 1ull;
+    const int half = (int)(e & 1ull);
+    if (threadIdx.x == 0) mg_wait_neighbours(P, M, e);
+    __syncthreads();
+    for (int d = 0; d < 2; d++) {
+        if (!M.has[d]) continue;
+        const uint32_t n = min(__ldcg(mg_recv_count(M.my_block, par, d)), M.cap);
+        const uint32_t* gid = reinterpret_cast<const uint32_t*>(M.my_block + mg_off_gid(M.cap, par, d));
+        const int4* rec = reinterpret_cast<const int4*>(M.my_block + mg_off_rec(M.cap, d, half));
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 5u; t += gridDim.x * blockDim.x) {
+            const uint32_t i = t / 5u, part = t - i * 5u;
+            const uint32_t g = __ldcg(&gid[i]);  // written by the peer: never through this SM's L1
+            int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + g) + part : reinterpret_cast<int4*>(P.spin + g);
+            *dst = __ldcg(&rec[(size_t)i * 5u + part]);
+        }
+        const uint32_t nround = (n + 31u) & ~31u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+            const bool in = i < n;
+            const uint32_t g = in ? __ldcg(&gid[i]) : 0u;
+            if (in) M.flag[g] = 2;
+            const uint32_t slot = warp_append(in, &M.counts[par][3]);
+            if (in) M.active_list[par][slot] = g;
+        }
+    }
+    mg_finish_exchange(M, e);
 }
-int launch_mg_pull(const DevParams& P, const MgP2P& X, cudaStream_t s) {
-    const uint32_t n = (X.n_recv[0] + X.n_recv[1]) * 5u;
-    k_mg_pull<<<(n + 255) / 256 + (n == 0 ? 1 : 0), 256, 0, s>>>(P, X);
+
+// ---- step 5: compact list of the spheres of the active owners: the rebuild walks this list instead of all spheres, so
+// its cost follows the slab, not the whole bed.  The spheres of a clump stay adjacent, which is all the owner-major
+// contact order needs. ----
+__global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    if (M.owner_sph) {
+        const uint32_t n = M.counts[par][3];
+        const uint32_t nround = (n + 31u) & ~31u;
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
+            uint2 r = make_uint2(0u, 0u);
+            if (t < n) r = M.owner_sph[M.active_list[par][t]];
+            const uint32_t base = warp_claim_n(r.y, &M.counts[par][4]);
+            for (uint32_t k = 0; k < r.y; k++) M.act_sph[base + k] = r.x + k;
+        }
+    } else {
+        // (spheres of an owner are not contiguous in this input: scan them all)
+        const uint32_t nround = (P.nSpheres + 31u) & ~31u;
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
+            const bool act = (i < P.nSpheres) && (M.flag[P.sph[i].x] != 0);
+            const uint32_t slot = warp_append(act, &M.counts[par][4]);
+            if (act) M.act_sph[slot] = i;
+        }
+    }
+}
+
+int launch_mg_redistribute(const DevParams& P, const MgDev& M, const GridInfo* grid, int par, int num_sms, cudaStream_t s) {
+    const int g = num_sms * 2;
+    k_mg_unmap<<<32, 256, 0, s>>>(P, M);
+    launch_zero_u32(M.counts[par], 8, P.flags, num_sms, s);
+    k_mg_classify<<<g, 256, 0, s>>>(P, M, grid, par);
+    k_mg_push_full<<<std::min(g, 64), 256, 0, s>>>(P, M, par);
+    k_mg_pull_full<<<std::min(g, 64), 256, 0, s>>>(P, M, par);
+    k_mg_active_spheres<<<g, 256, 0, s>>>(P, M, par);
+    return 6;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Per-step exchange.  The integrator (the previous kernel in this stream) stored my halo records into the neighbours'
+// buffers; block 0 tells them the exchange is complete BEFORE anybody waits for theirs (no rank waits for another's
+// wait), every block waits for the neighbours' flags and scatters the records they stored here.  Receive buffers are
+// double buffered by exchange parity: a rank can run at most one exchange ahead of its neighbour (it cannot finish
+// pull(e) before the neighbour has pushed e), so the half written in exchange e+1 is the one the neighbour finished
+// reading in exchange e-1.  The membership lists are double buffered by cycle parity for the same reason.
+__global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const unsigned long long e = *M.epoch + 1ull;
+    const int half = (int)(e & 1ull);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        __threadfence_system();
+        for (int d = 0; d < 2; d++)
+            if (M.has[d]) st_release_sys(mg_flag(M.peer_block[M.rank + (d == 0 ? -1 : 1)], 1 - d), e);
+    }
+    if (threadIdx.x == 0) mg_wait_neighbours(P, M, e);
+    __syncthreads();
+    for (int d = 0; d < 2; d++) {
+        if (!M.has[d]) continue;
+        const uint32_t n = min(__ldcg(mg_recv_count(M.my_block, par, d)), M.cap);
+        const uint32_t* gid = reinterpret_cast<const uint32_t*>(M.my_block + mg_off_gid(M.cap, par, d));
+        const int4* rec = reinterpret_cast<const int4*>(M.my_block + mg_off_rec(M.cap, d, half));
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 5u; t += gridDim.x * blockDim.x) {
+            const uint32_t i = t / 5u, part = t - i * 5u;
+            const uint32_t g = __ldcg(&gid[i]);
+            int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + g) + part : reinterpret_cast<int4*>(P.spin + g);
+            *dst = __ldcg(&rec[(size_t)i * 5u + part]);
+        }
+    }
+    mg_finish_exchange(M, e);
+}
+
+int launch_mg_pull(const DevParams& P, const MgDev& M, int par, int num_sms, cudaStream_t s) {
+    k_mg_pull<<<std::min(num_sms, 64), 256, 0, s>>>(P, M, par);
     return 1;
 }
 
-int launch_mg_classify(const DevParams& P, const MgParams& M, cudaStream_t s) {
-    cudaMemsetAsync(M.counts, 0, sizeof(uint32_t) * 8, s);
-    if (P.nOwners) k_mg_classify<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, M);
-    return 1;
+// device-side barrier over the ranks (one all-gather with nothing in it): what bench.py enqueues right before its first
+// timing event, so that the timed region starts with all GPUs level
+__global__ void __launch_bounds__(32) k_mg_barrier(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M) {
+    uint32_t o0, o1;
+    mg_allgather(M, 0u, 0u, o0, o1, P.flags);
 }
-int launch_mg_pack(const DevParams& P, const uint32_t* gid, uint32_t n, void* buf, cudaStream_t s) {
-    if (n == 0) return 0;
-    k_mg_pack<<<(n * 5u + 255) / 256, 256, 0, s>>>(P, gid, n, reinterpret_cast<int4*>(buf));
-    return 1;
-}
-int launch_mg_unpack(const DevParams& P, const uint32_t* gid, uint32_t n, const void* buf, uint8_t* flag, cudaStream_t s) {
-    if (n == 0) return 0;
-    k_mg_unpack<<<(n * 5u + 255) / 256, 256, 0, s>>>(P, gid, n, reinterpret_cast<const int4*>(buf), flag);
-    return 1;
-}
-// owner id -> slot in the neighbour's receive buffer (the integrator's fused push looks its owners up here)
-__global__ void __launch_bounds__(256) k_mg_send_map(const uint32_t* __restrict__ gid, uint32_t n, int32_t* __restrict__ slot) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) slot[gid[i]] = (int32_t)i;
-}
-int launch_mg_send_map(const uint32_t* gid, uint32_t n, int32_t* slot, uint32_t nOwners, cudaStream_t s) {
-    cudaMemsetAsync(slot, 0xff, sizeof(int32_t) * (size_t)nOwners, s);
-    if (n) k_mg_send_map<<<(n + 255) / 256, 256, 0, s>>>(gid, n, slot);
+int launch_mg_barrier(const DevParams& P, const MgDev& M, cudaStream_t s) {
+    k_mg_barrier<<<1, 32, 0, s>>>(P, M);
     return 1;
 }
 
-int launch_mg_active_spheres(const DevParams& P, const MgParams& M, cudaStream_t s) {
-    if (P.nSpheres) k_mg_active_spheres<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, M);
-    return 1;
+// In-process decomposition (all contexts in one process, peer access enabled): copy into MY arrays the records of the
+// clump owners a peer owns, straight out of the peer's arrays -- afterwards this context holds the merged state of the
+// whole system for trackers / writers / inspectors.
+__global__ void __launch_bounds__(256) k_mg_gather_owned(const __grid_constant__ DevParams P,
+                                                         const OwnerState* __restrict__ peer_state,
+                                                         const float4* __restrict__ peer_spin,
+                                                         const uint8_t* __restrict__ peer_flag, uint32_t nClumpOwners) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nClumpOwners * 5u; t += gridDim.x * blockDim.x) {
+        const uint32_t o = t / 5u, part = t - o * 5u;
+        if (peer_flag[o] != 1) continue;
+        int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + o) + part : reinterpret_cast<int4*>(P.spin + o);
+        const int4* src = (part < 4) ? reinterpret_cast<const int4*>(peer_state + o) + part
+                                     : reinterpret_cast<const int4*>(peer_spin + o);
+        *dst = *src;
+    }
 }
-int launch_mg_active_list(const DevParams& P, const MgParams& M, cudaStream_t s) {
-    if (P.nOwners) k_mg_active_list<<<(P.nOwners + 255) / 256, 256, 0, s>>>(P, M);
+int launch_mg_gather_owned(const DevParams& P, const OwnerState* peer_state, const float4* peer_spin,
+                           const uint8_t* peer_flag, uint32_t nClumpOwners, cudaStream_t s) {
+    if (nClumpOwners == 0) return 0;
+    k_mg_gather_owned<<<148 * 4, 256, 0, s>>>(P, peer_state, peer_spin, peer_flag, nClumpOwners);
     return 1;
 }
 

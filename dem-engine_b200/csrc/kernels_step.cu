@@ -11,6 +11,8 @@
 // Reference behaviour being reproduced: src/kernel/DEMCalcForceKernels.cu:44-267 (calculateContactForces),
 // DEMCustomizablePolicies/FullHertzianForceModel.cu, FrictionlessHertzianForceModel.cu,
 // src/kernel/DEMCollectForceKernels_Compact.cu:13-102 (forceToAcc), src/kernel/DEMIntegrationKernels.cu:100-264.
+#include <algorithm>
+
 #include "dem_kernels.h"
 
 namespace demb {
@@ -132,6 +134,7 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
 // candidates' warps skip the force model).  Counts are DEVICE-resident (no host sync).
 template <int MODEL, bool RECORD, int MINB, bool FAST>
 __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     const uint32_t nT = *P.ss.count;
     const uint32_t n = nT + *P.sn.count;
     const uint32_t step = gridDim.x * blockDim.x;
@@ -312,6 +315,7 @@ __device__ __forceinline__ void wall_flush(CtaWallAcc& w, const DevParams& P) {
 // sphere--analytical contacts (planes, infinite cylinders): checkSphereEntityOverlap, DEMHelperKernels.cuh:459-521
 template <int MODEL, bool RECORD>
 __global__ void __launch_bounds__(256) k_force_sa(const __grid_constant__ DevParams P) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     __shared__ CtaWallAcc wall;
     wall_init(wall);
     const uint32_t n = *P.sa.count;
@@ -459,6 +463,7 @@ __device__ __forceinline__ bool snap_to_face(D3 A, D3 B, D3 C, D3 Pt, D3& res) {
 
 template <int MODEL, bool RECORD>
 __global__ void __launch_bounds__(256) k_force_st(const __grid_constant__ DevParams P) {
+    if (P.flags[DEM_FLAG_POISON]) return;
     __shared__ CtaWallAcc wall;
     wall_init(wall);
     const uint32_t n = *P.st.count;
@@ -662,12 +667,13 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
     // (the record layout of k_mg_push: four 16-byte words of state, one of spin).  No fence here: the stores are
     // complete when this kernel is, and k_mg_pull -- next in the stream -- publishes the epoch to the neighbours.
     if (P.send_slot[0]) {
+        const uint32_t half = (uint32_t)((*P.epoch + 1ull) & 1ull);  // the exchange this step's k_mg_pull will complete
 #pragma unroll
         for (int d = 0; d < 2; d++) {
             const int32_t slot = P.send_slot[d][o];
-            if (slot >= 0) {
+            if (slot >= 0 && P.peer_rec[d]) {
                 // 80-byte records are only 16-byte aligned: five 128-bit stores
-                float4* r = reinterpret_cast<float4*>(P.peer_recv[d] + (size_t)slot * 5u);
+                float4* r = reinterpret_cast<float4*>(P.peer_rec[d] + (size_t)half * P.rec_half_int4 + (size_t)slot * 5u);
                 r[0] = make_float4(__uint_as_float((uint32_t)(pos.voxel & 0xffffffffull)),
                                    __uint_as_float((uint32_t)(pos.voxel >> 32)), __uint_as_float(p2), __uint_as_float(p3));
                 r[1] = q;
@@ -685,22 +691,23 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
 }
 
 __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.flags[DEM_FLAG_POISON]) return;
     // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
     // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.
-    if (t == 0) *P.maxvel = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *P.maxvel = 0.f;
     float absv = 0.f;
-    const uint32_t n = P.active_list ? P.nActive : P.nOwners;
-    if (t < n) {
+    const uint32_t n = P.active_list ? *P.nActivePtr : P.nOwners;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
         const uint32_t o = P.active_list ? P.active_list[t] : t;
+        float a = 0.f;
         if (P.active && P.active[o] == 2) {
             // ghost: its state arrives from the owning rank; only consume the (unused) wrench
             st_v8(P.wrench + o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
         } else {
-            absv = integrate_one(P, o);
+            a = integrate_one(P, o);
         }
-        if (!isfinite(absv) || absv > P.errOutVel) atomicOr(&P.flags[3], 1u);
-        if (!isfinite(absv)) absv = 0.f;
+        if (!isfinite(a) || a > P.errOutVel) atomicOr(&P.flags[DEM_FLAG_VELOCITY], 1u);
+        if (isfinite(a)) absv = fmaxf(absv, a);
     }
     // non-negative floats order like their bit patterns: integer max in the warp (REDUX), then in the CTA, then ONE
     // atomic per CTA (a per-warp atomic on a single address serialises 30k updates in L2)
@@ -756,10 +763,11 @@ void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaS
     }
 }
 
-void launch_integrate(const DevParams& P, cudaStream_t s) {
+void launch_integrate(const DevParams& P, int num_sms, cudaStream_t s) {
     const int block = 256;
-    const uint32_t n = P.active_list ? P.nActive : P.nOwners;
-    const int grid = (int)((n + block - 1) / block);
+    // single GPU: one owner per thread; decomposed: grid-stride over the DEVICE-resident number of active owners
+    int grid = (int)((P.nOwners + block - 1) / block);
+    if (P.active_list) grid = std::min(grid, num_sms * 8);
     if (grid > 0) k_integrate<<<grid, block, 0, s>>>(P);
 }
 

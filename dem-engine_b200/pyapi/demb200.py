@@ -26,6 +26,7 @@ EXPORTED_SYMBOLS = [
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
+    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
 ]
 
 
@@ -345,6 +346,9 @@ class Engine:
         uid = np.ascontiguousarray(unique_id, "u1")
         self._ck(self.lib.dem_mgpu_init(self.ctx, int(rank), int(world), _p(uid)))
 
+    def mgpu_barrier(self):
+        self._ck(self.lib.dem_mgpu_barrier(self.ctx))
+
     def mgpu_info(self):
         out = np.zeros(6, "u8")
         self._ck(self.lib.dem_mgpu_info(self.ctx, _p(out)))
@@ -367,3 +371,44 @@ class Engine:
         self._ck(self.lib.dem_profile_steps(self.ctx, C.c_uint64(n), out))
         return {"force_ss_us": out[0], "force_sa_us": out[1], "integrate_us": out[2], "rebuild_us_per_step": out[3],
                 "step_us": out[4], "halo_exchange_us": out[5]}
+
+
+class EngineGroup:
+    """Slab decomposition over several GPUs of THIS process (dem_mgpu_init_local): one Engine per device, all loaded with
+    the same flattened scene, stepped together (dem_group_step_async / dem_group_sync)."""
+
+    def __init__(self, flat, devices, contact_capacity=0, options=None):
+        self.lib = load_library()
+        self.engines = [Engine(d) for d in devices]
+        for e in self.engines:
+            for k, v in (options or {}).items():
+                e.set_option(k, v)
+            e.load_flat(flat, contact_capacity)
+        self.world = len(self.engines)
+        self._arr = (C.c_void_p * self.world)(*[e.ctx for e in self.engines])
+        self._ck(self.lib.dem_mgpu_init_local(self._arr, self.world))
+
+    def _ck(self, rc):
+        if rc != 0:
+            msgs = [self.lib.dem_last_error(e.ctx).decode() for e in self.engines]
+            raise DemError(rc, " | ".join(m for m in msgs if m))
+
+    def step_async(self, n):
+        self.lib.dem_group_step_async.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        self._ck(self.lib.dem_group_step_async(self._arr, self.world, int(n)))
+
+    def sync(self):
+        self._ck(self.lib.dem_group_sync(self._arr, self.world))
+
+    def step(self, n):
+        self.step_async(n)
+        self.sync()
+
+    def gather(self):
+        """merge the owners of all ranks into engines[0] (positions(), owner_state() of engines[0] then see everything)"""
+        self._ck(self.lib.dem_group_gather(self._arr, self.world))
+        return self.engines[0]
+
+    def close(self):
+        for e in self.engines:
+            e.close()

@@ -511,3 +511,29 @@ def config5_spheres(n=5000000, r=0.001, packing=0.5, seed=11, x_range=None):
     s.force_model = D.HERTZIAN_FRICTIONLESS
     s.cd_update_freq = 20
     return s
+
+
+def write_scene_file(path, scene, xyz=None, quat=None, vel=None, omg=None, scale=0.005):
+    """The scene file baseline/run_ref.cpp reads (it rebuilds the same C2 bed through the UNMODIFIED reference's own API):
+    "DEMS", u32 version 1, u32 nClumps, f32 box[3], scale, h, E, nu, CoR, mu, Crr, beta, u32 has_vel, then xyz[n][3],
+    quat_wxyz[n][4] and, when has_vel, vel[n][3], omgBar[n][3] (all f32, little endian).  xyz / quat / vel / omg default
+    to the scene's initial state; pass a downloaded state to hand a settled bed to the reference."""
+    import struct
+    xyz = np.ascontiguousarray(scene.clump_xyz if xyz is None else xyz, "<f4").reshape(-1, 3)
+    n = len(xyz)
+    quat = np.ascontiguousarray(scene.clump_quat if quat is None else quat, "<f4").reshape(n, 4)
+    has_vel = vel is not None or omg is not None or bool(np.any(scene.clump_vel)) or bool(np.any(scene.clump_omg))
+    m = scene.materials[0]
+    with open(path, "wb") as fh:
+        fh.write(b"DEMS")
+        fh.write(struct.pack("<II", 1, n))
+        fh.write(struct.pack("<3f", *[float(v) for v in scene.box]))
+        fh.write(struct.pack("<8f", float(scale), float(scene.h), float(m["E"]), float(m["nu"]), float(m["CoR"]),
+                             float(m["mu"]), float(m.get("Crr", 0.0)), float(scene.beta)))
+        fh.write(struct.pack("<I", 1 if has_vel else 0))
+        fh.write(xyz.tobytes())
+        fh.write(quat.tobytes())
+        if has_vel:
+            fh.write(np.ascontiguousarray(scene.clump_vel if vel is None else vel, "<f4").reshape(n, 3).tobytes())
+            fh.write(np.ascontiguousarray(scene.clump_omg if omg is None else omg, "<f4").reshape(n, 3).tobytes())
+    return path

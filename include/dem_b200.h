@@ -182,7 +182,11 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
 int dem_do_dynamics(DemCtx* ctx, double t);
 /* DoStepDynamics() x n (API.h:1252-1263). Blocking. */
 int dem_step(DemCtx* ctx, uint64_t n_steps);
-/* enqueue n steps on the stream without waiting (dem_sync() later); lets callers time with their own events */
+/* enqueue n steps on the stream without waiting (dem_sync() later); lets callers time with their own events.  Contact-
+ * list rebuilds are enqueued like steps: their verdict (counts, overflow, too-fast owners) is read one cycle later or at
+ * dem_sync, which is where DEM_ERR_VELOCITY / DEM_ERR_CAPACITY surface.  A rebuild that overflowed freezes the state on
+ * the device; the host grows the lists and replays from that rebuild on, so the result is the same as if nothing had
+ * happened (family tables uploaded in between are replayed with their latest values). */
 int dem_step_async(DemCtx* ctx, uint64_t n_steps);
 int dem_sync(DemCtx* ctx);
 /* force a contact-list rebuild now (kT contactDetection(), DEMCubContactDetection.cu:38-1123) */
@@ -221,18 +225,32 @@ int dem_reduce(DemCtx* ctx, int kind, double* out);
  * frame (DEMInspector::GetValue in a loop, e.g. DEMdemo_Mixer.cpp:130-140) should use. */
 int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]);
 
-/* ---- multi-GPU: slab decomposition with ghost-owner halo exchange over NCCL (no counterpart in the reference, whose
- * "multi-GPU" is the kT/dT thread pair of APIPublic.cpp:35-48).  One process and one context per GPU; every rank
- * uploads the SAME complete input, then calls dem_mgpu_init with the id rank 0 created.  From then on each rank
- * integrates the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step
- * (NVLink peer stores + flags when the GPUs can map each other's memory, ncclSend/ncclRecv otherwise).  Wall owners
- * (analytical boundaries) are replicated: exact while they are fixed or prescribed.  Scenes with triangle meshes are
- * refused (DEM_ERR_INVALID): their facets are not partitioned yet. */
+/* ---- multi-GPU: slab decomposition with ghost-owner halo exchange (no counterpart in the reference, whose
+ * "multi-GPU" is the kT/dT thread pair of APIPublic.cpp:35-48; extends the <= 2 GPUs of src/DEM/API.h:53,56 to the 8 of a
+ * box).  Every rank holds a context that was given the SAME complete input; from dem_mgpu_init* on each rank integrates
+ * the owners whose centre lies in its x-slab and exchanges the halo owners with its neighbours each step.  All exchanges
+ * -- per step and per rebuild -- are device-driven over peer-mapped memory (NVLink stores + system-scope flag words): no
+ * library call and no host synchronisation on the path; NCCL only carries the cudaIpc handles at set-up in the
+ * one-process-per-GPU form.  Wall and mesh owners are replicated (every rank registers the facets that can meet its
+ * slab): exact while they are fixed or follow a fully prescribed motion -- anything else is refused (DEM_ERR_INVALID).
+ *   dem_mgpu_init        one process per GPU (torchrun): every rank calls it with the id rank 0 created
+ *   dem_mgpu_init_local  all ranks are contexts of the calling process, one per GPU (what DEMSolver(nGPUs) uses); such
+ *                        contexts must be stepped together through dem_group_step_async / dem_group_sync, because
+ *                        their kernels wait for each other on the device */
 int dem_mgpu_unique_id(uint8_t out[128]);
 int dem_mgpu_init(DemCtx* ctx, int rank, int world, const uint8_t unique_id[128]);
-/* out: [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right [4] halo bytes sent per step
- * [5] world size in the low 32 bits; bit 32 set when the per-step exchange goes through peer memory (NVLink stores +
- * flags) instead of ncclSend/ncclRecv */
+int dem_mgpu_init_local(DemCtx** ctxs, int world);
+/* enqueue a device-side barrier over the ranks on the context's stream (no host wait) */
+int dem_mgpu_barrier(DemCtx* ctx);
+/* n steps on every context of a local group (enqueued cycle by cycle across the ranks); dem_group_sync blocks until all
+ * are done and replays on all ranks what a failed (overflowed) rebuild dropped */
+int dem_group_step_async(DemCtx** ctxs, int world, uint64_t n_steps);
+int dem_group_sync(DemCtx** ctxs, int world);
+/* after dem_group_sync: ctxs[0] receives the records of the clump owners the other ranks own, so that it holds the
+ * merged state of the whole system for trackers / writers / inspectors */
+int dem_group_gather(DemCtx** ctxs, int world);
+/* out (as of the last confirmed rebuild): [0] owners owned [1] owners active (own + ghost) [2] sent left [3] sent right
+ * [4] halo bytes sent per step [5] world size in the low 32 bits; bit 32 set when decomposed (peer-memory exchange) */
 int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]);
 /* the x-slab (LBF-relative) of `rank` out of `world` */
 int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, float* hi);

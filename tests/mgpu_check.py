@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Multi-GPU parity check (run under torchrun on a box with >= 2 GPUs; not collected by pytest):
+"""Multi-GPU parity check, one process per GPU (run under torchrun on a box with >= 2 GPUs; launched by
+tests/test_gpu_mgpu.py::test_torchrun_ranks_match_single_gpu when the box has the GPUs):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tests/mgpu_check.py
@@ -27,7 +28,8 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    sc = scenes.config2_clumps(28, 8, 6, cd_update_freq=10, spacing=2.7)
+    dims = [int(v) for v in os.environ.get("MGPU_CHECK_DIMS", "28,8,6").split(",")]
+    sc = scenes.config2_clumps(dims[0], dims[1], dims[2], cd_update_freq=10, spacing=2.7)
     n = len(sc.clump_type)
     rng = np.random.RandomState(7)
     # a shearing, colliding bed: owners cross the cuts in both directions
@@ -100,11 +102,13 @@ def main():
                 " ".join("r%d own %d act %d halo %dB" % (r, i["n_own"], i["n_active"], i["halo_bytes_per_step"]) for r, i in enumerate(infos))), flush=True)
             if cp == 2000:
                 ok = ok and crossed > 0 and all(i["halo_bytes_per_step"] > 0 for i in infos)
-                ok = ok and sum(i["n_own"] for i in infos) == f.nOwners + (world - 1) * (f.nOwners - n)
+                ok = ok and sum(i["n_own"] for i in infos) == n  # every clump has exactly one owner rank
+                for r, i in enumerate(infos):  # interior ranks push both ways
+                    ok = ok and (i["n_send_left"] > 0) == (r > 0) and (i["n_send_right"] > 0) == (r < world - 1)
     res = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(res, 0)
     if rank == 0:
-        print("exchange:", "NVLink peer stores + flags" if eng.mgpu_info()["peer_memory_exchange"] else "ncclSend/ncclRecv", flush=True)
+        print("exchange: NVLink peer stores + flags, device-driven (no NCCL, no host synchronisation on the path)", flush=True)
         print("MGPU_CHECK", "PASS" if ok else "FAIL", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if int(res.item()) == 1 else 1)
