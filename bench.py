@@ -142,9 +142,11 @@ def traffic_from_profiles():
         return None
 
 
-def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, budget_s=20.0):
-    """Times the reference's own kernel text (oracle/_ref, host-compiled) -- or the C port when _ref is absent -- on a
-    bounded sample of the workload. Returns (clump_updates_per_s, kind, cores, description, steps_run)."""
+def cpu_reference_run(n_clumps, steps, warmup, cd_update_freq, spacing, settle_steps, budget_s=20.0, settle_budget_s=60.0):
+    """Times the reference's own kernel text (oracle/_ref, host-compiled, OpenMP over all host cores) -- or the C port
+    when _ref is absent -- on the workload's bed of n_clumps clumps.  The CPU cannot settle a 1M-clump bed in minutes
+    (80 000 steps at ~0.1 s each), so settling is bounded by settle_budget_s of wall time and the description says how far
+    it got.  Returns (steps_per_s, kind, cores, description, steps_run, seconds, n_contacts)."""
     from oracle import pyoracle
     from pyapi import scenes
     sc, dims = build_scene(n_clumps, cd_update_freq, spacing)
@@ -156,21 +158,27 @@ def cpu_reference_run(n_clumps, steps, cd_update_freq, spacing, settle_steps, bu
         pyoracle.ref_set_threads(cores)
     else:
         cores = 1
-    w.step(settle_steps, cd_every=cd_update_freq, use_ref=use_ref)
+    chunk = max(1, cd_update_freq)
+    t0 = time.perf_counter()
+    settled = 0
+    while settled < settle_steps and time.perf_counter() - t0 < settle_budget_s:
+        w.step(chunk, cd_every=cd_update_freq, use_ref=use_ref)
+        settled += chunk
+    if warmup:
+        w.step(warmup, cd_every=cd_update_freq, use_ref=use_ref)
     t0 = time.perf_counter()
     done = 0
-    chunk = max(1, min(steps, cd_update_freq))
     while done < steps:
-        w.step(chunk, cd_every=cd_update_freq, use_ref=use_ref)
-        done += chunk
+        n = min(chunk, steps - done)
+        w.step(n, cd_every=cd_update_freq, use_ref=use_ref)
+        done += n
         if time.perf_counter() - t0 > budget_s:
             break
     dt = time.perf_counter() - t0
-    rate = done * f.nClumps / dt
-    return rate, ("reference" if use_ref else "port"), cores, (
-        "%d clumps (%dx%dx%d lattice of the same bed), %d steps after %d settling steps, the reference's own force / "
-        "accumulation / integration kernels on %d host threads (contact rebuild serial); value extrapolated linearly "
-        "in clump count to the 1M-clump workload" % (f.nClumps, dims[0], dims[1], dims[2], done, settle_steps, cores)), done, dt
+    return done / dt, ("reference" if use_ref else "port"), cores, (
+        "%d clumps (%dx%dx%d lattice, the workload's bed), %d timed steps after %d settling + %d warm-up steps on the host "
+        "(%d contacts listed at the end), the reference's own force / accumulation / integration kernels on %d host "
+        "threads (contact rebuild serial)" % (f.nClumps, dims[0], dims[1], dims[2], done, settled, warmup, int(w.nContacts), cores)), done, dt, int(w.nContacts)
 
 
 def run_c5(args, rank, local_rank, world):
@@ -228,7 +236,11 @@ def main():
                     help="untimed gravity-settling steps before warm-up (0.4 s of simulated time: the bed is at rest)")
     ap.add_argument("--cd-update-freq", type=int, default=20)
     ap.add_argument("--spacing", type=float, default=2.7, help="initial lattice spacing in units of the clump scale")
-    ap.add_argument("--cpu-clumps", type=int, default=8000, help="sample size of the CPU baseline")
+    ap.add_argument("--cpu-clumps", type=int, default=0,
+                    help="clumps of the CPU runs (--impl reference and the cpu_baseline leg); 0 = the workload's full size")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the leg that times the unmodified reference (baseline/_ref) on this box's GPU(s)")
+    ap.add_argument("--reference-gpu-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--clock-period", type=float, default=0.01, help="seconds between NVML clock samples")
@@ -250,15 +262,20 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, max(args.steps, 1), args.cd_update_freq,
-                                                             args.spacing, settle_steps=min(args.settle_steps, 4000),
-                                                             budget_s=60.0)
-        value = rate / float(args.clumps)
+        # the reference's CPU leg of the path on this box's host cores, on the workload's own bed (full size unless
+        # --cpu-clumps says otherwise); every step is one pass over all of it
+        n_cpu = args.cpu_clumps if args.cpu_clumps > 0 else args.clumps
+        value, kind, cores, desc, done, dt, n_cnt = cpu_reference_run(
+            n_cpu, max(args.steps, 1), min(args.warmup, 5), args.cd_update_freq, args.spacing,
+            settle_steps=args.settle_steps, budget_s=90.0, settle_budget_s=60.0)
+        value *= n_cpu / float(args.clumps)  # (identity at full size)
         line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus,
-                "steps": done, "warmup": args.warmup, "ms_per_step": 1000.0 / value, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 geometry)", "data": "synthetic",
-                "config": {"workload": workload, "cd_update_freq": args.cd_update_freq},
-                "grain_updates_per_s": rate,
+                "steps": done, "warmup": min(args.warmup, 5), "ms_per_step": 1000.0 / value, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f32 (f64 centre distance)", "data": "synthetic",
+                "config": {"workload": workload, "lattice": list(lattice_dims(args.clumps)), "clumps_total": args.clumps,
+                           "cd_update_freq": args.cd_update_freq, "force_record": False,
+                           "cpu_sample_clumps": n_cpu, "contacts_listed": n_cnt},
+                "grain_updates_per_s": value * args.clumps,
                 "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": desc},
                 "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -305,6 +322,8 @@ def main():
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if args.profile_window:
             torch.cuda.profiler.start()
+        if world > 1:
+            eng.mgpu_barrier()  # device-side rank barrier on the stream: the timed region starts with all GPUs level
         ev0.record(stream)
         eng.step_async(args.steps)
         ev1.record(stream)
@@ -376,10 +395,33 @@ def main():
         "clocks": sampler.summary(t_timed0, t_timed1),
     }
     if not args.no_cpu_baseline and world == 1:
-        rate, kind, cores, desc, done, dt = cpu_reference_run(args.cpu_clumps, 400, args.cd_update_freq, args.spacing,
-                                                             settle_steps=4000, budget_s=20.0)
-        line["cpu_baseline"] = {"value": rate / float(args.clumps), "unit": unit, "cores": cores, "kind": kind,
+        # bounded: ~20 s of timed CPU work on the full-size bed (a few hundred ms per step on the host cores)
+        n_cpu = args.cpu_clumps if args.cpu_clumps > 0 else args.clumps
+        rate, kind, cores, desc, done, dt, n_cnt = cpu_reference_run(n_cpu, 40, 2, args.cd_update_freq, args.spacing,
+                                                                    settle_steps=args.settle_steps, budget_s=20.0,
+                                                                    settle_budget_s=25.0)
+        line["cpu_baseline"] = {"value": rate * n_cpu / float(args.clumps), "unit": unit, "cores": cores, "kind": kind,
                                 "sample": desc}
+    if not args.no_reference_gpu and world == 1:
+        # the UNMODIFIED reference (DEMSolver(1), and DEMSolver(2) when the box has a second GPU) on the same settled
+        # bed, through its own API: baseline/run_ref.cpp around DoDynamicsThenSync (src/DEM/APIPublic.cpp:2446-2479)
+        from tools import run_reference_gpu as rr
+        if rr.reference_available():
+            import tempfile
+            path = os.path.join(tempfile.gettempdir(), "dem_c2_settled_rank0.bin")
+            rr.dump_settled_scene(eng, sc, f, path)
+            eng.close()
+            ref = {}
+            for g in (1, 2):
+                if g > torch.cuda.device_count():
+                    ref["DEMSolver(%d)" % g] = {"unavailable": "box has %d GPU(s)" % torch.cuda.device_count()}
+                    continue
+                d = rr.run_reference(path, g, args.reference_gpu_steps, 100, timeout=600)
+                d.pop("stats_tail", None)
+                ref["DEMSolver(%d)" % g] = d
+            line["reference_gpu"] = ref
+        else:
+            line["reference_gpu"] = {"unavailable": "baseline/_ref/run_ref not built"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

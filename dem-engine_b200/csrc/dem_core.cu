@@ -75,8 +75,7 @@ struct MgState {
     uint32_t* d_active_list[2] = {nullptr, nullptr};
     uint32_t* d_counts = nullptr;  // [2 parities][8]
     uint32_t* d_send_gid[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
-    int32_t* d_send_slot[2] = {nullptr, nullptr};
-    uint32_t* d_act_sph = nullptr;
+    uint32_t* d_act_sph[2] = {nullptr, nullptr};
     uint2* d_owner_sph = nullptr;
     uint32_t last[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // counts of the last confirmed rebuild (RebuildStatus::mg)
 };
@@ -177,6 +176,7 @@ struct DemCtx {
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
     unsigned long long* d_scan_desc = nullptr;
+    uint32_t* d_cand = nullptr;               // candidates accepted by the sweep's count pass (16 words per sphere)
     uint32_t* d_idA[2] = {nullptr, nullptr};  // sphere A of every new sphere--sphere contact (fill pass -> history pass)
     // triangles
     float4* d_tri[3] = {nullptr, nullptr, nullptr};   // owner-frame nodes
@@ -223,10 +223,17 @@ struct DemCtx {
     int ctas_per_sm = 4;
     int fast_math = 1;  // sphere--sphere force kernel: MUFU reciprocal / rsqrt instead of IEEE division / sqrt
     int fast_encode = 1;
+    int force_opts = 2;  // bit 0: skip candidates that cannot touch yet; bit 1: fetch velocities only for pairs in touch
     int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     MgState mg;
+    // in-process GPU group (dem_ctx_create_group): this context is rank 0, peers are ranks 1..; every entry point called
+    // on it acts on the whole group
+    std::vector<DemCtx*> peers;
+    bool group_on = false;     // the scene is sharded over the group (otherwise the peers idle)
+    bool merged = true;        // this context holds the merged state of all ranks
+    double group_min_owners = 50000.0;  // shard only when every GPU gets at least this many clump owners
     float rclump = 0.f;
     int sa_grid = 148;
     int last_sorted_buf = 0;
@@ -243,6 +250,8 @@ float3 host_rotate(float3 v, float4 q) {
     r.z = (2.0f * (x * z - w * y)) * v.x + (2.0f * (y * z + w * x)) * v.y + (2.0f * (w * w + z * z) - 1.0f) * v.z;
     return r;
 }
+
+int mg_reset_ownership(DemCtx* ctx);
 
 int fail(DemCtx* c, int code, const char* fmt, ...) {
     char buf[1024];
@@ -326,8 +335,7 @@ MgDev make_mgdev(const DemCtx* c) {
         M.counts[p] = g.d_counts + 8 * p;
         for (int d = 0; d < 2; d++) M.send_gid[p][d] = g.d_send_gid[p][d];
     }
-    for (int d = 0; d < 2; d++) M.send_slot[d] = g.d_send_slot[d];
-    M.act_sph = g.d_act_sph;
+    M.act_sph[0] = g.d_act_sph[0]; M.act_sph[1] = g.d_act_sph[1];
     M.owner_sph = g.d_owner_sph;
     M.cut_lo = g.cut_lo; M.cut_hi = g.cut_hi;
     M.nClumpOwners = c->nClumpOwners;
@@ -350,6 +358,7 @@ DevParams make_params(const DemCtx* c) {
     P.maxDrift = s.cd_update_freq;
     P.state = c->d_state; P.spin = c->d_spin; P.wrench = c->d_wrench; P.acc_out = c->keep_acc ? c->d_acc : nullptr;
     P.fast_encode = (uint32_t)c->fast_encode;
+    P.force_opts = (uint32_t)c->force_opts;
     P.inv_voxelSize = 1.0 / s.voxelSize;
     P.sph = c->d_sph; P.comp = c->d_comp; P.massprop = c->d_massprop; P.matpair = c->d_matpair; P.anal = c->d_anal;
     P.familyMasks = c->d_masks; P.familyExtraMargin = c->d_extra; P.presc = c->d_presc;
@@ -364,16 +373,6 @@ DevParams make_params(const DemCtx* c) {
         P.active = g.d_flag;
         P.active_list = g.d_active_list[c->cur];
         P.nActivePtr = g.d_counts + 8 * c->cur + 3;
-        for (int d = 0; d < 2; d++) {
-            const int peer = g.rank + (d == 0 ? -1 : 1);
-            P.send_slot[d] = g.d_send_slot[d];
-            // my records for the neighbour in direction d arrive there as "from direction 1-d"
-            P.peer_rec[d] = (peer >= 0 && peer < g.world)
-                                ? reinterpret_cast<int4*>(g.peer_block[peer] + mg_off_rec(g.cap, 1 - d, 0))
-                                : nullptr;
-        }
-        P.rec_half_int4 = g.cap * 5u;
-        P.epoch = g.d_ctrs;
     }
     P.maxvel = c->d_maxvel + c->maxvel_slot;
     P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
@@ -400,7 +399,7 @@ CdParams make_cd(const DemCtx* c) {
     C.analw = c->d_analw;
     if (c->mg.on) {
         C.slab_on = 1; C.slab_lo = c->mg.cut_lo; C.slab_hi = c->mg.cut_hi;
-        C.act_sph = c->mg.d_act_sph;
+        C.act_sph = c->mg.d_act_sph[c->cur ^ 1];
         C.act_count = c->mg.d_counts + 8 * (c->cur ^ 1) + 4;
     }
     C.oldss = as_list(c->lists[0][c->cur]);
@@ -411,6 +410,7 @@ CdParams make_cd(const DemCtx* c) {
     C.triCellStart = c->d_triCellStart; C.triCellFill = c->d_triCellFill; C.triCellList = c->d_triCellList;
     C.tri_pair_cap = (uint32_t)c->tri_pair_cap;
     C.rs_hist = c->d_rs_hist; C.scan_tmp = c->d_scan_tmp; C.scan_desc = c->d_scan_desc;
+    C.cand = c->d_cand;
     C.idA_ss = c->d_idA[0]; C.idA_sn = c->d_idA[1];
     C.status = c->d_status;
     return C;
@@ -426,14 +426,14 @@ void free_device(DemCtx* c) {
     dfree(c->d_tri_info); dfree(c->d_triCellStart); dfree(c->d_triCellFill); dfree(c->d_triCellList);
     dfree(c->d_grid); dfree(c->d_sphF); dfree(c->d_keys[0]); dfree(c->d_keys[1]); dfree(c->d_vals[0]);
     dfree(c->d_vals[1]); dfree(c->d_cellStart); dfree(c->d_sortedSph); dfree(c->d_sortedAux); dfree(c->d_sortedMeta); dfree(c->d_analw);
-    dfree(c->d_rs_hist); dfree(c->d_scan_tmp); dfree(c->d_scan_desc); dfree(c->d_idA[0]); dfree(c->d_idA[1]);
+    dfree(c->d_rs_hist); dfree(c->d_scan_tmp); dfree(c->d_scan_desc); dfree(c->d_idA[0]); dfree(c->d_idA[1]); dfree(c->d_cand);
     c->device_bytes = 0;
 }
 
 void free_mg(DemCtx* c) {
     MgState& g = c->mg;
-    dfree(g.d_flag); dfree(g.d_active_list[0]); dfree(g.d_active_list[1]); dfree(g.d_act_sph); dfree(g.d_owner_sph);
-    dfree(g.d_send_slot[0]); dfree(g.d_send_slot[1]); dfree(g.d_counts); dfree(g.d_ctrs);
+    dfree(g.d_flag); dfree(g.d_active_list[0]); dfree(g.d_active_list[1]); dfree(g.d_act_sph[0]); dfree(g.d_act_sph[1]); dfree(g.d_owner_sph);
+    dfree(g.d_counts); dfree(g.d_ctrs);
     for (int p = 0; p < 2; p++)
         for (int d = 0; d < 2; d++) dfree(g.d_send_gid[p][d]);
     for (int r = 0; r < (int)MG_MAX_WORLD; r++) {
@@ -544,7 +544,9 @@ int launch_rebuild_kernels(DemCtx* ctx, cudaEvent_t* sev) {
     if (sev) cudaEventRecord(sev[0], s);
     launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 0, ctx->num_sms, s);
     launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 1, ctx->num_sms, s);
+    if (sev) cudaEventRecord(sev[8], s);
     if (ctx->mg.on) launches += launch_mg_redistribute(P, M, ctx->d_grid, par, ctx->num_sms, s);
+    if (sev) cudaEventRecord(sev[9], s);
     launches += launch_cd_prepare(P, C, Mp, ctx->need_maxvel, 2, ctx->num_sms, s);
     launches += launch_cd_triangles(P, C, 0, ctx->num_sms, s);  // triangle -> cell registration
     launches += launch_cd_triangles(P, C, 1, ctx->num_sms, s);  // per-sphere triangle candidates (+ history)
@@ -659,16 +661,16 @@ int enqueue_rebuild(DemCtx* ctx, float* stage_us = nullptr) {
     int rc = confirm_rebuild(ctx, &rolled);
     if (rc) return rc;
     if (rolled && !stage_us) return DEM_OK;
-    cudaEvent_t sev[8];
+    cudaEvent_t sev[10];
     if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
     ctx->launches += launch_rebuild_kernels(ctx, stage_us ? sev : nullptr);
     note_rebuild_enqueued(ctx);
     if (stage_us) {
         CK(cudaStreamSynchronize(ctx->stream));
         // [0] margins+keys+histogram+analytical list [1] sort [2] cell-table scan [3] gather [4] sweep
-        // [5] counts [6] unused [7] whole rebuild on the device
+        // [5] counts [6] redistribution over the ranks (inside [0]) [7] whole rebuild on the device
         for (int k = 0; k < 6; k++) cudaEventElapsedTime(&stage_us[k], sev[k], sev[k + 1]);
-        stage_us[6] = 0.f;
+        cudaEventElapsedTime(&stage_us[6], sev[8], sev[9]);  // multi-GPU: ownership + halo lists (part of [0])
         cudaEventElapsedTime(&stage_us[7], sev[0], sev[7]);
         for (int k = 0; k < 8; k++) stage_us[k] *= 1000.f;
         for (auto& e : sev) cudaEventDestroy(e);
@@ -858,9 +860,80 @@ int settle(DemCtx* ctx) {
     return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
 }
 
+// ---- in-process GPU group behind ONE context (dem_ctx_create_group) ------------------------------------------------
+std::vector<DemCtx*> group_ranks(DemCtx* ctx) {
+    std::vector<DemCtx*> v{ctx};
+    v.insert(v.end(), ctx->peers.begin(), ctx->peers.end());
+    return v;
+}
+int peer_fail(DemCtx* ctx, DemCtx* peer, int rc) {
+    ctx->err = "GPU " + std::to_string(peer->device) + ": " + peer->err;
+    return rc;
+}
+// make rank 0 hold the state of all owners (after stepping, each rank only holds its slab + halo)
+int ensure_merged(DemCtx* ctx) {
+    if (!ctx->group_on || ctx->merged) return DEM_OK;
+    std::vector<DemCtx*> v = group_ranks(ctx);
+    int rc = dem_group_sync(v.data(), (int)v.size());
+    if (rc) {
+        for (DemCtx* c : v)
+            if (c != ctx && !c->err.empty()) return peer_fail(ctx, c, rc);
+        return rc;
+    }
+    rc = dem_group_gather(v.data(), (int)v.size());
+    if (rc) return rc;
+    ctx->merged = true;
+    return DEM_OK;
+}
+// rank 0's owner arrays -> every rank, ownership re-derived from them (after the host changed owner state)
+int group_broadcast_state(DemCtx* ctx) {
+    if (!ctx->group_on) return DEM_OK;
+    for (DemCtx* pc : ctx->peers) {
+        CK(cudaMemcpyPeer(pc->d_state, pc->device, ctx->d_state, ctx->device, sizeof(OwnerState) * ctx->nOwners));
+        CK(cudaMemcpyPeer(pc->d_spin, pc->device, ctx->d_spin, ctx->device, sizeof(float4) * ctx->nOwners));
+    }
+    for (DemCtx* c : group_ranks(ctx)) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, DEM_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        const int rc = mg_reset_ownership(c);
+        if (rc) return c == ctx ? rc : peer_fail(ctx, c, rc);
+    }
+    CK(cudaSetDevice(ctx->device));
+    ctx->merged = true;
+    return DEM_OK;
+}
+void free_mg(DemCtx* c);
+// after dem_initialize of every rank: shard when the scene qualifies, otherwise the peers stay idle
+int group_try_enable(DemCtx* ctx) {
+    ctx->group_on = false;
+    ctx->merged = true;
+    if (ctx->peers.empty()) return DEM_OK;
+    const size_t n = ctx->peers.size() + 1;
+    if ((double)ctx->nClumpOwners < ctx->group_min_owners * (double)n) return DEM_OK;
+    std::vector<DemCtx*> v = group_ranks(ctx);
+    const int rc = dem_mgpu_init_local(v.data(), (int)v.size());
+    if (rc == DEM_ERR_INVALID) {
+        // (free-moving wall / mesh owners: the decomposition would not be exact -- stay on one GPU)
+        for (DemCtx* c : v) {
+            cudaSetDevice(c->device);
+            free_mg(c);
+            c->err.clear();
+        }
+        cudaSetDevice(ctx->device);
+        return DEM_OK;
+    }
+    if (rc) return rc;
+    ctx->group_on = true;
+    return DEM_OK;
+}
+#define FORWARD_TO_PEERS(call)                                 \
+    for (DemCtx* pc_ : ctx->peers) {                           \
+        DemCtx* peer = pc_;                                    \
+        const int rcp_ = (call);                               \
+        if (rcp_) return peer_fail(ctx, peer, rcp_);           \
+    }
+
 }  // namespace
 
-// ===============================================================================================================
 // ===============================================================================================================
 extern "C" {
 
@@ -969,8 +1042,38 @@ int dem_ctx_create(DemCtx** out, int device) {
     return DEM_OK;
 }
 
+int dem_device_count(void) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return ndev;
+}
+
+int dem_ctx_create_group(DemCtx** out, const int* devices, int n) {
+    if (!out || n < 1 || n > (int)MG_MAX_WORLD) return DEM_ERR_INVALID;
+    *out = nullptr;
+    DemCtx* first = nullptr;
+    for (int r = 0; r < n; r++) {
+        DemCtx* c = nullptr;
+        const int rc = dem_ctx_create(&c, devices ? devices[r] : r);
+        if (rc) {
+            if (first) dem_ctx_destroy(first);
+            return rc;
+        }
+        if (r == 0) first = c; else first->peers.push_back(c);
+    }
+    cudaSetDevice(first->device);
+    *out = first;
+    return DEM_OK;
+}
+
 int dem_ctx_destroy(DemCtx* ctx) {
     if (!ctx) return DEM_ERR_INVALID;
+    if (ctx->group_on) {  // nothing may be left waiting for a peer that is about to disappear
+        std::vector<DemCtx*> v = group_ranks(ctx);
+        dem_group_sync(v.data(), (int)v.size());
+    }
+    for (DemCtx* pc : ctx->peers) dem_ctx_destroy(pc);
+    ctx->peers.clear();
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->mg.comm) g_nccl.CommDestroy(ctx->mg.comm);
@@ -1007,6 +1110,7 @@ int dem_set_stream(DemCtx* ctx, void* cuda_stream) {
 
 int dem_set_params(DemCtx* ctx, const DemSimParams* p) {
     if (!ctx || !p) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_set_params(peer, p))
     if (p->cd_update_freq < 1) return fail(ctx, DEM_ERR_INVALID, "cd_update_freq must be >= 1");
     if (!(p->l > 0) || !(p->h > 0)) return fail(ctx, DEM_ERR_INVALID, "l and h must be positive");
     if (p->force_model > DEM_HERTZIAN_FRICTIONLESS || p->integrator > DEM_EXTENDED_TAYLOR)
@@ -1031,6 +1135,7 @@ int dem_set_params(DemCtx* ctx, const DemSimParams* p) {
 int dem_upload_templates(DemCtx* ctx, uint32_t nComp, const float* radii, const float* relX, const float* relY,
                          const float* relZ, uint32_t nMassProps, const float* mass, const float* moiX,
                          const float* moiY, const float* moiZ) {
+    if (ctx) { FORWARD_TO_PEERS(dem_upload_templates(peer, nComp, radii, relX, relY, relZ, nMassProps, mass, moiX, moiY, moiZ)) }
     if (!ctx || (nComp && (!radii || !relX || !relY || !relZ)) || (nMassProps && (!mass || !moiX || !moiY || !moiZ)))
         return DEM_ERR_INVALID;
     if (nComp > 65535) return fail(ctx, DEM_ERR_INVALID, "more than 65535 distinct clump components");
@@ -1049,6 +1154,7 @@ int dem_upload_templates(DemCtx* ctx, uint32_t nComp, const float* radii, const 
 
 int dem_upload_materials(DemCtx* ctx, uint32_t nMat, const float* E, const float* nu, const float* CoR,
                          const float* mu, const float* Crr) {
+    if (ctx) { FORWARD_TO_PEERS(dem_upload_materials(peer, nMat, E, nu, CoR, mu, Crr)) }
     if (!ctx || !nMat || !E || !nu || !CoR || !mu || !Crr) return DEM_ERR_INVALID;
     if (nMat > 255) return fail(ctx, DEM_ERR_INVALID, "more than 255 materials");
     ctx->nMat = nMat;
@@ -1080,6 +1186,8 @@ int dem_upload_analytical(DemCtx* ctx, uint32_t nAnal, const uint32_t* objOwner,
                           const float* rotZ, const float* size1, const float* size2, const float* size3,
                           const float* objMass) {
     if (!ctx) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_upload_analytical(peer, nAnal, objOwner, objType, objMaterial, objNormal, relPosX, relPosY, relPosZ, rotX,
+                                           rotY, rotZ, size1, size2, size3, objMass))
     if (nAnal > 255) return fail(ctx, DEM_ERR_INVALID, "more than 255 analytical components (objID_t is 8 bit)");
     ctx->h_anal.resize(nAnal);
     for (uint32_t i = 0; i < nAnal; i++) {
@@ -1100,6 +1208,7 @@ int dem_upload_analytical(DemCtx* ctx, uint32_t nAnal, const uint32_t* objOwner,
 
 int dem_upload_families(DemCtx* ctx, const uint8_t* masks, const float* extraMargin, const DemPrescription* presc) {
     if (!ctx) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_upload_families(peer, masks, extraMargin, presc))
     const std::vector<uint8_t> old_masks = ctx->h_masks;
     const std::vector<float> old_extra = ctx->h_extra;
     ctx->h_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
@@ -1129,6 +1238,10 @@ int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, co
                       const float* oriQy, const float* oriQz, const float* vX, const float* vY, const float* vZ,
                       const float* omgBarX, const float* omgBarY, const float* omgBarZ, const uint8_t* familyID,
                       const uint16_t* inertiaPropOffsets) {
+    if (ctx) {
+        FORWARD_TO_PEERS(dem_upload_owners(peer, nOwners, voxelID, locX, locY, locZ, oriQw, oriQx, oriQy, oriQz, vX, vY, vZ, omgBarX,
+                                           omgBarY, omgBarZ, familyID, inertiaPropOffsets))
+    }
     if (!ctx || (nOwners && (!voxelID || !locX || !locY || !locZ || !oriQw || !oriQx || !oriQy || !oriQz || !vX ||
                              !vY || !vZ || !omgBarX || !omgBarY || !omgBarZ || !familyID || !inertiaPropOffsets)))
         return DEM_ERR_INVALID;
@@ -1160,6 +1273,7 @@ int dem_upload_owners(DemCtx* ctx, uint32_t nOwners, const uint64_t* voxelID, co
 
 int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClumpBody,
                        const uint16_t* clumpComponentOffset, const uint16_t* sphereMaterialOffset) {
+    if (ctx) { FORWARD_TO_PEERS(dem_upload_spheres(peer, nSpheres, ownerClumpBody, clumpComponentOffset, sphereMaterialOffset)) }
     if (!ctx || (nSpheres && (!ownerClumpBody || !clumpComponentOffset || !sphereMaterialOffset))) return DEM_ERR_INVALID;
     ctx->h_sph.resize(nSpheres);
     uint32_t maxOwner = 0;
@@ -1181,6 +1295,7 @@ int dem_upload_spheres(DemCtx* ctx, uint32_t nSpheres, const uint32_t* ownerClum
 int dem_upload_triangles(DemCtx* ctx, uint32_t nTri, const uint32_t* ownerMesh, const float* node1, const float* node2,
                          const float* node3, const uint16_t* triMaterialOffset) {
     // the flattened m_mesh_facet_owner / m_mesh_facets / material arrays of dT::populateEntityArrays (dT.cpp:960-1010)
+    if (ctx) { FORWARD_TO_PEERS(dem_upload_triangles(peer, nTri, ownerMesh, node1, node2, node3, triMaterialOffset)) }
     if (!ctx || (nTri && (!ownerMesh || !node1 || !node2 || !node3 || !triMaterialOffset))) return DEM_ERR_INVALID;
     ctx->h_tri1.resize(nTri); ctx->h_tri2.resize(nTri); ctx->h_tri3.resize(nTri); ctx->h_tri_info.resize(nTri);
     for (uint32_t t = 0; t < nTri; t++) {
@@ -1201,6 +1316,7 @@ int dem_update_triangle_nodes(DemCtx* ctx, uint32_t first, uint32_t n, const flo
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if (n == 0) return DEM_OK;
     if (!node1 || !node2 || !node3) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_update_triangle_nodes(peer, first, n, node1, node2, node3))
     if ((uint64_t)first + n > ctx->nTri) return fail(ctx, DEM_ERR_INVALID, "triangle range out of bounds");
     CK(cudaSetDevice(ctx->device));
     std::vector<float4>* dst[3] = {&ctx->h_tri1, &ctx->h_tri2, &ctx->h_tri3};
@@ -1216,8 +1332,19 @@ int dem_update_triangle_nodes(DemCtx* ctx, uint32_t first, uint32_t n, const flo
     return DEM_OK;
 }
 
-int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
+}  // extern "C"
+namespace {
+int initialize_one(DemCtx* ctx, uint64_t contact_capacity);
+}
+extern "C" int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     if (!ctx) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(initialize_one(peer, contact_capacity))
+    int rc = initialize_one(ctx, contact_capacity);
+    if (rc) return rc;
+    return group_try_enable(ctx);
+}
+namespace {
+int initialize_one(DemCtx* ctx, uint64_t contact_capacity) {
     if (!ctx->params_set) return fail(ctx, DEM_ERR_INVALID, "dem_set_params must precede dem_initialize");
     if (ctx->h_matpair.empty()) return fail(ctx, DEM_ERR_INVALID, "no materials uploaded");
     if (ctx->h_masks.empty()) {
@@ -1308,6 +1435,7 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
     if ((rc = dalloc(ctx, &ctx->d_scan_tmp, scan_n / 4096 + 2))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_scan_desc, scan_n / 4096 + 8))) return rc;
+    if ((rc = dalloc(ctx, &ctx->d_cand, (size_t)nS * 20 + 20))) return rc;  // SW_REC words per sphere (kernels_sweep.cu)
 
     if (ctx->nTri) {
         const uint32_t nT = ctx->nTri;
@@ -1340,11 +1468,18 @@ int dem_initialize(DemCtx* ctx, uint64_t contact_capacity) {
     for (auto& v : ctx->n_list) v = 0;
     return DEM_OK;
 }
+}  // namespace
+extern "C" {
 
 int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_t* idB, const uint8_t* type,
                      const float* wildcards4) {
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if (n && (!idA || !idB || !type)) return DEM_ERR_INVALID;
+    if (ctx->group_on) {  // every rank takes the whole list: a rank only ever looks up the spheres it holds
+        int rcm = ensure_merged(ctx);
+        if (rcm) return rcm;
+        FORWARD_TO_PEERS(dem_set_contacts(peer, n, idA, idB, type, wildcards4))
+    }
     CK(cudaSetDevice(ctx->device));
     { int rcs = settle(ctx); if (rcs) return rcs; }
     if (n > ctx->capacity) {
@@ -1400,29 +1535,69 @@ int dem_set_contacts(DemCtx* ctx, uint64_t n, const uint32_t* idA, const uint32_
     return DEM_OK;
 }
 
-int dem_rebuild_contacts(DemCtx* ctx) {
-    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+}  // extern "C"
+namespace {
+int rebuild_one(DemCtx* ctx) {
     CK(cudaSetDevice(ctx->device));
     int rc = settle(ctx);
     if (rc) return rc;
     return rebuild_blocking(ctx);
 }
-
-int dem_step_async(DemCtx* ctx, uint64_t n_steps) {
-    if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
+int step_async_one(DemCtx* ctx, uint64_t n_steps) {
     CK(cudaSetDevice(ctx->device));
     ctx->steps_target = ctx->n_steps + n_steps;
     return pump(ctx);
 }
-
-int dem_sync(DemCtx* ctx) {
-    if (!ctx) return DEM_ERR_INVALID;
+int sync_one(DemCtx* ctx) {
     CK(cudaSetDevice(ctx->device));
     if (!ctx->initialized) {
         CK(cudaStreamSynchronize(ctx->stream));
         return DEM_OK;
     }
     return settle(ctx);
+}
+int group_rc(DemCtx* ctx, const std::vector<DemCtx*>& v, int rc) {
+    if (rc)
+        for (DemCtx* c : v)
+            if (c != ctx && !c->err.empty()) return peer_fail(ctx, c, rc);
+    return rc;
+}
+}  // namespace
+extern "C" {
+
+int dem_rebuild_contacts(DemCtx* ctx) {
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if (ctx->group_on) {
+        std::vector<DemCtx*> v = group_ranks(ctx);
+        std::vector<int> rcs(v.size(), DEM_OK);
+        std::vector<std::thread> th;
+        for (size_t r = 0; r < v.size(); r++) th.emplace_back([&, r]() { rcs[r] = rebuild_one(v[r]); });
+        for (auto& t : th) t.join();
+        ctx->merged = false;
+        for (size_t r = 0; r < v.size(); r++)
+            if (rcs[r]) return r == 0 ? rcs[r] : peer_fail(ctx, v[r], rcs[r]);
+        return DEM_OK;
+    }
+    return rebuild_one(ctx);
+}
+
+int dem_step_async(DemCtx* ctx, uint64_t n_steps) {
+    if (!ctx || !ctx->initialized) return fail(ctx, DEM_ERR_INVALID, "dem_initialize has not been called");
+    if (ctx->group_on) {
+        std::vector<DemCtx*> v = group_ranks(ctx);
+        ctx->merged = false;
+        return group_rc(ctx, v, dem_group_step_async(v.data(), (int)v.size(), n_steps));
+    }
+    return step_async_one(ctx, n_steps);
+}
+
+int dem_sync(DemCtx* ctx) {
+    if (!ctx) return DEM_ERR_INVALID;
+    if (ctx->group_on) {
+        std::vector<DemCtx*> v = group_ranks(ctx);
+        return group_rc(ctx, v, dem_group_sync(v.data(), (int)v.size()));
+    }
+    return sync_one(ctx);
 }
 
 int dem_step(DemCtx* ctx, uint64_t n_steps) {
@@ -1446,12 +1621,14 @@ int dem_do_dynamics(DemCtx* ctx, double t) {
 
 int dem_set_sim_time(DemCtx* ctx, double t) {
     if (!ctx) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_set_sim_time(peer, t))
     ctx->sim_time = t;  // host-side clock only (the kernels never see it): SetSimTime, dT.cpp:2709-2713
     return DEM_OK;
 }
 
 int dem_update_step_size(DemCtx* ctx, float h) {
     if (!ctx || !(h > 0)) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_update_step_size(peer, h))
     ctx->sp.h = h;
     ctx->need_rebuild = true;  // margins depend on h
     return DEM_OK;
@@ -1463,6 +1640,7 @@ int dem_download_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, uint64_t* 
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
@@ -1499,6 +1677,7 @@ int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz32
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
@@ -1524,6 +1703,7 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
     if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
     CK(cudaSetDevice(ctx->device));
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     { int rcs = settle(ctx); if (rcs) return rcs; }
     std::vector<OwnerState> st(n);
     std::vector<float4> sp(n);
@@ -1548,7 +1728,7 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     CK(cudaMemcpy(ctx->d_spin + first, sp.data(), sizeof(float4) * n, cudaMemcpyHostToDevice));
     ctx->need_rebuild = true;
     ctx->need_maxvel = true;
-    return DEM_OK;
+    return group_broadcast_state(ctx);  // (no-op on a single GPU)
 }
 
 int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB, uint8_t* type,
@@ -1556,18 +1736,13 @@ int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint3
     return dem_download_contact_records(ctx, capacity, n_out, idA, idB, type, wildcards4, force_xyz, nullptr);
 }
 
-int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB,
-                                 uint8_t* type, float* wildcards4, float* force_xyz, float* point_xyz) {
-    if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
+}  // extern "C"
+namespace {
+struct ContactRow { uint32_t a, b; uint8_t t; float4 h; float4 f; float4 p; };
+// the rows of one context's current lists, normalised to the reference's conventions (smaller sphere id = geometry A)
+int collect_contact_rows(DemCtx* ctx, bool want_points, std::vector<ContactRow>& rows) {
     CK(cudaSetDevice(ctx->device));
     { int rcs = settle(ctx); if (rcs) return rcs; }
-    const uint64_t n = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2] + ctx->n_list[3];
-    *n_out = n;
-    if (!idA && !idB && !type && !wildcards4 && !force_xyz && !point_xyz) return DEM_OK;
-    if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
-    struct Row { uint32_t a, b; uint8_t t; float4 h; float4 f; float4 p; };
-    std::vector<Row> rows;
-    rows.reserve(n);
     for (int kind = 0; kind < 4; kind++) {
         const ListBuf& L = ctx->lists[kind][ctx->cur];
         const uint64_t m = ctx->n_list[kind];
@@ -1586,11 +1761,12 @@ int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out
         std::vector<float4> hist(m, make_float4(0, 0, 0, 0)), frc(m, make_float4(0, 0, 0, 0)), cpt(m, make_float4(0, 0, 0, 0));
         if (L.hist) CK(cudaMemcpy(hist.data(), L.hist, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         if (L.force) CK(cudaMemcpy(frc.data(), L.force, sizeof(float4) * m, cudaMemcpyDeviceToHost));
-        if (L.cpoint && point_xyz) CK(cudaMemcpy(cpt.data(), L.cpoint, sizeof(float4) * m, cudaMemcpyDeviceToHost));
+        if (L.cpoint && want_points) CK(cudaMemcpy(cpt.data(), L.cpoint, sizeof(float4) * m, cudaMemcpyDeviceToHost));
         std::vector<uint4> ci(m);
         CK(cudaMemcpy(ci.data(), L.cinfo, sizeof(uint4) * m, cudaMemcpyDeviceToHost));
         for (uint64_t i = 0; i < m; i++) {
-            Row r;
+            if (pair[i].x == 0xffffffffu) continue;  // (a slot no segment points at: decomposed lists of another cycle)
+            ContactRow r;
             r.a = pair[i].x; r.b = pair[i].y;
             bool flip = false;
             if (which == 0 && r.a > r.b) { std::swap(r.a, r.b); flip = true; }
@@ -1610,11 +1786,49 @@ int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out
             rows.push_back(r);
         }
     }
-    std::sort(rows.begin(), rows.end(), [](const Row& x, const Row& y) {
+    return DEM_OK;
+}
+}  // namespace
+extern "C" {
+
+int dem_download_contact_records(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB,
+                                 uint8_t* type, float* wildcards4, float* force_xyz, float* point_xyz) {
+    if (!ctx || !ctx->initialized || !n_out) return DEM_ERR_INVALID;
+    std::vector<ContactRow> rows;
+    if (!ctx->group_on && !idA && !idB && !type && !wildcards4 && !force_xyz && !point_xyz) {  // only the count is asked for
+        CK(cudaSetDevice(ctx->device));
+        { int rcs = settle(ctx); if (rcs) return rcs; }
+        *n_out = ctx->n_list[0] + ctx->n_list[1] + ctx->n_list[2] + ctx->n_list[3];
+        return DEM_OK;
+    }
+    if (ctx->group_on) {
+        // every rank lists the contacts of the spheres it holds; pairs across a cut appear on both sides, with
+        // identical history and force (same inputs, same arithmetic): keep one
+        std::vector<DemCtx*> v = group_ranks(ctx);
+        int rc = group_rc(ctx, v, dem_group_sync(v.data(), (int)v.size()));
+        if (rc) return rc;
+        for (DemCtx* c : v) {
+            rc = collect_contact_rows(c, point_xyz != nullptr, rows);
+            if (rc) return c == ctx ? rc : peer_fail(ctx, c, rc);
+        }
+        CK(cudaSetDevice(ctx->device));
+    } else {
+        int rc = collect_contact_rows(ctx, point_xyz != nullptr, rows);
+        if (rc) return rc;
+    }
+    std::sort(rows.begin(), rows.end(), [](const ContactRow& x, const ContactRow& y) {
         if (x.t != y.t) return x.t < y.t;
         if (x.a != y.a) return x.a < y.a;
         return x.b < y.b;
     });
+    if (ctx->group_on)
+        rows.erase(std::unique(rows.begin(), rows.end(), [](const ContactRow& x, const ContactRow& y) {
+                       return x.t == y.t && x.a == y.a && x.b == y.b;
+                   }), rows.end());
+    const uint64_t n = rows.size();
+    *n_out = n;
+    if (!idA && !idB && !type && !wildcards4 && !force_xyz && !point_xyz) return DEM_OK;
+    if (capacity < n) return fail(ctx, DEM_ERR_CAPACITY, "dem_download_contacts: need room for %llu contacts", (unsigned long long)n);
     for (uint64_t i = 0; i < n; i++) {
         if (idA) idA[i] = rows[i].a;
         if (idB) idB[i] = rows[i].b;
@@ -1640,17 +1854,25 @@ int dem_get_stats(DemCtx* ctx, DemStats* out) {
     out->sim_time = ctx->sim_time; out->max_margin = ctx->last_grid.max_margin; out->cell_size = ctx->last_grid.cs;
     out->n_cells[0] = ctx->last_grid.nbx; out->n_cells[1] = ctx->last_grid.nby; out->n_cells[2] = ctx->last_grid.nbz;
     out->overflow = ctx->overflow_seen;
+    if (ctx->group_on)  // (contacts across a cut are listed on both sides: the sums count them twice)
+        for (DemCtx* pc : ctx->peers) {
+            out->n_contacts_ss += pc->n_list[0] + pc->n_list[1]; out->n_contacts_sa += pc->n_list[2]; out->n_contacts_st += pc->n_list[3];
+            out->n_contacts_ss_touching += pc->n_list[0];
+            out->kernel_launches += pc->launches; out->device_bytes += pc->device_bytes; out->overflow += pc->overflow_seen;
+        }
     return DEM_OK;
 }
 
 int dem_reduce(DemCtx* ctx, int kind, double* out) {
     if (!ctx || !ctx->initialized || !out) return DEM_ERR_INVALID;
     if (kind < DEM_REDUCE_MAX_ABSV || kind > DEM_REDUCE_TOTAL_MASS) return fail(ctx, DEM_ERR_INVALID, "unknown reduction");
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     CK(cudaSetDevice(ctx->device));
     const double init = (kind == DEM_REDUCE_MIN_Z) ? 1e300 : ((kind == DEM_REDUCE_MAX_Z) ? -1e300 : 0.0);
     CK(cudaMemcpyAsync(ctx->d_reduce, &init, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     DevParams P = make_params(ctx);
     P.nOwners = ctx->nClumpOwners;  // inspectors of the reference look at clumps only
+    if (ctx->group_on) P.active = nullptr;  // rank 0 holds the merged state of all ranks
     ctx->launches += launch_reduce(P, kind, ctx->d_reduce, ctx->stream);
     CK(cudaMemcpyAsync(out, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1660,6 +1882,7 @@ int dem_reduce(DemCtx* ctx, int kind, double* out) {
 int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]) {
     if (!ctx || !ctx->initialized || !out) return DEM_ERR_INVALID;
     if (kind_mask == 0 || kind_mask >= (1u << 5)) return fail(ctx, DEM_ERR_INVALID, "unknown reduction in mask");
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     CK(cudaSetDevice(ctx->device));
     double* hp = reinterpret_cast<double*>(ctx->h_pinned + 112);  // pinned scratch: words 112..131
     const double init[5] = {0.0, -1e300, 1e300, 0.0, 0.0};
@@ -1667,6 +1890,7 @@ int dem_reduce_many(DemCtx* ctx, uint32_t kind_mask, double out[5]) {
     CK(cudaMemcpyAsync(ctx->d_reduce_many, hp, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
     DevParams P = make_params(ctx);
     P.nOwners = ctx->nClumpOwners;
+    if (ctx->group_on) P.active = nullptr;
     ctx->launches += launch_reduce_many(P, kind_mask, ctx->d_reduce_many, ctx->stream);
     CK(cudaMemcpyAsync(hp + 5, ctx->d_reduce_many, sizeof(init), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -1724,6 +1948,44 @@ int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float 
 
 namespace {
 
+// (Re-)derive who owns what from the positions this rank's device arrays hold: own inside my slab, unknown elsewhere (the
+// next rebuild brings the ghosts in); replicated analytical / mesh owners are owned everywhere.  The "previous cycle's
+// active list" that rebuild walks is the list of these own owners; halo send lists start empty.  The per-parity sphere
+// lists (act_sph, counts[.][4]) are left alone: they describe what the contact-list buffers of that parity hold.
+int mg_reset_ownership(DemCtx* ctx) {
+    MgState& g = ctx->mg;
+    const uint32_t nO = ctx->nOwners;
+    std::vector<uint8_t> flag(nO, 0);
+    std::vector<uint32_t> act;
+    const DemSimParams& p = ctx->sp;
+    // (what the device holds now, not what was uploaded: the context may have stepped before)
+    std::vector<OwnerState> st(nO);
+    CK(cudaMemcpy(st.data(), ctx->d_state, sizeof(OwnerState) * nO, cudaMemcpyDeviceToHost));
+    for (uint32_t o = 0; o < nO; o++) {
+        bool own = true;
+        if (o < ctx->nClumpOwners) {
+            const OwnerPos& s = st[o].pos;
+            const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
+            const float x = (float)((double)vx * p.voxelSize + (double)s.lx * p.l);
+            own = (x >= g.cut_lo && x < g.cut_hi);
+        }
+        flag[o] = own ? 1 : 0;
+        if (own) act.push_back(o);
+    }
+    CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
+    const int prev = ctx->cur;  // the next rebuild builds parity cur^1 and walks the list of parity cur
+    CK(cudaMemcpy(g.d_active_list[prev], act.data(), sizeof(uint32_t) * act.size(), cudaMemcpyHostToDevice));
+    uint32_t cnt[2][8];
+    CK(cudaMemcpy(cnt, g.d_counts, sizeof(cnt), cudaMemcpyDeviceToHost));
+    for (int q = 0; q < 2; q++)
+        for (int k = 0; k < 4; k++) cnt[q][k] = 0;
+    cnt[prev][3] = (uint32_t)act.size();
+    CK(cudaMemcpy(g.d_counts, cnt, sizeof(cnt), cudaMemcpyHostToDevice));
+    ctx->need_rebuild = true;
+    ctx->need_maxvel = true;
+    return DEM_OK;
+}
+
 // Everything of the decomposition that does not depend on how the peers' blocks get mapped: slab, buffers, the initial
 // ownership.  Leaves g.my_block allocated and zeroed; the caller fills g.peer_block[] and switches g.on.
 int mg_prepare(DemCtx* ctx, int rank, int world) {
@@ -1754,11 +2016,8 @@ int mg_prepare(DemCtx* ctx, int rank, int world) {
         for (int d = 0; d < 2; d++)
             if ((rc = dalloc(ctx, &g.d_send_gid[p][d], g.cap))) return rc;
     }
-    if ((rc = dalloc(ctx, &g.d_act_sph, std::max<uint32_t>(nS, 1u)))) return rc;
-    for (int d = 0; d < 2; d++) {
-        if ((rc = dalloc(ctx, &g.d_send_slot[d], std::max<uint32_t>(nO, 1u)))) return rc;
-        CK(cudaMemset(g.d_send_slot[d], 0xff, sizeof(int32_t) * std::max<uint32_t>(nO, 1u)));
-    }
+    for (int p = 0; p < 2; p++)
+        if ((rc = dalloc(ctx, &g.d_act_sph[p], std::max<uint32_t>(nS, 1u)))) return rc;
     if ((rc = dalloc(ctx, &g.d_counts, 16))) return rc;
     if ((rc = dalloc(ctx, &g.d_ctrs, 4))) return rc;
     CK(cudaMemset(g.d_counts, 0, sizeof(uint32_t) * 16));
@@ -1779,33 +2038,7 @@ int mg_prepare(DemCtx* ctx, int rank, int world) {
             CK(cudaMemcpy(g.d_owner_sph, os.data(), sizeof(uint2) * nO, cudaMemcpyHostToDevice));
         }
     }
-    // initial ownership from the uploaded positions: own inside my slab, unknown elsewhere (the first rebuild brings
-    // the ghosts in); replicated analytical / mesh owners are owned everywhere.  The "previous cycle's active list" the
-    // first rebuild walks is the list of these own owners.
-    {
-        std::vector<uint8_t> flag(nO, 0);
-        std::vector<uint32_t> act;
-        const DemSimParams& p = ctx->sp;
-        // (what the device holds now, not what was uploaded: the context may have stepped on one GPU before)
-        std::vector<OwnerState> st(nO);
-        CK(cudaMemcpy(st.data(), ctx->d_state, sizeof(OwnerState) * nO, cudaMemcpyDeviceToHost));
-        for (uint32_t o = 0; o < nO; o++) {
-            bool own = true;
-            if (o < ctx->nClumpOwners) {
-                const OwnerPos& s = st[o].pos;
-                const uint64_t vx = s.voxel & ((1ull << p.nvXp2) - 1ull);
-                const float x = (float)((double)vx * p.voxelSize + (double)s.lx * p.l);
-                own = (x >= g.cut_lo && x < g.cut_hi);
-            }
-            flag[o] = own ? 1 : 0;
-            if (own) act.push_back(o);
-        }
-        CK(cudaMemcpy(g.d_flag, flag.data(), nO, cudaMemcpyHostToDevice));
-        const int prev = ctx->cur;  // the first rebuild builds parity cur^1 and walks the list of parity cur
-        CK(cudaMemcpy(g.d_active_list[prev], act.data(), sizeof(uint32_t) * act.size(), cudaMemcpyHostToDevice));
-        uint32_t cnt[8] = {0, 0, 0, (uint32_t)act.size(), 0, 0, 0, 0};
-        CK(cudaMemcpy(g.d_counts + 8 * prev, cnt, sizeof(cnt), cudaMemcpyHostToDevice));
-    }
+    if ((rc = mg_reset_ownership(ctx))) return rc;
     const size_t block_bytes = mg_block_bytes(g.cap);
     CK(cudaMalloc((void**)&g.my_block, block_bytes));
     CK(cudaMemset(g.my_block, 0, block_bytes));
@@ -1898,56 +2131,35 @@ int dem_mgpu_init_local(DemCtx** ctxs, int world) {
     return DEM_OK;
 }
 
-/* n steps on every context of a local group, cycle by cycle across the ranks so that no rank's host-side wait can come
- * before the work its peers' kernels are waiting for has been enqueued.  dem_group_sync blocks until all are done. */
+/* n steps on every context of a local group.  One host thread per rank for the duration of the call: the ranks' kernels
+ * wait for each other on the device, so no rank's host-side wait (a rebuild confirmation, a first-use module load, an
+ * allocation while growing a list) may keep another rank's work from being enqueued. */
 int dem_group_step_async(DemCtx** ctxs, int world, uint64_t n_steps) {
     if (!ctxs || world < 1) return DEM_ERR_INVALID;
-    for (int r = 0; r < world; r++) {
+    for (int r = 0; r < world; r++)
         if (!ctxs[r] || !ctxs[r]->initialized) return DEM_ERR_INVALID;
-        ctxs[r]->steps_target = ctxs[r]->n_steps + n_steps;
-    }
-    for (;;) {
-        bool busy = false;
-        for (int r = 0; r < world; r++) {
-            DemCtx* ctx = ctxs[r];
-            if (ctx->n_steps >= ctx->steps_target) continue;
-            busy = true;
-            CK(cudaSetDevice(ctx->device));
-            // one cycle's worth: up to the next rebuild boundary
-            const uint64_t target = ctx->steps_target;
-            const uint64_t L = ctx->sp.cd_update_freq;
-            const uint64_t room = (ctx->need_rebuild || ctx->steps_since_rebuild >= L) ? L : L - ctx->steps_since_rebuild;
-            ctx->steps_target = std::min<uint64_t>(target, ctx->n_steps + room);
-            const int rc = pump(ctx);
-            ctx->steps_target = target;
-            if (rc) return rc;
-        }
-        if (!busy) break;
-    }
+    std::vector<int> rcs(world, DEM_OK);
+    std::vector<std::thread> th;
+    for (int r = 0; r < world; r++)
+        th.emplace_back([&, r]() { rcs[r] = step_async_one(ctxs[r], n_steps); });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < world; r++)
+        if (rcs[r]) return rcs[r];
     return DEM_OK;
 }
 
 int dem_group_sync(DemCtx** ctxs, int world) {
     if (!ctxs || world < 1) return DEM_ERR_INVALID;
-    for (int attempt = 0; attempt < 16; attempt++) {
-        bool again = false;
-        for (int r = 0; r < world; r++) {
-            DemCtx* ctx = ctxs[r];
-            CK(cudaSetDevice(ctx->device));
-            CK(cudaStreamSynchronize(ctx->stream));
-            bool rolled = false;
-            const int rc = confirm_rebuild(ctx, &rolled);
-            if (rc) return rc;
-            again = again || rolled || ctx->n_steps < ctx->steps_target;
-        }
-        if (!again) return DEM_OK;
-        // a rebuild overflowed (on every rank alike: the verdict is agreed on the device): replay together
-        uint64_t left = 0;
-        for (int r = 0; r < world; r++) left = std::max<uint64_t>(left, ctxs[r]->steps_target - ctxs[r]->n_steps);
-        const int rc = dem_group_step_async(ctxs, world, left);
-        if (rc) return rc;
-    }
-    return DEM_ERR_CAPACITY;
+    std::vector<int> rcs(world, DEM_OK);
+    std::vector<std::thread> th;
+    // (a rebuild that overflowed did so on every rank alike -- the verdict is agreed on the device -- so every rank
+    // rolls back and replays on its own, and they meet again in the device-side exchanges)
+    for (int r = 0; r < world; r++)
+        th.emplace_back([&, r]() { rcs[r] = sync_one(ctxs[r]); });
+    for (auto& t : th) t.join();
+    for (int r = 0; r < world; r++)
+        if (rcs[r]) return rcs[r];
+    return DEM_OK;
 }
 
 /* After dem_group_sync: copy into ctxs[0] the records of the clump owners the other ranks own, so that ctxs[0] holds the
@@ -1985,12 +2197,15 @@ int dem_mgpu_info(DemCtx* ctx, uint64_t out[6]) {
 
 int dem_set_option(DemCtx* ctx, const char* name, double value) {
     if (!ctx || !name) return DEM_ERR_INVALID;
+    FORWARD_TO_PEERS(dem_set_option(peer, name, value))
     const std::string n(name);
+    if (n == "group_min_owners") { ctx->group_min_owners = value; return DEM_OK; }
     if (n == "ctas_per_sm") ctx->ctas_per_sm = std::max(2, std::min(4, (int)value));
     else if (n == "fast_math") ctx->fast_math = value != 0.0;
     else if (n == "use_graph") { ctx->use_graph = (int)value; if (ctx->use_graph == 0) graph_drop(ctx); }
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
+    else if (n == "force_opts") ctx->force_opts = (int)value;
     else if (n == "sort_mode") ctx->sort_mode = (int)value;
     else if (n == "overlap_walls") ctx->overlap_walls = value != 0.0;
     else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);
@@ -1999,6 +2214,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
 
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
+    if (ctx->group_on) return fail(ctx, DEM_ERR_INVALID, "profiling hooks act on one device: create the context with dem_ctx_create");
     CK(cudaSetDevice(ctx->device));
     int rc = settle(ctx);
     if (rc) return rc;
@@ -2007,6 +2223,7 @@ int dem_profile_rebuild(DemCtx* ctx, float out_us[8]) {
 
 int dem_profile_binning(DemCtx* ctx, uint32_t repeats, float out_us[3]) {
     if (!ctx || !ctx->initialized || !out_us || repeats == 0) return DEM_ERR_INVALID;
+    if (ctx->group_on) return fail(ctx, DEM_ERR_INVALID, "profiling hooks act on one device: create the context with dem_ctx_create");
     if (ctx->mg.on) return fail(ctx, DEM_ERR_INVALID, "dem_profile_binning: single-device contexts only (shard the spheres, one context per GPU)");
     CK(cudaSetDevice(ctx->device));
     { int rcs = settle(ctx); if (rcs) return rcs; }
@@ -2067,6 +2284,7 @@ int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uin
 
 int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
     if (!ctx || !ctx->initialized || !out_us) return DEM_ERR_INVALID;
+    if (ctx->group_on) return fail(ctx, DEM_ERR_INVALID, "profiling hooks act on one device: create the context with dem_ctx_create");
     CK(cudaSetDevice(ctx->device));
     { int rcs = settle(ctx); if (rcs) return rcs; }
     double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -102,9 +102,13 @@ enum {
     DEM_FLAG_POISON = 4,    // != 0: a rebuild failed; every kernel of every later step / rebuild is a no-op until the
                             // host has grown the lists and cleared it (value = sequence number of the failed rebuild)
     DEM_FLAG_SEQ = 5,       // rebuilds finished so far (device-side counter: graph replays carry no host arguments)
+    DEM_FLAG_CYCLE_STEP = 6,  // integrations since the last rebuild (zeroed by the rebuild, advanced by the integrator)
     DEM_NUM_FLAGS = 8
 };
 constexpr uint32_t CINFO_NO_HISTORY = 0x40000000u;  // sweep -> k_history: this contact carries no history over
+// cinfo.w of a sphere--sphere candidate: bits 0-15 material pair, bits 16-23 the first step of the cycle at which the
+// two spheres can possibly touch (see pair_first_step, kernels_sweep.cu), bit 30 CINFO_NO_HISTORY, bit 31 alive
+constexpr uint32_t CINFO_FIRST_SHIFT = 16;
 
 // Multi-GPU (slab decomposition) state as the kernels see it.  Everything that changes from step to step or rebuild
 // to rebuild lives in DEVICE memory (epoch counters, counts, lists), so that the same parameter block -- hence the same
@@ -130,8 +134,7 @@ struct MgDev {
     uint32_t* active_list[2];         // [par] compact list of active owners (own + ghost) of the cycle with parity par
     uint32_t* counts[2];              // [par] {own, send-left, send-right, active, active spheres, -, -, -}
     uint32_t* send_gid[2][2];         // [par][dir] own owners inside the halo of the left / right cut
-    int32_t* send_slot[2];            // [dir] per owner: slot in that neighbour's receive buffer, or -1
-    uint32_t* act_sph;                // spheres of the active owners (the rebuild walks these only)
+    uint32_t* act_sph[2];             // [par] spheres of the active owners of that cycle (the rebuild walks these only)
     const uint2* owner_sph;           // per owner {first sphere, number of spheres} (nullptr: not contiguous)
     float cut_lo, cut_hi;             // my slab in LBF-relative x
     uint32_t nClumpOwners;            // owners >= this index are analytical / mesh owners, replicated on every rank
@@ -160,6 +163,7 @@ struct DevParams {
     float errOutVel;
     uint32_t maxDrift;
     uint32_t fast_encode;        // integrator: division-free position encode
+    uint32_t force_opts;         // sphere--sphere force kernel: bit 0 skip candidates that cannot touch yet, bit 1 lazy kinematics
     double inv_voxelSize;
     // owners
     OwnerState* state;
@@ -171,13 +175,6 @@ struct DevParams {
     const uint8_t* active;
     const uint32_t* active_list;
     const uint32_t* nActivePtr;
-    // ... and the per-step halo push fused into the integrator: per owner the slot of its {state, spin} record in the
-    // left / right neighbour's receive buffer (-1 = not in that halo; nullptr = no fused push), the neighbours' record
-    // areas for my direction (both epoch halves, in THEIR memory) and the exchange counter that selects the half
-    const int32_t* send_slot[2];
-    int4* peer_rec[2];
-    uint32_t rec_half_int4;             // int4 words per epoch half (cap * 5)
-    const unsigned long long* epoch;
     // spheres / templates
     const uint2* sph;
     const float4* comp;      // {relx, rely, relz, radius}

@@ -72,6 +72,7 @@ struct CdParams {
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the radix sort's scans
     unsigned long long* scan_desc;  // [0] tile counter, [1..] tile descriptors of the single-pass scan
+    uint32_t* cand;       // scratch: 16 words per sorted position, the candidates the count pass accepted (-> fill pass)
     uint32_t* idA_ss;     // scratch: sphere A of every contact of the new lists (sweep fill -> k_history)
     uint32_t* idA_sn;
     // domain decomposition (nullptr on a single GPU): the rebuild walks the spheres of the active owners only and
@@ -110,7 +111,8 @@ int launch_scan_exclusive(uint32_t* data, uint32_t n, uint32_t* tmp, uint32_t* t
 // single-pass (decoupled look-back) exclusive scan of n = (n_ptr ? *n_ptr + n_add : n_add) words, in -> out (may alias);
 // *total receives the sum.  desc: [0] tile counter + tile descriptors, cleared here.
 int launch_scan_lookback(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_add, uint32_t n_max,
-                         unsigned long long* desc, uint32_t* total, const uint32_t* flags, int num_sms, cudaStream_t s);
+                         unsigned long long* desc, uint32_t* total, const uint32_t* flags, int num_sms, cudaStream_t s,
+                         const uint32_t* idx = nullptr);
 int launch_zero_u32(uint32_t* p, size_t n, const uint32_t* flags, int num_sms, cudaStream_t s);
 int launch_reduce(const DevParams& P, int kind, double* d_out, cudaStream_t s);
 int launch_reduce_many(const DevParams& P, uint32_t mask, double* d_out, cudaStream_t s);

@@ -385,10 +385,13 @@ constexpr int LB_THREADS = 256;
 constexpr int LB_ITEMS = 16;
 constexpr int LB_TILE = LB_THREADS * LB_ITEMS;
 
+// idx != nullptr: element i of the scan is in[idx[i]] and its prefix goes to out[idx[i]] (the decomposed rebuild scans the
+// per-sphere counts in the order of its active-sphere list instead of walking all spheres of the system).
 __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in, uint32_t* out,
                                                               const uint32_t* __restrict__ n_ptr, uint32_t n_add,
                                                               unsigned long long* desc, uint32_t* total_out,
-                                                              const uint32_t* __restrict__ flags) {
+                                                              const uint32_t* __restrict__ flags,
+                                                              const uint32_t* __restrict__ idx) {
     if (flags[DEM_FLAG_POISON]) return;
     __shared__ uint32_t sm[33];
     __shared__ uint32_t s_tile, s_prefix;
@@ -408,7 +411,14 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in
         const uint32_t base = tile * LB_TILE + threadIdx.x * LB_ITEMS;
         uint32_t v[LB_ITEMS];
         uint32_t acc = 0;
-        if (base + LB_ITEMS <= n) {
+        uint32_t id[LB_ITEMS];
+        if (idx) {
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS; k++) {
+                id[k] = (base + k < n) ? idx[base + k] : 0xffffffffu;
+                v[k] = (base + k < n) ? in[id[k]] : 0u;
+            }
+        } else if (base + LB_ITEMS <= n) {
             const uint4* src = reinterpret_cast<const uint4*>(in + base);
 #pragma unroll
             for (int k = 0; k < LB_ITEMS / 4; k++) {
@@ -443,7 +453,13 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in
         }
         __syncthreads();
         ex += s_prefix;
-        if (base + LB_ITEMS <= n) {
+        if (idx) {
+#pragma unroll
+            for (int k = 0; k < LB_ITEMS; k++) {
+                if (base + k < n) out[id[k]] = ex;
+                ex += v[k];
+            }
+        } else if (base + LB_ITEMS <= n) {
             uint4* dst = reinterpret_cast<uint4*>(out + base);
 #pragma unroll
             for (int k = 0; k < LB_ITEMS / 4; k++) {
@@ -466,11 +482,12 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in
 }
 
 int launch_scan_lookback(const uint32_t* in, uint32_t* out, const uint32_t* n_ptr, uint32_t n_add, uint32_t n_max,
-                         unsigned long long* desc, uint32_t* total, const uint32_t* flags, int num_sms, cudaStream_t s) {
+                         unsigned long long* desc, uint32_t* total, const uint32_t* flags, int num_sms, cudaStream_t s,
+                         const uint32_t* idx) {
     const uint32_t max_tiles = (n_max + LB_TILE - 1) / LB_TILE;
     cudaMemsetAsync(desc, 0, sizeof(unsigned long long) * ((size_t)max_tiles + 2), s);
     const int grid = (int)std::max<uint32_t>(1u, std::min<uint32_t>(max_tiles, (uint32_t)num_sms * 4u));
-    k_scan_lookback<<<grid, LB_THREADS, 0, s>>>(in, out, n_ptr, n_add, desc, total, flags);
+    k_scan_lookback<<<grid, LB_THREADS, 0, s>>>(in, out, n_ptr, n_add, desc, total, flags, idx);
     return 1;
 }
 
@@ -922,6 +939,7 @@ __global__ void __launch_bounds__(32) k_finish_counts(const __grid_constant__ De
         if (cap) poison = seq;
         if (lane == 0) {
             if (poison) P.flags[DEM_FLAG_POISON] = poison;
+            else P.flags[DEM_FLAG_CYCLE_STEP] = 0u;  // the new lists are in use from here on
             RebuildStatus* st = C.status + (seq % REBUILD_STATUS_SLOTS);
             st->poison = poison;
             st->capflags = cap;
@@ -981,14 +999,8 @@ int launch_cd_prepare(const DevParams& P, const CdParams& C, const MgDev* M, boo
         cudaMemsetAsync(P.ss.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sn.count, 0, sizeof(uint32_t) * 4, s);
         cudaMemsetAsync(P.sa.count, 0, sizeof(uint32_t) * 4, s);
-        if (C.act_sph) {
-            // spheres this rank does not hold are not visited: leave empty segments behind for them, so that later
-            // history look-ups find nothing stale
-            launches += launch_zero_u32(P.ss.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
-            launches += launch_zero_u32(P.sn.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
-            launches += launch_zero_u32(P.sa.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
-            if (P.nTri) launches += launch_zero_u32(P.st.seg_count, (size_t)P.nSpheres + 1, P.flags, num_sms, s);
-        }
+        // (decomposed: spheres this rank does not hold are not visited; k_mg_clear_segs has emptied the segments their
+        // last visit to these buffers left behind)
         if (P.nSpheres) {
             k_sphere_prep<<<gs_grid(P.nSpheres, 256, num_sms, 8), 256, 0, s>>>(P, C);
             launches++;
@@ -1019,9 +1031,13 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, const MgDev* M, int p
             const uint32_t* keys = sorted_buf < 0 ? C.vals[0] : C.keys[sorted_buf];
             const int grid = gs_grid(n, 128, num_sms, 8);
             launch_sweep_count(P, C, keys, grid, s);
-            launches += 1 + launch_scan_lookback(P.ss.seg_count, P.ss.seg_start, nullptr, n, n, C.scan_desc, P.ss.count, P.flags, num_sms, s);
-            launches += launch_scan_lookback(P.sn.seg_count, P.sn.seg_start, nullptr, n, n, C.scan_desc, P.sn.count, P.flags, num_sms, s);
-            launch_sweep_fill(P, C, keys, grid, s);
+            // per-sphere counts -> first slots: over all spheres in sphere-id order, or (decomposed) over the active
+            // spheres in the order of their list -- owner-major either way
+            const uint32_t* np = C.act_sph ? C.act_count : nullptr;
+            const uint32_t na = C.act_sph ? 0u : n;
+            launches += 1 + launch_scan_lookback(P.ss.seg_count, P.ss.seg_start, np, na, n, C.scan_desc, P.ss.count, P.flags, num_sms, s, C.act_sph);
+            launches += launch_scan_lookback(P.sn.seg_count, P.sn.seg_start, np, na, n, C.scan_desc, P.sn.count, P.flags, num_sms, s, C.act_sph);
+            launch_sweep_fill(P, C, keys, gs_grid(n, 256, num_sms, 8), s);
             launches++;
             if (P.ss.hist) {  // (a history-less force model has nothing to carry over)
                 k_history<<<num_sms * 8, 256, 0, s>>>(P, C);

@@ -7,9 +7,9 @@
 // EVERYTHING here is device-driven over peer-mapped memory (NVLink stores + system-scope flag words): no library call,
 // no host synchronisation, and no host-side argument changes from one step or rebuild to the next -- exchange numbers
 // and all counts live in device memory -- so whole steps and whole rebuilds replay as CUDA graphs on every rank.
-//   * per step   : the integrator stores the {state, spin} record (80 B) of each own owner inside a halo straight into
-//                  the neighbour's receive buffer; k_mg_pull publishes the exchange number to the neighbours, waits for
-//                  theirs and scatters what they stored here into the same global slots;
+//   * per step   : k_mg_exchange, right after the integrator, copies the {state, spin} records (80 B) of the own owners
+//                  inside a halo into the neighbours' receive buffers, publishes the exchange number to the neighbours,
+//                  waits for theirs and scatters what they stored here into the same global slots;
 //   * per rebuild: max |v| is all-gathered through per-rank mailboxes (same cell grid everywhere), ownership is
 //                  re-decided from positions by the same rule on both sides of a cut (the data is an exact copy, so
 //                  both sides agree without talking) walking only the owners this rank already holds, the halo
@@ -58,18 +58,6 @@ __device__ __forceinline__ uint32_t* mg_recv_count(char* block, int par, int dir
     return reinterpret_cast<uint32_t*>(block + MG_HDR_RECV_COUNT) + par * 2 + dir;
 }
 
-// ---- rebuild, step 1: forget the slots of the previous halo lists (both parities: the other one may hold the lists of
-// a failed attempt), so that the slot map only needs touching where it changes ----
-__global__ void __launch_bounds__(256) k_mg_unmap(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M) {
-    if (P.flags[DEM_FLAG_POISON]) return;
-    for (int par = 0; par < 2; par++)
-        for (int d = 0; d < 2; d++) {
-            const uint32_t n = min(M.counts[par][1 + d], M.cap);
-            for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-                M.send_slot[d][M.send_gid[par][d][i]] = -1;
-        }
-}
-
 // ---- step 2: re-decide ownership from positions, walking the owners of the previous cycle's active list only; own
 // owners go to the new active list, those inside the halo of a cut additionally to that cut's send list ----
 //   flag[g]: 0 unknown here, 1 own, 2 ghost.   counts[par]: [0] own, [1] send-left, [2] send-right, [3] active
@@ -104,8 +92,8 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
         warp_append(own && g < M.nClumpOwners, &cnt[0]);
         const uint32_t sl = warp_append(toL, &cnt[1]);
         const uint32_t sr = warp_append(toR, &cnt[2]);
-        if (toL && sl < M.cap) { M.send_gid[par][0][sl] = g; M.send_slot[0][g] = (int32_t)sl; }
-        if (toR && sr < M.cap) { M.send_gid[par][1][sr] = g; M.send_slot[1][g] = (int32_t)sr; }
+        if (toL && sl < M.cap) M.send_gid[par][0][sl] = g;
+        if (toR && sr < M.cap) M.send_gid[par][1][sr] = g;
         if ((toL && sl >= M.cap) || (toR && sr >= M.cap)) atomicOr(&P.flags[DEM_FLAG_HALO], 8u);
     }
 }
@@ -216,7 +204,7 @@ __global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant
             uint2 r = make_uint2(0u, 0u);
             if (t < n) r = M.owner_sph[M.active_list[par][t]];
             const uint32_t base = warp_claim_n(r.y, &M.counts[par][4]);
-            for (uint32_t k = 0; k < r.y; k++) M.act_sph[base + k] = r.x + k;
+            for (uint32_t k = 0; k < r.y; k++) M.act_sph[par][base + k] = r.x + k;
         }
     } else {
         // (spheres of an owner are not contiguous in this input: scan them all)
@@ -224,39 +212,80 @@ __global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += gridDim.x * blockDim.x) {
             const bool act = (i < P.nSpheres) && (M.flag[P.sph[i].x] != 0);
             const uint32_t slot = warp_append(act, &M.counts[par][4]);
-            if (act) M.act_sph[slot] = i;
+            if (act) M.act_sph[par][slot] = i;
         }
+    }
+}
+
+// ---- step 1b: the list buffers of parity par were last written two rebuilds ago, for the active spheres of THAT cycle
+// (still listed in act_sph[par]): empty their segments, so that spheres this rank no longer holds leave nothing stale
+// behind for later history look-ups.  P carries the NEW lists. ----
+__global__ void __launch_bounds__(256) k_mg_clear_segs(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const uint32_t n = M.counts[par][4];
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t i = M.act_sph[par][t];
+        P.ss.seg_count[i] = 0u;
+        P.sn.seg_count[i] = 0u;
+        P.sa.seg_count[i] = 0u;
+        if (P.nTri) P.st.seg_count[i] = 0u;
     }
 }
 
 int launch_mg_redistribute(const DevParams& P, const MgDev& M, const GridInfo* grid, int par, int num_sms, cudaStream_t s) {
     const int g = num_sms * 2;
-    k_mg_unmap<<<32, 256, 0, s>>>(P, M);
+    k_mg_clear_segs<<<g, 256, 0, s>>>(P, M, par);
     launch_zero_u32(M.counts[par], 8, P.flags, num_sms, s);
-    k_mg_classify<<<g, 256, 0, s>>>(P, M, grid, par);
+    // (one owner per thread where the count allows: the per-owner work is a dependent chain of loads)
+    const int gfull = (int)std::min<uint32_t>((P.nOwners + 255u) / 256u, (uint32_t)num_sms * 16u);
+    k_mg_classify<<<std::max(gfull, 1), 256, 0, s>>>(P, M, grid, par);
     k_mg_push_full<<<std::min(g, 64), 256, 0, s>>>(P, M, par);
     k_mg_pull_full<<<std::min(g, 64), 256, 0, s>>>(P, M, par);
-    k_mg_active_spheres<<<g, 256, 0, s>>>(P, M, par);
+    k_mg_active_spheres<<<std::max(gfull, 1), 256, 0, s>>>(P, M, par);
     return 6;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Per-step exchange.  The integrator (the previous kernel in this stream) stored my halo records into the neighbours'
-// buffers; block 0 tells them the exchange is complete BEFORE anybody waits for theirs (no rank waits for another's
-// wait), every block waits for the neighbours' flags and scatters the records they stored here.  Receive buffers are
-// double buffered by exchange parity: a rank can run at most one exchange ahead of its neighbour (it cannot finish
-// pull(e) before the neighbour has pushed e), so the half written in exchange e+1 is the one the neighbour finished
-// reading in exchange e-1.  The membership lists are double buffered by cycle parity for the same reason.
-__global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
+// Per-step exchange, ONE kernel right after the integrator.  Phase 1: every block copies its share of the {state, spin}
+// records (80 B) of my halo owners -- the send lists of this cycle -- into the neighbours' receive buffers (coalesced
+// 16-byte stores over NVLink); the last block to finish tells the neighbours that exchange e is complete.  Phase 2: every
+// block waits for the neighbours' word and scatters the records they stored here into the global slots.  No rank waits
+// for another rank's wait (phase 1 depends on nobody), so there is no cycle.  Receive buffers are double buffered by
+// exchange parity: a rank can run at most one exchange ahead of its neighbour (it cannot finish exchange e before the
+// neighbour has pushed e), so the half written in exchange e+1 is the one the neighbour finished reading in e-1.  The
+// membership lists are double buffered by cycle parity for the same reason.  (Storing the records from inside the
+// integrator instead -- one or two lanes of nearly every warp own a halo owner -- made the integrator as slow on half the
+// owners (47 us) as it is on all of them on one GPU.)
+__global__ void __launch_bounds__(256) k_mg_exchange(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
     if (P.flags[DEM_FLAG_POISON]) return;
     const unsigned long long e = *M.epoch + 1ull;
     const int half = (int)(e & 1ull);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        __threadfence_system();
-        for (int d = 0; d < 2; d++)
-            if (M.has[d]) st_release_sys(mg_flag(M.peer_block[M.rank + (d == 0 ? -1 : 1)], 1 - d), e);
+    for (int d = 0; d < 2; d++) {
+        if (!M.has[d]) continue;
+        char* peer = M.peer_block[M.rank + (d == 0 ? -1 : 1)];
+        const uint32_t n = min(M.counts[par][1 + d], M.cap);
+        int4* pr = reinterpret_cast<int4*>(peer + mg_off_rec(M.cap, 1 - d, half));
+        const uint32_t* gid = M.send_gid[par][d];
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n * 5u; t += gridDim.x * blockDim.x) {
+            const uint32_t i = t / 5u, part = t - i * 5u;
+            const uint32_t g = gid[i];
+            const int4* src = (part < 4) ? reinterpret_cast<const int4*>(P.state + g) + part
+                                         : reinterpret_cast<const int4*>(P.spin + g);
+            pr[(size_t)i * 5u + part] = *src;
+        }
     }
-    if (threadIdx.x == 0) mg_wait_neighbours(P, M, e);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t done = atomicAdd(&M.block_ctr[1], 1u);
+        if (done == gridDim.x - 1) {
+            M.block_ctr[1] = 0;
+            __threadfence_system();
+            for (int d = 0; d < 2; d++)
+                if (M.has[d]) st_release_sys(mg_flag(M.peer_block[M.rank + (d == 0 ? -1 : 1)], 1 - d), e);
+        }
+        mg_wait_neighbours(P, M, e);
+    }
     __syncthreads();
     for (int d = 0; d < 2; d++) {
         if (!M.has[d]) continue;
@@ -274,7 +303,7 @@ __global__ void __launch_bounds__(256) k_mg_pull(const __grid_constant__ DevPara
 }
 
 int launch_mg_pull(const DevParams& P, const MgDev& M, int par, int num_sms, cudaStream_t s) {
-    k_mg_pull<<<std::min(num_sms, 64), 256, 0, s>>>(P, M, par);
+    k_mg_exchange<<<std::min(num_sms, 64), 256, 0, s>>>(P, M, par);
     return 1;
 }
 

@@ -26,17 +26,14 @@ struct End {
     float mass;
 };
 
-__device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, uint32_t o, OwnerPos& pos, End& e) {
-    // two 256-bit loads: {pos,quat} and {vel,omg}
+// the owner record is two 32-byte sectors, one 256-bit load each: geometry {pos, quat} and kinematics {vel+mass, omg}
+__device__ __forceinline__ void load_owner_geom(const OwnerState* __restrict__ st, uint32_t o, OwnerPos& pos, End& e) {
     const float* base = reinterpret_cast<const float*>(st + o);
     uint32_t a0, a1, a2, a3;
-    float q0, q1, q2, q3, v0, v1, v2, v3, w0, w1, w2, w3;
+    float q0, q1, q2, q3;
     asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3), "=f"(q0), "=f"(q1), "=f"(q2), "=f"(q3)
                  : "l"(base));
-    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3), "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
-                 : "l"(base + 8));
     pos.voxel = ((unsigned long long)a1 << 32) | a0;
     pos.lx = (unsigned short)(a2 & 0xffffu);
     pos.ly = (unsigned short)(a2 >> 16);
@@ -44,9 +41,20 @@ __device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, ui
     pos.family = (unsigned char)((a3 >> 16) & 0xffu);
     pos.flags = (unsigned char)(a3 >> 24);
     e.q = make_float4(q0, q1, q2, q3);
+}
+__device__ __forceinline__ void load_owner_kin(const OwnerState* __restrict__ st, uint32_t o, End& e) {
+    const float* base = reinterpret_cast<const float*>(st + o);
+    float v0, v1, v2, v3, w0, w1, w2, w3;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v0), "=f"(v1), "=f"(v2), "=f"(v3), "=f"(w0), "=f"(w1), "=f"(w2), "=f"(w3)
+                 : "l"(base + 8));
     e.v = f3(v0, v1, v2);
     e.mass = v3;
     e.ww = f3(w0, w1, w2);
+}
+__device__ __forceinline__ void load_owner(const OwnerState* __restrict__ st, uint32_t o, OwnerPos& pos, End& e) {
+    load_owner_geom(st, o, pos, e);
+    load_owner_kin(st, o, e);
 }
 
 // contact point in the world frame (LBF-relative), for the per-contact record: owner A's position + lever arm
@@ -136,22 +144,40 @@ template <int MODEL, bool RECORD, int MINB, bool FAST>
 __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
     if (P.flags[DEM_FLAG_POISON]) return;
     const uint32_t nT = *P.ss.count;
-    const uint32_t n = nT + *P.sn.count;
+    // (force_opts bits 2 / 3: measurement only -- leave the candidate list / the touching list out)
+    const uint32_t n = (P.force_opts & 4u) ? nT : nT + *P.sn.count;
     const uint32_t step = gridDim.x * blockDim.x;
     const uint32_t nround = (n + 31u) & ~31u;  // whole warps take part in the A-side reduction
+    const uint32_t cfirst = (P.force_opts & 8u) ? (nT & ~31u) : 0u;
     const int lane = threadIdx.x & 31;
-    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += step) {
+    // integrations since the rebuild that made these lists: a candidate whose gap cannot have closed yet is skipped
+    // after its 16-byte record alone (no owner gathers) -- it cannot be in touch, so it contributes nothing.
+    // Measured on the settled 1M-clump bed (tools/force_opts_prof.py): the candidate list costs 50 us of the 158 with or
+    // without the skip and with or without the lazy velocity fetch, and fetching the next record ahead in registers made
+    // the kernel slower (170 us): the loop runs at the speed of one thread's chain of dependent loads at 50 %
+    // occupancy, not of the memory pipes.  The skip is therefore off by default (force_opts bit 0).
+    const uint32_t cyc = (P.force_opts & 1u) ? P.flags[DEM_FLAG_CYCLE_STEP] : 0xffffffffu;
+    const bool lazy = (P.force_opts & 2u) != 0u;
+    for (uint32_t c = cfirst + blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += step) {
         float wA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         uint32_t keyA = 0xffffffffu - (uint32_t)lane;  // never equal to a neighbour's key
         bool touch = false;
-        if (c < n) {
+        bool work = c < n;
         const bool inT = c < nT;
         const uint32_t idx = inT ? c : c - nT;
         uint4* const cinfo = inT ? P.ss.cinfo : P.sn.cinfo;
         float4* const histp = inT ? P.ss.hist : P.sn.hist;
-        const uint4 ci = __ldcs(&cinfo[idx]);  // streaming: evict-first
+        uint4 ci = make_uint4(0u, 0u, 0u, 0u);
+        if (work) {
+            ci = __ldcs(&cinfo[idx]);  // streaming: evict-first
+            keyA = ci.x;
+            if (!inT && (ci.w >> 31) == 0u && ((ci.w >> CINFO_FIRST_SHIFT) & 0xffu) > cyc) {
+                work = false;
+                if (RECORD) P.sn.force[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (work) {
         const uint32_t oA = ci.x, oB = ci.y;
-        keyA = oA;
         const bool alive = (ci.w >> 31) != 0u;
         float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
         if (MODEL == 0 && alive) hist = __ldcs(&histp[idx]);
@@ -159,8 +185,14 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
         const float4 compB = __ldg(&P.comp[ci.z >> 16]);
         OwnerPos pA, pB;
         End A, B;
-        load_owner(P.state, oA, pA, A);
-        load_owner(P.state, oB, pB, B);
+        load_owner_geom(P.state, oA, pA, A);
+        load_owner_geom(P.state, oB, pB, B);
+        // velocities are only needed for pairs in touch: the list of pairs that overlapped at the rebuild fetches them
+        // up front (independent loads in flight together), the candidate list only once the narrow phase says so
+        if (inT || !lazy) {
+            load_owner_kin(P.state, oA, A);
+            load_owner_kin(P.state, oB, B);
+        }
 
         // ---- narrow phase (checkSpheresOverlap<double,float>, DEMHelperKernels.cuh:292-326) ----
         const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
@@ -183,6 +215,10 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
         const float depth = fdiv<FAST>((float)(R * R - d2), (float)R + mag);
 
         if (depth > 0.f) {
+            if (!inT && lazy) {
+                load_owner_kin(P.state, oA, A);
+                load_owner_kin(P.state, oB, B);
+            }
             nrm = nrm * (FAST ? imag : 1.f / mag);
             // contact point = centre(B) + (rB - depth/2) n ; lever arms from each owner (world frame)
             const float s = rB - 0.5f * depth;
@@ -222,7 +258,7 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
                 frc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        }  // c < n
+        }  // work
         // A side: the list is owner-major, so the contacts of one owner sit in adjacent lanes. Segmented suffix sum over
         // runs of equal owner, then ONE pair of vector reductions per run instead of one per contact.
         if (__any_sync(0xffffffffu, touch)) {
@@ -663,26 +699,6 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
           __uint_as_float(p2), __uint_as_float(p3), q.x, q.y, q.z, q.w);
     st_v8(dst + 8, v[0], v[1], v[2], e.mass, ww.x, ww.y, ww.z, 0.f);
     P.spin[o] = make_float4(w[0], w[1], w[2], spin.w);
-    // multi-GPU: an own owner inside a neighbour's halo goes straight into that neighbour's receive buffer over NVLink
-    // (the record layout of k_mg_push: four 16-byte words of state, one of spin).  No fence here: the stores are
-    // complete when this kernel is, and k_mg_pull -- next in the stream -- publishes the epoch to the neighbours.
-    if (P.send_slot[0]) {
-        const uint32_t half = (uint32_t)((*P.epoch + 1ull) & 1ull);  // the exchange this step's k_mg_pull will complete
-#pragma unroll
-        for (int d = 0; d < 2; d++) {
-            const int32_t slot = P.send_slot[d][o];
-            if (slot >= 0 && P.peer_rec[d]) {
-                // 80-byte records are only 16-byte aligned: five 128-bit stores
-                float4* r = reinterpret_cast<float4*>(P.peer_rec[d] + (size_t)half * P.rec_half_int4 + (size_t)slot * 5u);
-                r[0] = make_float4(__uint_as_float((uint32_t)(pos.voxel & 0xffffffffull)),
-                                   __uint_as_float((uint32_t)(pos.voxel >> 32)), __uint_as_float(p2), __uint_as_float(p3));
-                r[1] = q;
-                r[2] = make_float4(v[0], v[1], v[2], e.mass);
-                r[3] = make_float4(ww.x, ww.y, ww.z, 0.f);
-                r[4] = make_float4(w[0], w[1], w[2], spin.w);
-            }
-        }
-    }
     // per-owner acceleration read-out (ContactAcc / ContactAngAccLocal trackers), only when requested
     if (P.acc_out) st_v8(P.acc_out + o, acc[0], acc[1], acc[2], 0.f, ang[0], ang[1], ang[2], 0.f);
     // consume the wrench: the accumulator is zero again for the next step's reductions
@@ -694,7 +710,10 @@ __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevPa
     if (P.flags[DEM_FLAG_POISON]) return;
     // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
     // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.
-    if (blockIdx.x == 0 && threadIdx.x == 0) *P.maxvel = 0.f;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        *P.maxvel = 0.f;
+        P.flags[DEM_FLAG_CYCLE_STEP] += 1u;  // (read by the next step's force kernel: stream order)
+    }
     float absv = 0.f;
     const uint32_t n = P.active_list ? *P.nActivePtr : P.nOwners;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -766,8 +785,10 @@ void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaS
 void launch_integrate(const DevParams& P, int num_sms, cudaStream_t s) {
     const int block = 256;
     // single GPU: one owner per thread; decomposed: grid-stride over the DEVICE-resident number of active owners
+    // (decomposed: the number of active owners lives on the device; CTAs beyond it return at once, which is cheaper
+    // than making fewer threads walk several owners each: the loads of one owner form a dependent chain)
     int grid = (int)((P.nOwners + block - 1) / block);
-    if (P.active_list) grid = std::min(grid, num_sms * 8);
+    (void)num_sms;
     if (grid > 0) k_integrate<<<grid, block, 0, s>>>(P);
 }
 

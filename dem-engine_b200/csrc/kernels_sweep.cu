@@ -16,7 +16,8 @@
 //   * two passes, COUNT (per-sphere counts -> exclusive scan in sphere-id order) and FILL, so the list is
 //     deterministic, owner-major (the force kernel streams the A side and reduces it inside the warp) and there is NO
 //     cap on the number of candidates per sphere (the reference allows up to 32768 spheres per bin,
-//     DEMContactKernels_SphereSphere.cu:121-126).
+//     DEMContactKernels_SphereSphere.cu:121-126).  The distance tests run ONCE: the count pass hands the candidates
+//     it accepted to the fill pass through a 64-byte record per sphere.
 #include "dem_kernels.h"
 
 namespace demb {
@@ -61,9 +62,88 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// FILL = false: per-sphere counts into ss.seg_count / sn.seg_count.  FILL = true: the compiled records at
-// seg_start[sphere] + k (seg_start = exclusive scan of the counts over sphere ids).
-template <bool FILL>
+// Per sorted position j the count pass leaves the candidates it accepted in cand[j * SW_K .. ): the candidate's sorted
+// position | CAND_TOUCH | CAND_NOHIST.  The fill pass only has to look those up -- it never repeats a distance test.  A
+// sphere with more than SW_K accepted candidates (dense polydisperse packings, many-component clumps) is rare; the fill
+// pass finds its candidates again with plain loads (fill_slow).
+constexpr uint32_t SW_K = 16;
+constexpr uint32_t SW_REC = SW_K + SW_K / 4;  // words per record: SW_K candidates + one "first step" byte for each
+constexpr uint32_t CAND_TOUCH = 0x80000000u;
+constexpr uint32_t CAND_NOHIST = 0x40000000u;
+constexpr uint32_t CAND_POS = 0x3fffffffu;
+
+// the five forward runs [qb, qe) of the sphere at sorted position j in cell `key`
+__device__ __forceinline__ void forward_runs(const CdParams& C, const GridInfo& g, uint32_t j, uint32_t key, uint32_t qb[5],
+                                             uint32_t qe[5]) {
+    const int cx = (int)(key % g.nbx);
+    const int cy = (int)((key / g.nbx) % g.nby);
+    const int cz = (int)(key / (g.nbx * g.nby));
+    const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        qb[r] = 0xffffffffu; qe[r] = 0u;
+        // r=0: own row behind me; r=1: (dy=+1,dz=0); r=2..4: (dy=-1,0,+1; dz=+1)
+        const int dy = (r == 0) ? 0 : (r == 1 ? 1 : r - 3);
+        const int dz = (r < 2) ? 0 : 1;
+        const int y = cy + dy, z = cz + dz;
+        if (y < 0 || y >= (int)g.nby || z >= (int)g.nbz) continue;
+        const uint32_t row = g.nbx * ((uint32_t)y + g.nby * (uint32_t)z);
+        const uint32_t b = (r == 0) ? j + 1 : __ldg(&C.cellStart[row + x0]);
+        const uint32_t e = __ldg(&C.cellStart[row + x1 + 1]);
+        if (b < e) { qb[r] = b; qe[r] = e; }
+    }
+}
+
+// Acceptance of the pair (me at j, ot at q): 0 = no candidate, else CAND_* flags | 1.  Superset of the double-precision
+// test d2 <= R^2 && R - d > min(extraA, extraB) (DEMContactKernels_SphereSphere.cu:57-89).
+__device__ __forceinline__ bool pair_near(const float4 me, const float4 ot, float& d2) {
+    const float dx = me.x - ot.x, dy = me.y - ot.y, dz = me.z - ot.z;
+    d2 = dx * dx + dy * dy + dz * dz;
+    const float R = me.w + ot.w;
+    return d2 <= R * R * 1.000001f + 1e-20f;
+}
+__device__ __forceinline__ uint32_t pair_verdict_near(const DevParams& P, const CdParams& C, const float4 me, const uint2 myAux,
+                                                      const float4 ot, const uint2 oa, float d2, uint32_t q, bool fam_on,
+                                                      uint32_t myFam, float extraA, bool want_hist, uint32_t& first) {
+    first = 0u;
+    if (oa.x == myAux.x) return 0u;  // same owner
+    if (fam_on) {
+        const uint32_t famB = __ldg(&C.sortedMeta[q]).w;
+        if (C.any_mask && P.familyMasks[mask_pair(myFam, famB)] != 0) return 0u;
+        const float Rt = me.w + ot.w - fminf(extraA, P.familyExtraMargin[famB]);
+        if (d2 > Rt * Rt * 1.000001f + 1e-20f) return 0u;
+    }
+    // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
+    const float Rtrue = __uint_as_float(myAux.y) + __uint_as_float(oa.y);
+    if (d2 < Rtrue * Rtrue) return CAND_TOUCH | 1u;
+    // A candidate that is clearly apart at these very positions (float positions: allow for their rounding) would have
+    // its history destroyed by the force pass that follows this rebuild (no overlap => wildcards zeroed,
+    // DEMCalcForceKernels.cu:258-261): it carries none over, so k_history has nothing to look up or write for it.
+    const float slack = 3e-7f * (fabsf(me.x) + fabsf(me.y) + fabsf(me.z)) + 1e-8f;
+    const float gap = sqrtf(d2) * 0.999999f - Rtrue * 1.000001f - slack;
+    if (gap <= 0.f) return 1u;
+    // The first step of the coming cycle at which this pair can possibly touch.  The margin of an owner IS the bound on
+    // how far it travels during the maxDrift steps a list is used (DEMMiscKernels.cu:37-61), so after k integrations
+    // the gap has closed by at most k (marginA + marginB) / maxDrift; until then the force kernel skips the pair after
+    // reading its 16-byte record -- it cannot overlap, so it contributes nothing (margins include the family extra
+    // margin, which only makes the bound more cautious).  A fixed expand factor carries no such promise: always test.
+    if (P.beta < 0.f) {
+        const float closing = ((me.w - __uint_as_float(myAux.y)) + (ot.w - __uint_as_float(oa.y))) / (float)P.maxDrift;
+        const float f = floorf(gap / fmaxf(closing, 1e-30f));
+        first = (uint32_t)fminf(fmaxf(f, 0.f), 255.f);
+    }
+    return want_hist ? (CAND_NOHIST | 1u) : 1u;
+}
+__device__ __forceinline__ uint32_t pair_verdict(const DevParams& P, const CdParams& C, const float4 me, const uint2 myAux,
+                                                 const float4 ot, const uint2 oa, uint32_t q, bool fam_on, uint32_t myFam,
+                                                 float extraA, bool want_hist, uint32_t& first) {
+    float d2;
+    first = 0u;
+    if (!pair_near(me, ot, d2)) return 0u;
+    return pair_verdict_near(P, C, me, myAux, ot, oa, d2, q, fam_on, myFam, extraA, want_hist, first);
+}
+
+// COUNT pass: per-sphere counts into ss.seg_count / sn.seg_count, accepted candidates into C.cand.
 __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant__ DevParams P,
                                                           const __grid_constant__ CdParams C,
                                                           const uint32_t* __restrict__ keys) {
@@ -76,6 +156,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
     __syncthreads();
     uint32_t parity = 0;
     const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
+    const bool want_hist = P.sn.hist != nullptr;
     for (uint32_t base = blockIdx.x * SW_THREADS; base < nSorted; base += gridDim.x * SW_THREADS) {
         const uint32_t j = base + tid;
         const bool valid = j < nSorted;
@@ -87,23 +168,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
         if (valid) {
             me = C.sortedSph[j];
             myAux = C.sortedAux[j];
-            const uint32_t key = keys[j];
-            const int cx = (int)(key % g.nbx);
-            const int cy = (int)((key / g.nbx) % g.nby);
-            const int cz = (int)(key / (g.nbx * g.nby));
-            const int x0 = max(cx - 1, 0), x1 = min(cx + 1, (int)g.nbx - 1);
-#pragma unroll
-            for (int r = 0; r < 5; r++) {
-                // r=0: own row behind me; r=1: (dy=+1,dz=0); r=2..4: (dy=-1,0,+1; dz=+1)
-                const int dy = (r == 0) ? 0 : (r == 1 ? 1 : r - 3);
-                const int dz = (r < 2) ? 0 : 1;
-                const int y = cy + dy, z = cz + dz;
-                if (y < 0 || y >= (int)g.nby || z >= (int)g.nbz) continue;
-                const uint32_t row = g.nbx * ((uint32_t)y + g.nby * (uint32_t)z);
-                const uint32_t b = (r == 0) ? j + 1 : __ldg(&C.cellStart[row + x0]);
-                const uint32_t e = __ldg(&C.cellStart[row + x1 + 1]);
-                if (b < e) { qb[r] = b; qe[r] = e; }
-            }
+            forward_runs(C, g, j, keys[j], qb, qe);
         }
         // ---- the stretch of the sorted stream this CTA needs for each run type ----
         if (tid < 5) { sm.rb[tid] = 0xffffffffu; sm.re[tid] = 0u; }
@@ -123,18 +188,14 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
             if (sm.rb[r] >= sm.re[r]) { pos[r] = 0u; end[r] = 0u; }
         }
         __syncthreads();  // (rb / re are reset at the top of the next work item)
-        uint32_t nT = 0, nN = 0;
-        uint32_t slotT = 0, slotN = 0;
-        uint32_t sid = 0, myMeta_z = 0, myFam = 0;
+        uint32_t nT = 0, nN = 0, myFam = 0;
         float extraA = 0.f;
-        if (valid && (FILL || fam_on)) {
-            const uint4 meta = C.sortedMeta[j];
-            sid = meta.y; myMeta_z = meta.z; myFam = meta.w;
-            if (fam_on) extraA = P.familyExtraMargin[myFam];
-            if (FILL) { slotT = P.ss.seg_start[sid]; slotN = P.sn.seg_start[sid]; }
-        } else if (valid) {
-            sid = C.sortedMeta[j].y;
+        if (valid && fam_on) {
+            myFam = C.sortedMeta[j].w;
+            extraA = P.familyExtraMargin[myFam];
         }
+        uint32_t* mycand = C.cand + (size_t)j * SW_REC;
+        uint8_t* myfirst = reinterpret_cast<uint8_t*>(mycand + SW_K);
         // ---- phases: stage up to SW_CH entries of every run, test, advance ----
         for (;;) {
             uint32_t cnt[5];
@@ -159,54 +220,63 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
                         bulk_g2s(&sm.aux[r][0], C.sortedAux + pos[r], cnt[r] * 8u, &sm.mbar);
                     }
             }
-            mbar_wait(&sm.mbar, parity);
+            // one thread waits for the bulk copies (try_wait spins: 127 other threads would only burn issue slots),
+            // the CTA barrier releases the rest
+            if (tid == 0) mbar_wait(&sm.mbar, parity);
             parity ^= 1u;
+            __syncthreads();
             if (valid) {
+                // Pass 1, all lanes in step: the distance test only; a hit sets a bit.  Pass 2: the few hits (same-owner
+                // filter, family rules, which list, history flag, hand-over record) with the lanes converged on "my next
+                // hit" instead of one or two lanes dragging the warp through that code for every hit.
+                uint32_t hits[5];
+#pragma unroll
+                for (int r = 0; r < 5; r++) {
+                    hits[r] = 0u;
+                    const uint32_t lo = max(qb[r], pos[r]);
+                    const uint32_t hi = min(qe[r], pos[r] + cnt[r]);
+                    for (uint32_t q0 = lo; q0 < hi; q0 += 32u) {
+                        const uint32_t q1 = min(hi, q0 + 32u);
+                        uint32_t m = 0u;
+                        for (uint32_t q = q0; q < q1; q++) {
+                            float d2;
+                            if (pair_near(me, sm.sph[r][q - pos[r]], d2)) m |= 1u << (q - q0);
+                        }
+                        if (q1 == hi && q0 == lo) { hits[r] = m; break; }  // the usual case: at most 32 candidates in the run
+                        // a longer run: handle this stretch of 32 right away
+                        while (m) {
+                            const uint32_t q = q0 + (uint32_t)__ffs(m) - 1u;
+                            m &= m - 1u;
+                            float d2;
+                            const float4 ot = sm.sph[r][q - pos[r]];
+                            pair_near(me, ot, d2);
+                            uint32_t first;
+                            const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[r][q - pos[r]], d2, q, fam_on, myFam,
+                                                                 extraA, want_hist, first);
+                            if (v == 0u) continue;
+                            const uint32_t k = nT + nN;
+                            if (k < SW_K) { mycand[k] = q | (v & ~1u); myfirst[k] = (uint8_t)first; }
+                            if (v & CAND_TOUCH) nT++; else nN++;
+                        }
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < 5; r++) {
                     const uint32_t lo = max(qb[r], pos[r]);
-                    const uint32_t hi = min(qe[r], pos[r] + cnt[r]);
-                    for (uint32_t q = lo; q < hi; q++) {
+                    uint32_t m = hits[r];
+                    while (m) {
+                        const uint32_t q = lo + (uint32_t)__ffs(m) - 1u;
+                        m &= m - 1u;
+                        float d2;
                         const float4 ot = sm.sph[r][q - pos[r]];
-                        const float dx = me.x - ot.x, dy = me.y - ot.y, dz = me.z - ot.z;
-                        const float d2 = dx * dx + dy * dy + dz * dz;
-                        const float R = me.w + ot.w;
-                        // superset of the double-precision test d2 <= R^2 && R - d > min(extraA, extraB)
-                        // (DEMContactKernels_SphereSphere.cu:57-89)
-                        if (d2 > R * R * 1.000001f + 1e-20f) continue;
-                        const uint2 oa = sm.aux[r][q - pos[r]];
-                        if (oa.x == myAux.x) continue;  // same owner
-                        uint4 om = make_uint4(0, 0, 0, 0);
-                        if (fam_on || FILL) om = __ldg(&C.sortedMeta[q]);
-                        if (fam_on) {
-                            if (C.any_mask && P.familyMasks[mask_pair(myFam, om.w)] != 0) continue;
-                            const float Rt = R - fminf(extraA, P.familyExtraMargin[om.w]);
-                            if (d2 > Rt * Rt * 1.000001f + 1e-20f) continue;
-                        }
-                        // do the un-inflated spheres overlap right now? (only decides which list the pair goes to)
-                        const float Rtrue = __uint_as_float(myAux.y) + __uint_as_float(oa.y);
-                        const bool touching = d2 < Rtrue * Rtrue;
-                        if (!FILL) {
-                            if (touching) nT++; else nN++;
-                        } else {
-                            const ContactList& L = touching ? P.ss : P.sn;
-                            const uint32_t slot = touching ? slotT++ : slotN++;
-                            if (slot < C.capacity) {
-                                uint32_t skip = 0;
-                                if (!touching) {
-                                    // A candidate that is clearly apart at these very positions (float positions: allow
-                                    // for their rounding) would have its history destroyed by the force pass that follows
-                                    // this rebuild (no overlap => wildcards zeroed, DEMCalcForceKernels.cu:258-261): it
-                                    // carries none over, so k_history has nothing to look up or write for it.
-                                    const float slack = 3e-7f * (fabsf(me.x) + fabsf(me.y) + fabsf(me.z)) + 1e-8f;
-                                    if (L.hist && sqrtf(d2) * 0.999999f - Rtrue * 1.000001f - slack > 0.f) skip = CINFO_NO_HISTORY;
-                                }
-                                const uint32_t matpair = (myMeta_z >> 16) * P.nMat + (om.z >> 16);
-                                L.idB[slot] = om.y;
-                                (touching ? C.idA_ss : C.idA_sn)[slot] = sid;
-                                L.cinfo[slot] = make_uint4(myAux.x, om.x, (myMeta_z & 0xffffu) | ((om.z & 0xffffu) << 16), matpair | skip);
-                            }
-                        }
+                        pair_near(me, ot, d2);
+                        uint32_t first;
+                        const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[r][q - pos[r]], d2, q, fam_on, myFam, extraA,
+                                                             want_hist, first);
+                        if (v == 0u) continue;
+                        const uint32_t k = nT + nN;
+                        if (k < SW_K) { mycand[k] = q | (v & ~1u); myfirst[k] = (uint8_t)first; }
+                        if (v & CAND_TOUCH) nT++; else nN++;
                     }
                 }
             }
@@ -214,19 +284,80 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
 #pragma unroll
             for (int r = 0; r < 5; r++) pos[r] += cnt[r];
         }
-        if (!FILL && valid) {
+        if (valid) {
+            const uint32_t sid = C.sortedMeta[j].y;
             P.ss.seg_count[sid] = nT;
             P.sn.seg_count[sid] = nN;
         }
     }
 }
 
+// write contact (A at sorted position j, B at q) of the new lists
+__device__ __forceinline__ void emit_contact(const DevParams& P, const CdParams& C, uint32_t flags, uint32_t first, uint32_t q,
+                                             uint32_t sid, uint32_t ownerA, uint32_t metaA_z, uint32_t& slotT, uint32_t& slotN) {
+    const bool touching = (flags & CAND_TOUCH) != 0u;
+    const ContactList& L = touching ? P.ss : P.sn;
+    const uint32_t slot = touching ? slotT++ : slotN++;
+    if (slot >= C.capacity) return;
+    const uint4 om = __ldg(&C.sortedMeta[q]);
+    const uint32_t matpair = (metaA_z >> 16) * P.nMat + (om.z >> 16);
+    L.idB[slot] = om.y;
+    (touching ? C.idA_ss : C.idA_sn)[slot] = sid;
+    L.cinfo[slot] = make_uint4(ownerA, om.x, (metaA_z & 0xffffu) | ((om.z & 0xffffu) << 16),
+                               matpair | (first << CINFO_FIRST_SHIFT) | ((flags & CAND_NOHIST) ? CINFO_NO_HISTORY : 0u));
+}
+
+// FILL pass: one thread per sorted position; the compiled records go to seg_start[sphere] + k (seg_start = exclusive scan
+// of the counts over sphere ids: the lists are sphere-major, hence owner-major, and deterministic).
+__global__ void __launch_bounds__(256) k_sweep_fill(const __grid_constant__ DevParams P, const __grid_constant__ CdParams C,
+                                                    const uint32_t* __restrict__ keys) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    const GridInfo g = *C.grid;
+    const uint32_t nSorted = C.cellStart[g.ncells];
+    const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
+    const bool want_hist = P.sn.hist != nullptr;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nSorted; j += gridDim.x * blockDim.x) {
+        const uint4 meta = C.sortedMeta[j];
+        const uint32_t sid = meta.y;
+        const uint32_t n = P.ss.seg_count[sid] + P.sn.seg_count[sid];
+        if (n == 0u) continue;
+        uint32_t slotT = P.ss.seg_start[sid], slotN = P.sn.seg_start[sid];
+        if (n <= SW_K) {
+            const uint4* cp = reinterpret_cast<const uint4*>(C.cand + (size_t)j * SW_REC);
+            const uint4 f4 = cp[SW_K / 4];
+            const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
+            for (uint32_t k0 = 0; k0 < n; k0 += 4) {
+                const uint4 c4 = cp[k0 >> 2];
+                const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
+                const uint32_t f = fw[k0 >> 2];
+#pragma unroll
+                for (int t = 0; t < 4; t++)
+                    if (k0 + t < n) emit_contact(P, C, c[t], (f >> (8 * t)) & 0xffu, c[t] & CAND_POS, sid, meta.x, meta.z, slotT, slotN);
+            }
+        } else {
+            // more accepted candidates than the hand-over buffer holds: find them again (plain loads)
+            const float4 me = C.sortedSph[j];
+            const uint2 myAux = C.sortedAux[j];
+            const float extraA = fam_on ? P.familyExtraMargin[meta.w] : 0.f;
+            uint32_t qb[5], qe[5];
+            forward_runs(C, g, j, keys[j], qb, qe);
+            for (int r = 0; r < 5; r++)
+                for (uint32_t q = qb[r]; q < qe[r]; q++) {
+                    uint32_t first;
+                    const uint32_t v = pair_verdict(P, C, me, myAux, __ldg(&C.sortedSph[q]), __ldg(&C.sortedAux[q]), q, fam_on,
+                                                    meta.w, extraA, want_hist, first);
+                    if (v) emit_contact(P, C, v, first, q, sid, meta.x, meta.z, slotT, slotN);
+                }
+        }
+    }
+}
+
 // count -> (scan by the caller) -> fill
 void launch_sweep_count(const DevParams& P, const CdParams& C, const uint32_t* keys, int grid, cudaStream_t s) {
-    k_sweep_tma<false><<<grid, SW_THREADS, 0, s>>>(P, C, keys);
+    k_sweep_tma<<<grid, SW_THREADS, 0, s>>>(P, C, keys);
 }
 void launch_sweep_fill(const DevParams& P, const CdParams& C, const uint32_t* keys, int grid, cudaStream_t s) {
-    k_sweep_tma<true><<<grid, SW_THREADS, 0, s>>>(P, C, keys);
+    k_sweep_fill<<<grid, 256, 0, s>>>(P, C, keys);
 }
 
 }  // namespace demb

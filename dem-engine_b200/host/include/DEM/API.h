@@ -278,7 +278,7 @@ class DEMForceModel {
 // ---------------------------------------------------------------------------------------------------------------
 class DEMSolver {
   public:
-    /// nGPUs is accepted for source compatibility; this core runs the whole hot path on one device per context
+    /// nGPUs devices (those the box has, at most 8) form one group; large scenes are sharded over them (x-slabs)
     explicit DEMSolver(unsigned int nGPUs = 2);
     explicit DEMSolver(const std::vector<int>& gpu_ids);
     ~DEMSolver();

@@ -145,17 +145,33 @@ void DEMExternObj::AddCylinder(const float3 pos, const float3 axis, const float 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// DEMSolver(nGPUs) (src/DEM/API.h:53; APIPublic.cpp:23-74): the reference gives each of its two worker threads a GPU.  Here
+// nGPUs devices (as many as the box has, at most 8) form ONE group context: a scene large enough to be worth it is sharded
+// into x-slabs over them, anything else runs on the first device.  DEME_B200_GPUS overrides the count, DEME_B200_DEVICE
+// picks the (first) device.
+static DemCtx* create_group_ctx(std::vector<int> ids) {
+    const int have = dem_device_count();
+    if (have <= 0) fail("DEMSolver: no usable CUDA device (this core has no CPU fallback)");
+    std::vector<int> use;
+    for (int d : ids)
+        if (d >= 0 && d < have && std::find(use.begin(), use.end(), d) == use.end() && use.size() < 8) use.push_back(d);
+    if (use.empty()) use.push_back(0);
+    DemCtx* c = nullptr;
+    const int rc = dem_ctx_create_group(&c, use.data(), (int)use.size());
+    if (rc != DEM_OK) fail("DEMSolver: dem_ctx_create_group returned " + std::to_string(rc) + " (this core has no CPU fallback)");
+    return c;
+}
 DEMSolver::DEMSolver(unsigned int nGPUs) {
-    (void)nGPUs;
-    int device = 0;
-    if (const char* e = std::getenv("DEME_B200_DEVICE")) device = std::atoi(e);
-    const int rc = dem_ctx_create(&ctx, device);
-    if (rc != DEM_OK) fail("DEMSolver: no usable CUDA device (this core has no CPU fallback); dem_ctx_create returned " + std::to_string(rc));
+    int first = 0, n = (int)nGPUs;
+    if (const char* e = std::getenv("DEME_B200_DEVICE")) first = std::atoi(e);
+    if (const char* e = std::getenv("DEME_B200_GPUS")) n = std::atoi(e);
+    std::vector<int> ids;
+    for (int k = 0; k < std::max(n, 1); k++) ids.push_back(first + k);
+    ctx = create_group_ctx(ids);
     m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
 }
 DEMSolver::DEMSolver(const std::vector<int>& gpu_ids) {
-    const int rc = dem_ctx_create(&ctx, gpu_ids.empty() ? 0 : gpu_ids[0]);
-    if (rc != DEM_OK) fail("DEMSolver: no usable CUDA device (this core has no CPU fallback)");
+    ctx = create_group_ctx(gpu_ids);
     m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
 }
 DEMSolver::~DEMSolver() {

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
-    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
+    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
 ]
 
 
@@ -153,10 +153,15 @@ class DemError(RuntimeError):
 class Engine:
     """One DemCtx. Mirrors the call order of DEMSolver::Initialize / DoDynamics of the reference."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one GPU; devices=[...]: ONE context driving a group of GPUs (dem_ctx_create_group)"""
         self.lib = load_library()
         self.ctx = C.c_void_p()
-        rc = self.lib.dem_ctx_create(C.byref(self.ctx), int(device))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = self.lib.dem_ctx_create_group(C.byref(self.ctx), arr, len(devices))
+        else:
+            rc = self.lib.dem_ctx_create(C.byref(self.ctx), int(device))
         if rc != 0:
             raise DemError(rc, "dem_ctx_create failed (no CUDA device? there is no CPU fallback)")
         self.params = None
@@ -363,7 +368,7 @@ class Engine:
     def profile_rebuild(self):
         out = (C.c_float * 8)()
         self._ck(self.lib.dem_profile_rebuild(self.ctx, out))
-        names = ["prep_us", "sort_us", "cellscan_us", "gather_us", "sweep_us", "counts_us", "unused", "total_us"]
+        names = ["prep_us", "sort_us", "cellscan_us", "gather_us", "sweep_us", "counts_us", "redistribute_us", "total_us"]
         return dict(zip(names, [float(x) for x in out]))
 
     def profile_steps(self, n):

@@ -128,6 +128,16 @@ int dem_host_encode_positions(const DemSimParams* p, const float* xyz_world, uin
 
 /* ---- life cycle: DEMSolver::DEMSolver / ~DEMSolver (APIPublic.cpp:23-92) ------------------------------- */
 int dem_ctx_create(DemCtx** out, int device);
+/* Number of CUDA devices (0 without a driver / device). */
+int dem_device_count(void);
+/* DEMSolver(nGPUs) / DEMSolver(std::vector<int>) (src/DEM/API.h:53,56; the reference caps nGPUs at 2, one for each of its
+ * worker threads -- here up to the 8 GPUs of a box): ONE context that drives n devices.  Every entry point called on it
+ * acts on the whole group: set-up calls reach every device, dem_initialize shards the scene into x-slabs (see the
+ * multi-GPU section below) when it qualifies -- at least "group_min_owners" (dem_set_option, default 50 000) clump owners
+ * per GPU and no free-moving wall / mesh owner; otherwise the scene runs on devices[0] alone -- stepping calls step all
+ * ranks together, and read-back calls first merge the ranks' owners into the first device (peer copies).  devices may
+ * be NULL (0 .. n-1). */
+int dem_ctx_create_group(DemCtx** out, const int* devices, int n);
 int dem_ctx_destroy(DemCtx* ctx);
 const char* dem_last_error(const DemCtx* ctx);
 int dem_abi_version(void);
@@ -275,7 +285,7 @@ int dem_set_option(DemCtx* ctx, const char* name, double value);
 int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]);
 /* One contact-list rebuild with CUDA events between its stages (microseconds): [0] margins + cell keys + histogram +
  * sphere-analytical list [1] sort [2] cell-table scan [3] gather [4] sweep (+ history carry-over) [5] counts
- * [6] unused [7] whole rebuild */
+ * [6] multi-GPU: re-deciding ownership + halo lists (part of [0]) [7] whole rebuild */
 int dem_profile_rebuild(DemCtx* ctx, float out_us[8]);
 
 /* Binning + sort only (the neighbour-search stress case): `repeats` times { margins, sphere world positions, cell keys,

@@ -108,3 +108,62 @@ def test_torchrun_ranks_match_single_gpu(built, world):
     r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     print(r.stdout[-4000:])
     assert r.returncode == 0 and "MGPU_CHECK PASS" in r.stdout
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_group_context_is_a_drop_in_for_one_gpu(built, world):
+    """dem_ctx_create_group: ONE context driving several GPUs (what deme::DEMSolver(nGPUs) creates).  Every C-ABI call a
+    single-GPU caller makes must give the same answers: stepping, state read-back (merged from the ranks), reductions,
+    the contact list (union of the ranks' lists, pairs across a cut listed once), host-side state changes in between
+    (broadcast to the ranks, ownership re-derived), and the same again after more steps."""
+    _need(world)
+    sc = shear_bed(40, 12, 10)
+    f = scenes.flatten(sc)
+    n = f.nClumps
+    fp = scenes.flatten(sc)
+    for name in ("vX", "vY", "vZ"):
+        a = getattr(fp, name)
+        a[:] = (a.astype("f8") * (1.0 + 1e-6)).astype("f4")
+    e1, e1p = demb200.Engine(0), demb200.Engine(0)
+    e1.load_flat(f)
+    e1p.load_flat(fp)
+    eg = demb200.Engine(devices=list(range(world)))
+    eg.set_option("group_min_owners", 100)   # (the default only shards scenes with >= 50 000 clumps per GPU)
+    eg.load_flat(f)
+    assert eg.mgpu_info()["world"] == world
+
+    def compare(label):
+        ref_p, ref_v = e1.positions()[:n], e1.owner_state()["vel"][:n].astype("f8")
+        sens_x = np.abs(e1p.positions()[:n] - ref_p).max()
+        sens_v = np.abs(e1p.owner_state()["vel"][:n].astype("f8") - ref_v).max()
+        err_x = np.abs(eg.positions()[:n] - ref_p).max()
+        err_v = np.abs(eg.owner_state()["vel"][:n].astype("f8") - ref_v).max()
+        print("%s: |dx| %.2e (sens %.2e) |dv| %.2e (sens %.2e)" % (label, err_x, sens_x, err_v, sens_v))
+        assert err_x <= 10 * sens_x + 1e-7 and err_v <= 10 * sens_v + 1e-5, (label, err_x, sens_x, err_v, sens_v)
+        # inspectors: same reductions over ALL clumps
+        a = eg.reduce_many((demb200.REDUCE_MAX_ABSV, demb200.REDUCE_KINETIC_ENERGY, demb200.REDUCE_TOTAL_MASS, demb200.REDUCE_MAX_Z))
+        b = e1.reduce_many((demb200.REDUCE_MAX_ABSV, demb200.REDUCE_KINETIC_ENERGY, demb200.REDUCE_TOTAL_MASS, demb200.REDUCE_MAX_Z))
+        assert abs(a[demb200.REDUCE_TOTAL_MASS] - b[demb200.REDUCE_TOTAL_MASS]) <= 1e-9 * b[demb200.REDUCE_TOTAL_MASS]
+        assert abs(a[demb200.REDUCE_KINETIC_ENERGY] - b[demb200.REDUCE_KINETIC_ENERGY]) <= 1e-3 * b[demb200.REDUCE_KINETIC_ENERGY] + 20 * sens_v
+        assert abs(a[demb200.REDUCE_MAX_Z] - b[demb200.REDUCE_MAX_Z]) <= 10 * sens_x + 1e-6
+        # contact list: the touching pairs of the merged list are those of the single-GPU list
+        ga, gb, gt, gw = eg.contacts()
+        sa, sb, st_, sw = e1.contacts()
+        key = lambda a_, b_, t_: (t_.astype("u8") << np.uint64(60)) | (a_.astype("u8") << np.uint64(30)) | b_.astype("u8")
+        kg, ks = key(ga, gb, gt), key(sa, sb, st_)
+        assert len(np.unique(kg)) == len(kg), "a pair across a cut is listed twice"
+        tg, ts = set(kg[np.abs(gw).max(1) > 0].tolist()), set(ks[np.abs(sw).max(1) > 0].tolist())
+        diff = len(tg ^ ts)
+        print("%s: %d / %d touching pairs, symmetric difference %d" % (label, len(tg), len(ts), diff))
+        assert diff <= max(2, len(ts) // 200)
+
+    eg.step(200); e1.step(200); e1p.step(200)
+    compare("N=%d after 200 steps" % world)
+    # a host-side change of state in the middle (what trackers' SetVel / SetPos do): kick a block of clumps
+    kick = np.tile(np.array([[0.0, 0.3, 0.5]], "f4"), (50, 1))
+    for e in (eg, e1, e1p):
+        e.upload_owner_state(100, vel=kick)
+    eg.step(400); e1.step(400); e1p.step(400)
+    compare("N=%d after the kick + 400 steps" % world)
+    for e in (eg, e1, e1p):
+        e.close()

@@ -718,3 +718,141 @@ def test_cpp_facade_demo_scripts(built):
     # the lid moves down at the prescribed 0.2 m/s: 1 mm per 0.005 s frame
     assert abs((lid[0] - lid[1]) - 0.001) < 2e-5 and abs((lid[1] - lid[2]) - 0.001) < 2e-5, lid
     assert "v_z = 0" in out.stdout.split("Lid after being fixed:")[1]
+
+
+def _single_step_vs_ref_at_full_size(f, warm_steps, label):
+    """ONE step from identical state at a BASELINE configuration's full size, device against the reference's OWN kernel
+    text (oracle/_ref: calculateContactForces + force model + forceToAcc + integrateOwners host-compiled; the C port
+    when _ref is not built).  The device first advances the bed into a contact-rich state; that exact state (position
+    codes, orientations, velocities) and the device's contact list with its history are loaded into the checker; both
+    sides then take one step without a rebuild in between.  Tolerances are those of
+    test_single_step_from_identical_state: |dv| <= 2e-5 max|v| + 1e-7 m/s, |d omega| <= 2e-5 max|omega| + 1e-6 rad/s,
+    position codes equal up to the truncation unit (+ v_tol * h / l), history of touching contacts to 2e-4 relative."""
+    po = _oracle()
+    use_ref = po.ref() is not None
+    if use_ref:
+        import os
+        po.ref_set_threads(os.cpu_count() or 1)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    cd = int(f.cd_update_freq)
+    eng.step(warm_steps - warm_steps % cd + cd // 2)      # the list in use is cd/2 steps old
+    st = eng.owner_state()
+    idA, idB, ct, wc = eng.contacts()
+    n = len(idA)
+    touching_before = int((np.abs(wc).max(1) > 0).sum())
+    print("%s: %d owners, %d listed contacts (%d with history); checker = %s" % (
+        label, f.nOwners, n, touching_before, "reference kernel text (oracle/_ref)" if use_ref else "C port"))
+    assert touching_before > 1000
+    w = po.world_from_flat(f, contact_capacity=n + 16)
+    for name in ("voxelID", "locX", "locY", "locZ"):
+        getattr(w, name)[: f.nOwners] = st[name]
+    for k, name in enumerate(("oriQw", "oriQx", "oriQy", "oriQz")):
+        getattr(w, name)[: f.nOwners] = st["oriQ"][:, k]
+    for k, name in enumerate(("vX", "vY", "vZ")):
+        getattr(w, name)[: f.nOwners] = st["vel"][:, k]
+    for k, name in enumerate(("omgBarX", "omgBarY", "omgBarZ")):
+        getattr(w, name)[: f.nOwners] = st["omg"][:, k]
+    w.idGeometryA[:n], w.idGeometryB[:n], w.contactType[:n] = idA, idB, ct
+    for k in range(4):
+        w.contactWildcards[k][:n] = wc[:, k]
+    w.nContacts = n
+    # one step on each side, no rebuild in between
+    eng.step(1)
+    w.prepare_acc(use_ref)
+    w.calc_forces(use_ref)
+    w.force_to_acc(use_ref)
+    w.integrate(use_ref)
+    g = eng.owner_state()
+    nC = f.nClumps
+    vw = np.stack([w.vX, w.vY, w.vZ], 1)[:nC]
+    ow = np.stack([w.omgBarX, w.omgBarY, w.omgBarZ], 1)[:nC]
+    vtol = 2e-5 * np.abs(vw).max() + 1e-7
+    otol = 2e-5 * max(np.abs(ow).max(), 1.0) + 1e-6
+    dv, do = np.abs(g["vel"][:nC] - vw).max(), np.abs(g["omg"][:nC] - ow).max()
+    print("%s single step at full size: |dv| %.3e (tol %.3e)  |domega| %.3e (tol %.3e)  max|v| %.3f" % (
+        label, dv, vtol, do, otol, np.abs(vw).max()))
+    assert dv <= vtol and do <= otol
+
+    def ints(vox, lx, ly, lz):
+        vx = vox & np.uint64((1 << f.nvXp2) - 1)
+        vy = (vox >> np.uint64(f.nvXp2)) & np.uint64((1 << f.nvYp2) - 1)
+        vz = vox >> np.uint64(f.nvXp2 + f.nvYp2)
+        return np.stack([(vx.astype("i8") << 16) + lx, (vy.astype("i8") << 16) + ly, (vz.astype("i8") << 16) + lz], 1)
+    ig = ints(g["voxelID"][:nC], g["locX"][:nC].astype("i8"), g["locY"][:nC].astype("i8"), g["locZ"][:nC].astype("i8"))
+    iw = ints(w.voxelID[:nC], w.locX[:nC].astype("i8"), w.locY[:nC].astype("i8"), w.locZ[:nC].astype("i8"))
+    unit_tol = max(2, int(vtol * float(f.h) / f.l) + 2)
+    assert np.abs(ig - iw).max() <= unit_tol, (np.abs(ig - iw).max(), unit_tol)
+    qg = g["oriQ"][:nC]
+    qw = np.stack([w.oriQw, w.oriQx, w.oriQy, w.oriQz], 1)[:nC]
+    assert np.abs(qg - qw).max() <= 1e-6
+    # history after the step, contact by contact (vectorised: both lists sorted by (type, A, B))
+    idA2, idB2, ct2, wc2 = eng.contacts()
+    key_g = (ct2.astype("u8") << np.uint64(60)) | (idA2.astype("u8") << np.uint64(30)) | idB2.astype("u8")
+    key_o = (ct.astype("u8") << np.uint64(60)) | (idA.astype("u8") << np.uint64(30)) | idB.astype("u8")
+    wco = np.stack([c[:n] for c in w.contactWildcards], 1)
+    alive = np.abs(wco).max(1) > 0
+    order = np.argsort(key_g, kind="stable")
+    pos = np.searchsorted(key_g[order], key_o[alive])
+    assert (pos < len(order)).all() and (key_g[order][pos] == key_o[alive]).all(), "a touching contact left the device list"
+    got = wc2[order][pos]
+    bad = np.nonzero(~np.isclose(got, wco[alive], rtol=2e-4, atol=1e-9).all(1))[0]
+    # The few pairs beyond 2e-4 are judged against their overlap depth, recomputed here in double from the state both
+    # sides started from: the geometry the two sides work with differs by the rounding of the rotated sphere offsets
+    # (~3e-10 m), and the Coulomb-clamped tangential spring (mu |Fn| t + gamma_t v_t) / (-k_t) -- a difference of nearly
+    # equal terms, k_t ~ depth^(1/2), gamma_n ~ depth^(1/4) -- passes that on amplified.  Allowed: 2e-4 + 1e-8 m / depth;
+    # a pair shallower than 1e-8 m may be seen as "not in touch" by either side.
+    def sphere_centres(ids):
+        own = f.ownerClumpBody[ids]
+        comp = f.clumpComponentOffset[ids]
+        q = st["oriQ"][own].astype("f8")
+        rel = np.stack([f.CDRelPosX[comp], f.CDRelPosY[comp], f.CDRelPosZ[comp]], 1).astype("f8")
+        qw, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        rx = (2 * (qw * qw + qx * qx) - 1) * rel[:, 0] + 2 * (qx * qy - qw * qz) * rel[:, 1] + 2 * (qx * qz + qw * qy) * rel[:, 2]
+        ry = 2 * (qx * qy + qw * qz) * rel[:, 0] + (2 * (qw * qw + qy * qy) - 1) * rel[:, 1] + 2 * (qy * qz - qw * qx) * rel[:, 2]
+        rz = 2 * (qx * qz - qw * qy) * rel[:, 0] + 2 * (qy * qz + qw * qx) * rel[:, 1] + (2 * (qw * qw + qz * qz) - 1) * rel[:, 2]
+        P = ints(st["voxelID"][own], st["locX"][own].astype("i8"), st["locY"][own].astype("i8"), st["locZ"][own].astype("i8")).astype("f8") * f.l
+        return P + np.stack([rx, ry, rz], 1), f.Radii[comp].astype("f8")
+    kk = np.nonzero(alive)[0][bad]
+    ss_bad = ct[kk] == 1
+    depth = np.full(len(bad), 1.0)
+    if ss_bad.any():
+        ca, ra = sphere_centres(idA[kk][ss_bad])
+        cb, rb = sphere_centres(idB[kk][ss_bad])
+        depth[ss_bad] = ra + rb - np.linalg.norm(ca - cb, axis=1)
+    rel = np.abs(got[bad] - wco[alive][bad])[:, :3].max(1) / np.maximum(np.abs(wco[alive][bad][:, :3]).max(1), 1e-30)
+    allowed = np.where(depth < 1e-8, np.inf, 2e-4 + 1e-8 / np.maximum(depth, 1e-30))
+    allowed[~ss_bad] = 5e-3   # (sphere--wall / sphere--facet pairs: no depth recomputed here)
+    hard = np.nonzero(rel > allowed)[0]
+    for i in hard[:10]:
+        k = kk[i]
+        print("  history mismatch: contact (%d, %d, type %d) depth %.3e rel %.2e device %s checker %s before %s" % (
+            idA[k], idB[k], ct[k], depth[i], rel[i], got[bad][i], wco[alive][bad][i], wc[k]))
+    order_d = np.argsort(depth)
+    print("%s: %d of %d touching contacts beyond 2e-4; (depth, relative difference) of a sample: %s" % (
+        label, len(bad), int(alive.sum()), ", ".join("(%.1e, %.1e)" % (depth[i], rel[i]) for i in order_d[:: max(1, len(bad) // 12)])))
+    assert len(hard) == 0, "%d of %d touching contacts differ in history" % (len(hard), int(alive.sum()))
+    assert len(bad) <= 0.01 * alive.sum()
+    assert np.abs(got[:, 3] - wco[alive][:, 3])[np.abs(got[:, :3]).max(1) > 0].max() <= 1e-9   # contact duration
+    print("%s: history of %d touching contacts agrees" % (label, int(alive.sum())))
+    eng.close()
+
+
+def test_config2_full_size_single_step_vs_ref(built):
+    """BASELINE configs[1] (1M three-sphere clumps) at full size against the reference's own kernel text."""
+    sc = scenes.config2_clumps(100, 100, 100, scale=0.005, h=5e-6, cd_update_freq=20, seed=4150, mu=0.2, Crr=0.0, spacing=2.7)
+    n = len(sc.clump_type)
+    rng = np.random.RandomState(3)
+    sc.clump_vel = (rng.normal(size=(n, 3)) * 0.8 + np.array([0.0, 0.0, -1.0])).astype("f4")
+    f = scenes.flatten(sc)
+    assert f.nClumps == 1000000
+    _single_step_vs_ref_at_full_size(f, 3000, "C2")
+
+
+def test_drum_config4_full_size_single_step_vs_ref(built):
+    """BASELINE configs[3] (500k polydisperse clumps in a 50k-facet drum) at full size against the reference's own
+    kernel text (sphere--triangle branch included)."""
+    sc = scenes.config4_drum(500000, 50000, omega=3.0, init_vel=(0.0, 0.0, -1.5), spacing=2.7)
+    f = scenes.flatten(sc)
+    assert f.nClumps == 500000
+    _single_step_vs_ref_at_full_size(f, 1200, "C4")
