@@ -1,10 +1,14 @@
 // run_ref.cpp -- drives the UNMODIFIED reference (projectchrono/DEM-Engine, built by baseline/build_ref.sh into
 // baseline/_ref/build) through its own public API (src/DEM/API.h of the reference) on the scene files bench.py /
-// tools/dump_scene.py write.  Nothing of this repository's engine is linked or called here.
+// tools/run_reference_gpu.py write.  Built twice from this ONE source: baseline/_ref/run_ref links the unmodified reference
+// (baseline/build_ref.sh; nothing of this repository's engine is linked or called there), dem-engine_b200/host/run_b200
+// links this repository's deme::DEMSolver facade instead -- the same script drives both, which is the drop-in claim.
 //
 //   run_ref bench  <scene.bin> <nGPUs> <steps> <warmup_steps> [cd_update_freq (0 = the reference's adaptive default)]
 //       builds the bed, Initialize(), DoDynamicsThenSync(warmup*h), then times DoDynamicsThenSync(steps*h)
 //       (src/DEM/APIPublic.cpp:2446-2479) with a wall clock, as SURVEY.md 8(d) prescribes; prints one JSON line.
+//   run_ref e2e    <scene.bin> <nGPUs> <frames> <warmup_steps> [cd_update_freq]
+//       every frame: DoDynamics(h) (one step), then a tracked clump's Pos / Vel and two inspectors read back to the host
 //   run_ref parity <scene.bin> <steps_per_checkpoint> <n_checkpoints> <out.bin>
 //       the lock-step recipe of DEMdemo_TestPack.cpp:30-45 (SetCDUpdateFreq(0), UseAdaptiveUpdateFreq(false),
 //       DisableAdaptiveBinSize, UseCubForceCollection, jitify of templates off); dumps pos / quat / vel / angvel of
@@ -65,7 +69,7 @@ static bool read_scene(const char* path, SceneFile& s) {
     return ok;
 }
 
-static void build(DEMSolver& sim, const SceneFile& s) {
+static std::shared_ptr<DEMClumpBatch> build(DEMSolver& sim, const SceneFile& s) {
     sim.SetVerbosity(ERR);
     sim.SetOutputFormat(OUTPUT_FORMAT::CSV);
     auto mat = sim.LoadMaterial({{"E", s.E}, {"nu", s.nu}, {"CoR", s.CoR}, {"mu", s.mu}, {"Crr", s.Crr}});
@@ -83,6 +87,7 @@ static void build(DEMSolver& sim, const SceneFile& s) {
     }
     sim.SetInitTimeStep(s.h);
     sim.SetGravitationalAcceleration(make_float3(0, 0, -9.81f));
+    return batch;
 }
 
 int main(int argc, char** argv) {
@@ -122,6 +127,37 @@ int main(int argc, char** argv) {
             fflush(stdout);
             sim.ShowThreadCollaborationStats();
             sim.ShowTimingStats();
+        } else if (mode == "e2e") {
+            // what a co-simulating caller does every step: advance one step, read a tracked body and two inspectors
+            // back to the host (DEMdemo_Mixer.cpp:130-140 polls its inspectors the same way)
+            if (argc < 6) return 2;
+            const int ngpu = atoi(argv[3]);
+            const long frames = atol(argv[4]), warm = atol(argv[5]);
+            const int freq = argc > 6 ? atoi(argv[6]) : 0;
+            DEMSolver sim(ngpu);
+            auto batch = build(sim, s);
+            if (freq > 0) {
+                sim.SetCDUpdateFreq(freq);
+                sim.UseAdaptiveUpdateFreq(false);
+            }
+            auto tracker = sim.Track(batch);
+            auto max_v = sim.CreateInspector("clump_max_absv");
+            auto ke = sim.CreateInspector("clump_kinetic_energy");
+            sim.Initialize();
+            sim.DoDynamicsThenSync((double)warm * (double)s.h);
+            const size_t probe = s.n / 2;
+            double checksum = 0.0;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (long k = 0; k < frames; k++) {
+                sim.DoDynamics((double)s.h);
+                const float3 p = tracker->Pos(probe);
+                const float3 v = tracker->Vel(probe);
+                checksum += (double)p.z + (double)v.z + (double)max_v->GetValue() + (double)ke->GetValue();
+            }
+            const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            printf("{\"impl\": \"deme::DEMSolver API\", \"mode\": \"e2e\", \"n_gpus\": %d, \"clumps\": %u, \"frames\": %ld, \"warmup\": %ld, "
+                   "\"wall_s\": %.6f, \"steps_per_s\": %.3f, \"d2h_bytes_per_step\": 32, \"checksum\": %.9g}\n",
+                   ngpu, s.n, frames, warm, wall, (double)frames / wall, checksum);
         } else if (mode == "parity") {
             if (argc < 6) return 2;
             const long per = atol(argv[3]);

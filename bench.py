@@ -238,8 +238,11 @@ def main():
     ap.add_argument("--spacing", type=float, default=2.7, help="initial lattice spacing in units of the clump scale")
     ap.add_argument("--cpu-clumps", type=int, default=0,
                     help="clumps of the CPU runs (--impl reference and the cpu_baseline leg); 0 = the workload's full size")
-    ap.add_argument("--no-reference-gpu", action="store_true",
-                    help="skip the leg that times the unmodified reference (baseline/_ref) on this box's GPU(s)")
+    ap.add_argument("--reference-gpu", action="store_true",
+                    help="also time the UNMODIFIED reference (baseline/_ref/run_ref) on this box's GPU(s): adds ~15 minutes "
+                         "(its Initialize() of the 1M-clump bed takes ~7 minutes per run); without it the recorded run "
+                         "profiles/reference_gpu_r02.json is quoted")
+    ap.add_argument("--no-facade", action="store_true", help="skip the legs that go through the C++ deme::DEMSolver facade")
     ap.add_argument("--reference-gpu-steps", type=int, default=400)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=200)
@@ -402,26 +405,46 @@ def main():
                                                                     settle_budget_s=25.0)
         line["cpu_baseline"] = {"value": rate * n_cpu / float(args.clumps), "unit": unit, "cores": cores, "kind": kind,
                                 "sample": desc}
-    if not args.no_reference_gpu and world == 1:
-        # the UNMODIFIED reference (DEMSolver(1), and DEMSolver(2) when the box has a second GPU) on the same settled
-        # bed, through its own API: baseline/run_ref.cpp around DoDynamicsThenSync (src/DEM/APIPublic.cpp:2446-2479)
+    if world == 1 and not args.no_facade:
+        # The same bed through the reference's own C++ API: baseline/run_ref.cpp -- the driver script of the reference arm,
+        # UNCHANGED -- compiled against this repository's deme::DEMSolver facade (dem-engine_b200/host/run_b200).
+        #   bench: Initialize(), DoDynamicsThenSync(warm-up), then wall clock around DoDynamicsThenSync(steps * h)
+        #   e2e  : every frame DoDynamics(h), a tracked clump's Pos / Vel and two inspectors read back to the host
         from tools import run_reference_gpu as rr
-        if rr.reference_available():
-            import tempfile
-            path = os.path.join(tempfile.gettempdir(), "dem_c2_settled_rank0.bin")
-            rr.dump_settled_scene(eng, sc, f, path)
-            eng.close()
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), "dem_c2_settled_rank0.bin")
+        rr.dump_settled_scene(eng, sc, f, path)
+        eng.close()
+        exe = os.path.join(ROOT, "dem-engine_b200", "host", "run_b200")
+        fac = {}
+        for mode, n in (("bench", args.steps), ("e2e", args.e2e_steps)):
+            d = rr.run_reference(path, 1, n, 200, cd_update_freq=args.cd_update_freq, timeout=600, exe=exe, mode=mode)
+            d.pop("stats_tail", None)
+            fac[mode] = d
+        line["facade"] = {"driver": "baseline/run_ref.cpp compiled against dem-engine_b200/host (run_b200)",
+                          "DoDynamicsThenSync_steps_per_s": fac["bench"].get("steps_per_s"),
+                          "e2e_steps_per_s": fac["e2e"].get("steps_per_s"), "runs": fac}
+        if args.reference_gpu:
+            # the UNMODIFIED reference (DEMSolver(1), and DEMSolver(2) when the box has a second GPU) on the same settled
+            # bed through the same driver script (baseline/_ref/run_ref); its Initialize() of 1M clumps alone takes ~7
+            # minutes, which is why this leg is opt-in and the recorded run is quoted otherwise
             ref = {}
             for g in (1, 2):
                 if g > torch.cuda.device_count():
                     ref["DEMSolver(%d)" % g] = {"unavailable": "box has %d GPU(s)" % torch.cuda.device_count()}
                     continue
-                d = rr.run_reference(path, g, args.reference_gpu_steps, 100, timeout=600)
+                d = rr.run_reference(path, g, args.reference_gpu_steps, 100, timeout=1500)
                 d.pop("stats_tail", None)
                 ref["DEMSolver(%d)" % g] = d
             line["reference_gpu"] = ref
-        else:
-            line["reference_gpu"] = {"unavailable": "baseline/_ref/run_ref not built"}
+    if "reference_gpu" not in line:
+        try:
+            with open(os.path.join(ROOT, "profiles", "reference_gpu_r02.json")) as fh:
+                rec = json.load(fh)
+            rec["recorded"] = True
+            line["reference_gpu"] = rec
+        except Exception:
+            line["reference_gpu"] = {"unavailable": "not measured in this run (--reference-gpu) and no recorded run under profiles/"}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

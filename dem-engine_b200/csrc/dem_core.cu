@@ -110,6 +110,8 @@ struct DemCtx {
     bool own_stream = true;
     cudaStream_t side = nullptr;   // wall / mesh contact kernels run here, next to the sphere--sphere kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t side2 = nullptr;  // decomposed runs: the halo exchange runs here, next to the integration of the bulk
+    cudaEvent_t ev_fork2 = nullptr, ev_join2 = nullptr;
     int overlap_walls = 1;
     int num_sms = 148;
     std::string err;
@@ -206,15 +208,36 @@ struct DemCtx {
     uint32_t overflow_seen = 0;
     uint32_t seq_host = 0;    // rebuilds enqueued so far == DEM_FLAG_SEQ on the device once they have run
     PendingRebuild pending;
-    // adaptive update frequency (UseAdaptiveUpdateFreq, src/DEM/dT.h:721-752): 0 = fixed at sp.cd_update_freq
-    int adaptive_freq = 0;
+    // Adaptive update frequency (UseAdaptiveUpdateFreq; the reference's tuner is AccumStepUpdater, src/DEM/dT.h:721-752,
+    // dT.cpp:2280-2297: it sizes the drift margin to how many steps dT gets through per kT update).  Here the list is
+    // rebuilt in-stream, so the question is only which frequency costs the least device time per step -- a longer cycle
+    // amortises the rebuild, a shorter one keeps the margin (hence the candidate list the force kernel walks) small.
+    // A hill climb on the measured device time of whole cycles answers it: events recorded at the head of every
+    // rebuild, read back when that rebuild is confirmed (no extra synchronisation).
+    struct FreqTuner {
+        int on = 0;
+        int fmin = 4, fmax = 200;
+        cudaEvent_t ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        uint64_t steps_at[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int freq_at[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        bool valid[8] = {false, false, false, false, false, false, false, false};
+        double acc_us = 0.0;
+        uint64_t acc_steps = 0;
+        int acc_cycles = 0;
+        double prev_us = -1.0;   // us per step measured at the previous frequency
+        int prev_f = 0;
+        int dir = +1;
+        int settled = 0;         // consecutive probes that did not pay: hold the frequency for a while
+        int hold_cycles = 0;
+        uint64_t changes = 0;
+    } tuner;
     // CUDA graph of one whole contact-list cycle (rebuild + cd_update_freq steps): [list buffer][max|v| slot]
     struct CycleGraph {
         cudaGraphExec_t exec = nullptr;
         DevParams P0;        // the parameters the captured kernels were launched with: validity check
         CdParams C0;
         uint32_t L = 0;      // steps in the graph
-        int cfg[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        int cfg[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         uint64_t launches = 0;
     };
     CycleGraph graphs[2][2];
@@ -373,6 +396,8 @@ DevParams make_params(const DemCtx* c) {
         P.active = g.d_flag;
         P.active_list = g.d_active_list[c->cur];
         P.nActivePtr = g.d_counts + 8 * c->cur + 3;
+        P.halo_gid[0] = g.d_send_gid[c->cur][0]; P.halo_gid[1] = g.d_send_gid[c->cur][1];
+        P.halo_counts = g.d_counts + 8 * c->cur;
     }
     P.maxvel = c->d_maxvel + c->maxvel_slot;
     P.maxvel_next = c->d_maxvel + (c->maxvel_slot ^ 1);
@@ -559,6 +584,58 @@ int launch_rebuild_kernels(DemCtx* ctx, cudaEvent_t* sev) {
     return launches;
 }
 
+// adaptive update frequency: time stamp at the head of the rebuild about to be enqueued (sequence number seq_host + 1)
+void tuner_mark(DemCtx* ctx) {
+    DemCtx::FreqTuner& t = ctx->tuner;
+    if (!t.on || ctx->mg.on) return;
+    const uint32_t k = (ctx->seq_host + 1u) & 7u;
+    if (!t.ev[k] && cudaEventCreate(&t.ev[k]) != cudaSuccess) { cudaGetLastError(); return; }
+    cudaEventRecord(t.ev[k], ctx->stream);
+    t.steps_at[k] = ctx->n_steps;
+    t.freq_at[k] = (int)ctx->sp.cd_update_freq;
+    t.valid[k] = true;
+}
+// rebuild `seq` has just been confirmed: the cycle before it (head seq-1 .. head seq) is complete on the device
+void tuner_update(DemCtx* ctx, uint32_t seq) {
+    DemCtx::FreqTuner& t = ctx->tuner;
+    if (!t.on || ctx->mg.on) return;
+    const uint32_t k1 = seq & 7u, k0 = (seq - 1u) & 7u;
+    const int f = (int)ctx->sp.cd_update_freq;
+    if (!t.valid[k0] || !t.valid[k1] || t.freq_at[k0] != f || t.steps_at[k1] <= t.steps_at[k0]) return;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.ev[k0], t.ev[k1]) != cudaSuccess) { cudaGetLastError(); return; }
+    const uint64_t steps = t.steps_at[k1] - t.steps_at[k0];
+    if (steps != (uint64_t)f) return;  // (a partial cycle: a host call asked for a rebuild in between)
+    if (t.hold_cycles > 0) { t.hold_cycles--; return; }
+    t.acc_us += (double)ms * 1000.0;
+    t.acc_steps += steps;
+    if (++t.acc_cycles < 3) return;
+    const double us = t.acc_us / (double)t.acc_steps;
+    t.acc_us = 0.0; t.acc_steps = 0; t.acc_cycles = 0;
+    if (t.prev_us > 0.0 && t.prev_f != f) {
+        if (us > t.prev_us * 0.995) {           // the move did not pay: go back and try the other way later
+            t.dir = -t.dir;
+            t.settled++;
+        } else {
+            t.settled = 0;
+        }
+    }
+    if (t.settled >= 2) {                        // both neighbours are worse: stay, look again after a while
+        t.settled = 0;
+        t.hold_cycles = 100;
+        const int best = (t.prev_us > 0.0 && t.prev_us < us) ? t.prev_f : f;
+        t.prev_us = -1.0;
+        if (best != f) { ctx->sp.cd_update_freq = (uint32_t)best; t.changes++; }
+        return;
+    }
+    t.prev_us = us;
+    t.prev_f = f;
+    const int stepf = std::max(1, f / 6);
+    const int nf = std::min(t.fmax, std::max(t.fmin, f + t.dir * stepf));
+    if (nf != f) { ctx->sp.cd_update_freq = (uint32_t)nf; t.changes++; }
+    else t.dir = -t.dir;
+}
+
 // host bookkeeping of a rebuild that has just been enqueued (plain launches or as the head of a cycle graph)
 void note_rebuild_enqueued(DemCtx* ctx) {
     PendingRebuild& p = ctx->pending;
@@ -642,6 +719,7 @@ int confirm_rebuild(DemCtx* ctx, bool* rolled_back) {
     }
     for (int kind = 0; kind < 4; kind++) ctx->n_list[kind] = r.count[kind];
     ctx->last_grid = r.grid;
+    tuner_update(ctx, r.seq);
     if (ctx->mg.on) memcpy(ctx->mg.last, r.mg, sizeof(r.mg));
     if (r.velflag != 0u) {
         const uint32_t zero = 0;
@@ -663,6 +741,7 @@ int enqueue_rebuild(DemCtx* ctx, float* stage_us = nullptr) {
     if (rolled && !stage_us) return DEM_OK;
     cudaEvent_t sev[10];
     if (stage_us) for (auto& e : sev) cudaEventCreate(&e);
+    tuner_mark(ctx);
     ctx->launches += launch_rebuild_kernels(ctx, stage_us ? sev : nullptr);
     note_rebuild_enqueued(ctx);
     if (stage_us) {
@@ -694,6 +773,14 @@ int rebuild_blocking(DemCtx* ctx, float* stage_us = nullptr) {
     return fail(ctx, DEM_ERR_CAPACITY, "contact list kept overflowing after repeated growth");
 }
 
+// decomposed runs: CTAs of the integrator, from the number of active owners the last confirmed rebuild reported (+15 %,
+// rounded up to a multiple of 64 CTAs: the value only changes when the slab's population does)
+int integrate_grid(const DemCtx* ctx) {
+    if (!ctx->mg.on || ctx->mg.last[3] == 0) return 0;
+    const uint64_t want = ((uint64_t)ctx->mg.last[3] * 115u / 100u + 255u) / 256u;
+    return (int)((want + 63u) / 64u * 64u);
+}
+
 // the kernels of ONE step on ctx->stream (+ side stream); flips the max|v| slot. No bookkeeping, no rebuild.
 int launch_step(DemCtx* ctx) {
     DevParams P = make_params(ctx);
@@ -719,10 +806,23 @@ int launch_step(DemCtx* ctx) {
     } else {
         CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     }
-    // integration; on several GPUs the integrator itself stores the halo records into the neighbours' buffers and
-    // k_mg_pull, next in the stream, publishes the exchange number, waits for theirs and scatters what they stored here
-    launch_integrate(P, ctx->num_sms, ctx->stream);
-    if (ctx->mg.on) ctx->launches += launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, ctx->stream);
+    // integration.  On several GPUs: first the owners in the halo send lists, then -- side by side -- the exchange of
+    // their records with the neighbours (k_mg_exchange: push, publish, wait, pull) and the integration of the rest
+    if (ctx->mg.on) {
+        const int hgrid = (int)(((uint64_t)ctx->mg.last[1] + ctx->mg.last[2]) * 115u / 100u / 256u + 64u) / 64 * 64;
+        launch_integrate_halo(P, hgrid, ctx->stream);
+        cudaStream_t xs = ctx->side2 ? ctx->side2 : ctx->stream;
+        if (xs != ctx->stream) {
+            CK(cudaEventRecord(ctx->ev_fork2, ctx->stream));
+            CK(cudaStreamWaitEvent(xs, ctx->ev_fork2, 0));
+        }
+        ctx->launches += 1 + launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, xs);
+        if (xs != ctx->stream) CK(cudaEventRecord(ctx->ev_join2, xs));
+        launch_integrate(P, integrate_grid(ctx), ctx->stream);
+        if (xs != ctx->stream) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_join2, 0));
+    } else {
+        launch_integrate(P, 0, ctx->stream);
+    }
     ctx->maxvel_slot ^= 1;  // the integrator left max |v| of the new state in the other slot
     ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
     return DEM_OK;
@@ -741,10 +841,10 @@ void note_steps_enqueued(DemCtx* ctx, uint64_t n) {
 // event records and two stream waits: ~20 us), or a decomposed run whose ranks must not drift apart, is captured once per
 // (list buffer, max|v| slot) and replayed with ONE cudaGraphLaunch; the graph stays valid for as long as the kernel
 // parameters are byte-identical.
-void graph_config(const DemCtx* ctx, int cfg[10]) {
+void graph_config(const DemCtx* ctx, int cfg[12]) {
     cfg[0] = (int)ctx->sp.force_model; cfg[1] = (int)ctx->sp.record_contact_forces; cfg[2] = ctx->ctas_per_sm;
     cfg[3] = ctx->fast_math; cfg[4] = ctx->overlap_walls; cfg[5] = (int)ctx->nAnal; cfg[6] = (int)ctx->nTri; cfg[7] = ctx->sa_grid;
-    cfg[8] = ctx->sort_mode; cfg[9] = ctx->key_bits;
+    cfg[8] = ctx->sort_mode; cfg[9] = ctx->key_bits; cfg[10] = integrate_grid(ctx); cfg[11] = ctx->force_opts;
 }
 bool graph_wanted(const DemCtx* ctx) {
     if (ctx->use_graph == 0) return false;
@@ -771,7 +871,7 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
     DemCtx::CycleGraph& G = ctx->graphs[ctx->cur][ctx->maxvel_slot];
     const DevParams P = make_params(ctx);
     const CdParams C = make_cd(ctx);
-    int cfg[10];
+    int cfg[12];
     graph_config(ctx, cfg);
     if (G.exec && (G.L != L || memcmp(&G.P0, &P, sizeof(P)) != 0 || memcmp(&G.C0, &C, sizeof(C)) != 0 ||
                    memcmp(G.cfg, cfg, sizeof(cfg)) != 0)) {
@@ -810,6 +910,7 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
         G.L = L;
         memcpy(G.cfg, cfg, sizeof(cfg));
     }
+    tuner_mark(ctx);
     CK(cudaGraphLaunch(G.exec, ctx->stream));
     ctx->graph_launches++;
     ctx->launches += G.launches;
@@ -1038,6 +1139,9 @@ int dem_ctx_create(DemCtx** out, int device) {
     cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking);
     cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
+    cudaStreamCreateWithFlags(&ctx->side2, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags(&ctx->ev_fork2, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_join2, cudaEventDisableTiming);
     *out = ctx;
     return DEM_OK;
 }
@@ -1080,11 +1184,16 @@ int dem_ctx_destroy(DemCtx* ctx) {
     free_mg(ctx);
     graph_drop(ctx);
     if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+    if (ctx->side2) { cudaStreamSynchronize(ctx->side2); cudaStreamDestroy(ctx->side2); }
+    if (ctx->ev_fork2) cudaEventDestroy(ctx->ev_fork2);
+    if (ctx->ev_join2) cudaEventDestroy(ctx->ev_join2);
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     free_device(ctx);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->h_status) cudaFreeHost(ctx->h_status);
+    for (auto& e : ctx->tuner.ev)
+        if (e) cudaEventDestroy(e);
     for (int k = 0; k < 2; k++) {
         if (ctx->h_famblob[k]) cudaFreeHost(ctx->h_famblob[k]);
         if (ctx->ev_fam[k]) cudaEventDestroy(ctx->ev_fam[k]);
@@ -1731,6 +1840,38 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     return group_broadcast_state(ctx);  // (no-op on a single GPU)
 }
 
+int dem_set_family_material(DemCtx* ctx, uint32_t family, uint32_t material, int meshes) {
+    // SetFamilyClumpMaterial / SetFamilyMeshMaterial (src/DEM/APIPublic.cpp:1597-1604, dT.cpp:2719-2738): every sphere
+    // (meshes != 0: every facet) whose owner is in `family` gets the material.  The compiled contact records carry the
+    // material pair, so the contact list is rebuilt before the next step (history is kept).
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if (family > 255 || material >= ctx->nMat) return fail(ctx, DEM_ERR_INVALID, "dem_set_family_material: bad family or material");
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
+    CK(cudaSetDevice(ctx->device));
+    { int rcs = settle(ctx); if (rcs) return rcs; }
+    std::vector<OwnerState> st(ctx->nOwners);
+    CK(cudaMemcpy(st.data(), ctx->d_state, sizeof(OwnerState) * ctx->nOwners, cudaMemcpyDeviceToHost));
+    std::vector<DemCtx*> all = group_ranks(ctx);
+    for (DemCtx* c : all) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, DEM_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        if (c != ctx) { int rcs = settle(c); if (rcs) return peer_fail(ctx, c, rcs); }
+        if (!meshes) {
+            for (uint32_t i = 0; i < c->nSpheres; i++)
+                if (st[c->h_sph[i].x].pos.family == family) c->h_sph[i].y = (c->h_sph[i].y & 0xffffu) | (material << 16);
+            if (cudaMemcpy(c->d_sph, c->h_sph.data(), sizeof(uint2) * c->nSpheres, cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(ctx, DEM_ERR_CUDA, "dem_set_family_material: upload failed");
+        } else if (c->nTri) {
+            for (uint32_t t = 0; t < c->nTri; t++)
+                if (st[c->h_tri_info[t].x].pos.family == family) c->h_tri_info[t].y = material;
+            if (cudaMemcpy(c->d_tri_info, c->h_tri_info.data(), sizeof(uint2) * c->nTri, cudaMemcpyHostToDevice) != cudaSuccess)
+                return fail(ctx, DEM_ERR_CUDA, "dem_set_family_material: upload failed");
+        }
+        c->need_rebuild = true;
+    }
+    CK(cudaSetDevice(ctx->device));
+    return DEM_OK;
+}
+
 int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n_out, uint32_t* idA, uint32_t* idB, uint8_t* type,
                           float* wildcards4, float* force_xyz) {
     return dem_download_contact_records(ctx, capacity, n_out, idA, idB, type, wildcards4, force_xyz, nullptr);
@@ -1854,6 +1995,7 @@ int dem_get_stats(DemCtx* ctx, DemStats* out) {
     out->sim_time = ctx->sim_time; out->max_margin = ctx->last_grid.max_margin; out->cell_size = ctx->last_grid.cs;
     out->n_cells[0] = ctx->last_grid.nbx; out->n_cells[1] = ctx->last_grid.nby; out->n_cells[2] = ctx->last_grid.nbz;
     out->overflow = ctx->overflow_seen;
+    out->cd_update_freq = ctx->sp.cd_update_freq;
     if (ctx->group_on)  // (contacts across a cut are listed on both sides: the sums count them twice)
         for (DemCtx* pc : ctx->peers) {
             out->n_contacts_ss += pc->n_list[0] + pc->n_list[1]; out->n_contacts_sa += pc->n_list[2]; out->n_contacts_st += pc->n_list[3];
@@ -2206,6 +2348,9 @@ int dem_set_option(DemCtx* ctx, const char* name, double value) {
     else if (n == "keep_acc") ctx->keep_acc = value != 0.0;
     else if (n == "fast_encode") ctx->fast_encode = value != 0.0;
     else if (n == "force_opts") ctx->force_opts = (int)value;
+    else if (n == "adaptive_update_freq") { ctx->tuner.on = value != 0.0; ctx->tuner.prev_us = -1.0; ctx->tuner.acc_cycles = 0; ctx->tuner.acc_us = 0.0; ctx->tuner.acc_steps = 0; }
+    else if (n == "update_freq_min") ctx->tuner.fmin = std::max(1, (int)value);
+    else if (n == "update_freq_max") ctx->tuner.fmax = std::max(ctx->tuner.fmin, (int)value);
     else if (n == "sort_mode") ctx->sort_mode = (int)value;
     else if (n == "overlap_walls") ctx->overlap_walls = value != 0.0;
     else return fail(ctx, DEM_ERR_INVALID, "unknown option '%s'", name);
@@ -2318,10 +2463,11 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
             if (ctx->nTri > 0) launch_force_st(P, model, rec, ctx->sa_grid, s);
             CK(cudaEventRecord(e[3], s));
             // (on several GPUs the integrator also stores the halo records; [5] is the pull, including the wait)
-            launch_integrate(P, ctx->num_sms, s);
+            if (ctx->mg.on) launch_integrate_halo(P, 256, s);
+            launch_integrate(P, integrate_grid(ctx), s);
             ctx->maxvel_slot ^= 1;
             CK(cudaEventRecord(e[4], s));
-            if (ctx->mg.on) ctx->launches += launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, s);
+            if (ctx->mg.on) ctx->launches += 1 + launch_mg_pull(P, make_mgdev(ctx), ctx->cur, ctx->num_sms, s);
             CK(cudaEventRecord(e[5], s));
             ctx->launches += 2 + (ctx->nAnal > 0 ? 1 : 0) + (ctx->nTri > 0 ? 1 : 0);
             note_steps_enqueued(ctx, 1);

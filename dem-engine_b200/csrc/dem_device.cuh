@@ -130,7 +130,7 @@ struct MgDev {
     unsigned long long* epoch;        // exchanges (per-step and per-rebuild alike) completed so far
     unsigned long long* mail_ctr;     // all-gathers completed so far
     uint32_t* block_ctr;              // [0] pull kernel, [1] push kernel: last-block detection
-    uint8_t* flag;                    // per global owner: 0 unknown here, 1 own, 2 ghost
+    uint8_t* flag;                    // per global owner: 0 unknown here, 1 own, 2 ghost, 3 / 4 own + halo (see DevParams::active)
     uint32_t* active_list[2];         // [par] compact list of active owners (own + ghost) of the cycle with parity par
     uint32_t* counts[2];              // [par] {own, send-left, send-right, active, active spheres, -, -, -}
     uint32_t* send_gid[2][2];         // [par][dir] own owners inside the halo of the left / right cut
@@ -172,9 +172,13 @@ struct DevParams {
     Wrench* acc_out;  // optional per-owner {a, alpha} read-out (nullptr = off)
     // domain decomposition (nullptr on a single GPU): per-owner activity flag (0 unknown, 1 own, 2 ghost), the
     // compact list of active owners the integrator walks and its DEVICE-resident length
-    const uint8_t* active;
+    const uint8_t* active;       // 0 unknown here, 1 own, 2 ghost, 3 own + in the left halo list, 4 own + in the right one only
     const uint32_t* active_list;
     const uint32_t* nActivePtr;
+    // the owners this rank sends to its left / right neighbour every step (integrated first, so that the exchange can
+    // run beside the integration of the rest) and their DEVICE-resident counts {-, left, right}
+    const uint32_t* halo_gid[2];
+    const uint32_t* halo_counts;
     // spheres / templates
     const uint2* sph;
     const float4* comp;      // {relx, rely, relz, radius}

@@ -95,7 +95,8 @@ void launch_force_ss(const DevParams& P, int model, bool record, int num_sms, in
 void launch_force_sa(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaStream_t s);
 int launch_cd_triangles(const DevParams& P, const CdParams& C, int stage, int num_sms, cudaStream_t s);
-void launch_integrate(const DevParams& P, int num_sms, cudaStream_t s);
+void launch_integrate(const DevParams& P, int grid_hint, cudaStream_t s);
+void launch_integrate_halo(const DevParams& P, int grid_hint, cudaStream_t s);
 
 // rebuild stages; each returns the number of kernels it launched
 // stage 0: max |v| (when stale); stage 1: grid + margin decision (all-gathers max |v| over the ranks);

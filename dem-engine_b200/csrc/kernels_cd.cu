@@ -1064,7 +1064,7 @@ int launch_cd_sweep(const DevParams& P, const CdParams& C, const MgDev* M, int p
 __global__ void k_reduce(const __grid_constant__ DevParams P, int kind, uint32_t nClumps, double* out) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     double v = (kind == DEM_REDUCE_MIN_Z) ? 1e300 : ((kind == DEM_REDUCE_MAX_Z) ? -1e300 : 0.0);
-    if (o < nClumps && (!P.active || P.active[o] == 1)) {
+    if (o < nClumps && (!P.active || P.active[o] == 1 || P.active[o] >= 3)) {
         const OwnerState st = P.state[o];
         if (kind == DEM_REDUCE_MAX_ABSV) {
             v = sqrtf(st.vel.x * st.vel.x + st.vel.y * st.vel.y + st.vel.z * st.vel.z);
@@ -1126,7 +1126,7 @@ __global__ void __launch_bounds__(256) k_reduce_many(const __grid_constant__ Dev
                                                      double* out) {
     const uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
     double v[5] = {0.0, -1e300, 1e300, 0.0, 0.0};
-    if (o < nClumps && (!P.active || P.active[o] == 1)) {
+    if (o < nClumps && (!P.active || P.active[o] == 1 || P.active[o] >= 3)) {
         const OwnerState st = P.state[o];
         v[DEM_REDUCE_MAX_ABSV] = sqrtf(st.vel.x * st.vel.x + st.vel.y * st.vel.y + st.vel.z * st.vel.z);
         if (mask & ((1u << DEM_REDUCE_MAX_Z) | (1u << DEM_REDUCE_MIN_Z))) {

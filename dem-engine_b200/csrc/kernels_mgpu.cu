@@ -85,7 +85,8 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
                     toR = M.has[1] && (x >= M.cut_hi - halo);
                 }
             }
-            M.flag[g] = own ? 1 : 0;  // ghosts are re-flagged when the neighbour's list arrives
+            // (ghosts are re-flagged when the neighbour's list arrives)
+            M.flag[g] = own ? (toL ? 3 : (toR ? 4 : 1)) : 0;
         }
         const uint32_t sa = warp_append(own, &cnt[3]);
         if (own) M.active_list[par][sa] = g;
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(256) k_mg_gather_owned(const __grid_constant__
                                                          const uint8_t* __restrict__ peer_flag, uint32_t nClumpOwners) {
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nClumpOwners * 5u; t += gridDim.x * blockDim.x) {
         const uint32_t o = t / 5u, part = t - o * 5u;
-        if (peer_flag[o] != 1) continue;
+        if (peer_flag[o] != 1 && peer_flag[o] < 3) continue;  // (1, 3, 4: the peer owns it)
         int4* dst = (part < 4) ? reinterpret_cast<int4*>(P.state + o) + part : reinterpret_cast<int4*>(P.spin + o);
         const int4* src = (part < 4) ? reinterpret_cast<const int4*>(peer_state + o) + part
                                      : reinterpret_cast<const int4*>(peer_spin + o);

@@ -706,27 +706,49 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
     return sqrtf(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
 }
 
+// MODE 0: every owner (single GPU).  Decomposed runs split the step's integration in two so that the halo exchange can
+// run beside the bulk of it: MODE 1 = the owners in this rank's halo send lists (first), MODE 2 = all other active owners
+// (ghosts only have their unused wrench consumed).
+template <int MODE>
 __global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
     if (P.flags[DEM_FLAG_POISON]) return;
     // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
     // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (MODE != 1 && blockIdx.x == 0 && threadIdx.x == 0) {
         *P.maxvel = 0.f;
         P.flags[DEM_FLAG_CYCLE_STEP] += 1u;  // (read by the next step's force kernel: stream order)
     }
     float absv = 0.f;
-    const uint32_t n = P.active_list ? *P.nActivePtr : P.nOwners;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
-        const uint32_t o = P.active_list ? P.active_list[t] : t;
-        float a = 0.f;
-        if (P.active && P.active[o] == 2) {
-            // ghost: its state arrives from the owning rank; only consume the (unused) wrench
-            st_v8(P.wrench + o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
-        } else {
-            a = integrate_one(P, o);
+    if (MODE == 1) {
+        const uint32_t nL = P.halo_counts[1], nR = P.halo_counts[2];
+        for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nL + nR; t += gridDim.x * blockDim.x) {
+            const uint32_t o = (t < nL) ? P.halo_gid[0][t] : P.halo_gid[1][t - nL];
+            if (t >= nL && P.active[o] == 3) continue;  // in both lists: done as a member of the left one
+            const float a = integrate_one(P, o);
+            if (!isfinite(a) || a > P.errOutVel) atomicOr(&P.flags[DEM_FLAG_VELOCITY], 1u);
+            if (isfinite(a)) absv = fmaxf(absv, a);
         }
-        if (!isfinite(a) || a > P.errOutVel) atomicOr(&P.flags[DEM_FLAG_VELOCITY], 1u);
-        if (isfinite(a)) absv = fmaxf(absv, a);
+    } else {
+        const uint32_t n = P.active_list ? *P.nActivePtr : P.nOwners;
+        auto one = [&](uint32_t t) {
+            const uint32_t o = P.active_list ? P.active_list[t] : t;
+            float a = 0.f;
+            const uint32_t role = P.active ? P.active[o] : 1u;
+            if (role == 2u) {
+                // ghost: its state arrives from the owning rank; only consume the (unused) wrench
+                st_v8(P.wrench + o, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+            } else if (MODE == 0 || role == 1u) {
+                a = integrate_one(P, o);
+            }
+            if (!isfinite(a) || a > P.errOutVel) atomicOr(&P.flags[DEM_FLAG_VELOCITY], 1u);
+            if (isfinite(a)) absv = fmaxf(absv, a);
+        };
+        const uint32_t t0 = blockIdx.x * blockDim.x + threadIdx.x;
+        if (MODE == 0) {
+            if (t0 < n) one(t0);  // launched with one thread per owner
+        } else {
+            for (uint32_t t = t0; t < n; t += gridDim.x * blockDim.x) one(t);
+        }
     }
     // non-negative floats order like their bit patterns: integer max in the warp (REDUX), then in the CTA, then ONE
     // atomic per CTA (a per-warp atomic on a single address serialises 30k updates in L2)
@@ -782,14 +804,22 @@ void launch_force_st(const DevParams& P, int model, bool record, int grid, cudaS
     }
 }
 
-void launch_integrate(const DevParams& P, int num_sms, cudaStream_t s) {
+void launch_integrate(const DevParams& P, int grid_hint, cudaStream_t s) {
     const int block = 256;
-    // single GPU: one owner per thread; decomposed: grid-stride over the DEVICE-resident number of active owners
-    // (decomposed: the number of active owners lives on the device; CTAs beyond it return at once, which is cheaper
-    // than making fewer threads walk several owners each: the loads of one owner form a dependent chain)
+    // single GPU: one owner per thread.  Decomposed: the number of active owners lives on the device and the kernel
+    // strides over it; the host sizes the grid from the count the last confirmed rebuild reported (grid_hint, with slack,
+    // in coarse steps so that a captured cycle stays valid) -- one owner per thread then, because the loads of one
+    // owner form a dependent chain, without the thousands of empty CTAs a full-size grid would launch.
     int grid = (int)((P.nOwners + block - 1) / block);
-    (void)num_sms;
-    if (grid > 0) k_integrate<<<grid, block, 0, s>>>(P);
+    if (P.active_list && grid_hint > 0) grid = std::min(grid, grid_hint);
+    if (grid <= 0) return;
+    if (P.active_list && P.halo_counts) k_integrate<2><<<grid, block, 0, s>>>(P);
+    else k_integrate<0><<<grid, block, 0, s>>>(P);
+}
+// decomposed runs, first half of the integration: the owners in the halo send lists
+void launch_integrate_halo(const DevParams& P, int grid_hint, cudaStream_t s) {
+    if (!P.halo_counts) return;
+    k_integrate<1><<<std::max(1, std::min(grid_hint, 1024)), 256, 0, s>>>(P);
 }
 
 }  // namespace demb

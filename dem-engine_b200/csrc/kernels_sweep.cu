@@ -127,7 +127,7 @@ __device__ __forceinline__ uint32_t pair_verdict_near(const DevParams& P, const 
     // the gap has closed by at most k (marginA + marginB) / maxDrift; until then the force kernel skips the pair after
     // reading its 16-byte record -- it cannot overlap, so it contributes nothing (margins include the family extra
     // margin, which only makes the bound more cautious).  A fixed expand factor carries no such promise: always test.
-    if (P.beta < 0.f) {
+    if (P.beta < 0.f && (P.force_opts & 1u)) {
         const float closing = ((me.w - __uint_as_float(myAux.y)) + (ot.w - __uint_as_float(oa.y))) / (float)P.maxDrift;
         const float f = floorf(gap / fmaxf(closing, 1e-30f));
         first = (uint32_t)fminf(fmaxf(f, 0.f), 255.f);
@@ -226,50 +226,14 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
             parity ^= 1u;
             __syncthreads();
             if (valid) {
-                // Pass 1, all lanes in step: the distance test only; a hit sets a bit.  Pass 2: the few hits (same-owner
-                // filter, family rules, which list, history flag, hand-over record) with the lanes converged on "my next
-                // hit" instead of one or two lanes dragging the warp through that code for every hit.
-                uint32_t hits[5];
 #pragma unroll
                 for (int r = 0; r < 5; r++) {
-                    hits[r] = 0u;
                     const uint32_t lo = max(qb[r], pos[r]);
                     const uint32_t hi = min(qe[r], pos[r] + cnt[r]);
-                    for (uint32_t q0 = lo; q0 < hi; q0 += 32u) {
-                        const uint32_t q1 = min(hi, q0 + 32u);
-                        uint32_t m = 0u;
-                        for (uint32_t q = q0; q < q1; q++) {
-                            float d2;
-                            if (pair_near(me, sm.sph[r][q - pos[r]], d2)) m |= 1u << (q - q0);
-                        }
-                        if (q1 == hi && q0 == lo) { hits[r] = m; break; }  // the usual case: at most 32 candidates in the run
-                        // a longer run: handle this stretch of 32 right away
-                        while (m) {
-                            const uint32_t q = q0 + (uint32_t)__ffs(m) - 1u;
-                            m &= m - 1u;
-                            float d2;
-                            const float4 ot = sm.sph[r][q - pos[r]];
-                            pair_near(me, ot, d2);
-                            uint32_t first;
-                            const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[r][q - pos[r]], d2, q, fam_on, myFam,
-                                                                 extraA, want_hist, first);
-                            if (v == 0u) continue;
-                            const uint32_t k = nT + nN;
-                            if (k < SW_K) { mycand[k] = q | (v & ~1u); myfirst[k] = (uint8_t)first; }
-                            if (v & CAND_TOUCH) nT++; else nN++;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int r = 0; r < 5; r++) {
-                    const uint32_t lo = max(qb[r], pos[r]);
-                    uint32_t m = hits[r];
-                    while (m) {
-                        const uint32_t q = lo + (uint32_t)__ffs(m) - 1u;
-                        m &= m - 1u;
-                        float d2;
+                    for (uint32_t q = lo; q < hi; q++) {
                         const float4 ot = sm.sph[r][q - pos[r]];
-                        pair_near(me, ot, d2);
+                        float d2;
+                        if (!pair_near(me, ot, d2)) continue;
                         uint32_t first;
                         const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[r][q - pos[r]], d2, q, fam_on, myFam, extraA,
                                                              want_hist, first);
@@ -292,14 +256,13 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
     }
 }
 
-// write contact (A at sorted position j, B at q) of the new lists
-__device__ __forceinline__ void emit_contact(const DevParams& P, const CdParams& C, uint32_t flags, uint32_t first, uint32_t q,
+// write contact (A at sorted position j, B described by om = sortedMeta[q]) of the new lists
+__device__ __forceinline__ void emit_contact(const DevParams& P, const CdParams& C, uint32_t flags, uint32_t first, const uint4 om,
                                              uint32_t sid, uint32_t ownerA, uint32_t metaA_z, uint32_t& slotT, uint32_t& slotN) {
     const bool touching = (flags & CAND_TOUCH) != 0u;
     const ContactList& L = touching ? P.ss : P.sn;
     const uint32_t slot = touching ? slotT++ : slotN++;
     if (slot >= C.capacity) return;
-    const uint4 om = __ldg(&C.sortedMeta[q]);
     const uint32_t matpair = (metaA_z >> 16) * P.nMat + (om.z >> 16);
     L.idB[slot] = om.y;
     (touching ? C.idA_ss : C.idA_sn)[slot] = sid;
@@ -330,9 +293,13 @@ __global__ void __launch_bounds__(256) k_sweep_fill(const __grid_constant__ DevP
                 const uint4 c4 = cp[k0 >> 2];
                 const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
                 const uint32_t f = fw[k0 >> 2];
+                // (the four gathers are in flight together: the loop is otherwise a chain of dependent loads per thread)
+                uint4 om[4];
+#pragma unroll
+                for (int t = 0; t < 4; t++) om[t] = __ldg(&C.sortedMeta[(k0 + t < n) ? (c[t] & CAND_POS) : j]);
 #pragma unroll
                 for (int t = 0; t < 4; t++)
-                    if (k0 + t < n) emit_contact(P, C, c[t], (f >> (8 * t)) & 0xffu, c[t] & CAND_POS, sid, meta.x, meta.z, slotT, slotN);
+                    if (k0 + t < n) emit_contact(P, C, c[t], (f >> (8 * t)) & 0xffu, om[t], sid, meta.x, meta.z, slotT, slotN);
             }
         } else {
             // more accepted candidates than the hand-over buffer holds: find them again (plain loads)
@@ -346,7 +313,7 @@ __global__ void __launch_bounds__(256) k_sweep_fill(const __grid_constant__ DevP
                     uint32_t first;
                     const uint32_t v = pair_verdict(P, C, me, myAux, __ldg(&C.sortedSph[q]), __ldg(&C.sortedAux[q]), q, fam_on,
                                                     meta.w, extraA, want_hist, first);
-                    if (v) emit_contact(P, C, v, first, q, sid, meta.x, meta.z, slotT, slotN);
+                    if (v) emit_contact(P, C, v, first, __ldg(&C.sortedMeta[q]), sid, meta.x, meta.z, slotT, slotN);
                 }
         }
     }

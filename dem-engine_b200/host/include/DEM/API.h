@@ -319,7 +319,7 @@ class DEMSolver {
     size_t GetDeviceMemUsageKinematic() const { return 0; }  // one context does both jobs here
     /// Owner ids of the clumps in (potential) contact with the given owner
     std::vector<bodyID_t> GetOwnerContactClumps(bodyID_t ownerID) const;
-    float GetUpdateFreq() const { return (float)m_cd_update_freq; }
+    float GetUpdateFreq() const;
     bool GetInitStatus() const { return sys_initialized; }
 
     void SetCDUpdateFreq(int freq);
@@ -348,14 +348,16 @@ class DEMSolver {
     void SetCollectAccRightAfterForceCalc(bool = true) {}
     void UseAdaptiveBinSize(bool = true) {}
     void DisableAdaptiveBinSize() {}
-    void UseAdaptiveUpdateFreq(bool = true) {}
+    /// let the solver pick the steps per contact-list cycle (on by default, as in the reference; SetCDUpdateFreq gives the
+    /// starting point, SetCDMaxUpdateFreq the upper bound)
+    void UseAdaptiveUpdateFreq(bool flag = true);
     void DisableAdaptiveUpdateFreq() {}
     void SetAdaptiveBinSizeDelaySteps(unsigned int) {}
     void SetAdaptiveBinSizeMaxRate(float) {}
     void SetAdaptiveBinSizeAcc(float) {}
     void SetAdaptiveBinSizeUpperProactivity(float) {}
     void SetAdaptiveBinSizeLowerProactivity(float) {}
-    void SetCDMaxUpdateFreq(unsigned int) {}
+    void SetCDMaxUpdateFreq(unsigned int max_freq);
     void SetCDNumStepsMaxDriftAheadOfAvg(float) {}
     void SetCDNumStepsMaxDriftMultipleOfAvg(float) {}
     void SetCDNumStepsMaxDriftHistorySize(unsigned int) {}
@@ -414,6 +416,11 @@ class DEMSolver {
     void DisableContactBetweenFamilies(unsigned int ID1, unsigned int ID2);
     void EnableContactBetweenFamilies(unsigned int ID1, unsigned int ID2);
     void SetFamilyFixed(unsigned int ID);
+    /// all clumps (meshes) of family N take the material (after Initialize; src/DEM/API.h, APIPublic.cpp:1597-1604)
+    void SetFamilyClumpMaterial(unsigned int N, const std::shared_ptr<DEMMaterial>& mat);
+    void SetFamilyMeshMaterial(unsigned int N, const std::shared_ptr<DEMMaterial>& mat);
+    /// (the reference re-compiles its kernels with line numbers in error messages; nothing is compiled at run time here)
+    void EnsureKernelErrMsgLineNum(bool flag = true) { (void)flag; }
     void SetFamilyPrescribedLinVel(unsigned int ID, const std::string& velX, const std::string& velY,
                                    const std::string& velZ, bool dictate = true);
     void SetFamilyPrescribedAngVel(unsigned int ID, const std::string& velX, const std::string& velY,
@@ -517,19 +524,21 @@ class DEMSolver {
                                  std::vector<float3>& forces) const;
 
     // raw owner access used by trackers (src/DEM/dT.cpp:3062-3130)
-    float3 GetOwnerPosition(bodyID_t ownerID) const;
-    float3 GetOwnerVelocity(bodyID_t ownerID) const;
-    float3 GetOwnerAngVel(bodyID_t ownerID) const;
-    float4 GetOwnerOriQ(bodyID_t ownerID) const;
-    float3 GetOwnerAcc(bodyID_t ownerID) const;
-    float3 GetOwnerAngAcc(bodyID_t ownerID) const;
-    unsigned int GetOwnerFamily(bodyID_t ownerID) const;
-    float GetOwnerMass(bodyID_t ownerID) const;
-    float3 GetOwnerMOI(bodyID_t ownerID) const;
-    void SetOwnerPosition(bodyID_t ownerID, float3 pos);
-    void SetOwnerVelocity(bodyID_t ownerID, float3 vel);
-    void SetOwnerAngVel(bodyID_t ownerID, float3 angVel);
-    void SetOwnerOriQ(bodyID_t ownerID, float4 oriQ);
+    /// state of n consecutive owners starting at ownerID (src/DEM/API.h:431-458 of the reference)
+    std::vector<float3> GetOwnerPosition(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float3> GetOwnerVelocity(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float3> GetOwnerAngVel(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float4> GetOwnerOriQ(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float3> GetOwnerAcc(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float3> GetOwnerAngAcc(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<unsigned int> GetOwnerFamily(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float> GetOwnerMass(bodyID_t ownerID, bodyID_t n = 1) const;
+    std::vector<float3> GetOwnerMOI(bodyID_t ownerID, bodyID_t n = 1) const;
+    /// set the state of consecutive owners starting at ownerID, one per element (src/DEM/API.h:460-471)
+    void SetOwnerPosition(bodyID_t ownerID, const std::vector<float3>& pos);
+    void SetOwnerVelocity(bodyID_t ownerID, const std::vector<float3>& vel);
+    void SetOwnerAngVel(bodyID_t ownerID, const std::vector<float3>& angVel);
+    void SetOwnerOriQ(bodyID_t ownerID, const std::vector<float4>& oriQ);
     void SetOwnerFamily(bodyID_t ownerID, unsigned int fam);
     double Reduce(int kind) const;
     DemCtx* GetCoreContext() const { return ctx; }
@@ -565,6 +574,8 @@ class DEMSolver {
     float3 G = make_float3(0, 0, -9.81f);
     double m_ts_size = 1e-5;
     int m_cd_update_freq = 20;
+    bool m_adaptive_update_freq = true;
+    unsigned int m_max_update_freq = 200;
     TIME_INTEGRATOR m_integrator = TIME_INTEGRATOR::EXTENDED_TAYLOR;
     FORCE_MODEL m_force_model = FORCE_MODEL::HERTZIAN;
     float m_expand_factor = -1.f;

@@ -2,6 +2,9 @@
 // (counterpart of src/kernel/CUDAMathHelpers.cuh + src/DEM/HostSideHelpers.hpp of the reference, host side only).
 #pragma once
 #include <cmath>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #include <vector_functions.h>
@@ -42,5 +45,37 @@ inline float4 QuatFromAxisAngle(const float3& axis, const float& theta) {
     Q.z = axis.z * sinf(theta / 2);
     Q.w = cosf(theta / 2);
     return Q;
+}
+/// applyOriQToVector3 (src/kernel/DEMHelperKernels.cuh:161-173): rotate (X, Y, Z) in place by the quaternion (w, x, y, z)
+template <typename T1, typename T2>
+inline void applyOriQToVector3(T1& X, T1& Y, T1& Z, const T2& Qw, const T2& Qx, const T2& Qy, const T2& Qz) {
+    const T1 oldX = X, oldY = Y, oldZ = Z;
+    X = ((T2)2.0 * (Qw * Qw + Qx * Qx) - (T2)1.0) * oldX + ((T2)2.0 * (Qx * Qy - Qw * Qz)) * oldY + ((T2)2.0 * (Qx * Qz + Qw * Qy)) * oldZ;
+    Y = ((T2)2.0 * (Qx * Qy + Qw * Qz)) * oldX + ((T2)2.0 * (Qw * Qw + Qy * Qy) - (T2)1.0) * oldY + ((T2)2.0 * (Qy * Qz - Qw * Qx)) * oldZ;
+    Z = ((T2)2.0 * (Qx * Qz - Qw * Qy)) * oldX + ((T2)2.0 * (Qy * Qz + Qw * Qx)) * oldY + ((T2)2.0 * (Qw * Qw + Qz * Qz) - (T2)1.0) * oldZ;
+}
+/// Rotate pos by rot_Q, then translate by vec (src/DEM/HostSideHelpers.hpp:563-569)
+template <typename T1, typename T2, typename T3>
+inline void applyFrameTransformLocalToGlobal(T1& pos, const T2& vec, const T3& rot_Q) {
+    applyOriQToVector3(pos.x, pos.y, pos.z, rot_Q.w, rot_Q.x, rot_Q.y, rot_Q.z);
+    pos.x += vec.x;
+    pos.y += vec.y;
+    pos.z += vec.z;
+}
+/// Translate by -vec, then rotate by the inverse of rot_Q (src/DEM/HostSideHelpers.hpp:608-614)
+template <typename T1, typename T2, typename T3>
+inline void applyFrameTransformGlobalToLocal(T1& pos, const T2& vec, const T3& rot_Q) {
+    pos.x -= vec.x;
+    pos.y -= vec.y;
+    pos.z -= vec.z;
+    applyOriQToVector3(pos.x, pos.y, pos.z, rot_Q.w, -rot_Q.x, -rot_Q.y, -rot_Q.z);
+}
+/// Decimal rendering with n digits after the point (src/DEM/HostSideHelpers.hpp:637-648)
+inline std::string to_string_with_precision(const double a_value, const unsigned int n = 17) {
+    std::string out(330 + n, '\0');
+    const int len = std::snprintf(&out[0], out.size(), "%.*f", (int)n, a_value);
+    if (len < 0 || (size_t)len >= out.size()) throw std::runtime_error("to_string_with_precision: value cannot be rendered");
+    out.resize((size_t)len);
+    return out;
 }
 }  // namespace deme

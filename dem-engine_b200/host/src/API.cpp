@@ -247,6 +247,20 @@ void DEMSolver::SetCDUpdateFreq(int freq) {
     // SetCDUpdateFreq(0) is the reference's lock-step mode: rebuild before every step
     m_cd_update_freq = std::max(1, freq);
 }
+float DEMSolver::GetUpdateFreq() const {
+    if (!sys_initialized) return (float)m_cd_update_freq;
+    DemStats st;
+    dem_get_stats(ctx, &st);
+    return (float)st.cd_update_freq;
+}
+void DEMSolver::UseAdaptiveUpdateFreq(bool flag) {
+    m_adaptive_update_freq = flag;
+    if (sys_initialized) check(dem_set_option(ctx, "adaptive_update_freq", flag ? 1.0 : 0.0), "UseAdaptiveUpdateFreq");
+}
+void DEMSolver::SetCDMaxUpdateFreq(unsigned int max_freq) {
+    m_max_update_freq = std::max(1u, max_freq);
+    if (sys_initialized) check(dem_set_option(ctx, "update_freq_max", (double)m_max_update_freq), "SetCDMaxUpdateFreq");
+}
 void DEMSolver::SetIntegrator(const std::string& intg) {
     const std::string u = upper(intg);
     if (u == "FORWARD_EULER") m_integrator = TIME_INTEGRATOR::FORWARD_EULER;
@@ -526,8 +540,8 @@ void DEMSolver::WriteMeshFile(const std::filesystem::path& outfilename) const {
     for (const auto& m : m_cached_meshes) { nV += m->m_vertices.size(); nF += m->nTri; }
     f << "# vtk DataFile Version 2.0\nmeshes\nASCII\nDATASET UNSTRUCTURED_GRID\nPOINTS " << nV << " float\n";
     for (const auto& m : m_cached_meshes) {
-        const float3 p = GetOwnerPosition(m->owner);
-        const float4 q = GetOwnerOriQ(m->owner);
+        const float3 p = GetOwnerPosition(m->owner)[0];
+        const float4 q = GetOwnerOriQ(m->owner)[0];
         for (const auto& v : m->m_vertices) {
             const float3 w = Rotate(v, q) + p;
             f << w.x << " " << w.y << " " << w.z << "\n";
@@ -571,6 +585,14 @@ void DEMSolver::SetFamilyFixed(unsigned int ID) {
     p.rotPosP = true;
     if (sys_initialized) uploadFamilies();
 }
+void DEMSolver::SetFamilyClumpMaterial(unsigned int N, const std::shared_ptr<DEMMaterial>& mat) {
+    assertInit("SetFamilyClumpMaterial");
+    check(dem_set_family_material(ctx, N, mat->load_order, 0), "SetFamilyClumpMaterial");
+}
+void DEMSolver::SetFamilyMeshMaterial(unsigned int N, const std::shared_ptr<DEMMaterial>& mat) {
+    assertInit("SetFamilyMeshMaterial");
+    check(dem_set_family_material(ctx, N, mat->load_order, 1), "SetFamilyMeshMaterial");
+}
 void DEMSolver::SetFamilyPrescribedLinVel(unsigned int ID, const std::string& velX, const std::string& velY,
                                           const std::string& velZ, bool dictate) {
     if (ID > 255) fail("Family numbers must not exceed 255.");
@@ -579,7 +601,11 @@ void DEMSolver::SetFamilyPrescribedLinVel(unsigned int ID, const std::string& ve
     const std::string* s[3] = {&velX, &velY, &velZ};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinVel[k])) { p.hasLinVel[k] = true; p.linVel[k] = v; p.linVelP[k] = dictate; }
+        // (src/DEM/APIPublic.cpp:1027-1047: with dictate, a linear-velocity prescription also holds the rotation -- and a
+        // component given a formula is dictated in any case; several prescriptions of one family add up, APIPrivate.cpp:898-908)
+        p.linVelP[k] = p.linVelP[k] || dictate;
+        p.rotVelP[k] = p.rotVelP[k] || dictate;
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinVel[k])) { p.hasLinVel[k] = true; p.linVel[k] = v; p.linVelP[k] = true; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -591,7 +617,10 @@ void DEMSolver::SetFamilyPrescribedAngVel(unsigned int ID, const std::string& ve
     const std::string* s[3] = {&velX, &velY, &velZ};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eRotVel[k])) { p.hasRotVel[k] = true; p.rotVel[k] = v; p.rotVelP[k] = dictate; }
+        // (src/DEM/APIPublic.cpp:1129-1150: with dictate, an angular-velocity prescription also holds the linear motion)
+        p.rotVelP[k] = p.rotVelP[k] || dictate;
+        p.linVelP[k] = p.linVelP[k] || dictate;
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eRotVel[k])) { p.hasRotVel[k] = true; p.rotVel[k] = v; p.rotVelP[k] = true; }
     }
     if (sys_initialized) uploadFamilies();
 }
@@ -603,8 +632,11 @@ void DEMSolver::SetFamilyPrescribedPosition(unsigned int ID, const std::string& 
     const std::string* s[3] = {&X, &Y, &Z};
     for (int k = 0; k < 3; k++) {
         float v;
-        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinPos[k])) { p.hasLinPos[k] = true; p.linPos[k] = v; p.linPosP[k] = dictate; }
+        // (src/DEM/APIPublic.cpp:1232-1250: with dictate, a position prescription also dictates the orientation)
+        p.linPosP[k] = p.linPosP[k] || dictate;
+        if (parse_prescription(*s[k], simTimeOrZero(), v, p.eLinPos[k])) { p.hasLinPos[k] = true; p.linPos[k] = v; p.linPosP[k] = true; }
     }
+    p.rotPosP = p.rotPosP || dictate;
     if (sys_initialized) uploadFamilies();
 }
 void DEMSolver::AddFamilyPrescribedAcc(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z) {
@@ -648,7 +680,8 @@ void DEMSolver::SetFamilyPrescribedQuaternion(unsigned int ID, const std::string
         fail("SetFamilyPrescribedQuaternion: a quaternion FORMULA is C++ code the reference compiles at run time; this "
              "ahead-of-time compiled core only supports the dictated form (no formula): set the orientation through a "
              "tracker, or prescribe the angular velocity instead.");
-    if (dictate) markPrescribed(ID, 3, 7);
+    // (src/DEM/APIPublic.cpp:1328-1332: with dictate, the linear position is dictated as well)
+    if (dictate) { markPrescribed(ID, 3, 7); markPrescribed(ID, 2, 7); }
 }
 void DEMSolver::ChangeFamilyWhen(unsigned int, unsigned int, const std::string&) {
     fail("ChangeFamilyWhen: condition strings need runtime compilation, which this ahead-of-time compiled core does "
@@ -909,6 +942,8 @@ void DEMSolver::Initialize(bool dry_run) {
     check(dem_upload_triangles(ctx, (uint32_t)triOwner.size(), triOwner.data(), tn1.data(), tn2.data(), tn3.data(), triMat.data()),
           "dem_upload_triangles");
     check(dem_initialize(ctx, 0), "dem_initialize");
+    check(dem_set_option(ctx, "update_freq_max", (double)m_max_update_freq), "SetCDMaxUpdateFreq");
+    check(dem_set_option(ctx, "adaptive_update_freq", m_adaptive_update_freq ? 1.0 : 0.0), "UseAdaptiveUpdateFreq");
     nOwnerClumps = nC; nOwnerBodies = nO; nSpheres = sph_owner.size();
     m_sphere_owner = sph_owner;
     m_tri_owner = triOwner;
@@ -1103,70 +1138,99 @@ void DEMSolver::ShowMemStats() const {
     std::cout << "Device memory held by the DEM core: " << s.device_bytes / (1024.0 * 1024.0) << " MiB" << std::endl;
 }
 
-// ---- raw owner access ----
-#define OWNER_GET(...)                                                                                      \
-    assertInit("owner query");                                                                              \
-    if (ownerID >= nOwnerBodies) fail("owner ID out of range");                                             \
-    check(dem_download_owner_state(ctx, ownerID, 1, __VA_ARGS__), "dem_download_owner_state")
+// ---- raw owner access: n consecutive owners per call (src/DEM/API.h:431-471, dT.cpp:3062-3130 of the reference) ----
+namespace {
+std::vector<float3> to_float3(const std::vector<float>& v) {
+    std::vector<float3> out(v.size() / 3);
+    for (size_t i = 0; i < out.size(); i++) out[i] = make_float3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+    return out;
+}
+}  // namespace
+#define OWNER_RANGE(what)                                                                       \
+    assertInit(what);                                                                           \
+    if ((size_t)ownerID + n > nOwnerBodies || n == 0) fail(std::string(what) + ": owner range out of bounds")
 
-float3 DEMSolver::GetOwnerPosition(bodyID_t ownerID) const {
-    assertInit("owner query");
-    if (ownerID >= nOwnerBodies) fail("owner ID out of range");
-    float p[3];
-    check(dem_download_positions(ctx, ownerID, 1, p, nullptr), "dem_download_positions");
-    return make_float3(p[0], p[1], p[2]);
+std::vector<float3> DEMSolver::GetOwnerPosition(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerPosition");
+    std::vector<float> p(3 * (size_t)n);
+    check(dem_download_positions(ctx, ownerID, n, p.data(), nullptr), "dem_download_positions");
+    return to_float3(p);
 }
-float3 DEMSolver::GetOwnerVelocity(bodyID_t ownerID) const {
-    float v[3];
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr, nullptr, nullptr);
-    return make_float3(v[0], v[1], v[2]);
+std::vector<float3> DEMSolver::GetOwnerVelocity(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerVelocity");
+    std::vector<float> v(3 * (size_t)n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, nullptr, v.data(), nullptr, nullptr, nullptr, nullptr), "dem_download_owner_state");
+    return to_float3(v);
 }
-float3 DEMSolver::GetOwnerAngVel(bodyID_t ownerID) const {
-    float v[3];
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr, nullptr);
-    return make_float3(v[0], v[1], v[2]);
+std::vector<float3> DEMSolver::GetOwnerAngVel(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerAngVel");
+    std::vector<float> v(3 * (size_t)n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v.data(), nullptr, nullptr, nullptr), "dem_download_owner_state");
+    return to_float3(v);
 }
-float4 DEMSolver::GetOwnerOriQ(bodyID_t ownerID) const {
-    float q[4];
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, q, nullptr, nullptr, nullptr, nullptr, nullptr);
-    return make_float4(q[1], q[2], q[3], q[0]);  // core stores w,x,y,z; the API speaks x,y,z,w
+std::vector<float4> DEMSolver::GetOwnerOriQ(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerOriQ");
+    std::vector<float> q(4 * (size_t)n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, q.data(), nullptr, nullptr, nullptr, nullptr, nullptr), "dem_download_owner_state");
+    std::vector<float4> out(n);
+    for (size_t i = 0; i < out.size(); i++)  // core stores w,x,y,z; the API speaks x,y,z,w
+        out[i] = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);
+    return out;
 }
-float3 DEMSolver::GetOwnerAcc(bodyID_t ownerID) const {
-    float v[3];
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr, nullptr);
-    return make_float3(v[0], v[1], v[2]);
+std::vector<float3> DEMSolver::GetOwnerAcc(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerAcc");
+    std::vector<float> v(3 * (size_t)n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v.data(), nullptr, nullptr), "dem_download_owner_state");
+    return to_float3(v);
 }
-float3 DEMSolver::GetOwnerAngAcc(bodyID_t ownerID) const {
-    float v[3];
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v, nullptr);
-    return make_float3(v[0], v[1], v[2]);
+std::vector<float3> DEMSolver::GetOwnerAngAcc(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerAngAcc");
+    std::vector<float> v(3 * (size_t)n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, v.data(), nullptr), "dem_download_owner_state");
+    return to_float3(v);
 }
-unsigned int DEMSolver::GetOwnerFamily(bodyID_t ownerID) const {
-    uint8_t f;
-    OWNER_GET(nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &f);
-    return f;
+std::vector<unsigned int> DEMSolver::GetOwnerFamily(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerFamily");
+    std::vector<uint8_t> f(n);
+    check(dem_download_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, f.data()), "dem_download_owner_state");
+    return std::vector<unsigned int>(f.begin(), f.end());
 }
-float DEMSolver::GetOwnerMass(bodyID_t ownerID) const { return m_owner_mass.at(ownerID); }
-float3 DEMSolver::GetOwnerMOI(bodyID_t ownerID) const { return m_owner_moi.at(ownerID); }
-void DEMSolver::SetOwnerPosition(bodyID_t ownerID, float3 pos) {
+std::vector<float> DEMSolver::GetOwnerMass(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerMass");
+    return std::vector<float>(m_owner_mass.begin() + ownerID, m_owner_mass.begin() + ownerID + n);
+}
+std::vector<float3> DEMSolver::GetOwnerMOI(bodyID_t ownerID, bodyID_t n) const {
+    OWNER_RANGE("GetOwnerMOI");
+    return std::vector<float3>(m_owner_moi.begin() + ownerID, m_owner_moi.begin() + ownerID + n);
+}
+namespace {
+std::vector<float> flat3(const std::vector<float3>& v) {
+    std::vector<float> out(3 * v.size());
+    for (size_t i = 0; i < v.size(); i++) { out[3 * i] = v[i].x; out[3 * i + 1] = v[i].y; out[3 * i + 2] = v[i].z; }
+    return out;
+}
+}  // namespace
+void DEMSolver::SetOwnerPosition(bodyID_t ownerID, const std::vector<float3>& pos) {
     assertInit("SetOwnerPosition");
-    const float p[3] = {pos.x, pos.y, pos.z};
-    check(dem_upload_owner_state(ctx, ownerID, 1, p, nullptr, nullptr, nullptr, nullptr), "dem_upload_owner_state");
+    if (pos.empty()) return;
+    check(dem_upload_owner_state(ctx, ownerID, (uint32_t)pos.size(), flat3(pos).data(), nullptr, nullptr, nullptr, nullptr), "dem_upload_owner_state");
 }
-void DEMSolver::SetOwnerVelocity(bodyID_t ownerID, float3 vel) {
+void DEMSolver::SetOwnerVelocity(bodyID_t ownerID, const std::vector<float3>& vel) {
     assertInit("SetOwnerVelocity");
-    const float p[3] = {vel.x, vel.y, vel.z};
-    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, p, nullptr, nullptr), "dem_upload_owner_state");
+    if (vel.empty()) return;
+    check(dem_upload_owner_state(ctx, ownerID, (uint32_t)vel.size(), nullptr, nullptr, flat3(vel).data(), nullptr, nullptr), "dem_upload_owner_state");
 }
-void DEMSolver::SetOwnerAngVel(bodyID_t ownerID, float3 angVel) {
+void DEMSolver::SetOwnerAngVel(bodyID_t ownerID, const std::vector<float3>& angVel) {
     assertInit("SetOwnerAngVel");
-    const float p[3] = {angVel.x, angVel.y, angVel.z};
-    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, nullptr, p, nullptr), "dem_upload_owner_state");
+    if (angVel.empty()) return;
+    check(dem_upload_owner_state(ctx, ownerID, (uint32_t)angVel.size(), nullptr, nullptr, nullptr, flat3(angVel).data(), nullptr), "dem_upload_owner_state");
 }
-void DEMSolver::SetOwnerOriQ(bodyID_t ownerID, float4 oriQ) {
+void DEMSolver::SetOwnerOriQ(bodyID_t ownerID, const std::vector<float4>& oriQ) {
     assertInit("SetOwnerOriQ");
-    const float q[4] = {oriQ.w, oriQ.x, oriQ.y, oriQ.z};
-    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, q, nullptr, nullptr, nullptr), "dem_upload_owner_state");
+    if (oriQ.empty()) return;
+    std::vector<float> q(4 * oriQ.size());
+    for (size_t i = 0; i < oriQ.size(); i++) { q[4 * i] = oriQ[i].w; q[4 * i + 1] = oriQ[i].x; q[4 * i + 2] = oriQ[i].y; q[4 * i + 3] = oriQ[i].z; }
+    check(dem_upload_owner_state(ctx, ownerID, (uint32_t)oriQ.size(), nullptr, q.data(), nullptr, nullptr, nullptr), "dem_upload_owner_state");
 }
 void DEMSolver::SetOwnerFamily(bodyID_t ownerID, unsigned int fam) {
     assertInit("SetOwnerFamily");
@@ -1194,19 +1258,19 @@ bodyID_t DEMTracker::GetOwnerID(size_t offset) {
     if (offset >= count()) fail("Tracker offset exceeds the number of owners it tracks.");
     return first() + (bodyID_t)offset;
 }
-float3 DEMTracker::Pos(size_t offset) { return sys->GetOwnerPosition(GetOwnerID(offset)); }
-float3 DEMTracker::Vel(size_t offset) { return sys->GetOwnerVelocity(GetOwnerID(offset)); }
-float3 DEMTracker::AngVelLocal(size_t offset) { return sys->GetOwnerAngVel(GetOwnerID(offset)); }
+float3 DEMTracker::Pos(size_t offset) { return sys->GetOwnerPosition(GetOwnerID(offset))[0]; }
+float3 DEMTracker::Vel(size_t offset) { return sys->GetOwnerVelocity(GetOwnerID(offset))[0]; }
+float3 DEMTracker::AngVelLocal(size_t offset) { return sys->GetOwnerAngVel(GetOwnerID(offset))[0]; }
 float3 DEMTracker::AngVelGlobal(size_t offset) {
     const bodyID_t id = GetOwnerID(offset);
-    return Rotate(sys->GetOwnerAngVel(id), sys->GetOwnerOriQ(id));
+    return Rotate(sys->GetOwnerAngVel(id)[0], sys->GetOwnerOriQ(id)[0]);
 }
-float4 DEMTracker::OriQ(size_t offset) { return sys->GetOwnerOriQ(GetOwnerID(offset)); }
-float3 DEMTracker::ContactAcc(size_t offset) { return sys->GetOwnerAcc(GetOwnerID(offset)); }
-float3 DEMTracker::ContactAngAccLocal(size_t offset) { return sys->GetOwnerAngAcc(GetOwnerID(offset)); }
-float DEMTracker::Mass(size_t offset) { return sys->GetOwnerMass(GetOwnerID(offset)); }
-float3 DEMTracker::MOI(size_t offset) { return sys->GetOwnerMOI(GetOwnerID(offset)); }
-unsigned int DEMTracker::GetFamily(size_t offset) { return sys->GetOwnerFamily(GetOwnerID(offset)); }
+float4 DEMTracker::OriQ(size_t offset) { return sys->GetOwnerOriQ(GetOwnerID(offset))[0]; }
+float3 DEMTracker::ContactAcc(size_t offset) { return sys->GetOwnerAcc(GetOwnerID(offset))[0]; }
+float3 DEMTracker::ContactAngAccLocal(size_t offset) { return sys->GetOwnerAngAcc(GetOwnerID(offset))[0]; }
+float DEMTracker::Mass(size_t offset) { return sys->GetOwnerMass(GetOwnerID(offset))[0]; }
+float3 DEMTracker::MOI(size_t offset) { return sys->GetOwnerMOI(GetOwnerID(offset))[0]; }
+unsigned int DEMTracker::GetFamily(size_t offset) { return sys->GetOwnerFamily(GetOwnerID(offset))[0]; }
 std::vector<float3> DEMTracker::Positions() {
     std::vector<float3> out;
     for (size_t i = 0; i < count(); i++) out.push_back(Pos(i));
@@ -1217,10 +1281,10 @@ std::vector<float3> DEMTracker::Velocities() {
     for (size_t i = 0; i < count(); i++) out.push_back(Vel(i));
     return out;
 }
-void DEMTracker::SetPos(float3 pos, size_t offset) { sys->SetOwnerPosition(GetOwnerID(offset), pos); }
-void DEMTracker::SetVel(float3 vel, size_t offset) { sys->SetOwnerVelocity(GetOwnerID(offset), vel); }
-void DEMTracker::SetAngVel(float3 angVel, size_t offset) { sys->SetOwnerAngVel(GetOwnerID(offset), angVel); }
-void DEMTracker::SetOriQ(float4 oriQ, size_t offset) { sys->SetOwnerOriQ(GetOwnerID(offset), oriQ); }
+void DEMTracker::SetPos(float3 pos, size_t offset) { sys->SetOwnerPosition(GetOwnerID(offset), std::vector<float3>{pos}); }
+void DEMTracker::SetVel(float3 vel, size_t offset) { sys->SetOwnerVelocity(GetOwnerID(offset), std::vector<float3>{vel}); }
+void DEMTracker::SetAngVel(float3 angVel, size_t offset) { sys->SetOwnerAngVel(GetOwnerID(offset), std::vector<float3>{angVel}); }
+void DEMTracker::SetOriQ(float4 oriQ, size_t offset) { sys->SetOwnerOriQ(GetOwnerID(offset), std::vector<float4>{oriQ}); }
 void DEMTracker::SetFamily(unsigned int fam_num, size_t offset) { sys->SetOwnerFamily(GetOwnerID(offset), fam_num); }
 
 // ---- inspectors ----
@@ -1403,8 +1467,8 @@ void DEMSolver::UpdateTriNodeRelPos(size_t owner, size_t triID, const std::vecto
 std::vector<float3> DEMSolver::GetMeshNodesGlobal(bodyID_t ownerID) {
     assertInit("GetMeshNodesGlobal");
     auto me = GetCachedMesh(ownerID);
-    const float3 pos = GetOwnerPosition(ownerID);
-    const float4 q = GetOwnerOriQ(ownerID);
+    const float3 pos = GetOwnerPosition(ownerID)[0];
+    const float4 q = GetOwnerOriQ(ownerID)[0];
     std::vector<float3> out(me->m_vertices.size());
     for (size_t i = 0; i < out.size(); i++) out[i] = Rotate(me->m_vertices[i], q) + pos;
     return out;

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
-    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
+    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_set_family_material", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
 ]
 
 
@@ -48,7 +48,7 @@ class DemStats(C.Structure):
         ("n_contacts_sa", C.c_uint64), ("n_contacts_st", C.c_uint64), ("contact_capacity", C.c_uint64),
         ("kernel_launches", C.c_uint64), ("device_bytes", C.c_uint64), ("sim_time", C.c_double),
         ("max_margin", C.c_float), ("cell_size", C.c_float), ("n_cells", C.c_uint32 * 3), ("overflow", C.c_uint32),
-        ("pad_", C.c_uint32), ("n_contacts_ss_touching", C.c_uint64),
+        ("cd_update_freq", C.c_uint32), ("n_contacts_ss_touching", C.c_uint64),
     ]
 
 

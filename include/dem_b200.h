@@ -111,7 +111,7 @@ typedef struct DemStats {
     float cell_size;           /* broad-phase cell edge of the last rebuild */
     uint32_t n_cells[3];
     uint32_t overflow;         /* !=0: a list overflowed (capacity was grown and the rebuild redone) */
-    uint32_t pad_;
+    uint32_t cd_update_freq;   /* steps per contact-list cycle right now (GetUpdateFreq; moves when "adaptive_update_freq" is on) */
     uint64_t n_contacts_ss_touching; /* sphere-sphere pairs that overlapped at the last rebuild */
 } DemStats;
 
@@ -216,6 +216,9 @@ int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz_f
 int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float* pos_xyz_world,
                            const float* oriQ_wxyz, const float* vel_xyz, const float* omg_xyz,
                            const uint8_t* family);
+/* SetFamilyClumpMaterial / SetFamilyMeshMaterial (src/DEM/APIPublic.cpp:1597-1604, dT.cpp:2719-2738): the spheres
+ * (meshes != 0: the facets) of every owner in `family` get `material`; contact history is kept. */
+int dem_set_family_material(DemCtx* ctx, uint32_t family, uint32_t material, int meshes);
 /* contact list in the reference's order (type, idA, idB). Pass NULL arrays to only query the count. */
 int dem_download_contacts(DemCtx* ctx, uint64_t capacity, uint64_t* n, uint32_t* idA, uint32_t* idB, uint8_t* type,
                           float* wildcards4, float* force_xyz);
@@ -272,7 +275,11 @@ int dem_host_slab_bounds(const DemSimParams* p, int world, int rank, float* lo, 
 int dem_host_partition_owners(const DemSimParams* p, int world, int rank, float halo, uint64_t n, const uint64_t* voxelID,
                               const uint16_t* locX, uint8_t* role, uint8_t* send);
 
-/* execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
+/* "adaptive_update_freq" (0/1; UseAdaptiveUpdateFreq, src/DEM/API.h, dT.h:721-752): let the core pick the steps per
+ * contact-list cycle that costs the least device time per step, starting from DemSimParams::cd_update_freq and staying
+ * inside ["update_freq_min", "update_freq_max"] (SetCDMaxUpdateFreq).  Single-device contexts only: the ranks of a
+ * decomposition must agree on the cycle length, so there it stays where it was set.
+ * Execution knobs that do not change results: "ctas_per_sm" (2..4, register budget / occupancy of the force kernel),
  * "fast_encode" (0/1), "sort_mode" (0 radix sort, 1 counting sort; identical order), "keep_acc" (0/1: write per-owner accelerations every step for ContactAcc trackers) */
 int dem_set_option(DemCtx* ctx, const char* name, double value);
 

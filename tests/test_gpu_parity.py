@@ -856,3 +856,41 @@ def test_drum_config4_full_size_single_step_vs_ref(built):
     f = scenes.flatten(sc)
     assert f.nClumps == 500000
     _single_step_vs_ref_at_full_size(f, 1200, "C4")
+
+
+def test_adaptive_update_frequency_keeps_the_physics(built):
+    """UseAdaptiveUpdateFreq (row a17; reference tuner: src/DEM/dT.h:721-752, dT.cpp:2280-2297): with the tuner on, the core
+    moves the number of steps per contact-list cycle to where a step costs the least device time.  Whatever it picks, the
+    contact list stays a superset of the pairs in touch, so the trajectory is the one of the fixed-frequency run up to
+    round-off (same yardstick as the trajectory tests: 10x the run's own sensitivity to a 1e-6 perturbation)."""
+    sc = scenes.config2_clumps(40, 24, 20, cd_update_freq=10, spacing=2.7, init_vel=(0.2, 0.0, -1.5))
+    f = scenes.flatten(sc)
+    n = f.nClumps
+    fp = scenes.flatten(sc)
+    for name in ("vX", "vY", "vZ"):
+        a = getattr(fp, name)
+        a[:] = (a.astype("f8") * (1.0 + 1e-6)).astype("f4")
+    fixed, fixed_p, tuned = demb200.Engine(0), demb200.Engine(0), demb200.Engine(0)
+    fixed.load_flat(f)
+    fixed_p.load_flat(fp)
+    tuned.load_flat(f)
+    tuned.set_option("update_freq_min", 4)
+    tuned.set_option("update_freq_max", 60)
+    tuned.set_option("adaptive_update_freq", 1)
+    seen = set()
+    done = 0
+    for cp in (500, 1500, 3000):
+        for e in (fixed, fixed_p, tuned):
+            e.step(cp - done)
+        done = cp
+        seen.add(int(tuned.stats().cd_update_freq))
+        ref = fixed.positions()[:n]
+        sens = np.abs(fixed_p.positions()[:n] - ref).max()
+        err = np.abs(tuned.positions()[:n] - ref).max()
+        print("step %d: update frequency now %d, |dx| %.2e (sensitivity %.2e)" % (cp, tuned.stats().cd_update_freq, err, sens))
+        assert err <= 10 * sens + 1e-7, (cp, err, sens)
+    assert all(4 <= v <= 60 for v in seen)
+    assert seen != {10}, "the tuner never moved off the starting frequency"
+    assert int(fixed.stats().cd_update_freq) == 10
+    for e in (fixed, fixed_p, tuned):
+        e.close()

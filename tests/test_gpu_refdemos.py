@@ -1,0 +1,71 @@
+"""Drop-in proof with the reference's OWN demo scripts: /root/reference/src/demo/DEMdemo_*.cpp compiled UNMODIFIED against
+this repository's deme::DEMSolver facade (dem-engine_b200/host, `make refdemos`; the binaries are built where the
+reference tree exists and travel to the GPU box) and run here for a bounded time each.  A demo simulates seconds to
+minutes of physical time, so it is stopped by `timeout` after a few seconds of wall time: what is asserted is that it
+initialises, steps, reads its trackers / inspectors, writes its first output files and prints no error -- and, for
+DEMdemo_TestPack, the rolling / slipping classification of the sphere on the incline (DEMdemo_TestPack.cpp:98-203).
+"""
+import glob
+import os
+import re
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "dem-engine_b200", "host", "refdemo")
+DATA = os.path.join(ROOT, "baseline", "_ref", "build", "data")
+
+
+def _run(name, seconds, tmp_path):
+    exe = os.path.join(BIN, "DEMdemo_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("refdemo/DEMdemo_%s not built (needs /root/reference at build time)" % name)
+    if not os.path.isdir(os.path.join(DATA, "clumps")):
+        pytest.skip("the reference's data directory (baseline/_ref/build/data) is not present")
+    env = dict(os.environ, DEME_DATA_PATH=DATA)
+    r = subprocess.run(["timeout", "-s", "INT", str(seconds), exe], cwd=str(tmp_path), env=env, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, errors="replace")
+    out = r.stdout
+    print(out[-1500:])
+    # 0: ran to its end; 124: still stepping when the time was up; 130 / -2: stopped by the interrupt itself
+    assert r.returncode in (0, 124, 130, -2), (name, r.returncode, out[-800:])
+    assert "terminate called" not in out and "what():" not in out, out[-800:]
+    return out
+
+
+# demo -> (seconds, glob of an output file it must have written by then, or None)
+DEMOS = {
+    "BallDrop": (20, None),
+    "Mixer": (25, "DemoOutput_Mixer/*"),
+    "RotatingDrum": (25, "DemoOutput_RotatingDrum/*"),
+    "Repose": (25, "DemoOutput_Repose/*"),
+    "Centrifuge": (25, "DemoOutput_Centrifuge/*"),
+    "Sieve": (20, None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DEMOS))
+def test_reference_demo_runs_unmodified(built, name, tmp_path):
+    seconds, pattern = DEMOS[name]
+    _run(name, seconds, tmp_path)
+    if pattern:
+        assert glob.glob(os.path.join(str(tmp_path), pattern)), "no output file matching %s" % pattern
+
+
+def test_reference_testpack_incline_classification(built, tmp_path):
+    """DEMdemo_TestPack.cpp:98-203: a sphere (mu = 0.25) sent up an incline of angle alpha with rolling resistance Crr; after
+    1 s the script classifies the motion.  A solid sphere rolls without slipping only while tan(alpha) <= 3.5 mu, i.e.
+    alpha <= 41.2 degrees: every case the run gets through (it starts at 60 degrees and works downwards) above 45 degrees
+    must be reported as slipping."""
+    out = _run("TestPack", 45, tmp_path)
+    cases = re.findall(r"Angle of incline: ([0-9.]+)\s+Rolling resistance: ([0-9.eE+-]+)\s+Velocity \(mag\) of the sphere: "
+                       r"([0-9.eE+-]+)\s+Angular velocity \(mag\) of the sphere: ([0-9.eE+-]+)\s+It is ([a-z ]+)", out)
+    assert len(cases) >= 10, "only %d incline cases finished" % len(cases)
+    for alpha, crr, v, w, verdict in cases:
+        if float(alpha) >= 45.0:
+            assert verdict.strip() in ("rolling with slipping", "pure slipping"), (alpha, crr, v, w, verdict)
+            # it slid back down: g (sin a - mu cos a) over most of a second
+            assert float(v) > 1.0
+    assert "WARNING!!! I do not know what happened" not in out

@@ -36,14 +36,22 @@ def dump_settled_scene(eng, sc, f, path):
     return path
 
 
-def run_reference(scene_path, n_gpus, steps, warmup, cd_update_freq=0, timeout=900, visible=None):
-    """one run of run_ref bench; returns its JSON line (dict) or {"unavailable": why}"""
-    if not reference_available():
-        return {"unavailable": "baseline/_ref/run_ref not built (baseline/build_ref.sh needs /root/reference)"}
+def run_reference(scene_path, n_gpus, steps, warmup, cd_update_freq=0, timeout=900, visible=None, exe=None, mode="bench"):
+    """one run of the driver script baseline/run_ref.cpp (exe: baseline/_ref/run_ref = the unmodified reference, or
+    dem-engine_b200/host/run_b200 = the same script against this repository's facade); returns its JSON line (dict) or
+    {"unavailable": why}"""
+    if exe is None:
+        if not reference_available():
+            return {"unavailable": "baseline/_ref/run_ref not built (baseline/build_ref.sh needs /root/reference)"}
+        exe = RUN_REF
+    elif not os.path.exists(exe):
+        return {"unavailable": "%s not built" % os.path.relpath(exe, ROOT)}
     env = dict(os.environ)
+    if exe != RUN_REF:  # (the reference has its data directory baked in at configure time; the facade reads this one)
+        env.setdefault("DEME_DATA_PATH", os.path.join(ROOT, "dem-engine_b200", "host", "data"))
     if visible is not None:
         env["CUDA_VISIBLE_DEVICES"] = visible
-    cmd = [RUN_REF, "bench", scene_path, str(n_gpus), str(steps), str(warmup), str(cd_update_freq)]
+    cmd = [exe, mode, scene_path, str(n_gpus), str(steps), str(warmup), str(cd_update_freq)]
     try:
         r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=timeout)
     except subprocess.TimeoutExpired:
