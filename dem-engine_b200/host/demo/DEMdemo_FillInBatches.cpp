@@ -29,6 +29,7 @@ int main(int argc, char** argv) {
     DEMSim.SetGravitationalAcceleration(make_float3(0, 0, -9.81));
     DEMSim.SetInitTimeStep(1e-5);
     DEMSim.SetCDUpdateFreq(10);
+    DEMSim.UseAdaptiveUpdateFreq(false);  // (this script compares contact lists: keep the cycle length, hence the margin, fixed)
 
     HCPSampler sampler(3.f * scale);
     auto layer = [&](float z) { return sampler.SampleBox(make_float3(0, 0, z), make_float3(0.15f, 0.15f, 0.03f)); };

@@ -27,6 +27,7 @@ static std::shared_ptr<DEMClumpTemplate> setup(DEMSolver& sim, std::shared_ptr<D
     sim.SetGravitationalAcceleration(make_float3(0, 0, -9.81));
     sim.SetInitTimeStep(1e-5);
     sim.SetCDUpdateFreq(10);
+    sim.UseAdaptiveUpdateFreq(false);  // (this script compares contact lists: keep the cycle length, hence the margin, fixed)
     return tmpl;
 }
 

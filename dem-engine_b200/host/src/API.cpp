@@ -169,10 +169,12 @@ DEMSolver::DEMSolver(unsigned int nGPUs) {
     for (int k = 0; k < std::max(n, 1); k++) ids.push_back(first + k);
     ctx = create_group_ctx(ids);
     m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
+    if (const char* e = std::getenv("DEME_B200_ADAPTIVE_FREQ")) m_adaptive_update_freq = std::atoi(e) != 0;
 }
 DEMSolver::DEMSolver(const std::vector<int>& gpu_ids) {
     ctx = create_group_ctx(gpu_ids);
     m_family_masks.assign(DEM_NUM_FAMILY_MASKS, 0);
+    if (const char* e = std::getenv("DEME_B200_ADAPTIVE_FREQ")) m_adaptive_update_freq = std::atoi(e) != 0;
 }
 DEMSolver::~DEMSolver() {
     if (ctx) dem_ctx_destroy(ctx);
