@@ -51,6 +51,32 @@ __device__ __forceinline__ uint32_t warp_claim_n(uint32_t count, uint32_t* curso
     return base + inc - count;
 }
 
+// Append with ONE global atomic per CTA and list (16 000 warps adding to the same word serialise in L2: ~40 us at half a
+// million owners): warps claim their stretch of the CTA's run in shared memory, thread 0 claims the CTA's run in the
+// global cursor.  Must be called by all threads of the CTA; count = entries this thread appends (0..), returns its
+// first slot.  sm: 2 words of shared memory.
+__device__ __forceinline__ uint32_t block_claim(uint32_t count, uint32_t* cursor, uint32_t* sm) {
+    const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) sm[0] = 0u;
+    __syncthreads();
+    uint32_t inc = count;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t wbase = 0;
+    if (lane == 31 && total) wbase = atomicAdd(&sm[0], total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    __syncthreads();
+    if (threadIdx.x == 0) sm[1] = sm[0] ? atomicAdd(cursor, sm[0]) : 0u;
+    __syncthreads();
+    const uint32_t r = sm[1] + wbase + inc - count;
+    __syncthreads();  // (sm is reused by the next call)
+    return r;
+}
+
 __device__ __forceinline__ unsigned long long* mg_flag(char* block, int dir) {
     return reinterpret_cast<unsigned long long*>(block + MG_HDR_STEP_FLAG) + dir;
 }
@@ -64,8 +90,9 @@ __device__ __forceinline__ uint32_t* mg_recv_count(char* block, int par, int dir
 __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M,
                                                      const GridInfo* __restrict__ grid, int par) {
     if (P.flags[DEM_FLAG_POISON]) return;
+    __shared__ uint32_t sm[2];
     const uint32_t n = M.counts[par ^ 1][3];
-    const uint32_t nround = (n + 31u) & ~31u;
+    const uint32_t nround = (n + blockDim.x - 1u) / blockDim.x * blockDim.x;  // whole CTAs take part in the claims
     const float halo = grid->halo;
     uint32_t* cnt = M.counts[par];
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
@@ -88,11 +115,11 @@ __global__ void __launch_bounds__(256) k_mg_classify(const __grid_constant__ Dev
             // (ghosts are re-flagged when the neighbour's list arrives)
             M.flag[g] = own ? (toL ? 3 : (toR ? 4 : 1)) : 0;
         }
-        const uint32_t sa = warp_append(own, &cnt[3]);
+        const uint32_t sa = block_claim(own ? 1u : 0u, &cnt[3], sm);
         if (own) M.active_list[par][sa] = g;
-        warp_append(own && g < M.nClumpOwners, &cnt[0]);
-        const uint32_t sl = warp_append(toL, &cnt[1]);
-        const uint32_t sr = warp_append(toR, &cnt[2]);
+        block_claim((own && g < M.nClumpOwners) ? 1u : 0u, &cnt[0], sm);
+        const uint32_t sl = block_claim(toL ? 1u : 0u, &cnt[1], sm);
+        const uint32_t sr = block_claim(toR ? 1u : 0u, &cnt[2], sm);
         if (toL && sl < M.cap) M.send_gid[par][0][sl] = g;
         if (toR && sr < M.cap) M.send_gid[par][1][sr] = g;
         if ((toL && sl >= M.cap) || (toR && sr >= M.cap)) atomicOr(&P.flags[DEM_FLAG_HALO], 8u);
@@ -199,12 +226,13 @@ __global__ void __launch_bounds__(256) k_mg_pull_full(const __grid_constant__ De
 __global__ void __launch_bounds__(256) k_mg_active_spheres(const __grid_constant__ DevParams P, const __grid_constant__ MgDev M, int par) {
     if (P.flags[DEM_FLAG_POISON]) return;
     if (M.owner_sph) {
+        __shared__ uint32_t sm[2];
         const uint32_t n = M.counts[par][3];
-        const uint32_t nround = (n + 31u) & ~31u;
+        const uint32_t nround = (n + blockDim.x - 1u) / blockDim.x * blockDim.x;
         for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < nround; t += gridDim.x * blockDim.x) {
             uint2 r = make_uint2(0u, 0u);
             if (t < n) r = M.owner_sph[M.active_list[par][t]];
-            const uint32_t base = warp_claim_n(r.y, &M.counts[par][4]);
+            const uint32_t base = block_claim(r.y, &M.counts[par][4], sm);
             for (uint32_t k = 0; k < r.y; k++) M.act_sph[par][base + k] = r.x + k;
         }
     } else {

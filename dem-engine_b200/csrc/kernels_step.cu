@@ -710,7 +710,7 @@ __device__ __forceinline__ float integrate_one(const DevParams& P, const uint32_
 // run beside the bulk of it: MODE 1 = the owners in this rank's halo send lists (first), MODE 2 = all other active owners
 // (ghosts only have their unused wrench consumed).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_integrate(const __grid_constant__ DevParams P) {
+__global__ void __launch_bounds__(256, 4) k_integrate(const __grid_constant__ DevParams P) {
     if (P.flags[DEM_FLAG_POISON]) return;
     // max |v| bookkeeping for the contact margin (replaces the absv inspector + cub max of kT.cpp:125-149):
     // this step accumulates into maxvel_next; the slot of the state being left behind is zeroed for the step after.

@@ -167,3 +167,52 @@ def test_group_context_is_a_drop_in_for_one_gpu(built, world):
     compare("N=%d after the kick + 400 steps" % world)
     for e in (eg, e1, e1p):
         e.close()
+
+
+def test_group_context_with_a_prescribed_mesh(built):
+    """A triangle mesh under the slab decomposition (every rank registers the facets that can meet its slab): clumps thrown
+    into a tilted, spinning box of facets, 2 GPUs against 1.  The mesh owner is replicated on both ranks, which is exact
+    because its motion is fully prescribed; a free-moving mesh makes the group fall back to one GPU instead."""
+    _need(2)
+    sc = scenes.config2_clumps(20, 6, 4, cd_update_freq=5, spacing=2.7, init_vel=(0.3, 0.1, -2.0))
+    sc.bounding = "none"
+    lo, hi = sc.clump_xyz.min(0), sc.clump_xyz.max(0)
+    v, fc = scenes.box_mesh((hi[0] - lo[0]) * 1.3, (hi[1] - lo[1]) * 1.6, (hi[2] - lo[2]) * 2.2, n=6, inward=True)
+    sc.add_mesh(v, fc, mat=0, mass=1.0, moi=(1, 1, 1), pos=tuple((lo + hi) / 2), quat=(0.9950042, 0.0998334, 0, 0), family=10)
+    sc.prescribed[10] = dict(linvel=(0.0, 0.0, 0.0), angvel=(0.0, 0.0, 2.0))
+    f = scenes.flatten(sc)
+    n = f.nClumps
+    fp = scenes.flatten(sc)
+    for name in ("vX", "vY", "vZ"):
+        a = getattr(fp, name)
+        a[:n] = (a[:n].astype("f8") * (1.0 + 1e-6)).astype("f4")
+    e1, e1p = demb200.Engine(0), demb200.Engine(0)
+    e1.load_flat(f)
+    e1p.load_flat(fp)
+    eg = demb200.Engine(devices=[0, 1])
+    eg.set_option("group_min_owners", 10)
+    eg.load_flat(f)
+    assert eg.mgpu_info()["world"] == 2
+    for cp in (300, 900):
+        for e in (eg, e1, e1p):
+            e.step(300 if cp == 300 else 600)
+        ref = e1.positions()[:n]
+        sens = np.abs(e1p.positions()[:n] - ref).max()
+        err = np.abs(eg.positions()[:n] - ref).max()
+        print("mesh, 2 GPUs, step %d: |dx| %.2e (sens %.2e), facet contacts %d vs %d" % (
+            cp, err, sens, eg.stats().n_contacts_st, e1.stats().n_contacts_st))
+        assert err <= 10 * sens + 1e-7, (cp, err, sens)
+    assert e1.stats().n_contacts_st > 0
+    # nothing left the box of facets
+    pos = eg.positions()[:n]
+    assert np.isfinite(pos).all()
+    # a mesh that moves freely cannot be replicated: the same scene without the prescription runs on one GPU
+    sc.prescribed.pop(10)
+    f2 = scenes.flatten(sc)
+    eg2 = demb200.Engine(devices=[0, 1])
+    eg2.set_option("group_min_owners", 10)
+    eg2.load_flat(f2)
+    assert eg2.mgpu_info()["world"] == 1
+    eg2.step(50)
+    for e in (eg, eg2, e1, e1p):
+        e.close()
