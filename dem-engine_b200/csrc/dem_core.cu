@@ -199,6 +199,7 @@ struct DemCtx {
     uint64_t n_steps = 0, n_rebuilds = 0, launches = 0, device_bytes = 0;
     uint64_t steps_target = 0;  // steps asked for so far (n_steps falls behind it while a failed rebuild is replayed)
     uint64_t steps_since_rebuild = 0;
+    uint32_t list_freq = 0;   // the drift (steps) the lists in use were built for: they are rebuilt after that many steps
     bool need_rebuild = true;
     bool need_maxvel = true;  // velocities changed outside the integrator
     int maxvel_slot = 0;
@@ -647,6 +648,7 @@ void note_rebuild_enqueued(DemCtx* ctx) {
     ctx->cur ^= 1;
     ctx->n_rebuilds++;
     ctx->steps_since_rebuild = 0;
+    ctx->list_freq = ctx->sp.cd_update_freq;
     ctx->need_rebuild = false;
     ctx->need_maxvel = false;
 }
@@ -868,6 +870,8 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
     if (rc) return rc;
     if (rolled || ctx->need_maxvel) return DEM_OK;
     const uint32_t L = ctx->sp.cd_update_freq;
+    // (confirming the previous rebuild may have moved the update frequency: a whole cycle must still fit)
+    if (L < 2 || ctx->steps_target - ctx->n_steps < L) return DEM_OK;
     DemCtx::CycleGraph& G = ctx->graphs[ctx->cur][ctx->maxvel_slot];
     const DevParams P = make_params(ctx);
     const CdParams C = make_cd(ctx);
@@ -926,13 +930,12 @@ int run_cycle_graph(DemCtx* ctx, bool* done) {
 int pump(DemCtx* ctx) {
     while (ctx->n_steps < ctx->steps_target) {
         const uint32_t L = ctx->sp.cd_update_freq;
-        if (ctx->need_rebuild || ctx->steps_since_rebuild >= L) {
+        if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->list_freq) {
             if (graph_wanted(ctx) && !ctx->need_maxvel && L >= 2 && ctx->steps_target - ctx->n_steps >= L) {
                 bool done = false;
                 int rc = run_cycle_graph(ctx, &done);
                 if (rc) return rc;
                 if (done) continue;
-                if (!ctx->need_rebuild && ctx->steps_since_rebuild < L) continue;
             }
             const uint64_t before = ctx->seq_host;
             int rc = enqueue_rebuild(ctx);
@@ -2449,7 +2452,7 @@ int dem_profile_steps(DemCtx* ctx, uint64_t n_steps, float out_us[8]) {
         for (int i = 0; i < nb; i++) {
             cudaEvent_t* e = &ev[(size_t)NE * i];
             CK(cudaEventRecord(e[0], s));
-            if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->sp.cd_update_freq) {
+            if (ctx->need_rebuild || ctx->steps_since_rebuild >= ctx->list_freq) {
                 const uint32_t before = ctx->seq_host;
                 int rc = enqueue_rebuild(ctx);
                 if (rc) { rc_out = rc; break; }

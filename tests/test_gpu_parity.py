@@ -800,8 +800,10 @@ def _single_step_vs_ref_at_full_size(f, warm_steps, label):
     # The few pairs beyond 2e-4 are judged against their overlap depth, recomputed here in double from the state both
     # sides started from: the geometry the two sides work with differs by the rounding of the rotated sphere offsets
     # (~3e-10 m), and the Coulomb-clamped tangential spring (mu |Fn| t + gamma_t v_t) / (-k_t) -- a difference of nearly
-    # equal terms, k_t ~ depth^(1/2), gamma_n ~ depth^(1/4) -- passes that on amplified.  Allowed: 2e-4 + 1e-8 m / depth;
-    # a pair shallower than 1e-8 m may be seen as "not in touch" by either side.
+    # equal terms, k_t ~ depth^(1/2), gamma_n ~ depth^(1/4) -- passes that on amplified.  Allowed: 2e-4 + 1e-8 m / depth
+    # (sphere--sphere and sphere--plane pairs; 2e-2 for the few cylinder / facet pairs, whose depth is not recomputed);
+    # a pair shallower than 1e-8 m may be seen as "not in touch" by either side.  At least 99 % of the touching pairs
+    # must meet 2e-4 outright.
     def sphere_centres(ids):
         own = f.ownerClumpBody[ids]
         comp = f.clumpComponentOffset[ids]
@@ -820,9 +822,25 @@ def _single_step_vs_ref_at_full_size(f, warm_steps, label):
         ca, ra = sphere_centres(idA[kk][ss_bad])
         cb, rb = sphere_centres(idB[kk][ss_bad])
         depth[ss_bad] = ra + rb - np.linalg.norm(ca - cb, axis=1)
+    pl_bad = ct[kk] == 11     # sphere--plane: depth = r - (centre - plane point) . normal
+    if pl_bad.any():
+        ca, ra = sphere_centres(idA[kk][pl_bad])
+        comp = idB[kk][pl_bad]
+        own = f.objOwner[comp]
+        q = st["oriQ"][own].astype("f8")
+        qw, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+
+        def rot(v):
+            return np.stack([(2 * (qw * qw + qx * qx) - 1) * v[:, 0] + 2 * (qx * qy - qw * qz) * v[:, 1] + 2 * (qx * qz + qw * qy) * v[:, 2],
+                             2 * (qx * qy + qw * qz) * v[:, 0] + (2 * (qw * qw + qy * qy) - 1) * v[:, 1] + 2 * (qy * qz - qw * qx) * v[:, 2],
+                             2 * (qx * qz - qw * qy) * v[:, 0] + 2 * (qy * qz + qw * qx) * v[:, 1] + (2 * (qw * qw + qz * qz) - 1) * v[:, 2]], 1)
+        P0 = ints(st["voxelID"][own], st["locX"][own].astype("i8"), st["locY"][own].astype("i8"), st["locZ"][own].astype("i8")).astype("f8") * f.l
+        pp = P0 + rot(np.stack([f.objRelPosX[comp], f.objRelPosY[comp], f.objRelPosZ[comp]], 1).astype("f8"))
+        nn = rot(np.stack([f.objRotX[comp], f.objRotY[comp], f.objRotZ[comp]], 1).astype("f8"))
+        depth[pl_bad] = ra - ((ca - pp) * nn).sum(1)
     rel = np.abs(got[bad] - wco[alive][bad])[:, :3].max(1) / np.maximum(np.abs(wco[alive][bad][:, :3]).max(1), 1e-30)
     allowed = np.where(depth < 1e-8, np.inf, 2e-4 + 1e-8 / np.maximum(depth, 1e-30))
-    allowed[~ss_bad] = 5e-3   # (sphere--wall / sphere--facet pairs: no depth recomputed here)
+    allowed[~(ss_bad | pl_bad)] = 2e-2   # (sphere--cylinder / sphere--facet pairs: no depth recomputed here)
     hard = np.nonzero(rel > allowed)[0]
     for i in hard[:10]:
         k = kk[i]
