@@ -89,6 +89,7 @@ struct ListBuf {
     uint32_t* count = nullptr;
     float4* force = nullptr;
     float4* cpoint = nullptr;
+    uint8_t* due = nullptr;  // sphere--sphere candidate list only
 };
 
 // host bookkeeping at the moment a rebuild was enqueued: what the host returns to when that rebuild turns out to
@@ -178,7 +179,7 @@ struct DemCtx {
     uint32_t* d_rs_hist = nullptr;
     uint32_t* d_scan_tmp = nullptr;
     unsigned long long* d_scan_desc = nullptr;
-    uint32_t* d_cand = nullptr;               // candidates accepted by the sweep's count pass (16 words per sphere)
+    uint32_t* d_cand = nullptr;               // candidates accepted by the sweep's count pass (SW_REC = 12 words per sphere)
     uint32_t* d_idA[2] = {nullptr, nullptr};  // sphere A of every new sphere--sphere contact (fill pass -> history pass)
     // triangles
     float4* d_tri[3] = {nullptr, nullptr, nullptr};   // owner-frame nodes
@@ -247,7 +248,11 @@ struct DemCtx {
     int ctas_per_sm = 4;
     int fast_math = 1;  // sphere--sphere force kernel: MUFU reciprocal / rsqrt instead of IEEE division / sqrt
     int fast_encode = 1;
-    int force_opts = 2;  // bit 0: skip candidates that cannot touch yet; bit 1: fetch velocities only for pairs in touch
+    // sphere--sphere force kernels (kernels_step.cu).  bit 0: leave candidates alone until the step at which they can
+    // touch (k_force_ss_due, chosen for lists that live >= 32 steps); bit 1: fetch velocities only for pairs in touch;
+    // bit 4: (with bit 0) compact the due candidates per warp; bit 5: every evaluation refreshes the step a candidate is
+    // due at; bit 6: use k_force_ss_due whatever the list's life time; bits 2 / 3: measurement only
+    int force_opts = 1 | 2 | 16 | 32;
     int sort_mode = 1;  // 0 radix sort, 1 counting sort + in-cell rank by sphere id (same order)
     bool keep_acc = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -307,8 +312,12 @@ void dfree(T*& p) {
     p = nullptr;
 }
 
-int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, bool force) {
+int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, bool force, bool due = false) {
     int rc;
+    if (due) {  // (+ one filter round of k_force_ss beyond the last entry; 0 = look at the pair at every step)
+        if ((rc = dalloc(ctx, &L.due, cap + 1024))) return rc;
+        CK(cudaMemset(L.due, 0, cap + 1024));
+    }
     if ((rc = dalloc(ctx, &L.idB, cap))) return rc;
     if ((rc = dalloc(ctx, &L.cinfo, cap))) return rc;
     if (hist && (rc = dalloc(ctx, &L.hist, cap))) return rc;
@@ -329,13 +338,13 @@ int alloc_list(DemCtx* ctx, ListBuf& L, uint64_t cap, uint32_t nSph, bool hist, 
 }
 void free_list(ListBuf& L) {
     dfree(L.idB); dfree(L.cinfo); dfree(L.hist); dfree(L.force); dfree(L.cpoint); dfree(L.seg_start); dfree(L.seg_count);
-    dfree(L.count);
+    dfree(L.count); dfree(L.due);
 }
 
 ContactList as_list(const ListBuf& L) {
     ContactList c;
     c.idB = L.idB; c.cinfo = L.cinfo; c.hist = L.hist; c.seg_start = L.seg_start; c.seg_count = L.seg_count;
-    c.count = L.count; c.force = L.force; c.cpoint = L.cpoint;
+    c.count = L.count; c.force = L.force; c.cpoint = L.cpoint; c.due = L.due;
     return c;
 }
 
@@ -503,7 +512,7 @@ int alloc_lists(DemCtx* ctx, uint64_t cap) {
     int rc;
     for (int kind = 0; kind < 4; kind++)
         for (int k = 0; k < 2; k++)
-            if ((rc = alloc_list(ctx, ctx->lists[kind][k], (kind == 3 && ctx->nTri == 0) ? 1 : cap, ctx->nSpheres, hist, rec))) return rc;
+            if ((rc = alloc_list(ctx, ctx->lists[kind][k], (kind == 3 && ctx->nTri == 0) ? 1 : cap, ctx->nSpheres, hist, rec, kind == 1))) return rc;
     for (int k = 0; k < 2; k++)
         if ((rc = dalloc(ctx, &ctx->d_idA[k], cap))) return rc;
     ctx->capacity = cap;
@@ -528,9 +537,9 @@ int grow_lists(DemCtx* ctx, uint64_t newcap) {
     for (int kind = 0; kind < (ctx->nTri ? 4 : 3); kind++) {
         int rc;
         free_list(ctx->lists[kind][ctx->cur ^ 1]);
-        if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec))) return rc;
+        if ((rc = alloc_list(ctx, ctx->lists[kind][ctx->cur ^ 1], newcap, ctx->nSpheres, hist, rec, kind == 1))) return rc;
         ListBuf src = ctx->lists[kind][ctx->cur], dst;
-        if ((rc = alloc_list(ctx, dst, newcap, ctx->nSpheres, hist, rec))) return rc;
+        if ((rc = alloc_list(ctx, dst, newcap, ctx->nSpheres, hist, rec, kind == 1))) return rc;  // (due = 0: every step)
         CK(cudaMemcpy(dst.idB, src.idB, sizeof(uint32_t) * oldcap, cudaMemcpyDeviceToDevice));
         CK(cudaMemcpy(dst.cinfo, src.cinfo, sizeof(uint4) * oldcap, cudaMemcpyDeviceToDevice));
         if (src.hist) CK(cudaMemcpy(dst.hist, src.hist, sizeof(float4) * oldcap, cudaMemcpyDeviceToDevice));
@@ -1547,7 +1556,7 @@ int initialize_one(DemCtx* ctx, uint64_t contact_capacity) {
     const size_t scan_n = std::max<size_t>(std::max<size_t>((size_t)ctx->max_cells + 2, (size_t)nS + 2), 256 * rs_blocks);
     if ((rc = dalloc(ctx, &ctx->d_scan_tmp, scan_n / 4096 + 2))) return rc;
     if ((rc = dalloc(ctx, &ctx->d_scan_desc, scan_n / 4096 + 8))) return rc;
-    if ((rc = dalloc(ctx, &ctx->d_cand, (size_t)nS * 20 + 20))) return rc;  // SW_REC words per sphere (kernels_sweep.cu)
+    if ((rc = dalloc(ctx, &ctx->d_cand, (size_t)nS * 12 + 12))) return rc;  // SW_REC words per sphere (kernels_sweep.cu)
 
     if (ctx->nTri) {
         const uint32_t nT = ctx->nTri;
@@ -2417,6 +2426,10 @@ int dem_debug_download(DemCtx* ctx, const char* what, void* out, uint64_t n, uin
     if (w == "sphere_keys") { src = ctx->d_keys[0]; avail = nS; }
     else if (w == "sorted_keys") { src = (ctx->sort_mode == 1) ? ctx->d_vals[0] : ctx->d_keys[ctx->last_sorted_buf]; avail = nS; }
     else if (w == "sphere_pos") { src = ctx->d_sphF; avail = nS * 4; }
+    // compiled records of the sphere--sphere candidate list in use (4 words each), then the status words
+    else if (w == "sn_cinfo") { src = ctx->lists[1][ctx->cur].cinfo; avail = ctx->n_list[1] * 4; }
+    else if (w == "sn_due") { src = ctx->lists[1][ctx->cur].due; avail = (ctx->n_list[1] + 3) / 4; }  // one byte per candidate
+    else if (w == "flags") { src = ctx->d_flags; avail = DEM_NUM_FLAGS; }
     else if (w == "sorted_ids") {
         // second word of the 16-byte sorted meta record
         const uint64_t m = std::min<uint64_t>(n, nS);

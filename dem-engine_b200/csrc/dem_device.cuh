@@ -3,7 +3,10 @@
 // HBM layout (see DESIGN.md "Data layout"):
 //   owners  : one 64-byte record per owner, fetched with TWO 256-bit loads (one per 32-byte sector)
 //             sector 0: pos  {u64 voxelID; u16 locX,locY,locZ; u8 family; u8 flags}   (the reference's voxelID / locX /
-//                            locY / locZ / familyID arrays, src/DEM/Defines.h:272-280, packed) + quat {w,x,y,z}
+//                            locY / locZ / familyID arrays, src/DEM/Defines.h:272-280, packed) + quat {w,x,y,z};
+//                            flags = 255 - c, c the owner's contact margin of the last rebuild in 256ths of the largest
+//                            one (rounded up; 0 = "as large as the largest"): k_sphere_prep writes it, k_force_ss reads
+//                            it with the record it gathers anyway
 //             sector 1: vel {vx,vy,vz,mass} + omg {WORLD-frame angular velocity, unused}
 //           + a 16-byte spin record {body-frame omgBar xyz, bits(inertiaPropOffset)} that only the integrator streams
 //           + one 32-byte wrench accumulator {Fx,Fy,Fz,0 | Tx,Ty,Tz,0}, force AND torque in the world frame (the
@@ -91,6 +94,8 @@ struct ContactList {
     uint32_t* count;     // device-resident number of contacts: [0] clamped to the capacity, [1] demand
     float4* force;       // optional per-contact force record (xyz) -- nullptr when SetNoForceRecord
     float4* cpoint;      // ... and the contact point (world frame, LBF-relative) the force acts at
+    uint8_t* due;        // sphere--sphere candidate list only: the step of the list's cycle from which on the pair has to
+                         // be looked at (set by the sweep, refreshed by k_force_ss); nullptr for the other lists
 };
 
 // status words of a context (DevParams::flags)
@@ -103,12 +108,12 @@ enum {
                             // host has grown the lists and cleared it (value = sequence number of the failed rebuild)
     DEM_FLAG_SEQ = 5,       // rebuilds finished so far (device-side counter: graph replays carry no host arguments)
     DEM_FLAG_CYCLE_STEP = 6,  // integrations since the last rebuild (zeroed by the rebuild, advanced by the integrator)
+    DEM_FLAG_INV_CLOSING = 7,  // float bits: maxDrift / (2 * largest margin of the last rebuild) = 1 / the most by which
+                               // the gap of any pair can shrink in one step (0: fixed expand factor, no such bound)
     DEM_NUM_FLAGS = 8
 };
 constexpr uint32_t CINFO_NO_HISTORY = 0x40000000u;  // sweep -> k_history: this contact carries no history over
-// cinfo.w of a sphere--sphere candidate: bits 0-15 material pair, bits 16-23 the first step of the cycle at which the
-// two spheres can possibly touch (see pair_first_step, kernels_sweep.cu), bit 30 CINFO_NO_HISTORY, bit 31 alive
-constexpr uint32_t CINFO_FIRST_SHIFT = 16;
+// cinfo.w: bits 0-15 material pair, bit 30 CINFO_NO_HISTORY (rebuild only), bit 31 alive
 
 // Multi-GPU (slab decomposition) state as the kernels see it.  Everything that changes from step to step or rebuild
 // to rebuild lives in DEVICE memory (epoch counters, counts, lists), so that the same parameter block -- hence the same
@@ -163,7 +168,7 @@ struct DevParams {
     float errOutVel;
     uint32_t maxDrift;
     uint32_t fast_encode;        // integrator: division-free position encode
-    uint32_t force_opts;         // sphere--sphere force kernel: bit 0 skip candidates that cannot touch yet, bit 1 lazy kinematics
+    uint32_t force_opts;         // sphere--sphere force kernels: see DemCtx::force_opts (dem_core.cu)
     double inv_voxelSize;
     // owners
     OwnerState* state;

@@ -72,7 +72,7 @@ struct CdParams {
     uint32_t* rs_hist;    // radix-sort tile histograms
     uint32_t* scan_tmp;   // block sums for the radix sort's scans
     unsigned long long* scan_desc;  // [0] tile counter, [1..] tile descriptors of the single-pass scan
-    uint32_t* cand;       // scratch: 16 words per sorted position, the candidates the count pass accepted (-> fill pass)
+    uint32_t* cand;       // scratch: 12 words per sorted position, the candidates the count pass accepted (-> fill pass)
     uint32_t* idA_ss;     // scratch: sphere A of every contact of the new lists (sweep fill -> k_history)
     uint32_t* idA_sn;
     // domain decomposition (nullptr on a single GPU): the rebuild walks the spheres of the active owners only and

@@ -93,6 +93,9 @@ __global__ void __launch_bounds__(32) k_grid_setup(const __grid_constant__ DevPa
     g.ncells = nbx * nby * nbz;
     g.max_margin = margin;
     g.maxvel = vmax;
+    // the most by which the gap of any pair can shrink in one step is 2 margin / maxDrift (k_force_ss leaves candidates
+    // alone until they can touch); a fixed expand factor promises no such bound
+    P.flags[DEM_FLAG_INV_CLOSING] = (P.beta < 0.f && margin > 0.f) ? __float_as_uint((float)P.maxDrift / (2.f * margin)) : 0u;
     // ghost layer: two clumps can touch up to 2 (R_clump + margin) apart; one more margin on each side covers the
     // distance an owner can travel before the next rebuild (that bound is what the margin is made of)
     g.halo = 2.f * (C.rclump + margin) + 2.f * margin;
@@ -216,6 +219,14 @@ __global__ void __launch_bounds__(256) k_sphere_prep(const __grid_constant__ Dev
             const float3 rel = rotate(f3(comp.x, comp.y, comp.z), q);
             sp = f3((float)(X + (double)rel.x), (float)(Y + (double)rel.y), (float)(Z + (double)rel.z));
             rInfl = comp.w + margin;
+            if (P.beta < 0.f) {
+                // the owner's margin relative to the largest one, as a byte in its state record (dem_device.cuh): the force
+                // kernel turns the two codes of a candidate pair into the bound on how fast their gap can close.  Every
+                // sphere of the owner stores the same value; nobody in this kernel looks at the byte.
+                uint32_t code = 255u;
+                if (g.max_margin > 0.f) code = min(255u, (uint32_t)(256.f * (margin / g.max_margin) * 1.000001f));  // (c + 1) / 256 >= m / max
+                reinterpret_cast<unsigned char*>(P.state + s.x)[15] = (unsigned char)(255u - code);
+            }
             C.sphF[i] = make_float4(sp.x, sp.y, sp.z, rInfl);
             int cx = (int)floorf(sp.x * g.inv_cs) - g.x0, cy = (int)floorf(sp.y * g.inv_cs), cz = (int)floorf(sp.z * g.inv_cs);
             cx = min(max(cx, 0), (int)g.nbx - 1);
@@ -433,23 +444,38 @@ __global__ void __launch_bounds__(LB_THREADS) k_scan_lookback(const uint32_t* in
         for (int k = 0; k < LB_ITEMS; k++) acc += v[k];
         uint32_t total;
         uint32_t ex = block_exclusive_scan(acc, sm, total);
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            // look-back by one WARP, 32 descriptors at a time (a single thread walking back one descriptor per L2 round
+            // trip made the chain of tiles the critical path: 24 us for 1200 tiles)
+            const int lane = threadIdx.x;
             uint32_t prefix = 0;
             if (tile == 0) {
-                D[0] = (unsigned long long)total | (2ull << 32);
+                if (lane == 0) D[0] = (unsigned long long)total | (2ull << 32);
             } else {
-                D[tile] = (unsigned long long)total | (1ull << 32);
-                __threadfence();
-                for (int p = (int)tile - 1; p >= 0; p--) {
-                    unsigned long long d;
-                    do { d = D[p]; } while ((d >> 32) == 0ull);
-                    prefix += (uint32_t)d;
-                    if ((d >> 32) == 2ull) break;
+                if (lane == 0) {
+                    D[tile] = (unsigned long long)total | (1ull << 32);
+                    __threadfence();
                 }
-                D[tile] = (unsigned long long)(prefix + total) | (2ull << 32);
+                for (int p = (int)tile - 1;; p -= 32) {
+                    const int q = p - lane;  // lane l looks at the l-th descriptor behind
+                    unsigned long long d = 2ull << 32;  // before the first tile: an inclusive prefix of zero
+                    if (q >= 0) {
+                        do { d = D[q]; } while ((d >> 32) == 0ull);
+                    }
+                    const uint32_t incl = __ballot_sync(0xffffffffu, (d >> 32) == 2ull);
+                    const int first = __ffs(incl) - 1;  // the nearest inclusive prefix, -1 = none among these 32
+                    uint32_t v = (first < 0 || lane <= first) ? (uint32_t)d : 0u;
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                    prefix += v;
+                    if (first >= 0) break;
+                }
+                if (lane == 0) D[tile] = (unsigned long long)(prefix + total) | (2ull << 32);
             }
-            s_prefix = prefix;
-            if (tile == ntiles - 1 && total_out) *total_out = prefix + total;
+            if (lane == 0) {
+                s_prefix = prefix;
+                if (tile == ntiles - 1 && total_out) *total_out = prefix + total;
+            }
         }
         __syncthreads();
         ex += s_prefix;

@@ -137,9 +137,15 @@ __device__ __forceinline__ void contact_model(const MatPair& mp, float h, float 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// sphere--sphere contacts.  One thread per contact over the virtual concatenation of the two sphere--sphere lists
-// (contacts in touch at the last rebuild first, mere candidates after them: warps are then homogeneous and the
-// candidates' warps skip the force model).  Counts are DEVICE-resident (no host sync).
+// sphere--sphere contacts, PLAIN kernel.  One thread per contact over the virtual concatenation of the two
+// sphere--sphere lists (contacts in touch at the last rebuild first, mere candidates after them: warps are then
+// homogeneous and the candidates' warps skip the force model).  Counts are DEVICE-resident (no host sync).  No shared
+// memory: the whole L1 serves the owner gathers (every KB of shared memory taken from it costs this kernel time: 118 us
+// for the touching list with none, 121 with 8 KB, 125 with 36 KB per CTA).  This is the kernel of choice while the
+// lists are short-lived (cd_update_freq < 32): every candidate is looked at every step, but its 16-byte record is
+// streamed, whereas the kernel below, which skips the candidates that cannot touch yet, has to fetch the records of
+// those that are due as scattered sectors -- on the settled 1M-clump bed at 20 steps per list both take the same 37-40 us
+// for the candidates (tools/tune2.py, gpurun_out/r2b_tune*.log); at 60 steps per list it is 93 us against 64.
 template <int MODEL, bool RECORD, int MINB, bool FAST>
 __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ DevParams P) {
     if (P.flags[DEM_FLAG_POISON]) return;
@@ -150,13 +156,6 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
     const uint32_t nround = (n + 31u) & ~31u;  // whole warps take part in the A-side reduction
     const uint32_t cfirst = (P.force_opts & 8u) ? (nT & ~31u) : 0u;
     const int lane = threadIdx.x & 31;
-    // integrations since the rebuild that made these lists: a candidate whose gap cannot have closed yet is skipped
-    // after its 16-byte record alone (no owner gathers) -- it cannot be in touch, so it contributes nothing.
-    // Measured on the settled 1M-clump bed (tools/force_opts_prof.py): the candidate list costs 50 us of the 158 with or
-    // without the skip and with or without the lazy velocity fetch, and fetching the next record ahead in registers made
-    // the kernel slower (170 us): the loop runs at the speed of one thread's chain of dependent loads at 50 %
-    // occupancy, not of the memory pipes.  The skip is therefore off by default (force_opts bit 0).
-    const uint32_t cyc = (P.force_opts & 1u) ? P.flags[DEM_FLAG_CYCLE_STEP] : 0xffffffffu;
     const bool lazy = (P.force_opts & 2u) != 0u;
     for (uint32_t c = cfirst + blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += step) {
         float wA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -171,10 +170,6 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
         if (work) {
             ci = __ldcs(&cinfo[idx]);  // streaming: evict-first
             keyA = ci.x;
-            if (!inT && (ci.w >> 31) == 0u && ((ci.w >> CINFO_FIRST_SHIFT) & 0xffu) > cyc) {
-                work = false;
-                if (RECORD) P.sn.force[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
         }
         if (work) {
         const uint32_t oA = ci.x, oB = ci.y;
@@ -282,6 +277,318 @@ __global__ void __launch_bounds__(256, MINB) k_force_ss(const __grid_constant__ 
                 red_add_v4(&P.wrench[keyA].f, wA[0], wA[1], wA[2]);
                 red_add_v4(&P.wrench[keyA].t, wA[3], wA[4], wA[5]);
             }
+        }
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// sphere--sphere contacts, kernel for LONG-LIVED lists.  One thread per contact: first the list of the pairs that were in touch at the last rebuild,
+// then the mere candidates (warps are homogeneous: candidate warps hardly ever run the force model).  Counts are
+// DEVICE-resident (no host sync).
+//
+// Candidates are the larger half of the work items of a settled bed and almost all of them are apart, so each carries
+// the next step of the list's cycle at which it can possibly touch (one byte, ContactList::due): the margin of an owner
+// IS the bound on how far it travels during the maxDrift steps a list is used (DEMMiscKernels.cu:37-61), so a gap g
+// cannot close in fewer than g / c steps, c = (marginA + marginB) / maxDrift (the margins ride along in the owner
+// records as a byte each, relative to the largest one: no extra gather).  The sweep sets the first value
+// (kernels_sweep.cu), and every evaluation that finds the pair still apart REFRESHES it from the exact gap it just
+// computed: a pair that stays g apart is looked at every g / c steps, so a cycle of D steps costs about ln D
+// evaluations per candidate instead of D -- and lengthening the cycle costs the force kernel next to nothing.  A pair
+// that is not evaluated contributes nothing (it cannot overlap), hence identical results.
+// A warp that skipped some of its lanes would still wait for the owner gathers of the others, so the candidate phase
+// COMPACTS per warp: each warp streams its contiguous share of the due bytes (one 32-bit load = 4 candidates per lane),
+// queues the indices of those that are due (order preserved: the list stays owner-major for the A-side reduction) in a
+// small ring in shared memory and pops 32 at a time.  No CTA barrier: the warps stay independent, which is what hides
+// the latency of the dependent gathers.
+
+// The step of the cycle at which a candidate that is `gap` apart now has to be looked at again: the gap closes by at
+// most (marginA + marginB) / maxDrift per step; inv_closing = maxDrift / (2 max margin), the owners' flag bytes hold
+// 255 - c with margin <= max margin (c + 1) / 256 (0.999, -1e-9 m: rounding of the float gap).
+__device__ __forceinline__ uint32_t cand_due_step(float gap, float inv_closing, uint32_t flagsA, uint32_t flagsB, uint32_t cyc) {
+    const float parts = (float)(512u - flagsA - flagsB);  // (cA + 1) + (cB + 1) of 512
+    const float steps = fminf(fmaxf(__fdividef((gap - 1e-9f) * inv_closing * (0.999f * 512.f), parts), 0.f), 250.f);
+    return min(cyc + (uint32_t)steps, 255u);
+}
+
+// One contact (lane) of a warp: narrow phase, force model, B-side reductions; then the warp's A-side reduction.  Called
+// by whole warps (lanes without a contact pass work = false).  IN_T: the list of pairs in touch at the rebuild.
+template <int MODEL, bool RECORD, bool FAST, bool IN_T>
+__device__ __forceinline__ void ss_contact(const DevParams& P, bool work, uint32_t idx, int lane, bool lazy, uint32_t cyc,
+                                           float inv_closing) {
+    float wA[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    uint32_t keyA = 0xffffffffu - (uint32_t)lane;  // never equal to a neighbour's key
+    bool touch = false;
+    uint4* const cinfo = IN_T ? P.ss.cinfo : P.sn.cinfo;
+    float4* const histp = IN_T ? P.ss.hist : P.sn.hist;
+    if (work) {
+        const uint4 ci = __ldcs(&cinfo[idx]);  // streaming: evict-first
+        keyA = ci.x;
+        const uint32_t oA = ci.x, oB = ci.y;
+        const bool alive = (ci.w >> 31) != 0u;
+        float4 hist = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (MODEL == 0 && alive) hist = __ldcs(&histp[idx]);
+        const float4 compA = __ldg(&P.comp[ci.z & 0xffffu]);
+        const float4 compB = __ldg(&P.comp[ci.z >> 16]);
+        OwnerPos pA, pB;
+        End A, B;
+        load_owner_geom(P.state, oA, pA, A);
+        load_owner_geom(P.state, oB, pB, B);
+        // velocities are only needed for pairs in touch: the list of pairs that overlapped at the rebuild fetches them
+        // up front (independent loads in flight together), the candidate list only once the narrow phase says so
+        if (IN_T || !lazy) {
+            load_owner_kin(P.state, oA, A);
+            load_owner_kin(P.state, oB, B);
+        }
+
+        // ---- narrow phase (checkSpheresOverlap<double,float>, DEMHelperKernels.cuh:292-326) ----
+        const float3 relA = rotate(f3(compA.x, compA.y, compA.z), A.q);
+        const float3 relB = rotate(f3(compB.x, compB.y, compB.z), B.q);
+        long long ax, ay, az, bx, by, bz;
+        pos_ints(pA, P.nvXp2, P.nvYp2, ax, ay, az);
+        pos_ints(pB, P.nvXp2, P.nvYp2, bx, by, bz);
+        // centre(A) - centre(B): exact integer owner difference (units of l) + rotated offsets
+        const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
+        const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
+        const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
+        const double d2 = dx * dx + dy * dy + dz * dz;
+        const float rA = compA.w, rB = compB.w;
+        const double R = (double)rA + (double)rB;
+        float3 nrm = f3((float)dx, (float)dy, (float)dz);
+        const float mag2 = dot(nrm, nrm);
+        const float imag = FAST ? rsqrtf(fmaxf(mag2, 1e-37f)) : 0.f;
+        const float mag = FAST ? mag2 * imag : sqrtf(mag2);
+        // overlap = R - |d| = (R^2 - d^2) / (R + |d|): numerator in double, the rest in float
+        const float depth = fdiv<FAST>((float)(R * R - d2), (float)R + mag);
+
+        if (depth > 0.f) {
+            if (!IN_T && lazy) {
+                load_owner_kin(P.state, oA, A);
+                load_owner_kin(P.state, oB, B);
+            }
+            nrm = nrm * (FAST ? imag : 1.f / mag);
+            // contact point = centre(B) + (rB - depth/2) n ; lever arms from each owner (world frame)
+            const float s = rB - 0.5f * depth;
+            const float3 armB = relB + s * nrm;
+            const float3 armA = f3(relA.x - (float)dx, relA.y - (float)dy, relA.z - (float)dz) + s * nrm;
+            const MatPair mp = P.matpair[ci.w & 0xffffu];
+            float3 force, troll;
+            contact_model<MODEL, FAST>(mp, P.h, depth, nrm, armA, armB, A, B, rA, rB, hist, force, troll);
+            // wrench scatter (forceToAcc semantics; force and WORLD-frame torque sums, divided by mass / rotated and
+            // divided by MOI once per owner in the integrator)
+            const float3 Ft = force + troll;
+            const float3 TA = cross(armA, Ft);
+            const float3 TB = cross(Ft, armB);  // armB x (-Ft)
+            wA[0] = force.x; wA[1] = force.y; wA[2] = force.z;
+            wA[3] = TA.x; wA[4] = TA.y; wA[5] = TA.z;
+            touch = true;
+            red_add_v4(&P.wrench[oB].f, -force.x, -force.y, -force.z);
+            red_add_v4(&P.wrench[oB].t, TB.x, TB.y, TB.z);
+            if (MODEL == 0) {
+                __stcs(&histp[idx], hist);
+                if (!alive) cinfo[idx].w = ci.w | 0x80000000u;
+            }
+            if (RECORD) {
+                float4* const frc = IN_T ? P.ss.force : P.sn.force;
+                float4* const cpt = IN_T ? P.ss.cpoint : P.sn.cpoint;
+                frc[idx] = make_float4(force.x, force.y, force.z, 0.f);
+                cpt[idx] = contact_point_world(P, pA, armA);
+            }
+        } else {
+            // not in touch: destroy history (FullHertzianForceModel.cu:129-136, DEMCalcForceKernels.cu:258-261)
+            if (MODEL == 0 && alive) {
+                __stcs(&histp[idx], make_float4(0.f, 0.f, 0.f, 0.f));
+                cinfo[idx].w = ci.w & 0x7fffffffu;
+            }
+            // a candidate also learns when it has to be looked at again
+            if (!IN_T && inv_closing > 0.f) {
+                const uint32_t due = cand_due_step(-depth, inv_closing, pA.flags, pB.flags, cyc);
+                if (due > cyc) P.sn.due[idx] = (uint8_t)due;
+            }
+            if (RECORD) {
+                float4* const frc = IN_T ? P.ss.force : P.sn.force;
+                frc[idx] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+    }
+    // A side: the list is owner-major, so the contacts of one owner sit in adjacent lanes. Segmented suffix sum over
+    // runs of equal owner, then ONE pair of vector reductions per run instead of one per contact.
+    if (__any_sync(0xffffffffu, touch)) {
+        // runs = maximal stretches of adjacent lanes with the same owner (robust to any key sequence)
+        const uint32_t kprev = __shfl_up_sync(0xffffffffu, keyA, 1);
+        const bool head = (lane == 0) || (kprev != keyA);
+        const uint32_t heads = __ballot_sync(0xffffffffu, head);
+        const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+        const int run_end = above ? lane + __ffs(above) : 32;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const bool take = lane + off < run_end;
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                const float up = __shfl_down_sync(0xffffffffu, wA[k], off);
+                if (take) wA[k] += up;
+            }
+        }
+        const bool any_force = (wA[0] != 0.f) | (wA[1] != 0.f) | (wA[2] != 0.f) | (wA[3] != 0.f) | (wA[4] != 0.f) | (wA[5] != 0.f);
+        if (head && any_force) {
+            red_add_v4(&P.wrench[keyA].f, wA[0], wA[1], wA[2]);
+            red_add_v4(&P.wrench[keyA].t, wA[3], wA[4], wA[5]);
+        }
+    }
+}
+
+// Screen of ONE candidate that is due: narrow phase only (same expressions as ss_contact, so both agree on who is in
+// touch).  Split in a load half and a compute half so that a lane can have the gathers of two candidates in flight
+// together: the candidate phase runs at the speed of a warp's chain of dependent loads (due bytes -> compiled record ->
+// owner records), not of any pipe.
+struct CandScreen {
+    uint4 ci;
+    OwnerPos pA, pB;
+    float4 qA, qB;
+};
+__device__ __forceinline__ void cand_owners(const DevParams& P, CandScreen& c) {
+    End e;
+    load_owner_geom(P.state, c.ci.x, c.pA, e);
+    c.qA = e.q;
+    load_owner_geom(P.state, c.ci.y, c.pB, e);
+    c.qB = e.q;
+}
+// true: the pair needs the full treatment (it is in touch, or it carries live history that has to be destroyed)
+template <bool FAST>
+__device__ __forceinline__ bool cand_screen(const DevParams& P, const CandScreen& c, uint32_t idx, uint32_t cyc,
+                                            float inv_closing) {
+    const float4 compA = __ldg(&P.comp[c.ci.z & 0xffffu]);
+    const float4 compB = __ldg(&P.comp[c.ci.z >> 16]);
+    const float3 relA = rotate(f3(compA.x, compA.y, compA.z), c.qA);
+    const float3 relB = rotate(f3(compB.x, compB.y, compB.z), c.qB);
+    long long ax, ay, az, bx, by, bz;
+    pos_ints(c.pA, P.nvXp2, P.nvYp2, ax, ay, az);
+    pos_ints(c.pB, P.nvXp2, P.nvYp2, bx, by, bz);
+    const double dx = (double)(ax - bx) * P.l + ((double)relA.x - (double)relB.x);
+    const double dy = (double)(ay - by) * P.l + ((double)relA.y - (double)relB.y);
+    const double dz = (double)(az - bz) * P.l + ((double)relA.z - (double)relB.z);
+    const double d2 = dx * dx + dy * dy + dz * dz;
+    const double R = (double)compA.w + (double)compB.w;
+    const float3 nrm = f3((float)dx, (float)dy, (float)dz);
+    const float mag2 = dot(nrm, nrm);
+    const float mag = FAST ? mag2 * rsqrtf(fmaxf(mag2, 1e-37f)) : sqrtf(mag2);
+    const float depth = fdiv<FAST>((float)(R * R - d2), (float)R + mag);
+    if (depth > 0.f || (c.ci.w >> 31) != 0u) return true;
+    if (inv_closing > 0.f) {
+        const uint32_t due = cand_due_step(-depth, inv_closing, c.pA.flags, c.pB.flags, cyc);
+        if (due > cyc) P.sn.due[idx] = (uint8_t)due;
+    }
+    return false;
+}
+
+constexpr int FQ_LOADS = 6;      // 32-bit words of due bytes filtered per lane and round (4 candidates each)
+constexpr int FQ_SLOTS = 1024;   // per-warp ring of due candidate indices: < 64 left over + 128 * FQ_LOADS new ones
+constexpr int HQ_SLOTS = 128;    // per-warp ring of the screened candidates that need the force model
+static_assert(63 + 128 * FQ_LOADS <= FQ_SLOTS, "ring too small");
+
+template <int MODEL, bool RECORD, int MINB, bool FAST>
+__global__ void __launch_bounds__(256, MINB) k_force_ss_due(const __grid_constant__ DevParams P) {
+    if (P.flags[DEM_FLAG_POISON]) return;
+    __shared__ uint32_t fq[8][FQ_SLOTS];
+    __shared__ uint32_t hq[8][HQ_SLOTS];
+    const int lane = threadIdx.x & 31;
+    // ---- the pairs that were in touch at the rebuild (force_opts bits 2 / 3: measurement only -- leave the candidate
+    //      list / this list out) ----
+    {
+        const uint32_t nT = (P.force_opts & 8u) ? 0u : *P.ss.count;
+        const uint32_t step = gridDim.x * blockDim.x;
+        const uint32_t nround = (nT + 31u) & ~31u;  // whole warps take part in the A-side reduction
+        for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < nround; c += step)
+            ss_contact<MODEL, RECORD, FAST, true>(P, c < nT, c, lane, false, 0u, 0.f);
+    }
+    // ---- the candidates ----
+    const uint32_t nN = (P.force_opts & 4u) ? 0u : *P.sn.count;
+    // a fixed expand factor (beta >= 0) is no bound on anybody's motion: then every candidate is looked at every step
+    const bool skip = (P.force_opts & 1u) != 0u && P.beta < 0.f && P.sn.due != nullptr;
+    const bool lazy = (P.force_opts & 2u) != 0u;
+    // integrations since the rebuild that made these lists
+    const uint32_t cyc = skip ? P.flags[DEM_FLAG_CYCLE_STEP] : 0xffffffffu;
+    const float inv_closing = (skip && (P.force_opts & 32u)) ? __uint_as_float(P.flags[DEM_FLAG_INV_CLOSING]) : 0.f;
+    // compacting: every warp owns a contiguous share of the list (a multiple of 128 candidates: aligned 32-bit loads)
+    uint32_t* const ring = fq[threadIdx.x >> 5];
+    uint32_t* const heavy = hq[threadIdx.x >> 5];
+    const uint32_t nwarps = gridDim.x * 8u;
+    const uint32_t share = ((nN + nwarps - 1u) / nwarps + 127u) & ~127u;
+    uint32_t next = min(nN, (blockIdx.x * 8u + (threadIdx.x >> 5)) * share);  // next unfiltered candidate of this warp
+    const uint32_t last = min(nN, next + share);
+    const uint32_t* const due4 = reinterpret_cast<const uint32_t*>(P.sn.due);
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t qhead = 0u, qcnt = 0u, hhead = 0u, hcnt = 0u;  // warp-uniform ring state
+    for (;;) {
+        // refill the ring until enough due candidates are queued or the share is used up
+        while (qcnt < 64u && next < last) {
+            uint32_t w[FQ_LOADS];
+#pragma unroll
+            for (int u = 0; u < FQ_LOADS; u++) {
+                const uint32_t k = next + (uint32_t)(u * 128 + lane * 4);
+                w[u] = (k < last) ? due4[k >> 2] : 0xffffffffu;  // (plain load: this kernel also stores due bytes)
+            }
+#pragma unroll
+            for (int u = 0; u < FQ_LOADS; u++) {
+                const uint32_t k = next + (uint32_t)(u * 128 + lane * 4);
+                uint32_t m[4];
+                bool d[4];
+                uint32_t below = 0u;  // due candidates of the lanes below me
+#pragma unroll
+                for (int b = 0; b < 4; b++) {
+                    d[b] = (k + b < last) && ((w[u] >> (8 * b)) & 0xffu) <= cyc;
+                    if (RECORD && (k + b < last) && !d[b]) P.sn.force[k + b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    m[b] = __ballot_sync(0xffffffffu, d[b]);
+                    below += (uint32_t)__popc(m[b] & lt);
+                }
+                uint32_t slot = qhead + qcnt + below;
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (d[b]) ring[(slot++) & (FQ_SLOTS - 1)] = k + b;
+                qcnt += (uint32_t)(__popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]));
+            }
+            next += 128u * FQ_LOADS;
+            __syncwarp();
+        }
+        if (qcnt == 0u && hcnt == 0u) break;
+        // ---- screen up to 64 due candidates: both compiled records, then all four owner records, in flight together ----
+        if (qcnt) {
+            const uint32_t take = min(qcnt, 64u);
+            const bool w0 = (uint32_t)lane < take, w1 = (uint32_t)lane + 32u < take;
+            uint32_t i0 = 0u, i1 = 0u;
+            if (w0) i0 = ring[(qhead + (uint32_t)lane) & (FQ_SLOTS - 1)];
+            if (w1) i1 = ring[(qhead + 32u + (uint32_t)lane) & (FQ_SLOTS - 1)];
+            __syncwarp();
+            qhead += take;
+            qcnt -= take;
+            CandScreen c0, c1;
+            c0.ci = c1.ci = make_uint4(0u, 0u, 0u, 0u);
+            if (w0) c0.ci = __ldcs(&P.sn.cinfo[i0]);
+            if (w1) c1.ci = __ldcs(&P.sn.cinfo[i1]);
+            if (w0) cand_owners(P, c0);
+            if (w1) cand_owners(P, c1);
+            const bool h0 = w0 && cand_screen<FAST>(P, c0, i0, cyc, inv_closing);
+            const bool h1 = w1 && cand_screen<FAST>(P, c1, i1, cyc, inv_closing);
+            if (RECORD) {
+                if (w0 && !h0) P.sn.force[i0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (w1 && !h1) P.sn.force[i1] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const uint32_t m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+            if (h0) heavy[(hhead + hcnt + (uint32_t)__popc(m0 & lt)) & (HQ_SLOTS - 1)] = i0;
+            if (h1) heavy[(hhead + hcnt + (uint32_t)__popc(m0) + (uint32_t)__popc(m1 & lt)) & (HQ_SLOTS - 1)] = i1;
+            hcnt += (uint32_t)(__popc(m0) + __popc(m1));
+            __syncwarp();
+        }
+        // ---- the force model for those in touch: full warps, or whatever is left once the share is used up ----
+        while (hcnt >= 32u || (hcnt && qcnt == 0u && next >= last)) {
+            const uint32_t take = min(hcnt, 32u);
+            const bool work = (uint32_t)lane < take;
+            uint32_t idx = 0u;
+            if (work) idx = heavy[(hhead + (uint32_t)lane) & (HQ_SLOTS - 1)];
+            __syncwarp();
+            hhead += take;
+            hcnt -= take;
+            ss_contact<MODEL, RECORD, FAST, false>(P, work, idx, lane, lazy, cyc, inv_closing);
         }
     }
 }
@@ -762,9 +1069,25 @@ __global__ void __launch_bounds__(256, 4) k_integrate(const __grid_constant__ De
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Which sphere--sphere kernel: the one that leaves candidates alone until they are due needs motion-bounded margins
+// (beta < 0) and lists that live long enough for the skipping to pay for the scattered record fetches (see the comment
+// on k_force_ss); force_opts bit 6 forces it (tests, measurements).
+static bool use_due_kernel(const DevParams& P) {
+    const bool can = (P.force_opts & 1u) && (P.force_opts & 16u) && P.beta < 0.f && P.sn.due != nullptr;
+    return can && (P.maxDrift >= 32u || (P.force_opts & 64u));
+}
+
 template <int MINB, bool FAST>
 static void launch_force_ss_t(const DevParams& P, int model, bool record, int grid, cudaStream_t s) {
     const int block = 256;
+    if (use_due_kernel(P)) {
+        if (model == DEM_HERTZIAN) {
+            if (record) k_force_ss_due<0, true, MINB, FAST><<<grid, block, 0, s>>>(P); else k_force_ss_due<0, false, MINB, FAST><<<grid, block, 0, s>>>(P);
+        } else {
+            if (record) k_force_ss_due<1, true, MINB, FAST><<<grid, block, 0, s>>>(P); else k_force_ss_due<1, false, MINB, FAST><<<grid, block, 0, s>>>(P);
+        }
+        return;
+    }
     if (model == DEM_HERTZIAN) {
         if (record) k_force_ss<0, true, MINB, FAST><<<grid, block, 0, s>>>(P); else k_force_ss<0, false, MINB, FAST><<<grid, block, 0, s>>>(P);
     } else {

@@ -17,7 +17,11 @@
 //     deterministic, owner-major (the force kernel streams the A side and reduces it inside the warp) and there is NO
 //     cap on the number of candidates per sphere (the reference allows up to 32768 spheres per bin,
 //     DEMContactKernels_SphereSphere.cu:121-126).  The distance tests run ONCE: the count pass hands the candidates
-//     it accepted to the fill pass through a 64-byte record per sphere.
+//     it accepted to the fill pass through a 48-byte record per sphere;
+//   * the count pass is bound by the instruction issue rate, so its inner loop is kept convergent: a thread walks its
+//     five runs as ONE loop (the warp pays max-over-lanes of the total, not the sum over runs of the per-run maxima)
+//     that does nothing but the distance test and notes the hits in shared memory; the acceptance rule (owner, family
+//     mask, extra margin, touching or not, first step due) runs in a second, short loop over the hits.
 #include "dem_kernels.h"
 
 namespace demb {
@@ -25,12 +29,18 @@ namespace demb {
 constexpr int SW_THREADS = 128;  // sorted positions per work item
 constexpr int SW_CH = 160;       // staged entries per run and phase (even: the 8-byte stream stays 16-byte aligned)
 
+constexpr int SW_HITS = 16;      // distance-test hits a thread notes before it stops to judge them
+
 struct __align__(16) SweepSmem {
-    float4 sph[5][SW_CH];
-    uint2 aux[5][SW_CH];
+    float4 sph[5 * SW_CH];
+    uint2 aux[5 * SW_CH];
     unsigned long long mbar;
     uint32_t rb[5], re[5];
+    uint32_t pb[5];                          // sorted position of staged entry i of run r = i + pb[r] (i = flat index)
+    uint32_t rng[5][SW_THREADS];             // per thread and run: its stretch as flat indices, first | end << 16
+    unsigned short hit[SW_HITS][SW_THREADS]; // flat indices of the staged spheres that passed the distance test
 };
+static_assert(5 * SW_CH < 65536, "flat indices are 16 bits");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -62,12 +72,12 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  : "memory");
 }
 
-// Per sorted position j the count pass leaves the candidates it accepted in cand[j * SW_K .. ): the candidate's sorted
+// Per sorted position j the count pass leaves the candidates it accepted in cand[j * SW_REC .. ): the candidate's sorted
 // position | CAND_TOUCH | CAND_NOHIST.  The fill pass only has to look those up -- it never repeats a distance test.  A
 // sphere with more than SW_K accepted candidates (dense polydisperse packings, many-component clumps) is rare; the fill
 // pass finds its candidates again with plain loads (fill_slow).
-constexpr uint32_t SW_K = 16;
-constexpr uint32_t SW_REC = SW_K + SW_K / 4;  // words per record: SW_K candidates + one "first step" byte for each
+constexpr uint32_t SW_K = 8;
+constexpr uint32_t SW_REC = 12;  // words per record: SW_K candidates, SW_K "first step" bytes, nT | nN << 16, spare
 constexpr uint32_t CAND_TOUCH = 0x80000000u;
 constexpr uint32_t CAND_NOHIST = 0x40000000u;
 constexpr uint32_t CAND_POS = 0x3fffffffu;
@@ -195,7 +205,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
             extraA = P.familyExtraMargin[myFam];
         }
         uint32_t* mycand = C.cand + (size_t)j * SW_REC;
-        uint8_t* myfirst = reinterpret_cast<uint8_t*>(mycand + SW_K);
+        uint32_t first_lo = 0u, first_hi = 0u;  // the "first step" bytes of candidates 0-3 / 4-7
         // ---- phases: stage up to SW_CH entries of every run, test, advance ----
         for (;;) {
             uint32_t cnt[5];
@@ -214,32 +224,70 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
                 for (int r = 0; r < 5; r++) bytes += cnt[r] * 24u;
                 mbar_expect_tx(&sm.mbar, bytes);
 #pragma unroll
-                for (int r = 0; r < 5; r++)
+                for (int r = 0; r < 5; r++) {
                     if (cnt[r]) {
-                        bulk_g2s(&sm.sph[r][0], C.sortedSph + pos[r], cnt[r] * 16u, &sm.mbar);
-                        bulk_g2s(&sm.aux[r][0], C.sortedAux + pos[r], cnt[r] * 8u, &sm.mbar);
+                        bulk_g2s(&sm.sph[r * SW_CH], C.sortedSph + pos[r], cnt[r] * 16u, &sm.mbar);
+                        bulk_g2s(&sm.aux[r * SW_CH], C.sortedAux + pos[r], cnt[r] * 8u, &sm.mbar);
                     }
+                    sm.pb[r] = pos[r] - (uint32_t)(r * SW_CH);
+                }
+            }
+            // my stretch of every run in this phase, as flat indices into the staged arrays
+#pragma unroll
+            for (int r = 0; r < 5; r++) {
+                const uint32_t lo = max(qb[r], pos[r]);
+                const uint32_t hi = min(qe[r], pos[r] + cnt[r]);
+                uint32_t w = 0u;
+                if (valid && lo < hi) w = ((uint32_t)(r * SW_CH) + lo - pos[r]) | (((uint32_t)(r * SW_CH) + hi - pos[r]) << 16);
+                sm.rng[r][tid] = w;
             }
             // one thread waits for the bulk copies (try_wait spins: 127 other threads would only burn issue slots),
             // the CTA barrier releases the rest
             if (tid == 0) mbar_wait(&sm.mbar, parity);
             parity ^= 1u;
             __syncthreads();
-            if (valid) {
-#pragma unroll
-                for (int r = 0; r < 5; r++) {
-                    const uint32_t lo = max(qb[r], pos[r]);
-                    const uint32_t hi = min(qe[r], pos[r] + cnt[r]);
-                    for (uint32_t q = lo; q < hi; q++) {
-                        const float4 ot = sm.sph[r][q - pos[r]];
+            {
+                int r = -1;
+                uint32_t a = 0u, b = 0u;
+                bool done = false;
+                while (!done) {
+                    // (1) distance tests only, all five runs as one loop
+                    uint32_t nh = 0u;
+                    for (;;) {
+                        if (a >= b) {
+                            do {
+                                r++;
+                                if (r < 5) {
+                                    const uint32_t w = sm.rng[r][tid];
+                                    a = w & 0xffffu;
+                                    b = w >> 16;
+                                }
+                            } while (r < 5 && a >= b);
+                            if (r >= 5) { done = true; break; }
+                        }
                         float d2;
-                        if (!pair_near(me, ot, d2)) continue;
+                        if (pair_near(me, sm.sph[a], d2)) {
+                            sm.hit[nh][tid] = (unsigned short)a;
+                            nh++;
+                        }
+                        a++;
+                        if (nh == (uint32_t)SW_HITS) break;
+                    }
+                    // (2) the acceptance rule for the hits
+                    for (uint32_t k = 0; k < nh; k++) {
+                        const uint32_t i = sm.hit[k][tid];
+                        const uint32_t q = i + sm.pb[i / (uint32_t)SW_CH];
+                        const float4 ot = sm.sph[i];
+                        float d2;
+                        pair_near(me, ot, d2);
                         uint32_t first;
-                        const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[r][q - pos[r]], d2, q, fam_on, myFam, extraA,
-                                                             want_hist, first);
+                        const uint32_t v = pair_verdict_near(P, C, me, myAux, ot, sm.aux[i], d2, q, fam_on, myFam, extraA, want_hist, first);
                         if (v == 0u) continue;
-                        const uint32_t k = nT + nN;
-                        if (k < SW_K) { mycand[k] = q | (v & ~1u); myfirst[k] = (uint8_t)first; }
+                        const uint32_t kk = nT + nN;
+                        if (kk < SW_K) {
+                            mycand[kk] = q | (v & ~1u);
+                            if (kk < 4u) first_lo |= first << (8u * kk); else first_hi |= first << (8u * (kk - 4u));
+                        }
                         if (v & CAND_TOUCH) nT++; else nN++;
                     }
                 }
@@ -252,6 +300,7 @@ __global__ void __launch_bounds__(SW_THREADS) k_sweep_tma(const __grid_constant_
             const uint32_t sid = C.sortedMeta[j].y;
             P.ss.seg_count[sid] = nT;
             P.sn.seg_count[sid] = nN;
+            reinterpret_cast<uint4*>(mycand)[2] = make_uint4(first_lo, first_hi, min(nT, 0xffffu) | (min(nN, 0xffffu) << 16), 0u);
         }
     }
 }
@@ -267,7 +316,8 @@ __device__ __forceinline__ void emit_contact(const DevParams& P, const CdParams&
     L.idB[slot] = om.y;
     (touching ? C.idA_ss : C.idA_sn)[slot] = sid;
     L.cinfo[slot] = make_uint4(ownerA, om.x, (metaA_z & 0xffffu) | ((om.z & 0xffffu) << 16),
-                               matpair | (first << CINFO_FIRST_SHIFT) | ((flags & CAND_NOHIST) ? CINFO_NO_HISTORY : 0u));
+                               matpair | ((flags & CAND_NOHIST) ? CINFO_NO_HISTORY : 0u));
+    if (!touching) L.due[slot] = (uint8_t)first;
 }
 
 // FILL pass: one thread per sorted position; the compiled records go to seg_start[sphere] + k (seg_start = exclusive scan
@@ -280,16 +330,18 @@ __global__ void __launch_bounds__(256) k_sweep_fill(const __grid_constant__ DevP
     const bool fam_on = (C.any_mask != 0) || (C.max_extra > 0.f);
     const bool want_hist = P.sn.hist != nullptr;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nSorted; j += gridDim.x * blockDim.x) {
+        const uint4* cp = reinterpret_cast<const uint4*>(C.cand + (size_t)j * SW_REC);
+        const uint4 tail = cp[2];  // {first bytes 0-3, first bytes 4-7, nT | nN << 16, -}
+        const uint32_t n = (tail.z & 0xffffu) + (tail.z >> 16);
+        if (n == 0u) continue;
         const uint4 meta = C.sortedMeta[j];
         const uint32_t sid = meta.y;
-        const uint32_t n = P.ss.seg_count[sid] + P.sn.seg_count[sid];
-        if (n == 0u) continue;
         uint32_t slotT = P.ss.seg_start[sid], slotN = P.sn.seg_start[sid];
         if (n <= SW_K) {
-            const uint4* cp = reinterpret_cast<const uint4*>(C.cand + (size_t)j * SW_REC);
-            const uint4 f4 = cp[SW_K / 4];
-            const uint32_t fw[4] = {f4.x, f4.y, f4.z, f4.w};
-            for (uint32_t k0 = 0; k0 < n; k0 += 4) {
+            const uint32_t fw[2] = {tail.x, tail.y};
+#pragma unroll
+            for (uint32_t k0 = 0; k0 < SW_K; k0 += 4) {
+                if (k0 >= n) break;
                 const uint4 c4 = cp[k0 >> 2];
                 const uint32_t c[4] = {c4.x, c4.y, c4.z, c4.w};
                 const uint32_t f = fw[k0 >> 2];

@@ -912,3 +912,71 @@ def test_adaptive_update_frequency_keeps_the_physics(built):
     assert int(fixed.stats().cd_update_freq) == 10
     for e in (fixed, fixed_p, tuned):
         e.close()
+
+
+def _rotate_wxyz(v, q):
+    """applyOriQToVector3 (reference DEMHelperKernels.cuh:161-173) in double, vectorised."""
+    w, x, y, z = (q[:, k] for k in range(4))
+    out = np.empty_like(v)
+    out[:, 0] = (2 * (w * w + x * x) - 1) * v[:, 0] + 2 * (x * y - w * z) * v[:, 1] + 2 * (x * z + w * y) * v[:, 2]
+    out[:, 1] = 2 * (x * y + w * z) * v[:, 0] + (2 * (w * w + y * y) - 1) * v[:, 1] + 2 * (y * z - w * x) * v[:, 2]
+    out[:, 2] = 2 * (x * z - w * y) * v[:, 0] + 2 * (y * z + w * x) * v[:, 1] + (2 * (w * w + z * z) - 1) * v[:, 2]
+    return out
+
+
+def test_skipped_candidates_cannot_be_in_touch(built):
+    """The force kernel leaves a sphere--sphere candidate alone until the step of the list's cycle at which its gap can
+    have closed (one "due" byte per candidate, set by the sweep and refreshed by every evaluation; the bound is the margin
+    the reference grants per step, DEMMiscKernels.cu:37-61).  Invariant checked here on a falling, colliding clump bed at
+    several points of several cycles: every candidate the NEXT force kernel would skip is apart (double precision, from
+    the downloaded owner state) -- so skipping it changes nothing -- and a good share of the list is in fact skipped."""
+    sc = scenes.config2_clumps(40, 24, 20, cd_update_freq=20, spacing=2.7, init_vel=(0.2, 0.0, -1.5))
+    f = scenes.flatten(sc)
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    eng.set_option("force_opts", 1 | 2 | 16 | 32 | 64)  # bit 6: the due-step kernel even for lists of 20 steps
+    rel = np.stack([f.CDRelPosX, f.CDRelPosY, f.CDRelPosZ], 1).astype("f8")
+    rad = np.asarray(f.Radii, "f8")
+    done, n_skipped, n_seen, cycs = 0, 0, 0, set()
+    for target in (1503, 1507, 1515, 1519, 2401, 2410, 2419, 3338):
+        eng.step(target - done)
+        done = target
+        cyc = int(eng.debug_download("flags", 8)[6])
+        cycs.add(cyc)
+        st = eng.stats()
+        nN = st.n_contacts_ss - st.n_contacts_ss_touching
+        ci = eng.debug_download("sn_cinfo", 4 * nN).reshape(-1, 4)
+        due = eng.debug_download("sn_due", (nN + 3) // 4).view("u1")[:nN]
+        w = ci[:, 3]
+        skipped = due > cyc
+        assert not (skipped & ((w >> 31) != 0)).any(), "a pair with live history must be looked at every step"
+        x = eng.positions()
+        q = eng.owner_state()["oriQ"].astype("f8")
+        cA, cB = (ci[:, 2] & 0xffff).astype("i8"), (ci[:, 2] >> 16).astype("i8")
+        oA, oB = ci[:, 0].astype("i8"), ci[:, 1].astype("i8")
+        a = x[oA] + _rotate_wxyz(rel[cA], q[oA])
+        b = x[oB] + _rotate_wxyz(rel[cB], q[oB])
+        gap = np.linalg.norm(a - b, axis=1) - rad[cA] - rad[cB]
+        print("step %d (cycle step %d): %d of %d candidates skipped, smallest gap among them %.3e, %d candidates in touch" % (
+            target, cyc, int(skipped.sum()), len(w), gap[skipped].min() if skipped.any() else np.inf, int((gap < 0).sum())))
+        assert (gap[skipped] > 0).all(), (target, cyc, gap[skipped].min())
+        n_skipped += int(skipped.sum())
+        n_seen += len(w)
+    assert len(cycs) >= 4
+    assert n_skipped > 0.2 * n_seen, (n_skipped, n_seen)
+    eng.close()
+
+
+@pytest.mark.parametrize("kind", ["clumps_full", "spheres_frictionless"])
+def test_due_step_kernel_matches_oracle(built, kind):
+    """The trajectory and single-step tests above run the plain sphere--sphere kernel (lists of 20 steps or fewer); this
+    one forces the kernel that leaves candidates alone until they are due (k_force_ss_due, chosen by itself for lists
+    that live 32 steps or more) onto the same scenes and holds it to the same yardstick against the oracle."""
+    po = _oracle()
+    f = scenes.flatten(_mk(kind))
+    eng = demb200.Engine(0)
+    eng.load_flat(f)
+    eng.set_option("force_opts", 1 | 2 | 16 | 32 | 64)
+    w = po.world_from_flat(f)
+    _check_trajectory(eng, f, w, (300, 1000, 2500), kind + " (due-step kernel)")
+    eng.close()

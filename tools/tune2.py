@@ -19,6 +19,9 @@ ap.add_argument("--settle-steps", type=int, default=80000)
 ap.add_argument("--steps", type=int, default=200)
 ap.add_argument("--spacing", type=float, default=2.7)
 ap.add_argument("--freqs", default="")
+ap.add_argument("--late-options", default="", help="like --options, timed last (for settings that disturb the bed)")
+ap.add_argument("--due", type=int, default=0, help="force_opts value to print the due-candidate counts of a cycle for")
+ap.add_argument("--pairs", type=int, default=0, help="print the owner-pair statistics of the settled bed")
 ap.add_argument("--options", default="b_agg=0;b_agg=1;b_agg=0;b_agg=1;fast_encode=3;fast_encode=1")
 args = ap.parse_args()
 
@@ -35,13 +38,14 @@ print("settled %d steps in %.1f s: ss %d (touching %d) sa %d, max|v| %.4f" % (
 
 
 import numpy as np  # noqa: E402
-idA, idB, ct, wc = eng.contacts()
-ss = ct == 1
-own = np.asarray(f.ownerClumpBody)
-oa, ob = own[idA[ss]].astype("u8"), own[idB[ss]].astype("u8")
-alive = np.abs(wc[ss]).sum(axis=1) > 0
-print("sphere pairs %d, alive %d; distinct owner pairs: all %d, alive %d" % (
-    ss.sum(), alive.sum(), len(np.unique(oa * (1 << 32) + ob)), len(np.unique(oa[alive] * (1 << 32) + ob[alive]))), flush=True)
+if args.pairs:
+    idA, idB, ct, wc = eng.contacts()
+    ss = ct == 1
+    own = np.asarray(f.ownerClumpBody)
+    oa, ob = own[idA[ss]].astype("u8"), own[idB[ss]].astype("u8")
+    alive = np.abs(wc[ss]).sum(axis=1) > 0
+    print("sphere pairs %d, alive %d; distinct owner pairs: all %d, alive %d" % (
+        ss.sum(), alive.sum(), len(np.unique(oa * (1 << 32) + ob)), len(np.unique(oa[alive] * (1 << 32) + ob[alive]))), flush=True)
 
 
 def rnd(r):
@@ -53,6 +57,20 @@ for opt in [o for o in args.options.split(";") if o]:
     eng.set_option(name, float(val))
     eng.profile_steps(20)
     print("%-16s %s" % (opt, rnd(eng.profile_steps(args.steps))), flush=True)
+
+if args.due:
+    # how many candidates are due (not skipped) at each step of a cycle
+    eng.set_option("force_opts", float(args.due))
+    eng.step(40)
+    for k in range(21):
+        eng.step(1)
+        st = eng.stats()
+        nN = st.n_contacts_ss - st.n_contacts_ss_touching
+        first = eng.debug_download("sn_due", (nN + 3) // 4).view("u1")[:nN]
+        cyc = int(eng.debug_download("flags", 8)[6])
+        due = first <= cyc
+        print("cycle step %2d: %8d of %8d candidates due (%.1f %%), due byte: median %d max %d; max margin %.3e" % (
+            cyc, int(due.sum()), nN, 100.0 * due.mean(), int(np.median(first)), int(first.max()), st.max_margin), flush=True)
 
 for k in [int(x) for x in args.freqs.split(",") if x]:
     eng.params.cd_update_freq = k
@@ -67,3 +85,9 @@ for k in [int(x) for x in args.freqs.split(",") if x]:
     st = eng.stats()
     print("cd_update_freq=%-3d %8.1f steps/s   ss %d (touching %d)  margin %.6f  rebuild %s" % (
         k, n / dt, st.n_contacts_ss, st.n_contacts_ss_touching, st.max_margin, rnd(eng.profile_rebuild())), flush=True)
+
+for opt in [o for o in args.late_options.split(";") if o]:
+    name, val = opt.split("=")
+    eng.set_option(name, float(val))
+    eng.profile_steps(20)
+    print("%-16s %s" % (opt, rnd(eng.profile_steps(args.steps))), flush=True)
