@@ -105,6 +105,12 @@ def main():
         f.write(subst(read(ref, "DEMBinSphereKernels.cu"), common))
     with open(os.path.join(out, "contact_ss.inc"), "w") as f:
         f.write(subst(read(ref, "DEMContactKernels_SphereSphere.cu"), common))
+    # ---- sphere--triangle broad phase: facet sandwich + facet -> bin registration (per-thread kernels, executed), and the
+    #      per-bin sweep (block-cooperative: only its per-thread helper functions are called) ----
+    with open(os.path.join(out, "bintriangle.inc"), "w") as f:
+        f.write(subst(read(ref, "DEMBinTriangleKernels.cu"), common))
+    with open(os.path.join(out, "contact_st.inc"), "w") as f:
+        f.write(subst(read(ref, "DEMContactKernels_SphereTriangle.cu"), common))
 
     # ---- integration: family prescriptions are table driven (constants only), see
     #      equipFamilyPrescribedMotions, APIPrivate.cpp:1601-1708 ----

@@ -14,10 +14,16 @@
  *   integrateOwners          src/kernel/DEMIntegrationKernels.cu:256
  *   computeMarginFromAbsv / fillMarginValues   src/kernel/DEMMiscKernels.cu:37,63
  *   getNumberOfBinsEachSphereTouches / populateBinSphereTouchingPairs   src/kernel/DEMBinSphereKernels.cu:11,133
- * plus the device function calcContactPoint (src/kernel/DEMContactKernels_SphereSphere.cu:57).
+ *   makeTriangleSandwich / getNumberOfBinsEachTriangleTouches / populateBinTriangleTouchingPairs
+ *                            src/kernel/DEMBinTriangleKernels.cu:22,87,139 (with DEMTriangleBoxIntersect.cu)
+ * plus the device functions calcContactPoint (src/kernel/DEMContactKernels_SphereSphere.cu:57), fillSharedMemSpheres /
+ * fillSharedMemTriangles (src/kernel/DEMContactKernels_SphereTriangle.cu:16,75), triangle_sphere_CD_directional and
+ * snap_to_face (src/kernel/DEMCollisionKernels.cu).
  */
 #include "cuda_host_shim.h"
 
+#include <algorithm>
+#include <utility>
 #include <vector>
 #include <cstring>
 
@@ -74,6 +80,12 @@ namespace ref_bin {
 }
 namespace ref_css {
 #include "contact_ss.inc"
+}
+namespace ref_bintri {
+#include "bintriangle.inc"
+}
+namespace ref_cst {
+#include "contact_st.inc"
 }
 namespace ref_euler {
 #include "integrate_euler.inc"
@@ -159,6 +171,10 @@ void bind(OrcWorld* w, Bound& b) {
     k.marginSize = w->marginSize; k.familyMasks = w->familyMasks;
     k.familyExtraMarginSize = w->familyExtraMarginSize;
     k.ownerClumpBody = w->ownerClumpBody; k.clumpComponentOffset = b.comp8.data();
+    k.ownerMesh = w->ownerMesh;
+    k.relPosNode1 = reinterpret_cast<float3*>(w->relPosNode1);
+    k.relPosNode2 = reinterpret_cast<float3*>(w->relPosNode2);
+    k.relPosNode3 = reinterpret_cast<float3*>(w->relPosNode3);
 }
 
 int g_threads = 1;
@@ -272,6 +288,152 @@ long ref_sphere_anal_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_
         outSphere[i] = idA[i]; outObj[i] = idB[i]; outType[i] = ct[i];
     }
     return cnt;
+}
+
+/* Sphere--triangle contact candidates as the reference finds them (contactDetection(), src/algorithms/
+ * DEMCubContactDetection.cu:262-470): facet sandwich, facet -> bin and sphere -> bin registration through the reference's
+ * own per-thread kernels; then, for every bin that holds both, the pair test of getNumberOfSphTriContactsEachBin
+ * (src/kernel/DEMContactKernels_SphereTriangle.cu:196-262) restated around the reference's own device functions (that
+ * kernel is block-cooperative: shared-memory staging + __syncthreads, it cannot run through the shim).
+ * Returns the number of (sphere, triangle) pairs written, or -1 if cap is too small; triBins (nTri entries, may be
+ * NULL) receives the number of bins each facet registered in. */
+long ref_sphere_tri_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_t nbY, uint32_t nbZ, uint32_t* outSphere,
+                             uint32_t* outTri, long cap, uint32_t* triBins) {
+    Bound b; bind(w, b);
+    b.sp.binSize = binSize; b.sp.nbX = nbX; b.sp.nbY = nbY; b.sp.nbZ = nbZ;
+    const uint32_t nT = w->nTri, nS = w->nSpheres;
+    if (nT == 0 || nS == 0) return 0;
+    std::vector<float3> sA1(nT), sA2(nT), sA3(nT), sB1(nT), sB2(nT), sB3(nT);
+    launch(nT, 128, [&] {
+        ref_bintri::makeTriangleSandwich(&b.sp, &b.kt, sA1.data(), sA2.data(), sA3.data(), sB1.data(), sB2.data(), sB3.data());
+    });
+    std::vector<deme::binsTriangleTouches_t> ntb(nT + 1, 0);
+    launch(nT, 128, [&] {
+        ref_bintri::getNumberOfBinsEachTriangleTouches(&b.sp, &b.kt, ntb.data(), sA1.data(), sA2.data(), sA3.data(), sB1.data(),
+                                                       sB2.data(), sB3.data());
+    });
+    std::vector<deme::binsTriangleTouchPairs_t> tscan(nT + 1, 0);
+    for (uint32_t t = 0; t < nT; t++) {
+        tscan[t + 1] = tscan[t] + ntb[t];
+        if (triBins) triBins[t] = ntb[t];
+    }
+    std::vector<deme::binID_t> tbin(tscan[nT] + 1);
+    std::vector<deme::bodyID_t> ttri(tscan[nT] + 1);
+    launch(nT, 128, [&] {
+        ref_bintri::populateBinTriangleTouchingPairs(&b.sp, &b.kt, tscan.data(), tbin.data(), ttri.data(), sA1.data(), sA2.data(),
+                                                     sA3.data(), sB1.data(), sB2.data(), sB3.data());
+    });
+    /* spheres -> bins */
+    std::vector<deme::binsSphereTouches_t> nsb(nS + 1, 0);
+    std::vector<deme::objID_t> na(nS + 1, 0);
+    launch(nS, 1024, [&] { ref_bin::getNumberOfBinsEachSphereTouches(&b.sp, &b.kt, nsb.data(), na.data()); });
+    std::vector<deme::binSphereTouchPairs_t> sscan(nS + 1, 0), ascan(nS + 1, 0);
+    for (uint32_t i = 0; i < nS; i++) {
+        sscan[i + 1] = sscan[i] + nsb[i];
+        ascan[i + 1] = ascan[i] + na[i];
+    }
+    std::vector<deme::binID_t> sbin(sscan[nS] + 1);
+    std::vector<deme::bodyID_t> ssph(sscan[nS] + 1);
+    std::vector<deme::bodyID_t> idA(ascan[nS] + 1), idB(ascan[nS] + 1);
+    std::vector<deme::contact_t> ct(ascan[nS] + 1);
+    launch(nS, 1024, [&] {
+        ref_bin::populateBinSphereTouchingPairs(&b.sp, &b.kt, sscan.data(), ascan.data(), sbin.data(), ssph.data(), idA.data(),
+                                                idB.data(), ct.data());
+    });
+    /* group by bin (what the reference does with a radix sort + run-length encode, :340-420) */
+    std::vector<std::pair<deme::binID_t, deme::bodyID_t>> tb, sb;
+    for (size_t i = 0; i < (size_t)tscan[nT]; i++)
+        if (tbin[i] != deme::NULL_BINID) tb.emplace_back(tbin[i], ttri[i]);
+    for (size_t i = 0; i < (size_t)sscan[nS]; i++)
+        if (sbin[i] != deme::NULL_BINID) sb.emplace_back(sbin[i], ssph[i]);
+    std::sort(tb.begin(), tb.end());
+    std::sort(sb.begin(), sb.end());
+    long cnt = 0;
+    size_t it = 0, is = 0;
+    while (it < tb.size() && is < sb.size()) {
+        if (tb[it].first < sb[is].first) { it++; continue; }
+        if (sb[is].first < tb[it].first) { is++; continue; }
+        const deme::binID_t binID = tb[it].first;
+        size_t te = it, se = is;
+        while (te < tb.size() && tb[te].first == binID) te++;
+        while (se < sb.size() && sb[se].first == binID) se++;
+        for (size_t a = it; a < te; a++) {
+            deme::bodyID_t triOwner, triID;
+            deme::family_t triFam;
+            float3 A1, A2, A3, B1, B2, B3;
+            ref_cst::fillSharedMemTriangles(&b.sp, &b.kt, 0, tb[a].second, &triOwner, &triID, &triFam, sA1.data(), sA2.data(),
+                                            sA3.data(), sB1.data(), sB2.data(), sB3.data(), &A1, &A2, &A3, &B1, &B2, &B3);
+            for (size_t c = is; c < se; c++) {
+                deme::bodyID_t sphereID = sb[c].second, ownerID;
+                deme::family_t ownerFamily;
+                float myRadius;
+                float3 sphXYZ;
+                ref_cst::fillSharedMemSpheres<float, float>(&b.sp, &b.kt, 0, sphereID, &ownerID, &sphereID, &ownerFamily, &myRadius,
+                                                            &sphXYZ.x, &sphXYZ.y, &sphXYZ.z);
+                if (ownerID == triOwner) continue;
+                unsigned int maskMatID = locateMaskPair<unsigned int>(ownerFamily, triFam);
+                if (b.kt.familyMasks[maskMatID] != deme::DONT_PREVENT_CONTACT) continue;
+                float artificialMargin = (b.kt.familyExtraMarginSize[ownerFamily] < b.kt.familyExtraMarginSize[triFam])
+                                             ? b.kt.familyExtraMarginSize[ownerFamily]
+                                             : b.kt.familyExtraMarginSize[triFam];
+                float3 cntPnt, normal;
+                float depth;
+                bool inA = triangle_sphere_CD_directional<float3, float>(A1, A2, A3, sphXYZ, myRadius, normal, depth, cntPnt);
+                inA = inA && (-depth > artificialMargin);
+                bool inB = triangle_sphere_CD_directional<float3, float>(B1, B2, B3, sphXYZ, myRadius, normal, depth, cntPnt);
+                inB = inB && (-depth > artificialMargin);
+                if (inA || inB) {
+                    snap_to_face(A1, A2, A3, sphXYZ, cntPnt);
+                    deme::binID_t contactPntBin = getPointBinID<deme::binID_t>(cntPnt.x, cntPnt.y, cntPnt.z, b.sp.binSize,
+                                                                               b.sp.nbX, b.sp.nbY);
+                    if (contactPntBin == binID) {
+                        if (cnt >= cap) return -1;
+                        outSphere[cnt] = sphereID;
+                        outTri[cnt] = triID;
+                        cnt++;
+                    }
+                }
+            }
+        }
+        it = te;
+        is = se;
+    }
+    return cnt;
+}
+
+/* One sphere against one facet with the reference's narrow-phase functions on the double-precision nodes the force kernel
+ * builds (src/kernel/DEMCalcForceKernels.cu:150-181): out[0] = distance from the sphere centre to the facet (snap_to_face),
+ * out[1] = the sphere's radius, out[2] = penetration reported by triangle_sphere_CD<double3,double> (0 when not in
+ * contact).  Returns 1 when triangle_sphere_CD reports contact. */
+int ref_tri_sphere_gap(OrcWorld* w, uint32_t sphereID, uint32_t triID, double out[3]) {
+    Bound b; bind(w, b);
+    const uint32_t oS = w->ownerClumpBody[sphereID], oT = w->ownerMesh[triID];
+    double3 ownS, ownT;
+    voxelIDToPosition<double, deme::voxelID_t, deme::subVoxelPos_t>(ownS.x, ownS.y, ownS.z, w->voxelID[oS], w->locX[oS],
+                                                                    w->locY[oS], w->locZ[oS], g_nvXp2, g_nvYp2, g_voxelSize, g_l);
+    voxelIDToPosition<double, deme::voxelID_t, deme::subVoxelPos_t>(ownT.x, ownT.y, ownT.z, w->voxelID[oT], w->locX[oT],
+                                                                    w->locY[oT], w->locZ[oT], g_nvXp2, g_nvYp2, g_voxelSize, g_l);
+    const uint32_t comp = w->clumpComponentOffset[sphereID];
+    float3 rel = make_float3(CDRelPosX[comp], CDRelPosY[comp], CDRelPosZ[comp]);
+    applyOriQToVector3<float, deme::oriQ_t>(rel.x, rel.y, rel.z, w->oriQw[oS], w->oriQx[oS], w->oriQy[oS], w->oriQz[oS]);
+    const double3 P = make_double3(ownS.x + (double)rel.x, ownS.y + (double)rel.y, ownS.z + (double)rel.z);
+    double3 nd[3];
+    const float* src[3] = {w->relPosNode1 + 3 * (size_t)triID, w->relPosNode2 + 3 * (size_t)triID, w->relPosNode3 + 3 * (size_t)triID};
+    for (int k = 0; k < 3; k++) {
+        nd[k] = make_double3((double)src[k][0], (double)src[k][1], (double)src[k][2]);
+        applyOriQToVector3<double, deme::oriQ_t>(nd[k].x, nd[k].y, nd[k].z, w->oriQw[oT], w->oriQx[oT], w->oriQy[oT], w->oriQz[oT]);
+        nd[k] = make_double3(nd[k].x + ownT.x, nd[k].y + ownT.y, nd[k].z + ownT.z);
+    }
+    double3 q;
+    snap_to_face<double3, double>(nd[0], nd[1], nd[2], P, q);
+    const double dx = P.x - q.x, dy = P.y - q.y, dz = P.z - q.z;
+    out[0] = sqrt(dx * dx + dy * dy + dz * dz);
+    out[1] = (double)Radii[comp];
+    double3 cn, cp;
+    double depth = 0.0;
+    const bool hit = triangle_sphere_CD<double3, double>(nd[0], nd[1], nd[2], P, (double)Radii[comp], cn, depth, cp);
+    out[2] = hit ? depth : 0.0;
+    return hit ? 1 : 0;
 }
 
 /* calcContactPoint (src/kernel/DEMContactKernels_SphereSphere.cu:57-89) on explicit inputs */

@@ -193,3 +193,93 @@ def test_figure_out_nv_matches_product(built):
         b = demb200.host_figure_out_nv(tmin, tmax)
         assert a[:3] == b[:3] and a[3] == b[3] and a[4] == b[4], (box, a, b)
         assert sum(a[:3]) == 64
+
+
+@needs_ref
+@pytest.mark.parametrize("scene", ["mesh_tray", "drum"])
+@pytest.mark.parametrize("bin_mult", [1.05, 2.0, 5.0])
+def test_facet_candidates_against_reference_triangle_broad_phase(built, bin_mult, scene):
+    """Sphere--triangle broad phase pinned to reference code.  The reference sandwiches every facet between two offset,
+    enlarged copies (makeTriangleSandwich), registers facets and spheres in bins (getNumberOfBinsEachTriangleTouches /
+    populateBinTriangleTouchingPairs with DEMTriangleBoxIntersect.cu; getNumberOfBinsEachSphereTouches) and tests the pairs
+    of every shared bin one-sidedly against both copies (triangle_sphere_CD_directional,
+    DEMContactKernels_SphereTriangle.cu:196-262), attributing a pair to the bin of its contact point.  All of that runs
+    here through the host shim on the oracle's state (ref_sphere_tri_contacts), for three bin sizes, next to the oracle's
+    geometric rule "distance to the facet < radius + sphere margin + mesh margin - smaller family extra margin":
+      * the oracle's list is exactly the pairs within that reach, measured with the reference's own snap_to_face;
+      * what the reference lists beyond it (its one-sided test admits every sphere behind a sandwich copy) is out of
+        reach, hence never in touch before the next rebuild;
+      * every pair in touch deeper than the mesh owner's margin is in both lists; shallower (grazing) contacts can be
+        missing from the reference's list -- the sandwich moves the rim of a facet by up to its margin and the contact
+        point may then fall into a bin the two do not share -- and are present in the oracle's."""
+    import ctypes as C
+    if scene == "drum":  # BASELINE config 4 at oracle scale: polydisperse clumps in a rotating drum of 1500 facets
+        f = scenes.flatten(scenes.config4_drum(600, 1500, omega=6.0, init_vel=(0.2, 0.0, -1.0), cd_update_freq=10, spacing=2.7))
+        checkpoints = (1200, 600)
+    else:
+        f = scenes.flatten(_scene("mesh_tray"))
+        checkpoints = (1500, 1500, 1000)
+    w = pyoracle.world_from_flat(f)
+    gapfn = pyoracle.ref().ref_tri_sphere_gap
+
+    def narrow(s, pair):
+        out = (C.c_double * 3)()
+        hit = gapfn(C.byref(s), C.c_uint32(pair[0]), C.c_uint32(pair[1]), out)
+        return bool(hit), out[0] - out[1], -out[2]  # in touch, gap (distance - radius), penetration
+
+    n_ref = n_grazing = 0
+    for nsteps in checkpoints:
+        w.step(nsteps, cd_every=5)
+        w.compute_margins(5)
+        w.detect_contacts()
+        w.prepare_acc()
+        w.calc_forces()
+        idA, idB, ct, _ = w.contacts()
+        n = w.nContacts
+        st = ct == 2  # ORC_SPHERE_MESH
+        mine = set(zip(idA[st].tolist(), idB[st].tolist()))
+        on = st & (np.abs(w.contactForces[: 3 * n].reshape(-1, 3)).max(1) > 0)
+        touching = set(zip(idA[on].tolist(), idB[on].tolist()))
+        rmax = float(np.max(w.Radii)) + float(np.max(w.marginSize))
+        bin_size = bin_mult * 2.0 * rmax
+        ext = [float(2 ** p) * float(w.voxelSize) for p in (w.nvXp2, w.nvYp2, w.nvZp2)]
+        nb = [int(np.ceil(e / bin_size)) for e in ext]
+        cap = 64 * w.nSpheres + 1024
+        oS, oT = np.zeros(cap, "u4"), np.zeros(cap, "u4")
+        tri_bins = np.zeros(max(w.nTri, 1), "u4")
+        s = w.struct()
+        fn = pyoracle.ref().ref_sphere_tri_contacts
+        fn.restype = C.c_long
+        got = fn(C.byref(s), C.c_double(bin_size), C.c_uint32(nb[0]), C.c_uint32(nb[1]), C.c_uint32(nb[2]),
+                 oS.ctypes.data_as(C.c_void_p), oT.ctypes.data_as(C.c_void_p), C.c_long(cap),
+                 tri_bins.ctypes.data_as(C.c_void_p))
+        assert got >= 0
+        theirs = set(zip(oS[:got].tolist(), oT[:got].tolist()))
+        assert got == len(theirs), "the reference attributes a pair to exactly one bin"
+        assert (tri_bins[: w.nTri] > 0).all(), "every facet lies in at least one bin"
+
+        def reach(pair):  # what the margins of this rebuild promise to cover
+            oSph, oTri = w.ownerClumpBody[pair[0]], w.ownerMesh[pair[1]]
+            extra = min(float(w.familyExtraMarginSize[w.familyID[oSph]]), float(w.familyExtraMarginSize[w.familyID[oTri]]))
+            return float(w.marginSize[oSph]) + float(w.marginSize[oTri]) - extra, float(w.marginSize[oTri])
+
+        for pair in mine:
+            hit, gap, pen = narrow(s, pair)
+            assert gap < reach(pair)[0] + 1e-9, (pair, gap)
+            assert hit == (pair in touching)
+        for pair in theirs - mine:
+            hit, gap, pen = narrow(s, pair)
+            assert not hit and gap >= reach(pair)[0] - 1e-9, (pair, gap, reach(pair))
+        for pair in mine - theirs:
+            hit, gap, pen = narrow(s, pair)
+            if hit:
+                assert pen < reach(pair)[1], (pair, pen, reach(pair))
+                n_grazing += 1
+        deep = {p for p in touching if narrow(s, p)[2] >= reach(p)[1]}
+        assert deep <= theirs and touching <= mine
+        print("bin %.4f: reference %d pairs, oracle %d (%d in common), in touch %d (%d deeper than the mesh margin); "
+              "facets register in %.1f bins on average" % (bin_size, len(theirs), len(mine), len(mine & theirs),
+                                                            len(touching), len(deep), tri_bins[: w.nTri].mean()))
+        n_ref += len(theirs)
+    assert n_ref > 10
+    print("grazing contacts the reference's broad phase misses at this bin size:", n_grazing)
