@@ -371,6 +371,21 @@ class DEMSolver {
     std::shared_ptr<DEMForceModel> ReadContactForceModel(const std::string&);
 
     std::shared_ptr<DEMMaterial> LoadMaterial(const std::unordered_map<std::string, float>& mat_prop);
+    std::shared_ptr<DEMMaterial> LoadMaterial(DEMMaterial& a_material) { return LoadMaterial(a_material.mat_prop); }
+    // deep copies of an already loaded material / clump template / batch, loaded as new objects
+    // (reference src/DEM/APIPublic.cpp:397-411)
+    std::shared_ptr<DEMMaterial> Duplicate(const std::shared_ptr<DEMMaterial>& ptr) {
+        DEMMaterial obj = *ptr;
+        return LoadMaterial(obj);
+    }
+    std::shared_ptr<DEMClumpTemplate> Duplicate(const std::shared_ptr<DEMClumpTemplate>& ptr) {
+        DEMClumpTemplate obj = *ptr;
+        return LoadClumpType(obj);
+    }
+    std::shared_ptr<DEMClumpBatch> Duplicate(const std::shared_ptr<DEMClumpBatch>& ptr) {
+        DEMClumpBatch obj = *ptr;
+        return AddClumps(obj);
+    }
     void SetMaterialPropertyPair(const std::string& name, const std::shared_ptr<DEMMaterial>& mat1,
                                  const std::shared_ptr<DEMMaterial>& mat2, float val);
     std::shared_ptr<DEMClumpTemplate> LoadClumpType(float mass, float3 moi, const std::vector<float>& sp_radii,

@@ -1,8 +1,12 @@
 // DEM/HostSideHelpers.hpp -- the float3/float4 helpers reference demo scripts rely on
 // (counterpart of src/kernel/CUDAMathHelpers.cuh + src/DEM/HostSideHelpers.hpp of the reference, host side only).
 #pragma once
+#include <algorithm>
+#include <cassert>
 #include <cmath>
+#include <cstdint>
 #include <cstdio>
+#include <numeric>
 #include <stdexcept>
 #include <string>
 #include <vector>
