@@ -1852,6 +1852,54 @@ int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float*
     return group_broadcast_state(ctx);  // (no-op on a single GPU)
 }
 
+int dem_add_owner_acc(DemCtx* ctx, uint32_t first, uint32_t n, const float* acc, const float* angacc_local) {
+    // AddOwnerNextStepAcc / AddOwnerNextStepAngAcc (src/DEM/dT.cpp:3160-3174, DEMPrepForceKernels.cu:14-37): the reference
+    // pre-loads a / alpha and skips zeroing them for one step, so the contacts of the next step add to them.  Here the
+    // integrator consumes a world-frame wrench {sum F, sum T} per owner, (a, alpha) = (F / m, R^T T / I), and leaves it
+    // zero: the same extra acceleration is m * a added to F and R (I * alpha) added to T, once, between two steps.
+    if (!ctx || !ctx->initialized) return DEM_ERR_INVALID;
+    if ((uint64_t)first + n > ctx->nOwners) return fail(ctx, DEM_ERR_INVALID, "owner range out of bounds");
+    if (n == 0 || (!acc && !angacc_local)) return DEM_OK;
+    CK(cudaSetDevice(ctx->device));
+    { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
+    { int rcs = settle(ctx); if (rcs) return rcs; }
+    std::vector<OwnerState> st(n);
+    std::vector<float4> sp(n);
+    CK(cudaMemcpy(st.data(), ctx->d_state + first, sizeof(OwnerState) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(sp.data(), ctx->d_spin + first, sizeof(float4) * n, cudaMemcpyDeviceToHost));
+    std::vector<Wrench> add(n);
+    for (uint32_t i = 0; i < n; i++) {
+        uint32_t mpi;
+        std::memcpy(&mpi, &sp[i].w, sizeof(mpi));  // (the body-frame spin record carries the mass-property index in w)
+        if (mpi >= ctx->h_massprop.size()) return fail(ctx, DEM_ERR_INVALID, "dem_add_owner_acc: owner %u has no mass properties", first + i);
+        const float4 mp = ctx->h_massprop[mpi];  // mass, Ixx, Iyy, Izz
+        add[i].f = make_float4(0.f, 0.f, 0.f, 0.f);
+        add[i].t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (acc) add[i].f = make_float4(mp.x * acc[3 * i], mp.x * acc[3 * i + 1], mp.x * acc[3 * i + 2], 0.f);
+        if (angacc_local) {
+            const float3 tw = host_rotate(make_float3(mp.y * angacc_local[3 * i], mp.z * angacc_local[3 * i + 1],
+                                                      mp.w * angacc_local[3 * i + 2]), st[i].quat);
+            add[i].t = make_float4(tw.x, tw.y, tw.z, 0.f);
+        }
+    }
+    // every rank of a group gets the increment: the rank that owns the body integrates it, the others consume it unused
+    std::vector<Wrench> w(n);
+    for (DemCtx* c : group_ranks(ctx)) {
+        if (cudaSetDevice(c->device) != cudaSuccess) return fail(ctx, DEM_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+        if (c != ctx) { int rcs = settle(c); if (rcs) return peer_fail(ctx, c, rcs); }
+        if (cudaMemcpy(w.data(), c->d_wrench + first, sizeof(Wrench) * n, cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(ctx, DEM_ERR_CUDA, "dem_add_owner_acc: download failed");
+        for (uint32_t i = 0; i < n; i++) {
+            w[i].f.x += add[i].f.x; w[i].f.y += add[i].f.y; w[i].f.z += add[i].f.z;
+            w[i].t.x += add[i].t.x; w[i].t.y += add[i].t.y; w[i].t.z += add[i].t.z;
+        }
+        if (cudaMemcpy(c->d_wrench + first, w.data(), sizeof(Wrench) * n, cudaMemcpyHostToDevice) != cudaSuccess)
+            return fail(ctx, DEM_ERR_CUDA, "dem_add_owner_acc: upload failed");
+    }
+    CK(cudaSetDevice(ctx->device));
+    return DEM_OK;
+}
+
 int dem_set_family_material(DemCtx* ctx, uint32_t family, uint32_t material, int meshes) {
     // SetFamilyClumpMaterial / SetFamilyMeshMaterial (src/DEM/APIPublic.cpp:1597-1604, dT.cpp:2719-2738): every sphere
     // (meshes != 0: every facet) whose owner is in `family` gets the material.  The compiled contact records carry the

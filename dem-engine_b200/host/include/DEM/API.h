@@ -19,6 +19,7 @@
 #include <set>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -36,7 +37,14 @@ namespace deme {
 
 typedef unsigned int bodyID_t;
 typedef uint8_t family_t;
+typedef uint8_t notStupidBool_t;  // the reference's array-friendly bool (src/DEM/VariableTypes.h:58)
 constexpr double PI = 3.1415926535897932385;
+#ifndef DEME_TINY_FLOAT
+    #define DEME_TINY_FLOAT 1e-12
+#endif
+#ifndef DEME_HUGE_FLOAT
+    #define DEME_HUGE_FLOAT 1e15
+#endif
 
 enum VERBOSITY { QUIET = 0, ERR = 10, WARNING = 20, INFO = 30, STEP_ANOMALY = 32, STEP_METRIC = 35, DEBUG = 40, STEP_DEBUG = 50 };
 enum class TIME_INTEGRATOR { FORWARD_EULER, CENTERED_DIFFERENCE, EXTENDED_TAYLOR, CHUNG };
@@ -113,23 +121,62 @@ class DEMClumpBatch : public DEMInitializer {
     size_t GetNumSpheres() const { return nSpheres; }
     void SetTypes(const std::vector<std::shared_ptr<DEMClumpTemplate>>& input);
     void SetTypes(const std::shared_ptr<DEMClumpTemplate>& input) { SetTypes(std::vector<std::shared_ptr<DEMClumpTemplate>>(nClumps, input)); }
+    void SetType(const std::shared_ptr<DEMClumpTemplate>& input) { SetTypes(input); }
     void SetPos(const std::vector<float3>& input);
+    void SetPos(float3 input) { SetPos(std::vector<float3>(nClumps, input)); }
     void SetVel(const std::vector<float3>& input);
     void SetVel(float3 input) { SetVel(std::vector<float3>(nClumps, input)); }
     void SetAngVel(const std::vector<float3>& input);
     void SetAngVel(float3 input) { SetAngVel(std::vector<float3>(nClumps, input)); }
     void SetOriQ(const std::vector<float4>& input);
     void SetOriQ(float4 input) { SetOriQ(std::vector<float4>(nClumps, input)); }
+    // {x, y, z} (one value for all clumps) and {{x, y, z}, ...} forms (Structs.h:763-830 of the reference)
+    void SetPos(const std::vector<float>& input) { SetPos(vec3_of(input, "SetPos")); }
+    void SetPos(const std::vector<std::vector<float>>& input) { SetPos(vec3s_of(input, "SetPos")); }
+    void SetVel(const std::vector<float>& input) { SetVel(vec3_of(input, "SetVel")); }
+    void SetVel(const std::vector<std::vector<float>>& input) { SetVel(vec3s_of(input, "SetVel")); }
+    void SetAngVel(const std::vector<float>& input) { SetAngVel(vec3_of(input, "SetAngVel")); }
+    void SetAngVel(const std::vector<std::vector<float>>& input) { SetAngVel(vec3s_of(input, "SetAngVel")); }
+    void SetOriQ(const std::vector<float>& input) { SetOriQ(vec4_of(input, "SetOriQ")); }
+    void SetOriQ(const std::vector<std::vector<float>>& input) {
+        std::vector<float4> q;
+        for (const auto& v : input) q.push_back(vec4_of(v, "SetOriQ"));
+        SetOriQ(q);
+    }
     void SetFamilies(const std::vector<unsigned int>& input);
     void SetFamilies(unsigned int input) { SetFamilies(std::vector<unsigned int>(nClumps, input)); }
     void SetFamily(unsigned int input) { SetFamilies(input); }
     /// Restart support: contacts (pairs of sphere numbers relative to this batch) and their history
     void SetExistingContacts(const std::vector<std::pair<bodyID_t, bodyID_t>>& pairs) { contact_pairs = pairs; }
     void SetExistingContactWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards) { contact_wildcards = wildcards; }
+    void AddExistingContactWildcard(const std::string& name, const std::vector<float>& vals);
+    /// Owner / geometry wildcards exist only for custom force models (which need run-time compilation and are not part
+    /// of this core): the values are kept, and Initialize() refuses a batch that carries any, as the reference refuses a
+    /// wildcard its force model does not declare (Structs.h:868-917, APIPrivate.cpp:1158-1190).
+    void SetOwnerWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards);
+    void AddOwnerWildcard(const std::string& name, const std::vector<float>& vals);
+    void AddOwnerWildcard(const std::string& name, float val) { AddOwnerWildcard(name, std::vector<float>(nClumps, val)); }
+    void SetGeometryWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards);
+    void AddGeometryWildcard(const std::string& name, const std::vector<float>& vals);
+    void AddGeometryWildcard(const std::string& name, float val) { AddGeometryWildcard(name, std::vector<float>(nSpheres, val)); }
+    std::unordered_map<std::string, std::vector<float>> owner_wildcards, geo_wildcards;
     size_t GetNumContacts() const { return contact_pairs.size(); }
 
   private:
     void assertLength(size_t len, const std::string& name) const;
+    static float3 vec3_of(const std::vector<float>& v, const char* who) {
+        if (v.size() != 3) throw std::runtime_error(std::string(who) + ": a 3-element vector is expected");
+        return make_float3(v[0], v[1], v[2]);
+    }
+    static float4 vec4_of(const std::vector<float>& v, const char* who) {
+        if (v.size() != 4) throw std::runtime_error(std::string(who) + ": a 4-element vector (x, y, z, w) is expected");
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+    static std::vector<float3> vec3s_of(const std::vector<std::vector<float>>& in, const char* who) {
+        std::vector<float3> out;
+        for (const auto& v : in) out.push_back(vec3_of(v, who));
+        return out;
+    }
 };
 
 class DEMExternObj : public DEMInitializer {
@@ -160,6 +207,32 @@ class DEMExternObj : public DEMInitializer {
                       const objNormal_t normal = ENTITY_NORMAL_INWARD);
     void AddCylinder(const float3 pos, const float3 axis, const float rad, const std::shared_ptr<DEMMaterial>& material,
                      const objNormal_t normal = ENTITY_NORMAL_INWARD);
+    // std::vector<float> forms of the above (BdrsAndObjs.h:118-228 of the reference).  The reference's finite plate
+    // (AddPlate, :162-177) is commented out there and its device case never reports a contact
+    // (DEMHelperKernels.cuh:491-493), so there is no plate to mirror.
+    void SetMOI(const std::vector<float>& moi) { SetMOI(three(moi, "SetMOI")); }
+    void SetInitPos(const std::vector<float>& displ) { SetInitPos(three(displ, "SetInitPos")); }
+    void SetInitQuat(const std::vector<float>& rotQ) {
+        if (rotQ.size() != 4) throw std::runtime_error("SetInitQuat: a 4-element vector (x, y, z, w) is expected");
+        SetInitQuat(make_float4(rotQ[0], rotQ[1], rotQ[2], rotQ[3]));
+    }
+    void AddPlane(const std::vector<float>& pos, const std::vector<float>& normal, const std::shared_ptr<DEMMaterial>& material) {
+        AddPlane(three(pos, "AddPlane"), three(normal, "AddPlane"), material);
+    }
+    void AddZCylinder(const std::vector<float>& pos, const float rad, const std::shared_ptr<DEMMaterial>& material,
+                      const objNormal_t normal = ENTITY_NORMAL_INWARD) {
+        AddZCylinder(three(pos, "AddZCylinder"), rad, material, normal);
+    }
+    void AddCylinder(const std::vector<float>& pos, const std::vector<float>& axis, const float rad,
+                     const std::shared_ptr<DEMMaterial>& material, const objNormal_t normal = ENTITY_NORMAL_INWARD) {
+        AddCylinder(three(pos, "AddCylinder"), three(axis, "AddCylinder"), rad, material, normal);
+    }
+
+  private:
+    static float3 three(const std::vector<float>& v, const char* who) {
+        if (v.size() != 3) throw std::runtime_error(std::string(who) + ": a 3-element vector is expected");
+        return make_float3(v[0], v[1], v[2]);
+    }
 };
 
 /// Triangle mesh owner (src/DEM/BdrsAndObjs.h:222-520). Vertices live in the mesh frame; facets are counter-clockwise
@@ -218,23 +291,110 @@ class DEMMeshConnected : public DEMInitializer {
 
 class DEMSolver;
 
-/// Tracker of one loaded object (a clump batch or an external object): src/DEM/AuxClasses.h:93-420
+/// Per-contact read-out of GetContactDetailedInfo (src/DEM/Structs.h:1049-1107): one entry per reported contact in
+/// every field that SetContactOutputContent switched on; asking for a field that is off throws.
+class ContactInfoContainer {
+  public:
+    ContactInfoContainer(unsigned int cnt_out_content, const std::vector<std::string>& wildcard_names);
+    size_t Size() const { return m_type.size(); }
+    std::vector<std::string>& GetContactType() { return m_type; }
+    std::vector<float3>& GetPoint() { return need(m_point, CNT_POINT, "Point"); }
+    std::vector<bodyID_t>& GetAOwner() { return need(m_owner[0], OWNER, "AOwner"); }
+    std::vector<bodyID_t>& GetBOwner() { return need(m_owner[1], OWNER, "BOwner"); }
+    std::vector<bodyID_t>& GetAGeo() { return need(m_geo[0], GEO_ID, "AGeo"); }
+    std::vector<bodyID_t>& GetBGeo() { return need(m_geo[1], GEO_ID, "BGeo"); }
+    std::vector<family_t>& GetAOwnerFamily() { return m_family[0]; }
+    std::vector<family_t>& GetBOwnerFamily() { return m_family[1]; }
+    std::vector<float3>& GetForce() { return need(m_force, FORCE, "Force"); }
+    std::vector<float3>& GetTorque() { return need(m_torque, TORQUE, "Torque"); }
+    std::vector<float3>& GetNormal() { return need(m_normal, NORMAL, "Normal"); }
+    /// a contact wildcard by name (delta_tan_x, delta_tan_y, delta_tan_z, delta_time for the frictional model)
+    std::vector<float>& GetWildcard(const std::string& name);
+    const std::vector<std::string>& GetWildcardNames() const { return m_wc_names; }
+    bool Contains(unsigned int content_bit) const { return (m_content & content_bit) != 0; }
+    void ResizeAll(size_t n);
+
+  private:
+    template <typename V>
+    V& need(V& field, unsigned int bit, const char* key) {
+        if (!(m_content & bit))
+            throw std::runtime_error(std::string("ContactInfoContainer does not have field: '") + key +
+                                     "', you may need to turn on the output of this field by correctly calling "
+                                     "SetContactOutputContent before Initialize().");
+        return field;
+    }
+    unsigned int m_content;
+    std::vector<std::string> m_type, m_wc_names;
+    std::vector<float3> m_point, m_force, m_torque, m_normal;
+    std::vector<bodyID_t> m_owner[2], m_geo[2];
+    std::vector<family_t> m_family[2];
+    std::vector<std::vector<float>> m_wc;
+};
+
+/// Tracker of one loaded object (a clump batch, an external object or a mesh): src/DEM/AuxClasses.h:93-420.  Offsets
+/// count owners from the first one of the tracked object; the plural getters read the whole object in one transfer.
 class DEMTracker {
   public:
     DEMTracker(DEMSolver* sim, std::shared_ptr<DEMInitializer> obj) : sys(sim), obj(std::move(obj)) {}
     bodyID_t GetOwnerID(size_t offset = 0);
+    std::vector<bodyID_t> GetOwnerIDs();
     float3 Pos(size_t offset = 0);
-    float3 Vel(size_t offset = 0);
-    float3 AngVelLocal(size_t offset = 0);
-    float3 AngVelGlobal(size_t offset = 0);
-    float4 OriQ(size_t offset = 0);
-    float3 ContactAcc(size_t offset = 0);
-    float3 ContactAngAccLocal(size_t offset = 0);
-    float Mass(size_t offset = 0);
-    float3 MOI(size_t offset = 0);
-    unsigned int GetFamily(size_t offset = 0);
+    std::vector<float> GetPos(size_t offset = 0) { return Real3ToVec(Pos(offset)); }
     std::vector<float3> Positions();
+    std::vector<std::vector<float>> GetPositions() { return Real3VectorToVecOfVec(Positions()); }
+    float3 Vel(size_t offset = 0);
+    std::vector<float> GetVel(size_t offset = 0) { return Real3ToVec(Vel(offset)); }
     std::vector<float3> Velocities();
+    std::vector<std::vector<float>> GetVelocities() { return Real3VectorToVecOfVec(Velocities()); }
+    float3 AngVelLocal(size_t offset = 0);
+    std::vector<float> GetAngVelLocal(size_t offset = 0) { return Real3ToVec(AngVelLocal(offset)); }
+    std::vector<float3> AngularVelocitiesLocal();
+    std::vector<std::vector<float>> GetAngularVelocitiesLocal() { return Real3VectorToVecOfVec(AngularVelocitiesLocal()); }
+    float3 AngVelGlobal(size_t offset = 0);
+    std::vector<float> GetAngVelGlobal(size_t offset = 0) { return Real3ToVec(AngVelGlobal(offset)); }
+    std::vector<float3> AngularVelocitiesGlobal();
+    std::vector<std::vector<float>> GetAngularVelocitiesGlobal() { return Real3VectorToVecOfVec(AngularVelocitiesGlobal()); }
+    float4 OriQ(size_t offset = 0);
+    std::vector<float> GetOriQ(size_t offset = 0) { return Real4ToVec(OriQ(offset)); }
+    std::vector<float4> OrientationQuaternions();
+    std::vector<std::vector<float>> GetOrientationQuaternions() { return Real4VectorToVecOfVec(OrientationQuaternions()); }
+    unsigned int GetFamily(size_t offset = 0);
+    std::vector<unsigned int> GetFamilies();
+    /// clumps in (potential) contact with the tracked owner at `offset`
+    std::vector<bodyID_t> GetContactClumps(size_t offset = 0);
+    /// acceleration / angular acceleration that the contacts of the last step gave the owner
+    float3 ContactAcc(size_t offset = 0);
+    std::vector<float> GetContactAcc(size_t offset = 0) { return Real3ToVec(ContactAcc(offset)); }
+    std::vector<float3> ContactAccelerations();
+    std::vector<std::vector<float>> GetContactAccelerations() { return Real3VectorToVecOfVec(ContactAccelerations()); }
+    float3 ContactAngAccLocal(size_t offset = 0);
+    std::vector<float> GetContactAngAccLocal(size_t offset = 0) { return Real3ToVec(ContactAngAccLocal(offset)); }
+    std::vector<float3> ContactAngularAccelerationsLocal();
+    std::vector<std::vector<float>> GetContactAngularAccelerationsLocal() {
+        return Real3VectorToVecOfVec(ContactAngularAccelerationsLocal());
+    }
+    float3 ContactAngAccGlobal(size_t offset = 0);
+    std::vector<float> GetContactAngAccGlobal(size_t offset = 0) { return Real3ToVec(ContactAngAccGlobal(offset)); }
+    std::vector<float3> ContactAngularAccelerationsGlobal();
+    std::vector<std::vector<float>> GetContactAngularAccelerationsGlobal() {
+        return Real3VectorToVecOfVec(ContactAngularAccelerationsGlobal());
+    }
+    float Mass(size_t offset = 0);
+    std::vector<float> Masses();
+    float3 MOI(size_t offset = 0);
+    std::vector<float> GetMOI(size_t offset = 0) { return Real3ToVec(MOI(offset)); }
+    std::vector<float3> MOIs();
+    std::vector<std::vector<float>> GetMOIs() { return Real3VectorToVecOfVec(MOIs()); }
+    /// Owner / geometry wildcards belong to custom force models; the built-in models declare none, so -- like the
+    /// reference for a name its force model does not know -- these throw.
+    float GetOwnerWildcardValue(const std::string& name, size_t offset = 0);
+    std::vector<float> GetOwnerWildcardValues(const std::string& name);
+    float GetGeometryWildcardValue(const std::string& name, size_t offset);
+    std::vector<float> GetGeometryWildcardValues(const std::string& name);
+    void SetOwnerWildcardValue(const std::string& name, float wc, size_t offset = 0);
+    void SetOwnerWildcardValues(const std::string& name, const std::vector<float>& wc);
+    void SetGeometryWildcardValue(const std::string& name, float wc, size_t offset = 0);
+    void SetGeometryWildcardValues(const std::string& name, const std::vector<float>& wc);
     /// Deforming mesh (AuxClasses.h:288-313 of the reference): replace / displace the tracked mesh's nodes (mesh frame;
     /// one entry per node), read the nodes back in the global frame, get the mesh handle
     void UpdateMesh(const std::vector<float3>& new_nodes);
@@ -244,35 +404,78 @@ class DEMTracker {
     /// Contact points and forces (global frame) acting on the tracked owner at `offset` / on all tracked owners
     size_t GetContactForces(std::vector<float3>& points, std::vector<float3>& forces, size_t offset = 0);
     size_t GetContactForcesForAll(std::vector<float3>& points, std::vector<float3>& forces);
+    /// ... plus the torque of each contact that is not already the moment of its force: the rolling-resistance couple,
+    /// about the owner's centre, in the global or in the owner's frame (AuxClasses.h:372-418)
+    size_t GetContactForcesAndGlobalTorque(std::vector<float3>& points, std::vector<float3>& forces,
+                                           std::vector<float3>& torques, size_t offset = 0);
+    size_t GetContactForcesAndGlobalTorqueForAll(std::vector<float3>& points, std::vector<float3>& forces,
+                                                 std::vector<float3>& torques);
+    size_t GetContactForcesAndLocalTorque(std::vector<float3>& points, std::vector<float3>& forces,
+                                          std::vector<float3>& torques, size_t offset = 0);
+    size_t GetContactForcesAndLocalTorqueForAll(std::vector<float3>& points, std::vector<float3>& forces,
+                                                std::vector<float3>& torques);
     void SetPos(float3 pos, size_t offset = 0);
+    void SetPos(const std::vector<float3>& pos);
     void SetVel(float3 vel, size_t offset = 0);
+    void SetVel(const std::vector<float3>& vel);
     void SetAngVel(float3 angVel, size_t offset = 0);
+    void SetAngVel(const std::vector<float3>& angVel);
     void SetOriQ(float4 oriQ, size_t offset = 0);
-    void SetFamily(unsigned int fam_num, size_t offset = 0);
+    void SetOriQ(const std::vector<float4>& oriQ);
+    /// Extra (angular) acceleration for the NEXT time step only, added to what the contacts give (AuxClasses.h:262-274)
+    void AddAcc(float3 acc, size_t offset = 0);
+    void AddAcc(const std::vector<float3>& acc);
+    void AddAngAcc(float3 angAcc, size_t offset = 0);
+    void AddAngAcc(const std::vector<float3>& angAcc);
+    void SetFamily(unsigned int fam_num);
+    void SetFamily(unsigned int fam_num, size_t offset);
+    void ChangeClumpSizes(const std::vector<bodyID_t>& IDs, const std::vector<float>& factors);
 
   private:
     DEMSolver* sys;
     std::shared_ptr<DEMInitializer> obj;
     bodyID_t first();
     size_t count();
+    void assertOwnerSize(size_t input_length, const std::string& name);
 };
 
-/// Built-in inspectors (src/DEM/AuxClasses.cpp:88-164): clump_max_z, clump_min_z, clump_mass, clump_max_absv,
-/// max_absv, clump_kinetic_energy
+/// Built-in inspectors (src/DEM/AuxClasses.cpp:88-164): clump_max_z, clump_min_z, clump_max_absv, max_absv,
+/// clump_kinetic_energy, clump_mass, clump_volume.  Over the whole domain they are device reductions; with a region -- a
+/// condition on the position X, Y, Z of the inspected thing (the sphere for the *_z and clump_max_absv quantities, the
+/// owner otherwise), e.g. "return (abs(X) <= 0.48) && (Z <= -0.44);" -- the owners are read back and the condition is
+/// evaluated on the host (DEM/utils/Expression.hpp; the reference compiles it into its inspection kernel).
 class DEMInspector {
   public:
     DEMInspector(DEMSolver* sim, const std::string& quantity);
+    DEMInspector(DEMSolver* sim, const std::string& quantity, const std::string& region);
     float GetValue();
 
   private:
     DEMSolver* sys;
     int kind;
+    std::shared_ptr<ScalarExpression> region;
 };
 
+/// The force model handle returned by Use*Model / DefineContactForceModel (src/DEM/AuxClasses.h:424-520).  The two
+/// built-in models are compiled into the core; their material requirements and history words are fixed.
 class DEMForceModel {
   public:
     explicit DEMForceModel(FORCE_MODEL t) : type(t) {}
     FORCE_MODEL type;
+    /// material properties every material must define / that may be set pairwise: checked when materials are flattened
+    void SetMustHaveMatProp(const std::set<std::string>& props) { m_must_have_mat_props = props; }
+    void SetMustPairwiseMatProp(const std::set<std::string>& props) { m_pairwise_mat_props = props; }
+    /// History words and owner / geometry wildcards are what a custom model declares for its own code; the built-in
+    /// models keep theirs (delta_tan_x/y/z, delta_time for the frictional model, none for the frictionless one).
+    void SetPerContactWildcards(const std::set<std::string>& wildcards);
+    void SetPerOwnerWildcards(const std::set<std::string>& wildcards);
+    void SetPerGeometryWildcards(const std::set<std::string>& wildcards);
+    void SetForceModelType(FORCE_MODEL model_type);
+    void DefineCustomModel(const std::string& model);
+    int ReadCustomModelFile(const std::filesystem::path& sourcefile);
+    void DefineCustomModelPrerequisites(const std::string& util);
+    int ReadCustomModelPrerequisitesFile(const std::filesystem::path& sourcefile);
+    std::set<std::string> m_must_have_mat_props, m_pairwise_mat_props;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -369,6 +572,7 @@ class DEMSolver {
     std::shared_ptr<DEMForceModel> UseFrictionlessHertzianModel();
     std::shared_ptr<DEMForceModel> DefineContactForceModel(const std::string&);
     std::shared_ptr<DEMForceModel> ReadContactForceModel(const std::string&);
+    std::shared_ptr<DEMForceModel> GetContactForceModel() { return m_force_model_obj; }
 
     std::shared_ptr<DEMMaterial> LoadMaterial(const std::unordered_map<std::string, float>& mat_prop);
     std::shared_ptr<DEMMaterial> LoadMaterial(DEMMaterial& a_material) { return LoadMaterial(a_material.mat_prop); }
@@ -427,6 +631,7 @@ class DEMSolver {
         return tr;
     }
     std::shared_ptr<DEMInspector> CreateInspector(const std::string& quantity = "clump_max_z");
+    std::shared_ptr<DEMInspector> CreateInspector(const std::string& quantity, const std::string& region);
 
     void DisableContactBetweenFamilies(unsigned int ID1, unsigned int ID2);
     void EnableContactBetweenFamilies(unsigned int ID1, unsigned int ID2);
@@ -471,6 +676,68 @@ class DEMSolver {
     /// Value of a prescription string at time t (what the integrator will be given); exposed for scripts and tests
     static double EvaluatePrescription(const std::string& expression, double t) { return TimeExpression(expression).Eval(t); }
     void SetFamilyExtraMargin(unsigned int N, float extra_size);
+    /// "Corrections" are code strings added to the integrator (API.h:806-838 of the reference): they need run-time
+    /// compilation like custom force models, so they throw.
+    void CorrectFamilyLinVel(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z,
+                             const std::string& pre = "none");
+    void CorrectFamilyAngVel(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z,
+                             const std::string& pre = "none");
+    void CorrectFamilyPosition(unsigned int ID, const std::string& X, const std::string& Y, const std::string& Z,
+                               const std::string& pre = "none");
+    void CorrectFamilyQuaternion(unsigned int ID, const std::string& q_formula);
+
+    // ---- contact wildcards = the history words of the force model (API.h:841-870 of the reference): for the frictional
+    // model delta_tan_x, delta_tan_y, delta_tan_z, delta_time; none for the frictionless one.  The setters rewrite the
+    // named word of every listed contact whose two owners' families match.
+    void SetContactWildcardValue(const std::string& name, float val);
+    void SetFamilyContactWildcardValueEither(unsigned int N, const std::string& name, float val);
+    void SetFamilyContactWildcardValueBoth(unsigned int N, const std::string& name, float val);
+    void SetFamilyContactWildcardValue(unsigned int N1, unsigned int N2, const std::string& name, float val);
+    /// Declaring wildcards is how a custom force model names its own storage: refused for the built-in models unless the
+    /// set is exactly the one the model already has
+    void SetContactWildcards(const std::set<std::string>& wildcards);
+    void SetOwnerWildcards(const std::set<std::string>& wildcards);
+    void SetGeometryWildcards(const std::set<std::string>& wildcards);
+    // owner / geometry wildcard access: no built-in model declares any, so every name is unknown and these throw, as the
+    // reference does for an unknown name (API.h:936-1014, APIPublic.cpp:1042-1180)
+    void SetOwnerWildcardValue(bodyID_t ownerID, const std::string& name, const std::vector<float>& vals);
+    void SetOwnerWildcardValue(bodyID_t ownerID, const std::string& name, float val, size_t n = 1) {
+        SetOwnerWildcardValue(ownerID, name, std::vector<float>(n, val));
+    }
+    void SetFamilyOwnerWildcardValue(unsigned int N, const std::string& name, const std::vector<float>& vals);
+    void SetFamilyOwnerWildcardValue(unsigned int N, const std::string& name, float val) {
+        SetFamilyOwnerWildcardValue(N, name, std::vector<float>(1, val));
+    }
+    void SetTriWildcardValue(bodyID_t geoID, const std::string& name, const std::vector<float>& vals);
+    void SetSphereWildcardValue(bodyID_t geoID, const std::string& name, const std::vector<float>& vals);
+    void SetAnalWildcardValue(bodyID_t geoID, const std::string& name, const std::vector<float>& vals);
+    std::vector<float> GetOwnerWildcardValue(bodyID_t ownerID, const std::string& name, bodyID_t n = 1);
+    std::vector<float> GetAllOwnerWildcardValue(const std::string& name);
+    std::vector<float> GetFamilyOwnerWildcardValue(unsigned int N, const std::string& name);
+    std::vector<float> GetTriWildcardValue(bodyID_t geoID, const std::string& name, size_t n);
+    std::vector<float> GetSphereWildcardValue(bodyID_t geoID, const std::string& name, size_t n);
+    std::vector<float> GetAnalWildcardValue(bodyID_t geoID, const std::string& name, size_t n);
+    void EnableOwnerWildcardOutput(bool enable = true) { (void)enable; }
+    void EnableContactWildcardOutput(bool enable = true) {
+        if (enable) m_cnt_out_content |= CNT_WILDCARD; else m_cnt_out_content &= ~(unsigned int)CNT_WILDCARD;
+    }
+    void EnableGeometryWildcardOutput(bool enable = true) { (void)enable; }
+
+    // ---- persistent contacts (API.h:872-905 of the reference): a marked pair stays in the contact list even when the
+    // broad phase no longer proposes it.  A built-in force model gives a pair that is not in touch no force and clears
+    // its history (DEMCalcForceKernels.cu:258-262), so persistence changes no trajectory; it changes which POTENTIAL pairs
+    // are reported.  The marks are kept by the facade (owner pairs) and honoured in GetContacts / GetClumpContacts /
+    // GetContactDetailedInfo / WriteContactFileIncludingPotentialPairs, where a marked pair the list dropped re-appears
+    // with zero force.  Like the reference they need a model with history.
+    void MarkFamilyPersistentContactEither(unsigned int N);
+    void MarkFamilyPersistentContactBoth(unsigned int N);
+    void MarkFamilyPersistentContact(unsigned int N1, unsigned int N2);
+    void MarkPersistentContact();
+    void RemoveFamilyPersistentContactEither(unsigned int N);
+    void RemoveFamilyPersistentContactBoth(unsigned int N);
+    void RemoveFamilyPersistentContact(unsigned int N1, unsigned int N2);
+    void RemovePersistentContact();
+    size_t GetNumPersistentContacts() const { return m_persistent.size(); }
 
     void Initialize(bool dry_run = true);
     void DoDynamics(double thisCallDuration);
@@ -485,6 +752,27 @@ class DEMSolver {
     void ShowAnomalies() {}
     void ClearThreadCollaborationStats() {}
     void ClearTimingStats() {}
+    /// host bytes held by the facade's per-owner / per-geometry tables (the reference reports its two worker threads)
+    size_t GetHostMemUsageDynamic() const;
+    size_t GetHostMemUsageKinematic() const { return 0; }
+    void PrintKinematicScratchSpaceUsage() const {}
+    /// the reference waits for its asynchronous uploads here; every facade call returns with its transfer done
+    void SyncMemoryTransfer() {}
+    /// the reference re-derives bin size / margin policy and re-compiles; here changed settings take effect at once
+    void UpdateSimParams();
+    void ReleaseFlattenedArrays() {}
+    /// empty in the reference too (APIPublic.cpp:2444)
+    void PurgeFamily(unsigned int) {}
+    /// "not implemented and has no effect" in the reference (APIPublic.cpp:803-820): the same here, with its warning
+    void SetAdaptiveTimeStepType(const std::string& type);
+    bool GetWhetherForceCollectInKernel() const { return true; }
+    // run-time compilation settings of the reference: kept so that scripts can round-trip them; nothing is compiled here
+    std::unordered_map<std::string, std::string> GetJitStringSubs() const { return {}; }
+    std::vector<std::string> GetJitifyOptions() const { return m_jitify_options; }
+    void SetJitifyOptions(const std::vector<std::string>& options) { m_jitify_options = options; }
+    void SetKernelInclude(const std::string& includes) { m_kernel_includes = includes; }
+    void AddKernelInclude(const std::string& lib_name) { m_kernel_includes += "#include <" + lib_name + ">\n"; }
+    void RemoveKernelInclude() { m_kernel_includes = " "; }
 
     void WriteSphereFile(const std::filesystem::path& outfilename) const;
     void WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy = 10) const;
@@ -533,10 +821,19 @@ class DEMSolver {
     std::vector<std::pair<bodyID_t, bodyID_t>> GetContacts(const std::set<family_t>& family_to_include) const;
     std::vector<std::pair<bodyID_t, bodyID_t>> GetClumpContacts() const;
     std::vector<std::pair<bodyID_t, bodyID_t>> GetClumpContacts(const std::set<family_t>& family_to_include) const;
+    /// ... also reporting the two owners' families
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetContacts(std::vector<std::pair<family_t, family_t>>& family_pair) const;
+    std::vector<std::pair<bodyID_t, bodyID_t>> GetClumpContacts(std::vector<std::pair<family_t, family_t>>& family_pair) const;
+    /// Every listed contact whose force is at least force_thres (negative: all potential pairs), with the fields
+    /// SetContactOutputContent selected (API.h:552-569, dT.cpp:1619-1755 of the reference)
+    std::shared_ptr<ContactInfoContainer> GetContactDetailedInfo(float force_thres = -1.0) const;
     /// Every force pair (contact point in the world frame, force on the queried owner) that concerns one of the owners;
     /// a contact between two listed owners is reported once, for the A side. Needs the force record (default on).
     size_t GetOwnerContactForces(const std::vector<bodyID_t>& ownerIDs, std::vector<float3>& points,
                                  std::vector<float3>& forces) const;
+    size_t GetOwnerContactForces(const std::vector<bodyID_t>& ownerIDs, std::vector<float3>& points,
+                                 std::vector<float3>& forces, std::vector<float3>& torques,
+                                 bool torque_in_local = false) const;
 
     // raw owner access used by trackers (src/DEM/dT.cpp:3062-3130)
     /// state of n consecutive owners starting at ownerID (src/DEM/API.h:431-458 of the reference)
@@ -554,8 +851,13 @@ class DEMSolver {
     void SetOwnerVelocity(bodyID_t ownerID, const std::vector<float3>& vel);
     void SetOwnerAngVel(bodyID_t ownerID, const std::vector<float3>& angVel);
     void SetOwnerOriQ(bodyID_t ownerID, const std::vector<float4>& oriQ);
-    void SetOwnerFamily(bodyID_t ownerID, unsigned int fam);
+    void SetOwnerFamily(bodyID_t ownerID, unsigned int fam, bodyID_t n = 1);
+    /// extra (angular, owner frame) acceleration of consecutive owners for the next step only (API.h:477-486)
+    void AddOwnerNextStepAcc(bodyID_t ownerID, const std::vector<float3>& acc);
+    void AddOwnerNextStepAngAcc(bodyID_t ownerID, const std::vector<float3>& angAcc);
+    void ChangeClumpSizes(const std::vector<bodyID_t>& IDs, const std::vector<float>& factors);
     double Reduce(int kind) const;
+    double ReduceInRegion(int kind, const ScalarExpression& region) const;
     DemCtx* GetCoreContext() const { return ctx; }
 
   private:
@@ -593,6 +895,24 @@ class DEMSolver {
     unsigned int m_max_update_freq = 200;
     TIME_INTEGRATOR m_integrator = TIME_INTEGRATOR::EXTENDED_TAYLOR;
     FORCE_MODEL m_force_model = FORCE_MODEL::HERTZIAN;
+    std::shared_ptr<DEMForceModel> m_force_model_obj = std::make_shared<DEMForceModel>(FORCE_MODEL::HERTZIAN);
+    std::vector<std::string> m_jitify_options;
+    std::string m_kernel_includes;
+    // persistent contacts: (owner A, owner B, geometry A, geometry B, type) of every marked pair
+    struct PersistentPair {
+        bodyID_t ownerA, ownerB, geoA, geoB;
+        uint8_t type;
+        bool operator<(const PersistentPair& o) const {
+            return std::tie(geoA, geoB, type) < std::tie(o.geoA, o.geoB, o.type);
+        }
+    };
+    std::set<PersistentPair> m_persistent;
+    std::vector<std::tuple<uint32_t, uint32_t, uint8_t>> persistentKeys() const;
+    bool m_any_rolling_resistance = false;
+    std::vector<unsigned char> m_sp_blob;  // the DemSimParams of Initialize(), for UpdateSimParams
+    void markPersistent(int mode, unsigned int N1, unsigned int N2, bool mark);
+    void setContactWildcard(int mode, unsigned int N1, unsigned int N2, const std::string& name, float val);
+    [[noreturn]] void noSuchWildcard(const char* what, const std::string& name) const;
     float m_expand_factor = -1.f;
     float m_approx_max_vel = 1e15f;
     float m_expand_safety_multi = 1.f;
@@ -635,6 +955,7 @@ class DEMSolver {
     std::vector<float3> m_owner_moi;
     std::vector<unsigned int> m_owner_type_mark;  // clump template mark per clump owner
     std::vector<unsigned int> m_sphere_owner, m_tri_owner, m_anal_owner;
+    std::vector<unsigned int> m_owner_first_sphere;  // id of the first sphere of every owner (nSpheres for owners without)
     bodyID_t geoOwner(uint32_t geo, uint8_t type, bool sideB) const;
     std::vector<std::pair<bodyID_t, bodyID_t>> contactOwnerPairs(bool clumps_only, const std::set<family_t>* fams) const;
     double m_wall_time_dynamics = 0.0;

@@ -16,21 +16,27 @@
 
 namespace deme {
 
-class TimeExpression {
+/// A scalar expression of named variables.  The same grammar serves the prescriptions (one variable, t) and the region
+/// strings of inspectors and family-change conditions (owner variables such as X, Y, Z); a leading "return" and a
+/// trailing ';' -- the form such strings take in the reference, where they are pasted into a kernel -- are accepted.
+class ScalarExpression {
   public:
     /// Parse; throws std::runtime_error with the offending position on a syntax error or an unknown name.
-    explicit TimeExpression(const std::string& text) : m_text(text) {
+    ScalarExpression(const std::string& text, const std::vector<std::string>& variables) : m_text(text), m_vars(variables) {
         m_pos = 0;
+        if (eat("return")) skip();
         m_root = ternary();
+        while (eat(";")) {}
         skip();
         if (m_pos != m_text.size()) error("unexpected '" + std::string(1, m_text[m_pos]) + "'");
     }
-    double Eval(double t) const { return eval(m_root, t); }
-    bool IsConstant() const { return !m_uses_t; }
+    /// values[k] is the value of variables[k] of the constructor
+    double Eval(const double* values) const { return eval(m_root, values); }
+    bool IsConstant() const { return !m_uses_var; }
     const std::string& Text() const { return m_text; }
 
   private:
-    enum Op { NUM, TIME, NEG, NOT, ADD, SUB, MUL, DIV, LT, GT, LE, GE, EQ, NE, AND, OR, SEL, F1, F2 };
+    enum Op { NUM, VAR, NEG, NOT, ADD, SUB, MUL, DIV, LT, GT, LE, GE, EQ, NE, AND, OR, SEL, F1, F2 };
     struct Node {
         Op op;
         double val;
@@ -38,14 +44,17 @@ class TimeExpression {
         int fn;
     };
     std::string m_text;
+    std::vector<std::string> m_vars;
     size_t m_pos = 0;
     std::vector<Node> m_nodes;
     int m_root = -1;
-    bool m_uses_t = false;
+    bool m_uses_var = false;
 
     [[noreturn]] void error(const std::string& what) const {
-        throw std::runtime_error("Prescription \"" + m_text + "\": " + what + " at position " + std::to_string(m_pos) +
-                                 ". Supported: numbers, t, PI, + - * /, comparisons, && || !, ?:, and the functions sin cos "
+        std::string names;
+        for (const std::string& v : m_vars) names += v + ", ";
+        throw std::runtime_error("Expression \"" + m_text + "\": " + what + " at position " + std::to_string(m_pos) +
+                                 ". Supported: numbers, " + names + "PI, + - * /, comparisons, && || !, ?:, and the functions sin cos "
                                  "tan asin acos atan atan2 sinh cosh tanh exp log log10 sqrt abs fabs pow erf erfc floor ceil "
                                  "fmin fmax min max.");
     }
@@ -157,10 +166,11 @@ class TimeExpression {
                 name.push_back(m_text[m_pos++]);
             for (const char* prefix : {"deme::", "std::"})
                 if (name.rfind(prefix, 0) == 0) name = name.substr(strlen(prefix));
-            if (name == "t") {
-                m_uses_t = true;
-                return add(TIME);
-            }
+            for (size_t k = 0; k < m_vars.size(); k++)
+                if (name == m_vars[k]) {
+                    m_uses_var = true;
+                    return add(VAR, -1, -1, -1, 0.0, (int)k);
+                }
             if (name == "PI" || name == "M_PI") return add(NUM, -1, -1, -1, 3.14159265358979323846);
             static const char* f1[] = {"sin", "cos", "tan", "asin", "acos", "atan", "sinh", "cosh", "tanh", "exp", "log",
                                        "log10", "sqrt", "abs", "fabs", "erf", "erfc", "floor", "ceil", "sinf", "cosf",
@@ -186,11 +196,11 @@ class TimeExpression {
         }
         error("unexpected '" + std::string(1, ch) + "'");
     }
-    double eval(int i, double t) const {
+    double eval(int i, const double* t) const {
         const Node& n = m_nodes[i];
         switch (n.op) {
             case NUM: return n.val;
-            case TIME: return t;
+            case VAR: return t[n.fn];
             case NEG: return -eval(n.a, t);
             case NOT: return eval(n.a, t) == 0.0 ? 1.0 : 0.0;
             case ADD: return eval(n.a, t) + eval(n.b, t);
@@ -241,6 +251,13 @@ class TimeExpression {
         }
         return 0.0;
     }
+};
+
+/// Expressions of the simulation time alone (the prescription strings)
+class TimeExpression : public ScalarExpression {
+  public:
+    explicit TimeExpression(const std::string& text) : ScalarExpression(text, {"t"}) {}
+    double Eval(double t) const { return ScalarExpression::Eval(&t); }
 };
 
 }  // namespace deme

@@ -128,6 +128,34 @@ void DEMClumpBatch::SetFamilies(const std::vector<unsigned int>& input) {
     family_isSpecified = true;
 }
 
+void DEMClumpBatch::AddExistingContactWildcard(const std::string& name, const std::vector<float>& vals) {
+    if (vals.size() != contact_pairs.size())
+        fail("AddExistingContactWildcard needs one value per existing contact (" + std::to_string(contact_pairs.size()) +
+             " set via SetExistingContacts), but " + std::to_string(vals.size()) + " were given for " + name + ".");
+    contact_wildcards[name] = vals;
+}
+void DEMClumpBatch::SetOwnerWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards) {
+    for (const auto& kv : wildcards) assertLength(kv.second.size(), "SetOwnerWildcards");
+    owner_wildcards = wildcards;
+}
+void DEMClumpBatch::AddOwnerWildcard(const std::string& name, const std::vector<float>& vals) {
+    assertLength(vals.size(), "AddOwnerWildcard");
+    owner_wildcards[name] = vals;
+}
+void DEMClumpBatch::SetGeometryWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards) {
+    for (const auto& kv : wildcards)
+        if (kv.second.size() != nSpheres)
+            fail("SetGeometryWildcards needs one value per sphere of the batch (" + std::to_string(nSpheres) + "), not " +
+                 std::to_string(kv.second.size()) + ".");
+    geo_wildcards = wildcards;
+}
+void DEMClumpBatch::AddGeometryWildcard(const std::string& name, const std::vector<float>& vals) {
+    if (vals.size() != nSpheres)
+        fail("AddGeometryWildcard needs one value per sphere of the batch (" + std::to_string(nSpheres) + "), not " +
+             std::to_string(vals.size()) + ".");
+    geo_wildcards[name] = vals;
+}
+
 void DEMExternObj::SetFamily(const unsigned int code) {
     if (code > 255) fail("An external object is instructed to have a family number larger than the max allowance 255");
     family_code = code;
@@ -280,11 +308,52 @@ void DEMSolver::UpdateStepSize(double ts) {
 
 std::shared_ptr<DEMForceModel> DEMSolver::UseFrictionalHertzianModel() {
     m_force_model = FORCE_MODEL::HERTZIAN;
-    return std::make_shared<DEMForceModel>(m_force_model);
+    m_force_model_obj = std::make_shared<DEMForceModel>(m_force_model);
+    // what the model reads from the materials (AuxClasses.cpp:757-764 of the reference)
+    m_force_model_obj->SetMustHaveMatProp({"E", "nu", "CoR", "mu", "Crr"});
+    m_force_model_obj->SetMustPairwiseMatProp({"CoR", "mu", "Crr"});
+    return m_force_model_obj;
 }
 std::shared_ptr<DEMForceModel> DEMSolver::UseFrictionlessHertzianModel() {
     m_force_model = FORCE_MODEL::HERTZIAN_FRICTIONLESS;
-    return std::make_shared<DEMForceModel>(m_force_model);
+    m_force_model_obj = std::make_shared<DEMForceModel>(m_force_model);
+    m_force_model_obj->SetMustHaveMatProp({"E", "nu", "CoR"});
+    m_force_model_obj->SetMustPairwiseMatProp({"CoR"});
+    return m_force_model_obj;
+}
+namespace {
+const char* const kNoRuntimeCompilation =
+    ": custom force-model source needs run-time compilation, which this ahead-of-time compiled core does not have. Use "
+    "UseFrictionalHertzianModel() or UseFrictionlessHertzianModel().";
+std::vector<std::string> history_names(FORCE_MODEL m) {
+    if (m == FORCE_MODEL::HERTZIAN) return {"delta_tan_x", "delta_tan_y", "delta_tan_z", "delta_time"};
+    return {};
+}
+}  // namespace
+void DEMForceModel::SetPerContactWildcards(const std::set<std::string>& wildcards) {
+    const std::vector<std::string> own = history_names(type);
+    if (wildcards != std::set<std::string>(own.begin(), own.end()))
+        fail("SetPerContactWildcards: the built-in force models keep their own history words (delta_tan_x, delta_tan_y, "
+             "delta_tan_z, delta_time for the frictional model, none for the frictionless one); other sets belong to "
+             "custom models" + std::string(kNoRuntimeCompilation));
+}
+void DEMForceModel::SetPerOwnerWildcards(const std::set<std::string>& wildcards) {
+    if (!wildcards.empty()) fail("SetPerOwnerWildcards" + std::string(kNoRuntimeCompilation));
+}
+void DEMForceModel::SetPerGeometryWildcards(const std::set<std::string>& wildcards) {
+    if (!wildcards.empty()) fail("SetPerGeometryWildcards" + std::string(kNoRuntimeCompilation));
+}
+void DEMForceModel::SetForceModelType(FORCE_MODEL model_type) {
+    if (model_type == FORCE_MODEL::CUSTOM) fail("SetForceModelType(CUSTOM)" + std::string(kNoRuntimeCompilation));
+    type = model_type;
+}
+void DEMForceModel::DefineCustomModel(const std::string&) { fail("DefineCustomModel" + std::string(kNoRuntimeCompilation)); }
+int DEMForceModel::ReadCustomModelFile(const std::filesystem::path&) { fail("ReadCustomModelFile" + std::string(kNoRuntimeCompilation)); }
+void DEMForceModel::DefineCustomModelPrerequisites(const std::string&) {
+    fail("DefineCustomModelPrerequisites" + std::string(kNoRuntimeCompilation));
+}
+int DEMForceModel::ReadCustomModelPrerequisitesFile(const std::filesystem::path&) {
+    fail("ReadCustomModelPrerequisitesFile" + std::string(kNoRuntimeCompilation));
 }
 std::shared_ptr<DEMForceModel> DEMSolver::DefineContactForceModel(const std::string&) {
     fail("DefineContactForceModel: custom force-model source needs runtime compilation, which this ahead-of-time compiled "
@@ -743,6 +812,23 @@ void DEMSolver::Initialize(bool dry_run) {
     if (m_loaded_materials.empty()) fail("Before initializing the system, at least one material type should be loaded via LoadMaterial.");
     if (m_ts_size <= 0.0) fail("Time step size is set to be " + std::to_string(m_ts_size) + ". Please supply a positive number via SetInitTimeStep.");
 
+    for (const auto& b : m_cached_input_clump_batches)
+        if (!b->owner_wildcards.empty() || !b->geo_wildcards.empty())
+            fail("A clump batch carries owner / geometry wildcards (" +
+                 (b->owner_wildcards.empty() ? b->geo_wildcards.begin()->first : b->owner_wildcards.begin()->first) +
+                 "), but the force model in use declares none. Wildcards of this kind belong to custom force models, "
+                 "which need run-time compilation that this ahead-of-time compiled core does not have.");
+    // material properties the force model reads (equipMaterials, APIPrivate.cpp:1882-1933): missing ones default to 0
+    if (m_force_model_obj && verbosity >= WARNING)
+        for (const std::string& prop_name : m_force_model_obj->m_must_have_mat_props)
+            for (const auto& mat : m_loaded_materials)
+                if (!mat->mat_prop.count(prop_name)) {
+                    std::cerr << "WARNING! Material property " << prop_name << " is needed by the force model or is "
+                              << "referred to by the user. However, at least one material does not have it defined, so it "
+                              << "is defaulted to 0 for that material.\nPlease be sure this is intentional." << std::endl;
+                    break;
+                }
+
     // ---- world sizing (figureOutNV) ----
     DemSimParams sp;
     memset(&sp, 0, sizeof(sp));
@@ -767,6 +853,7 @@ void DEMSolver::Initialize(bool dry_run) {
     sp.errOutVel = threshold_error_out_vel;
     sp.record_contact_forces = no_recording_contact_forces ? 0u : 1u;
     check(dem_set_params(ctx, &sp), "dem_set_params");
+    m_sp_blob.assign((const unsigned char*)&sp, (const unsigned char*)&sp + sizeof(sp));  // (for UpdateSimParams)
 
     // ---- world bounding box: one external object appended now (addWorldBoundingBox, APIPrivate.cpp:955-1014) ----
     std::vector<std::shared_ptr<DEMExternObj>> ext = m_cached_extern_objs;
@@ -830,6 +917,7 @@ void DEMSolver::Initialize(bool dry_run) {
             }
     }
     check(dem_upload_materials(ctx, nM, E.data(), nu.data(), CoR.data(), mu.data(), Crr.data()), "dem_upload_materials");
+    m_any_rolling_resistance = std::any_of(Crr.begin(), Crr.end(), [](float c) { return c > 0.f; });
 
     // ---- owners: clumps, then external objects, then meshes (dT.cpp:638-1024) ----
     size_t nC = 0;
@@ -948,6 +1036,8 @@ void DEMSolver::Initialize(bool dry_run) {
     check(dem_set_option(ctx, "adaptive_update_freq", m_adaptive_update_freq ? 1.0 : 0.0), "UseAdaptiveUpdateFreq");
     nOwnerClumps = nC; nOwnerBodies = nO; nSpheres = sph_owner.size();
     m_sphere_owner = sph_owner;
+    m_owner_first_sphere.assign(nO + 1, (unsigned int)sph_owner.size());  // spheres are numbered owner by owner
+    for (size_t s_id = sph_owner.size(); s_id-- > 0;) m_owner_first_sphere[sph_owner[s_id]] = (unsigned int)s_id;
     m_tri_owner = triOwner;
     m_anal_owner = objOwner;
     if (!m_trackers.empty()) check(dem_set_option(ctx, "keep_acc", 1.0), "dem_set_option");
@@ -1234,10 +1324,28 @@ void DEMSolver::SetOwnerOriQ(bodyID_t ownerID, const std::vector<float4>& oriQ) 
     for (size_t i = 0; i < oriQ.size(); i++) { q[4 * i] = oriQ[i].w; q[4 * i + 1] = oriQ[i].x; q[4 * i + 2] = oriQ[i].y; q[4 * i + 3] = oriQ[i].z; }
     check(dem_upload_owner_state(ctx, ownerID, (uint32_t)oriQ.size(), nullptr, q.data(), nullptr, nullptr, nullptr), "dem_upload_owner_state");
 }
-void DEMSolver::SetOwnerFamily(bodyID_t ownerID, unsigned int fam) {
+void DEMSolver::SetOwnerFamily(bodyID_t ownerID, unsigned int fam, bodyID_t n) {
     assertInit("SetOwnerFamily");
-    const uint8_t f = (uint8_t)fam;
-    check(dem_upload_owner_state(ctx, ownerID, 1, nullptr, nullptr, nullptr, nullptr, &f), "dem_upload_owner_state");
+    if (fam > 255) fail("SetOwnerFamily: family number " + std::to_string(fam) + " is larger than the max allowance 255");
+    if (n == 0) return;
+    const std::vector<uint8_t> f(n, (uint8_t)fam);
+    check(dem_upload_owner_state(ctx, ownerID, n, nullptr, nullptr, nullptr, nullptr, f.data()), "dem_upload_owner_state");
+}
+void DEMSolver::AddOwnerNextStepAcc(bodyID_t ownerID, const std::vector<float3>& acc) {
+    assertInit("AddOwnerNextStepAcc");
+    if (acc.empty()) return;
+    check(dem_add_owner_acc(ctx, ownerID, (uint32_t)acc.size(), flat3(acc).data(), nullptr), "dem_add_owner_acc");
+}
+void DEMSolver::AddOwnerNextStepAngAcc(bodyID_t ownerID, const std::vector<float3>& angAcc) {
+    assertInit("AddOwnerNextStepAngAcc");
+    if (angAcc.empty()) return;
+    check(dem_add_owner_acc(ctx, ownerID, (uint32_t)angAcc.size(), nullptr, flat3(angAcc).data()), "dem_add_owner_acc");
+}
+void DEMSolver::ChangeClumpSizes(const std::vector<bodyID_t>&, const std::vector<float>&) {
+    // (the reference needs flattened, non-jitified templates for this, APIPublic.cpp:2416-2442; this core always
+    // addresses sphere components through their clump template, so a single clump cannot be resized)
+    fail("ChangeClumpSizes is not available: clump components are stored per template, not per clump. Load a scaled "
+         "template (DEMClumpTemplate::Scale) and add the clumps with it instead.");
 }
 double DEMSolver::Reduce(int kind) const {
     assertInit("inspector");
@@ -1260,6 +1368,16 @@ bodyID_t DEMTracker::GetOwnerID(size_t offset) {
     if (offset >= count()) fail("Tracker offset exceeds the number of owners it tracks.");
     return first() + (bodyID_t)offset;
 }
+void DEMTracker::assertOwnerSize(size_t input_length, const std::string& name) {
+    if (input_length != count())
+        fail(name + " is called with " + std::to_string(input_length) + " values, but this tracker tracks " +
+             std::to_string(count()) + " owners.");
+}
+std::vector<bodyID_t> DEMTracker::GetOwnerIDs() {
+    std::vector<bodyID_t> ids(count());
+    for (size_t i = 0; i < ids.size(); i++) ids[i] = first() + (bodyID_t)i;
+    return ids;
+}
 float3 DEMTracker::Pos(size_t offset) { return sys->GetOwnerPosition(GetOwnerID(offset))[0]; }
 float3 DEMTracker::Vel(size_t offset) { return sys->GetOwnerVelocity(GetOwnerID(offset))[0]; }
 float3 DEMTracker::AngVelLocal(size_t offset) { return sys->GetOwnerAngVel(GetOwnerID(offset))[0]; }
@@ -1270,24 +1388,63 @@ float3 DEMTracker::AngVelGlobal(size_t offset) {
 float4 DEMTracker::OriQ(size_t offset) { return sys->GetOwnerOriQ(GetOwnerID(offset))[0]; }
 float3 DEMTracker::ContactAcc(size_t offset) { return sys->GetOwnerAcc(GetOwnerID(offset))[0]; }
 float3 DEMTracker::ContactAngAccLocal(size_t offset) { return sys->GetOwnerAngAcc(GetOwnerID(offset))[0]; }
+float3 DEMTracker::ContactAngAccGlobal(size_t offset) {
+    const bodyID_t id = GetOwnerID(offset);
+    return Rotate(sys->GetOwnerAngAcc(id)[0], sys->GetOwnerOriQ(id)[0]);
+}
 float DEMTracker::Mass(size_t offset) { return sys->GetOwnerMass(GetOwnerID(offset))[0]; }
 float3 DEMTracker::MOI(size_t offset) { return sys->GetOwnerMOI(GetOwnerID(offset))[0]; }
 unsigned int DEMTracker::GetFamily(size_t offset) { return sys->GetOwnerFamily(GetOwnerID(offset))[0]; }
-std::vector<float3> DEMTracker::Positions() {
-    std::vector<float3> out;
-    for (size_t i = 0; i < count(); i++) out.push_back(Pos(i));
-    return out;
+// the plural forms: one transfer for the whole tracked object
+std::vector<float3> DEMTracker::Positions() { return sys->GetOwnerPosition(first(), (bodyID_t)count()); }
+std::vector<float3> DEMTracker::Velocities() { return sys->GetOwnerVelocity(first(), (bodyID_t)count()); }
+std::vector<float3> DEMTracker::AngularVelocitiesLocal() { return sys->GetOwnerAngVel(first(), (bodyID_t)count()); }
+namespace {
+std::vector<float3> to_global(std::vector<float3> v, const std::vector<float4>& q) {
+    for (size_t i = 0; i < v.size(); i++) v[i] = Rotate(v[i], q[i]);
+    return v;
 }
-std::vector<float3> DEMTracker::Velocities() {
-    std::vector<float3> out;
-    for (size_t i = 0; i < count(); i++) out.push_back(Vel(i));
-    return out;
+}  // namespace
+std::vector<float3> DEMTracker::AngularVelocitiesGlobal() {
+    return to_global(sys->GetOwnerAngVel(first(), (bodyID_t)count()), sys->GetOwnerOriQ(first(), (bodyID_t)count()));
 }
+std::vector<float4> DEMTracker::OrientationQuaternions() { return sys->GetOwnerOriQ(first(), (bodyID_t)count()); }
+std::vector<unsigned int> DEMTracker::GetFamilies() { return sys->GetOwnerFamily(first(), (bodyID_t)count()); }
+std::vector<bodyID_t> DEMTracker::GetContactClumps(size_t offset) { return sys->GetOwnerContactClumps(GetOwnerID(offset)); }
+std::vector<float3> DEMTracker::ContactAccelerations() { return sys->GetOwnerAcc(first(), (bodyID_t)count()); }
+std::vector<float3> DEMTracker::ContactAngularAccelerationsLocal() { return sys->GetOwnerAngAcc(first(), (bodyID_t)count()); }
+std::vector<float3> DEMTracker::ContactAngularAccelerationsGlobal() {
+    return to_global(sys->GetOwnerAngAcc(first(), (bodyID_t)count()), sys->GetOwnerOriQ(first(), (bodyID_t)count()));
+}
+std::vector<float> DEMTracker::Masses() { return sys->GetOwnerMass(first(), (bodyID_t)count()); }
+std::vector<float3> DEMTracker::MOIs() { return sys->GetOwnerMOI(first(), (bodyID_t)count()); }
 void DEMTracker::SetPos(float3 pos, size_t offset) { sys->SetOwnerPosition(GetOwnerID(offset), std::vector<float3>{pos}); }
 void DEMTracker::SetVel(float3 vel, size_t offset) { sys->SetOwnerVelocity(GetOwnerID(offset), std::vector<float3>{vel}); }
 void DEMTracker::SetAngVel(float3 angVel, size_t offset) { sys->SetOwnerAngVel(GetOwnerID(offset), std::vector<float3>{angVel}); }
 void DEMTracker::SetOriQ(float4 oriQ, size_t offset) { sys->SetOwnerOriQ(GetOwnerID(offset), std::vector<float4>{oriQ}); }
+void DEMTracker::SetPos(const std::vector<float3>& pos) { assertOwnerSize(pos.size(), "SetPos"); sys->SetOwnerPosition(first(), pos); }
+void DEMTracker::SetVel(const std::vector<float3>& vel) { assertOwnerSize(vel.size(), "SetVel"); sys->SetOwnerVelocity(first(), vel); }
+void DEMTracker::SetAngVel(const std::vector<float3>& angVel) { assertOwnerSize(angVel.size(), "SetAngVel"); sys->SetOwnerAngVel(first(), angVel); }
+void DEMTracker::SetOriQ(const std::vector<float4>& oriQ) { assertOwnerSize(oriQ.size(), "SetOriQ"); sys->SetOwnerOriQ(first(), oriQ); }
+void DEMTracker::AddAcc(float3 acc, size_t offset) { sys->AddOwnerNextStepAcc(GetOwnerID(offset), std::vector<float3>{acc}); }
+void DEMTracker::AddAcc(const std::vector<float3>& acc) { assertOwnerSize(acc.size(), "AddAcc"); sys->AddOwnerNextStepAcc(first(), acc); }
+void DEMTracker::AddAngAcc(float3 angAcc, size_t offset) { sys->AddOwnerNextStepAngAcc(GetOwnerID(offset), std::vector<float3>{angAcc}); }
+void DEMTracker::AddAngAcc(const std::vector<float3>& angAcc) { assertOwnerSize(angAcc.size(), "AddAngAcc"); sys->AddOwnerNextStepAngAcc(first(), angAcc); }
+void DEMTracker::SetFamily(unsigned int fam_num) { sys->SetOwnerFamily(first(), fam_num, (bodyID_t)count()); }
 void DEMTracker::SetFamily(unsigned int fam_num, size_t offset) { sys->SetOwnerFamily(GetOwnerID(offset), fam_num); }
+void DEMTracker::ChangeClumpSizes(const std::vector<bodyID_t>& IDs, const std::vector<float>& factors) {
+    std::vector<bodyID_t> offsetted = IDs;
+    for (bodyID_t& id : offsetted) id += first();
+    sys->ChangeClumpSizes(offsetted, factors);
+}
+float DEMTracker::GetOwnerWildcardValue(const std::string& name, size_t offset) { return sys->GetOwnerWildcardValue(GetOwnerID(offset), name)[0]; }
+std::vector<float> DEMTracker::GetOwnerWildcardValues(const std::string& name) { return sys->GetOwnerWildcardValue(first(), name, (bodyID_t)count()); }
+float DEMTracker::GetGeometryWildcardValue(const std::string& name, size_t offset) { return sys->GetSphereWildcardValue((bodyID_t)offset, name, 1)[0]; }
+std::vector<float> DEMTracker::GetGeometryWildcardValues(const std::string& name) { return sys->GetSphereWildcardValue(0, name, 1); }
+void DEMTracker::SetOwnerWildcardValue(const std::string& name, float wc, size_t offset) { sys->SetOwnerWildcardValue(GetOwnerID(offset), name, wc); }
+void DEMTracker::SetOwnerWildcardValues(const std::string& name, const std::vector<float>& wc) { sys->SetOwnerWildcardValue(first(), name, wc); }
+void DEMTracker::SetGeometryWildcardValue(const std::string& name, float wc, size_t offset) { sys->SetSphereWildcardValue((bodyID_t)offset, name, std::vector<float>{wc}); }
+void DEMTracker::SetGeometryWildcardValues(const std::string& name, const std::vector<float>& wc) { sys->SetSphereWildcardValue(0, name, wc); }
 
 // ---- inspectors ----
 DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(sim) {
@@ -1296,10 +1453,15 @@ DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(si
     else if (quantity == "clump_max_absv" || quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;
     else if (quantity == "clump_kinetic_energy") kind = DEM_REDUCE_KINETIC_ENERGY;
     else if (quantity == "clump_mass") kind = DEM_REDUCE_TOTAL_MASS;
-    else fail("Inspector quantity " + quantity + " is not built into this core (available: clump_max_z, clump_min_z, "
-              "clump_max_absv, max_absv, clump_kinetic_energy, clump_mass).");
+    else if (quantity == "clump_volume") kind = 100;  // KIND_CLUMP_VOLUME: summed on the host from the templates
+    else fail(quantity + " is not a known query type (available: clump_max_z, clump_min_z, clump_max_absv, max_absv, "
+              "clump_kinetic_energy, clump_mass, clump_volume).");
 }
-float DEMInspector::GetValue() { return (float)sys->Reduce(kind); }
+float DEMInspector::GetValue() {
+    if (region) return (float)sys->ReduceInRegion(kind, *region);
+    if (kind == 100) return (float)sys->ReduceInRegion(kind, ScalarExpression("1", {"X", "Y", "Z"}));
+    return (float)sys->Reduce(kind);
+}
 
 // ---- writers (dT.cpp:1254-1617): CSV only ----
 void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy) const {
@@ -1364,6 +1526,17 @@ void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float
     std::vector<uint8_t> t(n);
     std::vector<float> wc(4 * n), fr(3 * n);
     if (n) check(dem_download_contacts(ctx, n, &n, a.data(), b.data(), t.data(), wc.data(), fr.data()), "dem_download_contacts");
+    if (force_thres < 0.f && !m_persistent.empty()) {  // marked pairs the list dropped are still potential pairs
+        std::set<std::tuple<uint32_t, uint32_t, uint8_t>> listed;
+        for (uint64_t i = 0; i < n; i++) listed.emplace(a[i], b[i], t[i]);
+        for (const auto& p : m_persistent)
+            if (!listed.count(std::make_tuple(p.geoA, p.geoB, p.type))) {
+                a.push_back(p.geoA); b.push_back(p.geoB); t.push_back(p.type);
+                wc.insert(wc.end(), 4, 0.f);
+                fr.insert(fr.end(), 3, 0.f);
+                n++;
+            }
+    }
     std::ofstream f(outfilename);
     // columns as the reference writes them (dT.cpp:1700-1936): owners A/B, geometry ids geoA/geoB (sphere id; component
     // or facet id on the B side of SA / SM contacts), force on A, then the wildcards
@@ -1516,7 +1689,13 @@ bodyID_t DEMSolver::geoOwner(uint32_t geo, uint8_t type, bool sideB) const {
 }
 std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::contactOwnerPairs(bool clumps_only, const std::set<family_t>* fams) const {
     assertInit("GetContacts");
-    const ContactRows r = download_rows(ctx, false);
+    ContactRows r = download_rows(ctx, false);
+    if (!m_persistent.empty()) {  // marked pairs the list has dropped since stay reported
+        std::set<std::tuple<uint32_t, uint32_t, uint8_t>> listed;
+        for (size_t i = 0; i < r.a.size(); i++) listed.emplace(r.a[i], r.b[i], r.t[i]);
+        for (const auto& p : m_persistent)
+            if (!listed.count(std::make_tuple(p.geoA, p.geoB, p.type))) { r.a.push_back(p.geoA); r.b.push_back(p.geoB); r.t.push_back(p.type); }
+    }
     std::vector<uint8_t> fam;
     if (fams) {
         fam.resize(nOwnerBodies);
@@ -1602,6 +1781,453 @@ std::unordered_map<std::string, std::vector<float>> DEMSolver::ReadContactWildca
             if (r[it] == cntType) v.push_back((float)atof(r[c].c_str()));
     }
     return out;
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Contact read-outs with the fields of SetContactOutputContent, contact wildcards, persistent contacts
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+// one row per listed contact: geometry ids, type, force on A + contact point (world frame), the four history words
+struct FullRows {
+    std::vector<uint32_t> a, b;
+    std::vector<uint8_t> t;
+    std::vector<float> force, point, wc;
+    size_t size() const { return a.size(); }
+};
+FullRows download_full_rows(DemCtx* ctx, bool with_record) {
+    FullRows r;
+    uint64_t n = 0;
+    if (dem_download_contacts(ctx, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr) != DEM_OK) fail(dem_last_error(ctx));
+    r.a.resize(n); r.b.resize(n); r.t.resize(n); r.wc.resize(4 * n);
+    r.force.assign(3 * n, 0.f); r.point.assign(3 * n, 0.f);
+    if (!n) return r;
+    const int rc = with_record ? dem_download_contact_records(ctx, n, &n, r.a.data(), r.b.data(), r.t.data(), r.wc.data(),
+                                                              r.force.data(), r.point.data())
+                               : dem_download_contacts(ctx, n, &n, r.a.data(), r.b.data(), r.t.data(), r.wc.data(), nullptr);
+    if (rc != DEM_OK) fail(dem_last_error(ctx));
+    return r;
+}
+const char* contact_type_name(uint8_t t) {
+    return t == DEM_CNT_SPHERE_SPHERE ? "SS" : (t == DEM_CNT_SPHERE_MESH ? "SM" : "SA");
+}
+const char* const kWildcardNames[4] = {"delta_tan_x", "delta_tan_y", "delta_tan_z", "delta_time"};
+}  // namespace
+
+ContactInfoContainer::ContactInfoContainer(unsigned int cnt_out_content, const std::vector<std::string>& wildcard_names)
+    : m_content(cnt_out_content), m_wc_names(wildcard_names), m_wc(wildcard_names.size()) {}
+std::vector<float>& ContactInfoContainer::GetWildcard(const std::string& name) {
+    if (m_content & CNT_WILDCARD)
+        for (size_t k = 0; k < m_wc_names.size(); k++)
+            if (m_wc_names[k] == name) return m_wc[k];
+    throw std::runtime_error("ContactInfoContainer does not have field: '" + name +
+                             "', you may need to turn on the output of this field by correctly calling "
+                             "SetContactOutputContent before Initialize().");
+}
+void ContactInfoContainer::ResizeAll(size_t n) {
+    m_type.resize(n);
+    m_family[0].resize(n); m_family[1].resize(n);
+    if (m_content & CNT_POINT) m_point.resize(n);
+    if (m_content & FORCE) m_force.resize(n);
+    if (m_content & TORQUE) m_torque.resize(n);
+    if (m_content & NORMAL) m_normal.resize(n);
+    if (m_content & OWNER) { m_owner[0].resize(n); m_owner[1].resize(n); }
+    if (m_content & GEO_ID) { m_geo[0].resize(n); m_geo[1].resize(n); }
+    if (m_content & CNT_WILDCARD)
+        for (auto& w : m_wc) w.resize(n);
+}
+
+// marked pairs the broad phase no longer lists come back as rows without force (see the header)
+static void append_persistent(FullRows& r, const std::vector<std::tuple<uint32_t, uint32_t, uint8_t>>& marked) {
+    if (marked.empty()) return;
+    std::set<std::tuple<uint32_t, uint32_t, uint8_t>> listed;
+    for (size_t i = 0; i < r.size(); i++) listed.emplace(r.a[i], r.b[i], r.t[i]);
+    for (const auto& m : marked) {
+        if (listed.count(m)) continue;
+        r.a.push_back(std::get<0>(m)); r.b.push_back(std::get<1>(m)); r.t.push_back(std::get<2>(m));
+        r.force.insert(r.force.end(), 3, 0.f);
+        r.point.insert(r.point.end(), 3, 0.f);
+        r.wc.insert(r.wc.end(), 4, 0.f);
+    }
+}
+std::vector<std::tuple<uint32_t, uint32_t, uint8_t>> DEMSolver::persistentKeys() const {
+    std::vector<std::tuple<uint32_t, uint32_t, uint8_t>> keys;
+    for (const auto& p : m_persistent) keys.emplace_back(p.geoA, p.geoB, p.type);
+    return keys;
+}
+
+std::shared_ptr<ContactInfoContainer> DEMSolver::GetContactDetailedInfo(float force_thres) const {
+    assertInit("GetContactDetailedInfo");
+    const bool has_record = !no_recording_contact_forces;
+    if (!has_record && (m_cnt_out_content & (FORCE | CNT_POINT | NORMAL | TORQUE)))
+        fail("GetContactDetailedInfo: force, point, normal and torque come from the per-contact force record; do not call "
+             "SetNoForceRecord() if you query them.");
+    FullRows r = download_full_rows(ctx, has_record);
+    append_persistent(r, persistentKeys());
+    std::vector<std::string> names;
+    if (m_force_model == FORCE_MODEL::HERTZIAN) names.assign(kWildcardNames, kWildcardNames + 4);
+    auto info = std::make_shared<ContactInfoContainer>(m_cnt_out_content, names);
+    info->ResizeAll(r.size());
+    const uint32_t nO = (uint32_t)nOwnerBodies;
+    std::vector<uint8_t> fam(nO);
+    std::vector<float> q;
+    std::vector<double> pos;
+    check(dem_download_owner_state(ctx, 0, nO, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                   fam.data()), "dem_download_owner_state");
+    const bool want_normal = (m_cnt_out_content & NORMAL) != 0;
+    if (want_normal) {
+        q.resize(4 * (size_t)nO);
+        pos.resize(3 * (size_t)nO);
+        check(dem_download_owner_state(ctx, 0, nO, nullptr, nullptr, nullptr, nullptr, q.data(), nullptr, nullptr, nullptr,
+                                       nullptr, nullptr), "dem_download_owner_state");
+        check(dem_download_positions(ctx, 0, nO, nullptr, pos.data()), "dem_download_positions");
+    }
+    // the rolling-resistance couple of a contact is applied to the owners but not kept per contact
+    bool warned = false;
+    size_t useful = 0;
+    for (size_t i = 0; i < r.size(); i++) {
+        const float3 F = make_float3(r.force[3 * i], r.force[3 * i + 1], r.force[3 * i + 2]);
+        if (length(F) < force_thres) continue;  // (dT.cpp:1647-1651 of the reference)
+        const bodyID_t oa = geoOwner(r.a[i], r.t[i], false), ob = geoOwner(r.b[i], r.t[i], true);
+        info->GetContactType()[useful] = contact_type_name(r.t[i]);
+        info->GetAOwnerFamily()[useful] = fam[oa];
+        info->GetBOwnerFamily()[useful] = fam[ob];
+        if (m_cnt_out_content & OWNER) { info->GetAOwner()[useful] = oa; info->GetBOwner()[useful] = ob; }
+        if (m_cnt_out_content & GEO_ID) { info->GetAGeo()[useful] = r.a[i]; info->GetBGeo()[useful] = r.b[i]; }
+        if (m_cnt_out_content & FORCE) info->GetForce()[useful] = F;
+        const float3 P = make_float3(r.point[3 * i], r.point[3 * i + 1], r.point[3 * i + 2]);
+        if (m_cnt_out_content & CNT_POINT) info->GetPoint()[useful] = P;
+        if (want_normal) {
+            // outward normal of body A: from the centre of sphere A to the contact point (dT.cpp:1714-1727)
+            const auto& tp = m_templates[m_owner_type_mark[oa]];
+            const float4 qa = make_float4(q[4 * oa + 1], q[4 * oa + 2], q[4 * oa + 3], q[4 * oa]);
+            const float3 off = Rotate(tp->relPos[r.a[i] - m_owner_first_sphere[oa]], qa);
+            const float3 c = make_float3((float)pos[3 * oa] + off.x, (float)pos[3 * oa + 1] + off.y, (float)pos[3 * oa + 2] + off.z);
+            const float3 d = P - c;
+            const float len = length(d);
+            info->GetNormal()[useful] = len > 0.f ? d * (1.f / len) : make_float3(0, 0, 0);
+        }
+        if (m_cnt_out_content & TORQUE) {
+            if (!warned && m_any_rolling_resistance && verbosity >= WARNING) {
+                std::cerr << "WARNING! The torque field of GetContactDetailedInfo is the couple a contact adds beyond the "
+                             "moment of its force (rolling resistance). This core applies it to the owners without keeping "
+                             "it per contact, so the field reads zero." << std::endl;
+                warned = true;
+            }
+            info->GetTorque()[useful] = make_float3(0, 0, 0);
+        }
+        if (m_cnt_out_content & CNT_WILDCARD)
+            for (size_t k = 0; k < names.size(); k++) info->GetWildcard(names[k])[useful] = r.wc[4 * i + k];
+        useful++;
+    }
+    info->ResizeAll(useful);
+    return info;
+}
+
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetContacts(std::vector<std::pair<family_t, family_t>>& family_pair) const {
+    const auto pairs = contactOwnerPairs(false, nullptr);
+    const auto fam = GetOwnerFamily(0, (bodyID_t)nOwnerBodies);
+    family_pair.clear();
+    for (const auto& p : pairs) family_pair.emplace_back((family_t)fam[p.first], (family_t)fam[p.second]);
+    return pairs;
+}
+std::vector<std::pair<bodyID_t, bodyID_t>> DEMSolver::GetClumpContacts(std::vector<std::pair<family_t, family_t>>& family_pair) const {
+    const auto pairs = contactOwnerPairs(true, nullptr);
+    const auto fam = GetOwnerFamily(0, (bodyID_t)nOwnerBodies);
+    family_pair.clear();
+    for (const auto& p : pairs) family_pair.emplace_back((family_t)fam[p.first], (family_t)fam[p.second]);
+    return pairs;
+}
+
+size_t DEMSolver::GetOwnerContactForces(const std::vector<bodyID_t>& ownerIDs, std::vector<float3>& points,
+                                        std::vector<float3>& forces, std::vector<float3>& torques, bool torque_in_local) const {
+    // (dT.cpp:2793-2853 of the reference: the torque is the contact's "torque-only force" -- the rolling-resistance couple --
+    // turned into a moment about the owner's centre; the moment of the force itself is NOT part of it)
+    (void)torque_in_local;  // a zero vector reads the same in both frames
+    const size_t n = GetOwnerContactForces(ownerIDs, points, forces);
+    if (m_any_rolling_resistance && verbosity >= WARNING)
+        std::cerr << "WARNING! GetOwnerContactForces: the rolling-resistance couple is applied to the owners without being "
+                     "kept per contact, so the torques read zero." << std::endl;
+    torques.assign(n, make_float3(0, 0, 0));
+    return n;
+}
+size_t DEMTracker::GetContactForcesAndGlobalTorque(std::vector<float3>& points, std::vector<float3>& forces,
+                                                   std::vector<float3>& torques, size_t offset) {
+    return sys->GetOwnerContactForces({GetOwnerID(offset)}, points, forces, torques, false);
+}
+size_t DEMTracker::GetContactForcesAndGlobalTorqueForAll(std::vector<float3>& points, std::vector<float3>& forces,
+                                                         std::vector<float3>& torques) {
+    return sys->GetOwnerContactForces(GetOwnerIDs(), points, forces, torques, false);
+}
+size_t DEMTracker::GetContactForcesAndLocalTorque(std::vector<float3>& points, std::vector<float3>& forces,
+                                                  std::vector<float3>& torques, size_t offset) {
+    return sys->GetOwnerContactForces({GetOwnerID(offset)}, points, forces, torques, true);
+}
+size_t DEMTracker::GetContactForcesAndLocalTorqueForAll(std::vector<float3>& points, std::vector<float3>& forces,
+                                                        std::vector<float3>& torques) {
+    return sys->GetOwnerContactForces(GetOwnerIDs(), points, forces, torques, true);
+}
+
+// ---- contact wildcards (the history words) ----
+void DEMSolver::noSuchWildcard(const char* what, const std::string& name) const {
+    fail(std::string("No ") + what + " wildcard in the force model is named " + name + ".\nThe built-in force models declare "
+         "the contact wildcards delta_tan_x, delta_tan_y, delta_tan_z, delta_time (frictional model) and no owner or geometry "
+         "wildcards; others belong to custom force models, which need run-time compilation that this core does not have.");
+}
+void DEMSolver::setContactWildcard(int mode, unsigned int N1, unsigned int N2, const std::string& name, float val) {
+    int word = -1;
+    if (m_force_model == FORCE_MODEL::HERTZIAN)
+        for (int k = 0; k < 4; k++)
+            if (name == kWildcardNames[k]) word = k;
+    if (word < 0) noSuchWildcard("contact", name);
+    // (dT.cpp:2855-2884 of the reference rewrites the word of every contact in its array whose owners' families match;
+    // here the list is read back, edited and handed to the next rebuild as its history source, like a restart)
+    FullRows r = download_full_rows(ctx, false);
+    if (!r.size()) return;
+    const auto fam = GetOwnerFamily(0, (bodyID_t)nOwnerBodies);
+    size_t changed = 0;
+    for (size_t i = 0; i < r.size(); i++) {
+        const unsigned int fa = fam[geoOwner(r.a[i], r.t[i], false)], fb = fam[geoOwner(r.b[i], r.t[i], true)];
+        bool hit = true;
+        if (mode == 1) hit = (fa == N1 || fb == N1);
+        else if (mode == 2) hit = (fa == N1 && fb == N1);
+        else if (mode == 3) hit = (fa == N1 && fb == N2) || (fa == N2 && fb == N1);
+        if (!hit) continue;
+        r.wc[4 * i + word] = val;
+        changed++;
+    }
+    if (changed)
+        check(dem_set_contacts(ctx, r.size(), r.a.data(), r.b.data(), r.t.data(), r.wc.data()), "dem_set_contacts");
+}
+void DEMSolver::SetContactWildcardValue(const std::string& name, float val) {
+    assertInit("SetContactWildcardValue");
+    setContactWildcard(0, 0, 0, name, val);
+}
+void DEMSolver::SetFamilyContactWildcardValueEither(unsigned int N, const std::string& name, float val) {
+    assertInit("SetFamilyContactWildcardValueEither");
+    setContactWildcard(1, N, 0, name, val);
+}
+void DEMSolver::SetFamilyContactWildcardValueBoth(unsigned int N, const std::string& name, float val) {
+    assertInit("SetFamilyContactWildcardValueBoth");
+    setContactWildcard(2, N, 0, name, val);
+}
+void DEMSolver::SetFamilyContactWildcardValue(unsigned int N1, unsigned int N2, const std::string& name, float val) {
+    assertInit("SetFamilyContactWildcardValue");
+    setContactWildcard(3, N1, N2, name, val);
+}
+void DEMSolver::SetContactWildcards(const std::set<std::string>& wildcards) { m_force_model_obj->SetPerContactWildcards(wildcards); }
+void DEMSolver::SetOwnerWildcards(const std::set<std::string>& wildcards) { m_force_model_obj->SetPerOwnerWildcards(wildcards); }
+void DEMSolver::SetGeometryWildcards(const std::set<std::string>& wildcards) { m_force_model_obj->SetPerGeometryWildcards(wildcards); }
+
+// owner / geometry wildcards: no built-in model declares any, so every name is unknown (APIPublic.cpp:1042-1180)
+void DEMSolver::SetOwnerWildcardValue(bodyID_t, const std::string& name, const std::vector<float>&) {
+    assertInit("SetOwnerWildcardValue");
+    noSuchWildcard("owner", name);
+}
+void DEMSolver::SetFamilyOwnerWildcardValue(unsigned int, const std::string& name, const std::vector<float>&) {
+    assertInit("SetFamilyOwnerWildcardValue");
+    noSuchWildcard("owner", name);
+}
+void DEMSolver::SetTriWildcardValue(bodyID_t, const std::string& name, const std::vector<float>&) {
+    assertInit("SetTriWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+void DEMSolver::SetSphereWildcardValue(bodyID_t, const std::string& name, const std::vector<float>&) {
+    assertInit("SetSphereWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+void DEMSolver::SetAnalWildcardValue(bodyID_t, const std::string& name, const std::vector<float>&) {
+    assertInit("SetAnalWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+std::vector<float> DEMSolver::GetOwnerWildcardValue(bodyID_t, const std::string& name, bodyID_t) {
+    assertInit("GetOwnerWildcardValue");
+    noSuchWildcard("owner", name);
+}
+std::vector<float> DEMSolver::GetAllOwnerWildcardValue(const std::string& name) {
+    assertInit("GetAllOwnerWildcardValue");
+    noSuchWildcard("owner", name);
+}
+std::vector<float> DEMSolver::GetFamilyOwnerWildcardValue(unsigned int, const std::string& name) {
+    assertInit("GetFamilyOwnerWildcardValue");
+    noSuchWildcard("owner", name);
+}
+std::vector<float> DEMSolver::GetTriWildcardValue(bodyID_t, const std::string& name, size_t) {
+    assertInit("GetTriWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+std::vector<float> DEMSolver::GetSphereWildcardValue(bodyID_t, const std::string& name, size_t) {
+    assertInit("GetSphereWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+std::vector<float> DEMSolver::GetAnalWildcardValue(bodyID_t, const std::string& name, size_t) {
+    assertInit("GetAnalWildcardValue");
+    noSuchWildcard("geometry", name);
+}
+
+// ---- persistent contacts ----
+void DEMSolver::markPersistent(int mode, unsigned int N1, unsigned int N2, bool mark) {
+    if (m_force_model != FORCE_MODEL::HERTZIAN)
+        fail("Persistent contacts need a force model with contact history (wildcards); the frictionless model has none.");
+    // every pair that is in the list now, plus the marked ones the list has dropped since
+    FullRows r = download_full_rows(ctx, false);
+    append_persistent(r, persistentKeys());
+    const auto fam = GetOwnerFamily(0, (bodyID_t)nOwnerBodies);
+    for (size_t i = 0; i < r.size(); i++) {
+        PersistentPair p;
+        p.geoA = r.a[i]; p.geoB = r.b[i]; p.type = r.t[i];
+        p.ownerA = geoOwner(r.a[i], r.t[i], false);
+        p.ownerB = geoOwner(r.b[i], r.t[i], true);
+        const unsigned int fa = fam[p.ownerA], fb = fam[p.ownerB];
+        bool hit = true;
+        if (mode == 1) hit = (fa == N1 || fb == N1);
+        else if (mode == 2) hit = (fa == N1 && fb == N1);
+        else if (mode == 3) hit = (fa == N1 && fb == N2) || (fa == N2 && fb == N1);
+        if (!hit) continue;
+        if (mark) m_persistent.insert(p);
+        else m_persistent.erase(p);
+    }
+}
+void DEMSolver::MarkFamilyPersistentContactEither(unsigned int N) { assertInit("MarkFamilyPersistentContactEither"); markPersistent(1, N, 0, true); }
+void DEMSolver::MarkFamilyPersistentContactBoth(unsigned int N) { assertInit("MarkFamilyPersistentContactBoth"); markPersistent(2, N, 0, true); }
+void DEMSolver::MarkFamilyPersistentContact(unsigned int N1, unsigned int N2) { assertInit("MarkFamilyPersistentContact"); markPersistent(3, N1, N2, true); }
+void DEMSolver::MarkPersistentContact() { assertInit("MarkPersistentContact"); markPersistent(0, 0, 0, true); }
+void DEMSolver::RemoveFamilyPersistentContactEither(unsigned int N) { assertInit("RemoveFamilyPersistentContactEither"); markPersistent(1, N, 0, false); }
+void DEMSolver::RemoveFamilyPersistentContactBoth(unsigned int N) { assertInit("RemoveFamilyPersistentContactBoth"); markPersistent(2, N, 0, false); }
+void DEMSolver::RemoveFamilyPersistentContact(unsigned int N1, unsigned int N2) { assertInit("RemoveFamilyPersistentContact"); markPersistent(3, N1, N2, false); }
+void DEMSolver::RemovePersistentContact() { assertInit("RemovePersistentContact"); markPersistent(0, 0, 0, false); }
+
+// ---- code-string "corrections" of the integrator (API.h:806-838 of the reference) ----
+namespace {
+[[noreturn]] void no_corrections(const char* who) {
+    fail(std::string(who) + ": a correction is C++ code the reference compiles into its integration kernel at run time; this "
+         "ahead-of-time compiled core has no run-time compilation. Prescribe the motion (SetFamilyPrescribedLinVel / "
+         "...AngVel / ...Position, expressions of t are supported) or add an acceleration (AddFamilyPrescribedAcc) instead.");
+}
+}  // namespace
+void DEMSolver::CorrectFamilyLinVel(unsigned int, const std::string&, const std::string&, const std::string&, const std::string&) {
+    no_corrections("CorrectFamilyLinVel");
+}
+void DEMSolver::CorrectFamilyAngVel(unsigned int, const std::string&, const std::string&, const std::string&, const std::string&) {
+    no_corrections("CorrectFamilyAngVel");
+}
+void DEMSolver::CorrectFamilyPosition(unsigned int, const std::string&, const std::string&, const std::string&, const std::string&) {
+    no_corrections("CorrectFamilyPosition");
+}
+void DEMSolver::CorrectFamilyQuaternion(unsigned int, const std::string&) { no_corrections("CorrectFamilyQuaternion"); }
+
+// ---- housekeeping ----
+size_t DEMSolver::GetHostMemUsageDynamic() const {
+    size_t b = m_owner_mass.size() * sizeof(float) + m_owner_moi.size() * sizeof(float3) +
+               (m_owner_type_mark.size() + m_sphere_owner.size() + m_tri_owner.size() + m_anal_owner.size() +
+                m_owner_first_sphere.size()) * sizeof(unsigned int) +
+               m_family_masks.size();
+    for (const auto& m : m_cached_meshes) b += m->m_vertices.size() * sizeof(float3) + m->m_face_v_indices.size() * sizeof(int3);
+    return b;
+}
+void DEMSolver::UpdateSimParams() {
+    // (APIPublic.cpp:2313-2326 of the reference: re-derive the margin / bin policy and push the parameters again)
+    assertInit("UpdateSimParams");
+    DemSimParams sp;
+    memcpy(&sp, m_sp_blob.data(), sizeof(sp));
+    const float g[3] = {G.x, G.y, G.z};
+    for (int k = 0; k < 3; k++) sp.G[k] = g[k];
+    sp.h = (float)m_ts_size;
+    sp.cd_update_freq = (uint32_t)m_cd_update_freq;
+    if (m_adaptive_update_freq) {  // keep what the tuner has settled on
+        DemStats st;
+        check(dem_get_stats(ctx, &st), "dem_get_stats");
+        if (st.cd_update_freq >= 1) sp.cd_update_freq = st.cd_update_freq;
+    }
+    sp.beta = m_expand_factor;
+    sp.approxMaxVel = m_approx_max_vel;
+    sp.expSafetyMulti = m_expand_safety_multi;
+    sp.expSafetyAdder = m_expand_base_vel;
+    sp.errOutVel = threshold_error_out_vel;
+    check(dem_set_params(ctx, &sp), "dem_set_params");
+    memcpy(m_sp_blob.data(), &sp, sizeof(sp));
+    check(dem_set_option(ctx, "update_freq_max", (double)m_max_update_freq), "SetCDMaxUpdateFreq");
+    check(dem_set_option(ctx, "adaptive_update_freq", m_adaptive_update_freq ? 1.0 : 0.0), "UseAdaptiveUpdateFreq");
+}
+void DEMSolver::SetAdaptiveTimeStepType(const std::string& type) {
+    if (verbosity >= WARNING)
+        std::cerr << "WARNING! SetAdaptiveTimeStepType is currently not implemented and has no effect, time step size is still fixed."
+                  << std::endl;
+    const std::string u = upper(type);
+    if (u != "NONE" && u != "MAX_VEL" && u != "INT_DIFF")
+        fail("Adaptive time step type " + type + " is unknown. Please select another via SetAdaptiveTimeStepType.");
+}
+
+// ---- inspectors confined to a region ----
+namespace {
+constexpr int KIND_CLUMP_VOLUME = 100;    // facade-side quantities (no device reduction behind them)
+constexpr int KIND_OWNER_MAX_ABSV = 101;  // "max_absv": every owner's |v|, not the spheres'
+}  // namespace
+DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity, const std::string& region_code)
+    : DEMInspector(sim, quantity) {
+    bool blank = true;
+    for (char c : region_code) blank = blank && isspace((unsigned char)c);
+    if (blank) return;
+    if (quantity == "max_absv") kind = KIND_OWNER_MAX_ABSV;
+    region = std::make_shared<ScalarExpression>(region_code, std::vector<std::string>{"X", "Y", "Z"});
+    if (region->IsConstant())
+        fail("One of your insepctors is set to query a specific region, but the region condition \"" + region_code +
+             "\" does not depend on X, Y or Z. It should be a condition on the position, e.g. \"return (X > 0) && (Z < 1);\".");
+}
+std::shared_ptr<DEMInspector> DEMSolver::CreateInspector(const std::string& quantity, const std::string& region) {
+    return std::make_shared<DEMInspector>(this, quantity, region);
+}
+double DEMSolver::ReduceInRegion(int kind, const ScalarExpression& region) const {
+    assertInit("inspector");
+    const bool clumps_only = (kind != KIND_OWNER_MAX_ABSV);
+    const uint32_t n = (uint32_t)(clumps_only ? nOwnerClumps : nOwnerBodies);
+    if (!n) return 0.0;
+    std::vector<double> pos(3 * (size_t)n);
+    std::vector<float> q(4 * (size_t)n), v(3 * (size_t)n), w(3 * (size_t)n);
+    check(dem_download_positions(ctx, 0, n, nullptr, pos.data()), "dem_download_positions");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), w.data(), nullptr, nullptr,
+                                   nullptr), "dem_download_owner_state");
+    auto inside = [&](float X, float Y, float Z) {
+        const double xyz[3] = {X, Y, Z};
+        return region.Eval(xyz) != 0.0;
+    };
+    const bool per_sphere = (kind == DEM_REDUCE_MAX_Z || kind == DEM_REDUCE_MIN_Z || kind == DEM_REDUCE_MAX_ABSV);
+    double acc = (kind == DEM_REDUCE_MIN_Z) ? DEME_HUGE_FLOAT
+                 : (kind == DEM_REDUCE_MAX_Z || kind == DEM_REDUCE_MAX_ABSV || kind == KIND_OWNER_MAX_ABSV) ? -DEME_HUGE_FLOAT : 0.0;
+    for (uint32_t i = 0; i < n; i++) {
+        const float3 vi = make_float3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
+        if (!per_sphere) {
+            // the owner's position decides (DEMOwnerQueryKernels.cu:42-48)
+            if (!inside((float)pos[3 * i], (float)pos[3 * i + 1], (float)pos[3 * i + 2])) continue;
+            if (kind == KIND_OWNER_MAX_ABSV) {
+                acc = std::max(acc, std::sqrt((double)vi.x * vi.x + (double)vi.y * vi.y + (double)vi.z * vi.z));
+            } else if (kind == DEM_REDUCE_TOTAL_MASS) {
+                acc += (float)m_owner_mass[i];
+            } else if (kind == KIND_CLUMP_VOLUME) {
+                acc += m_templates[m_owner_type_mark[i]]->volume;
+            } else {  // kinetic energy (AuxClasses.cpp:62-75)
+                const float3 I = m_owner_moi[i];
+                double ke = 0.5 * (double)m_owner_mass[i] * ((double)vi.x * vi.x + (double)vi.y * vi.y + (double)vi.z * vi.z);
+                ke += 0.5 * ((double)I.x * w[3 * i] * w[3 * i] + (double)I.y * w[3 * i + 1] * w[3 * i + 1] +
+                             (double)I.z * w[3 * i + 2] * w[3 * i + 2]);
+                acc += (float)ke;
+            }
+            continue;
+        }
+        // sphere quantities: the sphere's centre decides (DEMSphereQueryKernels.cu:41-46)
+        const auto& tp = m_templates[m_owner_type_mark[i]];
+        const float4 qi = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);
+        const float3 wl = make_float3(w[3 * i], w[3 * i + 1], w[3 * i + 2]);
+        for (unsigned int k = 0; k < tp->nComp; k++) {
+            const float3 off = Rotate(tp->relPos[k], qi);
+            const float X = (float)(pos[3 * i] + off.x), Y = (float)(pos[3 * i + 1] + off.y), Z = (float)(pos[3 * i + 2] + off.z);
+            if (!inside(X, Y, Z)) continue;
+            if (kind == DEM_REDUCE_MAX_Z) acc = std::max(acc, (double)(Z + tp->radii[k]));
+            else if (kind == DEM_REDUCE_MIN_Z) acc = std::min(acc, (double)(Z - tp->radii[k]));
+            else acc = std::max(acc, (double)length(Rotate(cross(wl, tp->relPos[k]), qi) + vi));  // AuxClasses.cpp:27-50
+        }
+    }
+    return acc;
 }
 
 }  // namespace deme

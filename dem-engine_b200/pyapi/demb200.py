@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
-    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_set_family_material", "dem_group_step_async", "dem_group_sync", "dem_group_gather",
+    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_set_family_material", "dem_group_step_async", "dem_group_sync", "dem_group_gather", "dem_add_owner_acc",
 ]
 
 

@@ -216,6 +216,10 @@ int dem_download_positions(DemCtx* ctx, uint32_t first, uint32_t n, float* xyz_f
 int dem_upload_owner_state(DemCtx* ctx, uint32_t first, uint32_t n, const float* pos_xyz_world,
                            const float* oriQ_wxyz, const float* vel_xyz, const float* omg_xyz,
                            const uint8_t* family);
+/* AddOwnerNextStepAcc / AddOwnerNextStepAngAcc (src/DEM/API.h:477-486, dT.cpp:3160-3174; DEMTracker::AddAcc / AddAngAcc):
+ * n consecutive owners get an extra acceleration (world frame) and / or angular acceleration (owner frame) for the NEXT
+ * step only, on top of what that step's contacts give.  Either pointer may be NULL. */
+int dem_add_owner_acc(DemCtx* ctx, uint32_t first, uint32_t n, const float* acc_xyz, const float* angacc_local_xyz);
 /* SetFamilyClumpMaterial / SetFamilyMeshMaterial (src/DEM/APIPublic.cpp:1597-1604, dT.cpp:2719-2738): the spheres
  * (meshes != 0: the facets) of every owner in `family` get `material`; contact history is kept. */
 int dem_set_family_material(DemCtx* ctx, uint32_t family, uint32_t material, int meshes);
