@@ -178,3 +178,17 @@ def test_wavefront_mesh_loading_and_transforms(built, tmp_path):
     Rv, Rf = np.array(R["v"]), np.array(R["f"])
     n1 = np.cross(Rv[Rf[:, 1]] - Rv[Rf[:, 0]], Rv[Rf[:, 2]] - Rv[Rf[:, 0]])
     assert np.allclose(n1, n0 * np.array([-1, 1, 1]))          # normals are reflected, not inverted
+
+
+def test_facade_host_side_pieces(built, tmp_path):
+    """Facade logic that never touches the device (region expressions of inspectors, the per-contact read-out container, the
+    vector-form setters and wildcard bookkeeping of a clump batch, the force-model handle, frame / quaternion helpers):
+    tests/host/facade_host_check.cpp asserts each against the behaviour the reference documents."""
+    exe = str(tmp_path / "facade_host_check")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I" + os.path.join(HOST, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "tests", "host", "facade_host_check.cpp"), "-o", exe,
+                    "-L" + os.path.join(ROOT, "dem-engine_b200"), "-ldeme_b200", "-ldemcore",
+                    "-Wl,-rpath," + os.path.join(ROOT, "dem-engine_b200")], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.split("\n")[:5] == ["ok regions", "ok contact_info", "ok clump_batch", "ok force_model", "ok helpers"]
