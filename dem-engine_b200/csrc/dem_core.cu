@@ -2067,15 +2067,18 @@ int dem_get_stats(DemCtx* ctx, DemStats* out) {
 
 int dem_reduce(DemCtx* ctx, int kind, double* out) {
     if (!ctx || !ctx->initialized || !out) return DEM_ERR_INVALID;
-    if (kind < DEM_REDUCE_MAX_ABSV || kind > DEM_REDUCE_TOTAL_MASS) return fail(ctx, DEM_ERR_INVALID, "unknown reduction");
+    if (kind < DEM_REDUCE_MAX_ABSV || kind > DEM_REDUCE_SPHERE_MAX_ABSV) return fail(ctx, DEM_ERR_INVALID, "unknown reduction");
     { int rcm = ensure_merged(ctx); if (rcm) return rcm; }
     CK(cudaSetDevice(ctx->device));
-    const double init = (kind == DEM_REDUCE_MIN_Z) ? 1e300 : ((kind == DEM_REDUCE_MAX_Z) ? -1e300 : 0.0);
+    const bool per_sphere = kind >= DEM_REDUCE_SPHERE_MAX_Z;
+    const double init = (kind == DEM_REDUCE_MIN_Z || kind == DEM_REDUCE_SPHERE_MIN_Z) ? 1e300
+                        : ((kind == DEM_REDUCE_MAX_Z || kind == DEM_REDUCE_SPHERE_MAX_Z) ? -1e300 : 0.0);
     CK(cudaMemcpyAsync(ctx->d_reduce, &init, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     DevParams P = make_params(ctx);
     P.nOwners = ctx->nClumpOwners;  // inspectors of the reference look at clumps only
     if (ctx->group_on) P.active = nullptr;  // rank 0 holds the merged state of all ranks
-    ctx->launches += launch_reduce(P, kind, ctx->d_reduce, ctx->stream);
+    ctx->launches += per_sphere ? launch_reduce_spheres(P, kind, ctx->d_reduce, ctx->stream)
+                                : launch_reduce(P, kind, ctx->d_reduce, ctx->stream);
     CK(cudaMemcpyAsync(out, ctx->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return DEM_OK;

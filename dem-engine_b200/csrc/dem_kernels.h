@@ -117,5 +117,6 @@ int launch_scan_lookback(const uint32_t* in, uint32_t* out, const uint32_t* n_pt
 int launch_zero_u32(uint32_t* p, size_t n, const uint32_t* flags, int num_sms, cudaStream_t s);
 int launch_reduce(const DevParams& P, int kind, double* d_out, cudaStream_t s);
 int launch_reduce_many(const DevParams& P, uint32_t mask, double* d_out, cudaStream_t s);
+int launch_reduce_spheres(const DevParams& P, int kind, double* d_out, cudaStream_t s);
 
 }  // namespace demb

@@ -1193,6 +1193,44 @@ __global__ void __launch_bounds__(256) k_reduce_many(const __grid_constant__ Dev
     }
 }
 
+// Sphere-level inspector quantities (AuxClasses.cpp:19-50, DEMSphereQueryKernels.cu:13-52 of the reference): its
+// clump_max_z / clump_min_z / clump_max_absv look at every SPHERE -- the top / bottom of the sphere, the velocity of its
+// centre v + omega x r -- not at the owner's centre.  One thread per sphere; *out holds the neutral element on entry.
+__global__ void __launch_bounds__(256) k_reduce_spheres(const __grid_constant__ DevParams P, int kind, double* out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool is_min = (kind == DEM_REDUCE_SPHERE_MIN_Z);
+    double v = is_min ? 1e300 : ((kind == DEM_REDUCE_SPHERE_MAX_ABSV) ? 0.0 : -1e300);
+    if (i < P.nSpheres) {
+        const uint2 s = P.sph[i];
+        if (!P.active || P.active[s.x] == 1 || P.active[s.x] >= 3) {
+            const OwnerState st = P.state[s.x];
+            const float4 comp = P.comp[s.y & 0xffffu];
+            const float3 rel = rotate(f3(comp.x, comp.y, comp.z), st.quat);
+            if (kind == DEM_REDUCE_SPHERE_MAX_ABSV) {
+                const float3 u = cross(f3(st.omg.x, st.omg.y, st.omg.z), rel) + f3(st.vel.x, st.vel.y, st.vel.z);
+                v = sqrtf(dot(u, u));
+            } else {
+                double X, Y, Z;
+                pos_decode(st.pos, P, X, Y, Z);
+                const float z = (float)(Z + (double)rel.z + (double)P.LBF[2]);
+                v = is_min ? z - comp.w : z + comp.w;
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const double t = __shfl_xor_sync(0xffffffffu, v, off);
+        v = is_min ? fmin(v, t) : fmax(v, t);
+    }
+    if ((threadIdx.x & 31) == 0) atomic_minmax_double(out, v, !is_min);
+}
+
+int launch_reduce_spheres(const DevParams& P, int kind, double* d_out, cudaStream_t s) {
+    if (P.nSpheres == 0) return 0;
+    k_reduce_spheres<<<(P.nSpheres + 255) / 256, 256, 0, s>>>(P, kind, d_out);
+    return 1;
+}
+
 int launch_reduce_many(const DevParams& P, uint32_t mask, double* d_out, cudaStream_t s) {
     const uint32_t n = P.nOwners;
     if (n == 0) return 0;

@@ -1448,9 +1448,11 @@ void DEMTracker::SetGeometryWildcardValues(const std::string& name, const std::v
 
 // ---- inspectors ----
 DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(sim) {
-    if (quantity == "clump_max_z") kind = DEM_REDUCE_MAX_Z;
-    else if (quantity == "clump_min_z") kind = DEM_REDUCE_MIN_Z;
-    else if (quantity == "clump_max_absv" || quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;
+    // (AuxClasses.cpp:88-164 of the reference: the first three look at every sphere, the others at the owners)
+    if (quantity == "clump_max_z") kind = DEM_REDUCE_SPHERE_MAX_Z;
+    else if (quantity == "clump_min_z") kind = DEM_REDUCE_SPHERE_MIN_Z;
+    else if (quantity == "clump_max_absv") kind = DEM_REDUCE_SPHERE_MAX_ABSV;
+    else if (quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;
     else if (quantity == "clump_kinetic_energy") kind = DEM_REDUCE_KINETIC_ENERGY;
     else if (quantity == "clump_mass") kind = DEM_REDUCE_TOTAL_MASS;
     else if (quantity == "clump_volume") kind = 100;  // KIND_CLUMP_VOLUME: summed on the host from the templates
@@ -1996,8 +1998,10 @@ void DEMSolver::setContactWildcard(int mode, unsigned int N1, unsigned int N2, c
         r.wc[4 * i + word] = val;
         changed++;
     }
-    if (changed)
-        check(dem_set_contacts(ctx, r.size(), r.a.data(), r.b.data(), r.t.data(), r.wc.data()), "dem_set_contacts");
+    if (!changed) return;
+    check(dem_set_contacts(ctx, r.size(), r.a.data(), r.b.data(), r.t.data(), r.wc.data()), "dem_set_contacts");
+    // the edited list is a history source only: rebuild now, so that contact queries made before the next step see a list
+    check(dem_rebuild_contacts(ctx), "dem_rebuild_contacts");
 }
 void DEMSolver::SetContactWildcardValue(const std::string& name, float val) {
     assertInit("SetContactWildcardValue");
@@ -2160,15 +2164,13 @@ void DEMSolver::SetAdaptiveTimeStepType(const std::string& type) {
 
 // ---- inspectors confined to a region ----
 namespace {
-constexpr int KIND_CLUMP_VOLUME = 100;    // facade-side quantities (no device reduction behind them)
-constexpr int KIND_OWNER_MAX_ABSV = 101;  // "max_absv": every owner's |v|, not the spheres'
+constexpr int KIND_CLUMP_VOLUME = 100;  // a facade-side quantity (no device reduction behind it)
 }  // namespace
 DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity, const std::string& region_code)
     : DEMInspector(sim, quantity) {
     bool blank = true;
     for (char c : region_code) blank = blank && isspace((unsigned char)c);
     if (blank) return;
-    if (quantity == "max_absv") kind = KIND_OWNER_MAX_ABSV;
     region = std::make_shared<ScalarExpression>(region_code, std::vector<std::string>{"X", "Y", "Z"});
     if (region->IsConstant())
         fail("One of your insepctors is set to query a specific region, but the region condition \"" + region_code +
@@ -2179,7 +2181,7 @@ std::shared_ptr<DEMInspector> DEMSolver::CreateInspector(const std::string& quan
 }
 double DEMSolver::ReduceInRegion(int kind, const ScalarExpression& region) const {
     assertInit("inspector");
-    const bool clumps_only = (kind != KIND_OWNER_MAX_ABSV);
+    const bool clumps_only = (kind != DEM_REDUCE_MAX_ABSV);  // "max_absv" looks at every owner
     const uint32_t n = (uint32_t)(clumps_only ? nOwnerClumps : nOwnerBodies);
     if (!n) return 0.0;
     std::vector<double> pos(3 * (size_t)n);
@@ -2191,15 +2193,14 @@ double DEMSolver::ReduceInRegion(int kind, const ScalarExpression& region) const
         const double xyz[3] = {X, Y, Z};
         return region.Eval(xyz) != 0.0;
     };
-    const bool per_sphere = (kind == DEM_REDUCE_MAX_Z || kind == DEM_REDUCE_MIN_Z || kind == DEM_REDUCE_MAX_ABSV);
-    double acc = (kind == DEM_REDUCE_MIN_Z) ? DEME_HUGE_FLOAT
-                 : (kind == DEM_REDUCE_MAX_Z || kind == DEM_REDUCE_MAX_ABSV || kind == KIND_OWNER_MAX_ABSV) ? -DEME_HUGE_FLOAT : 0.0;
+    const bool per_sphere = (kind == DEM_REDUCE_SPHERE_MAX_Z || kind == DEM_REDUCE_SPHERE_MIN_Z || kind == DEM_REDUCE_SPHERE_MAX_ABSV);
+    double acc = (kind == DEM_REDUCE_SPHERE_MIN_Z) ? DEME_HUGE_FLOAT : (kind == DEM_REDUCE_SPHERE_MAX_Z) ? -DEME_HUGE_FLOAT : 0.0;
     for (uint32_t i = 0; i < n; i++) {
         const float3 vi = make_float3(v[3 * i], v[3 * i + 1], v[3 * i + 2]);
         if (!per_sphere) {
             // the owner's position decides (DEMOwnerQueryKernels.cu:42-48)
             if (!inside((float)pos[3 * i], (float)pos[3 * i + 1], (float)pos[3 * i + 2])) continue;
-            if (kind == KIND_OWNER_MAX_ABSV) {
+            if (kind == DEM_REDUCE_MAX_ABSV) {
                 acc = std::max(acc, std::sqrt((double)vi.x * vi.x + (double)vi.y * vi.y + (double)vi.z * vi.z));
             } else if (kind == DEM_REDUCE_TOTAL_MASS) {
                 acc += (float)m_owner_mass[i];
@@ -2222,8 +2223,8 @@ double DEMSolver::ReduceInRegion(int kind, const ScalarExpression& region) const
             const float3 off = Rotate(tp->relPos[k], qi);
             const float X = (float)(pos[3 * i] + off.x), Y = (float)(pos[3 * i + 1] + off.y), Z = (float)(pos[3 * i + 2] + off.z);
             if (!inside(X, Y, Z)) continue;
-            if (kind == DEM_REDUCE_MAX_Z) acc = std::max(acc, (double)(Z + tp->radii[k]));
-            else if (kind == DEM_REDUCE_MIN_Z) acc = std::min(acc, (double)(Z - tp->radii[k]));
+            if (kind == DEM_REDUCE_SPHERE_MAX_Z) acc = std::max(acc, (double)(Z + tp->radii[k]));
+            else if (kind == DEM_REDUCE_SPHERE_MIN_Z) acc = std::min(acc, (double)(Z - tp->radii[k]));
             else acc = std::max(acc, (double)length(Rotate(cross(wl, tp->relPos[k]), qi) + vi));  // AuxClasses.cpp:27-50
         }
     }

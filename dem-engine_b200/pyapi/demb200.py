@@ -280,6 +280,12 @@ class Engine:
         n = next(len(a.reshape(-1, w)) for a, w in zip(arrs, (3, 4, 3, 3, 1)) if a is not None)
         self._ck(self.lib.dem_upload_owner_state(self.ctx, C.c_uint32(first), C.c_uint32(n), *[_p(a) for a in arrs]))
 
+    def add_owner_acc(self, first, acc=None, angacc_local=None):
+        """AddOwnerNextStepAcc / AddOwnerNextStepAngAcc: extra (angular) acceleration of consecutive owners, next step only."""
+        arrs = [None if a is None else np.ascontiguousarray(a, "f4").reshape(-1, 3) for a in (acc, angacc_local)]
+        n = next(len(a) for a in arrs if a is not None)
+        self._ck(self.lib.dem_add_owner_acc(self.ctx, C.c_uint32(first), C.c_uint32(n), *[_p(a) for a in arrs]))
+
     def contacts(self, with_force=False):
         n = C.c_uint64(0)
         self._ck(self.lib.dem_download_contacts(self.ctx, C.c_uint64(0), C.byref(n), None, None, None, None, None))

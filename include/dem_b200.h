@@ -235,7 +235,10 @@ int dem_get_stats(DemCtx* ctx, DemStats* out);
 
 /* reductions over clump owners (DEMInspector built-ins, AuxClasses.cpp:88-164) */
 enum { DEM_REDUCE_MAX_ABSV = 0, DEM_REDUCE_MAX_Z = 1, DEM_REDUCE_MIN_Z = 2, DEM_REDUCE_KINETIC_ENERGY = 3,
-       DEM_REDUCE_TOTAL_MASS = 4 };
+       DEM_REDUCE_TOTAL_MASS = 4,
+       /* (dem_reduce only) the reference's sphere-level forms, AuxClasses.cpp:19-50: top / bottom of every sphere (centre
+        * z +- radius) and the speed of every sphere centre (v + omega x r), where 0..2 look at the owners' centres */
+       DEM_REDUCE_SPHERE_MAX_Z = 5, DEM_REDUCE_SPHERE_MIN_Z = 6, DEM_REDUCE_SPHERE_MAX_ABSV = 7 };
 int dem_reduce(DemCtx* ctx, int kind, double* out);
 /* Several reductions in one pass over the owners and one read-back: bit k of kind_mask selects DEM_REDUCE_<k>;
  * out[k] receives it (entries of unselected kinds are left untouched). What a caller polling several inspectors per

@@ -71,3 +71,16 @@ def test_reference_testpack_incline_classification(built, tmp_path):
             # it slid back down: g (sin a - mu cos a) over most of a second
             assert float(v) > 1.0
     assert "WARNING!!! I do not know what happened" not in out
+
+
+def test_facade_contact_queries_demo(built):
+    """dem-engine_b200/host/demo/DEMdemo_ContactQueries.cpp: a settled 4 x 4 x 2 block of spheres plus one falling sphere,
+    checked against what can be said exactly -- GetContactDetailedInfo (16 floor contacts with normal (0, 0, -1) carrying
+    the block's weight, one entry per potential pair at a negative threshold), SetFamilyContactWildcardValue reaching the 16
+    inter-layer contacts only, persistent marks keeping dropped pairs reported, sphere-level and region inspectors against
+    tracker read-outs, AddAcc acting in the next step only, UpdateSimParams.  (Kept last in the GPU suite.)"""
+    exe = os.path.join(ROOT, "dem-engine_b200", "host", "demo", "DEMdemo_ContactQueries")
+    r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    print(r.stdout)
+    assert "FAIL" not in r.stdout and "0 checks failed" in r.stdout and r.returncode == 0, r.stdout[-1500:]
+    assert r.stdout.count("PASS") >= 24
