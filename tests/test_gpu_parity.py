@@ -8,7 +8,8 @@ identical forces) is compared exactly; floating-point state is compared to the s
     change of the initial velocities moves the oracle's own result by 1e-4 m after 3000 steps), so trajectories are
     compared at checkpoints against the oracle's measured round-off sensitivity: the device may differ from the oracle
     by at most 10x what the oracle differs from itself when its velocities are perturbed by 1e-6 relative (the size of
-    the per-step device/oracle difference established by the single-step test), plus 1e-7 m.
+    the per-step device/oracle difference established by the single-step test), plus 1e-7 m.  The first checkpoint
+    (step 200, before collisions have amplified anything) is held to FIXED bounds instead: 1e-7 m and 1e-3 m/s.
 """
 import numpy as np
 import pytest
@@ -16,6 +17,11 @@ import pytest
 from pyapi import demb200, scenes
 
 pytestmark = pytest.mark.gpu
+
+# every trajectory comparison starts with a checkpoint held to fixed absolute bounds
+EARLY_STEP = 200
+EARLY_BOUND_X = 1e-7   # m
+EARLY_BOUND_V = 1e-3   # m/s (velocities are 1 .. 3 m/s)
 
 
 def _oracle():
@@ -40,7 +46,7 @@ def _vel(w, n):
     return np.stack([w.vX, w.vY, w.vZ], 1)[:n]
 
 
-def _check_trajectory(eng, f, w, checkpoints, label):
+def _check_trajectory(eng, f, w, checkpoints, label, early=True):
     """Step device and oracle side by side; at every checkpoint the device/oracle distance must stay within 10x the
     oracle's own round-off sensitivity (see module docstring)."""
     wp = w.copy()
@@ -49,6 +55,9 @@ def _check_trajectory(eng, f, w, checkpoints, label):
         a[:] = (a.astype("f8") * (1.0 + 1e-6)).astype("f4")
     nC = f.nClumps
     done = 0
+    checkpoints = list(checkpoints)
+    if early and checkpoints[0] > EARLY_STEP:
+        checkpoints.insert(0, EARLY_STEP)
     for cp in checkpoints:
         eng.step(cp - done)
         w.step(cp - done, cd_every=f.cd_update_freq)
@@ -61,6 +70,10 @@ def _check_trajectory(eng, f, w, checkpoints, label):
         err_v = np.abs(eng.owner_state()["vel"][:nC] - _vel(w, nC)).max()
         print("%s step %d: |dx| %.2e (sensitivity %.2e)  |dv| %.2e (sensitivity %.2e)" % (label, cp, err_x, sens_x, err_v, sens_v))
         assert err_x <= 10 * sens_x + 1e-7, (cp, err_x, sens_x)
+        if cp <= EARLY_STEP:
+            # before collisions have amplified anything the bound is FIXED, not calibrated: the oracle's own sensitivity is
+            # 1e-9 .. 6e-9 m and up to 4e-5 m/s at this point in every scene (measured on the CPU); grains are 2 .. 10 mm
+            assert err_x <= EARLY_BOUND_X and err_v <= EARLY_BOUND_V, (cp, err_x, err_v)
         assert err_v <= 10 * sens_v + 1e-5 * max(1.0, np.abs(_vel(w, nC)).max()), (cp, err_v, sens_v)
 
 
@@ -451,7 +464,7 @@ def test_capacity_overflow_grows_list(built):
     eng = demb200.Engine(0)
     eng.load_flat(f, contact_capacity=16)
     w = po.world_from_flat(f)
-    _check_trajectory(eng, f, w, [1000, 2000, 3000], "overflow")
+    _check_trajectory(eng, f, w, [1000, 2000, 3000], "overflow", early=False)
     s = eng.stats()
     assert s.overflow > 0 and s.contact_capacity > 16
     eng.close()
