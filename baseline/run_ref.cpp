@@ -29,6 +29,11 @@
 #include <string>
 #include <vector>
 
+// which engine this binary was linked with (the facade's Makefile passes -DRUN_IMPL_NAME=...)
+#ifndef RUN_IMPL_NAME
+    #define RUN_IMPL_NAME "DEME (unmodified reference)"
+#endif
+
 using namespace deme;
 
 struct SceneFile {
@@ -120,7 +125,7 @@ int main(int argc, char** argv) {
             const auto t0 = std::chrono::steady_clock::now();
             sim.DoDynamicsThenSync((double)steps * (double)s.h);
             const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            printf("{\"impl\": \"DEME (unmodified reference)\", \"n_gpus\": %d, \"clumps\": %u, \"steps\": %ld, \"warmup\": %ld, "
+            printf("{\"impl\": \"" RUN_IMPL_NAME "\", \"n_gpus\": %d, \"clumps\": %u, \"steps\": %ld, \"warmup\": %ld, "
                    "\"wall_s\": %.6f, \"steps_per_s\": %.3f, \"init_s\": %.2f, \"n_contacts\": %zu, \"update_freq\": %.2f, "
                    "\"cd_update_freq_setting\": %d}\n",
                    ngpu, s.n, steps, warm, wall, (double)steps / wall, init_s, sim.GetNumContacts(), sim.GetUpdateFreq(), freq);
@@ -188,7 +193,7 @@ int main(int argc, char** argv) {
                 fwrite(W.data(), sizeof(float3), s.n, out);
             }
             fclose(out);
-            printf("{\"impl\": \"DEME (unmodified reference)\", \"mode\": \"parity\", \"clumps\": %u, \"checkpoints\": %d, "
+            printf("{\"impl\": \"" RUN_IMPL_NAME "\", \"mode\": \"parity\", \"clumps\": %u, \"checkpoints\": %d, "
                    "\"steps_per_checkpoint\": %ld, \"n_contacts\": %zu}\n", s.n, ncp, per, sim.GetNumContacts());
         } else {
             return 2;
