@@ -39,6 +39,22 @@ def _scene(kind):
         v, fc = scenes.box_mesh((hi[0] - lo[0]) * 1.6, (hi[1] - lo[1]) * 1.6, (hi[2] - lo[2]) * 2.2, n=3, inward=True)
         sc.add_mesh(v, fc, mat=0, mass=1.0, moi=(1, 1, 1), pos=tuple((lo + hi) / 2), quat=(0.9950042, 0.0998334, 0, 0), family=10)
         sc.prescribed[10] = dict(linvel=(0.0, 0.0, 0.0), angvel=(0.0, 0.0, 2.0))
+    elif kind == "drum":
+        # BASELINE configs[3] at oracle size: polydisperse clump templates in a rotating drum of triangles
+        sc = scenes.config4_drum(1000, 1500, omega=6.0, init_vel=(0.2, 0.0, -1.0), cd_update_freq=10, spacing=2.7)
+    elif kind == "families":
+        # fixed and prescribed families, a disabled family pair, an extra contact margin
+        sc = scenes.config2_clumps(5, 5, 4, cd_update_freq=5, spacing=2.7, init_vel=(0.2, 0.1, -2.0))
+        fam = np.zeros(len(sc.clump_type), "u1")
+        fam[::7] = 3
+        fam[1::7] = 5
+        sc.clump_family = fam
+        sc.fixed_families.append(3)
+        sc.prescribed[5] = dict(linvel=(0.1, None, -0.5), dictate=True)
+        sc.disabled_pairs.append((3, 5))
+    elif kind in ("forward_euler", "centered_difference"):
+        sc = scenes.config2_clumps(4, 4, 3, cd_update_freq=5, spacing=2.7, init_vel=(0.3, 0.1, -2.0))
+        sc.integrator = 0 if kind == "forward_euler" else 1  # DEM_FORWARD_EULER / DEM_CENTERED_DIFFERENCE
     else:
         raise KeyError(kind)
     return sc
@@ -55,7 +71,8 @@ def _assert_same_state(a, b):
 
 
 @needs_ref
-@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder", "mesh_tray"])
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder", "mesh_tray", "drum",
+                                  "families", "forward_euler", "centered_difference"])
 def test_step_bit_exact_vs_reference_kernels(built, kind):
     f = scenes.flatten(_scene(kind))
     a = pyoracle.world_from_flat(f)
@@ -165,7 +182,8 @@ def test_pair_acceptance_matches_calcContactPoint(built):
     assert len(ss) > 0 and ss == hits
 
 
-GOLDEN_CASES = ["clumps_full", "spheres_frictionless", "mesh_tray"]
+GOLDEN_CASES = ["clumps_full", "spheres_frictionless", "mesh_tray", "clumps_roll", "cylinder", "drum", "families",
+                "forward_euler"]
 
 
 @pytest.mark.parametrize("kind", GOLDEN_CASES)
@@ -181,6 +199,11 @@ def test_oracle_reproduces_golden_vectors(built, kind):
     assert w.nContacts == int(g["nContacts"])
     assert np.array_equal(w.idGeometryA[: w.nContacts], g["idGeometryA"])
     assert np.array_equal(w.idGeometryB[: w.nContacts], g["idGeometryB"])
+    # the early snapshot (what tests/test_gpu_parity.py holds the CUDA path against)
+    we = pyoracle.world_from_flat(f)
+    we.step(int(g["early_nsteps"]), cd_every=f.cd_update_freq)
+    assert np.array_equal(we.positions_f64()[: f.nClumps], g["early_pos"])
+    assert np.array_equal(np.stack([we.vX, we.vY, we.vZ], 1)[: f.nClumps].view("u4"), g["early_vel"].view("u4"))
 
 
 def test_figure_out_nv_matches_product(built):
