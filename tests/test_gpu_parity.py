@@ -77,36 +77,6 @@ def _check_trajectory(eng, f, w, checkpoints, label, early=True):
         assert err_v <= 10 * sens_v + 1e-5 * max(1.0, np.abs(_vel(w, nC)).max()), (cp, err_v, sens_v)
 
 
-def _golden_cases():
-    from test_oracle_vs_ref import GOLDEN_CASES
-    return GOLDEN_CASES
-
-
-@pytest.mark.parametrize("kind", _golden_cases())
-def test_early_state_matches_golden_fixture(built, kind):
-    """The CUDA path against the COMMITTED golden vectors (tests/golden/golden_*.npz, dumped from the reference's own kernel
-    text by tests/golden/make_golden.py; the oracle reproduces them bit for bit on the CPU side): state after 200 steps,
-    before collisions have amplified round-off, within the fixed bounds 1e-7 m / 1e-3 m/s.  No oracle call on this path."""
-    import os
-    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_%s.npz" % kind))
-    f = scenes.flatten(_mk(kind))
-    eng = demb200.Engine(0)
-    eng.load_flat(f)
-    eng.step(int(g["early_nsteps"]))
-    nC = f.nClumps
-    err_x = np.abs(eng.positions()[:nC] - g["early_pos"]).max()
-    st = eng.owner_state()
-    err_v = np.abs(st["vel"][:nC] - g["early_vel"]).max()
-    # orientation: compare as rotations (q and -q are the same orientation)
-    q, qg = st["oriQ"][:nC].astype("f8"), g["early_quat"].astype("f8")
-    q /= np.linalg.norm(q, axis=1, keepdims=True)
-    qg /= np.linalg.norm(qg, axis=1, keepdims=True)
-    err_q = (1.0 - np.abs((q * qg).sum(1))).max()
-    print("%s: after %d steps |dx| %.2e m, |dv| %.2e m/s, 1 - |q.q_golden| %.2e" % (kind, int(g["early_nsteps"]), err_x, err_v, err_q))
-    assert err_x <= EARLY_BOUND_X and err_v <= EARLY_BOUND_V and err_q <= 1e-6, (err_x, err_v, err_q)
-    eng.close()
-
-
 @pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "spheres_frictionless", "cylinder", "mesh_tray"])
 def test_trajectory_matches_oracle(built, kind):
     po = _oracle()
