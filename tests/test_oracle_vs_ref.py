@@ -306,3 +306,62 @@ def test_facet_candidates_against_reference_triangle_broad_phase(built, bin_mult
         n_ref += len(theirs)
     assert n_ref > 10
     print("grazing contacts the reference's broad phase misses at this bin size:", n_grazing)
+
+
+def _random_scene(seed):
+    """A small scene drawn from a seed: mixed clump templates (1 to 5 spheres of random size and offset), two materials of random
+    stiffness / restitution / friction / rolling resistance, random orientations, velocities and spins, a random integrator,
+    a random bounding mode plus an inclined plane, random step size and list lifetime."""
+    rng = np.random.RandomState(seed)
+    s = scenes.Scene()
+    mats = [s.load_material(E=float(10 ** rng.uniform(7, 9)), nu=float(rng.uniform(0.2, 0.4)), CoR=float(rng.uniform(0.2, 0.9)),
+                            mu=float(rng.uniform(0.0, 0.8)), Crr=float(rng.choice([0.0, 0.0, rng.uniform(0.01, 0.1)])))
+            for _ in range(2)]
+    scale = 0.004
+    types = []
+    for _ in range(3):
+        ncomp = int(rng.randint(1, 6))
+        radii = rng.uniform(0.5, 1.0, ncomp) * scale
+        rel = rng.uniform(-0.6, 0.6, (ncomp, 3)) * scale if ncomp > 1 else np.zeros((1, 3))
+        mass = float(2.6e3 * 4.19 * scale ** 3 * ncomp * rng.uniform(0.5, 1.0))
+        moi = mass * scale ** 2 * rng.uniform(0.3, 0.6, 3)
+        types.append(s.load_clump_type(mass, moi, radii, rel, [mats[int(rng.randint(2))] for _ in range(ncomp)]))
+    n_side = int(rng.randint(3, 5))
+    g = np.stack(np.meshgrid(*[np.arange(n_side)] * 3, indexing="ij"), -1).reshape(-1, 3)
+    sep = 3.4 * scale
+    pts = (g - (n_side - 1) / 2.0) * sep + rng.uniform(-0.1, 0.1, g.shape) * scale
+    half = n_side * sep / 2 + 2.5 * scale
+    s.box = (2 * half, 2 * half, 2 * half * 1.3)
+    s.bounding, s.bounding_mat = str(rng.choice(["top_open", "all", "only_bottom"])), mats[0]
+    n = len(pts)
+    s.add_clumps(rng.randint(0, 3, n).astype("i4") + types[0], pts, quat=scenes.random_unit_quats(n, seed + 17),
+                 vel=np.asarray(rng.uniform(-1, 1, (n, 3)) + np.array([0, 0, -1.5]), "f4"),
+                 omg=np.asarray(rng.uniform(-30, 30, (n, 3)), "f4"))
+    nrm = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 1.0])
+    s.add_plane((0.0, 0.0, -half * 0.9), nrm, mats[1])
+    s.h = float(rng.choice([5e-6, 1e-5]))
+    s.G = (0.0, 0.0, -9.81)
+    s.integrator = int(rng.randint(0, 3))
+    s.force_model = 0 if rng.rand() < 0.75 else 1  # DEM_HERTZIAN / DEM_HERTZIAN_FRICTIONLESS
+    s.cd_update_freq = int(rng.choice([1, 3, 5, 10]))
+    return s
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", list(range(100, 124)))
+def test_random_scenes_bit_exact_vs_reference_kernels(built, seed):
+    """The oracle against the reference's kernel text on scenes nobody tuned: 24 seeds, 6000 steps each (compared every 1500), every owner
+    state word, contact count, history word, force and contact point identical."""
+    f = scenes.flatten(_random_scene(seed))
+    a = pyoracle.world_from_flat(f)
+    b = a.copy()
+    touched = False
+    for _ in range(4):
+        a.step(1500, cd_every=f.cd_update_freq)
+        b.step(1500, cd_every=f.cd_update_freq, use_ref=True)
+        touched = touched or (a.nContacts > 0 and np.abs(a.contactForces[: 3 * a.nContacts]).max() > 0)
+        _assert_same_state(a, b)
+    assert touched, "nothing collided: the scene tests nothing"
+    n = a.nContacts
+    for name in ("contactForces", "contactTorque_convToForce", "contactPointGeometryA", "contactPointGeometryB"):
+        assert np.array_equal(getattr(a, name)[: 3 * n].view("u4"), getattr(b, name)[: 3 * n].view("u4")), name
