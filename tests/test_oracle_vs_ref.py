@@ -353,7 +353,7 @@ def test_random_scenes_bit_exact_vs_reference_kernels(built, seed):
     """The oracle against the reference's kernel text on scenes nobody tuned: 24 seeds, 6000 steps each (compared every 1500), every owner
     state word, contact count, history word, force and contact point identical."""
     f = scenes.flatten(_random_scene(seed))
-    a = pyoracle.world_from_flat(f)
+    a = pyoracle.world_from_flat(f, contact_capacity=64 * f.nSpheres + 1024)  # (a pile-up in a corner lists many pairs)
     b = a.copy()
     touched = False
     for _ in range(4):
