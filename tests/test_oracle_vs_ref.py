@@ -4,6 +4,7 @@
 There are no golden vectors or known-answer tests in the reference tree; what pins the oracle is
 (i) the reference's kernels executed here through the host shim and (ii) tests/golden/*.npz dumped from that.
 """
+import math
 import os
 
 import numpy as np
@@ -339,6 +340,14 @@ def _random_scene(seed):
                  omg=np.asarray(rng.uniform(-30, 30, (n, 3)), "f4"))
     nrm = np.array([rng.uniform(-0.3, 0.3), rng.uniform(-0.3, 0.3), 1.0])
     s.add_plane((0.0, 0.0, -half * 0.9), nrm, mats[1])
+    if rng.rand() < 0.4:
+        # every third scene or so: the grains sit in a tilted, spinning box of triangles instead of the analytical walls
+        s.bounding = "none"
+        v, fc = scenes.box_mesh(2 * half * 0.95, 2 * half * 0.95, 2 * half * 1.2, n=int(rng.randint(2, 5)), inward=True)
+        tilt = float(rng.uniform(-0.3, 0.3))
+        s.add_mesh(v, fc, mat=mats[0], mass=1.0, moi=(1, 1, 1), pos=(0.0, 0.0, 0.0),
+                   quat=(math.cos(tilt / 2), math.sin(tilt / 2), 0.0, 0.0), family=10)
+        s.prescribed[10] = dict(linvel=(0.0, 0.0, 0.0), angvel=(0.0, 0.0, float(rng.uniform(-4, 4))))
     s.h = float(rng.choice([5e-6, 1e-5]))
     s.G = (0.0, 0.0, -9.81)
     s.integrator = int(rng.randint(0, 3))
