@@ -100,7 +100,38 @@ class DEMClumpTemplate {
     void SetMaterial(const std::shared_ptr<DEMMaterial>& input) { materials.assign(nComp, input); }
     void SetVolume(float vol) { volume = vol; }
     void Scale(float s);
+    /// The component positions were given in a frame that is not the centroid / principal frame: report where that
+    /// frame sits (Structs.h:650-665 of the reference) and relPos is re-expressed in it ...
+    void InformCentroidPrincipal(float3 center, float4 prin_Q) {
+        for (auto& pos : relPos) applyFrameTransformGlobalToLocal(pos, center, prin_Q);
+    }
+    void InformCentroidPrincipal(const std::vector<float>& center, const std::vector<float>& prin_Q) {
+        InformCentroidPrincipal(vec3_arg(center, "InformCentroidPrincipal"), vec4_arg(prin_Q, "InformCentroidPrincipal"));
+    }
+    /// ... or rotate, then move the components (:667-679)
+    void Move(float3 vec, float4 rot_Q) {
+        for (auto& pos : relPos) applyFrameTransformLocalToGlobal(pos, vec, rot_Q);
+    }
+    void Move(const std::vector<float>& vec, const std::vector<float>& rot_Q) { Move(vec3_arg(vec, "Move"), vec4_arg(rot_Q, "Move")); }
     void AssignName(const std::string& some_name) { m_name = some_name; }
+
+  private:
+    static float3 vec3_arg(const std::vector<float>& v, const char* who) {
+        if (v.size() != 3) throw std::runtime_error(std::string(who) + ": a 3-element vector is expected");
+        return make_float3(v[0], v[1], v[2]);
+    }
+    static float4 vec4_arg(const std::vector<float>& v, const char* who) {
+        if (v.size() != 4) throw std::runtime_error(std::string(who) + ": a 4-element vector (x, y, z, w) is expected");
+        return make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+
+/// One facet, by value (src/DEM/Structs.h:550-558)
+class DEMTriangle {
+  public:
+    DEMTriangle(float3 pnt1, float3 pnt2, float3 pnt3) : p1(pnt1), p2(pnt2), p3(pnt3) {}
+    DEMTriangle() {}
+    float3 p1, p2, p3;
 };
 
 class DEMClumpBatch : public DEMInitializer {
@@ -247,6 +278,9 @@ class DEMMeshConnected : public DEMInitializer {
     std::vector<int3> m_face_v_indices;
     std::vector<int3> m_face_n_indices;
     std::vector<int3> m_face_uv_indices;
+    std::vector<float3> m_colors;
+    std::vector<int3> m_face_col_indices;
+    bool use_mesh_normals = false;
     std::vector<std::shared_ptr<DEMMaterial>> materials;
     bool isMaterialSet = false;
     unsigned int family_code = RESERVED_FAMILY_NUM;
@@ -273,7 +307,32 @@ class DEMMeshConnected : public DEMInitializer {
     size_t GetNumTriangles() const { return nTri; }
     size_t GetNumNodes() const { return m_vertices.size(); }
     std::vector<float3>& GetCoordsVertices() { return m_vertices; }
+    std::vector<std::vector<float>> GetCoordsVerticesAsVectorOfVectors();
+    std::vector<float3>& GetCoordsNormals() { return m_normals; }
+    std::vector<float3>& GetCoordsUV() { return m_UV; }
+    std::vector<float3>& GetCoordsColors() { return m_colors; }
     std::vector<int3>& GetIndicesVertexes() { return m_face_v_indices; }
+    std::vector<std::vector<int>> GetIndicesVertexesAsVectorOfVectors();
+    std::vector<int3>& GetIndicesNormals() { return m_face_n_indices; }
+    std::vector<int3>& GetIndicesUV() { return m_face_uv_indices; }
+    std::vector<int3>& GetIndicesColors() { return m_face_col_indices; }
+    /// the facet normals always come from the winding of the nodes here (as in the reference's contact kernels); the flag
+    /// is kept for scripts that set it
+    void UseNormals(bool use = true) { use_mesh_normals = use; }
+    DEMTriangle GetTriangle(size_t index) const {
+        const int3 f = m_face_v_indices.at(index);
+        return DEMTriangle(m_vertices[f.x], m_vertices[f.y], m_vertices[f.z]);
+    }
+    /// All meshes as ONE Wavefront object: vertices, normals where a mesh has them, faces (src/DEM/MeshUtils.cpp:137-184)
+    static void WriteWavefront(const std::string& filename, std::vector<DEMMeshConnected>& meshes);
+    /// One mesh holding the nodes, normals, facets and materials of all (the reference declares this without defining it)
+    static DEMMeshConnected Merge(std::vector<DEMMeshConnected>& meshes);
+    // per-facet wildcards exist only for custom force models: kept, and refused at Initialize() like a batch's
+    std::unordered_map<std::string, std::vector<float>> geo_wildcards;
+    void ClearWildcards() { geo_wildcards.clear(); }
+    void SetGeometryWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards);
+    void AddGeometryWildcard(const std::string& name, const std::vector<float>& vals);
+    void AddGeometryWildcard(const std::string& name, float val) { AddGeometryWildcard(name, std::vector<float>(nTri, val)); }
     void Clear();
     void SetMass(float m) { mass = m; }
     void SetMOI(float3 moi) { MOI = moi; }
@@ -449,11 +508,17 @@ class DEMInspector {
     DEMInspector(DEMSolver* sim, const std::string& quantity);
     DEMInspector(DEMSolver* sim, const std::string& quantity, const std::string& region);
     float GetValue();
+    /// The un-reduced form: one value per owner for the quantity "absv" (every owner's speed), in owner order.  The
+    /// pointer stays valid until the next call.
+    float* GetValues();
+    /// Inspection code is C++ text the reference compiles into its query kernel: not available here
+    void SetInspectionCode(const std::string& code);
 
   private:
     DEMSolver* sys;
     int kind;
     std::shared_ptr<ScalarExpression> region;
+    std::vector<float> m_values;
 };
 
 /// The force model handle returned by Use*Model / DefineContactForceModel (src/DEM/AuxClasses.h:424-520).  The two

@@ -534,9 +534,90 @@ void DEMMeshConnected::SetGeometry(const std::vector<float3>& vertices, const st
             fail("SetGeometry: a facet refers to a vertex that does not exist.");
     nTri = faces.size();
 }
+std::vector<std::vector<float>> DEMMeshConnected::GetCoordsVerticesAsVectorOfVectors() {
+    std::vector<std::vector<float>> out;
+    out.reserve(m_vertices.size());
+    for (const float3& v : m_vertices) out.push_back({v.x, v.y, v.z});
+    return out;
+}
+std::vector<std::vector<int>> DEMMeshConnected::GetIndicesVertexesAsVectorOfVectors() {
+    std::vector<std::vector<int>> out;
+    out.reserve(m_face_v_indices.size());
+    for (const int3& f : m_face_v_indices) out.push_back({f.x, f.y, f.z});
+    return out;
+}
+void DEMMeshConnected::WriteWavefront(const std::string& filename, std::vector<DEMMeshConnected>& meshes) {
+    std::ofstream mf(filename);
+    if (!mf) fail("WriteWavefront: " + filename + " cannot be opened for writing.");
+    // Wavefront indices count from 1 and run through the whole file: first all nodes, then all normals, then the faces
+    std::vector<size_t> v_base, n_base;
+    size_t nv = 1, nn = 1;
+    for (const auto& m : meshes) {
+        v_base.push_back(nv);
+        nv += m.m_vertices.size();
+        for (const float3& v : m.m_vertices) mf << "v " << v.x << " " << v.y << " " << v.z << "\n";
+    }
+    for (const auto& m : meshes) {
+        n_base.push_back(nn);
+        nn += m.m_normals.size();
+        for (const float3& v : m.m_normals) mf << "vn " << v.x << " " << v.y << " " << v.z << "\n";
+    }
+    for (size_t k = 0; k < meshes.size(); k++) {
+        const auto& m = meshes[k];
+        const bool with_normals = !m.m_normals.empty() && m.m_face_n_indices.size() == m.m_face_v_indices.size();
+        for (size_t j = 0; j < m.m_face_v_indices.size(); j++) {
+            const int3 f = m.m_face_v_indices[j];
+            if (with_normals) {
+                const int3 g = m.m_face_n_indices[j];
+                mf << "f " << f.x + v_base[k] << "//" << g.x + n_base[k] << " " << f.y + v_base[k] << "//" << g.y + n_base[k]
+                   << " " << f.z + v_base[k] << "//" << g.z + n_base[k] << "\n";
+            } else {
+                mf << "f " << f.x + v_base[k] << " " << f.y + v_base[k] << " " << f.z + v_base[k] << "\n";
+            }
+        }
+    }
+}
+DEMMeshConnected DEMMeshConnected::Merge(std::vector<DEMMeshConnected>& meshes) {
+    DEMMeshConnected out;
+    bool all_have_materials = !meshes.empty();
+    for (const auto& m : meshes) {
+        const int vb = (int)out.m_vertices.size(), nb = (int)out.m_normals.size(), ub = (int)out.m_UV.size();
+        out.m_vertices.insert(out.m_vertices.end(), m.m_vertices.begin(), m.m_vertices.end());
+        out.m_normals.insert(out.m_normals.end(), m.m_normals.begin(), m.m_normals.end());
+        out.m_UV.insert(out.m_UV.end(), m.m_UV.begin(), m.m_UV.end());
+        for (const int3& f : m.m_face_v_indices) out.m_face_v_indices.push_back(make_int3(f.x + vb, f.y + vb, f.z + vb));
+        for (const int3& f : m.m_face_n_indices) out.m_face_n_indices.push_back(make_int3(f.x + nb, f.y + nb, f.z + nb));
+        for (const int3& f : m.m_face_uv_indices) out.m_face_uv_indices.push_back(make_int3(f.x + ub, f.y + ub, f.z + ub));
+        all_have_materials = all_have_materials && m.isMaterialSet && m.materials.size() == m.nTri;
+    }
+    out.nTri = out.m_face_v_indices.size();
+    if (out.m_face_n_indices.size() != out.nTri) { out.m_normals.clear(); out.m_face_n_indices.clear(); }  // (only some had normals)
+    if (out.m_face_uv_indices.size() != out.nTri) { out.m_UV.clear(); out.m_face_uv_indices.clear(); }
+    if (all_have_materials) {
+        for (const auto& m : meshes) out.materials.insert(out.materials.end(), m.materials.begin(), m.materials.end());
+        out.isMaterialSet = true;
+    }
+    return out;
+}
+void DEMMeshConnected::SetGeometryWildcards(const std::unordered_map<std::string, std::vector<float>>& wildcards) {
+    for (const auto& kv : wildcards)
+        if (kv.second.size() != nTri)
+            fail("Input gemometry wildcard arrays in a SetGeometryWildcards call must all have the same size as the number of "
+                 "triangles in this mesh.\nHere, the input array has length " + std::to_string(kv.second.size()) +
+                 " but this mesh has " + std::to_string(nTri) + " triangles.");
+    geo_wildcards = wildcards;
+}
+void DEMMeshConnected::AddGeometryWildcard(const std::string& name, const std::vector<float>& vals) {
+    if (vals.size() != nTri)
+        fail("Input gemometry wildcard array in a AddGeometryWildcard call must have the same size as the number of triangles "
+             "in this mesh.\nHere, the input array has length " + std::to_string(vals.size()) + " but this mesh has " +
+             std::to_string(nTri) + " triangles.");
+    geo_wildcards[name] = vals;
+}
 void DEMMeshConnected::Clear() {
-    m_vertices.clear(); m_normals.clear(); m_UV.clear();
-    m_face_v_indices.clear(); m_face_n_indices.clear(); m_face_uv_indices.clear();
+    m_vertices.clear(); m_normals.clear(); m_UV.clear(); m_colors.clear();
+    m_face_v_indices.clear(); m_face_n_indices.clear(); m_face_uv_indices.clear(); m_face_col_indices.clear();
+    geo_wildcards.clear();
     materials.clear(); isMaterialSet = false;
     nTri = 0;
 }
@@ -818,6 +899,11 @@ void DEMSolver::Initialize(bool dry_run) {
                  (b->owner_wildcards.empty() ? b->geo_wildcards.begin()->first : b->owner_wildcards.begin()->first) +
                  "), but the force model in use declares none. Wildcards of this kind belong to custom force models, "
                  "which need run-time compilation that this ahead-of-time compiled core does not have.");
+    for (const auto& m : m_cached_meshes)
+        if (!m->geo_wildcards.empty())
+            fail("A mesh carries geometry wildcards (" + m->geo_wildcards.begin()->first + "), but the force model in use "
+                 "declares none. Wildcards of this kind belong to custom force models, which need run-time compilation "
+                 "that this ahead-of-time compiled core does not have.");
     // material properties the force model reads (equipMaterials, APIPrivate.cpp:1882-1933): missing ones default to 0
     if (m_force_model_obj && verbosity >= WARNING)
         for (const std::string& prop_name : m_force_model_obj->m_must_have_mat_props)
@@ -1456,10 +1542,25 @@ DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(si
     else if (quantity == "clump_kinetic_energy") kind = DEM_REDUCE_KINETIC_ENERGY;
     else if (quantity == "clump_mass") kind = DEM_REDUCE_TOTAL_MASS;
     else if (quantity == "clump_volume") kind = 100;  // KIND_CLUMP_VOLUME: summed on the host from the templates
-    else fail(quantity + " is not a known query type (available: clump_max_z, clump_min_z, clump_max_absv, max_absv, "
+    else if (quantity == "absv") kind = 102;          // KIND_ABSV_ALL: un-reduced, one value per owner (GetValues)
+    else fail(quantity + " is not a known query type (available: clump_max_z, clump_min_z, clump_max_absv, max_absv, absv, "
               "clump_kinetic_energy, clump_mass, clump_volume).");
 }
+float* DEMInspector::GetValues() {
+    if (kind != 102)
+        fail("GetValues is for un-reduced quantities (absv); this inspector reduces its quantity to one number: use GetValue().");
+    const auto v = sys->GetOwnerVelocity(0, (bodyID_t)sys->GetNumOwners());
+    m_values.resize(v.size());
+    for (size_t i = 0; i < v.size(); i++)
+        m_values[i] = (float)std::sqrt((double)v[i].x * v[i].x + (double)v[i].y * v[i].y + (double)v[i].z * v[i].z);  // AuxClasses.cpp:54-61
+    return m_values.data();
+}
+void DEMInspector::SetInspectionCode(const std::string&) {
+    fail("SetInspectionCode: inspection code is C++ text the reference compiles into its query kernel at run time; this "
+         "ahead-of-time compiled core offers the built-in quantities (optionally confined to a region) instead.");
+}
 float DEMInspector::GetValue() {
+    if (kind == 102) return GetValues()[0];
     if (region) return (float)sys->ReduceInRegion(kind, *region);
     if (kind == 100) return (float)sys->ReduceInRegion(kind, ScalarExpression("1", {"X", "Y", "Z"}));
     return (float)sys->Reduce(kind);

@@ -131,5 +131,53 @@ int main() {
         EXPECT((Real4ToVec(make_float4(1, 2, 3, 4)) == std::vector<float>{1, 2, 3, 4}));
         puts("ok helpers");
     }
+    {  // clump template frames, mesh accessors, Wavefront round trip, Merge
+        DEMClumpTemplate t;
+        t.relPos = {make_float3(1, 0, 0), make_float3(0, 2, 0), make_float3(0.5f, 0.5f, 3)};
+        t.radii = {1, 1, 1};
+        t.nComp = 3;
+        const std::vector<float3> before = t.relPos;
+        const float4 q = QuatFromAxisAngle(make_float3(0, 0, 1), 0.9f);
+        t.Move(make_float3(0.3f, -0.2f, 0.1f), q);
+        EXPECT(!close(t.relPos[0].x, before[0].x, 1e-3));
+        t.InformCentroidPrincipal(std::vector<float>{0.3f, -0.2f, 0.1f}, std::vector<float>{q.x, q.y, q.z, q.w});  // the inverse
+        for (size_t i = 0; i < 3; i++)
+            EXPECT(close(t.relPos[i].x, before[i].x, 1e-6) && close(t.relPos[i].y, before[i].y, 1e-6) && close(t.relPos[i].z, before[i].z, 1e-6));
+        EXPECT(throws([&] { t.Move(std::vector<float>{1, 2}, std::vector<float>{0, 0, 0, 1}); }, "3-element"));
+
+        DEMMeshConnected a, b;
+        a.SetGeometry({make_float3(0, 0, 0), make_float3(1, 0, 0), make_float3(0, 1, 0), make_float3(0, 0, 1)},
+                      {make_int3(0, 1, 2), make_int3(0, 1, 3)});
+        b.SetGeometry({make_float3(5, 0, 0), make_float3(6, 0, 0), make_float3(5, 1, 0)}, {make_int3(0, 1, 2)});
+        b.m_normals = {make_float3(0, 0, 1)};
+        b.m_face_n_indices = {make_int3(0, 0, 0)};
+        EXPECT(a.GetNumTriangles() == 2 && a.GetTriangle(1).p3.z == 1.f && a.GetIndicesVertexesAsVectorOfVectors()[1][2] == 3);
+        EXPECT(a.GetCoordsVerticesAsVectorOfVectors()[1][0] == 1.f && a.GetCoordsNormals().empty() && b.GetIndicesNormals().size() == 1);
+        EXPECT(throws([&] { a.GetTriangle(2); }));
+        a.AddGeometryWildcard("wear", 0.f);
+        EXPECT(a.geo_wildcards.at("wear").size() == 2);
+        EXPECT(throws([&] { a.AddGeometryWildcard("wear", std::vector<float>{1.f}); }, "2 triangles"));
+        a.ClearWildcards();
+        std::vector<DEMMeshConnected> both = {a, b};
+        const char* path = "/tmp/facade_host_check_merged.obj";
+        DEMMeshConnected::WriteWavefront(path, both);
+        DEMMeshConnected back;
+        EXPECT(back.LoadWavefrontMesh(path));
+        EXPECT(back.GetNumNodes() == 7 && back.GetNumTriangles() == 3);
+        EXPECT(back.GetIndicesVertexes()[2].x == 4 && back.GetIndicesVertexes()[2].z == 6 && back.GetCoordsVertices()[6].y == 1.f);
+        DEMMeshConnected merged = DEMMeshConnected::Merge(both);
+        EXPECT(merged.GetNumNodes() == 7 && merged.GetNumTriangles() == 3 && merged.GetIndicesVertexes()[2].y == 5);
+        EXPECT(merged.GetCoordsNormals().empty());  // only one of the two had normals
+        for (size_t i = 0; i < 3; i++) {
+            const int3 f = merged.GetIndicesVertexes()[i], g = back.GetIndicesVertexes()[i];
+            EXPECT(f.x == g.x && f.y == g.y && f.z == g.z);
+        }
+        auto mat = std::make_shared<DEMMaterial>(std::unordered_map<std::string, float>{{"E", 1e8f}});
+        both[0].SetMaterial(mat);
+        both[1].SetMaterial(mat);
+        EXPECT(DEMMeshConnected::Merge(both).materials.size() == 3);
+        EXPECT(throws([] { DEMInspector(nullptr, "absv").SetInspectionCode("quantity[myOwner] = 1;"); }, "run time"));
+        puts("ok mesh_and_templates");
+    }
     return 0;
 }
