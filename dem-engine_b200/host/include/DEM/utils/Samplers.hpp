@@ -4,7 +4,10 @@
 #pragma once
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <random>
+#include <stdexcept>
+#include <string>
 #include <unordered_map>
 #include <vector>
 
@@ -12,10 +15,48 @@
 
 namespace deme {
 
+/// One process-wide random engine, and a draw from a normal distribution restricted to [minVal, maxVal] (what scripts use
+/// for polydisperse sizes; Samplers.hpp:48-71 of the reference)
+inline std::default_random_engine& rengine() {
+    static std::default_random_engine engine;
+    return engine;
+}
+template <typename T>
+inline T sampleTruncatedDist(std::normal_distribution<T>& distribution, T minVal, T maxVal) {
+    for (;;) {
+        const T val = distribution(rengine());
+        if (!(val < minVal) && !(val > maxVal)) return val;
+    }
+}
+
+enum class SamplingType { REGULAR_GRID, POISSON_DISK, HCP_PACK };
+
 class Sampler {
   public:
     explicit Sampler(float separation) : m_separation(separation) {}
     virtual ~Sampler() {}
+    /// Points in the ball of given radius
+    std::vector<float3> SampleSphere(const float3& center, float radius) {
+        m_center = center;
+        m_size = make_float3(radius, radius, radius);
+        return Sample(4);
+    }
+    // {x, y, z} forms returning {{x, y, z}, ...} (what the reference's Python layer calls)
+    std::vector<std::vector<float>> SampleBox(const std::vector<float>& center, const std::vector<float>& halfDim) {
+        return Real3VectorToVecOfVec(SampleBox(xyz(center, "SampleBox"), xyz(halfDim, "SampleBox")));
+    }
+    std::vector<std::vector<float>> SampleSphere(const std::vector<float>& center, float radius) {
+        return Real3VectorToVecOfVec(SampleSphere(xyz(center, "SampleSphere"), radius));
+    }
+    std::vector<std::vector<float>> SampleCylinderX(const std::vector<float>& center, float radius, float halfHeight) {
+        return Real3VectorToVecOfVec(SampleCylinderX(xyz(center, "SampleCylinderX"), radius, halfHeight));
+    }
+    std::vector<std::vector<float>> SampleCylinderY(const std::vector<float>& center, float radius, float halfHeight) {
+        return Real3VectorToVecOfVec(SampleCylinderY(xyz(center, "SampleCylinderY"), radius, halfHeight));
+    }
+    std::vector<std::vector<float>> SampleCylinderZ(const std::vector<float>& center, float radius, float halfHeight) {
+        return Real3VectorToVecOfVec(SampleCylinderZ(xyz(center, "SampleCylinderZ"), radius, halfHeight));
+    }
     /// Points in the box centred at `center` with half dimensions `halfDim`
     std::vector<float3> SampleBox(const float3& center, const float3& halfDim) {
         m_center = center;
@@ -49,9 +90,14 @@ class Sampler {
         const float fuzz = (m_size.x < 1) ? 1e-6f * m_size.x : 1e-6f;
         if (volume == 0)
             return std::fabs(v.x) <= m_size.x + fuzz && std::fabs(v.y) <= m_size.y + fuzz && std::fabs(v.z) <= m_size.z + fuzz;
+        if (volume == 4) return dot(v, v) <= m_size.x * m_size.x;
         if (volume == 2) return (v.y * v.y + v.z * v.z <= m_size.y * m_size.y) && std::fabs(v.x) <= m_size.x + fuzz;
         if (volume == 3) return (v.x * v.x + v.z * v.z <= m_size.x * m_size.x) && std::fabs(v.y) <= m_size.y + fuzz;
         return (v.x * v.x + v.y * v.y <= m_size.x * m_size.x) && std::fabs(v.z) <= m_size.z + fuzz;
+    }
+    static float3 xyz(const std::vector<float>& v, const char* who) {
+        if (v.size() != 3) throw std::runtime_error(std::string(who) + ": a 3-element vector is expected");
+        return make_float3(v[0], v[1], v[2]);
     }
     float m_separation;
     float3 m_center = make_float3(0, 0, 0);
@@ -218,6 +264,43 @@ inline std::vector<float3> DEMBoxGridSampler(float3 BoxCenter, float3 HalfDims, 
 inline std::vector<float3> DEMBoxHCPSampler(float3 BoxCenter, float3 HalfDims, float GridSize) {
     HCPSampler sampler(GridSize);
     return sampler.SampleBox(BoxCenter, HalfDims);
+}
+// {x, y, z} forms of the three free samplers (Samplers.hpp:589-660 of the reference)
+namespace sampler_detail {
+inline float3 xyz(const std::vector<float>& v, const char* who) {
+    if (v.size() != 3) throw std::runtime_error(std::string(who) + ": a 3-element vector is expected");
+    return make_float3(v[0], v[1], v[2]);
+}
+}  // namespace sampler_detail
+inline std::vector<float3> DEMBoxGridSampler(const std::vector<float>& BoxCenter, const std::vector<float>& HalfDims,
+                                             float GridSizeX, float GridSizeY = -1.0, float GridSizeZ = -1.0) {
+    return DEMBoxGridSampler(sampler_detail::xyz(BoxCenter, "DEMBoxGridSampler"), sampler_detail::xyz(HalfDims, "DEMBoxGridSampler"),
+                             GridSizeX, GridSizeY, GridSizeZ);
+}
+inline std::vector<float3> DEMBoxHCPSampler(const std::vector<float>& BoxCenter, const std::vector<float>& HalfDims, float GridSize) {
+    return DEMBoxHCPSampler(sampler_detail::xyz(BoxCenter, "DEMBoxHCPSampler"), sampler_detail::xyz(HalfDims, "DEMBoxHCPSampler"), GridSize);
+}
+inline std::vector<std::vector<float>> DEMCylSurfSampler(const std::vector<float>& CylCenter, const std::vector<float>& CylAxis,
+                                                         float CylRad, float CylHeight, float ParticleRad, float spacing = 1.2f) {
+    return Real3VectorToVecOfVec(DEMCylSurfSampler(sampler_detail::xyz(CylCenter, "DEMCylSurfSampler"),
+                                                   sampler_detail::xyz(CylAxis, "DEMCylSurfSampler"), CylRad, CylHeight, ParticleRad, spacing));
+}
+
+/// A box filled layer by layer: Poisson-disk sampling in horizontal planes `padding_factor * diam` apart -- much cheaper
+/// than a volumetric Poisson-disk cloud, at the price of regular spacing across the layers (Samplers.hpp:464-496)
+inline std::vector<float3> PDLayerSampler_BOX(float3 center, float3 hdims, float diam, float padding_factor = 1.02f,
+                                              bool verbose = false) {
+    const float pitch = diam * padding_factor, top = center.z + hdims.z;
+    std::vector<float3> all;
+    if (!(pitch > 0.f)) return all;
+    PDSampler sampler(pitch);
+    const float3 flat = make_float3(hdims.x, hdims.y, 0.f);
+    for (float z = center.z - hdims.z; z < top; z += pitch) {
+        if (verbose) std::printf("Create layer at %g\n", z);
+        const std::vector<float3> layer = sampler.SampleBox(make_float3(center.x, center.y, z), flat);
+        all.insert(all.end(), layer.begin(), layer.end());
+    }
+    return all;
 }
 
 }  // namespace deme

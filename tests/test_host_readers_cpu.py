@@ -4,6 +4,7 @@ import os
 import subprocess
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HOST = os.path.join(ROOT, "dem-engine_b200", "host")
@@ -92,6 +93,21 @@ def test_point_samplers(built, tmp_path):
     shell = sets["cyl_surf"]
     assert np.allclose(np.hypot(shell[:, 0], shell[:, 1]), 0.5, atol=1e-5)
     assert shell[:, 2].min() >= 0.5 - 1e-5 and shell[:, 2].max() <= 1.5 + 1e-5 and len(shell) > 1000
+    ball = sets["pd_sphere"]
+    assert (np.linalg.norm(ball - np.array([1, 2, 3]), axis=1) <= 0.3 + 1e-6).all()
+    assert min_dist(ball) >= 0.04 * (1 - 1e-5) and len(ball) > 800
+    hb = sets["hcp_sphere"]
+    assert (np.linalg.norm(hb, axis=1) <= 0.3 + 1e-6).all() and abs(min_dist(hb) - 0.05) < 1e-5
+    assert len(hb) < len(sets["hcp_box"]) * 0.6                           # a ball fills 52 % of its bounding cube
+    lay = sets["pd_layers"]
+    zs = np.unique(np.round(lay[:, 2], 6))
+    assert np.allclose(np.diff(zs), 0.04 * 1.05, atol=1e-6) and len(zs) == 5 and zs[0] == pytest.approx(0.4)
+    assert (np.abs(lay[:, 0]) <= 0.3 + 1e-6).all() and (np.abs(lay[:, 1]) <= 0.2 + 1e-6).all()
+    for z in zs:                                                           # Poisson-disk inside every layer
+        assert min_dist(lay[np.abs(lay[:, 2] - z) < 1e-6]) >= 0.04 * 1.05 * (1 - 1e-5)
+    assert np.array_equal(sets["hcp_box_vec"], sets["hcp_box"]) and np.array_equal(sets["grid_box_vec"], sets["grid_box"])
+    tr = sets["truncated"][:, 0]
+    assert tr.min() >= 0.8 and tr.max() <= 1.2 and tr.std() > 0.05
 
 
 def test_prescription_expression_parser(tmp_path):
