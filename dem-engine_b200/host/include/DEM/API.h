@@ -555,14 +555,17 @@ class DEMSolver {
 
     void SetVerbosity(VERBOSITY verbose) { verbosity = verbose; }
     void SetVerbosity(const std::string& verbose);
-    void SetOutputFormat(OUTPUT_FORMAT) {}
-    void SetOutputFormat(const std::string&) {}
+    /// Files are written as CSV.  As in a reference build without ChPF (APIPublic.cpp:171-210): "CHPF" is refused, "BINARY"
+    /// is accepted and answered with CSV plus a warning at write time, anything else is an error.
+    void SetOutputFormat(OUTPUT_FORMAT format);
+    void SetOutputFormat(const std::string& format);
     void SetOutputContent(unsigned int content) { m_out_content = content; }
     void SetOutputContent(const std::vector<std::string>& content);
     void SetContactOutputContent(unsigned int content) { m_cnt_out_content = content; }
     void SetContactOutputContent(const std::vector<std::string>& content);
-    void SetMeshOutputFormat(MESH_FORMAT) {}
-    void SetMeshOutputFormat(const std::string&) {}
+    /// Meshes are written as VTK; OBJ is accepted here and refused by WriteMeshFile, as in the reference (:2082-2096)
+    void SetMeshOutputFormat(MESH_FORMAT format) { m_mesh_out_format = format; }
+    void SetMeshOutputFormat(const std::string& format);
 
     void InstructBoxDomainDimension(float x, float y, float z, const std::string& dir_exact = "none");
     void InstructBoxDomainDimension(const std::pair<float, float>& x, const std::pair<float, float>& y,
@@ -844,8 +847,8 @@ class DEMSolver {
     void WriteContactFile(const std::filesystem::path& outfilename, float force_thres = 1e-15) const;
     void WriteMeshFile(const std::filesystem::path& outfilename) const;
     void WriteContactFileIncludingPotentialPairs(const std::filesystem::path& outfilename) const { WriteContactFile(outfilename, -1.0f); }
-    void SetContactOutputFormat(OUTPUT_FORMAT) {}
-    void SetContactOutputFormat(const std::string&) {}
+    void SetContactOutputFormat(OUTPUT_FORMAT format);
+    void SetContactOutputFormat(const std::string& format);
     /// Clumps of this family are left out of the clump / sphere files
     void DisableFamilyOutput(unsigned int ID) { m_no_output_families.insert((family_t)ID); }
     static std::unordered_map<std::string, std::vector<float3>> ReadClumpFloat3FromCsv(
@@ -952,6 +955,9 @@ class DEMSolver {
     DemCtx* ctx = nullptr;
     VERBOSITY verbosity = INFO;
     unsigned int m_out_content = QUAT | ABSV;
+    OUTPUT_FORMAT m_out_format = OUTPUT_FORMAT::CSV, m_cnt_out_format = OUTPUT_FORMAT::CSV;
+    MESH_FORMAT m_mesh_out_format = MESH_FORMAT::VTK;
+    void warnIfBinary(OUTPUT_FORMAT f, const char* what) const;
     unsigned int m_cnt_out_content = OWNER | FORCE | CNT_POINT;
     float3 G = make_float3(0, 0, -9.81f);
     double m_ts_size = 1e-5;

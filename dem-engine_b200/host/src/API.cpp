@@ -223,6 +223,37 @@ void DEMSolver::SetVerbosity(const std::string& verbose) {
     else if (u == "STEP_DEBUG") verbosity = STEP_DEBUG;
     else fail("Instruction " + verbose + " is unknown in SetVerbosity call.");
 }
+namespace {
+OUTPUT_FORMAT parse_output_format(const std::string& format, const char* who) {
+    const std::string u = upper(format);
+    if (u == "CSV") return OUTPUT_FORMAT::CSV;
+    if (u == "BINARY") return OUTPUT_FORMAT::BINARY;
+    if (u == "CHPF") fail("ChPF is not enabled when the code was compiled.");
+    fail("Instruction " + format + " is unknown in " + who + " call.");
+}
+}  // namespace
+void DEMSolver::SetOutputFormat(OUTPUT_FORMAT format) {
+    if (format == OUTPUT_FORMAT::CHPF) fail("ChPF is not enabled when the code was compiled.");
+    m_out_format = format;
+}
+void DEMSolver::SetOutputFormat(const std::string& format) { m_out_format = parse_output_format(format, "SetOutputFormat"); }
+void DEMSolver::SetContactOutputFormat(OUTPUT_FORMAT format) {
+    if (format == OUTPUT_FORMAT::CHPF) fail("ChPF is not enabled when the code was compiled.");
+    m_cnt_out_format = format;
+}
+void DEMSolver::SetContactOutputFormat(const std::string& format) {
+    m_cnt_out_format = parse_output_format(format, "SetContactOutputFormat");
+}
+void DEMSolver::SetMeshOutputFormat(const std::string& format) {
+    const std::string u = upper(format);
+    if (u == "VTK") m_mesh_out_format = MESH_FORMAT::VTK;
+    else if (u == "OBJ") m_mesh_out_format = MESH_FORMAT::OBJ;
+    else fail("Instruction " + format + " is unknown in SetMeshOutputFormat call.");
+}
+void DEMSolver::warnIfBinary(OUTPUT_FORMAT f, const char* what) const {
+    if (f == OUTPUT_FORMAT::BINARY && verbosity >= WARNING)
+        std::cerr << "WARNING! Binary " << what << " output is not implemented yet, using CSV..." << std::endl;
+}
 void DEMSolver::SetOutputContent(const std::vector<std::string>& content) {
     unsigned int c = XYZ;
     for (const auto& a : content) {
@@ -687,6 +718,8 @@ std::shared_ptr<DEMMeshConnected> DEMSolver::AddWavefrontMeshObject(const std::s
 
 void DEMSolver::WriteMeshFile(const std::filesystem::path& outfilename) const {
     assertInit("WriteMeshFile");
+    if (m_mesh_out_format != MESH_FORMAT::VTK)
+        fail("Mesh output file format is unknown or not implemented. Please re-set it via SetMeshOutputFormat.");
     std::ofstream f(outfilename);
     size_t nV = 0, nF = 0;
     for (const auto& m : m_cached_meshes) { nV += m->m_vertices.size(); nF += m->nTri; }
@@ -1569,6 +1602,7 @@ float DEMInspector::GetValue() {
 // ---- writers (dT.cpp:1254-1617): CSV only ----
 void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy) const {
     assertInit("WriteClumpFile");
+    warnIfBinary(m_out_format, "clump");
     const uint32_t n = (uint32_t)nOwnerClumps;
     std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n), w(3 * (size_t)n);
     std::vector<uint8_t> fam(n);
@@ -1599,6 +1633,7 @@ void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigne
 }
 void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const {
     assertInit("WriteSphereFile");
+    warnIfBinary(m_out_format, "sphere");
     const uint32_t n = (uint32_t)nOwnerClumps;
     std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n);
     check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
@@ -1623,6 +1658,7 @@ void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const 
 }
 void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float force_thres) const {
     assertInit("WriteContactFile");
+    warnIfBinary(m_cnt_out_format, "contact pair");
     uint64_t n = 0;
     check(dem_download_contacts(ctx, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_download_contacts");
     std::vector<uint32_t> a(n), b(n);
