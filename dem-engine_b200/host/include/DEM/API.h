@@ -598,11 +598,13 @@ class DEMSolver {
     void SetIntegrator(TIME_INTEGRATOR intg) { m_integrator = intg; }
     void SetExpandFactor(float beta, bool fix = true);
     void SetMaxVelocity(float max_vel) { m_approx_max_vel = max_vel; }
-    void SetExpandSafetyType(const std::string&) {}
+    /// only "auto" exists (margin from the measured top speed, the default): anything else is an error, as in the reference
+    void SetExpandSafetyType(const std::string& insp_type);
     void SetExpandSafetyMultiplier(float param) { m_expand_safety_multi = param; }
     void SetExpandSafetyAdder(float vel) { m_expand_base_vel = vel; }
     void SetErrorOutVelocity(float vel) { threshold_error_out_vel = vel; }
-    void SetErrorOutAvgContacts(float) {}
+    /// stop with an error when a sphere has more listed contacts than this on average (default 100, Structs.h:527)
+    void SetErrorOutAvgContacts(float num_cnts) { threshold_error_out_num_cnts = num_cnts; }
     void SetNoForceRecord(bool flag = true) { no_recording_contact_forces = flag; }
     // Tuning knobs of the reference's two-thread / jitify machinery: accepted and ignored
     void SetInitBinSize(double) {}
@@ -622,7 +624,7 @@ class DEMSolver {
     /// let the solver pick the steps per contact-list cycle (on by default, as in the reference; SetCDUpdateFreq gives the
     /// starting point, SetCDMaxUpdateFreq the upper bound)
     void UseAdaptiveUpdateFreq(bool flag = true);
-    void DisableAdaptiveUpdateFreq() {}
+    void DisableAdaptiveUpdateFreq() { UseAdaptiveUpdateFreq(false); }
     void SetAdaptiveBinSizeDelaySteps(unsigned int) {}
     void SetAdaptiveBinSizeMaxRate(float) {}
     void SetAdaptiveBinSizeAcc(float) {}
@@ -989,6 +991,7 @@ class DEMSolver {
     float m_expand_safety_multi = 1.f;
     float m_expand_base_vel = 3.f;
     float threshold_error_out_vel = 1e3f;
+    float threshold_error_out_num_cnts = 100.f;
     bool no_recording_contact_forces = false;
     bool sys_initialized = false;
     float3 m_user_box_min = make_float3(-10, -10, -10), m_user_box_max = make_float3(10, 10, 10);

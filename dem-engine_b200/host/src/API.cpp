@@ -305,8 +305,13 @@ void DEMSolver::InstructBoxDomainBoundingBC(const std::string& inst, const std::
 }
 
 void DEMSolver::SetCDUpdateFreq(int freq) {
-    // SetCDUpdateFreq(0) is the reference's lock-step mode: rebuild before every step
+    // SetCDUpdateFreq(0) is the reference's lock-step mode: rebuild before every step; a negative value also switches the
+    // adaptive frequency off (API.h:107-113 of the reference)
     m_cd_update_freq = std::max(1, freq);
+    if (freq < 0) UseAdaptiveUpdateFreq(false);
+}
+void DEMSolver::SetExpandSafetyType(const std::string& insp_type) {
+    if (insp_type != "auto") fail("Unknown string input \"" + insp_type + "\" for SetExpandSafetyType.");
 }
 float DEMSolver::GetUpdateFreq() const {
     if (!sys_initialized) return (float)m_cd_update_freq;
@@ -1249,6 +1254,16 @@ void DEMSolver::DoDynamics(double thisCallDuration) {
     } else
     check(dem_do_dynamics(ctx, thisCallDuration), "DoDynamics");
     m_wall_time_dynamics += std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
+    // the reference's contact detection stops a run whose lists explode (DEMCubContactDetection.cu:876-892)
+    const float avg = GetAvgSphContacts();
+    if (avg > threshold_error_out_num_cnts)
+        fail("On average a sphere has " + std::to_string(avg) + " contacts, more than the max allowance (" +
+             std::to_string(threshold_error_out_num_cnts) + ").\nIf you believe this is not abnormal, set the allowance high "
+             "using SetErrorOutAvgContacts before initialization.\nIf you think this is because the contact margin added is too "
+             "big, use SetCDMaxUpdateFreq to limit the number of steps a contact list is used for.\nOtherwise, the simulation "
+             "may have diverged and relaxing the physics may help, such as decreasing the step size and modifying material "
+             "properties.\nIf this happens at the start of simulation, check if there are initial penetrations, a.k.a. elements "
+             "initialized inside walls.");
 }
 void DEMSolver::DoDynamicsThenSync(double thisCallDuration) { DoDynamics(thisCallDuration); }
 
