@@ -1054,7 +1054,13 @@ int dem_abi_version(void) { return DEM_B200_ABI_VERSION; }
 
 int dem_host_figure_out_nv(const float box_min[3], const float box_max[3], uint32_t nv_p2[3], double* l,
                            double* voxel_size) {
-    // DEMSolver::figureOutNV, APIPrivate.cpp:373-487 (m_box_dir_length_is_exact == NONE)
+    return dem_host_figure_out_nv_exact(box_min, box_max, -1, nv_p2, l, voxel_size);
+}
+
+int dem_host_figure_out_nv_exact(const float box_min[3], const float box_max[3], int exact_dir, uint32_t nv_p2[3], double* l,
+                                 double* voxel_size) {
+    // DEMSolver::figureOutNV, APIPrivate.cpp:373-487; exact_dir = -1 is m_box_dir_length_is_exact == NONE
+    if (!box_min || !box_max || !nv_p2 || !l || !voxel_size || exact_dir < -1 || exact_dir > 2) return DEM_ERR_INVALID;
     float XYZ[3] = {box_max[0] - box_min[0], box_max[1] - box_min[1], box_max[2] - box_min[2]};
     int rank[3] = {0, 1, 2};
     for (int i = 0; i < 2; i++)
@@ -1079,11 +1085,27 @@ int dem_host_figure_out_nv(const float box_min[3], const float box_max[3], uint3
         if (b3 < b2) b3++; else if (b2 < b1) b2++; else b1++;
         left--;
     }
-    const int bits[3] = {b3, b2, b1};
-    const double l3 = (double)user321[0] / std::pow(2., 16) / std::pow(2., b3);
-    const double l2 = (double)user321[1] / std::pow(2., 16) / std::pow(2., b2);
-    const double l1 = (double)user321[2] / std::pow(2., 16) / std::pow(2., b1);
-    *l = std::max(l3, std::max(l2, l1));
+    int bits[3] = {b3, b2, b1};
+    if (exact_dir < 0) {
+        const double l3 = (double)user321[0] / std::pow(2., 16) / std::pow(2., b3);
+        const double l2 = (double)user321[1] / std::pow(2., 16) / std::pow(2., b2);
+        const double l1 = (double)user321[2] / std::pow(2., 16) / std::pow(2., b1);
+        *l = std::max(l3, std::max(l2, l1));
+    } else {
+        // the world spans the box EXACTLY along one axis (2^bits voxels of 2^16 l): l follows from that axis alone, and
+        // the axis lends bits to the other two until they cover their lengths as well (:442-476)
+        int e = 0;
+        while (rank[e] != exact_dir) e++;
+        const int others[2] = {e == 0 ? 1 : 0, e == 2 ? 1 : 2};
+        auto unit = [&]() { return (double)user321[e] / std::pow(2., 16) / std::pow(2., bits[e]); };
+        *l = unit();
+        for (int k = 1; k >= 0; k--)
+            while (*l * std::pow(2., 16) * std::pow(2., bits[others[k]]) < user321[others[k]]) {
+                bits[e] -= 1;
+                bits[others[k]] += 1;
+                *l = unit();
+            }
+    }
     for (int p = 0; p < 3; p++) nv_p2[rank[p]] = (uint32_t)bits[p];
     *voxel_size = (double)((size_t)1 << 16) * (*l);
     return DEM_OK;

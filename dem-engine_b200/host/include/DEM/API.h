@@ -996,6 +996,7 @@ class DEMSolver {
     bool sys_initialized = false;
     float3 m_user_box_min = make_float3(-10, -10, -10), m_user_box_max = make_float3(10, 10, 10);
     float3 m_target_box_min = make_float3(-12, -12, -12), m_target_box_max = make_float3(12, 12, 12);
+    int m_box_dir_exact = -1;  // axis along which the world spans the user's box exactly (-1: none)
     std::string m_user_add_bounding_box = "none";
     std::shared_ptr<DEMMaterial> m_bounding_box_material;
 

@@ -277,23 +277,38 @@ void DEMSolver::SetContactOutputContent(const std::vector<std::string>& content)
     m_cnt_out_content = c;
 }
 
+namespace {
+int exact_axis(const std::string& dir_exact) {
+    const std::string u = upper(dir_exact);
+    if (u == "X") return 0;
+    if (u == "Y") return 1;
+    if (u == "Z") return 2;
+    if (u == "NONE") return -1;
+    fail("Unknown '" + dir_exact + "' parameter in InstructBoxDomainDimension call.");
+}
+}  // namespace
 void DEMSolver::InstructBoxDomainDimension(float x, float y, float z, const std::string& dir_exact) {
-    if (upper(dir_exact) != "NONE") fail("InstructBoxDomainDimension: an exact direction is not supported by this core.");
-    float umin[3], umax[3], tmin[3], tmax[3];
-    dem_host_box_domain(x, y, z, umin, umax, tmin, tmax);
-    m_user_box_min = make_float3(umin[0], umin[1], umin[2]);
-    m_user_box_max = make_float3(umax[0], umax[1], umax[2]);
-    m_target_box_min = make_float3(tmin[0], tmin[1], tmin[2]);
-    m_target_box_max = make_float3(tmax[0], tmax[1], tmax[2]);
+    InstructBoxDomainDimension({-x / 2.f, x / 2.f}, {-y / 2.f, y / 2.f}, {-z / 2.f, z / 2.f}, dir_exact);
+    if (exact_axis(dir_exact) < 0) {  // (the centred form goes through the C ABI's own arithmetic)
+        float umin[3], umax[3], tmin[3], tmax[3];
+        dem_host_box_domain(x, y, z, umin, umax, tmin, tmax);
+        m_user_box_min = make_float3(umin[0], umin[1], umin[2]);
+        m_user_box_max = make_float3(umax[0], umax[1], umax[2]);
+        m_target_box_min = make_float3(tmin[0], tmin[1], tmin[2]);
+        m_target_box_max = make_float3(tmax[0], tmax[1], tmax[2]);
+    }
 }
 void DEMSolver::InstructBoxDomainDimension(const std::pair<float, float>& x, const std::pair<float, float>& y,
                                            const std::pair<float, float>& z, const std::string& dir_exact) {
-    if (upper(dir_exact) != "NONE") fail("InstructBoxDomainDimension: an exact direction is not supported by this core.");
-    // APIPublic.cpp:874-905: enlarge by 20 % about the user's box
+    m_box_dir_exact = exact_axis(dir_exact);
+    // APIPublic.cpp:874-905: enlarge by 20 % about the user's box, except along the axis whose length is to be exact
     m_user_box_min = make_float3(std::min(x.first, x.second), std::min(y.first, y.second), std::min(z.first, z.second));
     m_user_box_max = make_float3(std::max(x.first, x.second), std::max(y.first, y.second), std::max(z.first, z.second));
     const float3 sz = m_user_box_max - m_user_box_min;
-    const float3 enl = make_float3(sz.x * 0.2f / 2.f, sz.y * 0.2f / 2.f, sz.z * 0.2f / 2.f);
+    float3 enl = make_float3(sz.x * 0.2f / 2.f, sz.y * 0.2f / 2.f, sz.z * 0.2f / 2.f);
+    if (m_box_dir_exact == 0) enl.x = 0.f;
+    if (m_box_dir_exact == 1) enl.y = 0.f;
+    if (m_box_dir_exact == 2) enl.z = 0.f;
     m_target_box_min = m_user_box_min - enl;
     m_target_box_max = m_user_box_max + enl;
 }
@@ -959,7 +974,7 @@ void DEMSolver::Initialize(bool dry_run) {
     const float tmin[3] = {m_target_box_min.x, m_target_box_min.y, m_target_box_min.z};
     const float tmax[3] = {m_target_box_max.x, m_target_box_max.y, m_target_box_max.z};
     uint32_t nv[3];
-    dem_host_figure_out_nv(tmin, tmax, nv, &sp.l, &sp.voxelSize);
+    dem_host_figure_out_nv_exact(tmin, tmax, m_box_dir_exact, nv, &sp.l, &sp.voxelSize);
     sp.nvXp2 = nv[0]; sp.nvYp2 = nv[1]; sp.nvZp2 = nv[2];
     sp.integrator = (m_integrator == TIME_INTEGRATOR::FORWARD_EULER) ? DEM_FORWARD_EULER
                     : (m_integrator == TIME_INTEGRATOR::CENTERED_DIFFERENCE) ? DEM_CENTERED_DIFFERENCE : DEM_EXTENDED_TAYLOR;

@@ -26,7 +26,7 @@ EXPORTED_SYMBOLS = [
     "dem_download_owner_state", "dem_download_positions", "dem_upload_owner_state", "dem_download_contacts",
     "dem_get_stats", "dem_set_sim_time", "dem_download_contact_records", "dem_reduce", "dem_reduce_many", "dem_profile_steps", "dem_profile_rebuild", "dem_set_option",
     "dem_mgpu_unique_id", "dem_mgpu_init", "dem_mgpu_info", "dem_host_slab_bounds",
-    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_set_family_material", "dem_group_step_async", "dem_group_sync", "dem_group_gather", "dem_add_owner_acc",
+    "dem_mgpu_init_local", "dem_mgpu_barrier", "dem_device_count", "dem_ctx_create_group", "dem_set_family_material", "dem_group_step_async", "dem_group_sync", "dem_group_gather", "dem_add_owner_acc", "dem_host_figure_out_nv_exact",
 ]
 
 
@@ -88,13 +88,17 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
-def host_figure_out_nv(box_min, box_max):
+def host_figure_out_nv(box_min, box_max, exact_dir=None):
+    """figureOutNV; exact_dir = 0 / 1 / 2 makes the world span the box exactly along X / Y / Z."""
     lib = load_library()
     mn = np.ascontiguousarray(box_min, "f4")
     mx = np.ascontiguousarray(box_max, "f4")
     nv = np.zeros(3, "u4")
     l, vs = C.c_double(), C.c_double()
-    rc = lib.dem_host_figure_out_nv(_p(mn), _p(mx), _p(nv), C.byref(l), C.byref(vs))
+    if exact_dir is None:
+        rc = lib.dem_host_figure_out_nv(_p(mn), _p(mx), _p(nv), C.byref(l), C.byref(vs))
+    else:
+        rc = lib.dem_host_figure_out_nv_exact(_p(mn), _p(mx), C.c_int(exact_dir), _p(nv), C.byref(l), C.byref(vs))
     assert rc == 0
     return int(nv[0]), int(nv[1]), int(nv[2]), l.value, vs.value
 

@@ -119,6 +119,11 @@ typedef struct DemStats {
 /* DEMSolver::figureOutNV (APIPrivate.cpp:373-487): split 64 voxel bits, choose l. box_* is the target (enlarged) box. */
 int dem_host_figure_out_nv(const float box_min[3], const float box_max[3], uint32_t nv_p2[3], double* l,
                            double* voxel_size);
+/* ... with the length along one axis made exact (InstructBoxDomainDimension(..., dir_exact), APIPublic.cpp:855-868 and
+ * APIPrivate.cpp:442-476): exact_dir = 0 / 1 / 2 for X / Y / Z, -1 for none.  The caller passes a target box that is
+ * not enlarged along that axis. */
+int dem_host_figure_out_nv_exact(const float box_min[3], const float box_max[3], int exact_dir, uint32_t nv_p2[3],
+                                 double* l, double* voxel_size);
 /* InstructBoxDomainDimension(x,y,z) (APIPublic.cpp:845-872). Outputs user box and 20%-enlarged target box. */
 int dem_host_box_domain(float x, float y, float z, float user_min[3], float user_max[3], float target_min[3],
                         float target_max[3]);

@@ -60,6 +60,73 @@ def test_figure_out_nv_properties(x, y, z):
     assert l == l_ref
 
 
+@settings(max_examples=200, deadline=None)
+@given(dims, dims, dims, st.integers(min_value=0, max_value=2))
+def test_figure_out_nv_exact_direction(x, y, z, exact):
+    """InstructBoxDomainDimension(..., dir_exact) (APIPrivate.cpp:442-476 of the reference): the world spans the box EXACTLY
+    along the chosen axis, covers it along the other two, and all 64 bits are handed out."""
+    size = np.array([x, y, z], "f4")
+    lo = -size / 2
+    ext = ((lo + size) - lo).astype("f8")
+    nx, ny, nz, l, vs = demb200.host_figure_out_nv(lo, lo + size, exact_dir=exact)
+    bits = np.array([nx, ny, nz], "i8")
+    assert bits.sum() == 64 and vs == l * 65536.0
+    world = vs * (2.0 ** bits.astype("f8"))
+    assert world[exact] == ext[exact] or np.isclose(world[exact], ext[exact], rtol=1e-15)   # exact up to the power-of-two scaling
+    assert (world >= ext * (1 - 1e-12)).all()
+    # the reference's rule restated step by step (APIPrivate.cpp:378-476): rank the sides, split the bits, then let the
+    # exact axis lend bits to the other two, the longer one first
+    e32 = ((lo + size) - lo).astype("f4")
+    order = [0, 1, 2]
+    v = [float(e32[0]), float(e32[1]), float(e32[2])]
+    for i in range(2):
+        for j in range(i + 1, 3):
+            if v[i] > v[j]:
+                v[i], v[j] = v[j], v[i]
+                order[i], order[j] = order[j], order[i]
+    user = list(v)
+    more = [0, 0]
+    while v[0] < v[1] and not (math.sqrt(2.0) * v[0] > v[1]):
+        more[0] += 1
+        v[0] = float(np.float32(v[0] * 2.0))
+    while v[1] < v[2] and not (math.sqrt(2.0) * v[1] > v[2]):
+        more[1] += 1
+        v[1] = float(np.float32(v[1] * 2.0))
+    total = 64 - 2 * more[0] - more[1]
+    b = [total // 3, 0, 0]
+    b[1] = b[0] + more[0]
+    b[2] = b[1] + more[1]
+    for _ in range(total % 3):
+        if b[0] < b[1]:
+            b[0] += 1
+        elif b[1] < b[2]:
+            b[1] += 1
+        else:
+            b[2] += 1
+    e = order.index(exact)
+    others = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[e]
+    unit = lambda: user[e] / 65536.0 / 2.0 ** b[e]
+    l_ref = unit()
+    for k in (others[1], others[0]):
+        while l_ref * 65536.0 * 2.0 ** b[k] < user[k]:
+            b[e] -= 1
+            b[k] += 1
+            l_ref = unit()
+    assert l == l_ref and [int(bits[order[p]]) for p in range(3)] == b
+    # the axis lent no more bits than needed: with one bit back, one of the other two axes would fall short -- unless it
+    # never lent any (then the split is the plain one of the rule above)
+    nx0, ny0, nz0, _, _ = demb200.host_figure_out_nv(lo, lo + size)
+    plain = np.array([nx0, ny0, nz0], "i8")
+    lent = int(plain[exact] - bits[exact])
+    assert lent >= 0
+    if lent > 0:
+        l_back = ext[exact] / 65536.0 / 2.0 ** (bits[exact] + 1)
+        others = [k for k in range(3) if k != exact]
+        short = [l_back * 65536.0 * 2.0 ** (bits[k] - 1) < ext[k] for k in others] + \
+                [l_back * 65536.0 * 2.0 ** bits[k] < ext[k] for k in others]
+        assert any(short)
+
+
 @settings(max_examples=100, deadline=None)
 @given(dims, dims, dims, st.integers(min_value=0, max_value=2 ** 31 - 1))
 def test_position_code_round_trip(x, y, z, seed):
