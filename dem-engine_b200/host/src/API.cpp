@@ -1179,7 +1179,8 @@ void DEMSolver::Initialize(bool dry_run) {
     for (size_t s_id = sph_owner.size(); s_id-- > 0;) m_owner_first_sphere[sph_owner[s_id]] = (unsigned int)s_id;
     m_tri_owner = triOwner;
     m_anal_owner = objOwner;
-    if (!m_trackers.empty()) check(dem_set_option(ctx, "keep_acc", 1.0), "dem_set_option");
+    if (!m_trackers.empty() || (m_out_content & (ABS_ACC | ACC | ANG_ACC)))
+        check(dem_set_option(ctx, "keep_acc", 1.0), "dem_set_option");
 
     // ---- restart: existing contacts + wildcards of the batches (Structs.h:857-882, dT.cpp:849-881) ----
     {
@@ -1630,34 +1631,60 @@ float DEMInspector::GetValue() {
 }
 
 // ---- writers (dT.cpp:1254-1617): CSV only ----
+namespace {
+// the per-owner columns both writers share, in the reference's order (dT.cpp:1266-1301 / :1503-1530)
+struct OwnerColumns {
+    std::vector<float> q, v, w, acc, angacc;
+    std::vector<uint8_t> fam;
+};
+void owner_header(std::ostream& f, unsigned int content) {
+    if (content & ABSV) f << ",absv";
+    if (content & VEL) f << ",v_x,v_y,v_z";
+    if (content & ANG_VEL) f << ",w_x,w_y,w_z";
+    if (content & ABS_ACC) f << ",abs_acc";
+    if (content & ACC) f << ",a_x,a_y,a_z";
+    if (content & ANG_ACC) f << ",alpha_x,alpha_y,alpha_z";
+    if (content & FAMILY) f << ",family";
+}
+void owner_row(std::ostream& f, unsigned int content, const OwnerColumns& c, size_t i) {
+    const float* v = &c.v[3 * i];
+    const float* w = &c.w[3 * i];
+    const float* a = &c.acc[3 * i];
+    const float* al = &c.angacc[3 * i];
+    if (content & ABSV) f << "," << std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    if (content & VEL) f << "," << v[0] << "," << v[1] << "," << v[2];
+    if (content & ANG_VEL) f << "," << w[0] << "," << w[1] << "," << w[2];
+    if (content & ABS_ACC) f << "," << std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (content & ACC) f << "," << a[0] << "," << a[1] << "," << a[2];
+    if (content & ANG_ACC) f << "," << al[0] << "," << al[1] << "," << al[2];
+    if (content & FAMILY) f << "," << (unsigned)c.fam[i];
+}
+}  // namespace
 void DEMSolver::WriteClumpFile(const std::filesystem::path& outfilename, unsigned int accuracy) const {
     assertInit("WriteClumpFile");
     warnIfBinary(m_out_format, "clump");
     const uint32_t n = (uint32_t)nOwnerClumps;
-    std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n), w(3 * (size_t)n);
-    std::vector<uint8_t> fam(n);
+    std::vector<float> pos(3 * (size_t)n);
+    OwnerColumns c;
+    c.q.resize(4 * (size_t)n); c.v.resize(3 * (size_t)n); c.w.resize(3 * (size_t)n);
+    c.acc.resize(3 * (size_t)n); c.angacc.resize(3 * (size_t)n); c.fam.resize(n);
+    const bool want_acc = (m_out_content & (ABS_ACC | ACC | ANG_ACC)) != 0;
     check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
-    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), w.data(), nullptr,
-                                   nullptr, fam.data()), "dem_download_owner_state");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, c.q.data(), c.v.data(), c.w.data(),
+                                   want_acc ? c.acc.data() : nullptr, want_acc ? c.angacc.data() : nullptr, c.fam.data()),
+          "dem_download_owner_state");
     std::ofstream f(outfilename);
     f << std::setprecision(accuracy);
-    f << "X,Y,Z";
-    if (m_out_content & QUAT) f << ",Qw,Qx,Qy,Qz";
-    f << ",clump_type";
-    if (m_out_content & ABSV) f << ",absv";
-    if (m_out_content & VEL) f << ",v_x,v_y,v_z";
-    if (m_out_content & ANG_VEL) f << ",w_x,w_y,w_z";
-    if (m_out_content & FAMILY) f << ",family";
+    // position, orientation and type always; the rest as SetOutputContent says (dT.cpp:1501-1531 of the reference)
+    f << "X,Y,Z,Qw,Qx,Qy,Qz,clump_type";
+    owner_header(f, m_out_content);
     f << "\n";
     for (uint32_t i = 0; i < n; i++) {
-        if (m_no_output_families.count(fam[i])) continue;  // DisableFamilyOutput
+        if (m_no_output_families.count(c.fam[i])) continue;  // DisableFamilyOutput
         f << pos[3 * i] << "," << pos[3 * i + 1] << "," << pos[3 * i + 2];
-        if (m_out_content & QUAT) f << "," << q[4 * i] << "," << q[4 * i + 1] << "," << q[4 * i + 2] << "," << q[4 * i + 3];
+        f << "," << c.q[4 * i] << "," << c.q[4 * i + 1] << "," << c.q[4 * i + 2] << "," << c.q[4 * i + 3];
         f << "," << m_templates[m_owner_type_mark[i]]->m_name;
-        if (m_out_content & ABSV) f << "," << std::sqrt(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
-        if (m_out_content & VEL) f << "," << v[3 * i] << "," << v[3 * i + 1] << "," << v[3 * i + 2];
-        if (m_out_content & ANG_VEL) f << "," << w[3 * i] << "," << w[3 * i + 1] << "," << w[3 * i + 2];
-        if (m_out_content & FAMILY) f << "," << (unsigned)fam[i];
+        owner_row(f, m_out_content, c, i);
         f << "\n";
     }
 }
@@ -1665,23 +1692,28 @@ void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const 
     assertInit("WriteSphereFile");
     warnIfBinary(m_out_format, "sphere");
     const uint32_t n = (uint32_t)nOwnerClumps;
-    std::vector<float> pos(3 * (size_t)n), q(4 * (size_t)n), v(3 * (size_t)n);
+    std::vector<float> pos(3 * (size_t)n);
+    OwnerColumns c;
+    c.q.resize(4 * (size_t)n); c.v.resize(3 * (size_t)n); c.w.resize(3 * (size_t)n);
+    c.acc.resize(3 * (size_t)n); c.angacc.resize(3 * (size_t)n); c.fam.resize(n);
+    const bool want_acc = (m_out_content & (ABS_ACC | ACC | ANG_ACC)) != 0;
     check(dem_download_positions(ctx, 0, n, pos.data(), nullptr), "dem_download_positions");
-    std::vector<uint8_t> fam(n);
-    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, q.data(), v.data(), nullptr, nullptr,
-                                   nullptr, fam.data()), "dem_download_owner_state");
+    check(dem_download_owner_state(ctx, 0, n, nullptr, nullptr, nullptr, nullptr, c.q.data(), c.v.data(), c.w.data(),
+                                   want_acc ? c.acc.data() : nullptr, want_acc ? c.angacc.data() : nullptr, c.fam.data()),
+          "dem_download_owner_state");
     std::ofstream f(outfilename);
-    f << "x,y,z,r";
-    if (m_out_content & ABSV) f << ",absv";
+    // one row per sphere: centre, radius, then its owner's columns (dT.cpp:1263-1303, 1340-1400 of the reference)
+    f << "X,Y,Z,r";
+    owner_header(f, m_out_content);
     f << "\n";
     for (uint32_t i = 0; i < n; i++) {
-        if (m_no_output_families.count(fam[i])) continue;  // DisableFamilyOutput
+        if (m_no_output_families.count(c.fam[i])) continue;  // DisableFamilyOutput
         const auto& t = m_templates[m_owner_type_mark[i]];
-        const float4 quat = make_float4(q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], q[4 * i]);
+        const float4 quat = make_float4(c.q[4 * i + 1], c.q[4 * i + 2], c.q[4 * i + 3], c.q[4 * i]);
         for (unsigned int k = 0; k < t->nComp; k++) {
             const float3 r = Rotate(t->relPos[k], quat);
             f << pos[3 * i] + r.x << "," << pos[3 * i + 1] + r.y << "," << pos[3 * i + 2] + r.z << "," << t->radii[k];
-            if (m_out_content & ABSV) f << "," << std::sqrt(v[3 * i] * v[3 * i] + v[3 * i + 1] * v[3 * i + 1] + v[3 * i + 2] * v[3 * i + 2]);
+            owner_row(f, m_out_content, c, i);
             f << "\n";
         }
     }
