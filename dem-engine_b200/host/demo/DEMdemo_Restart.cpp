@@ -17,6 +17,8 @@ using namespace deme;
 static std::shared_ptr<DEMClumpTemplate> setup(DEMSolver& sim, std::shared_ptr<DEMMaterial>& mat) {
     sim.SetVerbosity(QUIET);
     sim.SetOutputContent({"XYZ", "QUAT", "VEL", "ANG_VEL", "FAMILY"});
+    // what a restart needs from the contact file: the geometry ids of each pair and its history words
+    sim.SetContactOutputContent({"OWNER", "GEO_ID", "FORCE", "CNT_WILDCARD"});
     mat = sim.LoadMaterial({{"E", 1e8}, {"nu", 0.3}, {"CoR", 0.5}, {"mu", 0.4}, {"Crr", 0.0}});
     auto tmpl = sim.LoadClumpType(2.6e3f * 5.5886717f, make_float3(2.928f, 2.6029f, 3.9908f) * 2.6e3f,
                                   GetDEMEDataFile("clumps/3_clump.csv").string(), mat);

@@ -981,6 +981,7 @@ class DEMSolver {
     };
     std::set<PersistentPair> m_persistent;
     std::vector<std::tuple<uint32_t, uint32_t, uint8_t>> persistentKeys() const;
+    std::shared_ptr<ContactInfoContainer> generateContactInfo(float force_thres, unsigned int content) const;
     bool m_any_rolling_resistance = false;
     std::vector<unsigned char> m_sp_blob;  // the DemSimParams of Initialize(), for UpdateSimParams
     void markPersistent(int mode, unsigned int N1, unsigned int N2, bool mark);

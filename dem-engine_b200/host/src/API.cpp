@@ -1719,41 +1719,40 @@ void DEMSolver::WriteSphereFile(const std::filesystem::path& outfilename) const 
     }
 }
 void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float force_thres) const {
+    // the columns SetContactOutputContent selected, in the reference's order (writeContactsAsCsv, dT.cpp:1757-1847):
+    // contact_type | A,B | geoA,geoB | f_x,f_y,f_z | X,Y,Z | n_x,n_y,n_z | torque_x,torque_y,torque_z | the wildcards
     assertInit("WriteContactFile");
     warnIfBinary(m_cnt_out_format, "contact pair");
-    uint64_t n = 0;
-    check(dem_download_contacts(ctx, 0, &n, nullptr, nullptr, nullptr, nullptr, nullptr), "dem_download_contacts");
-    std::vector<uint32_t> a(n), b(n);
-    std::vector<uint8_t> t(n);
-    std::vector<float> wc(4 * n), fr(3 * n);
-    if (n) check(dem_download_contacts(ctx, n, &n, a.data(), b.data(), t.data(), wc.data(), fr.data()), "dem_download_contacts");
-    if (force_thres < 0.f && !m_persistent.empty()) {  // marked pairs the list dropped are still potential pairs
-        std::set<std::tuple<uint32_t, uint32_t, uint8_t>> listed;
-        for (uint64_t i = 0; i < n; i++) listed.emplace(a[i], b[i], t[i]);
-        for (const auto& p : m_persistent)
-            if (!listed.count(std::make_tuple(p.geoA, p.geoB, p.type))) {
-                a.push_back(p.geoA); b.push_back(p.geoB); t.push_back(p.type);
-                wc.insert(wc.end(), 4, 0.f);
-                fr.insert(fr.end(), 3, 0.f);
-                n++;
-            }
+    unsigned int content = m_cnt_out_content;
+    if (no_recording_contact_forces) {  // without the force record there is nothing to threshold on or to report
+        content &= ~(unsigned int)(FORCE | CNT_POINT | NORMAL | TORQUE);
+        force_thres = -1.f;
     }
+    const auto info = generateContactInfo(force_thres, content);
     std::ofstream f(outfilename);
-    // columns as the reference writes them (dT.cpp:1700-1936): owners A/B, geometry ids geoA/geoB (sphere id; component
-    // or facet id on the B side of SA / SM contacts), force on A, then the wildcards
     f << std::setprecision(9);
-    f << "contact_type,A,B,geoA,geoB,f_x,f_y,f_z,delta_tan_x,delta_tan_y,delta_tan_z,delta_time\n";
-    for (uint64_t i = 0; i < n; i++) {
-        const float fm = std::sqrt(fr[3 * i] * fr[3 * i] + fr[3 * i + 1] * fr[3 * i + 1] + fr[3 * i + 2] * fr[3 * i + 2]);
-        if (!no_recording_contact_forces && fm < force_thres) continue;
-        const char* tn = (t[i] == DEM_CNT_SPHERE_SPHERE) ? "SS" : (t[i] == DEM_CNT_SPHERE_MESH ? "SM" : "SA");
-        const unsigned int oa = m_sphere_owner[a[i]];
-        unsigned int ob = 0;
-        if (t[i] == DEM_CNT_SPHERE_SPHERE) ob = m_sphere_owner[b[i]];
-        else if (t[i] == DEM_CNT_SPHERE_MESH) ob = b[i] < m_tri_owner.size() ? m_tri_owner[b[i]] : 0;
-        else ob = b[i] < m_anal_owner.size() ? m_anal_owner[b[i]] : 0;
-        f << tn << "," << oa << "," << ob << "," << a[i] << "," << b[i] << "," << fr[3 * i] << "," << fr[3 * i + 1]
-          << "," << fr[3 * i + 2] << "," << wc[4 * i] << "," << wc[4 * i + 1] << "," << wc[4 * i + 2] << "," << wc[4 * i + 3] << "\n";
+    f << "contact_type";
+    if (content & OWNER) f << ",A,B";
+    if (content & GEO_ID) f << ",geoA,geoB";
+    if (content & FORCE) f << ",f_x,f_y,f_z";
+    if (content & CNT_POINT) f << ",X,Y,Z";
+    if (content & NORMAL) f << ",n_x,n_y,n_z";
+    if (content & TORQUE) f << ",torque_x,torque_y,torque_z";
+    if (content & CNT_WILDCARD)
+        for (const std::string& name : info->GetWildcardNames()) f << "," << name;
+    f << "\n";
+    auto put3 = [&](const float3& v) { f << "," << v.x << "," << v.y << "," << v.z; };
+    for (size_t i = 0; i < info->Size(); i++) {
+        f << info->GetContactType()[i];
+        if (content & OWNER) f << "," << info->GetAOwner()[i] << "," << info->GetBOwner()[i];
+        if (content & GEO_ID) f << "," << info->GetAGeo()[i] << "," << info->GetBGeo()[i];
+        if (content & FORCE) put3(info->GetForce()[i]);
+        if (content & CNT_POINT) put3(info->GetPoint()[i]);
+        if (content & NORMAL) put3(info->GetNormal()[i]);
+        if (content & TORQUE) put3(info->GetTorque()[i]);
+        if (content & CNT_WILDCARD)
+            for (const std::string& name : info->GetWildcardNames()) f << "," << info->GetWildcard(name)[i];
+        f << "\n";
     }
 }
 
@@ -2059,6 +2058,9 @@ std::vector<std::tuple<uint32_t, uint32_t, uint8_t>> DEMSolver::persistentKeys()
 
 std::shared_ptr<ContactInfoContainer> DEMSolver::GetContactDetailedInfo(float force_thres) const {
     assertInit("GetContactDetailedInfo");
+    return generateContactInfo(force_thres, m_cnt_out_content);
+}
+std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force_thres, unsigned int m_cnt_out_content) const {
     const bool has_record = !no_recording_contact_forces;
     if (!has_record && (m_cnt_out_content & (FORCE | CNT_POINT | NORMAL | TORQUE)))
         fail("GetContactDetailedInfo: force, point, normal and torque come from the per-contact force record; do not call "
