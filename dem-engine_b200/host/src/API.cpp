@@ -2060,16 +2060,16 @@ std::shared_ptr<ContactInfoContainer> DEMSolver::GetContactDetailedInfo(float fo
     assertInit("GetContactDetailedInfo");
     return generateContactInfo(force_thres, m_cnt_out_content);
 }
-std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force_thres, unsigned int m_cnt_out_content) const {
+std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force_thres, unsigned int content) const {
     const bool has_record = !no_recording_contact_forces;
-    if (!has_record && (m_cnt_out_content & (FORCE | CNT_POINT | NORMAL | TORQUE)))
+    if (!has_record && (content & (FORCE | CNT_POINT | NORMAL | TORQUE)))
         fail("GetContactDetailedInfo: force, point, normal and torque come from the per-contact force record; do not call "
              "SetNoForceRecord() if you query them.");
     FullRows r = download_full_rows(ctx, has_record);
     append_persistent(r, persistentKeys());
     std::vector<std::string> names;
     if (m_force_model == FORCE_MODEL::HERTZIAN) names.assign(kWildcardNames, kWildcardNames + 4);
-    auto info = std::make_shared<ContactInfoContainer>(m_cnt_out_content, names);
+    auto info = std::make_shared<ContactInfoContainer>(content, names);
     info->ResizeAll(r.size());
     const uint32_t nO = (uint32_t)nOwnerBodies;
     std::vector<uint8_t> fam(nO);
@@ -2077,7 +2077,7 @@ std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force
     std::vector<double> pos;
     check(dem_download_owner_state(ctx, 0, nO, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                    fam.data()), "dem_download_owner_state");
-    const bool want_normal = (m_cnt_out_content & NORMAL) != 0;
+    const bool want_normal = (content & NORMAL) != 0;
     if (want_normal) {
         q.resize(4 * (size_t)nO);
         pos.resize(3 * (size_t)nO);
@@ -2095,11 +2095,11 @@ std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force
         info->GetContactType()[useful] = contact_type_name(r.t[i]);
         info->GetAOwnerFamily()[useful] = fam[oa];
         info->GetBOwnerFamily()[useful] = fam[ob];
-        if (m_cnt_out_content & OWNER) { info->GetAOwner()[useful] = oa; info->GetBOwner()[useful] = ob; }
-        if (m_cnt_out_content & GEO_ID) { info->GetAGeo()[useful] = r.a[i]; info->GetBGeo()[useful] = r.b[i]; }
-        if (m_cnt_out_content & FORCE) info->GetForce()[useful] = F;
+        if (content & OWNER) { info->GetAOwner()[useful] = oa; info->GetBOwner()[useful] = ob; }
+        if (content & GEO_ID) { info->GetAGeo()[useful] = r.a[i]; info->GetBGeo()[useful] = r.b[i]; }
+        if (content & FORCE) info->GetForce()[useful] = F;
         const float3 P = make_float3(r.point[3 * i], r.point[3 * i + 1], r.point[3 * i + 2]);
-        if (m_cnt_out_content & CNT_POINT) info->GetPoint()[useful] = P;
+        if (content & CNT_POINT) info->GetPoint()[useful] = P;
         if (want_normal) {
             // outward normal of body A: from the centre of sphere A to the contact point (dT.cpp:1714-1727)
             const auto& tp = m_templates[m_owner_type_mark[oa]];
@@ -2110,7 +2110,7 @@ std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force
             const float len = length(d);
             info->GetNormal()[useful] = len > 0.f ? d * (1.f / len) : make_float3(0, 0, 0);
         }
-        if (m_cnt_out_content & TORQUE) {
+        if (content & TORQUE) {
             if (!warned && m_any_rolling_resistance && verbosity >= WARNING) {
                 std::cerr << "WARNING! The torque field of GetContactDetailedInfo is the couple a contact adds beyond the "
                              "moment of its force (rolling resistance). This core applies it to the owners without keeping "
@@ -2119,7 +2119,7 @@ std::shared_ptr<ContactInfoContainer> DEMSolver::generateContactInfo(float force
             }
             info->GetTorque()[useful] = make_float3(0, 0, 0);
         }
-        if (m_cnt_out_content & CNT_WILDCARD)
+        if (content & CNT_WILDCARD)
             for (size_t k = 0; k < names.size(); k++) info->GetWildcard(names[k])[useful] = r.wc[4 * i + k];
         useful++;
     }
