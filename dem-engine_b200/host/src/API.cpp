@@ -1602,7 +1602,7 @@ DEMInspector::DEMInspector(DEMSolver* sim, const std::string& quantity) : sys(si
     if (quantity == "clump_max_z") kind = DEM_REDUCE_SPHERE_MAX_Z;
     else if (quantity == "clump_min_z") kind = DEM_REDUCE_SPHERE_MIN_Z;
     else if (quantity == "clump_max_absv") kind = DEM_REDUCE_SPHERE_MAX_ABSV;
-    else if (quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;
+    else if (quantity == "max_absv") kind = DEM_REDUCE_MAX_ABSV;  // every owner, not only clumps: see GetValue
     else if (quantity == "clump_kinetic_energy") kind = DEM_REDUCE_KINETIC_ENERGY;
     else if (quantity == "clump_mass") kind = DEM_REDUCE_TOTAL_MASS;
     else if (quantity == "clump_volume") kind = 100;  // KIND_CLUMP_VOLUME: summed on the host from the templates
@@ -1627,7 +1627,16 @@ float DEMInspector::GetValue() {
     if (kind == 102) return GetValues()[0];
     if (region) return (float)sys->ReduceInRegion(kind, *region);
     if (kind == 100) return (float)sys->ReduceInRegion(kind, ScalarExpression("1", {"X", "Y", "Z"}));
-    return (float)sys->Reduce(kind);
+    double value = sys->Reduce(kind);
+    if (kind == DEM_REDUCE_MAX_ABSV) {
+        // "max_absv" looks at EVERYTHING (AuxClasses.cpp:143-149 of the reference): the device reduction covers the clumps,
+        // the few external objects and meshes behind them are read back
+        const size_t nC = sys->GetNumClumps(), nO = sys->GetNumOwners();
+        if (nO > nC)
+            for (const float3& v : sys->GetOwnerVelocity((bodyID_t)nC, (bodyID_t)(nO - nC)))
+                value = std::max(value, std::sqrt((double)v.x * v.x + (double)v.y * v.y + (double)v.z * v.z));
+    }
+    return (float)value;
 }
 
 // ---- writers (dT.cpp:1254-1617): CSV only ----
