@@ -43,6 +43,13 @@ double fake_option(DemCtx*, const char* name, double missing);
 const float* fake_added_acc(DemCtx*);
 const FakeContact* fake_set_contact(DemCtx*, uint32_t i);
 uint32_t fake_num_contacts_set(DemCtx*);
+float fake_material(DemCtx*, const char* what, uint32_t i, uint32_t j);
+int fake_anal_type(DemCtx*, uint32_t k);
+uint32_t fake_anal_owner(DemCtx*, uint32_t k);
+const float* fake_anal_pos(DemCtx*, uint32_t k);
+const float* fake_anal_dir(DemCtx*, uint32_t k);
+float fake_anal_size(DemCtx*, uint32_t k);
+uint8_t fake_owner_family(DemCtx*, uint32_t o);
 }
 
 static void expect(bool cond, const char* what, int line) {
@@ -310,6 +317,88 @@ int main(int argc, char** argv) {
         EXPECT(throws([&] { sim.ChangeFamilyWhen(0, 1, "return Z < 0;"); }, "runtime compilation"));
         EXPECT(throws([&] { sim.CorrectFamilyLinVel(0, "1", "none", "none"); }, "run-time"));
         puts("ok controls");
+    }
+
+    {  // ---- a second solver: material pair tables, analytical components, restart contacts, UpdateClumps ----
+        DEMSolver sim2;
+        DemCtx* f2 = fake_last_ctx();
+        EXPECT(f2 != fake);
+        sim2.SetVerbosity(QUIET);
+        auto m1 = sim2.LoadMaterial({{"E", 1e8f}, {"nu", 0.3f}, {"CoR", 0.4f}, {"mu", 0.2f}, {"Crr", 0.0f}});
+        auto m2 = sim2.LoadMaterial({{"E", 2e8f}, {"nu", 0.2f}, {"CoR", 0.8f}, {"mu", 0.6f}, {"Crr", 0.1f}});
+        sim2.SetMaterialPropertyPair("CoR", m1, m2, 0.9f);
+        auto b1 = sim2.LoadSphereType(1.f, 0.05f, m1);
+        auto b2 = sim2.LoadSphereType(4.f, 0.1f, m2);
+        sim2.InstructBoxDomainDimension(4, 4, 4);
+        sim2.InstructBoxDomainBoundingBC("all", m2);
+        auto first = sim2.AddClumps(b1, std::vector<float3>{make_float3(0, 0, 0), make_float3(0.1f, 0, 0)});
+        first->SetExistingContacts({{0, 1}});
+        first->SetExistingContactWildcards({{"delta_tan_x", {1e-5f}}, {"delta_tan_y", {2e-5f}}, {"delta_tan_z", {3e-5f}}, {"delta_time", {0.5f}}});
+        auto second = sim2.AddClumps(b2, make_float3(1, 1, 1));
+        second->SetFamily(4);
+        auto can = sim2.AddExternalObject();
+        can->AddCylinder(make_float3(0, 0, 0), make_float3(0, 0, 2), 1.5f, m1, ENTITY_NORMAL_INWARD);
+        can->AddPlane(make_float3(0, 0, -1), make_float3(0, 0, 3), m1);
+        can->SetFamily(20);
+        sim2.SetFamilyFixed(20);
+        auto can_tracker = sim2.Track(can);
+        auto first_tracker = sim2.Track(first);
+        sim2.SetInitTimeStep(1e-5);
+        sim2.SetCDUpdateFreq(15);
+        sim2.UseAdaptiveUpdateFreq(false);
+        sim2.Initialize();
+        // materials: pairwise properties default to the mean unless set (APIPrivate.cpp:1944 of the reference)
+        EXPECT(close(fake_material(f2, "E", 1, 0), 2e8) && close(fake_material(f2, "nu", 0, 0), 0.3));
+        EXPECT(close(fake_material(f2, "CoR", 0, 0), 0.4) && close(fake_material(f2, "CoR", 0, 1), 0.9) && close(fake_material(f2, "CoR", 1, 0), 0.9));
+        EXPECT(close(fake_material(f2, "mu", 0, 1), 0.4) && close(fake_material(f2, "Crr", 1, 0), 0.05) && close(fake_material(f2, "Crr", 1, 1), 0.1));
+        // analytical components: the user's cylinder and plane (normals normalised), then the six planes of the box
+        EXPECT(fake_num_anal(f2) == 2 + 6 && fake_anal_type(f2, 0) == DEM_ANAL_CYL_INF && fake_anal_type(f2, 1) == DEM_ANAL_PLANE);
+        EXPECT(close(fake_anal_dir(f2, 0)[2], 1) && close(fake_anal_size(f2, 0), 1.5) && close(fake_anal_dir(f2, 1)[2], 1) && close(fake_anal_pos(f2, 1)[2], -1));
+        EXPECT(fake_anal_owner(f2, 0) == 3 && fake_anal_owner(f2, 1) == 3 && fake_anal_owner(f2, 2) == 4 && fake_anal_owner(f2, 7) == 4);
+        int up = 0, down = 0;
+        for (uint32_t k = 2; k < 8; k++) {
+            EXPECT(fake_anal_type(f2, k) == DEM_ANAL_PLANE);
+            up += fake_anal_dir(f2, k)[2] > 0.5f && close(fake_anal_pos(f2, k)[2], -2);
+            down += fake_anal_dir(f2, k)[2] < -0.5f && close(fake_anal_pos(f2, k)[2], 2);
+        }
+        EXPECT(up == 1 && down == 1);
+        EXPECT(fake_owner_family(f2, 3) == 20 && fake_owner_family(f2, 4) == RESERVED_FAMILY_NUM && can_tracker->GetOwnerID() == 3);
+        EXPECT(fake_params(f2)->cd_update_freq == 15 && fake_option(f2, "adaptive_update_freq", -1) == 0.0);
+        // the restart contacts went in as the history source of the first rebuild
+        EXPECT(fake_num_set_contacts(f2) == 1 && fake_num_contacts_set(f2) == 1);
+        EXPECT(fake_set_contact(f2, 0)->a == 0 && fake_set_contact(f2, 0)->b == 1 && fake_set_contact(f2, 0)->type == DEM_CNT_SPHERE_SPHERE);
+        EXPECT(close(fake_set_contact(f2, 0)->wc[1], 2e-5) && close(fake_set_contact(f2, 0)->wc[3], 0.5));
+
+        // ... the run goes on: things move, contacts exist; then more clumps are added on the fly
+        const float wc[4] = {1e-4f, 0, 0, 0.75f}, fz[3] = {0, 0, 1}, pt[3] = {0.05f, 0, 0};
+        fake_add_contact(f2, 0, 1, DEM_CNT_SPHERE_SPHERE, wc, fz, pt);
+        fake_add_contact(f2, 2, 0, DEM_CNT_SPHERE_CYL, wc, fz, pt);
+        sim2.DoDynamics(5e-5);
+        first_tracker->SetPos(make_float3(0.3f, 0.2f, 0.1f), 1);
+        first_tracker->SetVel(make_float3(-1, -2, -3), 1);
+        first_tracker->SetFamily(11, 1);
+        const double t_before = sim2.GetSimTime();
+        auto late = sim2.AddClumps(b2, std::vector<float3>{make_float3(-1, -1, 1), make_float3(-1, 1, 1)});
+        late->SetFamily(5);
+        late->SetVel(make_float3(0, 0, -1));
+        auto late_tracker = sim2.Track(late);
+        sim2.UpdateClumps();
+        // the newcomers are numbered right behind the existing clumps; everything that was there keeps its state
+        EXPECT(sim2.GetNumClumps() == 5 && sim2.GetNumOwners() == 7 && fake_num_owners(f2) == 7 && fake_num_spheres(f2) == 5);
+        EXPECT(close(first_tracker->Pos(1).x, 0.3) && close(first_tracker->Vel(1).z, -3) && first_tracker->GetFamily(1) == 11);
+        EXPECT(late_tracker->GetOwnerID(0) == 3 && close(late_tracker->Pos(1).y, 1) && close(late_tracker->Vel(0).z, -1) && late_tracker->GetFamily(1) == 5);
+        EXPECT(can_tracker->GetOwnerID() == 5 && fake_owner_family(f2, 5) == 20 && fake_anal_owner(f2, 0) == 5 && fake_anal_owner(f2, 2) == 6);
+        EXPECT(close(sim2.GetSimTime(), t_before, 1e-12));
+        // and the contact list of before went back in, pair by pair, with its history
+        EXPECT(fake_num_set_contacts(f2) == 2 && fake_num_contacts_set(f2) == 2);
+        bool ss = false, cyl = false;
+        for (uint32_t i = 0; i < 2; i++) {
+            const FakeContact* k = fake_set_contact(f2, i);
+            ss = ss || (k->type == DEM_CNT_SPHERE_SPHERE && k->a == 0 && k->b == 1 && close(k->wc[3], 0.75));
+            cyl = cyl || (k->type == DEM_CNT_SPHERE_CYL && k->a == 2 && k->b == 0 && close(k->wc[0], 1e-4));
+        }
+        EXPECT(ss && cyl);
+        puts("ok second_solver");
     }
     return 0;
 }

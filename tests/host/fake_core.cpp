@@ -26,8 +26,10 @@ struct DemCtx {
     // what was uploaded
     std::vector<float> radii, relX, relY, relZ, mass, moiX, moiY, moiZ;
     uint32_t nMat = 0;
-    std::vector<float> Crr;
+    std::vector<float> E, nu, CoR, mu, Crr;
     std::vector<uint32_t> analOwner;
+    std::vector<uint8_t> analType;
+    std::vector<float> analNormalSign, analPos, analDir, analSize1;
     std::vector<uint8_t> masks;
     std::vector<float> extra;
     std::vector<DemPrescription> presc;
@@ -97,6 +99,19 @@ double fake_option(DemCtx* c, const char* name, double missing) {
 }
 const float* fake_added_acc(DemCtx* c) { return c->added_acc.data(); }
 const FakeContact* fake_set_contact(DemCtx* c, uint32_t i) { return &c->contacts_set.at(i); }
+float fake_material(DemCtx* c, const char* what, uint32_t i, uint32_t j) {
+    const std::string w = what;
+    if (w == "E") return c->E.at(i);
+    if (w == "nu") return c->nu.at(i);
+    const std::vector<float>& t = (w == "CoR") ? c->CoR : (w == "mu" ? c->mu : c->Crr);
+    return t.at((size_t)i * c->nMat + j);
+}
+int fake_anal_type(DemCtx* c, uint32_t k) { return c->analType.at(k); }
+uint32_t fake_anal_owner(DemCtx* c, uint32_t k) { return c->analOwner.at(k); }
+const float* fake_anal_pos(DemCtx* c, uint32_t k) { return &c->analPos.at(3 * k); }
+const float* fake_anal_dir(DemCtx* c, uint32_t k) { return &c->analDir.at(3 * k); }
+float fake_anal_size(DemCtx* c, uint32_t k) { return c->analSize1.at(k); }
+uint8_t fake_owner_family(DemCtx* c, uint32_t o) { return c->family.at(o); }
 uint32_t fake_num_contacts_set(DemCtx* c) { return (uint32_t)c->contacts_set.size(); }
 
 // ---- the ABI ----
@@ -128,15 +143,27 @@ int dem_upload_templates(DemCtx* c, uint32_t nComp, const float* radii, const fl
     c->moiY.assign(moiY, moiY + nMassProps); c->moiZ.assign(moiZ, moiZ + nMassProps);
     return DEM_OK;
 }
-int dem_upload_materials(DemCtx* c, uint32_t nMat, const float*, const float*, const float*, const float*, const float* Crr) {
+int dem_upload_materials(DemCtx* c, uint32_t nMat, const float* E, const float* nu, const float* CoR, const float* mu,
+                         const float* Crr) {
     c->nMat = nMat;
+    c->E.assign(E, E + nMat); c->nu.assign(nu, nu + nMat);
+    c->CoR.assign(CoR, CoR + (size_t)nMat * nMat); c->mu.assign(mu, mu + (size_t)nMat * nMat);
     c->Crr.assign(Crr, Crr + (size_t)nMat * nMat);
     return DEM_OK;
 }
-int dem_upload_analytical(DemCtx* c, uint32_t nAnal, const uint32_t* objOwner, const uint8_t*, const uint16_t*, const float*,
-                          const float*, const float*, const float*, const float*, const float*, const float*, const float*,
-                          const float*, const float*, const float*) {
+int dem_upload_analytical(DemCtx* c, uint32_t nAnal, const uint32_t* objOwner, const uint8_t* objType, const uint16_t*,
+                          const float* objNormal, const float* relPosX, const float* relPosY, const float* relPosZ,
+                          const float* rotX, const float* rotY, const float* rotZ, const float* size1, const float*, const float*,
+                          const float*) {
     c->analOwner.assign(objOwner, objOwner + nAnal);
+    c->analType.assign(objType, objType + nAnal);
+    c->analNormalSign.assign(objNormal, objNormal + nAnal);
+    c->analSize1.assign(size1, size1 + nAnal);
+    c->analPos.clear(); c->analDir.clear();
+    for (uint32_t i = 0; i < nAnal; i++) {
+        c->analPos.insert(c->analPos.end(), {relPosX[i], relPosY[i], relPosZ[i]});
+        c->analDir.insert(c->analDir.end(), {rotX[i], rotY[i], rotZ[i]});
+    }
     return DEM_OK;
 }
 int dem_upload_families(DemCtx* c, const uint8_t* masks, const float* extra, const DemPrescription* presc) {

@@ -4,7 +4,9 @@ and computes no physics -- it is not a CPU path of the product, and nothing outs
 facade's own host logic, under AddressSanitizer / UBSan: the flattening Initialize() does (owner / sphere / facet / family
 tables as the reference's dT::populateEntityArrays lays them out, dT.cpp:638-1024), the step-count rule of DoDynamics, the
 clump / sphere / contact / mesh file writers with the reference's columns (dT.cpp:1254-1936), the detailed contact read-out
-(normals, owners, families), contact-wildcard edits, persistent-contact marks, region inspectors, trackers."""
+(normals, owners, families), contact-wildcard edits, persistent-contact marks, region inspectors, trackers, material
+pair tables, analytical components and the bounding box, restart contacts, UpdateClumps (state and contact list carried over,
+owners renumbered)."""
 import os
 import subprocess
 
@@ -28,7 +30,7 @@ def test_facade_host_logic_over_the_recording_fake(built, tmp_path):
     r = subprocess.run([exe, str(tmp_path)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr[-3000:]
     assert r.stdout.split() == ["ok", "initialize", "ok", "stepping", "ok", "contact_readout", "ok", "files", "ok",
-                                "wildcards_persistence", "ok", "inspectors", "ok", "controls"]
+                                "wildcards_persistence", "ok", "inspectors", "ok", "controls", "ok", "second_solver"]
     assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-3000:]
     # the contact file as a post-processing script would read it
     with open(tmp_path / "fake_contacts.csv") as fh:
