@@ -66,25 +66,28 @@ int DEMClumpTemplate::ReadComponentFromFile(const std::string filename, const st
             cols.push_back(c);
         }
     }
+    // A column the file does not have reads as 0 for every row (the reference opens the file with ignore_missing_column,
+    // Structs.h:629-648: data/clumps/ViperWheelSimple.csv has no radii and DEMdemo_WheelSlopeSlip sets them afterwards), and
+    // the rows are APPENDED to what the template already holds.
+    const size_t none = (size_t)-1;
     auto col = [&](const std::string& id) {
         auto it = std::find(cols.begin(), cols.end(), id);
-        if (it == cols.end()) fail("Column " + id + " not found in " + filename);
-        return (size_t)(it - cols.begin());
+        return it == cols.end() ? none : (size_t)(it - cols.begin());
     };
     const size_t ix = col(x_id), iy = col(y_id), iz = col(z_id), ir = col(r_id);
-    radii.clear();
-    relPos.clear();
+    unsigned int count = 0;
     while (std::getline(f, line)) {
         if (line.empty() || line[0] == '#') continue;
         std::stringstream ss(line);
         std::string c;
         std::vector<float> v;
         while (std::getline(ss, c, ',')) v.push_back((float)std::atof(c.c_str()));
-        if (v.size() <= std::max(std::max(ix, iy), std::max(iz, ir))) continue;
-        relPos.push_back(make_float3(v[ix], v[iy], v[iz]));
-        radii.push_back(v[ir]);
+        auto at = [&](size_t i) { return (i == none || i >= v.size()) ? 0.f : v[i]; };
+        relPos.push_back(make_float3(at(ix), at(iy), at(iz)));
+        radii.push_back(at(ir));
+        count++;
     }
-    nComp = (unsigned int)radii.size();
+    nComp += count;
     return 0;
 }
 
@@ -1768,17 +1771,25 @@ void DEMSolver::WriteContactFile(const std::filesystem::path& outfilename, float
 static std::vector<std::vector<std::string>> read_csv(const std::string& fn, std::vector<std::string>& header) {
     std::ifstream f(fn);
     if (!f) fail("File " + fn + " cannot be opened.");
+    // files written on Windows end their lines with \r\n (data/clumps/ContactChain_initial.csv does); cells are trimmed
+    auto trimmed = [](std::string t) {
+        while (!t.empty() && isspace((unsigned char)t.back())) t.pop_back();
+        size_t b = 0;
+        while (b < t.size() && isspace((unsigned char)t[b])) b++;
+        return t.substr(b);
+    };
     std::string line;
     std::getline(f, line);
-    std::stringstream hs(line);
+    std::stringstream hs(trimmed(line));
     std::string c;
-    while (std::getline(hs, c, ',')) header.push_back(c);
+    while (std::getline(hs, c, ',')) header.push_back(trimmed(c));
     std::vector<std::vector<std::string>> rows;
     while (std::getline(f, line)) {
+        line = trimmed(line);
         if (line.empty()) continue;
         std::stringstream ss(line);
         std::vector<std::string> r;
-        while (std::getline(ss, c, ',')) r.push_back(c);
+        while (std::getline(ss, c, ',')) r.push_back(trimmed(c));
         rows.push_back(r);
     }
     return rows;

@@ -179,5 +179,24 @@ int main() {
         EXPECT(throws([] { DEMInspector(nullptr, "absv").SetInspectionCode("quantity[myOwner] = 1;"); }, "run time"));
         puts("ok mesh_and_templates");
     }
+    {  // input files as they come: Windows line endings, padded cells, a template file without a radius column
+        FILE* f = fopen("/tmp/facade_host_check_crlf.csv", "wb");
+        fputs("X,Y,Z, Qw,Qx,Qy,Qz,clump_type\r\n-0.6,-0,-0.01,1,0,0,0,0\r\n-0.58, 0.25 ,-0.01,1,0,0,0,1\r\n\r\n0.5,0,0,1,0,0,0,0\r\n", f);
+        fclose(f);
+        auto xyz = DEMSolver::ReadClumpXyzFromCsv("/tmp/facade_host_check_crlf.csv");
+        EXPECT(xyz.size() == 2 && xyz.at("0").size() == 2 && xyz.at("1").size() == 1 && close(xyz.at("1")[0].y, 0.25) && close(xyz.at("0")[1].x, 0.5));
+        auto quat = DEMSolver::ReadClumpQuatFromCsv("/tmp/facade_host_check_crlf.csv");
+        EXPECT(quat.at("0").size() == 2 && close(quat.at("0")[0].w, 1));
+        f = fopen("/tmp/facade_host_check_noradius.csv", "wb");
+        fputs("x,y,z\r\n1,2,3\r\n4,5,6\r\n", f);
+        fclose(f);
+        DEMClumpTemplate t;
+        t.ReadComponentFromFile("/tmp/facade_host_check_noradius.csv");  // (the reference reads with ignore_missing_column)
+        EXPECT(t.nComp == 2 && t.radii.size() == 2 && t.radii[1] == 0.f && close(t.relPos[1].y, 5));
+        t.ReadComponentFromFile("/tmp/facade_host_check_noradius.csv");  // ... and appends
+        EXPECT(t.nComp == 4 && t.relPos.size() == 4 && close(t.relPos[2].x, 1));
+        EXPECT(throws([&] { t.ReadComponentFromFile("/nonexistent/file.csv"); }, "cannot be opened"));
+        puts("ok input_files");
+    }
     return 0;
 }

@@ -207,5 +207,5 @@ def test_facade_host_side_pieces(built, tmp_path):
                     "-Wl,-rpath," + os.path.join(ROOT, "dem-engine_b200")], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
-    assert r.stdout.split("\n")[:6] == ["ok regions", "ok contact_info", "ok clump_batch", "ok force_model", "ok helpers",
-                                        "ok mesh_and_templates"]
+    assert r.stdout.split("\n")[:7] == ["ok regions", "ok contact_info", "ok clump_batch", "ok force_model", "ok helpers",
+                                        "ok mesh_and_templates", "ok input_files"]
