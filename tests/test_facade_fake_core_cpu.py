@@ -48,3 +48,41 @@ def test_fake_core_is_test_infrastructure_only():
     for fn in ("bench.py", "__graft_entry__.py"):
         with open(os.path.join(ROOT, fn)) as fh:
             assert "fake_core" not in fh.read(), fn
+
+
+REF = "/root/reference"
+QUICK_DEMOS = ["BallDrop", "Repose", "TestPack", "ContactChain", "WheelDPSimplified", "Plow"]
+
+
+def _cuda_present():
+    from conftest import _cuda_device_count
+    return _cuda_device_count() > 0
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "src", "demo")), reason="the reference tree is not present on this machine")
+@pytest.mark.parametrize("name", QUICK_DEMOS)
+def test_reference_demo_host_side_over_the_recording_fake(built, name, tmp_path):
+    """The reference's own demo script (compiled unmodified, `make refdemos`) started with the recording fake preloaded in front
+    of the real core: no physics happens, but everything the script does on the HOST side does -- samplers, template and mesh
+    loading from the reference's data files (Windows line endings, files without a radius column), flattening at Initialize(),
+    trackers, inspectors, family changes, the clump / mesh / contact files it writes every frame -- and it must reach its
+    "exiting" line without an exception.  (This is how two reader bugs were found.)"""
+    exe = os.path.join(HOST, "refdemo", "DEMdemo_" + name)
+    if not os.path.exists(exe):
+        pytest.skip("refdemo/DEMdemo_%s not built" % name)
+    fake = str(tmp_path / "libfake_demcore.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", os.path.join(ROOT, "tests", "host", "fake_core.cpp"), "-o", fake,
+                    "-L" + LIBDIR, "-ldemcore", "-Wl,-rpath," + LIBDIR], check=True)
+    # some scripts address their input as ../data/... (they expect to run from <build>/bin)
+    work = tmp_path / "bin"
+    work.mkdir()
+    os.symlink(os.path.join(REF, "data"), str(tmp_path / "data"))
+    env = dict(os.environ, LD_PRELOAD=fake, DEME_DATA_PATH=os.path.join(REF, "data"))
+    r = subprocess.run(["timeout", "120", exe], cwd=str(work), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       errors="replace")
+    tail = r.stdout[-1500:]
+    assert r.returncode == 0, (name, r.returncode, tail)
+    assert "exiting" in tail and "what():" not in r.stdout and "terminate called" not in r.stdout, tail
