@@ -51,7 +51,7 @@ def test_fake_core_is_test_infrastructure_only():
 
 
 REF = "/root/reference"
-QUICK_DEMOS = ["BallDrop", "Repose", "TestPack", "ContactChain", "WheelDPSimplified", "Plow"]
+QUICK_DEMOS = ["BallDrop", "Repose", "TestPack", "ContactChain", "WheelDPSimplified", "Plow", "FlexibleMesh"]
 
 
 def _cuda_present():
