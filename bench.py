@@ -178,7 +178,7 @@ def cpu_reference_run(n_clumps, steps, warmup, cd_update_freq, spacing, settle_s
     return done / dt, ("reference" if use_ref else "port"), cores, (
         "%d clumps (%dx%dx%d lattice, the workload's bed), %d timed steps after %d settling + %d warm-up steps on the host "
         "(%d contacts listed at the end), the reference's own force / accumulation / integration kernels on %d host "
-        "threads (contact rebuild serial)" % (f.nClumps, dims[0], dims[1], dims[2], done, settled, warmup, int(w.nContacts), cores)), done, dt, int(w.nContacts)
+        "threads (contact rebuild: the oracle's grid search spread over the same threads, merge of the sorted runs and history map serial)" % (f.nClumps, dims[0], dims[1], dims[2], done, settled, warmup, int(w.nContacts), cores)), done, dt, int(w.nContacts)
 
 
 def run_c5(args, rank, local_rank, world):

@@ -689,7 +689,27 @@ void orc_integrate(OrcWorld* w) {
 
 /* ---------- broad phase (acceptance rule of src/kernel/DEMContactKernels_SphereSphere.cu:57-89,172-214 and
  *            src/kernel/DEMBinSphereKernels.cu:78-128) + history map (src/kernel/DEMHistoryMappingKernels.cu) ---------- */
+/* Host threads of the broad phase.  Only a build with OpenMP (oracle/_ref/libdemref.so, the timed reference arm) spreads
+ * the search; liboracle.so is compiled without it and stays serial.  The candidate SET does not depend on the number of
+ * threads, and the list is sorted by (type, A, B) before it is used, so neither does any result. */
+static int g_orc_threads = 1;
+void orc_set_threads(int n) { g_orc_threads = n < 1 ? 1 : n; }
+#ifdef _OPENMP
+#define ORC_CHUNKS (g_orc_threads > 64 ? 64 : g_orc_threads)
+#else
+#define ORC_CHUNKS 1
+#endif
+
 typedef struct { uint32_t a, b; uint8_t type; } CKey;
+typedef struct { CKey* keys; size_t n, cap; } CKeyBuf;
+static inline void ckey_push(CKeyBuf* kb, uint32_t a, uint32_t b, uint8_t type) {
+    if (kb->n == kb->cap) {
+        kb->cap = kb->cap ? kb->cap * 2 : 1024;
+        kb->keys = (CKey*)realloc(kb->keys, sizeof(CKey) * kb->cap);
+    }
+    kb->keys[kb->n].a = a; kb->keys[kb->n].b = b; kb->keys[kb->n].type = type;
+    kb->n++;
+}
 static int ckey_cmp(const void* pa, const void* pb) {
     const CKey* x = (const CKey*)pa; const CKey* y = (const CKey*)pb;
     if (x->type != y->type) return x->type < y->type ? -1 : 1;
@@ -713,17 +733,14 @@ int orc_detect_contacts(OrcWorld* w) {
             if (pos[3 * s + k] > hi[k]) hi[k] = pos[3 * s + k];
         }
     }
-    size_t cap = 16 + (size_t)nS * 8, n = 0;
-    CKey* keys = (CKey*)malloc(sizeof(CKey) * cap);
-#define PUSH(A_, B_, T_)                                          \
-    do {                                                          \
-        if (n == cap) {                                           \
-            cap *= 2;                                             \
-            keys = (CKey*)realloc(keys, sizeof(CKey) * cap);      \
-        }                                                         \
-        keys[n].a = (A_); keys[n].b = (B_); keys[n].type = (T_);  \
-        n++;                                                      \
-    } while (0)
+    /* every chunk of the sphere range collects into its own buffer (one chunk, i.e. the plain serial search, without OpenMP) */
+    const int nchunk = ORC_CHUNKS;
+    CKeyBuf* kb = (CKeyBuf*)calloc((size_t)nchunk + 1, sizeof(CKeyBuf));
+    for (int b = 0; b < nchunk; b++) {
+        kb[b].cap = 16 + (size_t)nS * 8 / (size_t)nchunk;
+        kb[b].keys = (CKey*)malloc(sizeof(CKey) * kb[b].cap);
+    }
+#define PUSH(A_, B_, T_) ckey_push(mine, (A_), (B_), (T_))
 
     if (nS > 0) {
         double cs = 2.0 * (double)rmax * 1.0001 + 1e-30;
@@ -755,7 +772,14 @@ int orc_detect_contacts(OrcWorld* w) {
         memcpy(fill, cstart, sizeof(uint32_t) * ncell);
         for (uint32_t s = 0; s < nS; s++) order[fill[cellOf[s]]++] = s;
         free(fill);
-        for (uint32_t A = 0; A < nS; A++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nchunk)
+#endif
+        for (int ch = 0; ch < nchunk; ch++) {
+        CKeyBuf* mine = &kb[ch];
+        const uint32_t A0 = (uint32_t)((uint64_t)nS * (uint64_t)ch / (uint64_t)nchunk);
+        const uint32_t A1 = (uint32_t)((uint64_t)nS * (uint64_t)(ch + 1) / (uint64_t)nchunk);
+        for (uint32_t A = A0; A < A1; A++) {
             long cx = cellOf[A] % nb[0], cy = (cellOf[A] / nb[0]) % nb[1], cz = cellOf[A] / (nb[0] * nb[1]);
             uint32_t oA = w->ownerClumpBody[A];
             unsigned famA = w->familyID[oA];
@@ -781,10 +805,18 @@ int orc_detect_contacts(OrcWorld* w) {
                         }
                     }
         }
+        }
         free(cstart); free(cellOf); free(order);
     }
     /* sphere--analytical, src/kernel/DEMBinSphereKernels.cu:78-128 */
-    for (uint32_t s = 0; s < nS && w->nAnal > 0; s++) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nchunk)
+#endif
+    for (int ch = 0; ch < nchunk; ch++) {
+    CKeyBuf* mine = &kb[ch];
+    const uint32_t s0 = (uint32_t)((uint64_t)nS * (uint64_t)ch / (uint64_t)nchunk);
+    const uint32_t s1 = (uint32_t)((uint64_t)nS * (uint64_t)(ch + 1) / (uint64_t)nchunk);
+    for (uint32_t s = s0; s < s1 && w->nAnal > 0; s++) {
         uint32_t oS = w->ownerClumpBody[s];
         unsigned famS = w->familyID[oS];
         unsigned c = w->clumpComponentOffset[s];
@@ -813,12 +845,14 @@ int orc_detect_contacts(OrcWorld* w) {
             if (t && depth > thr) PUSH(s, ob, (uint8_t)t);
         }
     }
+    }
     /* sphere--triangle.  The reference sandwiches each facet between two offset copies, bins them and tests the
      * inflated sphere against both copies with a one-sided test (src/kernel/DEMBinTriangleKernels.cu:22-221,
      * src/kernel/DEMContactKernels_SphereTriangle.cu:196-262); which non-touching pairs that admits depends on its bin
      * size.  What the force pass needs is every pair that can come within one radius of the facet before the next
      * rebuild, so the restated rule is geometric: distance(centre, facet) < r + margin(sphere) + margin(mesh), less the
      * smaller family extra margin (same shallow-contact drop as :238-247). */
+    CKeyBuf* mine = &kb[nchunk];
     for (uint32_t t = 0; t < w->nTri && nS > 0; t++) {
         uint32_t oT = w->ownerMesh[t];
         unsigned famT = w->familyID[oT];
@@ -860,7 +894,34 @@ int orc_detect_contacts(OrcWorld* w) {
     }
 #undef PUSH
     free(pos); free(rad);
-    qsort(keys, n, sizeof(CKey), ckey_cmp);
+    /* one list sorted by (type, A, B): every buffer is sorted on its own (in parallel where there are threads), then merged */
+    size_t n = 0;
+    for (int b = 0; b <= nchunk; b++) n += kb[b].n;
+    CKey* keys = (CKey*)malloc(sizeof(CKey) * (n ? n : 1));
+    if (nchunk == 1) {
+        n = 0;
+        for (int b = 0; b <= nchunk; b++) {
+            if (kb[b].n) memcpy(keys + n, kb[b].keys, sizeof(CKey) * kb[b].n);
+            n += kb[b].n;
+        }
+        qsort(keys, n, sizeof(CKey), ckey_cmp);  /* (the serial search: one sort of everything, as before) */
+    } else {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static, 1) num_threads(nchunk)
+#endif
+        for (int b = 0; b <= nchunk; b++)
+            if (kb[b].n) qsort(kb[b].keys, kb[b].n, sizeof(CKey), ckey_cmp);
+        size_t* head = (size_t*)calloc((size_t)nchunk + 1, sizeof(size_t));
+        for (size_t i = 0; i < n; i++) {
+            int best = -1;
+            for (int b = 0; b <= nchunk; b++)
+                if (head[b] < kb[b].n && (best < 0 || ckey_cmp(&kb[b].keys[head[b]], &kb[best].keys[head[best]]) < 0)) best = b;
+            keys[i] = kb[best].keys[head[best]++];
+        }
+        free(head);
+    }
+    for (int b = 0; b <= nchunk; b++) free(kb[b].keys);
+    free(kb);
     if (n > w->contactCapacity) { free(keys); return -1; }
 
     /* history carry-over: both lists sorted by (type,A,B) => merge */

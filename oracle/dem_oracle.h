@@ -165,6 +165,8 @@ void orc_compute_margins(OrcWorld* w, uint32_t maxDrift);
 
 /* broad phase + history: rebuilds w->contacts, carrying wildcards over */
 int orc_detect_contacts(OrcWorld* w);
+/* host threads of the broad phase (effective only in a build with OpenMP, i.e. oracle/_ref; results do not depend on it) */
+void orc_set_threads(int n);
 
 /* A.3-A.5 per-contact force;  A.6 accumulation;  A.7 integration */
 void orc_prepare_acc(OrcWorld* w);

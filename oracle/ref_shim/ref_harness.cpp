@@ -205,7 +205,7 @@ void launch(size_t n, unsigned block, F&& body) {
 extern "C" {
 
 /* number of host threads the kernels are spread over (1 = serial and deterministic) */
-void ref_set_threads(int n) { g_threads = n < 1 ? 1 : n; }
+void ref_set_threads(int n) { g_threads = n < 1 ? 1 : n; orc_set_threads(g_threads); }
 
 void ref_prepare_acc(OrcWorld* w) {
     Bound b; bind(w, b);

@@ -374,3 +374,31 @@ def test_random_scenes_bit_exact_vs_reference_kernels(built, seed):
     n = a.nContacts
     for name in ("contactForces", "contactTorque_convToForce", "contactPointGeometryA", "contactPointGeometryB"):
         assert np.array_equal(getattr(a, name)[: 3 * n].view("u4"), getattr(b, name)[: 3 * n].view("u4")), name
+
+
+@needs_ref
+@pytest.mark.parametrize("threads", [2, 5, 16])
+@pytest.mark.parametrize("kind", ["clumps_full", "mesh_tray", "cylinder", "families"])
+def test_threaded_broad_phase_lists_the_same_contacts(built, kind, threads):
+    """The reference arm of bench.py spreads the oracle's broad phase over the host cores (orc_set_threads; only the OpenMP build
+    inside oracle/_ref does): the sphere range is cut into chunks -- also in the middle of a clump --, every chunk is searched and
+    sorted on its own, the sorted runs are merged.  The list (pairs, types, carried history words) must be the serial one, entry
+    by entry, whatever the number of threads."""
+    f = scenes.flatten(_scene(kind))
+    a = pyoracle.world_from_flat(f)
+    a.step(1500, cd_every=f.cd_update_freq)              # a bed with live contact history
+    assert a.nContacts > 0 and max(np.abs(a.contactWildcards[k][: a.nContacts]).max() for k in range(4)) > 0
+    a.compute_margins(f.cd_update_freq)
+    b = a.copy()
+    assert a._call(pyoracle.lib().orc_detect_contacts) == 0
+    try:
+        pyoracle.ref_set_threads(threads)
+        assert b._call(pyoracle.ref().orc_detect_contacts) == 0
+    finally:
+        pyoracle.ref_set_threads(1)
+    n = a.nContacts
+    assert n == b.nContacts and n > 0
+    for name in ("idGeometryA", "idGeometryB", "contactType"):
+        assert np.array_equal(getattr(a, name)[:n], getattr(b, name)[:n]), name
+    for k in range(4):
+        assert np.array_equal(a.contactWildcards[k][:n].view("u4"), b.contactWildcards[k][:n].view("u4")), "wildcard %d" % k
