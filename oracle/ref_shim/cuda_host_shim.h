@@ -3,9 +3,11 @@
  *
  * Lets g++ compile the reference's per-thread CUDA kernel TEXT (src/kernel/*.cu of /root/reference)
  * as ordinary host C++, so that the reference's own arithmetic can be executed on the CPU and used
- * to pin oracle/dem_oracle.c.  Only kernels without intra-block cooperation are ever *called*
- * through this shim (one "thread" at a time); kernels that use __shared__/__syncthreads compile
- * but are never launched.
+ * to pin oracle/dem_oracle.c.  Kernels without intra-block cooperation are called one "thread" at
+ * a time.  Block-cooperative kernels (__shared__ + __syncthreads: the per-bin contact sweeps) run one
+ * block at a time with every CUDA thread of the block on its own fiber (ref_harness.cpp: launch_coop):
+ * __shared__ becomes a static (blocks run one after the other), __syncthreads hands control to the
+ * block's scheduler, which resumes the fibers only once all of them have arrived.
  */
 #ifndef DEM_CUDA_HOST_SHIM_H
 #define DEM_CUDA_HOST_SHIM_H
@@ -19,9 +21,9 @@
 #ifndef __global__
 #define __global__
 #endif
-#ifndef __shared__
+/* (cuda_runtime.h defines __shared__ as nothing for a host compiler, which would make the arrays per-fiber locals) */
+#undef __shared__
 #define __shared__ static
-#endif
 #ifndef __constant__
 #define __constant__
 #endif
@@ -34,7 +36,10 @@ static thread_local ShimDim3 shim_blockIdx = {0, 0, 0}, shim_blockDim = {1, 1, 1
 #define blockDim shim_blockDim
 #define threadIdx shim_threadIdx
 
-static inline void __syncthreads() {}
+static thread_local void (*shim_sync_hook)() = nullptr; /* set by launch_coop for the duration of a cooperative launch */
+static inline void __syncthreads() {
+    if (shim_sync_hook) shim_sync_hook();
+}
 static inline void __threadfence() {}
 /* atomicAdd(float*): a real atomic (CAS loop) so that the harness may run the per-thread kernels on several host
  * threads; with one thread it degenerates to a plain add in program order (used by the bit-exactness tests). */

@@ -7,7 +7,7 @@
  * C restatement (dem_oracle.c) and to generate tests/golden/*.npz, and by bench.py as the
  * cpu_baseline kind "reference".
  *
- * Kernels executed through this harness (all strictly per-thread, no intra-block cooperation):
+ * Kernels executed through this harness, per thread:
  *   calculateContactForces   src/kernel/DEMCalcForceKernels.cu:44
  *   forceToAcc               src/kernel/DEMCollectForceKernels_Compact.cu:13
  *   prepareAccArrays / prepareForceArrays   src/kernel/DEMPrepForceKernels.cu:32,39
@@ -16,6 +16,8 @@
  *   getNumberOfBinsEachSphereTouches / populateBinSphereTouchingPairs   src/kernel/DEMBinSphereKernels.cu:11,133
  *   makeTriangleSandwich / getNumberOfBinsEachTriangleTouches / populateBinTriangleTouchingPairs
  *                            src/kernel/DEMBinTriangleKernels.cu:22,87,139 (with DEMTriangleBoxIntersect.cu)
+ * block-cooperative (every CUDA thread of a block on its own fiber, launch_coop below):
+ *   getNumberOfSphereContactsEachBin / populateSphSphContactPairsEachBin   src/kernel/DEMContactKernels_SphereSphere.cu:91,267
  * plus the device functions calcContactPoint (src/kernel/DEMContactKernels_SphereSphere.cu:57), fillSharedMemSpheres /
  * fillSharedMemTriangles (src/kernel/DEMContactKernels_SphereTriangle.cu:16,75), triangle_sphere_CD_directional and
  * snap_to_face (src/kernel/DEMCollisionKernels.cu).
@@ -26,6 +28,8 @@
 #include <utility>
 #include <vector>
 #include <cstring>
+#include <functional>
+#include <ucontext.h>
 
 #include "../dem_oracle.h"
 
@@ -200,6 +204,62 @@ void launch(size_t n, unsigned block, F&& body) {
     }
 }
 
+/* A block-cooperative launch: the blocks run one after the other; the `block` CUDA threads of a block are fibers
+ * (ucontext) on this host thread, run round-robin from barrier to barrier -- __syncthreads (cuda_host_shim.h) parks the
+ * calling fiber, and the next round starts only when every fiber that has not returned is parked, which is the CUDA rule.
+ * Deterministic: fiber t always runs before fiber t + 1 between two barriers. */
+struct Coop {
+    ucontext_t sched;
+    std::vector<ucontext_t> ctx;
+    std::vector<char> done;
+    unsigned cur = 0;
+    const std::function<void()>* body = nullptr;
+};
+thread_local Coop* g_coop = nullptr;
+void coop_barrier() {
+    Coop* c = g_coop;
+    swapcontext(&c->ctx[c->cur], &c->sched);
+}
+void coop_entry() {
+    Coop* c = g_coop;
+    (*c->body)();
+    c->done[c->cur] = 1;  // (uc_link takes the fiber back to the scheduler)
+}
+void launch_coop(size_t nBlocks, unsigned block, const std::function<void()>& body) {
+    const size_t STACK = 128 * 1024;
+    Coop c;
+    c.body = &body;
+    c.ctx.resize(block);
+    c.done.assign(block, 0);
+    std::vector<char> stacks(STACK * block);
+    g_coop = &c;
+    shim_sync_hook = coop_barrier;
+    shim_blockDim.x = block;
+    for (size_t b = 0; b < nBlocks; b++) {
+        shim_blockIdx.x = (unsigned)b;
+        for (unsigned t = 0; t < block; t++) {
+            getcontext(&c.ctx[t]);
+            c.ctx[t].uc_stack.ss_sp = stacks.data() + STACK * t;
+            c.ctx[t].uc_stack.ss_size = STACK;
+            c.ctx[t].uc_link = &c.sched;
+            makecontext(&c.ctx[t], coop_entry, 0);
+            c.done[t] = 0;
+        }
+        unsigned remaining = block;
+        while (remaining)
+            for (unsigned t = 0; t < block; t++)
+                if (!c.done[t]) {
+                    c.cur = t;
+                    shim_threadIdx.x = t;
+                    swapcontext(&c.sched, &c.ctx[t]);
+                    if (c.done[t]) remaining--;
+                }
+    }
+    shim_sync_hook = nullptr;
+    g_coop = nullptr;
+    shim_threadIdx.x = 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -286,6 +346,86 @@ long ref_sphere_anal_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_
     if (cnt > cap) return -1;
     for (long i = 0; i < cnt; i++) {
         outSphere[i] = idA[i]; outObj[i] = idB[i]; outType[i] = ct[i];
+    }
+    return cnt;
+}
+
+/* Sphere--sphere contact pairs as the reference finds them (contactDetection(), src/algorithms/
+ * DEMCubContactDetection.cu:95-250 and :455-566): sphere -> bin registration through the reference's two per-thread
+ * kernels, the glue its CUB calls do (stable sort of the (bin, sphere) pairs by bin, run-length encode, scans) restated
+ * with the standard library, then the reference's OWN block-cooperative per-bin sweeps
+ * getNumberOfSphereContactsEachBin / populateSphSphContactPairsEachBin (src/kernel/DEMContactKernels_SphereSphere.cu:
+ * 91-265, 267-440) with DEME_KT_CD_NTHREADS_PER_BLOCK threads per bin, on fibers (launch_coop).
+ * Returns the number of pairs written, or -1 if cap is too small; stats[0] = active bins, stats[1] = most spheres in a
+ * bin, stats[2] = contact slots the count pass reserved (>= pairs written). */
+long ref_sphere_sphere_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_t nbY, uint32_t nbZ, uint32_t* outA,
+                                uint32_t* outB, long cap, uint64_t* stats) {
+    Bound b; bind(w, b);
+    b.sp.binSize = binSize; b.sp.nbX = nbX; b.sp.nbY = nbY; b.sp.nbZ = nbZ;
+    b.sp.errOutBinSphNum = 32768;  // the reference's default allowance (SetMaxSphereInBin)
+    const uint32_t n = w->nSpheres;
+    std::vector<deme::binsSphereTouches_t> nb(n + 1, 0);
+    std::vector<deme::objID_t> na(n + 1, 0);
+    launch(n, 1024, [&] { ref_bin::getNumberOfBinsEachSphereTouches(&b.sp, &b.kt, nb.data(), na.data()); });
+    std::vector<deme::binSphereTouchPairs_t> nbScan(n + 1, 0), naScan(n + 1, 0);
+    for (uint32_t i = 0; i < n; i++) {
+        nbScan[i + 1] = nbScan[i] + nb[i];
+        naScan[i + 1] = naScan[i] + na[i];
+    }
+    const size_t nPairs = nbScan[n];
+    std::vector<deme::binID_t> binIDs(nPairs + 1);
+    std::vector<deme::bodyID_t> sphIDs(nPairs + 1);
+    std::vector<deme::bodyID_t> idA(naScan[n] + 1), idB(naScan[n] + 1);
+    std::vector<deme::contact_t> ct(naScan[n] + 1);
+    launch(n, 1024, [&] {
+        ref_bin::populateBinSphereTouchingPairs(&b.sp, &b.kt, nbScan.data(), naScan.data(), binIDs.data(),
+                                                sphIDs.data(), idA.data(), idB.data(), ct.data());
+    });
+    // cubDEMSortByKeys (a stable radix sort): by bin, spheres of a bin in the order they were written
+    std::vector<size_t> order(nPairs);
+    for (size_t i = 0; i < nPairs; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return binIDs[x] < binIDs[y]; });
+    std::vector<deme::bodyID_t> sphSorted(nPairs + 1);
+    std::vector<deme::binID_t> activeBinIDs;
+    std::vector<deme::spheresBinTouches_t> numSpheresBinTouches;
+    for (size_t i = 0; i < nPairs; i++) {
+        sphSorted[i] = sphIDs[order[i]];
+        const deme::binID_t bin = binIDs[order[i]];
+        if (activeBinIDs.empty() || activeBinIDs.back() != bin) {  // cubDEMRunLengthEncode
+            activeBinIDs.push_back(bin);
+            numSpheresBinTouches.push_back(0);
+        }
+        numSpheresBinTouches.back()++;
+    }
+    const size_t nActive = activeBinIDs.size();
+    std::vector<deme::binSphereTouchPairs_t> lookUp(nActive + 1, 0);  // cubDEMPrefixScan (exclusive)
+    uint64_t most = 0;
+    for (size_t i = 0; i < nActive; i++) {
+        lookUp[i + 1] = lookUp[i] + numSpheresBinTouches[i];
+        if (numSpheresBinTouches[i] > most) most = numSpheresBinTouches[i];
+    }
+    std::vector<deme::binContactPairs_t> numCnt(nActive + 1, 0);
+    launch_coop(nActive, DEME_KT_CD_NTHREADS_PER_BLOCK, [&] {
+        ref_css::getNumberOfSphereContactsEachBin(&b.sp, &b.kt, sphSorted.data(), activeBinIDs.data(),
+                                                  numSpheresBinTouches.data(), lookUp.data(), numCnt.data(), nActive);
+    });
+    std::vector<deme::contactPairs_t> offsets(nActive + 1, 0);
+    for (size_t i = 0; i < nActive; i++) offsets[i + 1] = offsets[i] + numCnt[i];
+    const size_t nSlots = offsets[nActive];
+    std::vector<deme::bodyID_t> cA(nSlots + 1), cB(nSlots + 1);
+    std::vector<deme::contact_t> cT(nSlots + 1, deme::NOT_A_CONTACT);
+    launch_coop(nActive, DEME_KT_CD_NTHREADS_PER_BLOCK, [&] {
+        ref_css::populateSphSphContactPairsEachBin(&b.sp, &b.kt, sphSorted.data(), activeBinIDs.data(),
+                                                   numSpheresBinTouches.data(), lookUp.data(), offsets.data(), cA.data(),
+                                                   cB.data(), cT.data(), nActive);
+    });
+    if (stats) { stats[0] = nActive; stats[1] = most; stats[2] = nSlots; }
+    long cnt = 0;
+    for (size_t i = 0; i < nSlots; i++) {
+        if (cT[i] == deme::NOT_A_CONTACT) continue;
+        if (cnt >= cap) return -1;
+        outA[cnt] = cA[i]; outB[cnt] = cB[i];
+        cnt++;
     }
     return cnt;
 }
@@ -462,8 +602,9 @@ void ref_voxel_encode(OrcWorld* w, const double xyz[3], uint64_t* voxel, uint16_
     *voxel = id;
 }
 
-/* hot loop: reference kernels for force/accumulate/integrate, oracle's broad phase for the rebuild
- * (the reference's sweep kernels are block-cooperative and cannot run through the shim). */
+/* hot loop: reference kernels for force/accumulate/integrate, oracle's broad phase for the rebuild (its list is the one the
+ * reference's own sweep kernels produce, pair for pair: ref_sphere_sphere_contacts and the test that compares them; the sweeps
+ * themselves run on fibers, far too slowly for a loop like this one). */
 int ref_step(OrcWorld* w, uint32_t nsteps, uint32_t cd_every, uint64_t* step_counter) {
     if (cd_every < 1) cd_every = 1;
     for (uint32_t s = 0; s < nsteps; s++) {

@@ -402,3 +402,58 @@ def test_threaded_broad_phase_lists_the_same_contacts(built, kind, threads):
         assert np.array_equal(getattr(a, name)[:n], getattr(b, name)[:n]), name
     for k in range(4):
         assert np.array_equal(a.contactWildcards[k][:n].view("u4"), b.contactWildcards[k][:n].view("u4")), "wildcard %d" % k
+
+
+def _reference_sphere_sphere_sweep(w, bin_size):
+    """The reference's own per-bin sweep kernels on the world's current state (ref_sphere_sphere_contacts: the two
+    block-cooperative kernels of DEMContactKernels_SphereSphere.cu run on fibers).  Returns (pairs as a list, stats)."""
+    import ctypes as C
+    ext = [float(2 ** p) * float(w.voxelSize) for p in (w.nvXp2, w.nvYp2, w.nvZp2)]
+    nb = [int(np.ceil(e / bin_size)) for e in ext]
+    cap = 64 * w.nSpheres + 1024
+    oA, oB = np.zeros(cap, "u4"), np.zeros(cap, "u4")
+    stats = np.zeros(3, "u8")
+    s = w.struct()
+    fn = pyoracle.ref().ref_sphere_sphere_contacts
+    fn.restype = C.c_long
+    got = fn(C.byref(s), C.c_double(bin_size), C.c_uint32(nb[0]), C.c_uint32(nb[1]), C.c_uint32(nb[2]),
+             oA.ctypes.data_as(C.c_void_p), oB.ctypes.data_as(C.c_void_p), C.c_long(cap), stats.ctypes.data_as(C.c_void_p))
+    assert got >= 0
+    return [(min(a, b), max(a, b)) for a, b in zip(oA[:got].tolist(), oB[:got].tolist())], stats
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,bin_mult", [("clumps_full", 1.05), ("clumps_full", 3.0), ("clumps_roll", 1.5), ("mesh_tray", 1.05),
+                                           ("families", 2.0), ("drum", 2.0), ("drum", 30.0), ("seed101", 1.2), ("seed107", 2.5),
+                                           ("seed113", 1.05), ("seed119", 6.0)])
+def test_sphere_sphere_candidates_are_the_reference_sweeps(built, kind, bin_mult):
+    """Sphere--sphere broad phase pinned to reference code, end to end.  The reference registers spheres in bins, groups them by
+    bin and sweeps every bin with one thread block: shared-memory staging of up to 512 spheres, all pairs of the batch
+    spread over the 512 threads, the rest of a fuller bin against the batch, a pair attributed to the bin of its contact point
+    (getNumberOfSphereContactsEachBin / populateSphSphContactPairsEachBin, DEMContactKernels_SphereSphere.cu:91-440).  Those two
+    kernels run here UNCHANGED -- every CUDA thread of a block on its own fiber, __syncthreads as a real barrier -- behind the
+    reference's own sphere -> bin kernels, on states of settling beds, for several bin sizes (one of them puts all 3000 spheres
+    of the drum scene into ONE bin, which takes the batch loop and its left-over path).  The list must be the oracle's, pair for
+    pair: same-owner and family-masked pairs dropped, every pair once."""
+    if kind.startswith("seed"):
+        f = scenes.flatten(_random_scene(int(kind[4:])))
+        w = pyoracle.world_from_flat(f, contact_capacity=64 * f.nSpheres + 1024)
+    else:
+        f = scenes.flatten(_scene(kind))
+        w = pyoracle.world_from_flat(f)
+    total = 0
+    for nsteps in (600, 900, 1500):
+        w.step(nsteps, cd_every=f.cd_update_freq)
+        w.compute_margins(f.cd_update_freq)
+        w.detect_contacts()
+        idA, idB, ct, _ = w.contacts()
+        ss = ct == 1                                        # ORC_SPHERE_SPHERE (oracle/dem_oracle.h)
+        mine = sorted(zip(idA[ss].tolist(), idB[ss].tolist()))
+        rmax = float(np.max(w.Radii)) + float(np.max(w.marginSize))
+        theirs, stats = _reference_sphere_sphere_sweep(w, bin_mult * 2.0 * rmax)
+        assert len(theirs) == len(set(theirs)), "the reference attributes a pair to exactly one bin"
+        assert sorted(theirs) == mine, (len(theirs), len(mine), sorted(set(mine) ^ set(theirs))[:6])
+        assert int(stats[2]) == len(theirs), "the count pass and the fill pass of the reference agree"
+        total += len(mine)
+        print("%s step +%d: %d pairs in %d active bins (most spheres in a bin: %d)" % (kind, nsteps, len(mine), stats[0], stats[1]))
+    assert total > 0
