@@ -18,6 +18,7 @@
  *                            src/kernel/DEMBinTriangleKernels.cu:22,87,139 (with DEMTriangleBoxIntersect.cu)
  * block-cooperative (every CUDA thread of a block on its own fiber, launch_coop below):
  *   getNumberOfSphereContactsEachBin / populateSphSphContactPairsEachBin   src/kernel/DEMContactKernels_SphereSphere.cu:91,267
+ *   getNumberOfSphTriContactsEachBin / populateTriSphContactsEachBin       src/kernel/DEMContactKernels_SphereTriangle.cu:116,272
  * plus the device functions calcContactPoint (src/kernel/DEMContactKernels_SphereSphere.cu:57), fillSharedMemSpheres /
  * fillSharedMemTriangles (src/kernel/DEMContactKernels_SphereTriangle.cu:16,75), triangle_sphere_CD_directional and
  * snap_to_face (src/kernel/DEMCollisionKernels.cu).
@@ -430,11 +431,119 @@ long ref_sphere_sphere_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint3
     return cnt;
 }
 
+/* Sphere--triangle pairs through the reference's OWN block-cooperative per-bin kernels getNumberOfSphTriContactsEachBin /
+ * populateTriSphContactsEachBin (src/kernel/DEMContactKernels_SphereTriangle.cu:116-270, 272-440) on fibers, behind the same
+ * per-thread registration kernels as ref_sphere_tri_contacts below and the glue of contactDetection()
+ * (DEMCubContactDetection.cu:300-450: stable sort by bin, run-length encode, scans, hostMergeSearchMapGen).  Same outputs as
+ * ref_sphere_tri_contacts; the test holds the two against each other. */
+long ref_sphere_tri_contacts_coop(OrcWorld* w, double binSize, uint32_t nbX, uint32_t nbY, uint32_t nbZ, uint32_t* outSphere,
+                                  uint32_t* outTri, long cap) {
+    Bound b; bind(w, b);
+    b.sp.binSize = binSize; b.sp.nbX = nbX; b.sp.nbY = nbY; b.sp.nbZ = nbZ;
+    b.sp.errOutBinSphNum = 32768; b.sp.errOutBinTriNum = 32768;
+    const uint32_t nT = w->nTri, nS = w->nSpheres;
+    if (nT == 0 || nS == 0) return 0;
+    std::vector<float3> sA1(nT), sA2(nT), sA3(nT), sB1(nT), sB2(nT), sB3(nT);
+    launch(nT, 128, [&] {
+        ref_bintri::makeTriangleSandwich(&b.sp, &b.kt, sA1.data(), sA2.data(), sA3.data(), sB1.data(), sB2.data(), sB3.data());
+    });
+    std::vector<deme::binsTriangleTouches_t> ntb(nT + 1, 0);
+    launch(nT, 128, [&] {
+        ref_bintri::getNumberOfBinsEachTriangleTouches(&b.sp, &b.kt, ntb.data(), sA1.data(), sA2.data(), sA3.data(), sB1.data(),
+                                                       sB2.data(), sB3.data());
+    });
+    std::vector<deme::binsTriangleTouchPairs_t> tscan(nT + 1, 0);
+    for (uint32_t t = 0; t < nT; t++) tscan[t + 1] = tscan[t] + ntb[t];
+    std::vector<deme::binID_t> tbin(tscan[nT] + 1);
+    std::vector<deme::bodyID_t> ttri(tscan[nT] + 1);
+    launch(nT, 128, [&] {
+        ref_bintri::populateBinTriangleTouchingPairs(&b.sp, &b.kt, tscan.data(), tbin.data(), ttri.data(), sA1.data(), sA2.data(),
+                                                     sA3.data(), sB1.data(), sB2.data(), sB3.data());
+    });
+    std::vector<deme::binsSphereTouches_t> nsb(nS + 1, 0);
+    std::vector<deme::objID_t> na(nS + 1, 0);
+    launch(nS, 1024, [&] { ref_bin::getNumberOfBinsEachSphereTouches(&b.sp, &b.kt, nsb.data(), na.data()); });
+    std::vector<deme::binSphereTouchPairs_t> sscan(nS + 1, 0), ascan(nS + 1, 0);
+    for (uint32_t i = 0; i < nS; i++) {
+        sscan[i + 1] = sscan[i] + nsb[i];
+        ascan[i + 1] = ascan[i] + na[i];
+    }
+    std::vector<deme::binID_t> sbin(sscan[nS] + 1);
+    std::vector<deme::bodyID_t> ssph(sscan[nS] + 1);
+    std::vector<deme::bodyID_t> idA(ascan[nS] + 1), idB(ascan[nS] + 1);
+    std::vector<deme::contact_t> ct(ascan[nS] + 1);
+    launch(nS, 1024, [&] {
+        ref_bin::populateBinSphereTouchingPairs(&b.sp, &b.kt, sscan.data(), ascan.data(), sbin.data(), ssph.data(), idA.data(),
+                                                idB.data(), ct.data());
+    });
+    // stable sort by bin + run-length encode + exclusive scan, for spheres and for facets
+    auto group = [](const std::vector<deme::binID_t>& bins, const std::vector<deme::bodyID_t>& ids, size_t n,
+                    std::vector<deme::bodyID_t>& sorted, std::vector<deme::binID_t>& active, std::vector<uint32_t>& count,
+                    std::vector<uint32_t>& start) {
+        std::vector<size_t> order(n);
+        for (size_t i = 0; i < n; i++) order[i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](size_t x, size_t y) { return bins[x] < bins[y]; });
+        sorted.assign(n + 1, 0);
+        for (size_t i = 0; i < n; i++) {
+            sorted[i] = ids[order[i]];
+            if (active.empty() || active.back() != bins[order[i]]) { active.push_back(bins[order[i]]); count.push_back(0); }
+            count.back()++;
+        }
+        start.assign(active.size() + 1, 0);
+        for (size_t i = 0; i < active.size(); i++) start[i + 1] = start[i] + count[i];
+    };
+    std::vector<deme::bodyID_t> sphSorted, triSorted;
+    std::vector<deme::binID_t> actS, actT;
+    std::vector<uint32_t> cntS32, cntT32, startS, startT;
+    group(sbin, ssph, sscan[nS], sphSorted, actS, cntS32, startS);
+    group(tbin, ttri, tscan[nT], triSorted, actT, cntT32, startT);
+    std::vector<deme::spheresBinTouches_t> cntS(cntS32.begin(), cntS32.end());
+    std::vector<deme::trianglesBinTouches_t> cntT(cntT32.begin(), cntT32.end());
+    cntS.push_back(0); cntT.push_back(0);
+    std::vector<deme::binSphereTouchPairs_t> lookS(startS.begin(), startS.end());
+    std::vector<deme::binsTriangleTouchPairs_t> lookT(startT.begin(), startT.end());
+    const size_t nActT = actT.size();
+    std::vector<deme::binID_t> map(nActT + 1, deme::NULL_BINID);  // hostMergeSearchMapGen, HostSideHelpers.hpp:177-193
+    {
+        size_t i2 = 0;
+        for (size_t i1 = 0; i1 < nActT; i1++) {
+            while (i2 < actS.size() && actS[i2] < actT[i1]) i2++;
+            if (i2 < actS.size() && actS[i2] == actT[i1]) map[i1] = (deme::binID_t)i2;
+        }
+    }
+    actS.push_back(deme::NULL_BINID); actT.push_back(deme::NULL_BINID);
+    std::vector<deme::binContactPairs_t> numCnt(nActT + 1, 0);
+    launch_coop(nActT, DEME_KT_CD_NTHREADS_PER_BLOCK, [&] {
+        ref_cst::getNumberOfSphTriContactsEachBin(&b.sp, &b.kt, sphSorted.data(), actS.data(), cntS.data(), lookS.data(), map.data(),
+                                                  triSorted.data(), actT.data(), cntT.data(), lookT.data(), numCnt.data(),
+                                                  sA1.data(), sA2.data(), sA3.data(), sB1.data(), sB2.data(), sB3.data(), nActT);
+    });
+    std::vector<deme::contactPairs_t> offsets(nActT + 1, 0);
+    for (size_t i = 0; i < nActT; i++) offsets[i + 1] = offsets[i] + numCnt[i];
+    const size_t nSlots = offsets[nActT];
+    std::vector<deme::bodyID_t> cA(nSlots + 1), cB(nSlots + 1);
+    std::vector<deme::contact_t> cT(nSlots + 1, deme::NOT_A_CONTACT);
+    launch_coop(nActT, DEME_KT_CD_NTHREADS_PER_BLOCK, [&] {
+        ref_cst::populateTriSphContactsEachBin(&b.sp, &b.kt, sphSorted.data(), actS.data(), cntS.data(), lookS.data(), map.data(),
+                                               triSorted.data(), actT.data(), cntT.data(), lookT.data(), offsets.data(), cA.data(),
+                                               cB.data(), cT.data(), sA1.data(), sA2.data(), sA3.data(), sB1.data(), sB2.data(),
+                                               sB3.data(), nActT);
+    });
+    long cnt = 0;
+    for (size_t i = 0; i < nSlots; i++) {
+        if (cT[i] == deme::NOT_A_CONTACT) continue;
+        if (cnt >= cap) return -1;
+        outSphere[cnt] = cA[i]; outTri[cnt] = cB[i];
+        cnt++;
+    }
+    return cnt;
+}
+
 /* Sphere--triangle contact candidates as the reference finds them (contactDetection(), src/algorithms/
  * DEMCubContactDetection.cu:262-470): facet sandwich, facet -> bin and sphere -> bin registration through the reference's
  * own per-thread kernels; then, for every bin that holds both, the pair test of getNumberOfSphTriContactsEachBin
- * (src/kernel/DEMContactKernels_SphereTriangle.cu:196-262) restated around the reference's own device functions (that
- * kernel is block-cooperative: shared-memory staging + __syncthreads, it cannot run through the shim).
+ * (src/kernel/DEMContactKernels_SphereTriangle.cu:196-262) restated around the reference's own device functions (fast; the
+ * kernel itself runs in ref_sphere_tri_contacts_coop above, and a test holds the two lists against each other).
  * Returns the number of (sphere, triangle) pairs written, or -1 if cap is too small; triBins (nTri entries, may be
  * NULL) receives the number of bins each facet registered in. */
 long ref_sphere_tri_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_t nbY, uint32_t nbZ, uint32_t* outSphere,

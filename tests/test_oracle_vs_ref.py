@@ -280,6 +280,14 @@ def test_facet_candidates_against_reference_triangle_broad_phase(built, bin_mult
         assert got >= 0
         theirs = set(zip(oS[:got].tolist(), oT[:got].tolist()))
         assert got == len(theirs), "the reference attributes a pair to exactly one bin"
+        # the same through the reference's own block-cooperative per-bin kernels (getNumberOfSphTriContactsEachBin /
+        # populateTriSphContactsEachBin, unchanged, every CUDA thread of a block on its own fiber): the very same list
+        cS, cT = np.zeros(cap, "u4"), np.zeros(cap, "u4")
+        fnc = pyoracle.ref().ref_sphere_tri_contacts_coop
+        fnc.restype = C.c_long
+        gotc = fnc(C.byref(s), C.c_double(bin_size), C.c_uint32(nb[0]), C.c_uint32(nb[1]), C.c_uint32(nb[2]),
+                   cS.ctypes.data_as(C.c_void_p), cT.ctypes.data_as(C.c_void_p), C.c_long(cap))
+        assert gotc == got and set(zip(cS[:gotc].tolist(), cT[:gotc].tolist())) == theirs
         assert (tri_bins[: w.nTri] > 0).all(), "every facet lies in at least one bin"
 
         def reach(pair):  # what the margins of this rebuild promise to cover
