@@ -103,6 +103,8 @@ def main():
         f.write(subst(read(ref, "DEMMiscKernels.cu"), common))
     with open(os.path.join(out, "binsphere.inc"), "w") as f:
         f.write(subst(read(ref, "DEMBinSphereKernels.cu"), common))
+    with open(os.path.join(out, "history.inc"), "w") as f:
+        f.write(subst(read(ref, "DEMHistoryMappingKernels.cu"), common))
     with open(os.path.join(out, "contact_ss.inc"), "w") as f:
         f.write(subst(read(ref, "DEMContactKernels_SphereSphere.cu"), common))
     # ---- sphere--triangle broad phase: facet sandwich + facet -> bin registration (per-thread kernels, executed), and the

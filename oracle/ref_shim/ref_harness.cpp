@@ -16,6 +16,7 @@
  *   getNumberOfBinsEachSphereTouches / populateBinSphereTouchingPairs   src/kernel/DEMBinSphereKernels.cu:11,133
  *   makeTriangleSandwich / getNumberOfBinsEachTriangleTouches / populateBinTriangleTouchingPairs
  *                            src/kernel/DEMBinTriangleKernels.cu:22,87,139 (with DEMTriangleBoxIntersect.cu)
+ *   buildPersistentMap       src/kernel/DEMHistoryMappingKernels.cu:17
  * block-cooperative (every CUDA thread of a block on its own fiber, launch_coop below):
  *   getNumberOfSphereContactsEachBin / populateSphSphContactPairsEachBin   src/kernel/DEMContactKernels_SphereSphere.cu:91,267
  *   getNumberOfSphTriContactsEachBin / populateTriSphContactsEachBin       src/kernel/DEMContactKernels_SphereTriangle.cu:116,272
@@ -85,6 +86,9 @@ namespace ref_bin {
 }
 namespace ref_css {
 #include "contact_ss.inc"
+}
+namespace ref_hist {
+#include "history.inc"
 }
 namespace ref_bintri {
 #include "bintriangle.inc"
@@ -349,6 +353,38 @@ long ref_sphere_anal_contacts(OrcWorld* w, double binSize, uint32_t nbX, uint32_
         outSphere[i] = idA[i]; outObj[i] = idB[i]; outType[i] = ct[i];
     }
     return cnt;
+}
+
+/* Contact-history map through the reference's own buildPersistentMap (src/kernel/DEMHistoryMappingKernels.cu:17-61; the
+ * call site is DEMCubContactDetection.cu:860-960): both lists sorted by idA, per-sphere run lengths and their scans (the
+ * reference gets them from cub run-length encode + fillRunLengthArray + prefix scan; restated here), then one thread per
+ * sphere looks every new contact up among the sphere's old ones by (idB, type).  mapping[i] = index of new contact i's
+ * partner in the old list, or 0xFFFFFFFF for a new contact.  Returns 0, or -1 if a list is not sorted by idA. */
+int ref_history_map(uint32_t nSpheres, uint32_t nNew, const uint32_t* newA, const uint32_t* newB, const uint8_t* newT,
+                    uint32_t nOld, const uint32_t* oldA, const uint32_t* oldB, const uint8_t* oldT, uint32_t* mapping) {
+    for (uint32_t i = 1; i < nNew; i++) if (newA[i] < newA[i - 1]) return -1;
+    for (uint32_t i = 1; i < nOld; i++) if (oldA[i] < oldA[i - 1]) return -1;
+    std::vector<deme::geoSphereTouches_t> runNew(nSpheres + 1, 0), runOld(nSpheres + 1, 0);
+    for (uint32_t i = 0; i < nNew; i++) runNew[newA[i]]++;
+    for (uint32_t i = 0; i < nOld; i++) runOld[oldA[i]]++;
+    std::vector<deme::contactPairs_t> scanNew(nSpheres + 1, 0), scanOld(nSpheres + 1, 0);
+    for (uint32_t s = 0; s < nSpheres; s++) {
+        scanNew[s + 1] = scanNew[s] + runNew[s];
+        scanOld[s + 1] = scanOld[s] + runOld[s];
+    }
+    deme::DEMDataKT kt;
+    memset((void*)&kt, 0, sizeof(kt));
+    std::vector<deme::bodyID_t> nB(newB, newB + nNew), oB(oldB, oldB + nOld);
+    std::vector<deme::contact_t> nT(newT, newT + nNew), oT(oldT, oldT + nOld);
+    nB.push_back(0); oB.push_back(0); nT.push_back(0); oT.push_back(0);
+    kt.idGeometryB = nB.data(); kt.contactType = nT.data();
+    kt.previous_idGeometryB = oB.data(); kt.previous_contactType = oT.data();
+    std::vector<deme::contactPairs_t> map(nNew + 1, deme::NULL_MAPPING_PARTNER);
+    launch(nSpheres, 256, [&] {
+        ref_hist::buildPersistentMap(runNew.data(), runOld.data(), scanNew.data(), scanOld.data(), map.data(), &kt, nSpheres);
+    });
+    for (uint32_t i = 0; i < nNew; i++) mapping[i] = map[i];
+    return 0;
 }
 
 /* Sphere--sphere contact pairs as the reference finds them (contactDetection(), src/algorithms/

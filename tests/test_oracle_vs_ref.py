@@ -465,3 +465,49 @@ def test_sphere_sphere_candidates_are_the_reference_sweeps(built, kind, bin_mult
         total += len(mine)
         print("%s step +%d: %d pairs in %d active bins (most spheres in a bin: %d)" % (kind, nsteps, len(mine), stats[0], stats[1]))
     assert total > 0
+
+
+@needs_ref
+@pytest.mark.parametrize("kind", ["clumps_full", "clumps_roll", "mesh_tray", "cylinder", "families", "seed104", "seed117"])
+def test_history_carry_over_is_the_reference_persistent_map(built, kind):
+    """Row a9 against reference code: when a contact list is rebuilt the reference looks every new contact up among the old
+    contacts of the same sphere by (idB, type) -- buildPersistentMap, DEMHistoryMappingKernels.cu:17-61 -- and carries the
+    history words of the partner over (zeros for a new contact).  That kernel runs here through the shim on the oracle's old
+    and new lists (ref_history_map); the words the oracle carried must be exactly the partner's, for every contact of every
+    type, on beds where contacts appear and disappear between rebuilds."""
+    import ctypes as C
+    if kind.startswith("seed"):
+        f = scenes.flatten(_random_scene(int(kind[4:])))
+        w = pyoracle.world_from_flat(f, contact_capacity=64 * f.nSpheres + 1024)
+    else:
+        f = scenes.flatten(_scene(kind))
+        w = pyoracle.world_from_flat(f)
+    fn = pyoracle.ref().ref_history_map
+    fn.restype = C.c_int
+    carried = fresh = gone = 0
+    for nsteps in (700, 400, 400, 800):
+        w.step(nsteps, cd_every=f.cd_update_freq)          # (the list is one update period old now: the bed has moved)
+        w.step(2 * f.cd_update_freq, cd_every=10 ** 9)     # ... and two more periods without a rebuild
+        oA, oB, oT, oW = w.contacts()
+        w.compute_margins(f.cd_update_freq)
+        w.detect_contacts()
+        nA, nB, nT, nW = w.contacts()
+        po, pn = np.argsort(oA, kind="stable"), np.argsort(nA, kind="stable")
+        mapping = np.zeros(max(len(nA), 1), "u4")
+        args = [np.ascontiguousarray(a[p].astype(dt)) for a, p, dt in ((nA, pn, "u4"), (nB, pn, "u4"), (nT, pn, "u1"),
+                                                                         (oA, po, "u4"), (oB, po, "u4"), (oT, po, "u1"))]
+        rc = fn(C.c_uint32(w.nSpheres), C.c_uint32(len(nA)), *[x.ctypes.data_as(C.c_void_p) for x in args[:3]],
+                C.c_uint32(len(oA)), *[x.ctypes.data_as(C.c_void_p) for x in args[3:]], mapping.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        m = mapping[: len(nA)]
+        found = m != 0xFFFFFFFF
+        live = np.zeros(len(nA), bool)
+        for k in range(4):
+            expect = np.zeros(len(nA), "f4")
+            expect[found] = oW[po, k][m[found]]            # (contacts() returns copies: n x 4 history words)
+            assert np.array_equal(expect.view("u4"), np.ascontiguousarray(nW[pn, k]).view("u4")), (kind, "wildcard %d" % k)
+            live |= nW[pn, k] != 0
+        carried += int((found & live).sum())
+        fresh += int((~found).sum())
+        gone += len(oA) - int(found.sum())
+    assert carried > 0 and fresh + gone > 0, (carried, fresh, gone)
