@@ -911,12 +911,21 @@ int orc_detect_contacts(OrcWorld* w) {
 #endif
         for (int b = 0; b <= nchunk; b++)
             if (kb[b].n) qsort(kb[b].keys, kb[b].n, sizeof(CKey), ckey_cmp);
+        /* chunk b holds spheres below those of chunk b + 1 (and the facet pairs sit in a buffer of their own type), so the
+         * merged list is, type after type in ascending order, every buffer's run of that type in buffer order */
         size_t* head = (size_t*)calloc((size_t)nchunk + 1, sizeof(size_t));
-        for (size_t i = 0; i < n; i++) {
-            int best = -1;
+        size_t i = 0;
+        while (i < n) {
+            int t = 256;
             for (int b = 0; b <= nchunk; b++)
-                if (head[b] < kb[b].n && (best < 0 || ckey_cmp(&kb[b].keys[head[b]], &kb[best].keys[head[best]]) < 0)) best = b;
-            keys[i] = kb[best].keys[head[best]++];
+                if (head[b] < kb[b].n && (int)kb[b].keys[head[b]].type < t) t = (int)kb[b].keys[head[b]].type;
+            for (int b = 0; b <= nchunk; b++) {
+                size_t e = head[b];
+                while (e < kb[b].n && (int)kb[b].keys[e].type == t) e++;
+                if (e > head[b]) memcpy(keys + i, kb[b].keys + head[b], sizeof(CKey) * (e - head[b]));
+                i += e - head[b];
+                head[b] = e;
+            }
         }
         free(head);
     }

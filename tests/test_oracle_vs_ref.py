@@ -385,8 +385,8 @@ def test_random_scenes_bit_exact_vs_reference_kernels(built, seed):
 
 
 @needs_ref
-@pytest.mark.parametrize("threads", [2, 5, 16])
-@pytest.mark.parametrize("kind", ["clumps_full", "mesh_tray", "cylinder", "families"])
+@pytest.mark.parametrize("threads", [2, 5, 16, 64])
+@pytest.mark.parametrize("kind", ["clumps_full", "mesh_tray", "cylinder", "families", "drum"])
 def test_threaded_broad_phase_lists_the_same_contacts(built, kind, threads):
     """The reference arm of bench.py spreads the oracle's broad phase over the host cores (orc_set_threads; only the OpenMP build
     inside oracle/_ref does): the sphere range is cut into chunks -- also in the middle of a clump --, every chunk is searched and
