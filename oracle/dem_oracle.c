@@ -152,7 +152,11 @@ static inline void owner_pos_rot(const OrcWorld* w, uint32_t owner, f3* relPos, 
     bodyPos->z = ownerPos->z + (double)relPos->z;
 }
 
+static int g_orc_threads = 1; /* host threads of the broad phase, see orc_set_threads */
 void orc_sphere_positions(const OrcWorld* w, double* xyz, float* radius) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(g_orc_threads > 64 ? 64 : (g_orc_threads < 1 ? 1 : g_orc_threads))
+#endif
     for (uint32_t s = 0; s < w->nSpheres; s++) {
         uint32_t o = w->ownerClumpBody[s];
         unsigned c = w->clumpComponentOffset[s];
@@ -692,7 +696,6 @@ void orc_integrate(OrcWorld* w) {
 /* Host threads of the broad phase.  Only a build with OpenMP (oracle/_ref/libdemref.so, the timed reference arm) spreads
  * the search; liboracle.so is compiled without it and stays serial.  The candidate SET does not depend on the number of
  * threads, and the list is sorted by (type, A, B) before it is used, so neither does any result. */
-static int g_orc_threads = 1;
 void orc_set_threads(int n) { g_orc_threads = n < 1 ? 1 : n; }
 #ifdef _OPENMP
 #define ORC_CHUNKS (g_orc_threads > 64 ? 64 : g_orc_threads)
@@ -725,6 +728,10 @@ int orc_detect_contacts(OrcWorld* w) {
     orc_sphere_positions(w, pos, rad);
     float rmax = 0;
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    const int nchunk = ORC_CHUNKS;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nchunk) reduction(max : rmax) reduction(min : lo[:3]) reduction(max : hi[:3])
+#endif
     for (uint32_t s = 0; s < nS; s++) {
         rad[s] = rad[s] + w->marginSize[w->ownerClumpBody[s]]; /* float add, fillSharedMemSpheres */
         if (rad[s] > rmax) rmax = rad[s];
@@ -734,7 +741,6 @@ int orc_detect_contacts(OrcWorld* w) {
         }
     }
     /* every chunk of the sphere range collects into its own buffer (one chunk, i.e. the plain serial search, without OpenMP) */
-    const int nchunk = ORC_CHUNKS;
     CKeyBuf* kb = (CKeyBuf*)calloc((size_t)nchunk + 1, sizeof(CKeyBuf));
     for (int b = 0; b < nchunk; b++) {
         kb[b].cap = 16 + (size_t)nS * 8 / (size_t)nchunk;
@@ -758,6 +764,9 @@ int orc_detect_contacts(OrcWorld* w) {
         uint32_t* cstart = (uint32_t*)calloc(ncell + 1, sizeof(uint32_t));
         uint32_t* cellOf = (uint32_t*)malloc(sizeof(uint32_t) * nS);
         uint32_t* order = (uint32_t*)malloc(sizeof(uint32_t) * nS);
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(nchunk)
+#endif
         for (uint32_t s = 0; s < nS; s++) {
             long c[3];
             for (int k = 0; k < 3; k++) {
@@ -765,8 +774,8 @@ int orc_detect_contacts(OrcWorld* w) {
                 if (c[k] >= nb[k]) c[k] = nb[k] - 1;
             }
             cellOf[s] = (uint32_t)(c[0] + nb[0] * (c[1] + nb[1] * c[2]));
-            cstart[cellOf[s] + 1]++;
         }
+        for (uint32_t s = 0; s < nS; s++) cstart[cellOf[s] + 1]++;
         for (size_t c = 0; c < ncell; c++) cstart[c + 1] += cstart[c];
         uint32_t* fill = (uint32_t*)malloc(sizeof(uint32_t) * ncell);
         memcpy(fill, cstart, sizeof(uint32_t) * ncell);
