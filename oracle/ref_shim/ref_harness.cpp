@@ -747,6 +747,69 @@ void ref_voxel_encode(OrcWorld* w, const double xyz[3], uint64_t* voxel, uint16_
     *voxel = id;
 }
 
+/* The WHOLE contact rebuild through reference kernels (sphere scenes; slow -- fibers -- so for short runs of small scenes):
+ * sphere--analytical pairs from the sphere -> bin kernels, sphere--sphere pairs from the per-bin sweeps, the list ordered
+ * by (type, A, B) like the oracle's (the order fixes the order of the force accumulation), history words carried over through
+ * buildPersistentMap.  Facet pairs are not taken from the reference here: its list legitimately differs from the oracle's
+ * (facet broad phase), so a scene with a mesh is refused (-2).  Returns 0, -1 on capacity. */
+static double g_full_cd_bin_mult = 0.0;  // > 0: ref_step rebuilds this way, bin size = mult * 2 * (largest radius + margin)
+void ref_use_reference_rebuild(double bin_mult) { g_full_cd_bin_mult = bin_mult; }
+
+int ref_detect_contacts_full(OrcWorld* w, double bin_mult) {
+    if (w->nTri > 0) return -2;
+    const uint32_t nS = w->nSpheres;
+    float rmax = 0.f, mmax = 0.f;
+    for (uint32_t c = 0; c < w->nComp; c++) rmax = std::max(rmax, w->Radii[c]);
+    for (uint32_t o = 0; o < w->nOwners; o++) mmax = std::max(mmax, w->marginSize[o]);
+    const double binSize = bin_mult * 2.0 * ((double)rmax + (double)mmax);
+    const double ext[3] = {std::ldexp(w->voxelSize, w->nvXp2), std::ldexp(w->voxelSize, w->nvYp2), std::ldexp(w->voxelSize, w->nvZp2)};
+    uint32_t nb[3];
+    for (int k = 0; k < 3; k++) nb[k] = (uint32_t)std::ceil(ext[k] / binSize);
+    struct Key { uint32_t a, b; uint8_t t; };
+    std::vector<Key> keys;
+    {
+        const long cap = 64L * nS + 1024;
+        std::vector<uint32_t> A(cap), B(cap);
+        std::vector<uint8_t> T(cap);
+        long n = ref_sphere_anal_contacts(w, binSize, nb[0], nb[1], nb[2], A.data(), B.data(), T.data(), cap, nullptr);
+        if (n < 0) return -1;
+        for (long i = 0; i < n; i++) keys.push_back({A[i], B[i], T[i]});
+        n = ref_sphere_sphere_contacts(w, binSize, nb[0], nb[1], nb[2], A.data(), B.data(), cap, nullptr);
+        if (n < 0) return -1;
+        for (long i = 0; i < n; i++) keys.push_back({std::min(A[i], B[i]), std::max(A[i], B[i]), (uint8_t)ORC_SPHERE_SPHERE});
+    }
+    std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) {
+        return x.t != y.t ? x.t < y.t : (x.a != y.a ? x.a < y.a : x.b < y.b);
+    });
+    const uint32_t nNew = (uint32_t)keys.size(), nOld = (uint32_t)w->nContacts;
+    if (nNew > w->contactCapacity) return -1;
+    // buildPersistentMap wants both lists ordered by idA
+    std::vector<uint32_t> pn(nNew), po(nOld);
+    for (uint32_t i = 0; i < nNew; i++) pn[i] = i;
+    for (uint32_t i = 0; i < nOld; i++) po[i] = i;
+    std::stable_sort(pn.begin(), pn.end(), [&](uint32_t x, uint32_t y) { return keys[x].a < keys[y].a; });
+    std::stable_sort(po.begin(), po.end(), [&](uint32_t x, uint32_t y) { return w->idGeometryA[x] < w->idGeometryA[y]; });
+    std::vector<uint32_t> nA(nNew + 1), nB(nNew + 1), oA(nOld + 1), oB(nOld + 1), map(nNew + 1);
+    std::vector<uint8_t> nT(nNew + 1), oT(nOld + 1);
+    for (uint32_t i = 0; i < nNew; i++) { nA[i] = keys[pn[i]].a; nB[i] = keys[pn[i]].b; nT[i] = keys[pn[i]].t; }
+    for (uint32_t i = 0; i < nOld; i++) { oA[i] = w->idGeometryA[po[i]]; oB[i] = w->idGeometryB[po[i]]; oT[i] = w->contactType[po[i]]; }
+    if (ref_history_map(nS, nNew, nA.data(), nB.data(), nT.data(), nOld, oA.data(), oB.data(), oT.data(), map.data())) return -3;
+    const bool history = (w->force_model == ORC_HERTZIAN);
+    std::vector<float> wc[4];
+    for (int k = 0; k < 4; k++) wc[k].assign(nNew + 1, 0.f);
+    if (history)
+        for (uint32_t i = 0; i < nNew; i++)
+            if (map[i] != deme::NULL_MAPPING_PARTNER)
+                for (int k = 0; k < 4; k++) wc[k][pn[i]] = w->contactWildcards[k][po[map[i]]];
+    for (uint32_t i = 0; i < nNew; i++) {
+        w->idGeometryA[i] = keys[i].a; w->idGeometryB[i] = keys[i].b; w->contactType[i] = keys[i].t;
+        if (history)
+            for (int k = 0; k < 4; k++) w->contactWildcards[k][i] = wc[k][i];
+    }
+    w->nContacts = nNew;
+    return 0;
+}
+
 /* hot loop: reference kernels for force/accumulate/integrate, oracle's broad phase for the rebuild (its list is the one the
  * reference's own sweep kernels produce, pair for pair: ref_sphere_sphere_contacts and the test that compares them; the sweeps
  * themselves run on fibers, far too slowly for a loop like this one). */
@@ -755,7 +818,7 @@ int ref_step(OrcWorld* w, uint32_t nsteps, uint32_t cd_every, uint64_t* step_cou
     for (uint32_t s = 0; s < nsteps; s++) {
         if ((*step_counter) % cd_every == 0) {
             ref_compute_margins(w, cd_every);
-            int rc = orc_detect_contacts(w);
+            int rc = g_full_cd_bin_mult > 0.0 ? ref_detect_contacts_full(w, g_full_cd_bin_mult) : orc_detect_contacts(w);
             if (rc) return rc;
         }
         ref_prepare_acc(w);

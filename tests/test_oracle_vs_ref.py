@@ -511,3 +511,42 @@ def test_history_carry_over_is_the_reference_persistent_map(built, kind):
         fresh += int((~found).sum())
         gone += len(oA) - int(found.sum())
     assert carried > 0 and fresh + gone > 0, (carried, fresh, gone)
+
+
+@needs_ref
+@pytest.mark.parametrize("kind,bin_mult,nsteps", [("clumps_full", 8.0, 1000), ("families", 10.0, 600), ("cylinder", 12.0, 800),
+                                                  ("seed109", 8.0, 800)])
+def test_trajectory_with_the_reference_rebuild_is_the_oracle_trajectory(built, kind, bin_mult, nsteps):
+    """Everything at once: a run in which EVERY kernel is the reference's -- margins, sphere -> bin registration, the per-bin
+    sweeps (on fibers), buildPersistentMap for the history words, force, accumulation, integration (ref_step with
+    ref_use_reference_rebuild) -- against the oracle stepping on its own, bit for bit after every stretch: owner state, contact
+    list, history words.  (Sphere scenes; a rebuild through fibers costs 512 context switches per bin and barrier, hence the short
+    runs and the large bins -- the list does not depend on the bin size, see the sweep test above.)"""
+    if kind.startswith("seed"):
+        f = scenes.flatten(_random_scene(int(kind[4:])))
+        a = pyoracle.world_from_flat(f, contact_capacity=64 * f.nSpheres + 1024)
+    else:
+        f = scenes.flatten(_scene(kind))
+        a = pyoracle.world_from_flat(f)
+    if a.nTri:
+        pytest.skip("the reference's facet list legitimately differs from the oracle's (see the facet test)")
+    b = a.copy()
+    touched = False
+    try:
+        pyoracle.ref().ref_use_reference_rebuild(C_double(bin_mult))
+        for _ in range(2):
+            a.step(nsteps // 2, cd_every=f.cd_update_freq)
+            b.step(nsteps // 2, cd_every=f.cd_update_freq, use_ref=True)
+            _assert_same_state(a, b)
+            n = a.nContacts
+            for name in ("idGeometryA", "idGeometryB", "contactType"):
+                assert np.array_equal(getattr(a, name)[:n], getattr(b, name)[:n]), name
+            touched = touched or (n > 0 and np.abs(a.contactForces[: 3 * n]).max() > 0)
+    finally:
+        pyoracle.ref().ref_use_reference_rebuild(C_double(0.0))
+    assert touched
+
+
+def C_double(x):
+    import ctypes
+    return ctypes.c_double(x)
